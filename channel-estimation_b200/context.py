@@ -1,0 +1,283 @@
+"""Thin NumPy-facing wrapper of the C ABI (one `DeviceContext` == one `chest_create` handle).
+
+All arithmetic happens in the CUDA library; this file only marshals arrays (column-major,
+complex as interleaved doubles, 0-based indices) and raises on any non-zero status."""
+import ctypes as C
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+SCHEME_ID = {"aux": 0, "cod": 1, "ofdm": 2}
+SCHEME_NAME = {0: "aux", 1: "cod", 2: "ofdm"}
+WF_ID = {"F": 0, "O": 1}
+DETECT = {"select_real": 0, "despread_real": 1, "select_complex": 2}
+CONST_ID = {"PAM": 0, "QAM": 1}
+
+
+class ChestError(RuntimeError):
+    pass
+
+
+def _c(a):
+    """complex array -> contiguous complex128 (memory = interleaved doubles)"""
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class DeviceContext:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_uint64(0)
+        self._h = None
+        self._check(self.lib.chest_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.schemes = {}
+        self.n_snr = 0
+        self.N = 0
+        self.K = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise ChestError("chest_b200 error %d: %s" % (rc, self.lib.chest_last_error().decode()))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.chest_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ setup
+    def set_channel(self, n_samples, pdp_normalized, max_doppler, dt, paths, model="Jakes"):
+        pdp = np.ascontiguousarray(pdp_normalized, dtype=np.float64)
+        self._check(self.lib.chest_set_channel(self._h, n_samples, len(pdp), _ptr(pdp), max_doppler, dt, paths,
+                                               {"Jakes": 0, "Uniform": 1}[model]))
+        self.N, self.Lt = n_samples, len(pdp)
+        self.T = int(np.count_nonzero(pdp))
+        self.paths = paths
+
+    def set_waveform(self, wf, G, Q):
+        G, Q = np.asfortranarray(G, dtype=np.complex128), np.asfortranarray(Q, dtype=np.complex128)
+        assert G.shape == Q.shape
+        self._check(self.lib.chest_set_waveform(self._h, WF_ID[wf], G.shape[0], G.shape[1], _ptr(G), _ptr(Q)))
+        self.N = G.shape[0]
+        self.K[wf] = G.shape[1]
+
+    def set_constellation(self, which, symbol_mapping, bit_mapping):
+        s = _c(symbol_mapping)
+        b = np.asfortranarray(bit_mapping, dtype=np.uint8)
+        self._check(self.lib.chest_set_constellation(self._h, CONST_ID[which], len(s), _ptr(s), _ptr(b)))
+
+    def set_scheme(self, name, wf, C_mat, pilot_pos, data_pos, kappa, dpr, detect, constellation, considered_bits):
+        Cs = sp.csc_matrix(C_mat).astype(np.complex128)
+        Cs.sort_indices()
+        jc = Cs.indptr.astype(np.int64)
+        ir = Cs.indices.astype(np.int32)
+        val = _c(Cs.data)
+        pp = np.ascontiguousarray(pilot_pos, dtype=np.int32)
+        dp = np.ascontiguousarray(data_pos, dtype=np.int32) if data_pos is not None else None
+        cb = np.ascontiguousarray(considered_bits, dtype=np.uint8)
+        n_data = Cs.shape[1] - len(pp)
+        self._check(self.lib.chest_set_scheme(self._h, SCHEME_ID[name], WF_ID[wf], Cs.shape[1], len(pp), n_data,
+                                              _ptr(jc), _ptr(ir), _ptr(val), _ptr(pp), _ptr(dp), kappa, dpr,
+                                              DETECT[detect], CONST_ID[constellation], _ptr(cb)))
+        self.schemes[name] = dict(wf=wf, K=Cs.shape[0], P=len(pp), n_data=n_data, n_bits=len(cb))
+
+    def set_snr(self, pn_time):
+        pn = np.ascontiguousarray(pn_time, dtype=np.float64)
+        self._check(self.lib.chest_set_snr(self._h, len(pn), _ptr(pn)))
+        self.n_snr = len(pn)
+
+    def set_mmse(self, name, variant, W_csc):
+        """W_csc: scipy CSC of shape (K^2 P, n_snr) -- W_MMSE_* as DS.m:279-313 stores it."""
+        W = sp.csc_matrix(W_csc)
+        W.sort_indices()
+        jc = W.indptr.astype(np.int64)
+        ir = W.indices.astype(np.int64)
+        val = _c(W.data)
+        self._check(self.lib.chest_set_mmse(self._h, SCHEME_ID[name], variant, W.shape[1], _ptr(jc), _ptr(ir), _ptr(val)))
+
+    def set_mmse_arrays(self, name, variant, jc, ir, val):
+        jc = np.ascontiguousarray(jc, dtype=np.int64)
+        ir = np.ascontiguousarray(ir, dtype=np.int64)
+        val = _c(val)
+        self._check(self.lib.chest_set_mmse(self._h, SCHEME_ID[name], variant, len(jc) - 1, _ptr(jc), _ptr(ir), _ptr(val)))
+
+    def finalize(self, max_batch):
+        self._check(self.lib.chest_finalize(self._h, max_batch))
+        self.max_batch = max_batch
+
+    # ------------------------------------------------------------------ tier 1
+    def new_realization(self, doppler_u, phase_u):
+        du = np.ascontiguousarray(doppler_u, dtype=np.float64)
+        pu = np.ascontiguousarray(phase_u, dtype=np.float64)
+        batch = du.size // (self.T * self.paths)
+        self._check(self.lib.chest_new_realization(self._h, batch, _ptr(du), _ptr(pu)))
+
+    def new_realization_seeded(self, batch, seed, first_rep=0):
+        self._check(self.lib.chest_new_realization_seeded(self._h, batch, seed, first_rep))
+
+    def set_impulse_response(self, h):
+        """h: (batch, N, Lt) complex."""
+        h = np.asarray(h)
+        hb = _c(np.transpose(h, (0, 2, 1)))          # per realization column-major N x Lt
+        self._check(self.lib.chest_set_impulse_response(self._h, h.shape[0], _ptr(hb)))
+
+    def impulse_response(self, b=0):
+        out = np.zeros((self.Lt, self.N), dtype=np.complex128)
+        self._check(self.lib.chest_get_impulse_response(self._h, b, _ptr(out)))
+        return out.T.copy()
+
+    def convolution_matrix(self, b=0):
+        nnz = C.c_int64(0)
+        self._check(self.lib.chest_get_convolution_csc(self._h, b, C.byref(nnz), None, None, None))
+        jc = np.zeros(self.N + 1, dtype=np.int64)
+        ir = np.zeros(nnz.value, dtype=np.int32)
+        val = np.zeros(nnz.value, dtype=np.complex128)
+        self._check(self.lib.chest_get_convolution_csc(self._h, b, C.byref(nnz), _ptr(jc), _ptr(ir), _ptr(val)))
+        return sp.csc_matrix((val, ir, jc), shape=(self.N, self.N))
+
+    def convolve(self, s, b=0):
+        s2 = np.atleast_2d(np.asarray(s).T) if np.ndim(s) == 1 else np.asarray(s).T
+        s2 = _c(s2)
+        r = np.zeros_like(s2)
+        self._check(self.lib.chest_convolve(self._h, b, _ptr(s2), s2.shape[0], _ptr(r)))
+        return r[0] if np.ndim(s) == 1 else r.T.copy()
+
+    def transmission_matrix(self, wf, b=0):
+        K = self.K[wf]
+        D = np.zeros((K, K), dtype=np.complex128)
+        h = np.zeros(K, dtype=np.complex128)
+        self._check(self.lib.chest_transmission_matrix(self._h, b, WF_ID[wf], _ptr(D), _ptr(h)))
+        return D.T.copy(), h        # library writes column-major
+
+    def modulate(self, wf, x):
+        x2 = _c(np.atleast_2d(np.asarray(x).T) if np.ndim(x) == 1 else np.asarray(x).T)
+        s = np.zeros((x2.shape[0], self.N), dtype=np.complex128)
+        self._check(self.lib.chest_modulate(self._h, WF_ID[wf], _ptr(x2), x2.shape[0], _ptr(s)))
+        return s[0] if np.ndim(x) == 1 else s.T.copy()
+
+    def demodulate(self, wf, r):
+        r2 = _c(np.atleast_2d(np.asarray(r).T) if np.ndim(r) == 1 else np.asarray(r).T)
+        y = np.zeros((r2.shape[0], self.K[wf]), dtype=np.complex128)
+        self._check(self.lib.chest_demodulate(self._h, WF_ID[wf], _ptr(r2), r2.shape[0], _ptr(y)))
+        return y[0] if np.ndim(r) == 1 else y.T.copy()
+
+    def estimate(self, name, variant, i_snr, hP, want_D=True):
+        K = self.schemes[name]["K"]
+        hP = _c(hP)
+        D = np.zeros((K, K), dtype=np.complex128) if want_D else None
+        hd = np.zeros(K, dtype=np.complex128)
+        self._check(self.lib.chest_estimate(self._h, SCHEME_ID[name], variant, i_snr, _ptr(hP), _ptr(D), _ptr(hd)))
+        return (D.T.copy() if want_D else None), hd
+
+    # ------------------------------------------------------------------ tier 2
+    def pack_draws(self, draws_list):
+        """list of per-realization dicts (doppler_u, phase_u, bits_<scheme>, pil_idx_fbmc, pil_idx_ofdm,
+        noise) -> (ChestDraws struct, keep-alive arrays)."""
+        keep = {}
+        keep["du"] = np.ascontiguousarray(np.stack([d["doppler_u"].reshape(-1, order="F") for d in draws_list]))
+        keep["pu"] = np.ascontiguousarray(np.stack([d["phase_u"].reshape(-1, order="F") for d in draws_list]))
+        keep["noise"] = _c(np.stack([d["noise"] for d in draws_list]))
+        st = _lib.ChestDraws()
+        st.doppler_u, st.phase_u, st.noise = _ptr(keep["du"]), _ptr(keep["pu"]), _ptr(keep["noise"])
+        for name, sid in SCHEME_ID.items():
+            if name in self.schemes:
+                keep["b" + name] = np.ascontiguousarray(np.stack([d["bits_" + name] for d in draws_list]), dtype=np.uint8)
+                st.bits[sid] = keep["b" + name].ctypes.data
+        for key, wid in (("pil_idx_fbmc", 0), ("pil_idx_ofdm", 1)):
+            if any(s["wf"] == ("F", "O")[wid] for s in self.schemes.values()):
+                keep[key] = np.ascontiguousarray(np.stack([d[key] for d in draws_list]), dtype=np.int32)
+                st.pilot_idx[wid] = keep[key].ctypes.data
+        st.on_device = 0
+        return st, keep
+
+    def run_batch(self, n_rep, n_iter, draws=None, seed=0, first_rep=0):
+        """Returns err[rep, snr, it, scheme, csi, edge] (uint32)."""
+        err = np.zeros((n_rep, self.n_snr, n_iter + 1, 3, 2, 2), dtype=np.uint32)
+        dptr = C.byref(draws) if draws is not None else None
+        self._check(self.lib.chest_run_batch(self._h, n_rep, n_iter, dptr, seed, first_rep, _ptr(err)))
+        return err
+
+    def run_batch_device(self, n_rep, n_iter, draws=None, seed=0, first_rep=0, err_dev_ptr=None):
+        dptr = C.byref(draws) if draws is not None else None
+        self._check(self.lib.chest_run_batch_device(self._h, n_rep, n_iter, dptr, seed, first_rep, err_dev_ptr))
+
+    def generate_draws(self, n_rep, seed, first_rep=0):
+        st = _lib.ChestDraws()
+        self._check(self.lib.chest_generate_draws(self._h, n_rep, seed, first_rep, C.byref(st)))
+        return st
+
+    def download_draws(self, n_rep):
+        """Host copies of the device-resident draws, as a list of per-realization dicts."""
+        TP = self.T * self.paths
+        du, pu = np.zeros((n_rep, TP)), np.zeros((n_rep, TP))
+        noise = np.zeros((n_rep, self.n_snr, self.N), dtype=np.complex128)
+        bits = {n: np.zeros((n_rep, s["n_bits"]), dtype=np.uint8) for n, s in self.schemes.items()}
+        P = {("F", "O").index(s["wf"]): s["P"] for s in self.schemes.values()}
+        pidx = {w: np.zeros((n_rep, p), dtype=np.int32) for w, p in P.items()}
+        self._check(self.lib.chest_download_draws(
+            self._h, n_rep, _ptr(du), _ptr(pu), _ptr(bits.get("aux")), _ptr(bits.get("cod")), _ptr(bits.get("ofdm")),
+            _ptr(pidx.get(0)), _ptr(pidx.get(1)), _ptr(noise)))
+        out = []
+        for r in range(n_rep):
+            d = dict(doppler_u=du[r].reshape(self.T, self.paths, order="F"),
+                     phase_u=pu[r].reshape(self.T, self.paths, order="F"), noise=noise[r])
+            for n in bits:
+                d["bits_" + n] = bits[n][r]
+            if 0 in pidx:
+                d["pil_idx_fbmc"] = pidx[0][r]
+            if 1 in pidx:
+                d["pil_idx_ofdm"] = pidx[1][r]
+            out.append(d)
+        return out
+
+    def bit_counts(self):
+        nb = np.zeros((3, 2), dtype=np.int64)
+        self._check(self.lib.chest_bit_counts(self._h, nb.ctypes.data_as(C.POINTER(C.c_int64))))
+        return nb
+
+    def draws_bytes(self, n_rep):
+        return int(self.lib.chest_draws_bytes(self._h, n_rep))
+
+    def get_state(self, what, name, rep, i_snr):
+        s = self.schemes[name]
+        n = {"y": s["K"], "hP": s["P"], "xD_est": s["n_data"], "xD_perf": s["n_data"], "hdiag": s["K"]}[what]
+        code = {"y": 0, "hP": 1, "xD_est": 2, "xD_perf": 3, "hdiag": 4}[what]
+        out = np.zeros(n, dtype=np.complex128)
+        self._check(self.lib.chest_get_state(self._h, code, SCHEME_ID[name], rep, i_snr, _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ measurement helpers
+    def launch_count(self):
+        return int(self.lib.chest_launch_count(self._h))
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.chest_set_profiling(self._h, int(on)))
+
+    def stage_times(self):
+        ms = (C.c_float * 7)()
+        self._check(self.lib.chest_stage_times(self._h, ms))
+        return dict(zip(("draws", "k1_channel_tx", "k2_transmission_matrix", "k3_demod", "one_tap", "ic_iterations",
+                         "total"), [float(x) for x in ms]))
+
+    def work_model(self, n_iter):
+        out = (C.c_double * 8)()
+        self._check(self.lib.chest_work_model(self._h, n_iter, out))
+        return dict(k2_flops=out[0], est_flops=out[1], perf_flops=out[2], txdemod_flops=out[3],
+                    w_bytes_per_ic_launch=out[4], precode_flops=out[5])
+
+    def fp64_peak(self, mode="dmma", iters=20000):
+        t = C.c_double(0)
+        self._check(self.lib.chest_fp64_peak(self._h, 0 if mode == "dmma" else 1, iters, C.byref(t)))
+        return t.value

@@ -1,0 +1,1069 @@
+// chest_api.cu -- context, one-time setup and the extern "C" launchers declared in
+// include/chest_b200.h.  Host code only orchestrates: every arithmetic step of the loop body
+// runs in the kernels of kernels.cuh on the context's stream.  No CPU fallback.
+#include "../../include/chest_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(CHEST_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+#define ARG(cond)                                                                                  \
+    do {                                                                                           \
+        if (!(cond)) return fail(CHEST_ERR_ARG, std::string("argument check failed: ") + #cond);   \
+    } while (0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s) { return upload(v.data(), v.size(), s); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Waveform {
+    bool set = false;
+    int K = 0;
+    DevBuf<cplx> G, Q, Gt;
+    DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi;
+    std::vector<int> g_lo, g_hi, q_lo, q_hi;
+    int nsch = 0; int sch[2] = {0, 0};
+    // batch state
+    DevBuf<cplx> x, s, r0, y, D, htrue;
+    double flops_d = 0, flops_demod = 0, flops_mod = 0;
+};
+struct Constellation {
+    bool set = false;
+    int order = 0, nbits = 0, n_axis = 0, is_qam = 0;
+    DevBuf<cplx> symbol, pilot; DevBuf<double> level; DevBuf<int> word_of_grid;
+    ConstDev dev{};
+};
+struct MmseVariant {
+    bool set = false;
+    int n_tiles = 0;
+    DevBuf<int> tile_ptr, tile_delta;
+    std::vector<DevBuf<cplx>> frag, diag;
+    DevBuf<WTiles> table;
+    int64_t nnz_offdiag_pairs = 0;
+};
+struct Scheme {
+    bool set = false;
+    int waveform = 0, K = 0, K_in = 0, P = 0, n_data = 0, detect = 0, constellation = 0, n_bits = 0;
+    double kappa = 1, dpr = 1;
+    DevBuf<int> c_rowptr, c_col, ct_colptr, ct_row, pilot_pos, data_pos;
+    DevBuf<cplx> c_val, ct_val;
+    DevBuf<uint32_t> edge_mask;
+    std::vector<uint8_t> considered;
+    MmseVariant mm[2];
+    DevBuf<cplx> xP, hP, hdiag, xD[2];
+    DevBuf<uint32_t> txword;
+    DevBuf<uint8_t> bits;
+    int64_t n_bits_edge = 0;
+    int64_t c_nnz = 0;
+};
+
+struct Ctx {
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    // channel
+    bool chan_set = false;
+    int N = 0, Lt = 0, T = 0, paths = 0, model = 0;
+    double fD = 0, dt = 0;
+    std::vector<int> tap_delay; std::vector<double> tap_amp;
+    DevBuf<int> d_tap_delay; DevBuf<double> d_tap_amp;
+    Waveform wf[2];
+    Constellation cst[2];
+    Scheme sch[3];
+    int S = 0; std::vector<double> pn; DevBuf<double> d_noise_scale;
+    // batch
+    bool finalized = false;
+    int max_batch = 0, cur_batch = 0, last_iter = 0;
+    DevBuf<double> doppler_u, phase_u; DevBuf<cplx> noise, h;
+    DevBuf<int32_t> pilot_idx[2];
+    DevBuf<uint32_t> err;
+    DevBuf<cplx> scratch, tmp_a, tmp_b;
+    DevBuf<IcCta> ctas; int n_ctas = 0, ctas_for_batch = -1;
+    int K_max = 0;
+    int64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[8] = {};
+    float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    DevBuf<double> probe;
+};
+
+Ctx* from(uint64_t h) { return reinterpret_cast<Ctx*>(static_cast<uintptr_t>(h)); }
+
+void support_ranges(const double* A, int N, int K, std::vector<int>& lo, std::vector<int>& hi) {
+    lo.assign(K, N); hi.assign(K, 0);
+    for (int j = 0; j < K; ++j) {
+        const double* c = A + 2 * (size_t)N * j;
+        int a = 0, b = N;
+        while (a < N && c[2 * a] == 0.0 && c[2 * a + 1] == 0.0) ++a;
+        while (b > a && c[2 * (b - 1)] == 0.0 && c[2 * (b - 1) + 1] == 0.0) --b;
+        lo[j] = a; hi[j] = b;
+        if (a >= b) { lo[j] = 0; hi[j] = 0; }
+    }
+}
+void tile_ranges(const std::vector<int>& lo, const std::vector<int>& hi, int tile, int extra, int cap,
+                 std::vector<int>& tlo, std::vector<int>& thi) {
+    int n = (int)lo.size(), nt = (n + tile - 1) / tile;
+    tlo.assign(nt, cap); thi.assign(nt, 0);
+    for (int j = 0; j < n; ++j) {
+        if (hi[j] <= lo[j]) continue;
+        int t = j / tile;
+        tlo[t] = std::min(tlo[t], lo[j]);
+        thi[t] = std::max(thi[t], std::min(cap, hi[j] + extra));
+    }
+    for (int t = 0; t < nt; ++t) if (thi[t] <= tlo[t]) { tlo[t] = 0; thi[t] = 0; }
+}
+
+constexpr int GEMM_SMEM = 4 * 64 * 36 * (int)sizeof(double);
+
+template <int MODE>
+cudaError_t launch_gemm(Ctx* c, const GemmParams& p, int n_z) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((p.M + 63) / 64, (p.n_cols + 63) / 64, n_z);
+    k_gemm<MODE><<<grid, 256, GEMM_SMEM, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+SchemeDev scheme_dev(Ctx* c, int si) {
+    Scheme& s = c->sch[si];
+    Waveform& w = c->wf[s.waveform];
+    SchemeDev d{};
+    d.waveform = s.waveform; d.K = s.K; d.K_in = s.K_in; d.P = s.P; d.P4 = (s.P + 3) / 4;
+    d.n_data = s.n_data; d.nbits = c->cst[s.constellation].nbits; d.detect_mode = s.detect;
+    d.constellation = s.constellation; d.n_bits_total = s.n_bits;
+    d.sqrt_kappa = std::sqrt(s.kappa); d.dpr = s.dpr; d.sqrt_dpr = std::sqrt(s.dpr);
+    d.c_rowptr = s.c_rowptr.p; d.c_col = s.c_col.p; d.c_val = s.c_val.p;
+    d.ct_colptr = s.ct_colptr.p; d.ct_row = s.ct_row.p; d.ct_val = s.ct_val.p;
+    d.pilot_pos = s.pilot_pos.p; d.data_pos = s.data_pos.p; d.edge_mask = s.edge_mask.p;
+    for (int v = 0; v < 2; ++v) {
+        d.tile_ptr[v] = s.mm[v].tile_ptr.p; d.tile_delta[v] = s.mm[v].tile_delta.p; d.w[v] = s.mm[v].table.p;
+    }
+    int g = (w.sch[0] == si) ? 0 : 1;
+    int B = c->cur_batch;
+    d.xP = s.xP.p; d.txword = s.txword.p;
+    d.x = w.x.p + (size_t)g * B * s.K;
+    d.y = w.y.p + (size_t)g * c->S * B * s.K;
+    d.hP = s.hP.p; d.hdiag = s.hdiag.p; d.xD[0] = s.xD[0].p; d.xD[1] = s.xD[1].p;
+    return d;
+}
+
+int check_ready(Ctx* c) {
+    if (!c) return fail(CHEST_ERR_ARG, "null handle");
+    if (!c->finalized) return fail(CHEST_ERR_STATE, "context not finalized (call chest_finalize)");
+    return CHEST_OK;
+}
+
+// ---------------------------------------------------------------- pipeline stages (all async on c->stream)
+int stage_channel(Ctx* c, int n_rep, const double* du, const double* pu) {
+    dim3 grid((c->N + 127) / 128, c->T, n_rep);
+    k_synth_h<<<grid, 128, 2 * c->paths * sizeof(double), c->stream>>>(
+        c->h.p, du, pu, c->d_tap_amp.p, c->N, c->T, c->paths, c->fD, c->dt, c->model);
+    c->launches++;
+    CK(cudaGetLastError());
+    return CHEST_OK;
+}
+
+int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
+    Waveform& w = c->wf[wfi];
+    GemmParams p{};
+    p.M = w.K; p.Kc = c->N; p.n_cols = w.K; p.lda = c->N; p.ldc = w.K; p.conj_a = 1;
+    p.At = w.Q.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.D.p;
+    p.h = c->h.p; p.G = w.G.p; p.tap_delay = c->d_tap_delay.p; p.T = c->T; p.N = c->N;
+    p.nt_klo = w.hg_klo.p; p.nt_khi = w.hg_khi.p; p.hdiag = w.htrue.p; p.rep0 = rep0;
+    CK(launch_gemm<GEMM_D>(c, p, n_rep));
+    return CHEST_OK;
+}
+
+int build_ctas(Ctx* c, int n_rep) {
+    if (c->ctas_for_batch == n_rep) return CHEST_OK;
+    std::vector<IcCta> v;
+    auto est = [&](int si) {
+        if (!c->sch[si].set) return;
+        for (int snr = 0; snr < c->S; ++snr)
+            for (int b0 = 0; b0 < n_rep; b0 += NC_MAX) v.push_back({0, si, snr, b0, std::min(NC_MAX, n_rep - b0)});
+    };
+    auto perf = [&](int wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set || w.nsch == 0) return;
+        int tot = w.nsch * c->S;
+        for (int b = 0; b < n_rep; ++b)
+            for (int q0 = 0; q0 < tot; q0 += NC_MAX) v.push_back({1, wfi, b, q0, std::min(NC_MAX, tot - q0)});
+    };
+    est(CHEST_SCHEME_AUX); est(CHEST_SCHEME_COD); perf(CHEST_WF_FBMC); est(CHEST_SCHEME_OFDM); perf(CHEST_WF_OFDM);
+    c->n_ctas = (int)v.size();
+    CK(c->ctas.upload(v, c->stream));
+    CK(c->scratch.alloc((size_t)c->n_ctas * 3 * c->K_max * NC_MAX));
+    CK(cudaStreamSynchronize(c->stream));
+    c->ctas_for_batch = n_rep;
+    return CHEST_OK;
+}
+
+int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64_t seed, int64_t first_rep,
+                 uint32_t* err_host, uint32_t* err_dev) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    ARG(n_rep >= 1 && n_rep <= c->max_batch);
+    ARG(n_iter >= 0 && n_iter <= 16);
+    ARG(c->S >= 1);
+    const int S = c->S, N = c->N, TP = c->T * c->paths;
+    c->cur_batch = n_rep; c->last_iter = n_iter;
+    cudaStream_t st = c->stream;
+    if (c->profiling) CK(cudaEventRecord(c->ev[0], st));
+    // ---- stage 0: draws
+    const double *du = c->doppler_u.p, *pu = c->phase_u.p;
+    const cplx* noise = c->noise.p;
+    const uint8_t* bits[3] = {c->sch[0].bits.p, c->sch[1].bits.p, c->sch[2].bits.p};
+    const int32_t* pidx[2] = {c->pilot_idx[0].p, c->pilot_idx[1].p};
+    if (draws && draws->on_device) {
+        du = draws->doppler_u; pu = draws->phase_u; noise = reinterpret_cast<const cplx*>(draws->noise);
+        for (int i = 0; i < 3; ++i) bits[i] = draws->bits[i];
+        for (int i = 0; i < 2; ++i) pidx[i] = draws->pilot_idx[i];
+    } else if (draws) {
+        ARG(draws->doppler_u && draws->phase_u && draws->noise);
+        CK(cudaMemcpyAsync(c->doppler_u.p, draws->doppler_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->phase_u.p, draws->phase_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->noise.p, draws->noise, sizeof(cplx) * (size_t)n_rep * S * N, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < 3; ++i)
+            if (c->sch[i].set) {
+                ARG(draws->bits[i]);
+                CK(cudaMemcpyAsync(c->sch[i].bits.p, draws->bits[i], (size_t)n_rep * c->sch[i].n_bits, cudaMemcpyHostToDevice, st));
+            }
+        for (int i = 0; i < 2; ++i)
+            if (c->wf[i].set && c->wf[i].nsch) {
+                ARG(draws->pilot_idx[i]);
+                int P = c->sch[c->wf[i].sch[0]].P;
+                CK(cudaMemcpyAsync(c->pilot_idx[i].p, draws->pilot_idx[i], sizeof(int32_t) * n_rep * P, cudaMemcpyHostToDevice, st));
+            }
+    } else {
+        chest_draws tmp;
+        rc = chest_generate_draws((uint64_t)(uintptr_t)c, n_rep, seed, first_rep, &tmp);
+        if (rc) return rc;
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[1], st));
+    // ---- stage 1 (K1): channel realization, TX symbols, s = G x, r0 = H s
+    rc = stage_channel(c, n_rep, du, pu);
+    if (rc) return rc;
+    for (int si = 0; si < 3; ++si) {
+        if (!c->sch[si].set) continue;
+        SchemeDev sd = scheme_dev(c, si);
+        k_tx_symbols<<<n_rep, 256, sd.K_in * sizeof(cplx), st>>>(sd, c->cst[sd.constellation].dev, bits[si],
+                                                                 pidx[sd.waveform], n_rep);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set || !w.nsch) continue;
+        GemmParams p{};
+        p.M = N; p.Kc = w.K; p.n_cols = w.nsch * n_rep; p.lda = w.K; p.ldc = N; p.conj_a = 0;
+        p.At = w.Gt.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.out = w.s.p;
+        p.bsrc = w.x.p; p.ldb = w.K;
+        CK(launch_gemm<GEMM_PLAIN>(c, p, 1));
+        dim3 grid((N + 127) / 128, w.nsch * n_rep);
+        k_apply_h<<<grid, 128, 0, st>>>(w.r0.p, w.s.p, c->h.p, c->d_tap_delay.p, N, c->T, n_rep, -1);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
+    // ---- stage 2 (K2): D = Q^H H G, h = diag(D)
+    for (int wfi = 0; wfi < 2; ++wfi)
+        if (c->wf[wfi].set && c->wf[wfi].nsch) { rc = stage_transmission_matrix(c, wfi, n_rep, 0); if (rc) return rc; }
+    if (c->profiling) CK(cudaEventRecord(c->ev[3], st));
+    // ---- stage 3 (K3a): y = Q^H (r0 + noise) for every (scheme, SNR, realization)
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set || !w.nsch) continue;
+        GemmParams p{};
+        p.M = w.K; p.Kc = N; p.n_cols = w.nsch * S * n_rep; p.lda = N; p.ldc = w.K; p.conj_a = 1;
+        p.At = w.Q.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.y.p;
+        p.r0 = w.r0.p; p.noise = noise; p.noise_scale = c->d_noise_scale.p; p.n_snr = S; p.n_rep = n_rep; p.N = N;
+        CK(launch_gemm<GEMM_DEMOD>(c, p, 1));
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
+    // ---- stage 4/5 (K3b + K4): one-tap stage, then one fused launch per IC iteration
+    rc = build_ctas(c, n_rep);
+    if (rc) return rc;
+    IcParams ip{};
+    ip.n_iter = n_iter; ip.n_rep = n_rep; ip.n_snr = S; ip.K_max = c->K_max; ip.ctas = c->ctas.p;
+    for (int si = 0; si < 3; ++si) if (c->sch[si].set) ip.sch[si] = scheme_dev(c, si);
+    for (int k = 0; k < 2; ++k) ip.cst[k] = c->cst[k].dev;
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        ip.wf_nscheme[wfi] = c->wf[wfi].nsch;
+        ip.wf_scheme[wfi][0] = c->wf[wfi].sch[0]; ip.wf_scheme[wfi][1] = c->wf[wfi].sch[1];
+        ip.D[wfi] = c->wf[wfi].D.p; ip.htrue[wfi] = c->wf[wfi].htrue.p;
+    }
+    ip.scratch = c->scratch.p;
+    size_t n_err = (size_t)n_rep * S * (n_iter + 1) * 12;
+    uint32_t* err = err_dev ? err_dev : c->err.p;
+    CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
+    ip.err = err;
+    for (int it = 0; it <= n_iter; ++it) {
+        ip.it = it;
+        k_ic<<<c->n_ctas, 512, 0, st>>>(ip);
+        c->launches++;
+        CK(cudaGetLastError());
+        if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev[5], st));
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[6], st));
+    if (err_host) CK(cudaMemcpyAsync(err_host, err, n_err * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (c->profiling) {
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+        cudaEventElapsedTime(&c->stage_ms[6], c->ev[0], c->ev[6]);
+    }
+    return CHEST_OK;
+}
+
+}  // namespace
+
+// ================================================================================ extern "C"
+extern "C" {
+
+const char* chest_last_error(void) { return g_err.c_str(); }
+
+int chest_device_info(int device, int* n_sm, int* cc_major, int* cc_minor) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= device) return fail(CHEST_ERR_NO_DEVICE, "no CUDA device");
+    cudaDeviceProp pr;
+    CK(cudaGetDeviceProperties(&pr, device));
+    if (n_sm) *n_sm = pr.multiProcessorCount;
+    if (cc_major) *cc_major = pr.major;
+    if (cc_minor) *cc_minor = pr.minor;
+    return CHEST_OK;
+}
+
+int chest_create(int device, uint64_t* handle) {
+    ARG(handle);
+    int sm = 0, maj = 0, mnr = 0;
+    int rc = chest_device_info(device, &sm, &maj, &mnr);
+    if (rc) return rc;
+    if (maj != 10) return fail(CHEST_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200); no fallback path exists");
+    CK(cudaSetDevice(device));
+    Ctx* c = new Ctx();
+    c->device = device; c->n_sm = sm;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    *handle = (uint64_t)(uintptr_t)c;
+    return CHEST_OK;
+}
+
+int chest_destroy(uint64_t handle) {
+    Ctx* c = from(handle);
+    if (!c) return CHEST_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    // DevBuf has no destructor on purpose (plain members); release explicitly
+    auto relw = [](Waveform& w) {
+        w.G.release(); w.Q.release(); w.Gt.release(); w.q_klo.release(); w.q_khi.release(); w.gt_klo.release();
+        w.gt_khi.release(); w.hg_klo.release(); w.hg_khi.release(); w.x.release(); w.s.release(); w.r0.release();
+        w.y.release(); w.D.release(); w.htrue.release();
+    };
+    relw(c->wf[0]); relw(c->wf[1]);
+    for (auto& k : c->cst) { k.symbol.release(); k.pilot.release(); k.level.release(); k.word_of_grid.release(); }
+    for (auto& s : c->sch) {
+        s.c_rowptr.release(); s.c_col.release(); s.ct_colptr.release(); s.ct_row.release(); s.pilot_pos.release();
+        s.data_pos.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
+        s.hP.release(); s.hdiag.release(); s.xD[0].release(); s.xD[1].release(); s.txword.release(); s.bits.release();
+        for (auto& m : s.mm) {
+            m.tile_ptr.release(); m.tile_delta.release(); m.table.release();
+            for (auto& f : m.frag) f.release();
+            for (auto& f : m.diag) f.release();
+        }
+    }
+    c->d_tap_delay.release(); c->d_tap_amp.release(); c->d_noise_scale.release(); c->doppler_u.release();
+    c->phase_u.release(); c->noise.release(); c->h.release(); c->pilot_idx[0].release(); c->pilot_idx[1].release();
+    c->err.release(); c->scratch.release(); c->tmp_a.release(); c->tmp_b.release(); c->ctas.release(); c->probe.release();
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return CHEST_OK;
+}
+
+int chest_set_channel(uint64_t handle, int n_samples, int n_taps, const double* pdp, double fd, double dt,
+                      int n_paths, int model) {
+    Ctx* c = from(handle);
+    ARG(c && n_samples > 0 && n_taps > 0 && pdp && n_paths > 0 && dt > 0 && fd > 0);
+    ARG(model == CHEST_DOPPLER_JAKES || model == CHEST_DOPPLER_UNIFORM);
+    if (c->N && c->N != n_samples) return fail(CHEST_ERR_ARG, "Total number of samples must be the same for the channel and every waveform");
+    CK(cudaSetDevice(c->device));
+    c->N = n_samples; c->Lt = n_taps; c->fD = fd; c->dt = dt; c->paths = n_paths; c->model = model;
+    c->tap_delay.clear(); c->tap_amp.clear();
+    for (int m = 0; m < n_taps; ++m)
+        if (pdp[m] != 0.0) { c->tap_delay.push_back(m); c->tap_amp.push_back(std::sqrt(pdp[m])); }   // FF.m:131,237
+    c->T = (int)c->tap_delay.size();
+    ARG(c->T > 0);
+    CK(c->d_tap_delay.upload(c->tap_delay, c->stream));
+    CK(c->d_tap_amp.upload(c->tap_amp, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->chan_set = true; c->finalized = false;
+    return CHEST_OK;
+}
+
+int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const double* G, const double* Q) {
+    Ctx* c = from(handle);
+    ARG(c && (wfi == 0 || wfi == 1) && n_samples > 0 && K > 0 && G && Q);
+    if (c->N && c->N != n_samples) return fail(CHEST_ERR_ARG, "Total number of samples must be the same for the channel and every waveform");   // DS.m:79-81
+    CK(cudaSetDevice(c->device));
+    Waveform& w = c->wf[wfi];
+    const int N = n_samples;
+    c->N = N;
+    w.K = K;
+    CK(w.G.upload(reinterpret_cast<const cplx*>(G), (size_t)N * K, c->stream));
+    CK(w.Q.upload(reinterpret_cast<const cplx*>(Q), (size_t)N * K, c->stream));
+    std::vector<cplx> gt((size_t)N * K);
+    const cplx* g = reinterpret_cast<const cplx*>(G);
+    for (int j = 0; j < K; ++j)
+        for (int n = 0; n < N; ++n) gt[(size_t)j + (size_t)K * n] = g[(size_t)n + (size_t)N * j];
+    CK(w.Gt.upload(gt, c->stream));
+    support_ranges(G, N, K, w.g_lo, w.g_hi);
+    support_ranges(Q, N, K, w.q_lo, w.q_hi);
+    std::vector<int> lo, hi;
+    tile_ranges(w.q_lo, w.q_hi, 64, 0, N, lo, hi);
+    CK(w.q_klo.upload(lo, c->stream)); CK(w.q_khi.upload(hi, c->stream));
+    // row supports of G (which symbols j touch sample n) for s = G x
+    std::vector<int> rlo(N, K), rhi(N, 0);
+    for (int j = 0; j < K; ++j)
+        for (int n = w.g_lo[j]; n < w.g_hi[j]; ++n) { rlo[n] = std::min(rlo[n], j); rhi[n] = std::max(rhi[n], j + 1); }
+    tile_ranges(rlo, rhi, 64, 0, K, lo, hi);
+    CK(w.gt_klo.upload(lo, c->stream)); CK(w.gt_khi.upload(hi, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    w.set = true; c->finalized = false;
+    return CHEST_OK;
+}
+
+int chest_set_constellation(uint64_t handle, int which, int order, const double* sym, const uint8_t* bitmap) {
+    Ctx* c = from(handle);
+    ARG(c && (which == 0 || which == 1) && order >= 2 && sym && bitmap);
+    CK(cudaSetDevice(c->device));
+    Constellation& k = c->cst[which];
+    int nb = 0;
+    while ((1 << nb) < order) ++nb;
+    ARG((1 << nb) == order);
+    k.order = order; k.nbits = nb; k.is_qam = (which == CHEST_CONST_QAM);
+    // SymbolMapping is sorted by bit value, so the row index must equal bi2de(BitMapping(row,:)) (SC.m:64-66)
+    for (int m = 0; m < order; ++m) {
+        int w = 0;
+        for (int t = 0; t < nb; ++t) w |= (bitmap[m + (size_t)order * t] & 1) << t;
+        if (w != m) return fail(CHEST_ERR_ARG, "BitMapping rows are not sorted by bit value");
+    }
+    std::vector<cplx> s(order), pil(order);
+    for (int m = 0; m < order; ++m) {
+        s[m] = cmake(sym[2 * m], sym[2 * m + 1]);
+        double a = std::hypot(s[m].x, s[m].y);
+        pil[m] = cmake(s[m].x / a, s[m].y / a);                       // xP./abs(xP), DS.m:366,368
+    }
+    std::vector<double> lev;
+    for (int m = 0; m < order; ++m) lev.push_back(s[m].x);
+    std::sort(lev.begin(), lev.end());
+    lev.erase(std::unique(lev.begin(), lev.end()), lev.end());
+    k.n_axis = (int)lev.size();
+    ARG(k.n_axis >= 2);
+    std::vector<int> grid;
+    if (!k.is_qam) {
+        ARG(k.n_axis == order);
+        grid.assign(order, -1);
+        for (int m = 0; m < order; ++m) {
+            ARG(s[m].y == 0.0);
+            int t = (int)(std::lower_bound(lev.begin(), lev.end(), s[m].x) - lev.begin());
+            grid[t] = m;
+        }
+    } else {
+        ARG(k.n_axis * k.n_axis == order);
+        grid.assign(order, -1);
+        for (int m = 0; m < order; ++m) {
+            int ti = (int)(std::lower_bound(lev.begin(), lev.end(), s[m].x) - lev.begin());
+            auto itq = std::lower_bound(lev.begin(), lev.end(), s[m].y);
+            ARG(itq != lev.end() && *itq == s[m].y);
+            grid[ti * k.n_axis + (int)(itq - lev.begin())] = m;
+        }
+    }
+    for (int v : grid) ARG(v >= 0);
+    CK(k.symbol.upload(s, c->stream)); CK(k.pilot.upload(pil, c->stream));
+    CK(k.level.upload(lev, c->stream)); CK(k.word_of_grid.upload(grid, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    k.dev.order = order; k.dev.nbits = nb; k.dev.n_axis = k.n_axis; k.dev.is_qam = k.is_qam;
+    k.dev.symbol = k.symbol.p; k.dev.pilot = k.pilot.p; k.dev.level = k.level.p; k.dev.word_of_grid = k.word_of_grid.p;
+    k.set = true; c->finalized = false;
+    return CHEST_OK;
+}
+
+int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_data, const int64_t* jc,
+                     const int32_t* ir, const double* val, const int32_t* pilot_pos, const int32_t* data_pos,
+                     double kappa, double dpr, int detect, int constellation, const uint8_t* considered) {
+    Ctx* c = from(handle);
+    ARG(c && si >= 0 && si < 3 && (wfi == 0 || wfi == 1) && jc && ir && val && pilot_pos && considered);
+    ARG(c->wf[wfi].set && c->cst[constellation & 1].set);
+    ARG(detect >= 0 && detect <= 2 && (detect == CHEST_DETECT_DESPREAD_REAL || data_pos));
+    ARG(P > 0 && P <= 64 && n_data > 0 && k_in >= P + n_data && kappa > 0 && dpr > 0);
+    CK(cudaSetDevice(c->device));
+    Scheme& s = c->sch[si];
+    const int K = c->wf[wfi].K;
+    s.waveform = wfi; s.K = K; s.K_in = k_in; s.P = P; s.n_data = n_data; s.detect = detect;
+    s.constellation = constellation; s.kappa = kappa; s.dpr = dpr;
+    const int nb = c->cst[constellation].nbits;
+    s.n_bits = n_data * nb;
+    ARG(nb <= 32);
+    const int64_t nnz = jc[k_in];
+    s.c_nnz = nnz;
+    const cplx* v = reinterpret_cast<const cplx*>(val);
+    // CSC (columns of C) for the de-spreading C' x, CSR (rows of C) for the precoding C z
+    std::vector<int> colptr(k_in + 1), rows(nnz), rowptr(K + 1, 0), cols(nnz);
+    std::vector<cplx> vcsc(nnz), vcsr(nnz);
+    for (int k = 0; k <= k_in; ++k) colptr[k] = (int)jc[k];
+    for (int64_t e = 0; e < nnz; ++e) { ARG(ir[e] >= 0 && ir[e] < K); rows[e] = ir[e]; vcsc[e] = v[e]; rowptr[ir[e] + 1]++; }
+    for (int i = 0; i < K; ++i) rowptr[i + 1] += rowptr[i];
+    std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
+    for (int k = 0; k < k_in; ++k)
+        for (int e = colptr[k]; e < colptr[k + 1]; ++e) { int d = fill[rows[e]]++; cols[d] = k; vcsr[d] = vcsc[e]; }
+    CK(s.c_rowptr.upload(rowptr, c->stream)); CK(s.c_col.upload(cols, c->stream)); CK(s.c_val.upload(vcsr, c->stream));
+    CK(s.ct_colptr.upload(colptr, c->stream)); CK(s.ct_row.upload(rows, c->stream)); CK(s.ct_val.upload(vcsc, c->stream));
+    std::vector<int> pp(pilot_pos, pilot_pos + P);
+    for (int x : pp) ARG(x >= 0 && x < K);
+    CK(s.pilot_pos.upload(pp, c->stream));
+    if (data_pos) {
+        std::vector<int> dp(data_pos, data_pos + n_data);
+        for (int x : dp) ARG(x >= 0 && x < K);
+        CK(s.data_pos.upload(dp, c->stream));
+    }
+    std::vector<uint32_t> mask(n_data, 0);
+    s.considered.assign(considered, considered + (size_t)n_data * nb);
+    s.n_bits_edge = 0;
+    for (int d = 0; d < n_data; ++d)
+        for (int t = 0; t < nb; ++t)
+            if (considered[(size_t)d * nb + t]) { mask[d] |= 1u << t; s.n_bits_edge++; }
+    CK(s.edge_mask.upload(mask, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    s.set = true; c->finalized = false;
+    return CHEST_OK;
+}
+
+int chest_set_snr(uint64_t handle, int n_snr, const double* pn) {
+    Ctx* c = from(handle);
+    ARG(c && n_snr > 0 && pn);
+    CK(cudaSetDevice(c->device));
+    c->S = n_snr; c->pn.assign(pn, pn + n_snr);
+    std::vector<double> sc(n_snr);
+    for (int i = 0; i < n_snr; ++i) sc[i] = std::sqrt(pn[i] / 2.0);      // DS.m:399
+    CK(c->d_noise_scale.upload(sc, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->finalized = false;
+    return CHEST_OK;
+}
+
+int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_t* jc, const int64_t* ir,
+                   const double* val) {
+    Ctx* c = from(handle);
+    ARG(c && si >= 0 && si < 3 && (variant == 0 || variant == 1) && jc && ir && val);
+    ARG(c->sch[si].set && n_snr == c->S);
+    CK(cudaSetDevice(c->device));
+    Scheme& s = c->sch[si];
+    MmseVariant& m = s.mm[variant];
+    const int K = s.K, P = s.P, P4 = (P + 3) / 4, RT = (K + 7) / 8, ND = 2 * K - 1;
+    const int64_t K2 = (int64_t)K * K;
+    const cplx* v = reinterpret_cast<const cplx*>(val);
+    // pass 1: which (row tile, diagonal offset) pairs hold any off-diagonal non-zero
+    std::vector<int> lut((size_t)RT * ND, -1);
+    for (int64_t e = 0; e < jc[n_snr]; ++e) {
+        int64_t r = ir[e];
+        ARG(r >= 0 && r < K2 * P);
+        int64_t rem = r % K2;
+        int j = (int)(rem / K), i = (int)(rem % K);
+        if (i != j) lut[(size_t)(i >> 3) * ND + (j - i + K - 1)] = 0;
+    }
+    std::vector<int> tptr(RT + 1, 0), tdel;
+    for (int rt = 0; rt < RT; ++rt) {
+        for (int d = 0; d < ND; ++d)
+            if (lut[(size_t)rt * ND + d] == 0) { lut[(size_t)rt * ND + d] = (int)tdel.size(); tdel.push_back(d - (K - 1)); }
+        tptr[rt + 1] = (int)tdel.size();
+    }
+    m.n_tiles = (int)tdel.size();
+    CK(m.tile_ptr.upload(tptr, c->stream));
+    CK(m.tile_delta.upload(tdel.empty() ? std::vector<int>(1, 0) : tdel, c->stream));
+    for (auto& f : m.frag) f.release();
+    for (auto& f : m.diag) f.release();
+    m.frag.assign(n_snr, DevBuf<cplx>()); m.diag.assign(n_snr, DevBuf<cplx>());
+    std::vector<WTiles> table(n_snr);
+    std::vector<cplx> frag((size_t)std::max(m.n_tiles, 1) * P4 * 32), dg((size_t)K * P);
+    std::vector<char> pair_seen;
+    m.nnz_offdiag_pairs = 0;
+    for (int snr = 0; snr < n_snr; ++snr) {
+        std::fill(frag.begin(), frag.end(), cmake(0.0, 0.0));
+        std::fill(dg.begin(), dg.end(), cmake(0.0, 0.0));
+        for (int64_t e = jc[snr]; e < jc[snr + 1]; ++e) {
+            int64_t r = ir[e];
+            int p = (int)(r / K2);
+            int64_t rem = r % K2;
+            int j = (int)(rem / K), i = (int)(rem % K);
+            if (i == j) { dg[(size_t)i * P + p] = v[e]; continue; }
+            int t = lut[(size_t)(i >> 3) * ND + (j - i + K - 1)];
+            frag[((size_t)t * P4 + (p >> 2)) * 32 + (i & 7) * 4 + (p & 3)] = v[e];
+        }
+        CK(m.frag[snr].upload(frag, c->stream));
+        CK(m.diag[snr].upload(dg, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        table[snr].frag = m.frag[snr].p; table[snr].diag = m.diag[snr].p;
+    }
+    // exact count of off-diagonal (i,j) pairs with any non-zero pilot weight (work model)
+    {
+        std::vector<char> seen((size_t)K2, 0);
+        for (int64_t e = 0; e < jc[n_snr]; ++e) seen[(size_t)(ir[e] % K2)] = 1;
+        int64_t cnt = 0;
+        for (int64_t q = 0; q < K2; ++q) if (seen[q] && (q / K) != (q % K)) ++cnt;
+        m.nnz_offdiag_pairs = cnt;
+    }
+    CK(m.table.upload(table, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    m.set = true; c->finalized = false;
+    return CHEST_OK;
+}
+
+int chest_finalize(uint64_t handle, int max_batch) {
+    Ctx* c = from(handle);
+    ARG(c && max_batch >= 1);
+    if (!c->chan_set) return fail(CHEST_ERR_STATE, "channel not set");
+    CK(cudaSetDevice(c->device));
+    const int B = max_batch, S = c->S, N = c->N;
+    c->K_max = 0;
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set) continue;
+        const int K = w.K, max_delay = c->tap_delay.back();
+        std::vector<int> lo, hi;
+        tile_ranges(w.g_lo, w.g_hi, 64, max_delay, N, lo, hi);
+        CK(w.hg_klo.upload(lo, c->stream)); CK(w.hg_khi.upload(hi, c->stream));
+        // support-aware work model: 8 T supp_G K  +  8 sum |supp(Q_i) ^ supp((HG)_j)|
+        double f = 0;
+        for (int j = 0; j < K; ++j) f += 8.0 * c->T * (w.g_hi[j] - w.g_lo[j]);
+        for (int i = 0; i < K; ++i)
+            for (int j = 0; j < K; ++j) {
+                int a = std::max(w.q_lo[i], w.g_lo[j]), b = std::min(w.q_hi[i], std::min(N, w.g_hi[j] + max_delay));
+                if (b > a) f += 8.0 * (b - a);
+            }
+        w.flops_d = f;
+        double fq = 0, fg = 0;
+        for (int i = 0; i < K; ++i) { fq += 8.0 * (w.q_hi[i] - w.q_lo[i]); fg += 8.0 * (w.g_hi[i] - w.g_lo[i]); }
+        w.flops_demod = fq; w.flops_mod = fg;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    for (int wfi = 0; wfi < 2; ++wfi) { c->wf[wfi].nsch = 0; }
+    for (int si = 0; si < 3; ++si) {
+        Scheme& s = c->sch[si];
+        if (!s.set) continue;
+        if (!s.mm[0].set || !s.mm[1].set) return fail(CHEST_ERR_STATE, "scheme without both MMSE variants");
+        Waveform& w = c->wf[s.waveform];
+        if (w.nsch >= 2) return fail(CHEST_ERR_STATE, "more than two schemes on one waveform");
+        if (w.nsch == 1 && c->sch[w.sch[0]].P != s.P) return fail(CHEST_ERR_STATE, "schemes of one waveform must share the pilot count");
+        w.sch[w.nsch++] = si;
+        c->K_max = std::max(c->K_max, s.K);
+        CK(s.xP.alloc((size_t)B * s.P)); CK(s.txword.alloc((size_t)B * s.n_data)); CK(s.bits.alloc((size_t)B * s.n_bits));
+        CK(s.hP.alloc((size_t)S * B * s.P)); CK(s.hdiag.alloc((size_t)S * B * s.K));
+        CK(s.xD[0].alloc((size_t)S * B * s.n_data)); CK(s.xD[1].alloc((size_t)S * B * s.n_data));
+    }
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set) continue;
+        c->K_max = std::max(c->K_max, w.K);
+        int ns = std::max(w.nsch, 1);
+        CK(w.x.alloc((size_t)ns * B * w.K)); CK(w.s.alloc((size_t)ns * B * N)); CK(w.r0.alloc((size_t)ns * B * N));
+        CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.D.alloc((size_t)B * w.K * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
+        if (w.nsch) CK(c->pilot_idx[wfi].alloc((size_t)B * c->sch[w.sch[0]].P));
+    }
+    CK(c->doppler_u.alloc((size_t)B * c->T * c->paths)); CK(c->phase_u.alloc((size_t)B * c->T * c->paths));
+    CK(c->noise.alloc((size_t)B * std::max(S, 1) * N)); CK(c->h.alloc((size_t)B * c->T * N));
+    CK(c->err.alloc((size_t)B * std::max(S, 1) * 17 * 12));
+    c->max_batch = B; c->cur_batch = B; c->ctas_for_batch = -1;
+    c->finalized = true;
+    return CHEST_OK;
+}
+
+// ---------------------------------------------------------------- tier 1
+int chest_new_realization(uint64_t handle, int batch, const double* du, const double* pu) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(batch >= 1 && batch <= c->max_batch && du && pu);
+    CK(cudaSetDevice(c->device));
+    size_t n = (size_t)batch * c->T * c->paths;
+    CK(cudaMemcpyAsync(c->doppler_u.p, du, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->phase_u.p, pu, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->cur_batch = batch;
+    rc = stage_channel(c, batch, c->doppler_u.p, c->phase_u.p); if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+int chest_new_realization_seeded(uint64_t handle, int batch, uint64_t seed, int64_t first_rep) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(batch >= 1 && batch <= c->max_batch);
+    CK(cudaSetDevice(c->device));
+    int n = c->T * c->paths;
+    dim3 grid((n / 2 + 1 + 127) / 128, batch);
+    k_rng_uniform<<<grid, 128, 0, c->stream>>>(c->doppler_u.p, n, batch, RS_DOPPLER, seed, first_rep);
+    k_rng_uniform<<<grid, 128, 0, c->stream>>>(c->phase_u.p, n, batch, RS_PHASE, seed, first_rep);
+    c->launches += 2;
+    c->cur_batch = batch;
+    rc = stage_channel(c, batch, c->doppler_u.p, c->phase_u.p); if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+int chest_set_impulse_response(uint64_t handle, int batch, const double* h) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(batch >= 1 && batch <= c->max_batch && h);
+    CK(cudaSetDevice(c->device));
+    const size_t N = c->N;
+    const cplx* src = reinterpret_cast<const cplx*>(h);
+    for (int b = 0; b < batch; ++b)
+        for (int t = 0; t < c->T; ++t)
+            CK(cudaMemcpyAsync(c->h.p + ((size_t)b * c->T + t) * N, src + ((size_t)b * c->Lt + c->tap_delay[t]) * N,
+                               sizeof(cplx) * N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->cur_batch = batch;
+    return CHEST_OK;
+}
+
+int chest_get_impulse_response(uint64_t handle, int b, double* out) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(b >= 0 && b < c->cur_batch && out);
+    CK(cudaSetDevice(c->device));
+    std::vector<cplx> h((size_t)c->T * c->N);
+    CK(cudaMemcpyAsync(h.data(), c->h.p + (size_t)b * c->T * c->N, h.size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memset(out, 0, sizeof(double) * 2 * (size_t)c->N * c->Lt);          // zero columns for empty taps (FF.m:201)
+    for (int t = 0; t < c->T; ++t)
+        std::memcpy(out + 2 * (size_t)c->N * c->tap_delay[t], h.data() + (size_t)t * c->N, sizeof(cplx) * c->N);
+    return CHEST_OK;
+}
+
+int chest_get_convolution_csc(uint64_t handle, int b, int64_t* nnz, int64_t* jc, int32_t* ir, double* val) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(b >= 0 && b < c->cur_batch && nnz);
+    const int N = c->N;
+    int64_t tot = 0;
+    for (int d : c->tap_delay) tot += N - d;
+    *nnz = tot;
+    if (!jc || !ir || !val) return CHEST_OK;
+    CK(cudaSetDevice(c->device));
+    std::vector<cplx> h((size_t)c->T * N);
+    CK(cudaMemcpyAsync(h.data(), c->h.p + (size_t)b * c->T * N, h.size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    // column col holds H[col + d, col] = h[col + d, d] for every non-zero tap d, rows ascending (FF.m:284)
+    int64_t e = 0;
+    for (int col = 0; col < N; ++col) {
+        jc[col] = e;
+        for (int t = 0; t < c->T; ++t) {
+            int r = col + c->tap_delay[t];
+            if (r >= N) continue;
+            ir[e] = r; val[2 * e] = h[(size_t)t * N + r].x; val[2 * e + 1] = h[(size_t)t * N + r].y; ++e;
+        }
+    }
+    jc[N] = e;
+    return CHEST_OK;
+}
+
+int chest_convolve(uint64_t handle, int b, const double* s, int n_cols, double* r) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(b >= 0 && b < c->cur_batch && s && r && n_cols >= 1);
+    CK(cudaSetDevice(c->device));
+    size_t n = (size_t)n_cols * c->N;
+    CK(c->tmp_a.upload(reinterpret_cast<const cplx*>(s), n, c->stream));
+    CK(c->tmp_b.alloc(n));
+    dim3 grid((c->N + 127) / 128, n_cols);
+    k_apply_h<<<grid, 128, 0, c->stream>>>(c->tmp_b.p, c->tmp_a.p, c->h.p, c->d_tap_delay.p, c->N, c->T, 1, b);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(r, c->tmp_b.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+int chest_transmission_matrix(uint64_t handle, int b, int wfi, double* D_out, double* h_out) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(b >= 0 && b < c->cur_batch && (wfi == 0 || wfi == 1) && c->wf[wfi].set && D_out);
+    CK(cudaSetDevice(c->device));
+    Waveform& w = c->wf[wfi];
+    rc = stage_transmission_matrix(c, wfi, 1, b); if (rc) return rc;
+    CK(cudaMemcpyAsync(D_out, w.D.p + (size_t)b * w.K * w.K, sizeof(cplx) * (size_t)w.K * w.K, cudaMemcpyDeviceToHost, c->stream));
+    if (h_out) CK(cudaMemcpyAsync(h_out, w.htrue.p + (size_t)b * w.K, sizeof(cplx) * w.K, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+static int plain_gemm(Ctx* c, int wfi, bool demod, const double* in, int n_cols, double* out) {
+    Waveform& w = c->wf[wfi];
+    const int N = c->N, K = w.K;
+    const int len_in = demod ? N : K, len_out = demod ? K : N;
+    CK(c->tmp_a.upload(reinterpret_cast<const cplx*>(in), (size_t)n_cols * len_in, c->stream));
+    CK(c->tmp_b.alloc((size_t)n_cols * len_out));
+    GemmParams p{};
+    p.M = len_out; p.Kc = len_in; p.n_cols = n_cols; p.ldc = len_out; p.out = c->tmp_b.p;
+    p.bsrc = c->tmp_a.p; p.ldb = len_in;
+    if (demod) { p.At = w.Q.p; p.lda = N; p.conj_a = 1; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; }
+    else { p.At = w.Gt.p; p.lda = K; p.conj_a = 0; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; }
+    CK(launch_gemm<GEMM_PLAIN>(c, p, 1));
+    CK(cudaMemcpyAsync(out, c->tmp_b.p, sizeof(cplx) * (size_t)n_cols * len_out, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+int chest_modulate(uint64_t handle, int wfi, const double* x, int n_cols, double* s) {
+    Ctx* c = from(handle);
+    ARG(c && (wfi == 0 || wfi == 1) && c->wf[wfi].set && x && s && n_cols >= 1);
+    CK(cudaSetDevice(c->device));
+    return plain_gemm(c, wfi, false, x, n_cols, s);
+}
+int chest_demodulate(uint64_t handle, int wfi, const double* r, int n_cols, double* y) {
+    Ctx* c = from(handle);
+    ARG(c && (wfi == 0 || wfi == 1) && c->wf[wfi].set && r && y && n_cols >= 1);
+    CK(cudaSetDevice(c->device));
+    return plain_gemm(c, wfi, true, r, n_cols, y);
+}
+
+int chest_estimate(uint64_t handle, int si, int variant, int i_snr, const double* hP, double* Dhat_out, double* hdiag_out) {
+    Ctx* c = from(handle);
+    ARG(c && si >= 0 && si < 3 && (variant == 0 || variant == 1) && hP);
+    Scheme& s = c->sch[si];
+    ARG(s.set && s.mm[variant].set && i_snr >= 0 && i_snr < c->S);
+    CK(cudaSetDevice(c->device));
+    MmseVariant& m = s.mm[variant];
+    const int K = s.K, P = s.P;
+    CK(c->tmp_a.upload(reinterpret_cast<const cplx*>(hP), P, c->stream));
+    CK(c->tmp_b.alloc((size_t)K * K + K));
+    CK(cudaMemsetAsync(c->tmp_b.p, 0, sizeof(cplx) * ((size_t)K * K + K), c->stream));
+    WTiles wt; wt.frag = m.frag[i_snr].p; wt.diag = m.diag[i_snr].p;
+    int n = std::max(m.n_tiles * 8, K);
+    k_estimate<<<(n + 255) / 256, 256, 0, c->stream>>>(c->tmp_b.p, c->tmp_b.p + (size_t)K * K, wt, m.tile_ptr.p,
+                                                       m.tile_delta.p, c->tmp_a.p, K, P, (P + 3) / 4, (K + 7) / 8);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (Dhat_out) CK(cudaMemcpyAsync(Dhat_out, c->tmp_b.p, sizeof(cplx) * (size_t)K * K, cudaMemcpyDeviceToHost, c->stream));
+    if (hdiag_out) CK(cudaMemcpyAsync(hdiag_out, c->tmp_b.p + (size_t)K * K, sizeof(cplx) * K, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+// ---------------------------------------------------------------- tier 2
+int64_t chest_draws_bytes(uint64_t handle, int n_rep) {
+    Ctx* c = from(handle);
+    if (!c) return 0;
+    int64_t per = 2 * (int64_t)c->T * c->paths * 8 + (int64_t)c->S * c->N * 16;
+    for (int si = 0; si < 3; ++si) if (c->sch[si].set) per += c->sch[si].n_bits;
+    for (int wfi = 0; wfi < 2; ++wfi) if (c->wf[wfi].set && c->wf[wfi].nsch) per += 4 * c->sch[c->wf[wfi].sch[0]].P;
+    return per * n_rep;
+}
+
+int chest_generate_draws(uint64_t handle, int n_rep, uint64_t seed, int64_t first_rep, chest_draws* out) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(n_rep >= 1 && n_rep <= c->max_batch && out);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int n = c->T * c->paths;
+    dim3 gu((n / 2 + 1 + 127) / 128, n_rep);
+    k_rng_uniform<<<gu, 128, 0, st>>>(c->doppler_u.p, n, n_rep, RS_DOPPLER, seed, first_rep);
+    k_rng_uniform<<<gu, 128, 0, st>>>(c->phase_u.p, n, n_rep, RS_PHASE, seed, first_rep);
+    c->launches += 2;
+    std::memset(out, 0, sizeof(*out));
+    for (int si = 0; si < 3; ++si) {
+        Scheme& s = c->sch[si];
+        if (!s.set) continue;
+        dim3 gb(((s.n_bits + 127) / 128 + 127) / 128, n_rep);
+        k_rng_bits<<<gb, 128, 0, st>>>(s.bits.p, s.n_bits, n_rep, RS_BITS0 + si, seed, first_rep);
+        c->launches++;
+        out->bits[si] = s.bits.p;
+    }
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set || !w.nsch) continue;
+        Scheme& s = c->sch[w.sch[0]];
+        dim3 gp((s.P + 63) / 64, n_rep);
+        k_rng_index<<<gp, 64, 0, st>>>(c->pilot_idx[wfi].p, s.P, n_rep, c->cst[s.constellation].order, RS_PILOT0 + wfi, seed, first_rep);
+        c->launches++;
+        out->pilot_idx[wfi] = c->pilot_idx[wfi].p;
+    }
+    dim3 gn((c->N + 127) / 128, c->S, n_rep);
+    k_rng_normal<<<gn, 128, 0, st>>>(c->noise.p, c->N, c->S, n_rep, seed, first_rep);
+    c->launches++;
+    CK(cudaGetLastError());
+    out->doppler_u = c->doppler_u.p; out->phase_u = c->phase_u.p;
+    out->noise = reinterpret_cast<const double*>(c->noise.p); out->on_device = 1;
+    return CHEST_OK;
+}
+
+int chest_download_draws(uint64_t handle, int n_rep, double* du, double* pu, uint8_t* b0, uint8_t* b1, uint8_t* b2,
+                         int32_t* p0, int32_t* p1, double* noise) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(n_rep >= 1 && n_rep <= c->max_batch);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    size_t n = (size_t)n_rep * c->T * c->paths;
+    if (du) CK(cudaMemcpyAsync(du, c->doppler_u.p, n * 8, cudaMemcpyDeviceToHost, st));
+    if (pu) CK(cudaMemcpyAsync(pu, c->phase_u.p, n * 8, cudaMemcpyDeviceToHost, st));
+    uint8_t* bb[3] = {b0, b1, b2};
+    for (int si = 0; si < 3; ++si)
+        if (bb[si] && c->sch[si].set) CK(cudaMemcpyAsync(bb[si], c->sch[si].bits.p, (size_t)n_rep * c->sch[si].n_bits, cudaMemcpyDeviceToHost, st));
+    int32_t* pp[2] = {p0, p1};
+    for (int wfi = 0; wfi < 2; ++wfi)
+        if (pp[wfi] && c->wf[wfi].nsch) CK(cudaMemcpyAsync(pp[wfi], c->pilot_idx[wfi].p, sizeof(int32_t) * n_rep * c->sch[c->wf[wfi].sch[0]].P, cudaMemcpyDeviceToHost, st));
+    if (noise) CK(cudaMemcpyAsync(noise, c->noise.p, sizeof(cplx) * (size_t)n_rep * c->S * c->N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CHEST_OK;
+}
+
+int chest_run_batch(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws, uint64_t seed,
+                    int64_t first_rep, uint32_t* err_out) {
+    Ctx* c = from(handle);
+    ARG(c && err_out);
+    CK(cudaSetDevice(c->device));
+    return run_pipeline(c, n_rep, n_iter, draws, seed, first_rep, err_out, nullptr);
+}
+int chest_run_batch_device(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws, uint64_t seed,
+                           int64_t first_rep, uint32_t* err_dev) {
+    Ctx* c = from(handle);
+    ARG(c);
+    CK(cudaSetDevice(c->device));
+    return run_pipeline(c, n_rep, n_iter, draws, seed, first_rep, nullptr, err_dev);
+}
+
+int chest_bit_counts(uint64_t handle, int64_t* n_bits) {
+    Ctx* c = from(handle);
+    ARG(c && n_bits);
+    for (int si = 0; si < 3; ++si) {
+        n_bits[2 * si] = c->sch[si].set ? c->sch[si].n_bits : 0;
+        n_bits[2 * si + 1] = c->sch[si].set ? c->sch[si].n_bits_edge : 0;
+    }
+    return CHEST_OK;
+}
+
+int chest_get_state(uint64_t handle, int what, int si, int rep, int i_snr, double* out) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(si >= 0 && si < 3 && c->sch[si].set && rep >= 0 && rep < c->cur_batch && i_snr >= 0 && i_snr < c->S && out);
+    CK(cudaSetDevice(c->device));
+    Scheme& s = c->sch[si];
+    SchemeDev d = scheme_dev(c, si);
+    size_t col = (size_t)i_snr * c->cur_batch + rep;
+    const cplx* src = nullptr; size_t n = 0;
+    switch (what) {
+        case 0: src = d.y + col * s.K; n = s.K; break;
+        case 1: src = d.hP + col * s.P; n = s.P; break;
+        case 2: src = d.xD[0] + col * s.n_data; n = s.n_data; break;
+        case 3: src = d.xD[1] + col * s.n_data; n = s.n_data; break;
+        case 4: src = d.hdiag + col * s.K; n = s.K; break;
+        default: return fail(CHEST_ERR_ARG, "unknown state selector");
+    }
+    CK(cudaMemcpyAsync(out, src, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+int64_t chest_launch_count(uint64_t handle) { Ctx* c = from(handle); return c ? c->launches : 0; }
+
+int chest_set_profiling(uint64_t handle, int enable) {
+    Ctx* c = from(handle);
+    ARG(c);
+    c->profiling = enable != 0;
+    return CHEST_OK;
+}
+int chest_stage_times(uint64_t handle, float* ms) {
+    Ctx* c = from(handle);
+    ARG(c && ms);
+    for (int i = 0; i < 7; ++i) ms[i] = c->stage_ms[i];
+    return CHEST_OK;
+}
+
+int chest_work_model(uint64_t handle, int n_iter, double* out) {
+    Ctx* c = from(handle);
+    ARG(c && out);
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    const int S = c->S;
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set || !w.nsch) continue;
+        out[0] += w.flops_d;                                                   // K2
+        out[2] += 8.0 * ((double)w.K * w.K - w.K) * w.nsch * S * n_iter;        // perfect CSI (D - diag h) v
+        out[3] += w.nsch * (w.flops_mod + 8.0 * c->T * c->N) + w.nsch * S * w.flops_demod;   // TX + demod
+    }
+    for (int si = 0; si < 3; ++si) {
+        Scheme& s = c->sch[si];
+        if (!s.set) continue;
+        // estimated CSI: off-diagonal W products of iterations 1..n_iter (D-hat of it-1) + diagonal of 0..n_iter
+        double off = 0;
+        for (int it = 1; it <= n_iter; ++it) {
+            int var_prev = (it - 1 == 0 || (it - 1) <= n_iter / 2) ? 0 : 1;
+            off += 8.0 * s.mm[var_prev].nnz_offdiag_pairs * (s.P + 1);
+        }
+        out[1] += S * (off + 8.0 * s.K * s.P * (n_iter + 1));
+        out[4] += (double)S * s.mm[0].n_tiles * ((s.P + 3) / 4) * 32 * 16;     // W bytes streamed per IC launch
+        out[5] += S * n_iter * (8.0 * s.c_nnz);                                // precoding C z, x2 (est + perfect)
+    }
+    out[5] *= 2;
+    return CHEST_OK;
+}
+
+int chest_fp64_peak(uint64_t handle, int mode, int iters, double* tflops) {
+    Ctx* c = from(handle);
+    ARG(c && tflops && iters > 0);
+    CK(cudaSetDevice(c->device));
+    CK(c->probe.alloc(8));
+    const int blocks = c->n_sm * 4, threads = 256;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaEventRecord(a, c->stream));
+        if (mode == 0) k_peak_dmma<<<blocks, threads, 0, c->stream>>>(c->probe.p, iters);
+        else k_peak_dfma<<<blocks, threads, 0, c->stream>>>(c->probe.p, iters);
+        CK(cudaEventRecord(b, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->launches += 2;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    double flops = mode == 0 ? (double)blocks * (threads / 32) * iters * 8.0 * 512.0
+                             : (double)blocks * threads * iters * 16.0 * 2.0;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return CHEST_OK;
+}
+
+}  // extern "C"

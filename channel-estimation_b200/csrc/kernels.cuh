@@ -1,0 +1,636 @@
+// kernels.cuh -- the device side of the Monte-Carlo hot path (DS.m:350-565).
+//   K1  k_synth_h / k_apply_h      channel synthesis + banded, never-materialised H
+//   K2  k_gemm<GEMM_D>             D = Q^H (H G) on FP64 tensor cores (DMMA), support-aware tiles
+//   K3  k_gemm<GEMM_DEMOD>, k_estimate   demodulation GEMM over realizations, explicit D-hat
+//   K4  k_ic                       one launch per interference-cancellation iteration
+#pragma once
+#include "common.cuh"
+
+#define NC_MAX 16          // columns (realizations x SNR points) one IC CTA carries
+
+// ============================================================================ RNG kernels
+// uniforms: out[rep][n_per_rep]
+__global__ void k_rng_uniform(double* __restrict__ out, int n_per_rep, int n_rep, int stream,
+                              uint64_t seed, int64_t first_rep) {
+    int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // two doubles per Philox call
+    int rep = blockIdx.y;
+    int64_t e = pair * 2;
+    if (rep >= n_rep || e >= n_per_rep) return;
+    uint64_t r = (uint64_t)(first_rep + rep);
+    Philox4 p = philox4x32_10((uint32_t)pair, (uint32_t)r, (uint32_t)stream, (uint32_t)(r >> 32),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    double* o = out + (int64_t)rep * n_per_rep;
+    o[e] = u53(p.v[0], p.v[1]);
+    if (e + 1 < n_per_rep) o[e + 1] = u53(p.v[2], p.v[3]);
+}
+// bits: out[rep][n_bits] bytes; 128 bits per Philox call
+__global__ void k_rng_bits(uint8_t* __restrict__ out, int n_bits, int n_rep, int stream,
+                           uint64_t seed, int64_t first_rep) {
+    int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int rep = blockIdx.y;
+    if (rep >= n_rep || blk * 128 >= n_bits) return;
+    uint64_t r = (uint64_t)(first_rep + rep);
+    Philox4 p = philox4x32_10((uint32_t)blk, (uint32_t)r, (uint32_t)stream, (uint32_t)(r >> 32),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint8_t* o = out + (int64_t)rep * n_bits;
+    for (int t = 0; t < 128; ++t) {
+        int64_t e = blk * 128 + t;
+        if (e < n_bits) o[e] = (p.v[t >> 5] >> (t & 31)) & 1u;
+    }
+}
+// indices in [0, order): out[rep][n]
+__global__ void k_rng_index(int32_t* __restrict__ out, int n, int n_rep, int order, int stream,
+                            uint64_t seed, int64_t first_rep) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int rep = blockIdx.y;
+    if (rep >= n_rep || e >= n) return;
+    uint64_t r = (uint64_t)(first_rep + rep);
+    Philox4 p = philox4x32_10((uint32_t)(e >> 1), (uint32_t)r, (uint32_t)stream, (uint32_t)(r >> 32),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    double u = (e & 1) ? u53(p.v[2], p.v[3]) : u53(p.v[0], p.v[1]);
+    int v = (int)floor(u * order);
+    out[(int64_t)rep * n + e] = v < order ? v : order - 1;
+}
+// complex standard normals (Box-Muller): out[rep][snr][n]
+__global__ void k_rng_normal(cplx* __restrict__ out, int n, int n_snr, int n_rep,
+                             uint64_t seed, int64_t first_rep) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int snr = blockIdx.y, rep = blockIdx.z;
+    if (rep >= n_rep || e >= n) return;
+    uint64_t r = (uint64_t)(first_rep + rep);
+    Philox4 p = philox4x32_10((uint32_t)e, (uint32_t)r, (uint32_t)(RS_NOISE | (snr << 8)), (uint32_t)(r >> 32),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    double u1 = u53(p.v[0], p.v[1]), u2 = u53(p.v[2], p.v[3]);
+    double rad = sqrt(-2.0 * log(u1)), s, c;
+    sincospi(2.0 * u2, &s, &c);
+    out[((int64_t)rep * n_snr + snr) * n + e] = cmake(rad * c, rad * s);
+}
+
+// ============================================================================ K1: channel
+// h[rep][tap][n] = sqrt(pdp_tap) / sqrt(paths) * sum_p exp(j 2 pi (phase_p + shift_p n dt))
+// (FF.m:227-237).  One thread per sample n, paths staged in shared memory.
+__global__ void k_synth_h(cplx* __restrict__ h, const double* __restrict__ doppler_u,
+                          const double* __restrict__ phase_u, const double* __restrict__ tap_amp,
+                          int N, int T, int paths, double fD, double dt, int model) {
+    extern __shared__ double sm[];
+    double* shift = sm;
+    double* phase = sm + paths;
+    int tap = blockIdx.y, rep = blockIdx.z;
+    const double* du = doppler_u + (int64_t)rep * T * paths;
+    const double* pu = phase_u + (int64_t)rep * T * paths;
+    const double PI = 3.14159265358979323846;
+    for (int p = threadIdx.x; p < paths; p += blockDim.x) {
+        double u = du[tap + T * p];                       // rand([T 1 paths]): tap fastest
+        shift[p] = (model == 0) ? cos(u * 2.0 * PI) * fD : 2.0 * (u - 0.5) * fD;
+        phase[p] = pu[tap + T * p];
+    }
+    __syncthreads();
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double t = n * dt;
+    double sr = 0.0, si = 0.0;
+    for (int p = 0; p < paths; ++p) {
+        double arg = phase[p] + shift[p] * t;
+        double s, c;
+        sincos((2.0 * PI) * arg, &s, &c);
+        sr += c; si += s;
+    }
+    double inv = sqrt((double)paths);
+    double a = tap_amp[tap];
+    h[((int64_t)rep * T + tap) * N + n] = cmake(a * (sr / inv), a * (si / inv));
+}
+
+// r[col][n] = sum_tap h[rep(col)][tap][n] * s[col][n - delay_tap]   (banded H, never materialised)
+// cols are laid out [group][rep]: rep = col % n_rep.
+__global__ void k_apply_h(cplx* __restrict__ r, const cplx* __restrict__ s, const cplx* __restrict__ h,
+                          const int* __restrict__ tap_delay, int N, int T, int n_rep, int rep_fixed) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int col = blockIdx.y;
+    if (n >= N) return;
+    int rep = rep_fixed >= 0 ? rep_fixed : col % n_rep;
+    const cplx* sc = s + (int64_t)col * N;
+    cplx acc = cmake(0.0, 0.0);
+    for (int t = 0; t < T; ++t) {
+        int d = tap_delay[t];
+        if (n >= d) cfma(acc, h[((int64_t)rep * T + t) * N + n], sc[n - d]);
+    }
+    r[(int64_t)col * N + n] = acc;
+}
+
+// ============================================================================ constellations
+struct ConstDev {
+    int order, nbits, n_axis;           // n_axis = order (PAM) or sqrt(order) (QAM)
+    int is_qam;
+    const cplx* symbol;                 // SymbolMapping[word]
+    const cplx* pilot;                  // SymbolMapping[word] / |.|
+    const double* level;                // axis levels, ascending (n_axis)
+    const int* word_of_grid;            // PAM: [t] ; QAM: [ti * n_axis + tq] -> word
+};
+
+// nearest axis level, decided by the same |x - level| comparison the reference's argmin uses
+__device__ __forceinline__ int nearest_level(const double* __restrict__ lev, int n, double x) {
+    double step = lev[1] - lev[0];
+    int t = (int)floor((x - lev[0]) / step + 0.5);
+    t = t < 0 ? 0 : (t > n - 1 ? n - 1 : t);
+    double best = fabs(x - lev[t]);
+    if (t > 0 && fabs(x - lev[t - 1]) < best) { best = fabs(x - lev[t - 1]); t = t - 1; }
+    else if (t < n - 1 && fabs(x - lev[t + 1]) < best) { t = t + 1; }
+    return t;
+}
+__device__ __forceinline__ int demap_word(const ConstDev& cd, cplx x) {
+    if (!cd.is_qam) return cd.word_of_grid[nearest_level(cd.level, cd.n_axis, x.x)];
+    int ti = nearest_level(cd.level, cd.n_axis, x.x);
+    int tq = nearest_level(cd.level, cd.n_axis, x.y);
+    return cd.word_of_grid[ti * cd.n_axis + tq];
+}
+
+// ============================================================================ scheme descriptors
+struct WTiles {                    // one (variant, snr) MMSE matrix in diagonal-tile form
+    const cplx* frag;              // [tile][P4][32 lanes] : lane = 4*row + p%4  -> W[i, i+delta, p]
+    const cplx* diag;              // [K][P]  W[i,i,p]
+};
+struct SchemeDev {
+    int waveform, K, K_in, P, P4, n_data, nbits, detect_mode, constellation, n_bits_total;
+    double sqrt_kappa, dpr, sqrt_dpr;
+    const int* c_rowptr; const int* c_col; const cplx* c_val;      // precoder C, CSR (K rows)
+    const int* ct_colptr; const int* ct_row; const cplx* ct_val;   // precoder C, CSC (K_in cols)
+    const int* pilot_pos; const int* data_pos; const uint32_t* edge_mask;   // per data symbol bit mask
+    // MMSE matrices: tile lists per variant, fragments per (variant, snr)
+    const int* tile_ptr[2];        // [RT+1]
+    const int* tile_delta[2];      // [n_tiles]
+    const WTiles* w[2];            // [n_snr]
+    // per-batch state
+    cplx* xP;                      // [rep][P]      unit-modulus pilots
+    uint32_t* txword;              // [rep][n_data] transmitted bit words
+    cplx* x;                       // [rep][K]      precoded symbols
+    cplx* y;                       // [snr][rep][K]
+    cplx* hP;                      // [snr][rep][P]
+    cplx* hdiag;                   // [snr][rep][K]
+    cplx* xD[2];                   // [csi][snr][rep][n_data]
+};
+
+// ============================================================================ TX symbols
+// bits -> data symbols, pilot indices -> unit-modulus pilots, x = C [xP; xD]  (DS.m:355-373)
+__global__ void k_tx_symbols(SchemeDev sd, ConstDev cd, const uint8_t* __restrict__ bits,
+                             const int32_t* __restrict__ pilot_idx, int n_rep) {
+    extern __shared__ cplx zs[];
+    int rep = blockIdx.x;
+    if (rep >= n_rep) return;
+    const uint8_t* b = bits + (int64_t)rep * sd.n_bits_total;
+    for (int k = threadIdx.x; k < sd.K_in; k += blockDim.x) {
+        cplx z;
+        if (k < sd.P) {
+            z = cd.pilot[pilot_idx[(int64_t)rep * sd.P + k]];
+            sd.xP[(int64_t)rep * sd.P + k] = z;
+        } else {
+            int d = k - sd.P;
+            uint32_t w = 0;
+            for (int t = 0; t < sd.nbits; ++t) w |= (uint32_t)(b[d * sd.nbits + t] & 1) << t;
+            sd.txword[(int64_t)rep * sd.n_data + d] = w;
+            z = cd.symbol[w];
+        }
+        zs[k] = z;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < sd.K; i += blockDim.x) {
+        cplx acc = cmake(0.0, 0.0);
+        for (int e = sd.c_rowptr[i]; e < sd.c_rowptr[i + 1]; ++e) cfma(acc, sd.c_val[e], zs[sd.c_col[e]]);
+        sd.x[(int64_t)rep * sd.K + i] = acc;
+    }
+}
+
+// ============================================================================ shared-A complex GEMM
+// C[m, col] = sum_k opA[m,k] * B[k, col]  with A shared by every column (and every realization):
+//   A is given "k-contiguous": At[k + lda*m]; conj flag folds Q^H.
+//   B[k, col] comes from a mode-specific loader; C is written as out[col*ldc + m].
+// 64x64 CTA tile, 8 warps (2x4), warp tile 32x16 = 4x2 DMMA tiles, KT = 32.
+enum { GEMM_PLAIN = 0, GEMM_DEMOD = 1, GEMM_D = 2 };
+struct GemmParams {
+    int M, Kc, n_cols, lda, ldc, conj_a;
+    const cplx* At;
+    const int* mt_klo; const int* mt_khi;      // per 64-row tile k support range
+    cplx* out;                                  // [col][ldc]
+    // PLAIN: B[k,col] = bsrc[col*ldb + k]
+    const cplx* bsrc; int ldb;
+    // DEMOD: col = (g*n_snr + snr)*n_rep + rep ; B = r0[(g*n_rep+rep)*N + k] + sqrt(pn[snr]/2)*noise[(rep*n_snr+snr)*N + k]
+    const cplx* r0; const cplx* noise; const double* noise_scale; int n_snr, n_rep;
+    // D: per realization (blockIdx.z): B[k=n, col=j] = sum_t h[rep][t][n] G[n-d_t + N*j]; out += rep*ldc*n_cols
+    const cplx* h; const cplx* G; const int* tap_delay; int T, N;
+    const int* nt_klo; const int* nt_khi;      // per 64-col tile k support range of H*G
+    cplx* hdiag;                                // [rep][K] diagonal of D (may be null)
+    int rep0;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
+    constexpr int TM = 64, TN = 64, KT = 32, LDS = KT + 4;
+    extern __shared__ double smem[];
+    double (*Ar)[LDS] = reinterpret_cast<double (*)[LDS]>(smem);
+    double (*Ai)[LDS] = reinterpret_cast<double (*)[LDS]>(smem + TM * LDS);
+    double (*Br)[LDS] = reinterpret_cast<double (*)[LDS]>(smem + 2 * TM * LDS);
+    double (*Bi)[LDS] = reinterpret_cast<double (*)[LDS]>(smem + 2 * TM * LDS + TN * LDS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
+    const int g = lane >> 2, t4 = lane & 3;
+    const int mt = blockIdx.x, nt = blockIdx.y;
+    const int m0 = mt * TM, n0 = nt * TN;
+    const int rep = (MODE == GEMM_D) ? (int)blockIdx.z + p.rep0 : 0;
+    int klo = p.mt_klo ? p.mt_klo[mt] : 0, khi = p.mt_khi ? p.mt_khi[mt] : p.Kc;
+    if (MODE == GEMM_D) { klo = max(klo, p.nt_klo[nt]); khi = min(khi, p.nt_khi[nt]); }
+    cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * p.ldc * p.n_cols : 0);
+
+    double cr[4][2][2], ci[4][2][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0; }
+
+    for (int k0 = klo; k0 < khi; k0 += KT) {
+        // ---- stage A tile (64 rows x 32 k), planar, conj folded into the sign of Ai
+#pragma unroll
+        for (int e = 0; e < (TM * KT) / 256; ++e) {
+            int idx = tid + e * 256, kk = idx & (KT - 1), r = idx / KT;
+            int gk = k0 + kk, gm = m0 + r;
+            cplx v = cmake(0.0, 0.0);
+            if (gm < p.M && gk < khi) v = p.At[(int64_t)gk + (int64_t)p.lda * gm];
+            Ar[r][kk] = v.x;
+            Ai[r][kk] = p.conj_a ? -v.y : v.y;
+        }
+        // ---- stage B tile (64 cols x 32 k)
+#pragma unroll
+        for (int e = 0; e < (TN * KT) / 256; ++e) {
+            int idx = tid + e * 256, kk = idx & (KT - 1), c = idx / KT;
+            int gk = k0 + kk, col = n0 + c;
+            cplx v = cmake(0.0, 0.0);
+            if (col < p.n_cols && gk < khi) {
+                if (MODE == GEMM_PLAIN) {
+                    v = p.bsrc[(int64_t)col * p.ldb + gk];
+                } else if (MODE == GEMM_DEMOD) {
+                    int r_ = col % p.n_rep, q = col / p.n_rep, snr = q % p.n_snr, grp = q / p.n_snr;
+                    cplx a = p.r0[((int64_t)grp * p.n_rep + r_) * p.N + gk];
+                    cplx nz = p.noise[((int64_t)r_ * p.n_snr + snr) * p.N + gk];
+                    double sc = p.noise_scale[snr];
+                    v = cmake(a.x + sc * nz.x, a.y + sc * nz.y);
+                } else {
+                    const cplx* hr = p.h + (int64_t)rep * p.T * p.N;
+                    const cplx* gc = p.G + (int64_t)p.N * col;
+                    for (int t = 0; t < p.T; ++t) {
+                        int d = p.tap_delay[t];
+                        if (gk >= d) cfma(v, hr[(int64_t)t * p.N + gk], gc[gk - d]);
+                    }
+                }
+            }
+            Br[c][kk] = v.x;
+            Bi[c][kk] = v.y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < KT; kk += 4) {
+            double ar[4], ai[4], br[2], bi[2], nbi[2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                ar[a] = Ar[wm * 32 + a * 8 + g][kk + t4];
+                ai[a] = Ai[wm * 32 + a * 8 + g][kk + t4];
+            }
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                br[b] = Br[wn * 16 + b * 8 + g][kk + t4];
+                bi[b] = Bi[wn * 16 + b * 8 + g][kk + t4];
+                nbi[b] = dneg(bi[b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) zmma884(cr[a][b], ci[a][b], ar[a], ai[a], br[b], bi[b], nbi[b]);
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: C[g][2*t4 + e] of each 8x8 tile
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int m = m0 + wm * 32 + a * 8 + g, col = n0 + wn * 16 + b * 8 + 2 * t4 + e;
+                if (m < p.M && col < p.n_cols) {
+                    cplx v = cmake(cr[a][b][e], ci[a][b][e]);
+                    out[(int64_t)col * p.ldc + m] = v;
+                    if (MODE == GEMM_D && p.hdiag && m == col) p.hdiag[(int64_t)rep * p.M + m] = v;
+                }
+            }
+}
+
+// ============================================================================ explicit D-hat (API)
+// Dhat[i, i+delta] = sum_p W[i, i+delta, p] hP[p]  scattered into a zeroed dense K x K; diag from W.diag.
+__global__ void k_estimate(cplx* __restrict__ Dhat, cplx* __restrict__ hdiag, WTiles w,
+                           const int* __restrict__ tile_ptr, const int* __restrict__ tile_delta,
+                           const cplx* __restrict__ hP, int K, int P, int P4, int RT) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_tiles = tile_ptr[RT];
+    if (idx < n_tiles * 8) {
+        int t = idx >> 3, r = idx & 7;
+        int lo = 0, hi = RT;                      // row tile of t: largest rt with tile_ptr[rt] <= t
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (tile_ptr[mid] <= t) lo = mid; else hi = mid; }
+        int i = lo * 8 + r, j = i + tile_delta[t];
+        if (i < K && j >= 0 && j < K) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int p = 0; p < P; ++p) cfma(acc, w.frag[((int64_t)t * P4 + (p >> 2)) * 32 + r * 4 + (p & 3)], hP[p]);
+            if (Dhat) Dhat[(int64_t)j * K + i] = acc;
+        }
+    }
+    if (idx < K) {
+        cplx acc = cmake(0.0, 0.0);
+        for (int p = 0; p < P; ++p) cfma(acc, w.diag[(int64_t)idx * P + p], hP[p]);
+        if (Dhat) Dhat[(int64_t)idx * K + idx] = acc;
+        if (hdiag) hdiag[idx] = acc;
+    }
+}
+
+// ============================================================================ K4: fused IC iteration
+// One launch per iteration `it` (it = 0 is the one-tap stage).  Every CTA owns up to NC_MAX
+// columns and ALL K rows of them:
+//   EST  CTA: one scheme, one SNR point, 16 consecutive realizations (they share W_snr)
+//   PERF CTA: one realization, all (scheme-on-waveform, SNR) columns (they share D_rep)
+// phases: A quantise + precode -> v ; B interference = Woff(hP_prev) v  or  (D - diag h) v (DMMA) ;
+//         C new pilot estimates ; D one-tap channel + equalise ; E de-spread / select, demap, count.
+struct IcCta { int mode, scheme_or_wf, snr, first, n_cols; };   // mode 0 EST, 1 PERF
+struct IcParams {
+    int it, n_iter, n_rep, n_snr, K_max;
+    const IcCta* ctas;
+    SchemeDev sch[3];
+    ConstDev cst[2];
+    int wf_scheme[2][2]; int wf_nscheme[2];
+    const cplx* D[2];          // [rep][K*K] true transmission matrices
+    const cplx* htrue[2];      // [rep][K]
+    cplx* scratch;             // per CTA: 3 buffers of K_max*NC_MAX
+    uint32_t* err;             // [rep][snr][it][scheme][csi][edge]
+};
+
+__device__ __forceinline__ void ic_col(const IcParams& p, const IcCta& c, int col, int& scheme, int& snr, int& rep) {
+    if (c.mode == 0) { scheme = c.scheme_or_wf; snr = c.snr; rep = c.first + col; }
+    else { int q = c.first + col; scheme = p.wf_scheme[c.scheme_or_wf][q / p.n_snr]; snr = q % p.n_snr; rep = c.snr; }
+}
+
+__global__ void __launch_bounds__(512, 1) k_ic(IcParams p) {
+    constexpr int NC = NC_MAX;
+    const IcCta cta = p.ctas[blockIdx.x];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int csi = cta.mode;
+    const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
+    const int K = p.sch[p.wf_scheme[wf][0]].K;
+    cplx* zbuf = p.scratch + (int64_t)blockIdx.x * 3 * p.K_max * NC;
+    cplx* vbuf = zbuf + (int64_t)p.K_max * NC;
+    cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
+    constexpr int HS = NC + 2;             // row stride of the pilot tables: conflict-free 128-bit fragment loads
+    __shared__ cplx hPs[64 * HS];          // previous pilot estimates [p][col]   (P <= 64)
+    __shared__ cplx hPn[64 * HS];          // new pilot estimates
+    __shared__ unsigned int cnt[NC][2];
+    __shared__ int c_scheme[NC], c_snr[NC], c_rep[NC];
+    if (tid < NC) {
+        int s_ = 0, n_ = 0, r_ = 0;
+        if (tid < cta.n_cols) ic_col(p, cta, tid, s_, n_, r_);
+        c_scheme[tid] = s_; c_snr[tid] = n_; c_rep[tid] = (tid < cta.n_cols && r_ < p.n_rep) ? r_ : -1;
+        cnt[tid][0] = cnt[tid][1] = 0;
+    }
+    __syncthreads();
+    const int it = p.it;
+
+    if (it > 0) {
+        // ---------------- phase A: z = [xP; quantise(xD_prev)],  v = C z        (DS.m:482-484, 541-543)
+        int kin_max = 0;
+        for (int c = 0; c < cta.n_cols; ++c) kin_max = max(kin_max, p.sch[c_scheme[c]].K_in);
+        for (int idx = tid; idx < kin_max * NC; idx += nthr) {
+            int c = idx % NC, k = idx / NC;
+            cplx z = cmake(0.0, 0.0);
+            if (c_rep[c] >= 0) {
+                const SchemeDev& sd = p.sch[c_scheme[c]];
+                if (k < sd.P) z = sd.xP[(int64_t)c_rep[c] * sd.P + k];
+                else if (k < sd.K_in) {
+                    const ConstDev& cd = p.cst[sd.constellation];
+                    cplx xd = sd.xD[csi][((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.n_data + (k - sd.P)];
+                    z = cd.symbol[demap_word(cd, xd)];
+                }
+            }
+            zbuf[idx] = z;
+        }
+        if (csi == 0) {
+            const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+            for (int idx = tid; idx < sd.P4 * 4 * NC; idx += nthr) {      // rows P..4*P4-1 are zero padding
+                int c = idx % NC, pp = idx / NC;
+                hPs[pp * HS + c] = (c_rep[c] >= 0 && pp < sd.P)
+                                       ? sd.hP[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.P + pp] : cmake(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < K * NC; idx += nthr) {
+            int c = idx % NC, i = idx / NC;
+            cplx acc = cmake(0.0, 0.0);
+            if (c_rep[c] >= 0) {
+                const SchemeDev& sd = p.sch[c_scheme[c]];
+                for (int e = sd.c_rowptr[i]; e < sd.c_rowptr[i + 1]; ++e) cfma(acc, sd.c_val[e], zbuf[sd.c_col[e] * NC + c]);
+            }
+            vbuf[idx] = acc;
+        }
+        __syncthreads();
+        // ---------------- phase B: interference on FP64 tensor cores
+        const int RT = (K + 7) / 8;
+        if (csi == 0) {
+            const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+            // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
+            const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
+            const WTiles wt = sd.w[var_prev][cta.snr];
+            const int* tptr = sd.tile_ptr[var_prev];
+            const int* tdel = sd.tile_delta[var_prev];
+            const int P4 = sd.P4;
+            for (int rt = warp; rt < RT; rt += nwarp) {
+                double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
+                const int i = rt * 8 + g;
+                for (int t = tptr[rt]; t < tptr[rt + 1]; ++t) {
+                    double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
+                    const cplx* fr = wt.frag + (int64_t)t * P4 * 32 + lane;
+                    for (int pq = 0; pq < P4; ++pq) {
+                        cplx a = __ldg(fr + pq * 32);
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct) {
+                            cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+                            zmma884(tr[ct], ti[ct], a.x, a.y, b.x, b.y, dneg(b.y));
+                        }
+                    }
+                    int j = i + tdel[t];
+                    j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            cplx v = vbuf[j * NC + ct * 8 + 2 * t4 + e];
+                            accr[ct][e] = fma(tr[ct][e], v.x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v.y, accr[ct][e]);
+                            acci[ct][e] = fma(tr[ct][e], v.y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v.x, acci[ct][e]);
+                        }
+                }
+                if (i < K) {
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            int c = ct * 8 + 2 * t4 + e;
+                            cplx yv = cmake(0.0, 0.0);
+                            if (c_rep[c] >= 0) yv = sd.y[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i];
+                            ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
+                        }
+                }
+            }
+        } else {
+            const cplx* Dm = p.D[wf] + (int64_t)cta.snr * K * K;     // cta.snr holds the realization
+            for (int rt = warp; rt < RT; rt += nwarp) {
+                double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
+                const int i = rt * 8 + g;
+                for (int j0 = 0; j0 < K; j0 += 4) {
+                    int j = j0 + t4;
+                    cplx a = cmake(0.0, 0.0);
+                    if (i < K && j < K && i != j) a = __ldg(Dm + (int64_t)j * K + i);
+                    int jj = j < K ? j : K - 1;
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct) {
+                        cplx b = vbuf[jj * NC + ct * 8 + g];
+                        zmma884(accr[ct], acci[ct], a.x, a.y, b.x, b.y, dneg(b.y));
+                    }
+                }
+                if (i < K) {
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            int c = ct * 8 + 2 * t4 + e;
+                            cplx yv = cmake(0.0, 0.0);
+                            if (c_rep[c] >= 0) {
+                                const SchemeDev& sc = p.sch[c_scheme[c]];
+                                yv = sc.y[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i];
+                            }
+                            ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
+                        }
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        // one-tap stage: y itself is equalised
+        for (int idx = tid; idx < K * NC; idx += nthr) {
+            int c = idx % NC, i = idx / NC;
+            cplx yv = cmake(1.0, 0.0);
+            if (c_rep[c] >= 0) yv = p.sch[c_scheme[c]].y[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i];
+            ybuf[idx] = yv;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- phase C: LS pilot estimates from the (cancelled) symbols   (DS.m:412-414, 487-489)
+    if (csi == 0) {
+        const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+        for (int idx = tid; idx < sd.P * NC; idx += nthr) {
+            int c = idx % NC, pp = idx / NC;
+            cplx hp = cmake(0.0, 0.0);
+            if (c_rep[c] >= 0) {
+                cplx q = cdiv(ybuf[sd.pilot_pos[pp] * NC + c], sd.xP[(int64_t)c_rep[c] * sd.P + pp]);
+                hp = cmake(q.x / sd.sqrt_kappa, q.y / sd.sqrt_kappa);
+                sd.hP[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.P + pp] = hp;
+            }
+            hPn[pp * HS + c] = hp;
+        }
+        __syncthreads();
+    }
+    // ---------------- phase D: one-tap channel + equalisation                  (DS.m:428-429, 515-521)
+    {
+        const int var_cur = (it == 0 || it <= p.n_iter / 2) ? 0 : 1;
+        for (int idx = tid; idx < K * NC; idx += nthr) {
+            int c = idx % NC, i = idx / NC;
+            cplx xh = cmake(0.0, 0.0);
+            if (c_rep[c] >= 0) {
+                const SchemeDev& sd = p.sch[c_scheme[c]];
+                cplx hh;
+                if (csi == 0) {
+                    const cplx* wd = sd.w[var_cur][c_snr[c]].diag + (int64_t)i * sd.P;
+                    hh = cmake(0.0, 0.0);
+                    for (int pp = 0; pp < sd.P; ++pp) cfma(hh, wd[pp], hPn[pp * HS + c]);
+                    sd.hdiag[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i] = hh;
+                } else {
+                    hh = p.htrue[wf][(int64_t)c_rep[c] * K + i];
+                }
+                xh = cdiv(ybuf[idx], hh);
+            }
+            vbuf[idx] = xh;
+        }
+        __syncthreads();
+    }
+    // ---------------- phase E: data-symbol estimates, demap, bit errors         (DS.m:430-433 ...)
+    {
+        int nd_max = 0;
+        for (int c = 0; c < cta.n_cols; ++c) nd_max = max(nd_max, p.sch[c_scheme[c]].n_data);
+        for (int idx = tid; idx < nd_max * NC; idx += nthr) {
+            int c = idx % NC, d = idx / NC;
+            if (c_rep[c] < 0) continue;
+            const SchemeDev& sd = p.sch[c_scheme[c]];
+            if (d >= sd.n_data) continue;
+            const ConstDev& cd = p.cst[sd.constellation];
+            cplx xd;
+            if (sd.detect_mode == 1) {
+                cplx acc = cmake(0.0, 0.0);
+                int k = sd.P + d;
+                for (int e = sd.ct_colptr[k]; e < sd.ct_colptr[k + 1]; ++e) {
+                    cplx t = cmulc(sd.ct_val[e], vbuf[sd.ct_row[e] * NC + c]);
+                    acc.x += t.x; acc.y += t.y;
+                }
+                xd = cmake(acc.x / sd.dpr, 0.0);
+            } else {
+                cplx v = vbuf[sd.data_pos[d] * NC + c];
+                xd = cmake(v.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : v.y / sd.sqrt_dpr);
+            }
+            sd.xD[csi][((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.n_data + d] = xd;
+            uint32_t diff = (uint32_t)demap_word(cd, xd) ^ sd.txword[(int64_t)c_rep[c] * sd.n_data + d];
+            if (diff) {
+                atomicAdd(&cnt[c][0], __popc(diff));
+                uint32_t de = diff & sd.edge_mask[d];
+                if (de) atomicAdd(&cnt[c][1], __popc(de));
+            }
+        }
+        __syncthreads();
+        if (tid < 2 * NC) {
+            int c = tid >> 1, e = tid & 1;
+            if (c < cta.n_cols && c_rep[c] >= 0) {
+                int64_t o = ((((int64_t)c_rep[c] * p.n_snr + c_snr[c]) * (p.n_iter + 1) + it) * 3 + c_scheme[c]) * 4 + csi * 2 + e;
+                p.err[o] = cnt[c][e];
+            }
+        }
+    }
+}
+
+// ============================================================================ FP64 peak probes
+__global__ void k_peak_dmma(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i; }
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+__global__ void k_peak_dfma(double* out, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9 + i;
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 12345.678) out[0] = s;
+}

@@ -1,0 +1,205 @@
+/*
+ * chest_b200.h -- C ABI of the B200-native Monte-Carlo hot path of rnissel/Channel-Estimation.
+ *
+ * This is the drop-in boundary: a MATLAB MEX gateway (matlab/chest_mex.c), the Python host mirror
+ * (channel-estimation_b200/host.py, ctypes) or any other FFI binds exactly these entry points.
+ * The reference has no native interface of its own (it is 100 % MATLAB); each entry point cites
+ * the reference method / script lines it replaces.  `DS.m` = DoublySelectiveChannelEstimation.m,
+ * `FF.m` = +Channel/FastFading.m, `FBMC.m`/`OFDM.m`/`SC.m` = +Modulation/*.m.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative code on failure; the message is
+ *     available from chest_last_error() (thread-local, valid until the next call);
+ *   - all host arrays are column-major (MATLAB order); complex arrays are interleaved
+ *     (re,im) double pairs; indices are 0-based;
+ *   - a context owns all device memory; nothing here takes or returns torch / gpuArray types;
+ *   - there is NO CPU fallback: without an sm_100 device chest_create fails.
+ */
+#ifndef CHEST_B200_H
+#define CHEST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHEST_OK               0
+#define CHEST_ERR_ARG         -1
+#define CHEST_ERR_CUDA        -2
+#define CHEST_ERR_STATE       -3
+#define CHEST_ERR_NO_DEVICE   -4
+
+/* schemes simulated side by side on the same channel + noise (DS.m:371-373,399-403) */
+#define CHEST_SCHEME_AUX   0   /* FBMC, auxiliary symbols */
+#define CHEST_SCHEME_COD   1   /* FBMC, data spreading    */
+#define CHEST_SCHEME_OFDM  2
+#define CHEST_N_SCHEMES    3
+/* waveforms (one G/Q pair each, DS.m:191-195) */
+#define CHEST_WF_FBMC      0
+#define CHEST_WF_OFDM      1
+#define CHEST_N_WF         2
+/* how equalised symbols become data-symbol estimates */
+#define CHEST_DETECT_SELECT_REAL     0  /* real(x(idx)/sqrt(dpr))        DS.m:430,523 */
+#define CHEST_DETECT_DESPREAD_REAL   1  /* real((C'*x)(P+1:end))/dpr     DS.m:436-437,520,524 */
+#define CHEST_DETECT_SELECT_COMPLEX  2  /* x(idx)/sqrt(dpr)              DS.m:444,525 */
+/* constellations (SC.m) */
+#define CHEST_CONST_PAM    0
+#define CHEST_CONST_QAM    1
+/* Doppler models of Channel.FastFading.NewRealization (FF.m:225-232) */
+#define CHEST_DOPPLER_JAKES    0
+#define CHEST_DOPPLER_UNIFORM  1
+/* MMSE matrix variants (DS.m:492): W_MMSE / W_MMSE_noInterference */
+#define CHEST_W_WITH_INTERFERENCE  0
+#define CHEST_W_NO_INTERFERENCE    1
+
+const char* chest_last_error(void);
+
+/* Library / device probe.  n_sm, cc_major, cc_minor may be NULL. */
+int chest_device_info(int device, int* n_sm, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ context life-cycle */
+int chest_create(int device, uint64_t* handle);
+int chest_destroy(uint64_t handle);
+
+/* ------------------------------------------------------------------ one-time setup
+ * (the outputs of DS.m:50-313, which stay on the host)            */
+
+/* Channel.FastFading constructor state (FF.m:25-192): N samples, the normalised power delay
+ * profile over ALL Lt taps (zeros allowed, FF.m:129), maximum Doppler shift, dt, paths. */
+int chest_set_channel(uint64_t handle, int n_samples, int n_taps, const double* pdp_normalized,
+                      double max_doppler_hz, double dt, int n_paths, int doppler_model);
+
+/* G = GetTXMatrix (N x K) and Q = GetRXMatrix' (N x K) of one waveform
+ * (FBMC.m:318-354, OFDM.m:184-218; DS.m:191-195).  Complex interleaved, column-major. */
+int chest_set_waveform(uint64_t handle, int waveform, int n_samples, int n_symbols_k,
+                       const double* G, const double* Q);
+
+/* SignalConstellation tables (SC.m:24-74): SymbolMapping (order complex values, sorted by bit
+ * value) and BitMapping (order x nbits, column-major, 0/1 bytes). */
+int chest_set_constellation(uint64_t handle, int which, int order,
+                            const double* symbol_mapping, const uint8_t* bit_mapping);
+
+/* One transmission scheme: precoder C (K x K_in sparse CSC, complex; AuxiliaryMethod /
+ * CodingMethod .PrecodingMatrix or PilotMapping_OFDM, DS.m:116-137), pilot positions
+ * (find(PilotMatrix==1)), data positions (rows selected at DS.m:430/444; NULL for the
+ * de-spreading scheme), kappa (DS.m:140-142), data power reduction, detection mode, and the
+ * "NoEdge" bit mask ConsideredBits_* (DS.m:170-172; n_data*nbits bytes). */
+int chest_set_scheme(uint64_t handle, int scheme, int waveform, int k_in, int n_pilots, int n_data,
+                     const int64_t* c_jc, const int32_t* c_ir, const double* c_val,
+                     const int32_t* pilot_pos, const int32_t* data_pos,
+                     double kappa, double data_power_reduction, int detect_mode, int constellation,
+                     const uint8_t* considered_bits);
+
+/* Noise powers Pn_time per SNR point (DS.m:398). */
+int chest_set_snr(uint64_t handle, int n_snr, const double* pn_time);
+
+/* W_MMSE_* / W_MMSE_noInterference_* of one scheme (DS.m:279-313): a (K^2 P) x n_snr sparse
+ * matrix in CSC form exactly as MATLAB stores it (jc: n_snr+1, ir: row = i + K j + K^2 p). */
+int chest_set_mmse(uint64_t handle, int scheme, int variant, int n_snr,
+                   const int64_t* jc, const int64_t* ir, const double* val);
+
+/* Allocate device state for batches of up to max_batch realizations.  Must follow the setters. */
+int chest_finalize(uint64_t handle, int max_batch);
+
+/* ------------------------------------------------------------------ tier 1: method-level calls */
+
+/* Channel.FastFading.NewRealization (FF.m:194-250, Jakes/Uniform branch) for `batch` independent
+ * realizations.  doppler_u / phase_u: batch x (T x paths) uniforms in the order MATLAB's
+ * rand([T 1 paths]) produces them (tap fastest); host pointers. */
+int chest_new_realization(uint64_t handle, int batch, const double* doppler_u, const double* phase_u);
+/* Same, drawing the uniforms on the device with the counter-based generator
+ * (seed, first_rep + b) -- see DESIGN.md "Random numbers". */
+int chest_new_realization_seeded(uint64_t handle, int batch, uint64_t seed, int64_t first_rep);
+
+/* Load `batch` time-variant impulse responses computed elsewhere (channel realizations exported
+ * from the reference, or the banded pseudo-channels of the correlation setup, DS.m:213,260):
+ * h is batch x (N x Lt) complex, column-major per realization; only the non-zero taps are used. */
+int chest_set_impulse_response(uint64_t handle, int batch, const double* h);
+/* obj.ImpulseResponse(:,:,1,1) of realization b: N x Lt complex (FF.m:237). */
+int chest_get_impulse_response(uint64_t handle, int b, double* out);
+/* GetConvolutionMatrix{1,1} of realization b as CSC (FF.m:276-295): jc[N+1], ir[nnz], val[nnz]
+ * complex; nnz = sum over non-zero taps m of (N - m).  Pass NULLs to query nnz only. */
+int chest_get_convolution_csc(uint64_t handle, int b, int64_t* nnz, int64_t* jc, int32_t* ir, double* val);
+/* Convolution(signal) / ConvolutionMatrix*s (FF.m:253-264, DS.m:383-385): r = H_b * s for
+ * n_cols column vectors of length N (host, complex). */
+int chest_convolve(uint64_t handle, int b, const double* s, int n_cols, double* r);
+
+/* D = Q'*H_b*G and h = diag(D) (DS.m:388-393) of realization b; D_out K x K, h_out K (may be NULL). */
+int chest_transmission_matrix(uint64_t handle, int b, int waveform, double* D_out, double* h_out);
+
+/* s = G*x (Modulation, FBMC.m:319-320 / OFDM.m:185-186) and y = Q'*r (Demodulation,
+ * FBMC.m:344-345 / OFDM.m:206-207) in their matrix form for n_cols columns. */
+int chest_modulate(uint64_t handle, int waveform, const double* x, int n_cols, double* s);
+int chest_demodulate(uint64_t handle, int waveform, const double* r, int n_cols, double* y);
+
+/* D_est = sum_p W(:,:,p) hP(p), h_est = diag(D_est) (DS.m:417-428,493-517).
+ * hP: P complex; Dhat_out K x K (may be NULL); hdiag_out K (may be NULL). */
+int chest_estimate(uint64_t handle, int scheme, int variant, int i_snr, const double* hP,
+                   double* Dhat_out, double* hdiag_out);
+
+/* ------------------------------------------------------------------ tier 2: the loop body */
+
+/* Explicit random draws of n_rep realizations, in the order DS.m:352-368,399 consumes them.
+ * With on_device != 0 the pointers are device pointers (inputs resident in HBM). */
+typedef struct chest_draws {
+    const double*  doppler_u;      /* n_rep x (T x paths)                          FF.m:227 */
+    const double*  phase_u;        /* n_rep x (T x paths)                          FF.m:233 */
+    const uint8_t* bits[CHEST_N_SCHEMES];  /* n_rep x n_bits(scheme), 0/1         DS.m:355-357 */
+    const int32_t* pilot_idx[CHEST_N_WF];  /* n_rep x P, 0-based SymbolMapping idx DS.m:365,367 */
+    const double*  noise;          /* n_rep x n_snr x N complex, randn+1j*randn    DS.m:399 */
+    int            on_device;
+} chest_draws;
+
+/* Bytes a host->device upload of `n_rep` realizations' draws moves (for reporting). */
+int64_t chest_draws_bytes(uint64_t handle, int n_rep);
+
+/* DS.m:350-565 for n_rep realizations: new channel, TX, true D / h, and for every SNR point the
+ * MMSE estimate, one-tap equaliser, n_iter interference-cancellation iterations, the perfect-CSI
+ * twin and all bit-error counts.  Output: err[rep][snr][it][scheme][csi][edge] uint32 counts,
+ * it = 0 (one-tap) .. n_iter, csi 0 = estimated / 1 = perfect, edge 0 = all bits / 1 = NoEdge.
+ * BER_* of DS.m:322-345 = err / n_bits (chest_bit_counts).  err_out is a host pointer.
+ * Either draws (explicit) or, if draws == NULL, the device generator keyed by (seed, first_rep+r). */
+int chest_run_batch(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws,
+                    uint64_t seed, int64_t first_rep, uint32_t* err_out);
+/* Same with the result left on the device: err_dev is a device pointer (used by bench `value`). */
+int chest_run_batch_device(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws,
+                           uint64_t seed, int64_t first_rep, uint32_t* err_dev);
+
+/* n_bits[scheme][edge] used as BER denominators. */
+int chest_bit_counts(uint64_t handle, int64_t* n_bits /* [CHEST_N_SCHEMES][2] */);
+
+/* Fill device-resident draws for n_rep realizations with the counter-based generator; the
+ * returned struct points into context-owned device memory (valid until the next call). */
+int chest_generate_draws(uint64_t handle, int n_rep, uint64_t seed, int64_t first_rep, chest_draws* out);
+/* Copy generated draws back to host buffers laid out like chest_draws (any pointer may be NULL). */
+int chest_download_draws(uint64_t handle, int n_rep, double* doppler_u, double* phase_u,
+                         uint8_t* bits_aux, uint8_t* bits_cod, uint8_t* bits_ofdm,
+                         int32_t* pilot_idx_fbmc, int32_t* pilot_idx_ofdm, double* noise);
+
+/* Parity-mode read-back of per-realization state left by the last chest_run_batch:
+ * what = 0: y (K), 1: hP of the last iteration (P), 2: data-symbol estimates of the last iteration,
+ * estimated CSI (n_data), 3: same, perfect CSI (n_data), 4: h_est = diag(D_est) of the last
+ * iteration (K).  Complex interleaved. */
+int chest_get_state(uint64_t handle, int what, int scheme, int rep, int i_snr, double* out);
+
+/* Kernel-launch counter (all kernels launched by this context since creation). */
+int64_t chest_launch_count(uint64_t handle);
+/* Per-stage device time of the last chest_run_batch in ms (CUDA events on the context stream):
+ * [0] draws/rng, [1] K1 channel+TX, [2] K2 transmission matrix, [3] demodulation,
+ * [4] one-tap stage, [5] IC iterations, [6] total.  Requires chest_set_profiling(handle, 1). */
+int chest_set_profiling(uint64_t handle, int enable);
+int chest_stage_times(uint64_t handle, float* ms /* [7] */);
+/* Algorithmic work of one realization for the roofline:
+ * [0] K2 support-aware flops, [1] K3/K4 estimated-CSI flops per iteration-evaluation set,
+ * [2] perfect-CSI flops, [3] demod/TX flops, [4] bytes of W streamed per IC kernel launch. */
+int chest_work_model(uint64_t handle, int n_iter, double* out /* [8] */);
+
+/* FP64 peak probe: runs a register-resident DMMA (mode 0) or DFMA (mode 1) loop on every SM for
+ * `iters` iterations and returns achieved TFLOP/s; the roofline denominator for K2-K4. */
+int chest_fp64_peak(uint64_t handle, int mode, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEST_B200_H */
