@@ -58,6 +58,8 @@ SIGNATURES = {
     "chest_set_profiling": (c_int, [c_u64, c_int]),
     "chest_stage_times": (c_int, [c_u64, p_f]),
     "chest_work_model": (c_int, [c_u64, c_int, p_d]),
+    "chest_event_record": (c_int, [c_u64, c_int]),
+    "chest_event_elapsed": (c_int, [c_u64, c_int, c_int, p_f]),
     "chest_fp64_peak": (c_int, [c_u64, c_int, c_int, p_d]),
 }
 

@@ -271,6 +271,14 @@ class DeviceContext:
         return dict(zip(("draws", "k1_channel_tx", "k2_transmission_matrix", "k3_demod", "one_tap", "ic_iterations",
                          "total"), [float(x) for x in ms]))
 
+    def event_record(self, slot):
+        self._check(self.lib.chest_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float(0)
+        self._check(self.lib.chest_event_elapsed(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
     def work_model(self, n_iter):
         out = (C.c_double * 8)()
         self._check(self.lib.chest_work_model(self._h, n_iter, out))

@@ -113,6 +113,7 @@ struct Ctx {
     int64_t launches = 0;
     bool profiling = false;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     DevBuf<double> probe;
 };
@@ -378,6 +379,7 @@ int chest_create(int device, uint64_t* handle) {
     c->device = device; c->n_sm = sm;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    for (auto& e : c->user_ev) CK(cudaEventCreate(&e));
     *handle = (uint64_t)(uintptr_t)c;
     return CHEST_OK;
 }
@@ -409,6 +411,7 @@ int chest_destroy(uint64_t handle) {
     c->phase_u.release(); c->noise.release(); c->h.release(); c->pilot_idx[0].release(); c->pilot_idx[1].release();
     c->err.release(); c->scratch.release(); c->tmp_a.release(); c->tmp_b.release(); c->ctas.release(); c->probe.release();
     for (auto& e : c->ev) cudaEventDestroy(e);
+    for (auto& e : c->user_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return CHEST_OK;
@@ -1038,6 +1041,22 @@ int chest_work_model(uint64_t handle, int n_iter, double* out) {
         out[5] += S * n_iter * (8.0 * s.c_nnz);                                // precoding C z, x2 (est + perfect)
     }
     out[5] *= 2;
+    return CHEST_OK;
+}
+
+int chest_event_record(uint64_t handle, int slot) {
+    Ctx* c = from(handle);
+    ARG(c && slot >= 0 && slot < 4);
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->user_ev[slot], c->stream));
+    return CHEST_OK;
+}
+int chest_event_elapsed(uint64_t handle, int a, int b, float* ms) {
+    Ctx* c = from(handle);
+    ARG(c && a >= 0 && a < 4 && b >= 0 && b < 4 && ms);
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->user_ev[b]));
+    CK(cudaEventElapsedTime(ms, c->user_ev[a], c->user_ev[b]));
     return CHEST_OK;
 }
 

@@ -1,0 +1,273 @@
+"""Tier-2 host driver: DoublySelectiveChannelEstimation.m with its loop body (DS.m:350-565) replaced
+by batched device launches.
+
+`DoublySelectiveSimulation(**parameters)` keeps the script's parameter block (DS.m:16-37), runs the
+one-time setup (DS.m:50-313: modem objects, pilot patterns, precoders, correlation matrices, MMSE
+matrices) and hands its outputs to the CUDA library; `run()` returns the 24 BER arrays of
+DS.m:322-345.  The setup's dominant contraction  R_Dij_hP(:,p) = vec(Q' M_p G)  (DS.m:260) is the
+same banded-operator GEMM as the hot path's D = Q' H G, so it runs through K2 on the GPU with the
+pseudo-channel M_p uploaded as an impulse response; everything else in the setup is small host
+linear algebra, as in the reference."""
+import numpy as np
+
+from .channel import FastFading
+from .context import DeviceContext, SCHEME_ID
+from .estimation import ImaginaryInterferenceCancellationAtPilotPosition as _IIC
+from .modulation import FBMC, OFDM, SignalConstellation, _round_half_away
+
+BER_NAMES = {"aux": "FBMC_Aux", "cod": "FBMC_Cod", "ofdm": "OFDM"}
+
+
+class DoublySelectiveSimulation:
+    def __init__(self, M_SNR_dB=tuple(range(10, 41, 5)), NrRepetitions=25, ZeroThresholdSparse=8,
+                 L=24, F=15e3, SamplingRate=15e3 * 24, NrSubframes=1, QAM_ModulationOrder=256,
+                 PilotToDataPowerOffset=2, PilotToDataPowerOffsetAux=4.685, NrIterations=4,
+                 Velocity_kmh=500, PowerDelayProfile="VehicularA", DopplerModel="Jakes", Paths=200,
+                 schemes=("aux", "cod", "ofdm"), max_batch=256, device=0, seed=0, verbose=False):
+        self.p = dict(M_SNR_dB=tuple(M_SNR_dB), NrRepetitions=NrRepetitions, ZeroThresholdSparse=ZeroThresholdSparse,
+                      L=L, F=F, SamplingRate=SamplingRate, NrSubframes=NrSubframes,
+                      QAM_ModulationOrder=QAM_ModulationOrder, PilotToDataPowerOffset=PilotToDataPowerOffset,
+                      PilotToDataPowerOffsetAux=PilotToDataPowerOffsetAux, NrIterations=NrIterations,
+                      Velocity_kmh=Velocity_kmh, PowerDelayProfile=PowerDelayProfile, DopplerModel=DopplerModel,
+                      Paths=Paths)
+        self.schemes = tuple(schemes)
+        self.seed, self.verbose = seed, verbose
+        self.ctx = DeviceContext(device)
+        self._setup(max_batch)
+
+    @classmethod
+    def paper(cls, **kw):
+        """DS.m:42-46."""
+        base = dict(M_SNR_dB=tuple(range(10, 41, 2)), NrRepetitions=1000, SamplingRate=15e3 * 14 * 14, NrSubframes=2)
+        base.update(kw)
+        return cls(**base)
+
+    def _log(self, *a):
+        if self.verbose:
+            print(*a, flush=True)
+
+    # ------------------------------------------------------------------ DS.m:50-313
+    def _setup(self, max_batch):
+        p, ctx = self.p, self.ctx
+        L, F, fs, nsf = p["L"], p["F"], p["SamplingRate"], p["NrSubframes"]
+        self.FBMC = FBMC(L, 30 * nsf, F, fs, 0, False, "Hermite-OQAM", 8, 0, True)            # DS.m:51-62
+        zg = ((self.FBMC.Nr["SamplesTotal"] - (_round_half_away((1 / 15e3 / 14) * fs) + _round_half_away(fs / 15e3))
+               * 14 * nsf) / 2) / fs                                                          # DS.m:66
+        self.OFDM = OFDM(L, 14 * nsf, F, fs, 0, False, 1 / 15e3 / 14, zg)                     # DS.m:67-76
+        if self.OFDM.Nr["SamplesTotal"] != self.FBMC.Nr["SamplesTotal"]:                      # DS.m:79-81
+            raise ValueError("Total number of samples must be the same for OFDM and FBMC.")
+        N = self.N = self.OFDM.Nr["SamplesTotal"]
+        self.PAM = SignalConstellation(int(round(np.sqrt(p["QAM_ModulationOrder"]))), "PAM")  # DS.m:86-87
+        self.QAM = SignalConstellation(p["QAM_ModulationOrder"], "QAM")
+        pm_o, pm_f, pm_aux = self._pilot_matrices(L, nsf)
+        self.PilotMatrix_OFDM, self.PilotMatrix_FBMC, self.AuxilaryPilotMatrix_FBMC = pm_o, pm_f, pm_aux
+        pmo, pmf, pma = (m.reshape(-1, order="F") for m in (pm_o, pm_f, pm_aux))
+        G_F, G_O = self.FBMC.GetTXMatrix(), self.OFDM.GetTXMatrix()                           # DS.m:191-195
+        Q_F, Q_O = self.FBMC.GetRXMatrix().conj().T, self.OFDM.GetRXMatrix().conj().T
+        P = self.NrPilotSymbols = int(np.sum(pmo == 1))
+        use_fbmc = any(s in self.schemes for s in ("aux", "cod"))
+        sch = {}
+        if use_fbmc:
+            D0 = self.FBMC.GetFBMCMatrix()
+        if "aux" in self.schemes:
+            self.AuxiliaryMethod = a = _IIC("Auxiliary", pm_aux, D0, 28, p["PilotToDataPowerOffsetAux"])   # DS.m:116-122
+            sch["aux"] = dict(wf="F", C=a.PrecodingMatrix, dpr=a.DataPowerReduction, nD=a.NrDataSymbols,
+                              kappa=a.PilotToDataPowerOffset * a.DataPowerReduction, const="PAM",
+                              detect="select_real", data_pos=np.flatnonzero(pma == 0))
+        if "cod" in self.schemes:
+            self.CodingMethod = c = _IIC("Coding", pm_f, D0, 20, 2 * p["PilotToDataPowerOffset"])          # DS.m:123-129
+            sch["cod"] = dict(wf="F", C=c.PrecodingMatrix, dpr=c.DataPowerReduction, nD=c.NrDataSymbols,
+                              kappa=c.PilotToDataPowerOffset * c.DataPowerReduction, const="PAM",
+                              detect="despread_real", data_pos=None)
+        if "ofdm" in self.schemes:
+            Ko, nD = pmo.size, int(np.sum(pmo == 0))
+            pmap = np.zeros((Ko, Ko))                                                         # DS.m:134-138
+            pmap[np.flatnonzero(pmo == 1), np.arange(P)] = np.sqrt(p["PilotToDataPowerOffset"])
+            pmap[np.flatnonzero(pmo == 0), P + np.arange(nD)] = 1.0
+            pmap /= np.sqrt(np.mean(np.sum(pmap ** 2, axis=1)))
+            dpr = Ko / (P * p["PilotToDataPowerOffset"] + nD)
+            self.PilotMapping_OFDM, self.DataPowerReduction_OFDM = pmap, dpr
+            sch["ofdm"] = dict(wf="O", C=pmap.astype(np.complex128), dpr=dpr, nD=nD,
+                               kappa=p["PilotToDataPowerOffset"] * dpr, const="QAM", detect="select_complex",
+                               data_pos=np.flatnonzero(pmo == 0))
+        # ---- "NoEdge" masks, DS.m:145-172
+        ct_f = np.zeros(pm_f.shape); ct_f[4:-4, 10:-10] = 1
+        ct_o = np.zeros(pm_o.shape); ct_o[4:-4, 5:-5] = 1
+        ctf, cto = ct_f.reshape(-1, order="F"), ct_o.reshape(-1, order="F")
+        nb = {"PAM": self.PAM.BitMapping.shape[1], "QAM": self.QAM.BitMapping.shape[1]}
+        for name, s in sch.items():
+            Cd = s["C"][:, P:]
+            if name == "aux":
+                cons = np.sum(np.abs(Cd[(ctf == 1) & (pma == 0), :]), axis=0) > s["dpr"] * 0.9
+            elif name == "cod":
+                cons = ~np.any(Cd[ctf == 0, :] != 0, axis=0)
+            else:
+                cons = np.sum(np.abs(Cd[(cto == 1) & (pmo == 0), :]), axis=0) > s["dpr"] * 0.9
+            s["considered_bits"] = np.repeat(cons, nb[s["const"]]).astype(np.uint8)
+            s["nbits"] = nb[s["const"]]
+        self.sch = sch
+        # ---- channel, DS.m:176-186
+        fD = p["Velocity_kmh"] / 3.6 * 2.5e9 / 2.998e8
+        self.ChannelModel = chan = FastFading(fs, p["PowerDelayProfile"], N, fD, p["DopplerModel"], p["Paths"],
+                                              1, 1, False, create_device=False)
+        pdp = chan.Implementation["PowerDelayProfileNormalized"]
+        self.Pn = np.array([fs / (F * L) * 10 ** (-snr / 10) for snr in p["M_SNR_dB"]])      # DS.m:243,398
+        # ---- device context: static operands
+        ctx.set_channel(N, pdp, fD, chan.PHY["dt"], p["Paths"], p["DopplerModel"])
+        wfs = {}
+        if use_fbmc:
+            wfs["F"] = dict(G=G_F, Q=Q_F, pil=np.flatnonzero(pmf == 1))
+        if "ofdm" in self.schemes:
+            wfs["O"] = dict(G=G_O, Q=Q_O, pil=np.flatnonzero(pmo == 1))
+        for w, d in wfs.items():
+            ctx.set_waveform(w, d["G"], d["Q"])
+        ctx.set_constellation("PAM", self.PAM.SymbolMapping, self.PAM.BitMapping)
+        ctx.set_constellation("QAM", self.QAM.SymbolMapping, self.QAM.BitMapping)
+        ctx.set_snr(self.Pn)
+        ctx.finalize(max(P, 1))
+        # ---- correlation matrices (DS.m:208-268) and MMSE matrices (DS.m:277-313)
+        thr = 10.0 ** (-p["ZeroThresholdSparse"])
+        rt = chan.GetTimeCorrelation()[0]
+        taps = np.flatnonzero(pdp)
+        for w, d in wfs.items():
+            self._log("correlation matrices, waveform", w)
+            d["R_hP"], d["sup"], d["R_sup"] = self._pilot_correlations(d, pdp, taps, rt, thr, w)
+        self.wfs = wfs
+        for name, s in sch.items():
+            d = wfs[s["wf"]]
+            ctx.set_scheme(name, s["wf"], s["C"], d["pil"], s["data_pos"], s["kappa"], s["dpr"], s["detect"],
+                           s["const"], s["considered_bits"])
+            GA = d["G"] @ s["C"]                                                               # DS.m:203-205
+            R_nn = d["R_hP"].copy()
+            qn = np.zeros(P)
+            for ip in range(P):                                                                # DS.m:222-234
+                q = d["Q"][:, d["pil"][ip]]
+                R_nn[ip, ip] = self._pilot_power(q, GA, s["kappa"], pdp, taps, rt)
+                qn[ip] = np.real(np.vdot(q, q))
+            K2 = d["G"].shape[1] ** 2
+            for variant in (0, 1):
+                jc, ir, val = [0], [], []
+                for pn in self.Pn:                                                             # DS.m:238-253,282-313
+                    R = R_nn.copy()
+                    R[np.arange(P), np.arange(P)] = np.diag(R_nn) + pn * qn / s["kappa"]
+                    if variant == 1:
+                        R = R - (R_nn - d["R_hP"])
+                    Wv = d["R_sup"] @ np.linalg.pinv(R)
+                    Wv[np.abs(Wv) < thr] = 0
+                    pi, ai = np.nonzero(Wv.T)
+                    ir.append(d["sup"][ai].astype(np.int64) + K2 * pi.astype(np.int64))
+                    val.append(Wv.T[pi, ai])
+                    jc.append(jc[-1] + len(ai))
+                ctx.set_mmse_arrays(name, variant, np.array(jc), np.concatenate(ir), np.concatenate(val))
+            s["R_hP_est_noNoise"] = R_nn
+        ctx.finalize(max_batch)
+        self.max_batch = max_batch
+
+    @staticmethod
+    def _pilot_matrices(L, nsf):
+        """DS.m:91-113."""
+        pm_o = np.zeros((L, 14))
+        pm_o[1::12, 1::7] = 1; pm_o[4::12, 5::7] = 1; pm_o[7::12, 1::7] = 1; pm_o[10::12, 5::7] = 1
+        pm_o = np.tile(pm_o, (1, nsf))
+        pm_f = np.zeros((L, 30))
+        pm_f[1::12, 2::16] = 1; pm_f[4::12, 10::16] = 1; pm_f[7::12, 3::16] = 1; pm_f[10::12, 11::16] = 1
+        pm_f = np.tile(pm_f, (1, nsf))
+        aux = pm_f.copy()
+        for a, b in zip(*np.nonzero(pm_f)):
+            aux[a + 1, b] = aux[a - 1, b] = aux[a, b + 1] = aux[a, b - 1] = -1
+        return pm_o, pm_f, aux
+
+    # R_vecH addresses H(:)[a*(N+1)+m] for tap m and column a (FF.m:377); entries past the bottom of
+    # a column wrap to the top of the next one and those beyond N^2 are cropped (FF.m:406).
+    def _positions(self, m):
+        N = self.N
+        lin = np.arange(N) * (N + 1) + m
+        ok = lin < N * N
+        lin = np.where(ok, lin, 0)
+        return lin % N, lin // N, ok
+
+    def _pilot_correlations(self, d, pdp, taps, rt, thr, wname):
+        """R_hP (DS.m:213), support and values of R_Dij_hP (DS.m:260-267) of one waveform.  The
+        P pseudo-channels  M_p = reshape(R_vecH*kron(g_p.',q_p')',N,N)  are banded; their
+        Q' M_p G run as one batched K2 launch."""
+        N, G, Q, pil = self.N, d["G"], d["Q"], d["pil"]
+        P, K, Lt = len(pil), G.shape[1], len(pdp)
+        hps = np.zeros((P, N, Lt), dtype=np.complex128)
+        corner = []                                   # wrapped (upper-triangular) entries: (p, row, col, value)
+        n_idx = np.arange(N)
+        for ip in range(P):
+            q, g = Q[:, pil[ip]], G[:, pil[ip]]
+            for m in taps:
+                row, col, ok = self._positions(m)
+                zeta = np.where(ok, q[row] * np.conj(g[col]), 0)
+                nz = np.flatnonzero(zeta)
+                mu = pdp[m] * (rt[(N - 1) + n_idx[:, None] - nz[None, :]] @ zeta[nz])
+                reg = ok & (n_idx + m < N)
+                hps[ip, row[reg], m] = mu[reg]
+                for a in np.flatnonzero(ok & ~reg):
+                    corner.append((ip, row[a], col[a], mu[a]))
+        self.ctx.set_impulse_response(hps)
+        R_hP = np.zeros((P, P), dtype=np.complex128)
+        sup_mask = np.zeros(K * K, dtype=bool)
+        cols = []
+        for ip in range(P):
+            Dp, _ = self.ctx.transmission_matrix(wname, ip)
+            for (jp, r, c, v) in corner:                                                       # exactness of FF.m:377
+                if jp == ip and v != 0:
+                    Dp += v * np.outer(np.conj(Q[r, :]), G[c, :])
+            R_hP[:, ip] = Dp[pil, pil]
+            vec = Dp.reshape(-1, order="F")
+            vec[np.abs(vec) < thr] = 0
+            sup_mask |= vec != 0
+            cols.append(vec)
+        sup = np.flatnonzero(sup_mask)
+        R_sup = np.stack([v[sup] for v in cols], axis=1)
+        return R_hP, sup, R_sup
+
+    def _pilot_power(self, q, GA, kappa, pdp, taps, rt):
+        """abs(sum(sum((GA.'*(Temp*R_vecH*Temp')).*GA',2))) with Temp = kron(I, q')/sqrt(kappa), DS.m:224-233:
+        the total power received at one pilot position from all precoded unit-power symbols."""
+        N = self.N
+        tot = 0.0
+        for m in taps:
+            row, col, ok = self._positions(m)
+            sel = np.flatnonzero(ok & (q[row] != 0))
+            U = np.conj(q[row[sel]])[:, None] * GA[col[sel], :]
+            T = rt[(N - 1) + sel[:, None] - sel[None, :]]
+            tot = tot + pdp[m] / kappa * np.sum(np.conj(U) * (T @ U))
+        return abs(tot)
+
+    # ------------------------------------------------------------------ DS.m:350-565
+    def run(self, NrRepetitions=None, NrIterations=None, seed=None, draws=None, first_rep=0):
+        """Monte-Carlo loop.  Returns (ber, err): the 24 BER arrays of DS.m:322-345 keyed by the
+        reference's variable names (S x reps [x I]) and the raw error counts
+        err[rep, snr, it, scheme, csi, edge]."""
+        R = self.p["NrRepetitions"] if NrRepetitions is None else NrRepetitions
+        I = self.p["NrIterations"] if NrIterations is None else NrIterations
+        seed = self.seed if seed is None else seed
+        err = np.zeros((R, len(self.Pn), I + 1, 3, 2, 2), dtype=np.uint32)
+        for r0 in range(0, R, self.max_batch):
+            n = min(self.max_batch, R - r0)
+            if draws is not None:
+                st, keep = self.ctx.pack_draws(draws[r0:r0 + n])
+                err[r0:r0 + n] = self.ctx.run_batch(n, I, st)
+            else:
+                err[r0:r0 + n] = self.ctx.run_batch(n, I, None, seed=seed, first_rep=first_rep + r0)
+        return self.ber_arrays(err), err
+
+    def ber_arrays(self, err):
+        nb = self.ctx.bit_counts()
+        out = {}
+        for name in self.sch:
+            sid = SCHEME_ID[name]
+            for ci, ctag in ((0, ""), (1, "_PerfectCSI")):
+                for ei, etag in ((0, ""), (1, "_NoEdge")):
+                    e = np.transpose(err[:, :, :, sid, ci, ei], (1, 0, 2)) / float(nb[sid, ei])   # S x reps x (1+I)
+                    out["BER_%s_OneTapEqualizer%s%s" % (BER_NAMES[name], ctag, etag)] = e[:, :, 0]
+                    key = ("BER_%s_InterferenceCancellation%s" if ci == 0 else
+                           "BER_%s_PerfectCSI_InterferenceCancellation%s") % (BER_NAMES[name], etag)
+                    out[key] = e[:, :, 1:]
+        return out
+
+    def close(self):
+        self.ctx.close()

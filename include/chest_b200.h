@@ -5,7 +5,7 @@
  * (channel-estimation_b200/host.py, ctypes) or any other FFI binds exactly these entry points.
  * The reference has no native interface of its own (it is 100 % MATLAB); each entry point cites
  * the reference method / script lines it replaces.  `DS.m` = DoublySelectiveChannelEstimation.m,
- * `FF.m` = +Channel/FastFading.m, `FBMC.m`/`OFDM.m`/`SC.m` = +Modulation/*.m.
+ * `FF.m` = +Channel/FastFading.m, `FBMC.m`/`OFDM.m`/`SC.m` live in +Modulation.
  *
  * Conventions
  *   - every function returns 0 on success and a negative code on failure; the message is
@@ -194,6 +194,11 @@ int chest_stage_times(uint64_t handle, float* ms /* [7] */);
  * [0] K2 support-aware flops, [1] K3/K4 estimated-CSI flops per iteration-evaluation set,
  * [2] perfect-CSI flops, [3] demod/TX flops, [4] bytes of W streamed per IC kernel launch. */
 int chest_work_model(uint64_t handle, int n_iter, double* out /* [8] */);
+
+/* Device-timeline timing for callers that cannot see the context's stream: record event `slot`
+ * (0..3) on it; elapsed time between two recorded slots in ms (synchronises on the later one). */
+int chest_event_record(uint64_t handle, int slot);
+int chest_event_elapsed(uint64_t handle, int slot_a, int slot_b, float* ms);
 
 /* FP64 peak probe: runs a register-resident DMMA (mode 0) or DFMA (mode 1) loop on every SM for
  * `iters` iterations and returns achieved TFLOP/s; the roofline denominator for K2-K4. */

@@ -1,0 +1,114 @@
+"""CPU tests of the product's host-side mirror of the reference classes against the oracle: two
+independent restatements (closed-form matrices vs the oracle's literal IFFT modem) must agree."""
+import numpy as np
+import pytest
+
+import chest_b200
+from chest_b200.modulation import FBMC, OFDM, SignalConstellation
+from chest_b200.estimation import (ImaginaryInterferenceCancellationAtPilotPosition as IIC,
+                                   PilotSymbolAidedChannelEstimation as PSACE)
+from chest_b200.channel import FastFading
+from chest_b200.simulation import DoublySelectiveSimulation
+
+
+def test_constellation_tables_match_oracle():
+    from oracle.signal_constellation import SignalConstellation as Ref
+    for order, method in ((16, "PAM"), (4, "PAM"), (256, "QAM"), (16, "QAM"), (4, "QAM")):
+        a, b = SignalConstellation(order, method), Ref(order, method)
+        assert np.allclose(a.SymbolMapping, b.SymbolMapping, rtol=0, atol=1e-15)
+        assert np.array_equal(a.BitMapping, b.BitMapping)
+        bits = np.random.default_rng(0).integers(0, 2, 40 * a.BitMapping.shape[1])
+        assert np.array_equal(a.Symbol2Bit(a.Bit2Symbol(bits)), bits)
+
+
+def test_modem_matrices_match_oracle(ds_default):
+    S = ds_default
+    f = FBMC(24, 30, 15e3, 15e3 * 24, 0, False, "Hermite-OQAM", 8, 0, True)
+    assert f.Nr["SamplesTotal"] == S["N"] == 540
+    G = f.GetTXMatrix()
+    assert np.max(np.abs(G - S["wf"]["F"]["G"])) < 1e-13
+    assert np.max(np.abs(f.GetRXMatrix().conj().T - S["wf"]["F"]["Q"])) < 1e-13
+    assert np.max(np.abs(f.GetFBMCMatrix() - S["D0"])) < 1e-13
+    o = OFDM(24, 14, 15e3, 15e3 * 24, 0, False, 1 / 15e3 / 14, S["ofdm"].PHY["ZeroGuardTimeLength"])
+    assert o.Implementation["CyclicPrefix"] == 2 and o.Implementation["ZeroGuardSamples"] == 88
+    assert np.max(np.abs(o.GetTXMatrix() - S["wf"]["O"]["G"])) < 1e-13
+    assert np.max(np.abs(o.GetRXMatrix().conj().T - S["wf"]["O"]["Q"])) < 1e-13
+
+
+def test_modem_with_intermediate_frequency_matches_oracle():
+    """SimpleVersion_DoublyFlat.m geometry: 12 subcarriers, IF = 20 subcarriers, fs = 2.52 MHz."""
+    from oracle.fbmc import FBMC as RF
+    from oracle.ofdm import OFDM as RO
+    a = FBMC(12, 30, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, "Hermite-OQAM", 8, 0, True)
+    b = RF(12, 30, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, "Hermite-OQAM", 8, 0, True)
+    assert a.Nr["SamplesTotal"] == b.Nr["SamplesTotal"] == 3780
+    assert np.max(np.abs(a.GetTXMatrix() - b.GetTXMatrix())) < 1e-12
+    c = OFDM(12, 15, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, 0, (8 - 1 / 2) * 1 / 15e3 * 1 / 2)
+    d = RO(12, 15, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, 0, (8 - 1 / 2) * 1 / 15e3 * 1 / 2)
+    assert c.Nr["SamplesTotal"] == d.Nr["SamplesTotal"] == 3780
+    assert np.max(np.abs(c.GetTXMatrix() - d.GetTXMatrix())) < 1e-12
+    assert np.max(np.abs(c.GetRXMatrix() - d.GetRXMatrix())) < 1e-12
+
+
+def test_precoders_match_oracle(ds_default):
+    S = ds_default
+    pm_o, pm_f, pm_aux = DoublySelectiveSimulation._pilot_matrices(24, 1)
+    assert np.array_equal(pm_f, S["pm_f"]) and np.array_equal(pm_aux, S["pm_aux"]) and np.array_equal(pm_o, S["pm_o"])
+    a = IIC("Auxiliary", pm_aux, S["D0"], 28, 4.685)
+    assert (a.NrPilotSymbols, a.NrDataSymbols, a.NrAuxiliarySymbols) == (16, 640, 64)
+    assert np.max(np.abs(a.PrecodingMatrix - S["aux"].PrecodingMatrix)) < 1e-12
+    assert abs(a.DataPowerReduction - S["aux"].DataPowerReduction) < 1e-14
+    c = IIC("Coding", pm_f, S["D0"], 20, 4)
+    assert c.NrDataSymbols == 688
+    assert np.max(np.abs(c.PrecodingMatrix - S["cod"].PrecodingMatrix)) < 1e-12
+    assert np.allclose(c.SIR_dB, S["cod"].SIR_dB) and np.allclose(a.SIR_dB, S["aux"].SIR_dB)
+    with pytest.raises(ValueError):
+        IIC("Coding", pm_f, S["D0"], 200, 4)          # overlapping spreading sets (IIC.m:116-118)
+    with pytest.raises(ValueError):
+        IIC("Nonsense", pm_f, S["D0"], 20, 4)
+
+
+def test_pilot_pattern_and_interpolators():
+    d = PSACE("Diamond", [[12, 6], [30, 8]], "linear")
+    assert d.NrPilotSymbols == 8                       # SV.m:57-66
+    assert d.GetAuxiliaryMatrix(1).min() == -1 and np.sum(d.GetAuxiliaryMatrix(1) == -1) == 8
+    r = PSACE("Rectangular", [[12, 6], [30, 8]], "FullAverage")
+    assert np.allclose(r.ChannelInterpolation(np.full(r.NrPilotSymbols, 2 + 1j)), 2 + 1j)
+    mv = PSACE("Diamond", [[12, 6], [30, 8]], "MovingBlockAverage", [12, 30])
+    M = mv.GetInterpolationMatrix()
+    assert np.allclose(M.sum(axis=1), 1)
+    lin = d.GetInterpolationMatrix()
+    assert lin.shape == (360, 8) and np.allclose(lin.sum(axis=1), 1)
+    with pytest.raises(NotImplementedError):
+        PSACE("Diamond", [[12, 6], [30, 8]], "MMSE")   # PSACE.m:110-111: the reference errors too
+    with pytest.raises(ValueError):
+        PSACE("Hexagonal", [[12, 6], [30, 8]], "linear")
+
+
+def test_fast_fading_constructor_tables():
+    ch = FastFading(15e3 * 24, "VehicularA", 540, 1158.18, "Jakes", 200, 1, 1, False, create_device=False)
+    assert np.allclose(ch.Implementation["PowerDelayProfileNormalized"], [0.97981283, 0.02018717])
+    ch2 = FastFading(15e3 * 14 * 14, "VehicularA", 7350, 1158.18, "Jakes", 200, 1, 1, False, create_device=False)
+    assert list(ch2.Implementation["IndexDelayTaps"]) == [0, 1, 2, 3, 5, 7]
+    assert np.allclose(ch2.Implementation["PowerDelayProfileNormalized"][[0, 1, 2, 3, 5, 7]],
+                       [0.485, 0.3853, 0.0611, 0.0485, 0.0153, 0.0049], atol=5e-5)
+    from oracle.fast_fading import FastFading as Ref
+    for name in ("PedestrianA", "VehicularB", "TDL-A_30ns", "ExtendedPedestrianA"):
+        a = FastFading(7.68e6, name, 100, 100.0, "Jakes", 10, create_device=False)
+        b = Ref(7.68e6, name, 100, 100.0, "Jakes", 10)
+        assert np.allclose(a.Implementation["PowerDelayProfileNormalized"], b.Implementation["PowerDelayProfileNormalized"])
+    with pytest.raises(ValueError):
+        FastFading(1e6, "NoSuchModel", 10, 10.0, "Jakes", 4, create_device=False)
+    with pytest.raises(NotImplementedError):
+        FastFading(1e6, "Flat", 10, 10.0, "Discrete-Jakes", 4, create_device=False)
+
+
+def test_product_fails_loudly_without_gpu():
+    """No CPU fallback: on a box without an sm_100 device the product refuses to run."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(chest_b200.ChestError):
+        chest_b200.DeviceContext(0)
+    with pytest.raises(chest_b200.ChestError):
+        FBMC().Modulation(np.zeros((12, 30)))

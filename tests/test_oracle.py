@@ -1,0 +1,126 @@
+"""Oracle self-tests: the identities the reference states in its comments, its closed-form theory
+and hand-derived constants.  The reference ships no golden vectors -- parity unpinned."""
+import numpy as np
+
+from oracle.signal_constellation import SignalConstellation
+from oracle.fbmc import FBMC
+from oracle.ofdm import OFDM
+from oracle.bep import bit_error_probability_doubly_flat_rayleigh as bep
+
+
+def test_geometry_constants(ds_default):
+    S = ds_default
+    assert S["N"] == 540 and S["P"] == 16
+    o = S["ofdm"].Implementation
+    assert (o["CyclicPrefix"], o["ZeroGuardSamples"], o["FFTSize"]) == (2, 88, 24)          # CP 1.71 -> 2 (OFDM.m:73-77)
+    f = S["fbmc"]
+    assert (f.Implementation["TimeSpacing"], f.Nr["SamplesPrototypeFilter"], f.Implementation["FFTSize"]) == (12, 192, 24)
+    assert np.allclose(S["chan"].Implementation["PowerDelayProfileNormalized"], [0.9798, 0.0202], atol=5e-5)
+    assert abs(S["fD"] - 1158.18) < 0.01
+    assert S["wf"]["F"]["K"] == 720 and S["wf"]["O"]["K"] == 336
+    assert [S["schemes"][s]["nD"] for s in ("aux", "cod", "ofdm")] == [640, 688, 320]
+    assert [S["schemes"][s]["nD"] * S["schemes"][s]["nbits"] for s in ("aux", "cod", "ofdm")] == [2560, 2752, 2560]
+
+
+def test_stated_identities(ds_default):
+    S = ds_default
+    rng = np.random.default_rng(0)
+    f, o = S["fbmc"], S["ofdm"]
+    GF, QF, GO, QO = S["wf"]["F"]["G"], S["wf"]["F"]["Q"], S["wf"]["O"]["G"], S["wf"]["O"]["Q"]
+    x = rng.standard_normal((24, 30)) + 1j * rng.standard_normal((24, 30))
+    assert np.max(np.abs(GF @ x.reshape(-1, order="F") - f.Modulation(x))) < 1e-12        # FBMC.m:319-320
+    r = rng.standard_normal(540) + 1j * rng.standard_normal(540)
+    assert np.max(np.abs(QF.conj().T @ r - f.Demodulation(r).reshape(-1, order="F"))) < 1e-12   # FBMC.m:344-345
+    xo = rng.standard_normal((24, 14)) + 1j * rng.standard_normal((24, 14))
+    assert np.max(np.abs(GO @ xo.reshape(-1, order="F") - o.Modulation(xo))) < 1e-12      # OFDM.m:185-186
+    assert np.max(np.abs(QO.conj().T @ r - o.Demodulation(r).reshape(-1, order="F"))) < 1e-12   # OFDM.m:206-207
+    assert np.max(np.abs(QO.conj().T @ GO - np.eye(336))) < 1e-14
+    QG = QF.conj().T @ GF
+    assert np.max(np.abs(QG.real - np.eye(720))) < 5e-7                                    # Hermite residual 4.0e-7
+    assert np.max(np.abs(S["D0"] - QG)) < 1e-13                                            # fast GetFBMCMatrix == Q'G
+    assert np.max(np.abs(f.GetFBMCMatrix(False) - QG)) < 1e-12                             # FBMC.m:356-357
+    w = np.sort(np.unique(np.round(np.abs(S["D0"][:, 0]), 4)))[::-1]
+    assert np.allclose(w[:6], [1, 0.4357, 0.2393, 0.0369, 0.0098, 0.0054])
+
+
+def test_precoder_invariants(ds_default):
+    S = ds_default
+    a, c = S["aux"], S["cod"]
+    assert (a.NrPilotSymbols, a.NrDataSymbols, a.NrAuxiliarySymbols) == (16, 640, 64)
+    assert abs(a.PilotToDataPowerOffset * a.DataPowerReduction - S["kappa"]["aux"]) < 1e-15
+    assert abs(c.DataPowerReduction - 720 / 752) < 1e-14 and abs(S["kappa"]["cod"] - 4 * 720 / 752) < 1e-13
+    assert abs(S["dpr_o"] - 336 / 352) < 1e-15 and abs(S["kappa"]["ofdm"] - 2 * 336 / 352) < 1e-15
+    C = c.PrecodingMatrix
+    g = C.conj().T @ C
+    assert np.allclose(np.diag(g)[16:], c.DataPowerReduction)                              # FBMC.m:595: C'C = I (scaled)
+    assert np.max(np.abs(g - np.diag(np.diag(g)))) < 1e-14
+    pil = S["wf"]["F"]["pil"]
+    for obj in (a, c):                                                                     # IIC.m:9-11
+        T = S["D0"][pil, :] @ obj.PrecodingMatrix
+        assert np.all(obj.SIR_dB > 25)
+        assert np.max(np.abs(T[:, :16].imag)) < 1e-5
+    for obj in (a, c):                                                                     # unit mean TX power
+        assert abs(np.sum(np.abs(obj.PrecodingMatrix) ** 2) / 720 - 1) < 1e-12
+    assert int(S["schemes"]["ofdm"]["considered_bits"].sum()) == 58 * 8
+
+
+def test_correlation_matrices(ds_default):
+    from oracle.ds import ds_setup_literal_check
+    S = ds_default
+    for wf in ("F", "O"):
+        R = S["wf"][wf]["R_hP"]
+        assert np.max(np.abs(R - R.conj().T)) < 1e-14 and np.min(np.linalg.eigvalsh(R)) > -1e-12
+    assert abs(S["wf"]["F"]["R_hP"][0, 0].real - 0.99502) < 1e-5
+    dev = ds_setup_literal_check(S, "ofdm", (0, 9))          # kron / N^2 x N^2 form, FF.m:366-407, DS.m:213-260
+    assert max(dev.values()) < 1e-13
+    dev = ds_setup_literal_check(S, "cod", (5,))
+    assert max(dev.values()) < 1e-13
+    for sc in S["schemes"]:
+        K = S["wf"][S["schemes"][sc]["waveform"]]["K"]
+        frac = np.count_nonzero(S["schemes"][sc]["W"][0]) / (K * K * 16)
+        assert (0.15 < frac < 0.18) if sc != "ofdm" else abs(frac - 1 / 14) < 1e-12
+
+
+def test_constellations():
+    for order, method in ((16, "PAM"), (256, "QAM"), (4, "QAM")):
+        c = SignalConstellation(order, method)
+        assert abs(np.mean(np.abs(c.SymbolMapping) ** 2) - 1) < 1e-14
+        nb = c.BitMapping.shape[1]
+        assert np.array_equal(c.BitMapping @ (1 << np.arange(nb)), np.arange(order))       # sorted by bit value
+        bits = np.random.default_rng(1).integers(0, 2, 200 * nb)
+        sym = c.Bit2Symbol(bits)
+        assert np.array_equal(c.Symbol2Bit(sym), bits) and np.array_equal(c.SymbolQuantization(sym * 1.01), sym)
+        # Gray: nearest neighbours differ in one bit
+        d = np.abs(c.SymbolMapping[:, None] - c.SymbolMapping[None, :])
+        near = np.isclose(d, np.min(d[d > 1e-9]))
+        assert np.all(np.sum(c.BitMapping[:, None, :] != c.BitMapping[None, :, :], axis=2)[near] == 1)
+
+
+def test_theory_curve_known_values():
+    q4 = SignalConstellation(4, "QAM")
+    snr = np.array([0.0, 10.0, 20.0])
+    closed = 0.5 - 1 / (2 * np.sqrt(2 * (1 + 10 ** (-snr / 10)) - 1))                     # SV.m:179 (4-QAM closed form)
+    assert np.max(np.abs(bep(snr, q4.SymbolMapping, q4.BitMapping) - closed)) < 1e-12
+    q256 = SignalConstellation(256, "QAM")
+    v = bep([32.0], q256.SymbolMapping, q256.BitMapping)[0]
+    assert abs(v - 0.0130) < 5e-4                                                          # png/Figure5.png grey line
+
+
+def test_doubly_flat_simulation_matches_theory():
+    """SV.m:118-169 (perfect-CSI branch) with the FFT modem: y/h demapped against the theory curve."""
+    rng = np.random.default_rng(3)
+    o = OFDM(12, 15, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, 0, (8 - 1 / 2) * 1 / 15e3 * 1 / 2)
+    qam = SignalConstellation(16, "QAM")
+    snr_db, errs, tot = 15.0, 0, 0
+    Pn = o.PHY["SamplingRate"] / (o.PHY["SubcarrierSpacing"] * o.Nr["Subcarriers"]) * 10 ** (-snr_db / 10)   # SV.m:92
+    for _ in range(400):
+        bits = rng.integers(0, 2, 12 * 15 * 4)
+        x = qam.Bit2Symbol(bits).reshape(12, 15, order="F")
+        h = np.sqrt(0.5) * (rng.standard_normal() + 1j * rng.standard_normal())
+        s = o.Modulation(x)
+        n = np.sqrt(Pn / 2) * (rng.standard_normal(len(s)) + 1j * rng.standard_normal(len(s)))
+        y = o.Demodulation(h * s + n)
+        errs += np.sum(qam.Symbol2Bit(y.reshape(-1, order="F") / h) != bits)
+        tot += len(bits)
+    theory = bep([snr_db], qam.SymbolMapping, qam.BitMapping)[0]
+    assert abs(errs / tot - theory) < 0.25 * theory
