@@ -69,7 +69,7 @@ class FastFading:
                 raise ValueError("Power delay profile model not supported!")
             idx = np.floor(delays / dt + 0.5).astype(int)                                # round(), FF.m:111
             if WarningIfSampleRateDoesNotMatch and np.sum(np.abs(np.remainder(delays, dt))) > 0:
-                print("Sampling rate does not match the predefined delays of the channel model!")
+                import sys; print("Sampling rate does not match the predefined delays of the channel model!", file=sys.stderr)
             pdp = np.bincount(idx, weights=10.0 ** (np.asarray(p_db, dtype=float) / 10.0))   # FF.m:117-121
             self.PHY["DesiredPowerDelayProfiledB"] = np.vstack([p_db, delays])
         else:

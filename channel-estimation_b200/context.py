@@ -287,5 +287,5 @@ class DeviceContext:
 
     def fp64_peak(self, mode="dmma", iters=20000):
         t = C.c_double(0)
-        self._check(self.lib.chest_fp64_peak(self._h, 0 if mode == "dmma" else 1, iters, C.byref(t)))
+        self._check(self.lib.chest_fp64_peak(self._h, {"dmma": 0, "dfma": 1, "mix": 2}[mode], iters, C.byref(t)))
         return t.value

@@ -144,7 +144,7 @@ void tile_ranges(const std::vector<int>& lo, const std::vector<int>& hi, int til
     for (int t = 0; t < nt; ++t) if (thi[t] <= tlo[t]) { tlo[t] = 0; thi[t] = 0; }
 }
 
-constexpr int GEMM_SMEM = 4 * 64 * 36 * (int)sizeof(double);
+constexpr int GEMM_SMEM = 2 * 2 * 64 * 20 * (int)sizeof(cplx);   // 2 stages x (A + B) x 64 rows x (16+4) complex
 
 template <int MODE>
 cudaError_t launch_gemm(Ctx* c, const GemmParams& p, int n_z) {
@@ -335,7 +335,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     ip.err = err;
     for (int it = 0; it <= n_iter; ++it) {
         ip.it = it;
-        k_ic<<<c->n_ctas, 512, 0, st>>>(ip);
+        k_ic<<<c->n_ctas, 256, 0, st>>>(ip);
         c->launches++;
         CK(cudaGetLastError());
         if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev[5], st));
@@ -1071,6 +1071,7 @@ int chest_fp64_peak(uint64_t handle, int mode, int iters, double* tflops) {
     for (int rep = 0; rep < 2; ++rep) {
         CK(cudaEventRecord(a, c->stream));
         if (mode == 0) k_peak_dmma<<<blocks, threads, 0, c->stream>>>(c->probe.p, iters);
+        else if (mode == 2) k_peak_mix<<<blocks, threads, 0, c->stream>>>(c->probe.p, iters);
         else k_peak_dfma<<<blocks, threads, 0, c->stream>>>(c->probe.p, iters);
         CK(cudaEventRecord(b, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -1079,7 +1080,8 @@ int chest_fp64_peak(uint64_t handle, int mode, int iters, double* tflops) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, a, b));
     double flops = mode == 0 ? (double)blocks * (threads / 32) * iters * 8.0 * 512.0
-                             : (double)blocks * threads * iters * 16.0 * 2.0;
+                   : mode == 2 ? (double)blocks * (threads / 32) * iters * (4.0 * 512.0 + 8.0 * 64.0)
+                               : (double)blocks * threads * iters * 16.0 * 2.0;
     *tflops = flops / (ms * 1e-3) / 1e12;
     cudaEventDestroy(a); cudaEventDestroy(b);
     return CHEST_OK;

@@ -221,14 +221,23 @@ struct GemmParams {
     int rep0;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;                       // src-size 0 -> the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Tiles live in shared memory as interleaved complex [row][k] with a row stride of KT+4 elements, so a
+// lane's (re, im) fragment pair is one conflict-free LDS.128.  Two stages: while the tensor pipe works
+// on stage s, cp.async (A, and B when it is a plain copy) and the computed B values (noise add / banded
+// H applied to G on the fly) fill stage s^1; one barrier per k-tile.
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
-    constexpr int TM = 64, TN = 64, KT = 32, LDS = KT + 4;
+    constexpr int TM = 64, TN = 64, KT = 16, LDS = KT + 4;
     extern __shared__ double smem[];
-    double (*Ar)[LDS] = reinterpret_cast<double (*)[LDS]>(smem);
-    double (*Ai)[LDS] = reinterpret_cast<double (*)[LDS]>(smem + TM * LDS);
-    double (*Br)[LDS] = reinterpret_cast<double (*)[LDS]>(smem + 2 * TM * LDS);
-    double (*Bi)[LDS] = reinterpret_cast<double (*)[LDS]>(smem + 2 * TM * LDS + TN * LDS);
+    cplx (*As)[TM][LDS] = reinterpret_cast<cplx (*)[TM][LDS]>(smem);
+    cplx (*Bs)[TN][LDS] = reinterpret_cast<cplx (*)[TN][LDS]>(smem + 2 * 2 * TM * LDS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
     const int g = lane >> 2, t4 = lane & 3;
@@ -238,6 +247,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
     int klo = p.mt_klo ? p.mt_klo[mt] : 0, khi = p.mt_khi ? p.mt_khi[mt] : p.Kc;
     if (MODE == GEMM_D) { klo = max(klo, p.nt_klo[nt]); khi = min(khi, p.nt_khi[nt]); }
     cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * p.ldc * p.n_cols : 0);
+    const bool conj_a = p.conj_a != 0;
 
     double cr[4][2][2], ci[4][2][2];
 #pragma unroll
@@ -245,64 +255,74 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
 #pragma unroll
         for (int b = 0; b < 2; ++b) { cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0; }
 
-    for (int k0 = klo; k0 < khi; k0 += KT) {
-        // ---- stage A tile (64 rows x 32 k), planar, conj folded into the sign of Ai
+    auto fill = [&](int stage, int k0) {
 #pragma unroll
-        for (int e = 0; e < (TM * KT) / 256; ++e) {
+        for (int e = 0; e < (TM * KT) / 256; ++e) {          // A tile: 64 rows x 16 k
             int idx = tid + e * 256, kk = idx & (KT - 1), r = idx / KT;
             int gk = k0 + kk, gm = m0 + r;
-            cplx v = cmake(0.0, 0.0);
-            if (gm < p.M && gk < khi) v = p.At[(int64_t)gk + (int64_t)p.lda * gm];
-            Ar[r][kk] = v.x;
-            Ai[r][kk] = p.conj_a ? -v.y : v.y;
+            bool ok = gm < p.M && gk < khi;
+            cp_async16(&As[stage][r][kk], p.At + (ok ? (int64_t)gk + (int64_t)p.lda * gm : 0), ok);
         }
-        // ---- stage B tile (64 cols x 32 k)
 #pragma unroll
-        for (int e = 0; e < (TN * KT) / 256; ++e) {
+        for (int e = 0; e < (TN * KT) / 256; ++e) {          // B tile: 64 cols x 16 k
             int idx = tid + e * 256, kk = idx & (KT - 1), c = idx / KT;
             int gk = k0 + kk, col = n0 + c;
-            cplx v = cmake(0.0, 0.0);
-            if (col < p.n_cols && gk < khi) {
-                if (MODE == GEMM_PLAIN) {
-                    v = p.bsrc[(int64_t)col * p.ldb + gk];
-                } else if (MODE == GEMM_DEMOD) {
-                    int r_ = col % p.n_rep, q = col / p.n_rep, snr = q % p.n_snr, grp = q / p.n_snr;
-                    cplx a = p.r0[((int64_t)grp * p.n_rep + r_) * p.N + gk];
-                    cplx nz = p.noise[((int64_t)r_ * p.n_snr + snr) * p.N + gk];
-                    double sc = p.noise_scale[snr];
-                    v = cmake(a.x + sc * nz.x, a.y + sc * nz.y);
-                } else {
-                    const cplx* hr = p.h + (int64_t)rep * p.T * p.N;
-                    const cplx* gc = p.G + (int64_t)p.N * col;
-                    for (int t = 0; t < p.T; ++t) {
-                        int d = p.tap_delay[t];
-                        if (gk >= d) cfma(v, hr[(int64_t)t * p.N + gk], gc[gk - d]);
+            bool ok = col < p.n_cols && gk < khi;
+            if (MODE == GEMM_PLAIN) {
+                cp_async16(&Bs[stage][c][kk], p.bsrc + (ok ? (int64_t)col * p.ldb + gk : 0), ok);
+            } else {
+                cplx v = cmake(0.0, 0.0);
+                if (ok) {
+                    if (MODE == GEMM_DEMOD) {
+                        int r_ = col % p.n_rep, q = col / p.n_rep, snr = q % p.n_snr, grp = q / p.n_snr;
+                        cplx a = p.r0[((int64_t)grp * p.n_rep + r_) * p.N + gk];
+                        cplx nz = p.noise[((int64_t)r_ * p.n_snr + snr) * p.N + gk];
+                        double sc = p.noise_scale[snr];
+                        v = cmake(a.x + sc * nz.x, a.y + sc * nz.y);
+                    } else {
+                        const cplx* hr = p.h + (int64_t)rep * p.T * p.N;
+                        const cplx* gc = p.G + (int64_t)p.N * col;
+                        for (int t = 0; t < p.T; ++t) {
+                            int d = p.tap_delay[t];
+                            if (gk >= d) cfma(v, hr[(int64_t)t * p.N + gk], gc[gk - d]);
+                        }
                     }
                 }
+                Bs[stage][c][kk] = v;
             }
-            Br[c][kk] = v.x;
-            Bi[c][kk] = v.y;
         }
+    };
+
+    const int nk = (khi - klo + KT - 1) / KT;
+    if (nk > 0) {
+        fill(0, klo);
+        cp_async_wait_all();
         __syncthreads();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        const int st = kt & 1;
+        if (kt + 1 < nk) fill(st ^ 1, klo + (kt + 1) * KT);
 #pragma unroll
         for (int kk = 0; kk < KT; kk += 4) {
-            double ar[4], ai[4], br[2], bi[2], nbi[2];
+            cplx a[4], b[2];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                ar[a] = Ar[wm * 32 + a * 8 + g][kk + t4];
-                ai[a] = Ai[wm * 32 + a * 8 + g][kk + t4];
+            for (int x = 0; x < 4; ++x) a[x] = As[st][wm * 32 + x * 8 + g][kk + t4];
+#pragma unroll
+            for (int y = 0; y < 2; ++y) b[y] = Bs[st][wn * 16 + y * 8 + g][kk + t4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const double ai = conj_a ? dneg(a[x].y) : a[x].y;
+                const double nai = conj_a ? a[x].y : dneg(a[x].y);
+#pragma unroll
+                for (int y = 0; y < 2; ++y) {
+                    dmma884(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
+                    dmma884(cr[x][y][0], cr[x][y][1], nai, b[y].y);
+                    dmma884(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
+                    dmma884(ci[x][y][0], ci[x][y][1], ai, b[y].x);
+                }
             }
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                br[b] = Br[wn * 16 + b * 8 + g][kk + t4];
-                bi[b] = Bi[wn * 16 + b * 8 + g][kk + t4];
-                nbi[b] = dneg(bi[b]);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) zmma884(cr[a][b], ci[a][b], ar[a], ai[a], br[b], bi[b], nbi[b]);
         }
+        cp_async_wait_all();
         __syncthreads();
     }
     // ---- epilogue: C[g][2*t4 + e] of each 8x8 tile
@@ -372,11 +392,161 @@ __device__ __forceinline__ void ic_col(const IcParams& p, const IcCta& c, int co
     else { int q = c.first + col; scheme = p.wf_scheme[c.scheme_or_wf][q / p.n_snr]; snr = q % p.n_snr; rep = c.snr; }
 }
 
-__global__ void __launch_bounds__(512, 1) k_ic(IcParams p) {
+// ---- phase B, estimated CSI: acc[i, c] = sum_{delta} ( sum_p W[i, i+delta, p] hP[p, c] ) * v[i+delta, c]
+// One warp owns 8 rows (a row tile) at a time and walks its diagonal tiles.  Per tile the P4 pilot
+// quads are DMMA k-steps with the hP fragments as B operand (shared by every tile), followed by an
+// element-wise product with v on the C fragment.  The next tile's W fragments are prefetched into
+// registers while the current one is in the tensor pipe.
+template <int P4T>
+__device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
+                                                 const int* __restrict__ tdel, const cplx* hPs, const cplx* vbuf,
+                                                 cplx* ybuf, const cplx* const* ycolp, int K, int P4rt, int warp,
+                                                 int nwarp, int lane) {
+    constexpr int NC = NC_MAX, HS = NC + 2;
+    constexpr int PQ = P4T > 0 ? P4T : 1;
+    const int P4 = P4T > 0 ? P4T : P4rt;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int RT = (K + 7) / 8;
+    for (int rt = warp; rt < RT; rt += nwarp) {
+        double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
+        const int i = rt * 8 + g;
+        int t = tptr[rt];
+        const int tend = tptr[rt + 1];
+        if (P4T > 0) {
+            cplx nxt[PQ];
+            int nd = 0;
+            if (t < tend) {
+#pragma unroll
+                for (int pq = 0; pq < PQ; ++pq) nxt[pq] = __ldg(frag + ((int64_t)t * PQ + pq) * 32 + lane);
+                nd = tdel[t];
+            }
+            for (; t < tend; ++t) {
+                cplx cur[PQ];
+#pragma unroll
+                for (int pq = 0; pq < PQ; ++pq) cur[pq] = nxt[pq];
+                int j = i + nd;
+                if (t + 1 < tend) {
+#pragma unroll
+                    for (int pq = 0; pq < PQ; ++pq) nxt[pq] = __ldg(frag + ((int64_t)(t + 1) * PQ + pq) * 32 + lane);
+                    nd = tdel[t + 1];
+                }
+                j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
+                cplx v[2][2];
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) v[ct][e] = vbuf[j * NC + ct * 8 + 2 * t4 + e];
+                double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+                for (int pq = 0; pq < PQ; ++pq) {
+                    const double nai = dneg(cur[pq].y);
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct) {
+                        cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+                        dmma884(tr[ct][0], tr[ct][1], cur[pq].x, b.x);
+                        dmma884(tr[ct][0], tr[ct][1], nai, b.y);
+                        dmma884(ti[ct][0], ti[ct][1], cur[pq].x, b.y);
+                        dmma884(ti[ct][0], ti[ct][1], cur[pq].y, b.x);
+                    }
+                }
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        accr[ct][e] = fma(tr[ct][e], v[ct][e].x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v[ct][e].y, accr[ct][e]);
+                        acci[ct][e] = fma(tr[ct][e], v[ct][e].y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v[ct][e].x, acci[ct][e]);
+                    }
+            }
+        } else {
+            for (; t < tend; ++t) {
+                double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
+                const cplx* fr = frag + (int64_t)t * P4 * 32 + lane;
+                for (int pq = 0; pq < P4; ++pq) {
+                    cplx a = __ldg(fr + pq * 32);
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct) {
+                        cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+                        zmma884(tr[ct], ti[ct], a.x, a.y, b.x, b.y, dneg(b.y));
+                    }
+                }
+                int j = i + tdel[t];
+                j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        cplx v = vbuf[j * NC + ct * 8 + 2 * t4 + e];
+                        accr[ct][e] = fma(tr[ct][e], v.x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v.y, accr[ct][e]);
+                        acci[ct][e] = fma(tr[ct][e], v.y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v.x, acci[ct][e]);
+                    }
+            }
+        }
+        if (i < K) {
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int c = ct * 8 + 2 * t4 + e;
+                    const cplx* yp = ycolp[c];
+                    cplx yv = yp ? yp[i] : cmake(0.0, 0.0);
+                    ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
+                }
+        }
+    }
+}
+
+// ---- phase B, perfect CSI: acc[i, c] = sum_{j != i} D[i, j] v[j, c]   (DS.m:541-543)
+// A fragments come straight from the column-major D of this realization (8 rows x 4 columns per
+// DMMA k-step); four k-steps are loaded ahead of their use.
+__device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
+                                                  const cplx* const* ycolp, int K, int warp, int nwarp, int lane) {
+    constexpr int NC = NC_MAX, U = 4;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int RT = (K + 7) / 8;
+    for (int rt = warp; rt < RT; rt += nwarp) {
+        double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
+        const int i = rt * 8 + g;
+        const bool row_ok = i < K;
+        for (int j0 = 0; j0 < K; j0 += 4 * U) {
+            cplx a[U], b[U][2];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                int j = j0 + 4 * u + t4;
+                a[u] = (row_ok && j < K && i != j) ? __ldg(Dm + (int64_t)j * K + i) : cmake(0.0, 0.0);
+                int jj = j < K ? j : K - 1;
+                b[u][0] = vbuf[jj * NC + g];
+                b[u][1] = vbuf[jj * NC + 8 + g];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double nai = dneg(a[u].y);
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) {
+                    dmma884(accr[ct][0], accr[ct][1], a[u].x, b[u][ct].x);
+                    dmma884(accr[ct][0], accr[ct][1], nai, b[u][ct].y);
+                    dmma884(acci[ct][0], acci[ct][1], a[u].x, b[u][ct].y);
+                    dmma884(acci[ct][0], acci[ct][1], a[u].y, b[u][ct].x);
+                }
+            }
+        }
+        if (row_ok) {
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int c = ct * 8 + 2 * t4 + e;
+                    const cplx* yp = ycolp[c];
+                    cplx yv = yp ? yp[i] : cmake(0.0, 0.0);
+                    ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
     constexpr int NC = NC_MAX;
     const IcCta cta = p.ctas[blockIdx.x];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    const int g = lane >> 2, t4 = lane & 3;
     const int csi = cta.mode;
     const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
     const int K = p.sch[p.wf_scheme[wf][0]].K;
@@ -388,10 +558,13 @@ __global__ void __launch_bounds__(512, 1) k_ic(IcParams p) {
     __shared__ cplx hPn[64 * HS];          // new pilot estimates
     __shared__ unsigned int cnt[NC][2];
     __shared__ int c_scheme[NC], c_snr[NC], c_rep[NC];
+    __shared__ const cplx* ycolp[NC];      // y of each column (null for padding columns)
     if (tid < NC) {
         int s_ = 0, n_ = 0, r_ = 0;
         if (tid < cta.n_cols) ic_col(p, cta, tid, s_, n_, r_);
-        c_scheme[tid] = s_; c_snr[tid] = n_; c_rep[tid] = (tid < cta.n_cols && r_ < p.n_rep) ? r_ : -1;
+        const bool ok = tid < cta.n_cols && r_ < p.n_rep;
+        c_scheme[tid] = s_; c_snr[tid] = n_; c_rep[tid] = ok ? r_ : -1;
+        ycolp[tid] = ok ? p.sch[s_].y + ((int64_t)n_ * p.n_rep + r_) * p.sch[s_].K : nullptr;
         cnt[tid][0] = cnt[tid][1] = 0;
     }
     __syncthreads();
@@ -435,92 +608,30 @@ __global__ void __launch_bounds__(512, 1) k_ic(IcParams p) {
         }
         __syncthreads();
         // ---------------- phase B: interference on FP64 tensor cores
-        const int RT = (K + 7) / 8;
         if (csi == 0) {
             const SchemeDev& sd = p.sch[cta.scheme_or_wf];
             // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
             const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
-            const WTiles wt = sd.w[var_prev][cta.snr];
-            const int* tptr = sd.tile_ptr[var_prev];
-            const int* tdel = sd.tile_delta[var_prev];
-            const int P4 = sd.P4;
-            for (int rt = warp; rt < RT; rt += nwarp) {
-                double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
-                const int i = rt * 8 + g;
-                for (int t = tptr[rt]; t < tptr[rt + 1]; ++t) {
-                    double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
-                    const cplx* fr = wt.frag + (int64_t)t * P4 * 32 + lane;
-                    for (int pq = 0; pq < P4; ++pq) {
-                        cplx a = __ldg(fr + pq * 32);
-#pragma unroll
-                        for (int ct = 0; ct < 2; ++ct) {
-                            cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
-                            zmma884(tr[ct], ti[ct], a.x, a.y, b.x, b.y, dneg(b.y));
-                        }
-                    }
-                    int j = i + tdel[t];
-                    j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
-#pragma unroll
-                    for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            cplx v = vbuf[j * NC + ct * 8 + 2 * t4 + e];
-                            accr[ct][e] = fma(tr[ct][e], v.x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v.y, accr[ct][e]);
-                            acci[ct][e] = fma(tr[ct][e], v.y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v.x, acci[ct][e]);
-                        }
-                }
-                if (i < K) {
-#pragma unroll
-                    for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            int c = ct * 8 + 2 * t4 + e;
-                            cplx yv = cmake(0.0, 0.0);
-                            if (c_rep[c] >= 0) yv = sd.y[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i];
-                            ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
-                        }
-                }
-            }
+            if (sd.P4 == 4)
+                est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, vbuf,
+                                    ybuf, ycolp, K, 4, warp, nwarp, lane);
+            else if (sd.P4 == 8)
+                est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, vbuf,
+                                    ybuf, ycolp, K, 8, warp, nwarp, lane);
+            else
+                est_interference<0>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, vbuf,
+                                    ybuf, ycolp, K, sd.P4, warp, nwarp, lane);
         } else {
             const cplx* Dm = p.D[wf] + (int64_t)cta.snr * K * K;     // cta.snr holds the realization
-            for (int rt = warp; rt < RT; rt += nwarp) {
-                double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
-                const int i = rt * 8 + g;
-                for (int j0 = 0; j0 < K; j0 += 4) {
-                    int j = j0 + t4;
-                    cplx a = cmake(0.0, 0.0);
-                    if (i < K && j < K && i != j) a = __ldg(Dm + (int64_t)j * K + i);
-                    int jj = j < K ? j : K - 1;
-#pragma unroll
-                    for (int ct = 0; ct < 2; ++ct) {
-                        cplx b = vbuf[jj * NC + ct * 8 + g];
-                        zmma884(accr[ct], acci[ct], a.x, a.y, b.x, b.y, dneg(b.y));
-                    }
-                }
-                if (i < K) {
-#pragma unroll
-                    for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            int c = ct * 8 + 2 * t4 + e;
-                            cplx yv = cmake(0.0, 0.0);
-                            if (c_rep[c] >= 0) {
-                                const SchemeDev& sc = p.sch[c_scheme[c]];
-                                yv = sc.y[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i];
-                            }
-                            ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
-                        }
-                }
-            }
+            perf_interference(Dm, vbuf, ybuf, ycolp, K, warp, nwarp, lane);
         }
         __syncthreads();
     } else {
         // one-tap stage: y itself is equalised
         for (int idx = tid; idx < K * NC; idx += nthr) {
             int c = idx % NC, i = idx / NC;
-            cplx yv = cmake(1.0, 0.0);
-            if (c_rep[c] >= 0) yv = p.sch[c_scheme[c]].y[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i];
-            ybuf[idx] = yv;
+            const cplx* yp = ycolp[c];
+            ybuf[idx] = yp ? yp[i] : cmake(1.0, 0.0);
         }
         __syncthreads();
     }
@@ -618,6 +729,29 @@ __global__ void k_peak_dmma(double* out, int iters) {
     double s = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+// DMMA and DFMA interleaved: do the two FP64 pipes add up?
+__global__ void k_peak_mix(double* out, int iters) {
+    double c[4][2], f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = threadIdx.x * 1e-9 + i;
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dmma884(c[i][0], c[i][1], a, b);
+            f[2 * i] = fma(f[2 * i], a, b);
+            f[2 * i + 1] = fma(f[2 * i + 1], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
     if (s == 12345.678) out[0] = s;
 }
 __global__ void k_peak_dfma(double* out, int iters) {

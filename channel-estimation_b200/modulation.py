@@ -7,9 +7,16 @@ reference obtains them by calling its IFFT modulator once per subcarrier, FBMC.m
 (FBMC.m:319-320,344-345; OFDM.m:185-186,206-207) through the C ABI.
 `Modulation.SignalConstellation`: tables of SC.m:24-74; the nearest-neighbour demapping used on
 the hot path lives in the CUDA library (kernels.cuh, demap_word)."""
+import sys
+
 import numpy as np
 
 from .context import DeviceContext
+
+
+def _disp(msg):
+    """The reference disp()s a note when it adjusts an inconsistent parameter; keep stdout clean."""
+    print(msg, file=sys.stderr)
 
 
 def _round_half_away(x):
@@ -166,11 +173,11 @@ class FBMC(_Modem):
         fs = PHY["SamplingRate"]
         if (fs / (2 * PHY["SubcarrierSpacing"])) % 1 != 0:                                  # FBMC.m:65-69
             PHY["SubcarrierSpacing"] = fs / (2 * _round_half_away(fs / (2 * PHY["SubcarrierSpacing"])))
-            print("Sampling Rate divided by (Subcarrier spacing times 2) must be must be an integer!")
+            _disp("Sampling Rate divided by (Subcarrier spacing times 2) must be must be an integer!")
         F = PHY["SubcarrierSpacing"]
         if (PHY["IntermediateFrequency"] / F) % 1 != 0:                                     # FBMC.m:71-75
             PHY["IntermediateFrequency"] = _round_half_away(PHY["IntermediateFrequency"] / F) * F
-            print("The intermediate frequency must be a multiple of the subcarrier spacing!")
+            _disp("The intermediate frequency must be a multiple of the subcarrier spacing!")
         if fs < Nr["Subcarriers"] * F:                                                      # FBMC.m:77-79
             raise ValueError("Sampling Rate must be higher: at least Number of Subcarriers times Subcarrier Spacing")
         PHY["dt"] = 1.0 / fs
@@ -263,7 +270,7 @@ class OFDM(_Modem):
         fs = PHY["SamplingRate"]
         if (round(fs / PHY["SubcarrierSpacing"] * 1e5) / 1e5) % 1 != 0:                      # OFDM.m:57-61
             PHY["SubcarrierSpacing"] = fs / _round_half_away(fs / PHY["SubcarrierSpacing"])
-            print("Sampling rate must be a multiple of the subcarrier spacing!")
+            _disp("Sampling rate must be a multiple of the subcarrier spacing!")
         F = PHY["SubcarrierSpacing"]
         if (round(PHY["IntermediateFrequency"] / F * 1e5) / 1e5) % 1 != 0:                   # OFDM.m:63-67
             PHY["IntermediateFrequency"] = _round_half_away(PHY["IntermediateFrequency"] / F) * F
@@ -272,7 +279,7 @@ class OFDM(_Modem):
                              "of subcarriers times subcarrier spacing")
         if abs((round(PHY["CyclicPrefixLength"] * fs * 1e5) / 1e5) % 1) != 0:                # OFDM.m:73-77
             PHY["CyclicPrefixLength"] = _round_half_away(PHY["CyclicPrefixLength"] * fs) / fs
-            print("The length of the cyclic prefix times the sampling rate must be an integer!")
+            _disp("The length of the cyclic prefix times the sampling rate must be an integer!")
         Imp["CyclicPrefix"] = _round_half_away(PHY["CyclicPrefixLength"] * fs)
         Imp["ZeroGuardSamples"] = _round_half_away(PHY["ZeroGuardTimeLength"] * fs)
         Imp["FFTSize"] = _round_half_away(fs / F)
