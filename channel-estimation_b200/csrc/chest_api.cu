@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -55,7 +56,7 @@ struct Waveform {
     std::vector<int> g_lo, g_hi, q_lo, q_hi;
     int nsch = 0; int sch[2] = {0, 0};
     // batch state
-    DevBuf<cplx> x, s, r0, y, D, htrue;
+    DevBuf<cplx> x, s, r0, y, D, htrue, HG;
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
 };
 struct Constellation {
@@ -116,6 +117,8 @@ struct Ctx {
     cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     DevBuf<double> probe;
+    DevBuf<unsigned int> queue; int ic_grid = 0; size_t ic_smem = 0;
+    DevBuf<unsigned long long> trace;
 };
 
 Ctx* from(uint64_t h) { return reinterpret_cast<Ctx*>(static_cast<uintptr_t>(h)); }
@@ -204,8 +207,13 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     GemmParams p{};
     p.M = w.K; p.Kc = c->N; p.n_cols = w.K; p.lda = c->N; p.ldc = w.K; p.conj_a = 1;
     p.At = w.Q.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.D.p;
-    p.h = c->h.p; p.G = w.G.p; p.tap_delay = c->d_tap_delay.p; p.T = c->T; p.N = c->N;
+    p.bsrc = w.HG.p; p.ldb = c->N; p.N = c->N;
     p.nt_klo = w.hg_klo.p; p.nt_khi = w.hg_khi.p; p.hdiag = w.htrue.p; p.rep0 = rep0;
+    dim3 ghg(2, w.K, n_rep);
+    k_apply_hg<<<ghg, 128, 0, c->stream>>>(w.HG.p, w.G.p, c->h.p, c->d_tap_delay.p, w.hg_klo.p, w.hg_khi.p,
+                                           c->N, w.K, c->T, rep0);
+    c->launches++;
+    CK(cudaGetLastError());
     CK(launch_gemm<GEMM_D>(c, p, n_rep));
     return CHEST_OK;
 }
@@ -225,7 +233,29 @@ int build_ctas(Ctx* c, int n_rep) {
         for (int b = 0; b < n_rep; ++b)
             for (int q0 = 0; q0 < tot; q0 += NC_MAX) v.push_back({1, wfi, b, q0, std::min(NC_MAX, tot - q0)});
     };
-    est(CHEST_SCHEME_AUX); est(CHEST_SCHEME_COD); perf(CHEST_WF_FBMC); est(CHEST_SCHEME_OFDM); perf(CHEST_WF_OFDM);
+    // heavy work first; compute-bound EST CTAs and memory-heavy PERF CTAs are interleaved so that both the
+    // FP64 tensor pipe and HBM stay busy
+    std::vector<IcCta> e1, p1, e2, p2;
+    est(CHEST_SCHEME_AUX); est(CHEST_SCHEME_COD); e1.swap(v);
+    perf(CHEST_WF_FBMC); p1.swap(v);
+    est(CHEST_SCHEME_OFDM); e2.swap(v);
+    perf(CHEST_WF_OFDM); p2.swap(v);
+    auto weave = [&](std::vector<IcCta>& a, std::vector<IcCta>& b) {
+        size_t ia = 0, ib = 0;
+        while (ia < a.size() || ib < b.size()) {
+            // keep the ratio a:b constant along the list
+            if (ib >= b.size() || (ia < a.size() && ia * b.size() <= ib * a.size())) v.push_back(a[ia++]);
+            else v.push_back(b[ib++]);
+        }
+    };
+    if (const char* dbg = getenv("CHEST_DEBUG_ONLY")) {      // development knob: time one CTA class alone
+        if (!strcmp(dbg, "est")) { p1.clear(); p2.clear(); }
+        if (!strcmp(dbg, "perf")) { e1.clear(); e2.clear(); }
+        if (!strcmp(dbg, "est_fbmc")) { p1.clear(); p2.clear(); e2.clear(); }
+        if (!strcmp(dbg, "perf_fbmc")) { e1.clear(); e2.clear(); p2.clear(); }
+    }
+    weave(e1, p1);
+    weave(e2, p2);
     c->n_ctas = (int)v.size();
     CK(c->ctas.upload(v, c->stream));
     CK(c->scratch.alloc((size_t)c->n_ctas * 3 * c->K_max * NC_MAX));
@@ -329,20 +359,46 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         ip.D[wfi] = c->wf[wfi].D.p; ip.htrue[wfi] = c->wf[wfi].htrue.p;
     }
     ip.scratch = c->scratch.p;
+    ip.pilot_rows = 4;
+    for (int si = 0; si < 3; ++si) if (c->sch[si].set) ip.pilot_rows = std::max(ip.pilot_rows, 4 * ((c->sch[si].P + 3) / 4));
+    size_t cst_smem = 0;                                           // shared-memory copies of the constellation tables
+    for (int k = 0; k < 2; ++k)
+        cst_smem += sizeof(cplx) * ((size_t)c->cst[k].order + (c->cst[k].n_axis + 1) / 2 + (c->cst[k].order + 3) / 4);
+    const int ic_threads = 256;
+    const size_t ic_smem = (size_t)2 * ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx) + (size_t)(ic_threads / 32) * IC_RING_BYTES
+                           + (size_t)2 * PERF_CHUNK * (NC_MAX + 2) * sizeof(cplx) + cst_smem;
+    if (c->ic_grid == 0 || c->ic_smem != ic_smem) {                // persistent grid: every CTA resident (cooperative launch)
+        CK(cudaFuncSetAttribute(k_ic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ic, ic_threads, ic_smem));
+        if (per_sm < 1) return fail(CHEST_ERR_STATE, "k_ic does not fit on an SM (too many pilots for the shared tables)");
+        c->ic_grid = per_sm * c->n_sm; c->ic_smem = ic_smem;
+    }
+    CK(c->queue.alloc(32));
+    CK(cudaMemsetAsync(c->queue.p, 0, 32 * sizeof(unsigned int), st));
+    ip.queue = c->queue.p; ip.n_units = c->n_ctas;
     size_t n_err = (size_t)n_rep * S * (n_iter + 1) * 12;
     uint32_t* err = err_dev ? err_dev : c->err.p;
     CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
     ip.err = err;
+    const char* trace_path = getenv("CHEST_IC_TRACE");             // development: per-CTA stage timestamps of the last iteration
+    if (trace_path) CK(c->trace.alloc((size_t)c->ic_grid * 8));
     for (int it = 0; it <= n_iter; ++it) {
         ip.it = it;
-        k_ic<<<c->n_ctas, 256, 0, st>>>(ip);
+        ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
+        void* args[] = {&ip};
+        CK(cudaLaunchCooperativeKernel((const void*)k_ic, dim3(std::min(c->ic_grid, std::max(c->n_ctas, 1))), dim3(ic_threads), args, ic_smem, st));
         c->launches++;
-        CK(cudaGetLastError());
         if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev[5], st));
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[6], st));
     if (err_host) CK(cudaMemcpyAsync(err_host, err, n_err * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (trace_path) {
+        std::vector<unsigned long long> th((size_t)c->ic_grid * 8);
+        CK(cudaMemcpy(th.data(), c->trace.p, th.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(th.data(), 8, th.size(), f); fclose(f); }
+    }
     if (c->profiling) {
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&c->stage_ms[6], c->ev[0], c->ev[6]);
@@ -393,7 +449,7 @@ int chest_destroy(uint64_t handle) {
     auto relw = [](Waveform& w) {
         w.G.release(); w.Q.release(); w.Gt.release(); w.q_klo.release(); w.q_khi.release(); w.gt_klo.release();
         w.gt_khi.release(); w.hg_klo.release(); w.hg_khi.release(); w.x.release(); w.s.release(); w.r0.release();
-        w.y.release(); w.D.release(); w.htrue.release();
+        w.y.release(); w.D.release(); w.htrue.release(); w.HG.release();
     };
     relw(c->wf[0]); relw(c->wf[1]);
     for (auto& k : c->cst) { k.symbol.release(); k.pilot.release(); k.level.release(); k.word_of_grid.release(); }
@@ -409,7 +465,7 @@ int chest_destroy(uint64_t handle) {
     }
     c->d_tap_delay.release(); c->d_tap_amp.release(); c->d_noise_scale.release(); c->doppler_u.release();
     c->phase_u.release(); c->noise.release(); c->h.release(); c->pilot_idx[0].release(); c->pilot_idx[1].release();
-    c->err.release(); c->scratch.release(); c->tmp_a.release(); c->tmp_b.release(); c->ctas.release(); c->probe.release();
+    c->err.release(); c->scratch.release(); c->tmp_a.release(); c->tmp_b.release(); c->ctas.release(); c->probe.release(); c->queue.release();
     for (auto& e : c->ev) cudaEventDestroy(e);
     for (auto& e : c->user_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -532,7 +588,7 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
     ARG(c && si >= 0 && si < 3 && (wfi == 0 || wfi == 1) && jc && ir && val && pilot_pos && considered);
     ARG(c->wf[wfi].set && c->cst[constellation & 1].set);
     ARG(detect >= 0 && detect <= 2 && (detect == CHEST_DETECT_DESPREAD_REAL || data_pos));
-    ARG(P > 0 && P <= 64 && n_data > 0 && k_in >= P + n_data && kappa > 0 && dpr > 0);
+    ARG(P > 0 && P <= 128 && n_data > 0 && k_in >= P + n_data && kappa > 0 && dpr > 0);
     CK(cudaSetDevice(c->device));
     Scheme& s = c->sch[si];
     const int K = c->wf[wfi].K;
@@ -703,7 +759,8 @@ int chest_finalize(uint64_t handle, int max_batch) {
         c->K_max = std::max(c->K_max, w.K);
         int ns = std::max(w.nsch, 1);
         CK(w.x.alloc((size_t)ns * B * w.K)); CK(w.s.alloc((size_t)ns * B * N)); CK(w.r0.alloc((size_t)ns * B * N));
-        CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.D.alloc((size_t)B * w.K * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
+        CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.D.alloc((size_t)B * (((w.K + 7) / 8) * 8) * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
+        CK(w.HG.alloc((size_t)B * w.K * N));
         if (w.nsch) CK(c->pilot_idx[wfi].alloc((size_t)B * c->sch[w.sch[0]].P));
     }
     CK(c->doppler_u.alloc((size_t)B * c->T * c->paths)); CK(c->phase_u.alloc((size_t)B * c->T * c->paths));
@@ -826,9 +883,14 @@ int chest_transmission_matrix(uint64_t handle, int b, int wfi, double* D_out, do
     CK(cudaSetDevice(c->device));
     Waveform& w = c->wf[wfi];
     rc = stage_transmission_matrix(c, wfi, 1, b); if (rc) return rc;
-    CK(cudaMemcpyAsync(D_out, w.D.p + (size_t)b * w.K * w.K, sizeof(cplx) * (size_t)w.K * w.K, cudaMemcpyDeviceToHost, c->stream));
+    const size_t K = w.K, RT8 = ((K + 7) / 8) * 8;
+    std::vector<cplx> tiled(RT8 * K);
+    CK(cudaMemcpyAsync(tiled.data(), w.D.p + (size_t)b * RT8 * K, sizeof(cplx) * RT8 * K, cudaMemcpyDeviceToHost, c->stream));
     if (h_out) CK(cudaMemcpyAsync(h_out, w.htrue.p + (size_t)b * w.K, sizeof(cplx) * w.K, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    cplx* Dh = reinterpret_cast<cplx*>(D_out);                  // device layout [rt][col][8 rows] -> column-major K x K
+    for (size_t j = 0; j < K; ++j)
+        for (size_t i = 0; i < K; ++i) Dh[i + K * j] = tiled[((i >> 3) * K + j) * 8 + (i & 7)];
     return CHEST_OK;
 }
 

@@ -4,6 +4,7 @@
 //   K3  k_gemm<GEMM_DEMOD>, k_estimate   demodulation GEMM over realizations, explicit D-hat
 //   K4  k_ic                       one launch per interference-cancellation iteration
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 #define NC_MAX 16          // columns (realizations x SNR points) one IC CTA carries
@@ -117,6 +118,27 @@ __global__ void k_apply_h(cplx* __restrict__ r, const cplx* __restrict__ s, cons
     r[(int64_t)col * N + n] = acc;
 }
 
+// HG[rep][j][n] = sum_tap h[rep][tap][n] * G[n - delay_tap, j] for n inside the k-range of j's 64-column
+// tile (zero elsewhere in that range because G is zero outside its support).  K2 then reads H*G as a
+// plain k-contiguous operand with cp.async.
+__global__ void k_apply_hg(cplx* __restrict__ HG, const cplx* __restrict__ G, const cplx* __restrict__ h,
+                           const int* __restrict__ tap_delay, const int* __restrict__ nt_klo,
+                           const int* __restrict__ nt_khi, int N, int K, int T, int rep0) {
+    const int j = blockIdx.y, rep = blockIdx.z + rep0;
+    const int lo = nt_klo[j >> 6], hi = nt_khi[j >> 6];
+    const cplx* gc = G + (int64_t)N * j;
+    const cplx* hr = h + (int64_t)rep * T * N;
+    cplx* out = HG + ((int64_t)rep * K + j) * N;
+    for (int n = lo + blockIdx.x * blockDim.x + threadIdx.x; n < hi; n += gridDim.x * blockDim.x) {
+        cplx acc = cmake(0.0, 0.0);
+        for (int t = 0; t < T; ++t) {
+            int d = tap_delay[t];
+            if (n >= d) cfma(acc, hr[(int64_t)t * N + n], gc[n - d]);
+        }
+        out[n] = acc;
+    }
+}
+
 // ============================================================================ constellations
 struct ConstDev {
     int order, nbits, n_axis;           // n_axis = order (PAM) or sqrt(order) (QAM)
@@ -128,9 +150,11 @@ struct ConstDev {
 };
 
 // nearest axis level, decided by the same |x - level| comparison the reference's argmin uses
-__device__ __forceinline__ int nearest_level(const double* __restrict__ lev, int n, double x) {
-    double step = lev[1] - lev[0];
-    int t = (int)floor((x - lev[0]) / step + 0.5);
+__device__ __forceinline__ int nearest_level(const double* lev, int n, double x) {
+    // first guess from the uniform grid (reciprocal multiply: the guess only has to be within one level,
+    // the decision itself is made by the |x - level| comparisons below)
+    double inv_step = (double)(n - 1) / (lev[n - 1] - lev[0]);
+    int t = (int)floor((x - lev[0]) * inv_step + 0.5);
     t = t < 0 ? 0 : (t > n - 1 ? n - 1 : t);
     double best = fabs(x - lev[t]);
     if (t > 0 && fabs(x - lev[t - 1]) < best) { best = fabs(x - lev[t - 1]); t = t - 1; }
@@ -214,8 +238,9 @@ struct GemmParams {
     const cplx* bsrc; int ldb;
     // DEMOD: col = (g*n_snr + snr)*n_rep + rep ; B = r0[(g*n_rep+rep)*N + k] + sqrt(pn[snr]/2)*noise[(rep*n_snr+snr)*N + k]
     const cplx* r0; const cplx* noise; const double* noise_scale; int n_snr, n_rep;
-    // D: per realization (blockIdx.z): B[k=n, col=j] = sum_t h[rep][t][n] G[n-d_t + N*j]; out += rep*ldc*n_cols
-    const cplx* h; const cplx* G; const int* tap_delay; int T, N;
+    // D: per realization (blockIdx.z): B[k=n, col=j] = HG[rep][j][n] (k_apply_hg) = bsrc[(rep*n_cols+col)*ldb + k];
+    // out += rep*ldc*n_cols
+    int N;
     const int* nt_klo; const int* nt_khi;      // per 64-col tile k support range of H*G
     cplx* hdiag;                                // [rep][K] diagonal of D (may be null)
     int rep0;
@@ -246,7 +271,10 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
     const int rep = (MODE == GEMM_D) ? (int)blockIdx.z + p.rep0 : 0;
     int klo = p.mt_klo ? p.mt_klo[mt] : 0, khi = p.mt_khi ? p.mt_khi[mt] : p.Kc;
     if (MODE == GEMM_D) { klo = max(klo, p.nt_klo[nt]); khi = min(khi, p.nt_khi[nt]); }
-    cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * p.ldc * p.n_cols : 0);
+    // GEMM_D writes D row-tile-major: D[rep][rt = m/8][col][m%8], so that the perfect-CSI interference pass
+    // streams the 8 rows of a DMMA row tile as one contiguous block (K*128 bytes)
+    const int RT8 = ((p.M + 7) / 8) * 8;
+    cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * RT8 * p.n_cols : 0);
     const bool conj_a = p.conj_a != 0;
 
     double cr[4][2][2], ci[4][2][2];
@@ -270,23 +298,16 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
             bool ok = col < p.n_cols && gk < khi;
             if (MODE == GEMM_PLAIN) {
                 cp_async16(&Bs[stage][c][kk], p.bsrc + (ok ? (int64_t)col * p.ldb + gk : 0), ok);
+            } else if (MODE == GEMM_D) {
+                cp_async16(&Bs[stage][c][kk], p.bsrc + (ok ? ((int64_t)rep * p.n_cols + col) * p.ldb + gk : 0), ok);
             } else {
                 cplx v = cmake(0.0, 0.0);
                 if (ok) {
-                    if (MODE == GEMM_DEMOD) {
-                        int r_ = col % p.n_rep, q = col / p.n_rep, snr = q % p.n_snr, grp = q / p.n_snr;
-                        cplx a = p.r0[((int64_t)grp * p.n_rep + r_) * p.N + gk];
-                        cplx nz = p.noise[((int64_t)r_ * p.n_snr + snr) * p.N + gk];
-                        double sc = p.noise_scale[snr];
-                        v = cmake(a.x + sc * nz.x, a.y + sc * nz.y);
-                    } else {
-                        const cplx* hr = p.h + (int64_t)rep * p.T * p.N;
-                        const cplx* gc = p.G + (int64_t)p.N * col;
-                        for (int t = 0; t < p.T; ++t) {
-                            int d = p.tap_delay[t];
-                            if (gk >= d) cfma(v, hr[(int64_t)t * p.N + gk], gc[gk - d]);
-                        }
-                    }
+                    int r_ = col % p.n_rep, q = col / p.n_rep, snr = q % p.n_snr, grp = q / p.n_snr;
+                    cplx a = p.r0[((int64_t)grp * p.n_rep + r_) * p.N + gk];
+                    cplx nz = p.noise[((int64_t)r_ * p.n_snr + snr) * p.N + gk];
+                    double sc = p.noise_scale[snr];
+                    v = cmake(a.x + sc * nz.x, a.y + sc * nz.y);
                 }
                 Bs[stage][c][kk] = v;
             }
@@ -335,8 +356,12 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
                 int m = m0 + wm * 32 + a * 8 + g, col = n0 + wn * 16 + b * 8 + 2 * t4 + e;
                 if (m < p.M && col < p.n_cols) {
                     cplx v = cmake(cr[a][b][e], ci[a][b][e]);
-                    out[(int64_t)col * p.ldc + m] = v;
-                    if (MODE == GEMM_D && p.hdiag && m == col) p.hdiag[(int64_t)rep * p.M + m] = v;
+                    if (MODE == GEMM_D) {
+                        out[((int64_t)(m >> 3) * p.n_cols + col) * 8 + (m & 7)] = v;
+                        if (p.hdiag && m == col) p.hdiag[(int64_t)rep * p.M + m] = v;
+                    } else {
+                        out[(int64_t)col * p.ldc + m] = v;
+                    }
                 }
             }
 }
@@ -376,7 +401,7 @@ __global__ void k_estimate(cplx* __restrict__ Dhat, cplx* __restrict__ hdiag, WT
 //         C new pilot estimates ; D one-tap channel + equalise ; E de-spread / select, demap, count.
 struct IcCta { int mode, scheme_or_wf, snr, first, n_cols; };   // mode 0 EST, 1 PERF
 struct IcParams {
-    int it, n_iter, n_rep, n_snr, K_max;
+    int it, n_iter, n_rep, n_snr, K_max, pilot_rows;      // pilot_rows: rows of the shared pilot tables (4 * max P4)
     const IcCta* ctas;
     SchemeDev sch[3];
     ConstDev cst[2];
@@ -385,6 +410,9 @@ struct IcParams {
     const cplx* htrue[2];      // [rep][K]
     cplx* scratch;             // per CTA: 3 buffers of K_max*NC_MAX
     uint32_t* err;             // [rep][snr][it][scheme][csi][edge]
+    unsigned int* queue;       // [n_iter+1] unit counters of the main stage (zeroed per batch)
+    int n_units;
+    unsigned long long* trace; // development: per CTA {smid, t0, t_pre, t_main_own, t_main_all, t_end, B busy ns, units}
 };
 
 __device__ __forceinline__ void ic_col(const IcParams& p, const IcCta& c, int col, int& scheme, int& snr, int& rep) {
@@ -392,94 +420,134 @@ __device__ __forceinline__ void ic_col(const IcParams& p, const IcCta& c, int co
     else { int q = c.first + col; scheme = p.wf_scheme[c.scheme_or_wf][q / p.n_snr]; snr = q % p.n_snr; rep = c.snr; }
 }
 
+#define IC_RING_BYTES 8192      // per-warp cp.async ring (fragment stream staging)
+#define IC_PILOT_MAX 64         // pilots per scheme supported by the shared pilot tables
+
+__device__ __forceinline__ void cp_async16_plain(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
 // ---- phase B, estimated CSI: acc[i, c] = sum_{delta} ( sum_p W[i, i+delta, p] hP[p, c] ) * v[i+delta, c]
 // One warp owns 8 rows (a row tile) at a time and walks its diagonal tiles.  Per tile the P4 pilot
 // quads are DMMA k-steps with the hP fragments as B operand (shared by every tile), followed by an
-// element-wise product with v on the C fragment.  The next tile's W fragments are prefetched into
-// registers while the current one is in the tensor pipe.
+// element-wise product with v on the C fragment.  The W fragment stream of a row tile is contiguous;
+// every lane copies its own 16-byte fragment elements with cp.async into a private slot of the warp's
+// shared-memory ring, ST tiles ahead of their use (no barrier: a lane only reads what it copied).
 template <int P4T>
 __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
                                                  const int* __restrict__ tdel, const cplx* hPs, const cplx* vbuf,
-                                                 cplx* ybuf, const cplx* const* ycolp, int K, int P4rt, int warp,
+                                                 cplx* ybuf, const cplx* const* ycolp, cplx* ring, int K, int warp,
                                                  int nwarp, int lane) {
     constexpr int NC = NC_MAX, HS = NC + 2;
-    constexpr int PQ = P4T > 0 ? P4T : 1;
-    const int P4 = P4T > 0 ? P4T : P4rt;
+    constexpr int ST = IC_RING_BYTES / (P4T * 512);          // tiles in flight
+    const int g = lane >> 2, t4 = lane & 3;
+    const int RT = (K + 7) / 8;
+    cplx* slot = ring + lane;                                  // [stage][pq][32 lanes]
+    for (int rt = warp; rt < RT; rt += nwarp) {
+        double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
+        const int i = rt * 8 + g;
+        const int t0 = tptr[rt], tend = tptr[rt + 1];
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+            if (t0 + s < tend) {
+#pragma unroll
+                for (int pq = 0; pq < P4T; ++pq)
+                    cp_async16_plain(slot + (s * P4T + pq) * 32, frag + ((int64_t)(t0 + s) * P4T + pq) * 32 + lane);
+            }
+            cp_async_commit();
+        }
+        int nd = t0 < tend ? tdel[t0] : 0;
+        for (int t = t0; t < tend; ++t) {
+            const int s = (t - t0) % ST;
+            int j = i + nd;
+            if (t + 1 < tend) nd = tdel[t + 1];
+            j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
+            cplx v[2][2];
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) v[ct][e] = vbuf[j * NC + ct * 8 + 2 * t4 + e];
+            cp_async_wait_group<ST - 1>();
+            double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+            for (int pq = 0; pq < P4T; ++pq) {
+                const cplx a = slot[(s * P4T + pq) * 32];
+                const double nai = dneg(a.y);
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) {
+                    cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+                    dmma884(tr[ct][0], tr[ct][1], a.x, b.x);
+                    dmma884(tr[ct][0], tr[ct][1], nai, b.y);
+                    dmma884(ti[ct][0], ti[ct][1], a.x, b.y);
+                    dmma884(ti[ct][0], ti[ct][1], a.y, b.x);
+                }
+            }
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    accr[ct][e] = fma(tr[ct][e], v[ct][e].x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v[ct][e].y, accr[ct][e]);
+                    acci[ct][e] = fma(tr[ct][e], v[ct][e].y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v[ct][e].x, acci[ct][e]);
+                }
+            // refill this slot (its fragments have been consumed by the DMMAs above)
+            if (t + ST < tend) {
+#pragma unroll
+                for (int pq = 0; pq < P4T; ++pq)
+                    cp_async16_plain(slot + (s * P4T + pq) * 32, frag + ((int64_t)(t + ST) * P4T + pq) * 32 + lane);
+            }
+            cp_async_commit();
+        }
+        cp_async_wait_group<0>();
+        if (i < K) {
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int c = ct * 8 + 2 * t4 + e;
+                    const cplx* yp = ycolp[c];
+                    cplx yv = yp ? yp[i] : cmake(0.0, 0.0);
+                    ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
+                }
+        }
+    }
+}
+
+// generic pilot count (P4 not 4 or 8): direct fragment loads, no staging
+__device__ __forceinline__ void est_interference_generic(const cplx* __restrict__ frag, const int* __restrict__ tptr,
+                                                         const int* __restrict__ tdel, const cplx* hPs,
+                                                         const cplx* vbuf, cplx* ybuf, const cplx* const* ycolp, int K,
+                                                         int P4, int warp, int nwarp, int lane) {
+    constexpr int NC = NC_MAX, HS = NC + 2;
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
     for (int rt = warp; rt < RT; rt += nwarp) {
         double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
         const int i = rt * 8 + g;
-        int t = tptr[rt];
-        const int tend = tptr[rt + 1];
-        if (P4T > 0) {
-            cplx nxt[PQ];
-            int nd = 0;
-            if (t < tend) {
+        for (int t = tptr[rt]; t < tptr[rt + 1]; ++t) {
+            double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
+            const cplx* fr = frag + (int64_t)t * P4 * 32 + lane;
+            for (int pq = 0; pq < P4; ++pq) {
+                cplx a = __ldg(fr + pq * 32);
 #pragma unroll
-                for (int pq = 0; pq < PQ; ++pq) nxt[pq] = __ldg(frag + ((int64_t)t * PQ + pq) * 32 + lane);
-                nd = tdel[t];
-            }
-            for (; t < tend; ++t) {
-                cplx cur[PQ];
-#pragma unroll
-                for (int pq = 0; pq < PQ; ++pq) cur[pq] = nxt[pq];
-                int j = i + nd;
-                if (t + 1 < tend) {
-#pragma unroll
-                    for (int pq = 0; pq < PQ; ++pq) nxt[pq] = __ldg(frag + ((int64_t)(t + 1) * PQ + pq) * 32 + lane);
-                    nd = tdel[t + 1];
+                for (int ct = 0; ct < 2; ++ct) {
+                    cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+                    zmma884(tr[ct], ti[ct], a.x, a.y, b.x, b.y, dneg(b.y));
                 }
-                j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
-                cplx v[2][2];
-#pragma unroll
-                for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) v[ct][e] = vbuf[j * NC + ct * 8 + 2 * t4 + e];
-                double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
-#pragma unroll
-                for (int pq = 0; pq < PQ; ++pq) {
-                    const double nai = dneg(cur[pq].y);
-#pragma unroll
-                    for (int ct = 0; ct < 2; ++ct) {
-                        cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
-                        dmma884(tr[ct][0], tr[ct][1], cur[pq].x, b.x);
-                        dmma884(tr[ct][0], tr[ct][1], nai, b.y);
-                        dmma884(ti[ct][0], ti[ct][1], cur[pq].x, b.y);
-                        dmma884(ti[ct][0], ti[ct][1], cur[pq].y, b.x);
-                    }
-                }
-#pragma unroll
-                for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        accr[ct][e] = fma(tr[ct][e], v[ct][e].x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v[ct][e].y, accr[ct][e]);
-                        acci[ct][e] = fma(tr[ct][e], v[ct][e].y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v[ct][e].x, acci[ct][e]);
-                    }
             }
-        } else {
-            for (; t < tend; ++t) {
-                double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
-                const cplx* fr = frag + (int64_t)t * P4 * 32 + lane;
-                for (int pq = 0; pq < P4; ++pq) {
-                    cplx a = __ldg(fr + pq * 32);
+            int j = i + tdel[t];
+            j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
 #pragma unroll
-                    for (int ct = 0; ct < 2; ++ct) {
-                        cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
-                        zmma884(tr[ct], ti[ct], a.x, a.y, b.x, b.y, dneg(b.y));
-                    }
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    cplx v = vbuf[j * NC + ct * 8 + 2 * t4 + e];
+                    accr[ct][e] = fma(tr[ct][e], v.x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v.y, accr[ct][e]);
+                    acci[ct][e] = fma(tr[ct][e], v.y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v.x, acci[ct][e]);
                 }
-                int j = i + tdel[t];
-                j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
-#pragma unroll
-                for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        cplx v = vbuf[j * NC + ct * 8 + 2 * t4 + e];
-                        accr[ct][e] = fma(tr[ct][e], v.x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v.y, accr[ct][e]);
-                        acci[ct][e] = fma(tr[ct][e], v.y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v.x, acci[ct][e]);
-                    }
-            }
         }
         if (i < K) {
 #pragma unroll
@@ -496,42 +564,74 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
 }
 
 // ---- phase B, perfect CSI: acc[i, c] = sum_{j != i} D[i, j] v[j, c]   (DS.m:541-543)
-// A fragments come straight from the column-major D of this realization (8 rows x 4 columns per
-// DMMA k-step); four k-steps are loaded ahead of their use.
+// A mini-GEMM per CTA: the warps take one row tile each (a "row block" of nwarp row tiles) and walk the
+// columns j together in chunks of 32.  The v chunk (B operand) is staged ONCE per chunk in shared memory
+// for all warps (cp.async, two stages, padded rows -> conflict-free LDS.128); each warp streams its own
+// row tile of the row-tile-major D (A operand, contiguous 4 KB per chunk) through its private ring.
+#define PERF_CHUNK 32
+template <int NCT>
 __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
-                                                  const cplx* const* ycolp, int K, int warp, int nwarp, int lane) {
-    constexpr int NC = NC_MAX, U = 4;
+                                                  const cplx* const* ycolp, cplx* ring, cplx* vs, int K, int blk0,
+                                                  int blk_stride, int warp, int nwarp, int lane, int tid, int nthr) {
+    constexpr int NC = NC_MAX, U = PERF_CHUNK / 4, VS = NC + 2, ST = 2;
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
-    for (int rt = warp; rt < RT; rt += nwarp) {
+    cplx* slot = ring + lane;                                  // [stage][u][32 lanes]
+    const int nchunk = (K + PERF_CHUNK - 1) / PERF_CHUNK;
+    const int nblk = (RT + nwarp - 1) / nwarp;
+    for (int blk = blk0; blk < nblk; blk += blk_stride) {
+        const int rt = blk * nwarp + warp;
+        const bool active = rt < RT;
         double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
         const int i = rt * 8 + g;
-        const bool row_ok = i < K;
-        for (int j0 = 0; j0 < K; j0 += 4 * U) {
-            cplx a[U], b[U][2];
+        const cplx* Drt = Dm + (int64_t)(active ? rt : 0) * K * 8 + g;
+        auto issue = [&](int s, int ch) {
+            if (active) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                int j = j0 + 4 * u + t4;
-                a[u] = (row_ok && j < K && i != j) ? __ldg(Dm + (int64_t)j * K + i) : cmake(0.0, 0.0);
-                int jj = j < K ? j : K - 1;
-                b[u][0] = vbuf[jj * NC + g];
-                b[u][1] = vbuf[jj * NC + 8 + g];
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double nai = dneg(a[u].y);
-#pragma unroll
-                for (int ct = 0; ct < 2; ++ct) {
-                    dmma884(accr[ct][0], accr[ct][1], a[u].x, b[u][ct].x);
-                    dmma884(accr[ct][0], accr[ct][1], nai, b[u][ct].y);
-                    dmma884(acci[ct][0], acci[ct][1], a[u].x, b[u][ct].y);
-                    dmma884(acci[ct][0], acci[ct][1], a[u].y, b[u][ct].x);
+                for (int u = 0; u < U; ++u) {
+                    int j = ch * PERF_CHUNK + 4 * u + t4;
+                    j = j < K ? j : K - 1;                     // out-of-range columns are masked at use
+                    cp_async16_plain(slot + (s * U + u) * 32, Drt + (int64_t)j * 8);
                 }
             }
-        }
-        if (row_ok) {
+            for (int e = tid; e < PERF_CHUNK * NC; e += nthr) {   // v chunk, shared by all warps
+                int jr = e / NC, c = e % NC, j = ch * PERF_CHUNK + jr;
+                j = j < K ? j : K - 1;
+                cp_async16_plain(vs + (s * PERF_CHUNK + jr) * VS + c, vbuf + j * NC + c);
+            }
+        };
+        __syncthreads();                                       // previous row block done with both stages
+        issue(0, 0);
+        cp_async_commit();
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int s = ch & 1;
+            if (ch + 1 < nchunk) issue(s ^ 1, ch + 1);
+            cp_async_commit();
+            cp_async_wait_group<1>();
+            __syncthreads();                                   // chunk ch (v from every thread) has landed
+            if (active) {
 #pragma unroll
-            for (int ct = 0; ct < 2; ++ct)
+                for (int u = 0; u < U; ++u) {
+                    int j = ch * PERF_CHUNK + 4 * u + t4;
+                    cplx a = slot[(s * U + u) * 32];
+                    if (i >= K || j >= K || i == j) a = cmake(0.0, 0.0);
+                    const double nai = dneg(a.y);
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct) {
+                        const cplx b = vs[(s * PERF_CHUNK + 4 * u + t4) * VS + ct * 8 + g];
+                        dmma884(accr[ct][0], accr[ct][1], a.x, b.x);
+                        dmma884(accr[ct][0], accr[ct][1], nai, b.y);
+                        dmma884(acci[ct][0], acci[ct][1], a.x, b.y);
+                        dmma884(acci[ct][0], acci[ct][1], a.y, b.x);
+                    }
+                }
+            }
+            __syncthreads();                                   // stage s may be refilled in the next iteration
+        }
+        cp_async_wait_group<0>();
+        if (active && i < K) {
+#pragma unroll
+            for (int ct = 0; ct < NCT; ++ct)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     int c = ct * 8 + 2 * t4 + e;
@@ -543,177 +643,297 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
     }
 }
 
-__global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
-    constexpr int NC = NC_MAX;
-    const IcCta cta = p.ctas[blockIdx.x];
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    const int csi = cta.mode;
-    const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
-    const int K = p.sch[p.wf_scheme[wf][0]].K;
-    cplx* zbuf = p.scratch + (int64_t)blockIdx.x * 3 * p.K_max * NC;
-    cplx* vbuf = zbuf + (int64_t)p.K_max * NC;
-    cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
-    constexpr int HS = NC + 2;             // row stride of the pilot tables: conflict-free 128-bit fragment loads
-    __shared__ cplx hPs[64 * HS];          // previous pilot estimates [p][col]   (P <= 64)
-    __shared__ cplx hPn[64 * HS];          // new pilot estimates
-    __shared__ unsigned int cnt[NC][2];
-    __shared__ int c_scheme[NC], c_snr[NC], c_rep[NC];
-    __shared__ const cplx* ycolp[NC];      // y of each column (null for padding columns)
-    if (tid < NC) {
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define IC_TRACE(k, v) do { if (p.trace && threadIdx.x == 0) p.trace[(int64_t)blockIdx.x * 8 + (k)] = (v); } while (0)
+// ---------------------------------------------------------------------------------------------
+// k_ic: one launch per iteration `it` (it = 0 is the one-tap stage), persistent + cooperative.
+// Work units (IcCta): up to 16 columns and ALL K rows of them.
+//   EST  unit: one scheme, one SNR point, 16 consecutive realizations (they share W_snr)
+//   PERF unit: one realization, all (scheme-on-waveform, SNR) columns (they share D_rep)
+// Three grid-wide stages separated by grid barriers:
+//   pre  (A)     z = [xP; quantise(xD_prev)], v = C z              -- scalar FP64, latency-bound
+//   main (B)     y_ic = y - Woff(hP_prev) v   or   y - (D - diag h) v   -- FP64 tensor pipe (DMMA)
+//   post (C,D,E) pilot estimates, one-tap channel, equalise, de-spread / select, demap, count
+// The scalar stages run without DMMA competition (both share the SM's FP64 pipe: a DFMA queued behind
+// another CTA's DMMAs takes ~50 cycles), and in the main stage every resident CTA is in the tensor phase,
+// pulling units from a queue ordered heavy-first.
+// ---------------------------------------------------------------------------------------------
+struct IcShared {
+    unsigned int cnt[NC_MAX][2];
+    int c_scheme[NC_MAX], c_snr[NC_MAX], c_rep[NC_MAX];
+    const cplx* ycolp[NC_MAX];
+    ConstDev cst[2];
+    int unit;
+};
+
+__device__ __forceinline__ void ic_load_unit(const IcParams& p, const IcCta& cta, IcShared& sh) {
+    const int tid = threadIdx.x;
+    __syncthreads();                                   // previous unit's readers are done
+    if (tid < NC_MAX) {
         int s_ = 0, n_ = 0, r_ = 0;
         if (tid < cta.n_cols) ic_col(p, cta, tid, s_, n_, r_);
         const bool ok = tid < cta.n_cols && r_ < p.n_rep;
-        c_scheme[tid] = s_; c_snr[tid] = n_; c_rep[tid] = ok ? r_ : -1;
-        ycolp[tid] = ok ? p.sch[s_].y + ((int64_t)n_ * p.n_rep + r_) * p.sch[s_].K : nullptr;
-        cnt[tid][0] = cnt[tid][1] = 0;
+        sh.c_scheme[tid] = s_; sh.c_snr[tid] = n_; sh.c_rep[tid] = ok ? r_ : -1;
+        sh.ycolp[tid] = ok ? p.sch[s_].y + ((int64_t)n_ * p.n_rep + r_) * p.sch[s_].K : nullptr;
+        sh.cnt[tid][0] = sh.cnt[tid][1] = 0;
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
+    constexpr int NC = NC_MAX, HS = NC + 2;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int it = p.it;
+    extern __shared__ cplx ic_smem[];
+    cplx* hPs = ic_smem;                                    // previous pilot estimates [p][col]
+    cplx* hPn = ic_smem + p.pilot_rows * HS;                // new pilot estimates
+    cplx* ring = ic_smem + 2 * p.pilot_rows * HS + warp * (IC_RING_BYTES / (int)sizeof(cplx));
+    cplx* vstage = ic_smem + 2 * p.pilot_rows * HS + nwarp * (IC_RING_BYTES / (int)sizeof(cplx));   // 2 x 32 x HS
+    __shared__ IcShared sh;
+    {   // constellation tables (levels, grid -> word, word -> symbol) in shared memory
+        cplx* q = vstage + 2 * PERF_CHUNK * HS;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const ConstDev& cg = p.cst[k];
+            cplx* sym = q; q += cg.order;
+            double* lev = reinterpret_cast<double*>(q); q += (cg.n_axis + 1) / 2;
+            int* gr = reinterpret_cast<int*>(q); q += (cg.order + 3) / 4;
+            for (int e = tid; e < cg.order; e += nthr) { sym[e] = cg.symbol[e]; gr[e] = cg.word_of_grid[e]; }
+            for (int e = tid; e < cg.n_axis; e += nthr) lev[e] = cg.level[e];
+            if (tid == 0) { sh.cst[k] = cg; sh.cst[k].symbol = sym; sh.cst[k].level = lev; sh.cst[k].word_of_grid = gr; }
+        }
+    }
 
+    IC_TRACE(0, smid()); IC_TRACE(1, gtime());
     if (it > 0) {
-        // ---------------- phase A: z = [xP; quantise(xD_prev)],  v = C z        (DS.m:482-484, 541-543)
-        int kin_max = 0;
-        for (int c = 0; c < cta.n_cols; ++c) kin_max = max(kin_max, p.sch[c_scheme[c]].K_in);
-        for (int idx = tid; idx < kin_max * NC; idx += nthr) {
-            int c = idx % NC, k = idx / NC;
-            cplx z = cmake(0.0, 0.0);
-            if (c_rep[c] >= 0) {
-                const SchemeDev& sd = p.sch[c_scheme[c]];
-                if (k < sd.P) z = sd.xP[(int64_t)c_rep[c] * sd.P + k];
-                else if (k < sd.K_in) {
-                    const ConstDev& cd = p.cst[sd.constellation];
-                    cplx xd = sd.xD[csi][((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.n_data + (k - sd.P)];
-                    z = cd.symbol[demap_word(cd, xd)];
+        // =================== pre stage: phase A for every unit (DS.m:482-484, 541-543) ===================
+        for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+            const IcCta cta = p.ctas[unit];
+            ic_load_unit(p, cta, sh);
+            const int csi = cta.mode;
+            const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
+            const int K = p.sch[p.wf_scheme[wf][0]].K;
+            cplx* zbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC;
+            cplx* vbuf = zbuf + (int64_t)p.K_max * NC;
+            int kin_max = 0;
+            for (int c = 0; c < cta.n_cols; ++c) kin_max = max(kin_max, p.sch[sh.c_scheme[c]].K_in);
+            for (int idx = tid; idx < kin_max * NC; idx += nthr) {
+                int c = idx % NC, k = idx / NC;
+                cplx z = cmake(0.0, 0.0);
+                if (sh.c_rep[c] >= 0) {
+                    const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                    if (k < sd.P) z = sd.xP[(int64_t)sh.c_rep[c] * sd.P + k];
+                    else if (k < sd.K_in) {
+                        const ConstDev& cd = sh.cst[sd.constellation];
+                        cplx xd = sd.xD[csi][((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.n_data + (k - sd.P)];
+                        z = cd.symbol[demap_word(cd, xd)];
+                    }
+                }
+                zbuf[idx] = z;
+            }
+            __syncthreads();
+            // v = C z, one warp per row: lane = 16*h + c handles column c and every second entry of the row
+            // (h = 0/1), eight independent loads in flight per lane; the halves are combined with a shuffle.
+            {
+                const int c = lane & 15, h = lane >> 4;
+                const bool okc = sh.c_rep[c] >= 0;
+                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                const int* __restrict__ rp = sd.c_rowptr;
+                const int* __restrict__ cc = sd.c_col;
+                const cplx* __restrict__ cv = sd.c_val;
+                for (int i = warp; i < K; i += nwarp) {
+                    cplx acc = cmake(0.0, 0.0);
+                    if (okc) {
+                        const int e1 = rp[i + 1];
+                        int e = rp[i] + h;
+                        for (; e + 14 < e1; e += 16) {
+                            cplx cvv[8], zz[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { cvv[u] = cv[e + 2 * u]; zz[u] = zbuf[cc[e + 2 * u] * NC + c]; }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) cfma(acc, cvv[u], zz[u]);
+                        }
+                        for (; e < e1; e += 2) cfma(acc, cv[e], zbuf[cc[e] * NC + c]);
+                    }
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+                    if (h == 0) vbuf[i * NC + c] = acc;
                 }
             }
-            zbuf[idx] = z;
         }
-        if (csi == 0) {
-            const SchemeDev& sd = p.sch[cta.scheme_or_wf];
-            for (int idx = tid; idx < sd.P4 * 4 * NC; idx += nthr) {      // rows P..4*P4-1 are zero padding
-                int c = idx % NC, pp = idx / NC;
-                hPs[pp * HS + c] = (c_rep[c] >= 0 && pp < sd.P)
-                                       ? sd.hP[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.P + pp] : cmake(0.0, 0.0);
+        __threadfence();
+        grid.sync();
+        IC_TRACE(2, gtime());
+        unsigned long long n_done = 0;
+
+        // =================== main stage: phase B, units pulled from the queue ===================
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) sh.unit = (int)atomicAdd(p.queue + it, 1u);
+            __syncthreads();
+            const int unit = sh.unit;
+            if (unit >= p.n_units) break;
+            ++n_done;
+            const IcCta cta = p.ctas[unit];
+            ic_load_unit(p, cta, sh);
+            const int csi = cta.mode;
+            const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
+            const int K = p.sch[p.wf_scheme[wf][0]].K;
+            cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
+            cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
+            if (csi == 0) {
+                const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+                for (int idx = tid; idx < sd.P4 * 4 * NC; idx += nthr) {      // rows P..4*P4-1 are zero padding
+                    int c = idx % NC, pp = idx / NC;
+                    hPs[pp * HS + c] = (sh.c_rep[c] >= 0 && pp < sd.P)
+                                           ? sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] : cmake(0.0, 0.0);
+                }
+                __syncthreads();
+                // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
+                const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
+                if (sd.P4 == 4)
+                    est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs,
+                                        vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
+                else if (sd.P4 == 8)
+                    est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs,
+                                        vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
+                else
+                    est_interference_generic(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev],
+                                             hPs, vbuf, ybuf, sh.ycolp, K, sd.P4, warp, nwarp, lane);
+            } else {
+                const cplx* Dm = p.D[wf] + (int64_t)cta.snr * (((K + 7) / 8) * 8) * K;     // cta.snr holds the realization
+                if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, ring, vstage, K, 0, 1, warp, nwarp, lane, tid, nthr);
+                else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, ring, vstage, K, 0, 1, warp, nwarp, lane, tid, nthr);
             }
         }
-        __syncthreads();
-        for (int idx = tid; idx < K * NC; idx += nthr) {
-            int c = idx % NC, i = idx / NC;
-            cplx acc = cmake(0.0, 0.0);
-            if (c_rep[c] >= 0) {
-                const SchemeDev& sd = p.sch[c_scheme[c]];
-                for (int e = sd.c_rowptr[i]; e < sd.c_rowptr[i + 1]; ++e) cfma(acc, sd.c_val[e], zbuf[sd.c_col[e] * NC + c]);
-            }
-            vbuf[idx] = acc;
-        }
-        __syncthreads();
-        // ---------------- phase B: interference on FP64 tensor cores
-        if (csi == 0) {
-            const SchemeDev& sd = p.sch[cta.scheme_or_wf];
-            // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
-            const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
-            if (sd.P4 == 4)
-                est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, vbuf,
-                                    ybuf, ycolp, K, 4, warp, nwarp, lane);
-            else if (sd.P4 == 8)
-                est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, vbuf,
-                                    ybuf, ycolp, K, 8, warp, nwarp, lane);
-            else
-                est_interference<0>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, vbuf,
-                                    ybuf, ycolp, K, sd.P4, warp, nwarp, lane);
-        } else {
-            const cplx* Dm = p.D[wf] + (int64_t)cta.snr * K * K;     // cta.snr holds the realization
-            perf_interference(Dm, vbuf, ybuf, ycolp, K, warp, nwarp, lane);
-        }
-        __syncthreads();
-    } else {
-        // one-tap stage: y itself is equalised
-        for (int idx = tid; idx < K * NC; idx += nthr) {
-            int c = idx % NC, i = idx / NC;
-            const cplx* yp = ycolp[c];
-            ybuf[idx] = yp ? yp[i] : cmake(1.0, 0.0);
-        }
-        __syncthreads();
+        IC_TRACE(3, gtime()); IC_TRACE(7, n_done);
+        __threadfence();
+        grid.sync();
+        IC_TRACE(4, gtime());
     }
 
-    // ---------------- phase C: LS pilot estimates from the (cancelled) symbols   (DS.m:412-414, 487-489)
-    if (csi == 0) {
-        const SchemeDev& sd = p.sch[cta.scheme_or_wf];
-        for (int idx = tid; idx < sd.P * NC; idx += nthr) {
-            int c = idx % NC, pp = idx / NC;
-            cplx hp = cmake(0.0, 0.0);
-            if (c_rep[c] >= 0) {
-                cplx q = cdiv(ybuf[sd.pilot_pos[pp] * NC + c], sd.xP[(int64_t)c_rep[c] * sd.P + pp]);
-                hp = cmake(q.x / sd.sqrt_kappa, q.y / sd.sqrt_kappa);
-                sd.hP[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.P + pp] = hp;
-            }
-            hPn[pp * HS + c] = hp;
-        }
-        __syncthreads();
-    }
-    // ---------------- phase D: one-tap channel + equalisation                  (DS.m:428-429, 515-521)
-    {
-        const int var_cur = (it == 0 || it <= p.n_iter / 2) ? 0 : 1;
-        for (int idx = tid; idx < K * NC; idx += nthr) {
-            int c = idx % NC, i = idx / NC;
-            cplx xh = cmake(0.0, 0.0);
-            if (c_rep[c] >= 0) {
-                const SchemeDev& sd = p.sch[c_scheme[c]];
-                cplx hh;
-                if (csi == 0) {
-                    const cplx* wd = sd.w[var_cur][c_snr[c]].diag + (int64_t)i * sd.P;
-                    hh = cmake(0.0, 0.0);
-                    for (int pp = 0; pp < sd.P; ++pp) cfma(hh, wd[pp], hPn[pp * HS + c]);
-                    sd.hdiag[((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * K + i] = hh;
-                } else {
-                    hh = p.htrue[wf][(int64_t)c_rep[c] * K + i];
+    // =================== post stage: phases C, D, E for every unit ===================
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        const IcCta cta = p.ctas[unit];
+        ic_load_unit(p, cta, sh);
+        const int csi = cta.mode;
+        const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
+        const int K = p.sch[p.wf_scheme[wf][0]].K;
+        cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
+        const cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
+        // y_ic of this unit: the cancelled symbols, or y itself in the one-tap stage
+        auto yic = [&](int i, int c) -> cplx {
+            if (it > 0) return ybuf[i * NC + c];
+            const cplx* yp = sh.ycolp[c];
+            return yp ? yp[i] : cmake(1.0, 0.0);
+        };
+        // ---- phase C: LS pilot estimates from the (cancelled) symbols   (DS.m:412-414, 487-489)
+        if (csi == 0) {
+            const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+            for (int idx = tid; idx < sd.P * NC; idx += nthr) {
+                int c = idx % NC, pp = idx / NC;
+                cplx hp = cmake(0.0, 0.0);
+                if (sh.c_rep[c] >= 0) {
+                    cplx q = cdiv(yic(sd.pilot_pos[pp], c), sd.xP[(int64_t)sh.c_rep[c] * sd.P + pp]);
+                    hp = cmake(q.x / sd.sqrt_kappa, q.y / sd.sqrt_kappa);
+                    sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] = hp;
                 }
-                xh = cdiv(ybuf[idx], hh);
+                hPn[pp * HS + c] = hp;
             }
-            vbuf[idx] = xh;
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    // ---------------- phase E: data-symbol estimates, demap, bit errors         (DS.m:430-433 ...)
-    {
-        int nd_max = 0;
-        for (int c = 0; c < cta.n_cols; ++c) nd_max = max(nd_max, p.sch[c_scheme[c]].n_data);
-        for (int idx = tid; idx < nd_max * NC; idx += nthr) {
-            int c = idx % NC, d = idx / NC;
-            if (c_rep[c] < 0) continue;
-            const SchemeDev& sd = p.sch[c_scheme[c]];
-            if (d >= sd.n_data) continue;
-            const ConstDev& cd = p.cst[sd.constellation];
-            cplx xd;
-            if (sd.detect_mode == 1) {
-                cplx acc = cmake(0.0, 0.0);
-                int k = sd.P + d;
-                for (int e = sd.ct_colptr[k]; e < sd.ct_colptr[k + 1]; ++e) {
-                    cplx t = cmulc(sd.ct_val[e], vbuf[sd.ct_row[e] * NC + c]);
-                    acc.x += t.x; acc.y += t.y;
+        // ---- phase D: one-tap channel + equalisation                  (DS.m:428-429, 515-521)
+        {
+            const int var_cur = (it == 0 || it <= p.n_iter / 2) ? 0 : 1;
+            for (int idx = tid; idx < K * NC; idx += nthr) {
+                int c = idx % NC, i = idx / NC;
+                cplx xh = cmake(0.0, 0.0);
+                if (sh.c_rep[c] >= 0) {
+                    const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                    cplx hh;
+                    if (csi == 0) {
+                        const cplx* __restrict__ wd = sd.w[var_cur][sh.c_snr[c]].diag + (int64_t)i * sd.P;
+                        hh = cmake(0.0, 0.0);
+                        int pp = 0;
+                        for (; pp + 8 <= sd.P; pp += 8) {              // eight independent loads in flight
+                            cplx w8[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) w8[u] = __ldg(wd + pp + u);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) cfma(hh, w8[u], hPn[(pp + u) * HS + c]);
+                        }
+                        for (; pp < sd.P; ++pp) cfma(hh, __ldg(wd + pp), hPn[pp * HS + c]);
+                        sd.hdiag[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * K + i] = hh;
+                    } else {
+                        hh = p.htrue[wf][(int64_t)sh.c_rep[c] * K + i];
+                    }
+                    xh = cdiv(yic(i, c), hh);
                 }
-                xd = cmake(acc.x / sd.dpr, 0.0);
-            } else {
-                cplx v = vbuf[sd.data_pos[d] * NC + c];
-                xd = cmake(v.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : v.y / sd.sqrt_dpr);
+                vbuf[idx] = xh;
             }
-            sd.xD[csi][((int64_t)c_snr[c] * p.n_rep + c_rep[c]) * sd.n_data + d] = xd;
-            uint32_t diff = (uint32_t)demap_word(cd, xd) ^ sd.txword[(int64_t)c_rep[c] * sd.n_data + d];
-            if (diff) {
-                atomicAdd(&cnt[c][0], __popc(diff));
-                uint32_t de = diff & sd.edge_mask[d];
-                if (de) atomicAdd(&cnt[c][1], __popc(de));
-            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid < 2 * NC) {
-            int c = tid >> 1, e = tid & 1;
-            if (c < cta.n_cols && c_rep[c] >= 0) {
-                int64_t o = ((((int64_t)c_rep[c] * p.n_snr + c_snr[c]) * (p.n_iter + 1) + it) * 3 + c_scheme[c]) * 4 + csi * 2 + e;
-                p.err[o] = cnt[c][e];
+        // ---- phase E: data-symbol estimates, demap, bit errors         (DS.m:430-433 ...)
+        {
+            // the block size is a multiple of 16, so a thread keeps its column: counters stay in registers
+            const int c = tid % NC;
+            unsigned int e_all = 0, e_edge = 0;
+            if (sh.c_rep[c] >= 0) {
+                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                const ConstDev& cd = sh.cst[sd.constellation];
+                const int64_t colbase = ((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.n_data;
+                const uint32_t* __restrict__ txw = sd.txword + (int64_t)sh.c_rep[c] * sd.n_data;
+                const int dstep = nthr / NC;
+                for (int d0 = tid / NC; d0 < sd.n_data; d0 += 4 * dstep) {
+                    cplx xd[4];
+                    uint32_t tw[4], em[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {                      // four data symbols in flight per thread
+                        const int d = d0 + u * dstep;
+                        xd[u] = cmake(0.0, 0.0); tw[u] = 0; em[u] = 0;
+                        if (d < sd.n_data) {
+                            tw[u] = txw[d]; em[u] = sd.edge_mask[d];
+                            if (sd.detect_mode == 1) {
+                                cplx acc = cmake(0.0, 0.0);
+                                const int k = sd.P + d;
+                                for (int e = sd.ct_colptr[k]; e < sd.ct_colptr[k + 1]; ++e) {
+                                    cplx t = cmulc(sd.ct_val[e], vbuf[sd.ct_row[e] * NC + c]);
+                                    acc.x += t.x; acc.y += t.y;
+                                }
+                                xd[u] = cmake(acc.x / sd.dpr, 0.0);
+                            } else {
+                                cplx v = vbuf[sd.data_pos[d] * NC + c];
+                                xd[u] = cmake(v.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : v.y / sd.sqrt_dpr);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int d = d0 + u * dstep;
+                        if (d < sd.n_data) {
+                            sd.xD[csi][colbase + d] = xd[u];
+                            uint32_t diff = (uint32_t)demap_word(cd, xd[u]) ^ tw[u];
+                            e_all += __popc(diff);
+                            e_edge += __popc(diff & em[u]);
+                        }
+                    }
+                }
+            }
+            if (e_all) atomicAdd(&sh.cnt[c][0], e_all);
+            if (e_edge) atomicAdd(&sh.cnt[c][1], e_edge);
+            __syncthreads();
+            if (tid < 2 * NC) {
+                int cc = tid >> 1, e = tid & 1;
+                if (cc < cta.n_cols && sh.c_rep[cc] >= 0) {
+                    int64_t o = ((((int64_t)sh.c_rep[cc] * p.n_snr + sh.c_snr[cc]) * (p.n_iter + 1) + it) * 3 + sh.c_scheme[cc]) * 4 + csi * 2 + e;
+                    p.err[o] = sh.cnt[cc][e];
+                }
             }
         }
     }
+    IC_TRACE(5, gtime());
 }
 
 // ============================================================================ FP64 peak probes
