@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchest_b200.so")
+LIB_PATH = os.environ.get("CHEST_LIB", os.path.join(_HERE, "libchest_b200.so"))   # CHEST_LIB: development override
 
 c_u64, c_i64, c_i32, c_int = C.c_uint64, C.c_int64, C.c_int32, C.c_int
 p_d = C.POINTER(C.c_double)

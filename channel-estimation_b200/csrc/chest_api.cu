@@ -57,6 +57,7 @@ struct Waveform {
     int nsch = 0; int sch[2] = {0, 0};
     // batch state
     DevBuf<cplx> x, s, r0, y, D, htrue, HG;
+    int tile = 64;              // CTA tile size of the GEMMs on this waveform (48 or 64)
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
 };
 struct Constellation {
@@ -70,6 +71,7 @@ struct MmseVariant {
     int n_tiles = 0;
     DevBuf<int> tile_ptr, tile_delta;
     std::vector<DevBuf<cplx>> frag, diag;
+    DevBuf<cplx> diag_frag;        // [snr][rt][pq][32 lanes]
     DevBuf<WTiles> table;
     int64_t nnz_offdiag_pairs = 0;
 };
@@ -77,7 +79,8 @@ struct Scheme {
     bool set = false;
     int waveform = 0, K = 0, K_in = 0, P = 0, n_data = 0, detect = 0, constellation = 0, n_bits = 0;
     double kappa = 1, dpr = 1;
-    DevBuf<int> c_rowptr, c_col, ct_colptr, ct_row, pilot_pos, data_pos;
+    DevBuf<int> c_rowptr, c_col, ct_colptr, ct_row, pilot_pos, data_pos, row_col0, long_rows;
+    DevBuf<cplx> row_val0; int n_long_rows = 0;
     DevBuf<cplx> c_val, ct_val;
     DevBuf<uint32_t> edge_mask;
     std::vector<uint8_t> considered;
@@ -147,20 +150,26 @@ void tile_ranges(const std::vector<int>& lo, const std::vector<int>& hi, int til
     for (int t = 0; t < nt; ++t) if (thi[t] <= tlo[t]) { tlo[t] = 0; thi[t] = 0; }
 }
 
-constexpr int GEMM_SMEM = 2 * 2 * 64 * 20 * (int)sizeof(cplx);   // 2 stages x (A + B) x 64 rows x (16+4) complex
-
-template <int MODE>
-cudaError_t launch_gemm(Ctx* c, const GemmParams& p, int n_z) {
+template <int MODE, int WM, int WN, int TMW>
+cudaError_t launch_gemm_geo(Ctx* c, const GemmParams& p, int n_z) {
+    constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
+    constexpr int smem = 2 * (TM + TN) * 20 * (int)sizeof(cplx);     // 2 stages x (A + B) rows x (16+4) complex
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm<MODE, WM, WN, TMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    dim3 grid((p.M + 63) / 64, (p.n_cols + 63) / 64, n_z);
-    k_gemm<MODE><<<grid, 256, GEMM_SMEM, c->stream>>>(p);
+    dim3 grid((p.M + TM - 1) / TM, (p.n_cols + TN - 1) / TN, n_z);
+    k_gemm<MODE, WM, WN, TMW><<<grid, 32 * WM * WN, smem, c->stream>>>(p);
     c->launches++;
     return cudaGetLastError();
+}
+// tile = 64 or 48 (square CTA tiles); the per-tile k-range tables must have been built for the same size
+template <int MODE>
+cudaError_t launch_gemm(Ctx* c, const GemmParams& p, int n_z, int tile) {
+    if (tile == 48) return launch_gemm_geo<MODE, 2, 3, 3>(c, p, n_z);
+    return launch_gemm_geo<MODE, 2, 4, 4>(c, p, n_z);
 }
 
 SchemeDev scheme_dev(Ctx* c, int si) {
@@ -174,6 +183,8 @@ SchemeDev scheme_dev(Ctx* c, int si) {
     d.c_rowptr = s.c_rowptr.p; d.c_col = s.c_col.p; d.c_val = s.c_val.p;
     d.ct_colptr = s.ct_colptr.p; d.ct_row = s.ct_row.p; d.ct_val = s.ct_val.p;
     d.pilot_pos = s.pilot_pos.p; d.data_pos = s.data_pos.p; d.edge_mask = s.edge_mask.p;
+    d.row_col0 = s.row_col0.p; d.row_val0 = s.row_val0.p; d.long_rows = s.long_rows.p; d.n_long_rows = s.n_long_rows;
+    d.wdiag_frag[0] = s.mm[0].diag_frag.p; d.wdiag_frag[1] = s.mm[1].diag_frag.p;
     for (int v = 0; v < 2; ++v) {
         d.tile_ptr[v] = s.mm[v].tile_ptr.p; d.tile_delta[v] = s.mm[v].tile_delta.p; d.w[v] = s.mm[v].table.p;
     }
@@ -211,10 +222,10 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     p.nt_klo = w.hg_klo.p; p.nt_khi = w.hg_khi.p; p.hdiag = w.htrue.p; p.rep0 = rep0;
     dim3 ghg(2, w.K, n_rep);
     k_apply_hg<<<ghg, 128, 0, c->stream>>>(w.HG.p, w.G.p, c->h.p, c->d_tap_delay.p, w.hg_klo.p, w.hg_khi.p,
-                                           c->N, w.K, c->T, rep0);
+                                           c->N, w.K, c->T, rep0, w.tile);
     c->launches++;
     CK(cudaGetLastError());
-    CK(launch_gemm<GEMM_D>(c, p, n_rep));
+    CK(launch_gemm<GEMM_D>(c, p, n_rep, w.tile));
     return CHEST_OK;
 }
 
@@ -324,7 +335,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         p.M = N; p.Kc = w.K; p.n_cols = w.nsch * n_rep; p.lda = w.K; p.ldc = N; p.conj_a = 0;
         p.At = w.Gt.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.out = w.s.p;
         p.bsrc = w.x.p; p.ldb = w.K;
-        CK(launch_gemm<GEMM_PLAIN>(c, p, 1));
+        CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));
         dim3 grid((N + 127) / 128, w.nsch * n_rep);
         k_apply_h<<<grid, 128, 0, st>>>(w.r0.p, w.s.p, c->h.p, c->d_tap_delay.p, N, c->T, n_rep, -1);
         c->launches++;
@@ -343,7 +354,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         p.M = w.K; p.Kc = N; p.n_cols = w.nsch * S * n_rep; p.lda = N; p.ldc = w.K; p.conj_a = 1;
         p.At = w.Q.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.y.p;
         p.r0 = w.r0.p; p.noise = noise; p.noise_scale = c->d_noise_scale.p; p.n_snr = S; p.n_rep = n_rep; p.N = N;
-        CK(launch_gemm<GEMM_DEMOD>(c, p, 1));
+        CK(launch_gemm<GEMM_DEMOD>(c, p, 1, w.tile));
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
     // ---- stage 4/5 (K3b + K4): one-tap stage, then one fused launch per IC iteration
@@ -364,9 +375,14 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     size_t cst_smem = 0;                                           // shared-memory copies of the constellation tables
     for (int k = 0; k < 2; ++k)
         cst_smem += sizeof(cplx) * ((size_t)c->cst[k].order + (c->cst[k].n_axis + 1) / 2 + (c->cst[k].order + 3) / 4);
+#ifndef IC_MIN_BLOCKS
+#define IC_MIN_BLOCKS 2
+#endif
     const int ic_threads = 256;
-    const size_t ic_smem = (size_t)2 * ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx) + (size_t)(ic_threads / 32) * IC_RING_BYTES
-                           + (size_t)2 * PERF_CHUNK * (NC_MAX + 2) * sizeof(cplx) + cst_smem;
+    ip.ring_cplx = (EST_WSRC == 0) ? EST_RING * (ip.pilot_rows / 4) * 32 : 0;   // EST_RING tiles of P4 fragments x 32 lanes
+    const size_t ic_smem = (size_t)2 * ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx)
+                           + (size_t)2 * PERF_CHUNK * (NC_MAX + 2) * sizeof(cplx) + cst_smem
+                           + (size_t)(ic_threads / 32) * ip.ring_cplx * sizeof(cplx);
     if (c->ic_grid == 0 || c->ic_smem != ic_smem) {                // persistent grid: every CTA resident (cooperative launch)
         CK(cudaFuncSetAttribute(k_ic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         int per_sm = 0;
@@ -455,10 +471,10 @@ int chest_destroy(uint64_t handle) {
     for (auto& k : c->cst) { k.symbol.release(); k.pilot.release(); k.level.release(); k.word_of_grid.release(); }
     for (auto& s : c->sch) {
         s.c_rowptr.release(); s.c_col.release(); s.ct_colptr.release(); s.ct_row.release(); s.pilot_pos.release();
-        s.data_pos.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
+        s.data_pos.release(); s.row_col0.release(); s.long_rows.release(); s.row_val0.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
         s.hP.release(); s.hdiag.release(); s.xD[0].release(); s.xD[1].release(); s.txword.release(); s.bits.release();
         for (auto& m : s.mm) {
-            m.tile_ptr.release(); m.tile_delta.release(); m.table.release();
+            m.tile_ptr.release(); m.tile_delta.release(); m.table.release(); m.diag_frag.release();
             for (auto& f : m.frag) f.release();
             for (auto& f : m.diag) f.release();
         }
@@ -512,13 +528,29 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
     support_ranges(G, N, K, w.g_lo, w.g_hi);
     support_ranges(Q, N, K, w.q_lo, w.q_hi);
     std::vector<int> lo, hi;
-    tile_ranges(w.q_lo, w.q_hi, 64, 0, N, lo, hi);
+    {   // tile size: fewest padded flops of D = Q^H (H G) (k-ranges are unions over the tile's columns)
+        double best = -1;
+        for (int t : {64, 48}) {
+            std::vector<int> ql, qh, gl, gh;
+            tile_ranges(w.q_lo, w.q_hi, t, 0, N, ql, qh);
+            tile_ranges(w.g_lo, w.g_hi, t, 8, N, gl, gh);
+            double f = 0;
+            for (size_t a = 0; a < ql.size(); ++a)
+                for (size_t b = 0; b < gl.size(); ++b) {
+                    int l = std::max(ql[a], gl[b]), h = std::min(qh[a], gh[b]);
+                    if (h > l) f += (double)t * t * (((h - l) + 15) / 16) * 16;
+                }
+            if (best < 0 || f < best) { best = f; w.tile = t; }
+        }
+        if (const char* e = getenv("CHEST_GEMM_TILE")) w.tile = atoi(e) == 48 ? 48 : 64;
+    }
+    tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, lo, hi);
     CK(w.q_klo.upload(lo, c->stream)); CK(w.q_khi.upload(hi, c->stream));
     // row supports of G (which symbols j touch sample n) for s = G x
     std::vector<int> rlo(N, K), rhi(N, 0);
     for (int j = 0; j < K; ++j)
         for (int n = w.g_lo[j]; n < w.g_hi[j]; ++n) { rlo[n] = std::min(rlo[n], j); rhi[n] = std::max(rhi[n], j + 1); }
-    tile_ranges(rlo, rhi, 64, 0, K, lo, hi);
+    tile_ranges(rlo, rhi, w.tile, 0, K, lo, hi);
     CK(w.gt_klo.upload(lo, c->stream)); CK(w.gt_khi.upload(hi, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     w.set = true; c->finalized = false;
@@ -610,6 +642,18 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
     for (int k = 0; k < k_in; ++k)
         for (int e = colptr[k]; e < colptr[k + 1]; ++e) { int d = fill[rows[e]]++; cols[d] = k; vcsr[d] = vcsc[e]; }
     CK(s.c_rowptr.upload(rowptr, c->stream)); CK(s.c_col.upload(cols, c->stream)); CK(s.c_val.upload(vcsr, c->stream));
+    {   // ELL-1 view: rows with at most one entry are applied element-wise, the others are "long rows"
+        std::vector<int> col0(K, -1), longr;
+        std::vector<cplx> val0(K, cmake(0.0, 0.0));
+        for (int i = 0; i < K; ++i) {
+            int n = rowptr[i + 1] - rowptr[i];
+            if (n == 1) { col0[i] = cols[rowptr[i]]; val0[i] = vcsr[rowptr[i]]; }
+            else if (n > 1) { col0[i] = -2; longr.push_back(i); }
+        }
+        s.n_long_rows = (int)longr.size();
+        if (longr.empty()) longr.push_back(0);
+        CK(s.row_col0.upload(col0, c->stream)); CK(s.row_val0.upload(val0, c->stream)); CK(s.long_rows.upload(longr, c->stream));
+    }
     CK(s.ct_colptr.upload(colptr, c->stream)); CK(s.ct_row.upload(rows, c->stream)); CK(s.ct_val.upload(vcsc, c->stream));
     std::vector<int> pp(pilot_pos, pilot_pos + P);
     for (int x : pp) ARG(x >= 0 && x < K);
@@ -678,6 +722,7 @@ int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_
     m.frag.assign(n_snr, DevBuf<cplx>()); m.diag.assign(n_snr, DevBuf<cplx>());
     std::vector<WTiles> table(n_snr);
     std::vector<cplx> frag((size_t)std::max(m.n_tiles, 1) * P4 * 32), dg((size_t)K * P);
+    std::vector<cplx> dfrag((size_t)n_snr * RT * P4 * 32, cmake(0.0, 0.0));
     std::vector<char> pair_seen;
     m.nnz_offdiag_pairs = 0;
     for (int snr = 0; snr < n_snr; ++snr) {
@@ -688,7 +733,11 @@ int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_
             int p = (int)(r / K2);
             int64_t rem = r % K2;
             int j = (int)(rem / K), i = (int)(rem % K);
-            if (i == j) { dg[(size_t)i * P + p] = v[e]; continue; }
+            if (i == j) {
+                dg[(size_t)i * P + p] = v[e];
+                dfrag[(((size_t)snr * RT + (i >> 3)) * P4 + (p >> 2)) * 32 + (i & 7) * 4 + (p & 3)] = v[e];
+                continue;
+            }
             int t = lut[(size_t)(i >> 3) * ND + (j - i + K - 1)];
             frag[((size_t)t * P4 + (p >> 2)) * 32 + (i & 7) * 4 + (p & 3)] = v[e];
         }
@@ -706,6 +755,7 @@ int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_
         m.nnz_offdiag_pairs = cnt;
     }
     CK(m.table.upload(table, c->stream));
+    CK(m.diag_frag.upload(dfrag, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     m.set = true; c->finalized = false;
     return CHEST_OK;
@@ -723,7 +773,7 @@ int chest_finalize(uint64_t handle, int max_batch) {
         if (!w.set) continue;
         const int K = w.K, max_delay = c->tap_delay.back();
         std::vector<int> lo, hi;
-        tile_ranges(w.g_lo, w.g_hi, 64, max_delay, N, lo, hi);
+        tile_ranges(w.g_lo, w.g_hi, w.tile, max_delay, N, lo, hi);
         CK(w.hg_klo.upload(lo, c->stream)); CK(w.hg_khi.upload(hi, c->stream));
         // support-aware work model: 8 T supp_G K  +  8 sum |supp(Q_i) ^ supp((HG)_j)|
         double f = 0;
@@ -905,7 +955,7 @@ static int plain_gemm(Ctx* c, int wfi, bool demod, const double* in, int n_cols,
     p.bsrc = c->tmp_a.p; p.ldb = len_in;
     if (demod) { p.At = w.Q.p; p.lda = N; p.conj_a = 1; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; }
     else { p.At = w.Gt.p; p.lda = K; p.conj_a = 0; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; }
-    CK(launch_gemm<GEMM_PLAIN>(c, p, 1));
+    CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));
     CK(cudaMemcpyAsync(out, c->tmp_b.p, sizeof(cplx) * (size_t)n_cols * len_out, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return CHEST_OK;

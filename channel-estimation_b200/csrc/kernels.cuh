@@ -118,14 +118,14 @@ __global__ void k_apply_h(cplx* __restrict__ r, const cplx* __restrict__ s, cons
     r[(int64_t)col * N + n] = acc;
 }
 
-// HG[rep][j][n] = sum_tap h[rep][tap][n] * G[n - delay_tap, j] for n inside the k-range of j's 64-column
+// HG[rep][j][n] = sum_tap h[rep][tap][n] * G[n - delay_tap, j] for n inside the k-range of j's column
 // tile (zero elsewhere in that range because G is zero outside its support).  K2 then reads H*G as a
 // plain k-contiguous operand with cp.async.
 __global__ void k_apply_hg(cplx* __restrict__ HG, const cplx* __restrict__ G, const cplx* __restrict__ h,
                            const int* __restrict__ tap_delay, const int* __restrict__ nt_klo,
-                           const int* __restrict__ nt_khi, int N, int K, int T, int rep0) {
+                           const int* __restrict__ nt_khi, int N, int K, int T, int rep0, int tile) {
     const int j = blockIdx.y, rep = blockIdx.z + rep0;
-    const int lo = nt_klo[j >> 6], hi = nt_khi[j >> 6];
+    const int lo = nt_klo[j / tile], hi = nt_khi[j / tile];
     const cplx* gc = G + (int64_t)N * j;
     const cplx* hr = h + (int64_t)rep * T * N;
     cplx* out = HG + ((int64_t)rep * K + j) * N;
@@ -179,6 +179,9 @@ struct SchemeDev {
     const int* c_rowptr; const int* c_col; const cplx* c_val;      // precoder C, CSR (K rows)
     const int* ct_colptr; const int* ct_row; const cplx* ct_val;   // precoder C, CSC (K_in cols)
     const int* pilot_pos; const int* data_pos; const uint32_t* edge_mask;   // per data symbol bit mask
+    // precoder rows with a single entry (ELL-1): column (-1: empty row, -2: long row) and value; long rows listed
+    const int* row_col0; const cplx* row_val0; const int* long_rows; int n_long_rows;
+    const cplx* wdiag_frag[2];     // [snr][rt][pq][32 lanes]: W[i,i,p] in DMMA A-fragment order (phase D)
     // MMSE matrices: tile lists per variant, fragments per (variant, snr)
     const int* tile_ptr[2];        // [RT+1]
     const int* tile_delta[2];      // [n_tiles]
@@ -257,14 +260,18 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // lane's (re, im) fragment pair is one conflict-free LDS.128.  Two stages: while the tensor pipe works
 // on stage s, cp.async (A, and B when it is a plain copy) and the computed B values (noise add / banded
 // H applied to G on the fly) fill stage s^1; one barrier per k-tile.
-template <int MODE>
-__global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
-    constexpr int TM = 64, TN = 64, KT = 16, LDS = KT + 4;
+// Geometry: WM x WN warps, each owning TMW x 2 DMMA tiles -> CTA tile (8*TMW*WM) x (16*WN).
+//   <2,4,4>: 64 x 64, 8 warps, 2 CTAs/SM        <2,3,3>: 48 x 48, 6 warps, 3 CTAs/SM
+// The host picks, per waveform, the geometry whose tiles waste the fewest flops on padding (48 divides the
+// 720 / 336 symbols of the reference's grids and follows the 24-subcarrier support structure more closely).
+template <int MODE, int WM, int WN, int TMW>
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 2 : 3) k_gemm(GemmParams p) {
+    constexpr int TM = 8 * TMW * WM, TN = 16 * WN, KT = 16, LDS = KT + 4, NTHR = 32 * WM * WN;
     extern __shared__ double smem[];
     cplx (*As)[TM][LDS] = reinterpret_cast<cplx (*)[TM][LDS]>(smem);
     cplx (*Bs)[TN][LDS] = reinterpret_cast<cplx (*)[TN][LDS]>(smem + 2 * 2 * TM * LDS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
+    const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t4 = lane & 3;
     const int mt = blockIdx.x, nt = blockIdx.y;
     const int m0 = mt * TM, n0 = nt * TN;
@@ -277,23 +284,23 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
     cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * RT8 * p.n_cols : 0);
     const bool conj_a = p.conj_a != 0;
 
-    double cr[4][2][2], ci[4][2][2];
+    double cr[TMW][2][2], ci[TMW][2][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < TMW; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b) { cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0; }
 
     auto fill = [&](int stage, int k0) {
 #pragma unroll
-        for (int e = 0; e < (TM * KT) / 256; ++e) {          // A tile: 64 rows x 16 k
-            int idx = tid + e * 256, kk = idx & (KT - 1), r = idx / KT;
+        for (int e = 0; e < (TM * KT) / NTHR; ++e) {         // A tile: TM rows x 16 k
+            int idx = tid + e * NTHR, kk = idx & (KT - 1), r = idx / KT;
             int gk = k0 + kk, gm = m0 + r;
             bool ok = gm < p.M && gk < khi;
             cp_async16(&As[stage][r][kk], p.At + (ok ? (int64_t)gk + (int64_t)p.lda * gm : 0), ok);
         }
 #pragma unroll
-        for (int e = 0; e < (TN * KT) / 256; ++e) {          // B tile: 64 cols x 16 k
-            int idx = tid + e * 256, kk = idx & (KT - 1), c = idx / KT;
+        for (int e = 0; e < (TN * KT) / NTHR; ++e) {         // B tile: TN cols x 16 k
+            int idx = tid + e * NTHR, kk = idx & (KT - 1), c = idx / KT;
             int gk = k0 + kk, col = n0 + c;
             bool ok = col < p.n_cols && gk < khi;
             if (MODE == GEMM_PLAIN) {
@@ -325,13 +332,13 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
         if (kt + 1 < nk) fill(st ^ 1, klo + (kt + 1) * KT);
 #pragma unroll
         for (int kk = 0; kk < KT; kk += 4) {
-            cplx a[4], b[2];
+            cplx a[TMW], b[2];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) a[x] = As[st][wm * 32 + x * 8 + g][kk + t4];
+            for (int x = 0; x < TMW; ++x) a[x] = As[st][wm * 8 * TMW + x * 8 + g][kk + t4];
 #pragma unroll
             for (int y = 0; y < 2; ++y) b[y] = Bs[st][wn * 16 + y * 8 + g][kk + t4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
+            for (int x = 0; x < TMW; ++x) {
                 const double ai = conj_a ? dneg(a[x].y) : a[x].y;
                 const double nai = conj_a ? a[x].y : dneg(a[x].y);
 #pragma unroll
@@ -348,12 +355,12 @@ __global__ void __launch_bounds__(256, 2) k_gemm(GemmParams p) {
     }
     // ---- epilogue: C[g][2*t4 + e] of each 8x8 tile
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < TMW; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                int m = m0 + wm * 32 + a * 8 + g, col = n0 + wn * 16 + b * 8 + 2 * t4 + e;
+                int m = m0 + wm * 8 * TMW + a * 8 + g, col = n0 + wn * 16 + b * 8 + 2 * t4 + e;
                 if (m < p.M && col < p.n_cols) {
                     cplx v = cmake(cr[a][b][e], ci[a][b][e]);
                     if (MODE == GEMM_D) {
@@ -402,6 +409,7 @@ __global__ void k_estimate(cplx* __restrict__ Dhat, cplx* __restrict__ hdiag, WT
 struct IcCta { int mode, scheme_or_wf, snr, first, n_cols; };   // mode 0 EST, 1 PERF
 struct IcParams {
     int it, n_iter, n_rep, n_snr, K_max, pilot_rows;      // pilot_rows: rows of the shared pilot tables (4 * max P4)
+    int ring_cplx;                                        // complex elements of one warp's W-fragment ring
     const IcCta* ctas;
     SchemeDev sch[3];
     ConstDev cst[2];
@@ -420,8 +428,13 @@ __device__ __forceinline__ void ic_col(const IcParams& p, const IcCta& c, int co
     else { int q = c.first + col; scheme = p.wf_scheme[c.scheme_or_wf][q / p.n_snr]; snr = q % p.n_snr; rep = c.snr; }
 }
 
-#define IC_RING_BYTES 8192      // per-warp cp.async ring (fragment stream staging)
-#define IC_PILOT_MAX 64         // pilots per scheme supported by the shared pilot tables
+#define IC_PILOT_MAX 128
+#ifndef EST_WSRC
+#define EST_WSRC 0
+#endif
+#ifndef EST_RING
+#define EST_RING 2
+#endif        // pilots per scheme supported by the shared pilot tables
 
 __device__ __forceinline__ void cp_async16_plain(void* smem_dst, const void* gsrc) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -430,60 +443,120 @@ __device__ __forceinline__ void cp_async16_plain(void* smem_dst, const void* gsr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+// streaming 16-byte load: read-only path, no L1 allocation (W and D fragments are used once per CTA; the
+// L1 is kept for the v / y_ic rows, which are re-read many times)
+__device__ __forceinline__ cplx ld_stream(const cplx* ptr) {
+    cplx r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(ptr));
+    return r;
+}
 
 // ---- phase B, estimated CSI: acc[i, c] = sum_{delta} ( sum_p W[i, i+delta, p] hP[p, c] ) * v[i+delta, c]
 // One warp owns 8 rows (a row tile) at a time and walks its diagonal tiles.  Per tile the P4 pilot
 // quads are DMMA k-steps with the hP fragments as B operand (shared by every tile), followed by an
-// element-wise product with v on the C fragment.  The W fragment stream of a row tile is contiguous;
-// every lane copies its own 16-byte fragment elements with cp.async into a private slot of the warp's
-// shared-memory ring, ST tiles ahead of their use (no barrier: a lane only reads what it copied).
+// element-wise product with v on the C fragment.  The W fragment stream of a row tile is contiguous
+// (512 bytes per warp load).
+// Tuning knobs (compile-time, see profiles/ for the sweep):
+//   EST_WSRC  0: W fragments through a per-lane cp.async ring in shared memory (EST_RING tiles in flight)
+//             1: next tile's fragments prefetched into registers with streaming loads
+//             2: this tile's fragments loaded where they are used
+//   measured (profiles/r01_kic_variant_sweep.txt): 0 is best in the mixed EST+PERF main stage
+//   EST_VPRE  1: next tile's v rows prefetched into registers
+//   EST_HPREG 1: the hP B-fragments live in registers for the whole row tile (P4 <= 4 only)
+#ifndef EST_VPRE
+#define EST_VPRE 0
+#endif
+#ifndef EST_HPREG
+#define EST_HPREG 0
+#endif
+#ifndef EST_RING
+#define EST_RING 2
+#endif
 template <int P4T>
 __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
                                                  const int* __restrict__ tdel, const cplx* hPs, const cplx* vbuf,
                                                  cplx* ybuf, const cplx* const* ycolp, cplx* ring, int K, int warp,
                                                  int nwarp, int lane) {
-    constexpr int NC = NC_MAX, HS = NC + 2;
-    constexpr int ST = IC_RING_BYTES / (P4T * 512);          // tiles in flight
+    constexpr int NC = NC_MAX, HS = NC + 2, ST = EST_RING;
+    constexpr bool HPREG = EST_HPREG && P4T <= 4;
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
     cplx* slot = ring + lane;                                  // [stage][pq][32 lanes]
+    cplx hb[HPREG ? P4T : 1][2];
+    if (HPREG) {
+#pragma unroll
+        for (int pq = 0; pq < P4T; ++pq)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) hb[HPREG ? pq : 0][ct] = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+    }
     for (int rt = warp; rt < RT; rt += nwarp) {
         double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
         const int i = rt * 8 + g;
         const int t0 = tptr[rt], tend = tptr[rt + 1];
+        cplx nxt[EST_WSRC == 1 ? P4T : 1], vn[2][2];
+        auto load_w = [&](int t, int s) {
+            if (EST_WSRC == 0) {
+                if (t < tend) {
 #pragma unroll
-        for (int s = 0; s < ST; ++s) {
-            if (t0 + s < tend) {
+                    for (int pq = 0; pq < P4T; ++pq)
+                        cp_async16_plain(slot + (s * P4T + pq) * 32, frag + ((int64_t)t * P4T + pq) * 32 + lane);
+                }
+                cp_async_commit();
+            } else if (t < tend) {
 #pragma unroll
-                for (int pq = 0; pq < P4T; ++pq)
-                    cp_async16_plain(slot + (s * P4T + pq) * 32, frag + ((int64_t)(t0 + s) * P4T + pq) * 32 + lane);
+                for (int pq = 0; pq < P4T; ++pq) nxt[EST_WSRC == 1 ? pq : 0] = ld_stream(frag + ((int64_t)t * P4T + pq) * 32 + lane);
             }
-            cp_async_commit();
-        }
-        int nd = t0 < tend ? tdel[t0] : 0;
-        for (int t = t0; t < tend; ++t) {
-            const int s = (t - t0) % ST;
-            int j = i + nd;
-            if (t + 1 < tend) nd = tdel[t + 1];
+        };
+        auto load_v = [&](int t, cplx (&dst)[2][2]) {
+            int j = i + tdel[t];
             j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
-            cplx v[2][2];
 #pragma unroll
             for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) v[ct][e] = vbuf[j * NC + ct * 8 + 2 * t4 + e];
-            cp_async_wait_group<ST - 1>();
+                for (int e = 0; e < 2; ++e) dst[ct][e] = vbuf[j * NC + ct * 8 + 2 * t4 + e];
+        };
+        if (EST_WSRC == 0) {
+#pragma unroll
+            for (int s = 0; s < ST; ++s) load_w(t0 + s, s);
+        } else if (EST_WSRC == 1) {
+            load_w(t0, 0);
+        }
+        if (EST_VPRE && t0 < tend) load_v(t0, vn);
+        for (int t = t0; t < tend; ++t) {
+            const int s = (t - t0) % ST;
+            cplx cur[P4T], v[2][2];
+            if (EST_VPRE) {
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) v[ct][e] = vn[ct][e];
+                if (t + 1 < tend) load_v(t + 1, vn);
+            } else {
+                load_v(t, v);
+            }
+            if (EST_WSRC == 0) {
+                cp_async_wait_group<ST - 1>();
+#pragma unroll
+                for (int pq = 0; pq < P4T; ++pq) cur[pq] = slot[(s * P4T + pq) * 32];
+            } else if (EST_WSRC == 1) {
+#pragma unroll
+                for (int pq = 0; pq < P4T; ++pq) cur[pq] = nxt[EST_WSRC == 1 ? pq : 0];
+                load_w(t + 1, 0);
+            } else {                                          // direct streaming loads of this tile's fragments
+#pragma unroll
+                for (int pq = 0; pq < P4T; ++pq) cur[pq] = ld_stream(frag + ((int64_t)t * P4T + pq) * 32 + lane);
+            }
             double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll
             for (int pq = 0; pq < P4T; ++pq) {
-                const cplx a = slot[(s * P4T + pq) * 32];
-                const double nai = dneg(a.y);
+                const double nai = dneg(cur[pq].y);
 #pragma unroll
                 for (int ct = 0; ct < 2; ++ct) {
-                    cplx b = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
-                    dmma884(tr[ct][0], tr[ct][1], a.x, b.x);
+                    const cplx b = HPREG ? hb[HPREG ? pq : 0][ct] : hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+                    dmma884(tr[ct][0], tr[ct][1], cur[pq].x, b.x);
                     dmma884(tr[ct][0], tr[ct][1], nai, b.y);
-                    dmma884(ti[ct][0], ti[ct][1], a.x, b.y);
-                    dmma884(ti[ct][0], ti[ct][1], a.y, b.x);
+                    dmma884(ti[ct][0], ti[ct][1], cur[pq].x, b.y);
+                    dmma884(ti[ct][0], ti[ct][1], cur[pq].y, b.x);
                 }
             }
 #pragma unroll
@@ -493,15 +566,9 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
                     accr[ct][e] = fma(tr[ct][e], v[ct][e].x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v[ct][e].y, accr[ct][e]);
                     acci[ct][e] = fma(tr[ct][e], v[ct][e].y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v[ct][e].x, acci[ct][e]);
                 }
-            // refill this slot (its fragments have been consumed by the DMMAs above)
-            if (t + ST < tend) {
-#pragma unroll
-                for (int pq = 0; pq < P4T; ++pq)
-                    cp_async16_plain(slot + (s * P4T + pq) * 32, frag + ((int64_t)(t + ST) * P4T + pq) * 32 + lane);
-            }
-            cp_async_commit();
+            if (EST_WSRC == 0) load_w(t + ST, s);              // refill the slot just consumed
         }
-        cp_async_wait_group<0>();
+        if (EST_WSRC == 0) cp_async_wait_group<0>();
         if (i < K) {
 #pragma unroll
             for (int ct = 0; ct < 2; ++ct)
@@ -565,70 +632,68 @@ __device__ __forceinline__ void est_interference_generic(const cplx* __restrict_
 
 // ---- phase B, perfect CSI: acc[i, c] = sum_{j != i} D[i, j] v[j, c]   (DS.m:541-543)
 // A mini-GEMM per CTA: the warps take one row tile each (a "row block" of nwarp row tiles) and walk the
-// columns j together in chunks of 32.  The v chunk (B operand) is staged ONCE per chunk in shared memory
+// columns j together in chunks of 16.  The v chunk (B operand) is staged ONCE per chunk in shared memory
 // for all warps (cp.async, two stages, padded rows -> conflict-free LDS.128); each warp streams its own
-// row tile of the row-tile-major D (A operand, contiguous 4 KB per chunk) through its private ring.
-#define PERF_CHUNK 32
+// row tile of the row-tile-major D (A operand: 512 contiguous bytes per k-step) through registers, one
+// chunk ahead.
+#define PERF_CHUNK 16
 template <int NCT>
 __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
-                                                  const cplx* const* ycolp, cplx* ring, cplx* vs, int K, int blk0,
-                                                  int blk_stride, int warp, int nwarp, int lane, int tid, int nthr) {
-    constexpr int NC = NC_MAX, U = PERF_CHUNK / 4, VS = NC + 2, ST = 2;
+                                                  const cplx* const* ycolp, cplx* vs, int K, int warp, int nwarp,
+                                                  int lane, int tid, int nthr) {
+    constexpr int NC = NC_MAX, U = PERF_CHUNK / 4, VS = NC + 2;
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
-    cplx* slot = ring + lane;                                  // [stage][u][32 lanes]
     const int nchunk = (K + PERF_CHUNK - 1) / PERF_CHUNK;
     const int nblk = (RT + nwarp - 1) / nwarp;
-    for (int blk = blk0; blk < nblk; blk += blk_stride) {
+    for (int blk = 0; blk < nblk; ++blk) {
         const int rt = blk * nwarp + warp;
         const bool active = rt < RT;
         double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
         const int i = rt * 8 + g;
         const cplx* Drt = Dm + (int64_t)(active ? rt : 0) * K * 8 + g;
+        cplx an[U];
         auto issue = [&](int s, int ch) {
-            if (active) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    int j = ch * PERF_CHUNK + 4 * u + t4;
-                    j = j < K ? j : K - 1;                     // out-of-range columns are masked at use
-                    cp_async16_plain(slot + (s * U + u) * 32, Drt + (int64_t)j * 8);
-                }
+            for (int u = 0; u < U; ++u) {
+                int j = ch * PERF_CHUNK + 4 * u + t4;
+                j = j < K ? j : K - 1;                         // out-of-range columns are masked at use
+                an[u] = active ? ld_stream(Drt + (int64_t)j * 8) : cmake(0.0, 0.0);
             }
             for (int e = tid; e < PERF_CHUNK * NC; e += nthr) {   // v chunk, shared by all warps
                 int jr = e / NC, c = e % NC, j = ch * PERF_CHUNK + jr;
                 j = j < K ? j : K - 1;
                 cp_async16_plain(vs + (s * PERF_CHUNK + jr) * VS + c, vbuf + j * NC + c);
             }
+            cp_async_commit();
         };
         __syncthreads();                                       // previous row block done with both stages
         issue(0, 0);
-        cp_async_commit();
+        cp_async_wait_group<0>();
+        __syncthreads();
         for (int ch = 0; ch < nchunk; ++ch) {
             const int s = ch & 1;
-            if (ch + 1 < nchunk) issue(s ^ 1, ch + 1);
-            cp_async_commit();
-            cp_async_wait_group<1>();
-            __syncthreads();                                   // chunk ch (v from every thread) has landed
-            if (active) {
+            cplx a[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    int j = ch * PERF_CHUNK + 4 * u + t4;
-                    cplx a = slot[(s * U + u) * 32];
-                    if (i >= K || j >= K || i == j) a = cmake(0.0, 0.0);
-                    const double nai = dneg(a.y);
+            for (int u = 0; u < U; ++u) a[u] = an[u];
+            if (ch + 1 < nchunk) issue(s ^ 1, ch + 1);         // stage s^1 was last read before the previous barrier
 #pragma unroll
-                    for (int ct = 0; ct < NCT; ++ct) {
-                        const cplx b = vs[(s * PERF_CHUNK + 4 * u + t4) * VS + ct * 8 + g];
-                        dmma884(accr[ct][0], accr[ct][1], a.x, b.x);
-                        dmma884(accr[ct][0], accr[ct][1], nai, b.y);
-                        dmma884(acci[ct][0], acci[ct][1], a.x, b.y);
-                        dmma884(acci[ct][0], acci[ct][1], a.y, b.x);
-                    }
+            for (int u = 0; u < U; ++u) {
+                int j = ch * PERF_CHUNK + 4 * u + t4;
+                if (i >= K || j >= K || i == j) a[u] = cmake(0.0, 0.0);
+                const double nai = dneg(a[u].y);
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct) {
+                    const cplx b = vs[(s * PERF_CHUNK + 4 * u + t4) * VS + ct * 8 + g];
+                    dmma884(accr[ct][0], accr[ct][1], a[u].x, b.x);
+                    dmma884(accr[ct][0], accr[ct][1], nai, b.y);
+                    dmma884(acci[ct][0], acci[ct][1], a[u].x, b.y);
+                    dmma884(acci[ct][0], acci[ct][1], a[u].y, b.x);
                 }
             }
-            __syncthreads();                                   // stage s may be refilled in the next iteration
+            cp_async_wait_group<0>();
+            __syncthreads();                                   // chunk ch+1 has landed, chunk ch is consumed
         }
-        cp_async_wait_group<0>();
         if (active && i < K) {
 #pragma unroll
             for (int ct = 0; ct < NCT; ++ct)
@@ -681,7 +746,10 @@ __device__ __forceinline__ void ic_load_unit(const IcParams& p, const IcCta& cta
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
+#ifndef IC_MIN_BLOCKS
+#define IC_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
     constexpr int NC = NC_MAX, HS = NC + 2;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -689,11 +757,11 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
     extern __shared__ cplx ic_smem[];
     cplx* hPs = ic_smem;                                    // previous pilot estimates [p][col]
     cplx* hPn = ic_smem + p.pilot_rows * HS;                // new pilot estimates
-    cplx* ring = ic_smem + 2 * p.pilot_rows * HS + warp * (IC_RING_BYTES / (int)sizeof(cplx));
-    cplx* vstage = ic_smem + 2 * p.pilot_rows * HS + nwarp * (IC_RING_BYTES / (int)sizeof(cplx));   // 2 x 32 x HS
+    cplx* vstage = ic_smem + 2 * p.pilot_rows * HS;        // 2 x PERF_CHUNK x HS
+    cplx* ring = vstage + 2 * PERF_CHUNK * HS + warp * p.ring_cplx;     // per-warp W-fragment ring
     __shared__ IcShared sh;
     {   // constellation tables (levels, grid -> word, word -> symbol) in shared memory
-        cplx* q = vstage + 2 * PERF_CHUNK * HS;
+        cplx* q = vstage + 2 * PERF_CHUNK * HS + nwarp * p.ring_cplx;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const ConstDev& cg = p.cst[k];
@@ -719,23 +787,58 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
             cplx* vbuf = zbuf + (int64_t)p.K_max * NC;
             int kin_max = 0;
             for (int c = 0; c < cta.n_cols; ++c) kin_max = max(kin_max, p.sch[sh.c_scheme[c]].K_in);
-            for (int idx = tid; idx < kin_max * NC; idx += nthr) {
-                int c = idx % NC, k = idx / NC;
-                cplx z = cmake(0.0, 0.0);
-                if (sh.c_rep[c] >= 0) {
-                    const SchemeDev& sd = p.sch[sh.c_scheme[c]];
-                    if (k < sd.P) z = sd.xP[(int64_t)sh.c_rep[c] * sd.P + k];
-                    else if (k < sd.K_in) {
-                        const ConstDev& cd = sh.cst[sd.constellation];
-                        cplx xd = sd.xD[csi][((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.n_data + (k - sd.P)];
-                        z = cd.symbol[demap_word(cd, xd)];
+            {   // A1: z = [xP; quantise(xD_prev)].  A thread keeps its column; eight symbols in flight.
+                const int c = tid % NC;
+                const bool okc = sh.c_rep[c] >= 0;
+                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                const ConstDev& cd = sh.cst[sd.constellation];
+                const cplx* __restrict__ xdp = sd.xD[csi] + ((int64_t)sh.c_snr[c] * p.n_rep + (okc ? sh.c_rep[c] : 0)) * sd.n_data;
+                const cplx* __restrict__ xpp = sd.xP + (int64_t)(okc ? sh.c_rep[c] : 0) * sd.P;
+                const int kstep = nthr / NC;
+                for (int k0 = tid / NC; k0 < kin_max; k0 += 8 * kstep) {
+                    cplx in[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 + u * kstep;
+                        in[u] = cmake(0.0, 0.0);
+                        if (okc && k < sd.K_in) in[u] = k < sd.P ? xpp[k] : xdp[k - sd.P];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 + u * kstep;
+                        if (k < kin_max) {
+                            cplx z = in[u];
+                            if (okc && k >= sd.P && k < sd.K_in) z = cd.symbol[demap_word(cd, in[u])];
+                            zbuf[k * NC + c] = z;
+                        }
                     }
                 }
-                zbuf[idx] = z;
             }
             __syncthreads();
-            // v = C z, one warp per row: lane = 16*h + c handles column c and every second entry of the row
-            // (h = 0/1), eight independent loads in flight per lane; the halves are combined with a shuffle.
+            {   // A2, rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread
+                const int c = tid % NC;
+                const bool okc = sh.c_rep[c] >= 0;
+                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                const int istep = nthr / NC;
+                for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
+                    int col[8]; cplx val[8], zz[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * istep;
+                        col[u] = (okc && i < K) ? sd.row_col0[i] : -1;
+                        val[u] = (okc && i < K) ? sd.row_val0[i] : cmake(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) zz[u] = col[u] >= 0 ? zbuf[col[u] * NC + c] : cmake(0.0, 0.0);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * istep;
+                        if (i < K && col[u] != -2) vbuf[i * NC + c] = cmul(val[u], zz[u]);
+                    }
+                }
+            }
+            // A2, long rows (auxiliary symbols, spread symbols): one warp per row, lane = 16*h + c handles column c
+            // and every second entry (h = 0/1), eight independent loads in flight; halves combined by shuffle.
             {
                 const int c = lane & 15, h = lane >> 4;
                 const bool okc = sh.c_rep[c] >= 0;
@@ -743,9 +846,13 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
                 const int* __restrict__ rp = sd.c_rowptr;
                 const int* __restrict__ cc = sd.c_col;
                 const cplx* __restrict__ cv = sd.c_val;
-                for (int i = warp; i < K; i += nwarp) {
+                int nl = 0;
+                for (int q = 0; q < cta.n_cols; ++q) nl = max(nl, p.sch[sh.c_scheme[q]].n_long_rows);
+                for (int r = warp; r < nl; r += nwarp) {
+                    const bool okr = okc && r < sd.n_long_rows;
+                    const int i = okr ? sd.long_rows[r] : 0;
                     cplx acc = cmake(0.0, 0.0);
-                    if (okc) {
+                    if (okr) {
                         const int e1 = rp[i + 1];
                         int e = rp[i] + h;
                         for (; e + 14 < e1; e += 16) {
@@ -759,7 +866,7 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
                     }
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-                    if (h == 0) vbuf[i * NC + c] = acc;
+                    if (okr && h == 0) vbuf[i * NC + c] = acc;
                 }
             }
         }
@@ -804,8 +911,8 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
                                              hPs, vbuf, ybuf, sh.ycolp, K, sd.P4, warp, nwarp, lane);
             } else {
                 const cplx* Dm = p.D[wf] + (int64_t)cta.snr * (((K + 7) / 8) * 8) * K;     // cta.snr holds the realization
-                if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, ring, vstage, K, 0, 1, warp, nwarp, lane, tid, nthr);
-                else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, ring, vstage, K, 0, 1, warp, nwarp, lane, tid, nthr);
+                if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, vstage, K, warp, nwarp, lane, tid, nthr);
+                else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, vstage, K, warp, nwarp, lane, tid, nthr);
             }
         }
         IC_TRACE(3, gtime()); IC_TRACE(7, n_done);
@@ -832,10 +939,10 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
         // ---- phase C: LS pilot estimates from the (cancelled) symbols   (DS.m:412-414, 487-489)
         if (csi == 0) {
             const SchemeDev& sd = p.sch[cta.scheme_or_wf];
-            for (int idx = tid; idx < sd.P * NC; idx += nthr) {
+            for (int idx = tid; idx < sd.P4 * 4 * NC; idx += nthr) {      // rows P..4*P4-1: zero padding for the DMMA
                 int c = idx % NC, pp = idx / NC;
                 cplx hp = cmake(0.0, 0.0);
-                if (sh.c_rep[c] >= 0) {
+                if (sh.c_rep[c] >= 0 && pp < sd.P) {
                     cplx q = cdiv(yic(sd.pilot_pos[pp], c), sd.xP[(int64_t)sh.c_rep[c] * sd.P + pp]);
                     hp = cmake(q.x / sd.sqrt_kappa, q.y / sd.sqrt_kappa);
                     sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] = hp;
@@ -847,31 +954,67 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
         // ---- phase D: one-tap channel + equalisation                  (DS.m:428-429, 515-521)
         {
             const int var_cur = (it == 0 || it <= p.n_iter / 2) ? 0 : 1;
-            for (int idx = tid; idx < K * NC; idx += nthr) {
-                int c = idx % NC, i = idx / NC;
-                cplx xh = cmake(0.0, 0.0);
-                if (sh.c_rep[c] >= 0) {
-                    const SchemeDev& sd = p.sch[sh.c_scheme[c]];
-                    cplx hh;
-                    if (csi == 0) {
-                        const cplx* __restrict__ wd = sd.w[var_cur][sh.c_snr[c]].diag + (int64_t)i * sd.P;
-                        hh = cmake(0.0, 0.0);
-                        int pp = 0;
-                        for (; pp + 8 <= sd.P; pp += 8) {              // eight independent loads in flight
-                            cplx w8[8];
+            if (csi == 0) {
+                // h_est = W_diag * hP as a small DMMA product per row tile (A = W[i,i,p] fragments, B = hP_new),
+                // then x_hat = y_ic / h_est on the C fragment
+                const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+                const int g = lane >> 2, t4 = lane & 3, RT = (K + 7) / 8, P4 = sd.P4;
+                const cplx* __restrict__ wf_ = sd.wdiag_frag[var_cur] + (int64_t)cta.snr * RT * P4 * 32;
+                for (int rt = warp; rt < RT; rt += nwarp) {
+                    double hr[2][2] = {{0, 0}, {0, 0}}, hi[2][2] = {{0, 0}, {0, 0}};
+                    const int i = rt * 8 + g;
+                    cplx yv[2][2];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) w8[u] = __ldg(wd + pp + u);
+                    for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) cfma(hh, w8[u], hPn[(pp + u) * HS + c]);
+                        for (int e = 0; e < 2; ++e) yv[ct][e] = i < K ? yic(i, ct * 8 + 2 * t4 + e) : cmake(0.0, 0.0);
+                    for (int pq = 0; pq < P4; ++pq) {
+                        const cplx a = ld_stream(wf_ + ((int64_t)rt * P4 + pq) * 32 + lane);
+                        const double nai = dneg(a.y);
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct) {
+                            const cplx b = hPn[(pq * 4 + t4) * HS + ct * 8 + g];
+                            dmma884(hr[ct][0], hr[ct][1], a.x, b.x);
+                            dmma884(hr[ct][0], hr[ct][1], nai, b.y);
+                            dmma884(hi[ct][0], hi[ct][1], a.x, b.y);
+                            dmma884(hi[ct][0], hi[ct][1], a.y, b.x);
                         }
-                        for (; pp < sd.P; ++pp) cfma(hh, __ldg(wd + pp), hPn[pp * HS + c]);
-                        sd.hdiag[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * K + i] = hh;
-                    } else {
-                        hh = p.htrue[wf][(int64_t)sh.c_rep[c] * K + i];
                     }
-                    xh = cdiv(yic(i, c), hh);
+                    if (i < K) {
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = ct * 8 + 2 * t4 + e;
+                                cplx xh = cmake(0.0, 0.0);
+                                if (sh.c_rep[c] >= 0) {
+                                    const cplx hh = cmake(hr[ct][e], hi[ct][e]);
+                                    sd.hdiag[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * K + i] = hh;
+                                    xh = cdiv(yv[ct][e], hh);
+                                }
+                                vbuf[i * NC + c] = xh;
+                            }
+                    }
                 }
-                vbuf[idx] = xh;
+            } else {
+                const int c = tid % NC;
+                const bool okc = sh.c_rep[c] >= 0;
+                const cplx* __restrict__ ht = p.htrue[wf] + (int64_t)(okc ? sh.c_rep[c] : 0) * K;
+                const int istep = nthr / NC;
+                for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
+                    cplx yv[8], hv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * istep;
+                        yv[u] = (okc && i < K) ? yic(i, c) : cmake(0.0, 0.0);
+                        hv[u] = (okc && i < K) ? ht[i] : cmake(1.0, 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * istep;
+                        if (i < K) vbuf[i * NC + c] = okc ? cdiv(yv[u], hv[u]) : cmake(0.0, 0.0);
+                    }
+                }
             }
             __syncthreads();
         }
@@ -898,9 +1041,20 @@ __global__ void __launch_bounds__(256, 2) k_ic(IcParams p) {
                             if (sd.detect_mode == 1) {
                                 cplx acc = cmake(0.0, 0.0);
                                 const int k = sd.P + d;
-                                for (int e = sd.ct_colptr[k]; e < sd.ct_colptr[k + 1]; ++e) {
-                                    cplx t = cmulc(sd.ct_val[e], vbuf[sd.ct_row[e] * NC + c]);
-                                    acc.x += t.x; acc.y += t.y;
+                                const int e1 = sd.ct_colptr[k + 1];
+                                for (int e = sd.ct_colptr[k]; e < e1; e += 8) {
+                                    cplx cvv[8], xx[8];
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        const bool in = e + q < e1;
+                                        cvv[q] = in ? sd.ct_val[e + q] : cmake(0.0, 0.0);
+                                        xx[q] = in ? vbuf[sd.ct_row[e + q] * NC + c] : cmake(0.0, 0.0);
+                                    }
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        cplx t = cmulc(cvv[q], xx[q]);
+                                        acc.x += t.x; acc.y += t.y;
+                                    }
                                 }
                                 xd[u] = cmake(acc.x / sd.dpr, 0.0);
                             } else {

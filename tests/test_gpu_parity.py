@@ -246,3 +246,53 @@ def test_golden_error_counts(gpu_ctx):
     g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ds_default_seeded_errors.json")))
     err = gpu_ctx.run_batch(len(g["reps"]), g["n_iter"], None, seed=g["seed"], first_rep=g["first_rep"])
     assert np.array_equal(err, np.array(g["err"], dtype=np.uint32))
+
+
+@pytest.fixture(scope="module")
+def ds_paper():
+    """Paper geometry (DS.m:42-46: fs = 2.94 MHz, 2 subframes -> N = 7350, K = 1440 / 672, 32 pilots, 6 taps) with two
+    SNR points to keep the oracle setup around a minute."""
+    from oracle.ds import DSConfig, ds_setup
+    return ds_setup(DSConfig(M_SNR_dB=(20, 36), SamplingRate=15e3 * 14 * 14, NrSubframes=2))
+
+
+def test_paper_geometry_parity(ds_paper):
+    """BASELINE.json config 3 geometry: P = 32 (eight pilot quads per tile), 6 non-zero taps with gaps, K = 1440."""
+    from oracle.ds import ds_realization, new_draws
+    from tests.helpers import context_from_oracle
+    S = ds_paper
+    assert (S["N"], S["P"], S["wf"]["F"]["K"], S["wf"]["O"]["K"]) == (7350, 32, 1440, 672)
+    assert list(S["chan"].Implementation["IndexDelayTaps"]) == [0, 1, 2, 3, 5, 7]
+    ctx = context_from_oracle(S, max_batch=2)
+    rng = np.random.default_rng(77)
+    draws = [new_draws(S, rng) for _ in range(2)]
+    st, keep = ctx.pack_draws(draws)
+    err = ctx.run_batch(2, 4, st)
+    out = [ds_realization(S, d, keep=True) for d in draws]
+    for r in range(2):
+        assert np.array_equal(err[r], err_from_oracle(out[r], 4))
+        for sc in S["schemes"]:
+            assert rel(ctx.get_state("hP", sc, r, 1), out[r]["inter"]["hP_" + sc][1][-1]) < TOL
+            assert rel(ctx.get_state("xD_est", sc, r, 1), out[r]["inter"]["xD_est_" + sc][1][-1]) < 1e-7
+    ctx.new_realization(draws[1]["doppler_u"].reshape(1, -1, order="F"), draws[1]["phase_u"].reshape(1, -1, order="F"))
+    assert rel(ctx.impulse_response(0), out[1]["inter"]["h"]) < 1e-12
+    for wf in ("F", "O"):
+        D, h = ctx.transmission_matrix(wf, 0)
+        assert rel(D, out[1]["inter"]["D_" + wf]) < TOL
+    ctx.close()
+
+
+def test_velocity_sweep_setup(ds_default):
+    """BASELINE.json config 4: the MMSE matrices depend on the velocity through R_t (FF.m:333); the product's setup at
+    another velocity must match the oracle's, and the loop must agree on the same draws."""
+    from chest_b200.simulation import DoublySelectiveSimulation
+    from oracle.ds import DSConfig, ds_setup, ds_realization, new_draws
+    S = ds_setup(DSConfig(Velocity_kmh=120, schemes=("ofdm",), M_SNR_dB=(15, 30), NrIterations=2))
+    sim = DoublySelectiveSimulation(Velocity_kmh=120, schemes=("ofdm",), M_SNR_dB=(15, 30), NrIterations=2, max_batch=4)
+    assert abs(sim.ChannelModel.PHY["MaximumDopplerShift"] - S["fD"]) < 1e-9
+    assert rel(sim.wfs["O"]["R_hP"], S["wf"]["O"]["R_hP"]) < TOL
+    draws = [new_draws(S, np.random.default_rng(5)) for _ in range(2)]
+    ber, err = sim.run(NrRepetitions=2, draws=draws)
+    for r in range(2):
+        assert np.array_equal(err[r, :, :, 2], err_from_oracle(ds_realization(S, draws[r]), 2)[:, :, 2])
+    sim.close()
