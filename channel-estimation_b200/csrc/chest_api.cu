@@ -52,7 +52,8 @@ struct Waveform {
     bool set = false;
     int K = 0;
     DevBuf<cplx> G, Q, Gt;
-    DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi;
+    DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi, d_jlo, d_jhi;
+    double d_struct_pairs = 0;   // (i,j) pairs of D inside the structural support
     std::vector<int> g_lo, g_hi, q_lo, q_hi;
     int nsch = 0; int sch[2] = {0, 0};
     // batch state
@@ -368,6 +369,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         ip.wf_nscheme[wfi] = c->wf[wfi].nsch;
         ip.wf_scheme[wfi][0] = c->wf[wfi].sch[0]; ip.wf_scheme[wfi][1] = c->wf[wfi].sch[1];
         ip.D[wfi] = c->wf[wfi].D.p; ip.htrue[wfi] = c->wf[wfi].htrue.p;
+        ip.d_jlo[wfi] = c->wf[wfi].d_jlo.p; ip.d_jhi[wfi] = c->wf[wfi].d_jhi.p;
     }
     ip.scratch = c->scratch.p;
     ip.pilot_rows = 4;
@@ -464,7 +466,7 @@ int chest_destroy(uint64_t handle) {
     // DevBuf has no destructor on purpose (plain members); release explicitly
     auto relw = [](Waveform& w) {
         w.G.release(); w.Q.release(); w.Gt.release(); w.q_klo.release(); w.q_khi.release(); w.gt_klo.release();
-        w.gt_khi.release(); w.hg_klo.release(); w.hg_khi.release(); w.x.release(); w.s.release(); w.r0.release();
+        w.gt_khi.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
         w.y.release(); w.D.release(); w.htrue.release(); w.HG.release();
     };
     relw(c->wf[0]); relw(c->wf[1]);
@@ -784,6 +786,19 @@ int chest_finalize(uint64_t handle, int max_batch) {
                 if (b > a) f += 8.0 * (b - a);
             }
         w.flops_d = f;
+        {   // structural column range of D per 8-row tile: j with supp(Q_i) ^ supp((HG)_j) non-empty for some row i
+            const int RT = (K + 7) / 8;
+            std::vector<int> jlo(RT, K), jhi(RT, 0);
+            double pairs = 0;
+            for (int i = 0; i < K; ++i)
+                for (int j = 0; j < K; ++j) {
+                    int a = std::max(w.q_lo[i], w.g_lo[j]), b = std::min(w.q_hi[i], std::min(N, w.g_hi[j] + max_delay));
+                    if (b > a) { jlo[i >> 3] = std::min(jlo[i >> 3], j); jhi[i >> 3] = std::max(jhi[i >> 3], j + 1); if (i != j) pairs += 1; }
+                }
+            for (int r = 0; r < RT; ++r) if (jhi[r] <= jlo[r]) { jlo[r] = 0; jhi[r] = 0; }
+            CK(w.d_jlo.upload(jlo, c->stream)); CK(w.d_jhi.upload(jhi, c->stream));
+            w.d_struct_pairs = pairs;
+        }
         double fq = 0, fg = 0;
         for (int i = 0; i < K; ++i) { fq += 8.0 * (w.q_hi[i] - w.q_lo[i]); fg += 8.0 * (w.g_hi[i] - w.g_lo[i]); }
         w.flops_demod = fq; w.flops_mod = fg;
@@ -1136,7 +1151,7 @@ int chest_work_model(uint64_t handle, int n_iter, double* out) {
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch) continue;
         out[0] += w.flops_d;                                                   // K2
-        out[2] += 8.0 * ((double)w.K * w.K - w.K) * w.nsch * S * n_iter;        // perfect CSI (D - diag h) v
+        out[2] += 8.0 * w.d_struct_pairs * w.nsch * S * n_iter;              // perfect CSI (D - diag h) v over D's structural support
         out[3] += w.nsch * (w.flops_mod + 8.0 * c->T * c->N) + w.nsch * S * w.flops_demod;   // TX + demod
     }
     for (int si = 0; si < 3; ++si) {

@@ -414,7 +414,8 @@ struct IcParams {
     SchemeDev sch[3];
     ConstDev cst[2];
     int wf_scheme[2][2]; int wf_nscheme[2];
-    const cplx* D[2];          // [rep][K*K] true transmission matrices
+    const cplx* D[2];          // [rep][K/8][K][8] true transmission matrices (row-tile-major)
+    const int* d_jlo[2]; const int* d_jhi[2];   // per row tile: structural column range of D
     const cplx* htrue[2];      // [rep][K]
     cplx* scratch;             // per CTA: 3 buffers of K_max*NC_MAX
     uint32_t* err;             // [rep][snr][it][scheme][csi][edge]
@@ -639,14 +640,19 @@ __device__ __forceinline__ void est_interference_generic(const cplx* __restrict_
 #define PERF_CHUNK 16
 template <int NCT>
 __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
-                                                  const cplx* const* ycolp, cplx* vs, int K, int warp, int nwarp,
+                                                  const cplx* const* ycolp, cplx* vs, const int* __restrict__ rt_jlo,
+                                                  const int* __restrict__ rt_jhi, int K, int warp, int nwarp,
                                                   int lane, int tid, int nthr) {
     constexpr int NC = NC_MAX, U = PERF_CHUNK / 4, VS = NC + 2;
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
-    const int nchunk = (K + PERF_CHUNK - 1) / PERF_CHUNK;
     const int nblk = (RT + nwarp - 1) / nwarp;
     for (int blk = 0; blk < nblk; ++blk) {
+        // columns outside [jlo, jhi) are structurally zero for every row of this block (no support overlap
+        // between Q_i and H G_j): they are skipped exactly
+        int jlo = K, jhi = 0;
+        for (int r = blk * nwarp; r < min(RT, (blk + 1) * nwarp); ++r) { jlo = min(jlo, rt_jlo[r]); jhi = max(jhi, rt_jhi[r]); }
+        const int ch0 = jlo / PERF_CHUNK, nchunk = jhi > jlo ? (jhi + PERF_CHUNK - 1) / PERF_CHUNK : ch0;
         const int rt = blk * nwarp + warp;
         const bool active = rt < RT;
         double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
@@ -668,10 +674,10 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
             cp_async_commit();
         };
         __syncthreads();                                       // previous row block done with both stages
-        issue(0, 0);
+        if (ch0 < nchunk) issue(ch0 & 1, ch0);
         cp_async_wait_group<0>();
         __syncthreads();
-        for (int ch = 0; ch < nchunk; ++ch) {
+        for (int ch = ch0; ch < nchunk; ++ch) {
             const int s = ch & 1;
             cplx a[U];
 #pragma unroll
@@ -911,8 +917,8 @@ __global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
                                              hPs, vbuf, ybuf, sh.ycolp, K, sd.P4, warp, nwarp, lane);
             } else {
                 const cplx* Dm = p.D[wf] + (int64_t)cta.snr * (((K + 7) / 8) * 8) * K;     // cta.snr holds the realization
-                if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, vstage, K, warp, nwarp, lane, tid, nthr);
-                else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, vstage, K, warp, nwarp, lane, tid, nthr);
+                if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid, nthr);
+                else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid, nthr);
             }
         }
         IC_TRACE(3, gtime()); IC_TRACE(7, n_done);
