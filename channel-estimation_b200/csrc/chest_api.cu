@@ -266,8 +266,13 @@ int build_ctas(Ctx* c, int n_rep) {
         if (!strcmp(dbg, "est_fbmc")) { p1.clear(); p2.clear(); e2.clear(); }
         if (!strcmp(dbg, "perf_fbmc")) { e1.clear(); e2.clear(); p2.clear(); }
     }
-    weave(e1, p1);
-    weave(e2, p2);
+    if (getenv("CHEST_IC_WEAVE")) {                            // development: interleave compute- and memory-heavy units
+        weave(e1, p1);
+        weave(e2, p2);
+    } else {                                                   // longest units first: the short ones fill the tail of the queue
+        v.insert(v.end(), e1.begin(), e1.end()); v.insert(v.end(), p1.begin(), p1.end());
+        v.insert(v.end(), e2.begin(), e2.end()); v.insert(v.end(), p2.begin(), p2.end());
+    }
     c->n_ctas = (int)v.size();
     CK(c->ctas.upload(v, c->stream));
     CK(c->scratch.alloc((size_t)c->n_ctas * 3 * c->K_max * NC_MAX));

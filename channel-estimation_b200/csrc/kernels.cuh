@@ -633,17 +633,18 @@ __device__ __forceinline__ void est_interference_generic(const cplx* __restrict_
 
 // ---- phase B, perfect CSI: acc[i, c] = sum_{j != i} D[i, j] v[j, c]   (DS.m:541-543)
 // A mini-GEMM per CTA: the warps take one row tile each (a "row block" of nwarp row tiles) and walk the
-// columns j together in chunks of 16.  The v chunk (B operand) is staged ONCE per chunk in shared memory
+// columns j together in chunks of 32.  The v chunk (B operand) is staged ONCE per chunk in shared memory
 // for all warps (cp.async, two stages, padded rows -> conflict-free LDS.128); each warp streams its own
-// row tile of the row-tile-major D (A operand: 512 contiguous bytes per k-step) through registers, one
-// chunk ahead.
-#define PERF_CHUNK 16
+// row tile of the row-tile-major D (A operand: 512 contiguous bytes per k-step) through registers, 16
+// columns ahead.
+#define PERF_CHUNK 32          // v rows staged per barrier
+#define PERF_DSUB 16           // D columns prefetched in registers at a time
 template <int NCT>
 __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
                                                   const cplx* const* ycolp, cplx* vs, const int* __restrict__ rt_jlo,
                                                   const int* __restrict__ rt_jhi, int K, int warp, int nwarp,
                                                   int lane, int tid, int nthr) {
-    constexpr int NC = NC_MAX, U = PERF_CHUNK / 4, VS = NC + 2;
+    constexpr int NC = NC_MAX, U = PERF_DSUB / 4, NSUB = PERF_CHUNK / PERF_DSUB, VS = NC + 2;
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
     const int nblk = (RT + nwarp - 1) / nwarp;
@@ -659,14 +660,16 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
         const int i = rt * 8 + g;
         const cplx* Drt = Dm + (int64_t)(active ? rt : 0) * K * 8 + g;
         cplx an[U];
-        auto issue = [&](int s, int ch) {
+        auto load_d = [&](int j0) {                            // 16 columns of this warp's row tile -> registers
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                int j = ch * PERF_CHUNK + 4 * u + t4;
+                int j = j0 + 4 * u + t4;
                 j = j < K ? j : K - 1;                         // out-of-range columns are masked at use
                 an[u] = active ? ld_stream(Drt + (int64_t)j * 8) : cmake(0.0, 0.0);
             }
-            for (int e = tid; e < PERF_CHUNK * NC; e += nthr) {   // v chunk, shared by all warps
+        };
+        auto stage_v = [&](int s, int ch) {                    // v chunk, shared by all warps
+            for (int e = tid; e < PERF_CHUNK * NC; e += nthr) {
                 int jr = e / NC, c = e % NC, j = ch * PERF_CHUNK + jr;
                 j = j < K ? j : K - 1;
                 cp_async16_plain(vs + (s * PERF_CHUNK + jr) * VS + c, vbuf + j * NC + c);
@@ -674,27 +677,32 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
             cp_async_commit();
         };
         __syncthreads();                                       // previous row block done with both stages
-        if (ch0 < nchunk) issue(ch0 & 1, ch0);
+        if (ch0 < nchunk) { stage_v(ch0 & 1, ch0); load_d(ch0 * PERF_CHUNK); }
         cp_async_wait_group<0>();
         __syncthreads();
         for (int ch = ch0; ch < nchunk; ++ch) {
             const int s = ch & 1;
-            cplx a[U];
+            if (ch + 1 < nchunk) stage_v(s ^ 1, ch + 1);       // stage s^1 was last read before the previous barrier
 #pragma unroll
-            for (int u = 0; u < U; ++u) a[u] = an[u];
-            if (ch + 1 < nchunk) issue(s ^ 1, ch + 1);         // stage s^1 was last read before the previous barrier
+            for (int sub = 0; sub < NSUB; ++sub) {
+                cplx a[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                int j = ch * PERF_CHUNK + 4 * u + t4;
-                if (i >= K || j >= K || i == j) a[u] = cmake(0.0, 0.0);
-                const double nai = dneg(a[u].y);
+                for (int u = 0; u < U; ++u) a[u] = an[u];
+                const int jn = ch * PERF_CHUNK + (sub + 1) * PERF_DSUB;
+                if (jn < nchunk * PERF_CHUNK) load_d(jn);
 #pragma unroll
-                for (int ct = 0; ct < NCT; ++ct) {
-                    const cplx b = vs[(s * PERF_CHUNK + 4 * u + t4) * VS + ct * 8 + g];
-                    dmma884(accr[ct][0], accr[ct][1], a[u].x, b.x);
-                    dmma884(accr[ct][0], accr[ct][1], nai, b.y);
-                    dmma884(acci[ct][0], acci[ct][1], a[u].x, b.y);
-                    dmma884(acci[ct][0], acci[ct][1], a[u].y, b.x);
+                for (int u = 0; u < U; ++u) {
+                    int j = ch * PERF_CHUNK + sub * PERF_DSUB + 4 * u + t4;
+                    if (i >= K || j >= K || i == j) a[u] = cmake(0.0, 0.0);
+                    const double nai = dneg(a[u].y);
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct) {
+                        const cplx b = vs[(s * PERF_CHUNK + sub * PERF_DSUB + 4 * u + t4) * VS + ct * 8 + g];
+                        dmma884(accr[ct][0], accr[ct][1], a[u].x, b.x);
+                        dmma884(accr[ct][0], accr[ct][1], nai, b.y);
+                        dmma884(acci[ct][0], acci[ct][1], a[u].x, b.y);
+                        dmma884(acci[ct][0], acci[ct][1], a[u].y, b.x);
+                    }
                 }
             }
             cp_async_wait_group<0>();
