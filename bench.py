@@ -242,6 +242,14 @@ def run_b200(args):
         nb = ctx.bit_counts()
         ber40 = {name: float(tot[-1, -1, sid * 4].item()) / float(nb[sid, 0] * B * world)
                  for name, sid in chest_b200.context.SCHEME_ID.items() if name in sim.sch}
+        traffic, traffic_note = None, None
+        try:                                                       # ncu --set full capture, scaled to this batch size
+            tj = json.load(open(os.path.join(ROOT, "profiles", "kic_traffic.json")))
+            traffic = tj["dram_bytes_per_launch"] * B / tj["batch"]
+            traffic_note = "dram__bytes_read+write per k_ic launch from %s, scaled x%.2f to batch %d" % (
+                tj["source"], B / tj["batch"], B)
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": world * B * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -258,9 +266,10 @@ def run_b200(args):
                     "api": "chest_run_batch (C ABI) with pinned host buffers: explicit draws in, error counts out"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_ic (fused IC iteration: W(hP) v and (D - diag h) v on FP64 DMMA)",
+            "roofline": {"kernel": "k_ic (one persistent launch per IC iteration: W(hP) v and (D - diag h) v on FP64 DMMA)",
                          "bound": "tensor", "achieved": ic_flops / (ic_ms * 1e-3) / 1e12, "peak": peak_dmma,
-                         "unit": "TFLOP/s", "frac": ic_flops / (ic_ms * 1e-3) / 1e12 / peak_dmma, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ic_flops / (ic_ms * 1e-3) / 1e12 / peak_dmma, "traffic": traffic,
+                         "traffic_note": traffic_note,
                          "peak_source": "measured in this run: register-resident FP64 DMMA (m8n8k4) loop on every SM "
                                         "(chest_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; DFMA probe %.1f TFLOP/s"
                                         % peak_dfma,
