@@ -179,10 +179,13 @@ def run_b200(args):
     launches0 = ctx.launch_count()
     ctx.event_record(0)
     t_wall = time.perf_counter()
+    hg_ms, hg_bytes = 0.0, 0.0
     for _ in range(K):
         step_resident()
         for k, v in ctx.stage_times().items():
             stage_sum[k] = stage_sum.get(k, 0.0) + v
+        a, b = ctx.banded_apply_stats()
+        hg_ms, hg_bytes = hg_ms + a, hg_bytes + b
     ctx.event_record(1)
     dev_ms = ctx.event_elapsed_ms(0, 1)
     barrier()
@@ -242,6 +245,11 @@ def run_b200(args):
         nb = ctx.bit_counts()
         ber40 = {name: float(tot[-1, -1, sid * 4].item()) / float(nb[sid, 0] * B * world)
                  for name, sid in chest_b200.context.SCHEME_ID.items() if name in sim.sch}
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (MEASURED_PEAKS.json absent)"
         traffic, traffic_note = None, None
         try:                                                       # ncu --set full capture, scaled to this batch size
             tj = json.load(open(os.path.join(ROOT, "profiles", "kic_traffic.json")))
@@ -278,6 +286,10 @@ def run_b200(args):
                             "achieved": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12, "peak": peak_dmma, "unit": "TFLOP/s",
                             "frac": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12 / peak_dmma,
                             "algorithmic_flops_per_launch": B * wm["k2_flops"], "avg_launch_ms": k2_ms},
+            "roofline_k1": {"kernel": "k_apply_hg (banded, never-materialised H applied to G)", "bound": "hbm",
+                            "achieved": hg_bytes / (hg_ms * 1e-3) / 1e9 if hg_ms > 0 else None, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": hg_bytes / (hg_ms * 1e-3) / 1e9 / hbm_peak if hg_ms > 0 else None,
+                            "peak_source": hbm_src, "algorithmic_bytes_per_step": hg_bytes / K, "ms_per_step": hg_ms / K},
             "stage_ms_per_step": {k: v / K for k, v in stage_sum.items()},
             "wall_ms_per_step": wall_ms / K, "launches_per_step": launches_per_step, "setup_s": setup_s,
             "sanity_ber_40dB_last_iteration": ber40,

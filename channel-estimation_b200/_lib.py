@@ -57,6 +57,7 @@ SIGNATURES = {
     "chest_launch_count": (c_i64, [c_u64]),
     "chest_set_profiling": (c_int, [c_u64, c_int]),
     "chest_stage_times": (c_int, [c_u64, p_f]),
+    "chest_banded_apply_stats": (c_int, [c_u64, p_f, p_d]),
     "chest_work_model": (c_int, [c_u64, c_int, p_d]),
     "chest_event_record": (c_int, [c_u64, c_int]),
     "chest_event_elapsed": (c_int, [c_u64, c_int, c_int, p_f]),

@@ -271,6 +271,11 @@ class DeviceContext:
         return dict(zip(("draws", "k1_channel_tx", "k2_transmission_matrix", "k3_demod", "one_tap", "ic_iterations",
                          "total"), [float(x) for x in ms]))
 
+    def banded_apply_stats(self):
+        ms, by = C.c_float(0), C.c_double(0)
+        self._check(self.lib.chest_banded_apply_stats(self._h, C.byref(ms), C.byref(by)))
+        return float(ms.value), float(by.value)
+
     def event_record(self, slot):
         self._check(self.lib.chest_event_record(self._h, slot))
 

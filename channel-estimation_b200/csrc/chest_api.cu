@@ -55,6 +55,7 @@ struct Waveform {
     DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi, d_jlo, d_jhi;
     double d_struct_pairs = 0;   // (i,j) pairs of D inside the structural support
     std::vector<int> g_lo, g_hi, q_lo, q_hi;
+    std::vector<double> hg_rows;   // per column: rows of H*G written by k_apply_hg
     int nsch = 0; int sch[2] = {0, 0};
     // batch state
     DevBuf<cplx> x, s, r0, y, D, htrue, HG;
@@ -118,6 +119,8 @@ struct Ctx {
     int64_t launches = 0;
     bool profiling = false;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_hg[4] = {};   // k_apply_hg of the two waveforms (profiling)
+    float hg_ms = 0; double hg_bytes = 0;
     cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     DevBuf<double> probe;
@@ -222,10 +225,12 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     p.bsrc = w.HG.p; p.ldb = c->N; p.N = c->N;
     p.nt_klo = w.hg_klo.p; p.nt_khi = w.hg_khi.p; p.hdiag = w.htrue.p; p.rep0 = rep0;
     dim3 ghg(2, w.K, n_rep);
+    if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_hg[2 * wfi], c->stream));
     k_apply_hg<<<ghg, 128, 0, c->stream>>>(w.HG.p, w.G.p, c->h.p, c->d_tap_delay.p, w.hg_klo.p, w.hg_khi.p,
                                            c->N, w.K, c->T, rep0, w.tile);
     c->launches++;
     CK(cudaGetLastError());
+    if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_hg[2 * wfi + 1], c->stream));
     CK(launch_gemm<GEMM_D>(c, p, n_rep, w.tile));
     return CHEST_OK;
 }
@@ -425,6 +430,18 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     if (c->profiling) {
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&c->stage_ms[6], c->ev[0], c->ev[6]);
+        c->hg_ms = 0; c->hg_bytes = 0;
+        for (int wfi = 0; wfi < 2; ++wfi) {
+            Waveform& w = c->wf[wfi];
+            if (!w.set || !w.nsch) continue;
+            float t = 0;
+            cudaEventElapsedTime(&t, c->ev_hg[2 * wfi], c->ev_hg[2 * wfi + 1]);
+            c->hg_ms += t;
+            // algorithmic bytes of the banded apply to G: write H*G over each column tile's k-range, read h once
+            double rows = 0;
+            for (size_t tcol = 0; tcol < w.hg_rows.size(); ++tcol) rows += w.hg_rows[tcol];
+            c->hg_bytes += 16.0 * (rows * n_rep + (double)c->T * N * n_rep);
+        }
     }
     return CHEST_OK;
 }
@@ -459,6 +476,7 @@ int chest_create(int device, uint64_t* handle) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     for (auto& e : c->user_ev) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_hg) CK(cudaEventCreate(&e));
     *handle = (uint64_t)(uintptr_t)c;
     return CHEST_OK;
 }
@@ -491,6 +509,7 @@ int chest_destroy(uint64_t handle) {
     c->err.release(); c->scratch.release(); c->tmp_a.release(); c->tmp_b.release(); c->ctas.release(); c->probe.release(); c->queue.release();
     for (auto& e : c->ev) cudaEventDestroy(e);
     for (auto& e : c->user_ev) cudaEventDestroy(e);
+    for (auto& e : c->ev_hg) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return CHEST_OK;
@@ -782,6 +801,8 @@ int chest_finalize(uint64_t handle, int max_batch) {
         std::vector<int> lo, hi;
         tile_ranges(w.g_lo, w.g_hi, w.tile, max_delay, N, lo, hi);
         CK(w.hg_klo.upload(lo, c->stream)); CK(w.hg_khi.upload(hi, c->stream));
+        w.hg_rows.assign(K, 0.0);
+        for (int j = 0; j < K; ++j) w.hg_rows[j] = std::max(0, hi[j / w.tile] - lo[j / w.tile]);
         // support-aware work model: 8 T supp_G K  +  8 sum |supp(Q_i) ^ supp((HG)_j)|
         double f = 0;
         for (int j = 0; j < K; ++j) f += 8.0 * c->T * (w.g_hi[j] - w.g_lo[j]);
@@ -1144,6 +1165,12 @@ int chest_stage_times(uint64_t handle, float* ms) {
     Ctx* c = from(handle);
     ARG(c && ms);
     for (int i = 0; i < 7; ++i) ms[i] = c->stage_ms[i];
+    return CHEST_OK;
+}
+int chest_banded_apply_stats(uint64_t handle, float* ms, double* bytes) {
+    Ctx* c = from(handle);
+    ARG(c && ms && bytes);
+    *ms = c->hg_ms; *bytes = c->hg_bytes;
     return CHEST_OK;
 }
 

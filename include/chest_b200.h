@@ -190,6 +190,9 @@ int64_t chest_launch_count(uint64_t handle);
  * [4] one-tap stage, [5] IC iterations, [6] total.  Requires chest_set_profiling(handle, 1). */
 int chest_set_profiling(uint64_t handle, int enable);
 int chest_stage_times(uint64_t handle, float* ms /* [7] */);
+/* K1 banded operator applied to G (k_apply_hg) in the last profiled chest_run_batch: device time (ms) and
+ * algorithmic bytes (H*G rows written + h read), for the HBM roofline of the banded path. */
+int chest_banded_apply_stats(uint64_t handle, float* ms, double* bytes);
 /* Algorithmic work of one realization for the roofline:
  * [0] K2 support-aware flops, [1] K3/K4 estimated-CSI flops per iteration-evaluation set,
  * [2] perfect-CSI flops, [3] demod/TX flops, [4] bytes of W streamed per IC kernel launch. */

@@ -296,3 +296,80 @@ def test_velocity_sweep_setup(ds_default):
     for r in range(2):
         assert np.array_equal(err[r, :, :, 2], err_from_oracle(ds_realization(S, draws[r]), 2)[:, :, 2])
     sim.close()
+
+
+def test_simple_version_doubly_flat_chain():
+    """BASELINE.json config 1 (SimpleVersion_DoublyFlat.m:89-176) through the product's package API: FBMC / OFDM
+    Modulation and Demodulation on the GPU, auxiliary-symbol and data-spreading precoders, LS pilot estimates and
+    interpolation.  Checks: the GPU modem equals the oracle's FFT modem on the same symbols, and the perfect-CSI
+    BER matches the closed-form theory curve (Theory/BitErrorProbabilityDoublyFlatRayleigh.m) within Monte-Carlo error."""
+    import chest_b200
+    from oracle.fbmc import FBMC as RefFBMC
+    from oracle.ofdm import OFDM as RefOFDM
+    from oracle.bep import bit_error_probability_doubly_flat_rayleigh as bep
+    M = chest_b200.Modulation
+    CE = chest_b200.ChannelEstimation
+    fb = M.FBMC(12, 30, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, "Hermite-OQAM", 8, 0, True)          # SV.m:17-28
+    of = M.OFDM(12, 15, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, 0, (8 - 1 / 2) * 1 / 15e3 * 1 / 2)   # SV.m:31-40
+    pam, qam = M.SignalConstellation(4, "PAM"), M.SignalConstellation(16, "QAM")
+    ce_f = CE.PilotSymbolAidedChannelEstimation("Diamond", [[12, 6], [30, 8]], "linear")               # SV.m:57-66
+    ce_o = CE.PilotSymbolAidedChannelEstimation("Diamond", [[12, 6], [15, 4]], "linear")
+    D0 = fb.GetFBMCMatrix()
+    aux = CE.ImaginaryInterferenceCancellationAtPilotPosition("Auxiliary", ce_f.GetAuxiliaryMatrix(1), D0, 16, 2)
+    cod = CE.ImaginaryInterferenceCancellationAtPilotPosition("Coding", ce_f.PilotMatrix, D0, 16, 2)
+    assert fb.Nr["SamplesTotal"] == of.Nr["SamplesTotal"] == 3780 and ce_f.NrPilotSymbols == 8
+    rng = np.random.default_rng(12)
+    # --- GPU matrix-form modem vs the oracle's polyphase / IFFT modem (FBMC.m:255-315, OFDM.m:153-181)
+    rf = RefFBMC(12, 30, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, "Hermite-OQAM", 8, 0, True)
+    ro = RefOFDM(12, 15, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, 0, (8 - 1 / 2) * 1 / 15e3 * 1 / 2)
+    x = rng.standard_normal((12, 30))
+    s = fb.Modulation(x)
+    assert rel(s, rf.Modulation(x)) < 1e-12
+    assert rel(fb.Demodulation(s), rf.Demodulation(s)) < 1e-12
+    xo = rng.standard_normal((12, 15)) + 1j * rng.standard_normal((12, 15))
+    assert rel(of.Modulation(xo), ro.Modulation(xo)) < 1e-12 and rel(of.Demodulation(of.Modulation(xo)), xo) < 1e-12
+    # --- the SV.m loop at one SNR point, 60 repetitions
+    snr_db, reps = 20.0, 60
+    Pn = of.PHY["SamplingRate"] / (of.PHY["SubcarrierSpacing"] * of.Nr["Subcarriers"]) * 10 ** (-snr_db / 10)   # SV.m:92
+    P = ce_f.NrPilotSymbols
+    errs = {"aux": 0, "cod": 0, "fbmc_perfect": 0, "ofdm": 0, "ofdm_perfect": 0}
+    bits_tot = {"fbmc": 0, "ofdm": 0}
+    pmf, pmo = ce_f.PilotMatrix.reshape(-1, order="F"), ce_o.PilotMatrix.reshape(-1, order="F")
+    for _ in range(reps):
+        b_aux = rng.integers(0, 2, aux.NrDataSymbols * 2)
+        b_cod = rng.integers(0, 2, cod.NrDataSymbols * 2)
+        b_o = rng.integers(0, 2, (12 * 15 - ce_o.NrPilotSymbols) * 4)
+        xP = pam.SymbolMapping[rng.integers(0, 4, P)]; xP = xP / np.abs(xP)
+        xPo = qam.SymbolMapping[rng.integers(0, 16, ce_o.NrPilotSymbols)]; xPo = xPo / np.abs(xPo)
+        x_aux = (aux.PrecodingMatrix @ np.concatenate([xP, pam.Bit2Symbol(b_aux)])).reshape(12, 30, order="F")   # SV.m:111
+        x_cod = (cod.PrecodingMatrix @ np.concatenate([xP, pam.Bit2Symbol(b_cod)])).reshape(12, 30, order="F")
+        x_o = np.zeros(180, dtype=complex); x_o[pmo == 1] = xPo; x_o[pmo == 0] = qam.Bit2Symbol(b_o)
+        s3 = fb.Modulation(np.stack([x_aux, x_cod], axis=2))                                                     # SV.m:118-119
+        s_o = of.Modulation(x_o.reshape(12, 15, order="F"))
+        h = np.sqrt(0.5) * (rng.standard_normal() + 1j * rng.standard_normal())                                  # SV.m:123
+        n_f = np.sqrt(Pn / 2) * (rng.standard_normal(3780) + 1j * rng.standard_normal(3780))
+        n_o = np.sqrt(Pn / 2) * (rng.standard_normal(3780) + 1j * rng.standard_normal(3780))
+        y3 = fb.Demodulation(h * s3 + n_f[:, None])                                                              # SV.m:133-134
+        y_aux, y_cod = y3[:, :, 0].reshape(-1, order="F"), y3[:, :, 1].reshape(-1, order="F")
+        y_o = of.Demodulation(h * s_o + n_o).reshape(-1, order="F")
+        hP_aux = y_aux[pmf == 1] / xP / np.sqrt(aux.PilotToDataPowerOffset * aux.DataPowerReduction)             # SV.m:138-140
+        hP_cod = y_cod[pmf == 1] / xP / np.sqrt(cod.PilotToDataPowerOffset)
+        hP_o = y_o[pmo == 1] / xPo
+        h_aux = ce_f.ChannelInterpolation(hP_aux).reshape(-1, order="F")                                         # SV.m:143-145
+        h_cod = ce_f.ChannelInterpolation(hP_cod).reshape(-1, order="F")
+        h_o = ce_o.ChannelInterpolation(hP_o).reshape(-1, order="F")
+        am = aux.PilotMatrix.reshape(-1, order="F") == 0
+        eq_aux = np.real(y_aux[am] / h_aux[am] / np.sqrt(aux.DataPowerReduction))                                # SV.m:148-153
+        Cd = cod.PrecodingMatrix[:, P:]
+        eq_cod = np.real(Cd.conj().T @ (y_cod / h_cod))
+        eq_perf = np.real(Cd.conj().T @ (y_cod / h))
+        errs["aux"] += np.sum(pam.Symbol2Bit(eq_aux) != b_aux)
+        errs["cod"] += np.sum(pam.Symbol2Bit(eq_cod) != b_cod)
+        errs["fbmc_perfect"] += np.sum(pam.Symbol2Bit(eq_perf) != b_cod)
+        errs["ofdm"] += np.sum(qam.Symbol2Bit(y_o[pmo == 0] / h_o[pmo == 0]) != b_o)
+        errs["ofdm_perfect"] += np.sum(qam.Symbol2Bit(y_o[pmo == 0] / h) != b_o)
+        bits_tot["fbmc"] += len(b_cod); bits_tot["ofdm"] += len(b_o)
+    theory = bep([snr_db], qam.SymbolMapping, qam.BitMapping)[0]                                                 # SV.m:181
+    ber_fp, ber_op = errs["fbmc_perfect"] / bits_tot["fbmc"], errs["ofdm_perfect"] / bits_tot["ofdm"]
+    assert abs(ber_op - theory) < 0.6 * theory and abs(ber_fp - theory) < 0.6 * theory      # 60 fading draws: wide MC band
+    assert errs["cod"] >= errs["fbmc_perfect"] * 0.5 and errs["aux"] < 0.5 * aux.NrDataSymbols * 2 * reps
