@@ -124,7 +124,7 @@ struct Ctx {
     cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     DevBuf<double> probe;
-    DevBuf<unsigned int> queue; int ic_grid = 0; size_t ic_smem = 0;
+    DevBuf<unsigned int> queue; int ic_grid = 0, ic_light_grid = 0; size_t ic_smem = 0;
     DevBuf<unsigned long long> trace;
 };
 
@@ -387,20 +387,22 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     size_t cst_smem = 0;                                           // shared-memory copies of the constellation tables
     for (int k = 0; k < 2; ++k)
         cst_smem += sizeof(cplx) * ((size_t)c->cst[k].order + (c->cst[k].n_axis + 1) / 2 + (c->cst[k].order + 3) / 4);
-#ifndef IC_MIN_BLOCKS
-#define IC_MIN_BLOCKS 2
-#endif
-    const int ic_threads = 256;
+    const int ic_threads = IC_THREADS;
     ip.ring_cplx = (EST_WSRC == 0) ? EST_RING * (ip.pilot_rows / 4) * 32 : 0;   // EST_RING tiles of P4 fragments x 32 lanes
-    const size_t ic_smem = (size_t)2 * ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx)
-                           + (size_t)2 * PERF_CHUNK * (NC_MAX + 2) * sizeof(cplx) + cst_smem
-                           + (size_t)(ic_threads / 32) * ip.ring_cplx * sizeof(cplx);
-    if (c->ic_grid == 0 || c->ic_smem != ic_smem) {                // persistent grid: every CTA resident (cooperative launch)
-        CK(cudaFuncSetAttribute(k_ic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ic, ic_threads, ic_smem));
-        if (per_sm < 1) return fail(CHEST_ERR_STATE, "k_ic does not fit on an SM (too many pilots for the shared tables)");
-        c->ic_grid = per_sm * c->n_sm; c->ic_smem = ic_smem;
+    // main: pilot tables (2) + max(v-chunk stages of a PERF unit, W-fragment rings of an EST unit)
+    const size_t main_smem = (size_t)2 * ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx)
+                             + std::max((size_t)2 * PERF_STAGE_CPLX, (size_t)(ic_threads / 32) * ip.ring_cplx) * sizeof(cplx);
+    // light: new pilot estimates + constellation tables
+    const size_t light_smem = (size_t)ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx) + cst_smem;
+    if (c->ic_grid == 0 || c->ic_smem != main_smem) {              // persistent main grid: one wave of resident CTAs
+        CK(cudaFuncSetAttribute(k_ic_main, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CK(cudaFuncSetAttribute(k_ic_light, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        int per_sm = 0, per_sm_light = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ic_main, ic_threads, main_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, k_ic_light, ic_threads, light_smem));
+        if (per_sm < 1 || per_sm_light < 1)
+            return fail(CHEST_ERR_STATE, "the IC kernels do not fit on an SM (too many pilots for the shared tables)");
+        c->ic_grid = per_sm * c->n_sm; c->ic_light_grid = per_sm_light * c->n_sm; c->ic_smem = main_smem;
     }
     CK(c->queue.alloc(32));
     CK(cudaMemsetAsync(c->queue.p, 0, 32 * sizeof(unsigned int), st));
@@ -409,14 +411,21 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     uint32_t* err = err_dev ? err_dev : c->err.p;
     CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
     ip.err = err;
-    const char* trace_path = getenv("CHEST_IC_TRACE");             // development: per-CTA stage timestamps of the last iteration
-    if (trace_path) CK(c->trace.alloc((size_t)c->ic_grid * 8));
+    const char* trace_path = getenv("CHEST_IC_TRACE");             // development: per-CTA timestamps of the last main launch
+    if (trace_path) { CK(c->trace.alloc((size_t)c->ic_grid * 8)); CK(cudaMemsetAsync(c->trace.p, 0, (size_t)c->ic_grid * 64, st)); }
+    const int n_units = std::max(c->n_ctas, 1);
     for (int it = 0; it <= n_iter; ++it) {
         ip.it = it;
-        ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
-        void* args[] = {&ip};
-        CK(cudaLaunchCooperativeKernel((const void*)k_ic, dim3(std::min(c->ic_grid, std::max(c->n_ctas, 1))), dim3(ic_threads), args, ic_smem, st));
+        if (it > 0) {                                              // phase B of iteration it
+            ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
+            k_ic_main<<<std::min(c->ic_grid, n_units), ic_threads, main_smem, st>>>(ip);
+            c->launches++;
+            ip.trace = nullptr;
+        }
+        // phases C, D, E of iteration it (+ phase A of iteration it+1)
+        k_ic_light<<<std::min(c->ic_light_grid * IC_LIGHT_WAVES, n_units), ic_threads, light_smem, st>>>(ip);
         c->launches++;
+        CK(cudaGetLastError());
         if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev[5], st));
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[6], st));

@@ -35,6 +35,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// CHEST_3M: complex tile products on the tensor pipe use three real multiplications instead of four
+// ((ar+ai) br, -ai (br+bi), ar (bi-br); re = first + second, im = first + third).  The DMMA pipe is the
+// bound of K2 / K4, so this removes a quarter of its work; the rounding error stays O(eps * sum|a||b|).
+#ifndef CHEST_3M
+#define CHEST_3M 1
+#endif
 // complex tile update: (cr + j ci) += (ar + j ai) * (br + j bi), nbi = -bi
 __device__ __forceinline__ void zmma884(double (&cr)[2], double (&ci)[2], double ar, double ai,
                                         double br, double bi, double nbi) {

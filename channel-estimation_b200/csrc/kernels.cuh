@@ -265,7 +265,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // The host picks, per waveform, the geometry whose tiles waste the fewest flops on padding (48 divides the
 // 720 / 336 symbols of the reference's grids and follows the 24-subcarrier support structure more closely).
 template <int MODE, int WM, int WN, int TMW>
-__global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 2 : 3) k_gemm(GemmParams p) {
+__global__ void __launch_bounds__(32 * WM * WN, CHEST_3M ? ((WM * WN == 8) ? 1 : 2) : ((WM * WN == 8) ? 2 : 3))
+k_gemm(GemmParams p) {
     constexpr int TM = 8 * TMW * WM, TN = 16 * WN, KT = 16, LDS = KT + 4, NTHR = 32 * WM * WN;
     extern __shared__ double smem[];
     cplx (*As)[TM][LDS] = reinterpret_cast<cplx (*)[TM][LDS]>(smem);
@@ -284,11 +285,16 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 2 : 3) k_gemm(G
     cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * RT8 * p.n_cols : 0);
     const bool conj_a = p.conj_a != 0;
 
-    double cr[TMW][2][2], ci[TMW][2][2];
+    // Complex products use the three-multiplication form (CHEST_3M, common.cuh): per 8x8 tile the partial sums
+    // c1 = (ar+ai) br, cr = -ai (br+bi), ci = ar (bi-br); the epilogue forms re = c1 + cr, im = c1 + ci.
+    double cr[TMW][2][2], ci[TMW][2][2], c1[CHEST_3M ? TMW : 1][2][2];
 #pragma unroll
     for (int a = 0; a < TMW; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) { cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0; }
+        for (int b = 0; b < 2; ++b) {
+            cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = 0.0;
+            if (CHEST_3M) c1[a][b][0] = c1[a][b][1] = 0.0;
+        }
 
     auto fill = [&](int stage, int k0) {
 #pragma unroll
@@ -337,6 +343,23 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 2 : 3) k_gemm(G
             for (int x = 0; x < TMW; ++x) a[x] = As[st][wm * 8 * TMW + x * 8 + g][kk + t4];
 #pragma unroll
             for (int y = 0; y < 2; ++y) b[y] = Bs[st][wn * 16 + y * 8 + g][kk + t4];
+#if CHEST_3M
+            double bs[2], bd[2];
+#pragma unroll
+            for (int y = 0; y < 2; ++y) { bs[y] = b[y].x + b[y].y; bd[y] = b[y].y - b[y].x; }
+#pragma unroll
+            for (int x = 0; x < TMW; ++x) {
+                const double ai = conj_a ? dneg(a[x].y) : a[x].y;
+                const double nai = conj_a ? a[x].y : dneg(a[x].y);
+                const double as = a[x].x + ai;
+#pragma unroll
+                for (int y = 0; y < 2; ++y) {
+                    dmma884(c1[x][y][0], c1[x][y][1], as, b[y].x);
+                    dmma884(cr[x][y][0], cr[x][y][1], nai, bs[y]);
+                    dmma884(ci[x][y][0], ci[x][y][1], a[x].x, bd[y]);
+                }
+            }
+#else
 #pragma unroll
             for (int x = 0; x < TMW; ++x) {
                 const double ai = conj_a ? dneg(a[x].y) : a[x].y;
@@ -349,6 +372,7 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 2 : 3) k_gemm(G
                     dmma884(ci[x][y][0], ci[x][y][1], ai, b[y].x);
                 }
             }
+#endif
         }
         cp_async_wait_all();
         __syncthreads();
@@ -362,7 +386,8 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 2 : 3) k_gemm(G
             for (int e = 0; e < 2; ++e) {
                 int m = m0 + wm * 8 * TMW + a * 8 + g, col = n0 + wn * 16 + b * 8 + 2 * t4 + e;
                 if (m < p.M && col < p.n_cols) {
-                    cplx v = cmake(cr[a][b][e], ci[a][b][e]);
+                    cplx v = CHEST_3M ? cmake(c1[CHEST_3M ? a : 0][b][e] + cr[a][b][e], c1[CHEST_3M ? a : 0][b][e] + ci[a][b][e])
+                                      : cmake(cr[a][b][e], ci[a][b][e]);
                     if (MODE == GEMM_D) {
                         out[((int64_t)(m >> 3) * p.n_cols + col) * 8 + (m & 7)] = v;
                         if (p.hdiag && m == col) p.hdiag[(int64_t)rep * p.M + m] = v;
@@ -406,6 +431,7 @@ __global__ void k_estimate(cplx* __restrict__ Dhat, cplx* __restrict__ hdiag, WT
 //   PERF CTA: one realization, all (scheme-on-waveform, SNR) columns (they share D_rep)
 // phases: A quantise + precode -> v ; B interference = Woff(hP_prev) v  or  (D - diag h) v (DMMA) ;
 //         C new pilot estimates ; D one-tap channel + equalise ; E de-spread / select, demap, count.
+// (k_ic_main runs phase B, k_ic_light phases C, D, E and the next iteration's phase A.)
 struct IcCta { int mode, scheme_or_wf, snr, first, n_cols; };   // mode 0 EST, 1 PERF
 struct IcParams {
     int it, n_iter, n_rep, n_snr, K_max, pilot_rows;      // pilot_rows: rows of the shared pilot tables (4 * max P4)
@@ -475,7 +501,7 @@ __device__ __forceinline__ cplx ld_stream(const cplx* ptr) {
 #endif
 template <int P4T>
 __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
-                                                 const int* __restrict__ tdel, const cplx* hPs, const cplx* vbuf,
+                                                 const int* __restrict__ tdel, const cplx* hPs, const cplx* hP3, const cplx* vbuf,
                                                  cplx* ybuf, const cplx* const* ycolp, cplx* ring, int K, int warp,
                                                  int nwarp, int lane) {
     constexpr int NC = NC_MAX, HS = NC + 2, ST = EST_RING;
@@ -483,12 +509,15 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
     cplx* slot = ring + lane;                                  // [stage][pq][32 lanes]
-    cplx hb[HPREG ? P4T : 1][2];
+    cplx hb[HPREG ? P4T : 1][2], hb3[HPREG && CHEST_3M ? P4T : 1][2];
     if (HPREG) {
 #pragma unroll
         for (int pq = 0; pq < P4T; ++pq)
 #pragma unroll
-            for (int ct = 0; ct < 2; ++ct) hb[HPREG ? pq : 0][ct] = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+            for (int ct = 0; ct < 2; ++ct) {
+                hb[HPREG ? pq : 0][ct] = hPs[(pq * 4 + t4) * HS + ct * 8 + g];
+                if (CHEST_3M) hb3[HPREG && CHEST_3M ? pq : 0][ct] = hP3[(pq * 4 + t4) * HS + ct * 8 + g];
+            }
     }
     for (int rt = warp; rt < RT; rt += nwarp) {
         double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
@@ -548,6 +577,26 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
                 for (int pq = 0; pq < P4T; ++pq) cur[pq] = ld_stream(frag + ((int64_t)t * P4T + pq) * 32 + lane);
             }
             double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
+#if CHEST_3M
+            // three-multiplication complex product: hP3 holds (-(br+bi), bi-br) of the pilot estimates
+            double t1[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+            for (int pq = 0; pq < P4T; ++pq) {
+                const double as = cur[pq].x + cur[pq].y;
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) {
+                    const double b1 = HPREG ? hb[HPREG ? pq : 0][ct].x : hPs[(pq * 4 + t4) * HS + ct * 8 + g].x;
+                    const cplx b23 = HPREG ? hb3[HPREG ? pq : 0][ct] : hP3[(pq * 4 + t4) * HS + ct * 8 + g];
+                    dmma884(t1[ct][0], t1[ct][1], as, b1);
+                    dmma884(tr[ct][0], tr[ct][1], cur[pq].y, b23.x);
+                    dmma884(ti[ct][0], ti[ct][1], cur[pq].x, b23.y);
+                }
+            }
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) { tr[ct][e] += t1[ct][e]; ti[ct][e] += t1[ct][e]; }
+#else
 #pragma unroll
             for (int pq = 0; pq < P4T; ++pq) {
                 const double nai = dneg(cur[pq].y);
@@ -560,6 +609,7 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
                     dmma884(ti[ct][0], ti[ct][1], cur[pq].y, b.x);
                 }
             }
+#endif
 #pragma unroll
             for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
@@ -634,20 +684,28 @@ __device__ __forceinline__ void est_interference_generic(const cplx* __restrict_
 // ---- phase B, perfect CSI: acc[i, c] = sum_{j != i} D[i, j] v[j, c]   (DS.m:541-543)
 // A mini-GEMM per CTA: the warps take one row tile each (a "row block" of nwarp row tiles) and walk the
 // columns j together in chunks of 32.  The v chunk (B operand) is staged ONCE per chunk in shared memory
-// for all warps (cp.async, two stages, padded rows -> conflict-free LDS.128); each warp streams its own
-// row tile of the row-tile-major D (A operand: 512 contiguous bytes per k-step) through registers, 16
-// columns ahead.
+// for all warps, two stages, through registers: the loads of chunk ch+1 are in flight while chunk ch is
+// multiplied, and the store converts v into the three-multiplication operands  b1 = vr (plane v1, row
+// stride 20 doubles) and (b2, b3) = (-(vr+vi), vi-vr) (plane v23, row stride 18 complex) -- both strides
+// make the fragment loads conflict-free.  Each warp streams its own row tile of the row-tile-major D
+// (A operand: 512 contiguous bytes per k-step) through registers, 16 columns ahead.
 #define PERF_CHUNK 32          // v rows staged per barrier
 #define PERF_DSUB 16           // D columns prefetched in registers at a time
+#define PERF_V1S 20            // row stride (doubles) of the b1 plane
+#define IC_THREADS 256
+#define PERF_STAGE_CPLX (PERF_CHUNK * (NC_MAX + 2) + PERF_CHUNK * PERF_V1S / 2)   // one stage, in complex elements
 template <int NCT>
 __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
                                                   const cplx* const* ycolp, cplx* vs, const int* __restrict__ rt_jlo,
                                                   const int* __restrict__ rt_jhi, int K, int warp, int nwarp,
-                                                  int lane, int tid, int nthr) {
+                                                  int lane, int tid) {
     constexpr int NC = NC_MAX, U = PERF_DSUB / 4, NSUB = PERF_CHUNK / PERF_DSUB, VS = NC + 2;
+    constexpr int EPT = (PERF_CHUNK * NC + IC_THREADS - 1) / IC_THREADS;
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
     const int nblk = (RT + nwarp - 1) / nwarp;
+    cplx* v23 = vs;                                                            // [stage][row][VS]
+    double* v1 = reinterpret_cast<double*>(vs + 2 * PERF_CHUNK * VS);          // [stage][row][PERF_V1S]
     for (int blk = 0; blk < nblk; ++blk) {
         // columns outside [jlo, jhi) are structurally zero for every row of this block (no support overlap
         // between Q_i and H G_j): they are skipped exactly
@@ -656,10 +714,10 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
         const int ch0 = jlo / PERF_CHUNK, nchunk = jhi > jlo ? (jhi + PERF_CHUNK - 1) / PERF_CHUNK : ch0;
         const int rt = blk * nwarp + warp;
         const bool active = rt < RT;
-        double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}};
+        double accr[2][2] = {{0, 0}, {0, 0}}, acci[2][2] = {{0, 0}, {0, 0}}, acc1[2][2] = {{0, 0}, {0, 0}};
         const int i = rt * 8 + g;
         const cplx* Drt = Dm + (int64_t)(active ? rt : 0) * K * 8 + g;
-        cplx an[U];
+        cplx an[U], vreg[EPT];
         auto load_d = [&](int j0) {                            // 16 columns of this warp's row tile -> registers
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -668,21 +726,32 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
                 an[u] = active ? ld_stream(Drt + (int64_t)j * 8) : cmake(0.0, 0.0);
             }
         };
-        auto stage_v = [&](int s, int ch) {                    // v chunk, shared by all warps
-            for (int e = tid; e < PERF_CHUNK * NC; e += nthr) {
-                int jr = e / NC, c = e % NC, j = ch * PERF_CHUNK + jr;
+        auto fetch_v = [&](int ch) {                           // v chunk -> registers (shared by all warps)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int idx = tid + e * IC_THREADS, jr = idx / NC, c = idx % NC;
+                int j = ch * PERF_CHUNK + jr;
                 j = j < K ? j : K - 1;
-                cp_async16_plain(vs + (s * PERF_CHUNK + jr) * VS + c, vbuf + j * NC + c);
+                vreg[e] = vbuf[j * NC + c];
             }
-            cp_async_commit();
+        };
+        auto store_v = [&](int s) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int idx = tid + e * IC_THREADS, jr = idx / NC, c = idx % NC;
+                if (idx < PERF_CHUNK * NC) {
+                    const cplx b = vreg[e];
+                    v1[(s * PERF_CHUNK + jr) * PERF_V1S + c] = b.x;
+                    v23[(s * PERF_CHUNK + jr) * VS + c] = CHEST_3M ? cmake(-(b.x + b.y), b.y - b.x) : cmake(b.y, 0.0);
+                }
+            }
         };
         __syncthreads();                                       // previous row block done with both stages
-        if (ch0 < nchunk) { stage_v(ch0 & 1, ch0); load_d(ch0 * PERF_CHUNK); }
-        cp_async_wait_group<0>();
+        if (ch0 < nchunk) { fetch_v(ch0); load_d(ch0 * PERF_CHUNK); store_v(ch0 & 1); }
         __syncthreads();
         for (int ch = ch0; ch < nchunk; ++ch) {
             const int s = ch & 1;
-            if (ch + 1 < nchunk) stage_v(s ^ 1, ch + 1);       // stage s^1 was last read before the previous barrier
+            if (ch + 1 < nchunk) fetch_v(ch + 1);
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
                 cplx a[U];
@@ -694,19 +763,32 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
                 for (int u = 0; u < U; ++u) {
                     int j = ch * PERF_CHUNK + sub * PERF_DSUB + 4 * u + t4;
                     if (i >= K || j >= K || i == j) a[u] = cmake(0.0, 0.0);
+                    const int row = s * PERF_CHUNK + sub * PERF_DSUB + 4 * u + t4;
+#if CHEST_3M
+                    const double as = a[u].x + a[u].y;
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct) {
+                        const double b1 = v1[row * PERF_V1S + ct * 8 + g];
+                        const cplx b23 = v23[row * VS + ct * 8 + g];
+                        dmma884(acc1[ct][0], acc1[ct][1], as, b1);
+                        dmma884(accr[ct][0], accr[ct][1], a[u].y, b23.x);
+                        dmma884(acci[ct][0], acci[ct][1], a[u].x, b23.y);
+                    }
+#else
                     const double nai = dneg(a[u].y);
 #pragma unroll
                     for (int ct = 0; ct < NCT; ++ct) {
-                        const cplx b = vs[(s * PERF_CHUNK + sub * PERF_DSUB + 4 * u + t4) * VS + ct * 8 + g];
-                        dmma884(accr[ct][0], accr[ct][1], a[u].x, b.x);
-                        dmma884(accr[ct][0], accr[ct][1], nai, b.y);
-                        dmma884(acci[ct][0], acci[ct][1], a[u].x, b.y);
-                        dmma884(acci[ct][0], acci[ct][1], a[u].y, b.x);
+                        const double bx = v1[row * PERF_V1S + ct * 8 + g], by = v23[row * VS + ct * 8 + g].x;
+                        dmma884(accr[ct][0], accr[ct][1], a[u].x, bx);
+                        dmma884(accr[ct][0], accr[ct][1], nai, by);
+                        dmma884(acci[ct][0], acci[ct][1], a[u].x, by);
+                        dmma884(acci[ct][0], acci[ct][1], a[u].y, bx);
                     }
+#endif
                 }
             }
-            cp_async_wait_group<0>();
-            __syncthreads();                                   // chunk ch+1 has landed, chunk ch is consumed
+            if (ch + 1 < nchunk) store_v(s ^ 1);               // stage s^1 was last read before the previous barrier
+            __syncthreads();                                   // chunk ch+1 is staged, chunk ch is consumed
         }
         if (active && i < K) {
 #pragma unroll
@@ -716,7 +798,7 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
                     int c = ct * 8 + 2 * t4 + e;
                     const cplx* yp = ycolp[c];
                     cplx yv = yp ? yp[i] : cmake(0.0, 0.0);
-                    ybuf[i * NC + c] = cmake(yv.x - accr[ct][e], yv.y - acci[ct][e]);
+                    ybuf[i * NC + c] = cmake(yv.x - (accr[ct][e] + acc1[ct][e]), yv.y - (acci[ct][e] + acc1[ct][e]));
                 }
         }
     }
@@ -726,17 +808,17 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #define IC_TRACE(k, v) do { if (p.trace && threadIdx.x == 0) p.trace[(int64_t)blockIdx.x * 8 + (k)] = (v); } while (0)
 // ---------------------------------------------------------------------------------------------
-// k_ic: one launch per iteration `it` (it = 0 is the one-tap stage), persistent + cooperative.
-// Work units (IcCta): up to 16 columns and ALL K rows of them.
+// K4: one interference-cancellation iteration = two launches over the same work units (IcCta):
 //   EST  unit: one scheme, one SNR point, 16 consecutive realizations (they share W_snr)
 //   PERF unit: one realization, all (scheme-on-waveform, SNR) columns (they share D_rep)
-// Three grid-wide stages separated by grid barriers:
-//   pre  (A)     z = [xP; quantise(xD_prev)], v = C z              -- scalar FP64, latency-bound
-//   main (B)     y_ic = y - Woff(hP_prev) v   or   y - (D - diag h) v   -- FP64 tensor pipe (DMMA)
-//   post (C,D,E) pilot estimates, one-tap channel, equalise, de-spread / select, demap, count
-// The scalar stages run without DMMA competition (both share the SM's FP64 pipe: a DFMA queued behind
-// another CTA's DMMAs takes ~50 cycles), and in the main stage every resident CTA is in the tensor phase,
-// pulling units from a queue ordered heavy-first.
+// each owning up to 16 columns and ALL K rows of them.
+//   k_ic_main(it)   phase B: y_ic = y - Woff(hP_prev) v   or   y - (D - diag h) v   -- FP64 tensor pipe (DMMA);
+//                   persistent CTAs (2 per SM) pull units from a queue ordered heavy-first
+//   k_ic_light(it)  phases C, D, E of iteration it (pilot estimates, one-tap channel, equalise, de-spread /
+//                   select, demap, count) followed by phase A of iteration it+1 (z = [xP; quantised symbols],
+//                   v = C z) -- scalar FP64, latency-bound, so it runs at high occupancy and never shares an SM
+//                   with the tensor phase (both use the SM's one FP64 pipe: a DFMA queued behind another CTA's
+//                   DMMAs takes ~50 cycles).  it = 0 is the one-tap stage (DS.m:406-433).
 // ---------------------------------------------------------------------------------------------
 struct IcShared {
     unsigned int cnt[NC_MAX][2];
@@ -763,19 +845,79 @@ __device__ __forceinline__ void ic_load_unit(const IcParams& p, const IcCta& cta
 #ifndef IC_MIN_BLOCKS
 #define IC_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
+__global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams p) {
     constexpr int NC = NC_MAX, HS = NC + 2;
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int it = p.it;
     extern __shared__ cplx ic_smem[];
     cplx* hPs = ic_smem;                                    // previous pilot estimates [p][col]
-    cplx* hPn = ic_smem + p.pilot_rows * HS;                // new pilot estimates
-    cplx* vstage = ic_smem + 2 * p.pilot_rows * HS;        // 2 x PERF_CHUNK x HS
-    cplx* ring = vstage + 2 * PERF_CHUNK * HS + warp * p.ring_cplx;     // per-warp W-fragment ring
+    cplx* hP3 = ic_smem + p.pilot_rows * HS;                // their three-multiplication operands (-(re+im), im-re)
+    // staging area, one unit at a time: the v chunks of a PERF unit (2 stages) or the per-warp W-fragment
+    // rings of an EST unit -- never both
+    cplx* vstage = ic_smem + 2 * p.pilot_rows * HS;
+    cplx* ring = vstage + warp * p.ring_cplx;
+    __shared__ IcShared sh;
+    IC_TRACE(0, smid()); IC_TRACE(1, gtime());
+    unsigned long long n_done = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh.unit = (int)atomicAdd(p.queue + it, 1u);
+        __syncthreads();
+        const int unit = sh.unit;
+        if (unit >= p.n_units) break;
+        ++n_done;
+        const IcCta cta = p.ctas[unit];
+        ic_load_unit(p, cta, sh);
+        const int csi = cta.mode;
+        const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
+        const int K = p.sch[p.wf_scheme[wf][0]].K;
+        cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
+        cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
+        if (csi == 0) {
+            const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+            for (int idx = tid; idx < sd.P4 * 4 * NC; idx += nthr) {      // rows P..4*P4-1 are zero padding
+                int c = idx % NC, pp = idx / NC;
+                const cplx b = (sh.c_rep[c] >= 0 && pp < sd.P)
+                                   ? sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] : cmake(0.0, 0.0);
+                hPs[pp * HS + c] = b;
+                hP3[pp * HS + c] = cmake(-(b.x + b.y), b.y - b.x);
+            }
+            __syncthreads();
+            // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
+            const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
+            if (sd.P4 == 4)
+                est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3,
+                                    vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
+            else if (sd.P4 == 8)
+                est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3,
+                                    vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
+            else
+                est_interference_generic(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev],
+                                         hPs, vbuf, ybuf, sh.ycolp, K, sd.P4, warp, nwarp, lane);
+        } else {
+            const cplx* Dm = p.D[wf] + (int64_t)cta.snr * (((K + 7) / 8) * 8) * K;     // cta.snr holds the realization
+            if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid);
+            else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid);
+        }
+    }
+    IC_TRACE(3, gtime()); IC_TRACE(7, n_done);
+}
+
+#ifndef IC_LIGHT_BLOCKS
+#define IC_LIGHT_BLOCKS 4
+#endif
+#ifndef IC_LIGHT_WAVES
+#define IC_LIGHT_WAVES 64      // grid of the light kernel in units of one resident wave (i.e. one CTA per unit)
+#endif
+__global__ void __launch_bounds__(IC_THREADS, IC_LIGHT_BLOCKS) k_ic_light(IcParams p) {
+    constexpr int NC = NC_MAX, HS = NC + 2;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int it = p.it;
+    extern __shared__ cplx ic_smem[];
+    cplx* hPn = ic_smem;                                    // new pilot estimates [p][col]
     __shared__ IcShared sh;
     {   // constellation tables (levels, grid -> word, word -> symbol) in shared memory
-        cplx* q = vstage + 2 * PERF_CHUNK * HS + nwarp * p.ring_cplx;
+        cplx* q = ic_smem + p.pilot_rows * HS;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const ConstDev& cg = p.cst[k];
@@ -787,162 +929,15 @@ __global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
             if (tid == 0) { sh.cst[k] = cg; sh.cst[k].symbol = sym; sh.cst[k].level = lev; sh.cst[k].word_of_grid = gr; }
         }
     }
-
-    IC_TRACE(0, smid()); IC_TRACE(1, gtime());
-    if (it > 0) {
-        // =================== pre stage: phase A for every unit (DS.m:482-484, 541-543) ===================
-        for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
-            const IcCta cta = p.ctas[unit];
-            ic_load_unit(p, cta, sh);
-            const int csi = cta.mode;
-            const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
-            const int K = p.sch[p.wf_scheme[wf][0]].K;
-            cplx* zbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC;
-            cplx* vbuf = zbuf + (int64_t)p.K_max * NC;
-            int kin_max = 0;
-            for (int c = 0; c < cta.n_cols; ++c) kin_max = max(kin_max, p.sch[sh.c_scheme[c]].K_in);
-            {   // A1: z = [xP; quantise(xD_prev)].  A thread keeps its column; eight symbols in flight.
-                const int c = tid % NC;
-                const bool okc = sh.c_rep[c] >= 0;
-                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
-                const ConstDev& cd = sh.cst[sd.constellation];
-                const cplx* __restrict__ xdp = sd.xD[csi] + ((int64_t)sh.c_snr[c] * p.n_rep + (okc ? sh.c_rep[c] : 0)) * sd.n_data;
-                const cplx* __restrict__ xpp = sd.xP + (int64_t)(okc ? sh.c_rep[c] : 0) * sd.P;
-                const int kstep = nthr / NC;
-                for (int k0 = tid / NC; k0 < kin_max; k0 += 8 * kstep) {
-                    cplx in[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int k = k0 + u * kstep;
-                        in[u] = cmake(0.0, 0.0);
-                        if (okc && k < sd.K_in) in[u] = k < sd.P ? xpp[k] : xdp[k - sd.P];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int k = k0 + u * kstep;
-                        if (k < kin_max) {
-                            cplx z = in[u];
-                            if (okc && k >= sd.P && k < sd.K_in) z = cd.symbol[demap_word(cd, in[u])];
-                            zbuf[k * NC + c] = z;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            {   // A2, rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread
-                const int c = tid % NC;
-                const bool okc = sh.c_rep[c] >= 0;
-                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
-                const int istep = nthr / NC;
-                for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
-                    int col[8]; cplx val[8], zz[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u * istep;
-                        col[u] = (okc && i < K) ? sd.row_col0[i] : -1;
-                        val[u] = (okc && i < K) ? sd.row_val0[i] : cmake(0.0, 0.0);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) zz[u] = col[u] >= 0 ? zbuf[col[u] * NC + c] : cmake(0.0, 0.0);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u * istep;
-                        if (i < K && col[u] != -2) vbuf[i * NC + c] = cmul(val[u], zz[u]);
-                    }
-                }
-            }
-            // A2, long rows (auxiliary symbols, spread symbols): one warp per row, lane = 16*h + c handles column c
-            // and every second entry (h = 0/1), eight independent loads in flight; halves combined by shuffle.
-            {
-                const int c = lane & 15, h = lane >> 4;
-                const bool okc = sh.c_rep[c] >= 0;
-                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
-                const int* __restrict__ rp = sd.c_rowptr;
-                const int* __restrict__ cc = sd.c_col;
-                const cplx* __restrict__ cv = sd.c_val;
-                int nl = 0;
-                for (int q = 0; q < cta.n_cols; ++q) nl = max(nl, p.sch[sh.c_scheme[q]].n_long_rows);
-                for (int r = warp; r < nl; r += nwarp) {
-                    const bool okr = okc && r < sd.n_long_rows;
-                    const int i = okr ? sd.long_rows[r] : 0;
-                    cplx acc = cmake(0.0, 0.0);
-                    if (okr) {
-                        const int e1 = rp[i + 1];
-                        int e = rp[i] + h;
-                        for (; e + 14 < e1; e += 16) {
-                            cplx cvv[8], zz[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) { cvv[u] = cv[e + 2 * u]; zz[u] = zbuf[cc[e + 2 * u] * NC + c]; }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) cfma(acc, cvv[u], zz[u]);
-                        }
-                        for (; e < e1; e += 2) cfma(acc, cv[e], zbuf[cc[e] * NC + c]);
-                    }
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-                    if (okr && h == 0) vbuf[i * NC + c] = acc;
-                }
-            }
-        }
-        __threadfence();
-        grid.sync();
-        IC_TRACE(2, gtime());
-        unsigned long long n_done = 0;
-
-        // =================== main stage: phase B, units pulled from the queue ===================
-        for (;;) {
-            __syncthreads();
-            if (tid == 0) sh.unit = (int)atomicAdd(p.queue + it, 1u);
-            __syncthreads();
-            const int unit = sh.unit;
-            if (unit >= p.n_units) break;
-            ++n_done;
-            const IcCta cta = p.ctas[unit];
-            ic_load_unit(p, cta, sh);
-            const int csi = cta.mode;
-            const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
-            const int K = p.sch[p.wf_scheme[wf][0]].K;
-            cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
-            cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
-            if (csi == 0) {
-                const SchemeDev& sd = p.sch[cta.scheme_or_wf];
-                for (int idx = tid; idx < sd.P4 * 4 * NC; idx += nthr) {      // rows P..4*P4-1 are zero padding
-                    int c = idx % NC, pp = idx / NC;
-                    hPs[pp * HS + c] = (sh.c_rep[c] >= 0 && pp < sd.P)
-                                           ? sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] : cmake(0.0, 0.0);
-                }
-                __syncthreads();
-                // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
-                const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
-                if (sd.P4 == 4)
-                    est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs,
-                                        vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
-                else if (sd.P4 == 8)
-                    est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs,
-                                        vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
-                else
-                    est_interference_generic(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev],
-                                             hPs, vbuf, ybuf, sh.ycolp, K, sd.P4, warp, nwarp, lane);
-            } else {
-                const cplx* Dm = p.D[wf] + (int64_t)cta.snr * (((K + 7) / 8) * 8) * K;     // cta.snr holds the realization
-                if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid, nthr);
-                else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid, nthr);
-            }
-        }
-        IC_TRACE(3, gtime()); IC_TRACE(7, n_done);
-        __threadfence();
-        grid.sync();
-        IC_TRACE(4, gtime());
-    }
-
-    // =================== post stage: phases C, D, E for every unit ===================
+    const bool next_pre = it < p.n_iter;                    // build z and v of iteration it+1
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         const IcCta cta = p.ctas[unit];
         ic_load_unit(p, cta, sh);
         const int csi = cta.mode;
         const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
         const int K = p.sch[p.wf_scheme[wf][0]].K;
-        cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
+        cplx* zbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC;
+        cplx* vbuf = zbuf + (int64_t)p.K_max * NC;
         const cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
         // y_ic of this unit: the cancelled symbols, or y itself in the one-tap stage
         auto yic = [&](int i, int c) -> cplx {
@@ -1032,7 +1027,8 @@ __global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
             }
             __syncthreads();
         }
-        // ---- phase E: data-symbol estimates, demap, bit errors         (DS.m:430-433 ...)
+        // ---- phase E: data-symbol estimates, demap, bit errors         (DS.m:430-433 ...); the hard decisions
+        //      are also the quantised symbols of the next iteration's cancellation (DS.m:482-484): z = [xP; Q(xD)]
         {
             // the block size is a multiple of 16, so a thread keeps its column: counters stay in registers
             const int c = tid % NC;
@@ -1043,6 +1039,10 @@ __global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
                 const int64_t colbase = ((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.n_data;
                 const uint32_t* __restrict__ txw = sd.txword + (int64_t)sh.c_rep[c] * sd.n_data;
                 const int dstep = nthr / NC;
+                if (next_pre) {
+                    const cplx* __restrict__ xpp = sd.xP + (int64_t)sh.c_rep[c] * sd.P;
+                    for (int k = tid / NC; k < sd.P; k += dstep) zbuf[k * NC + c] = xpp[k];
+                }
                 for (int d0 = tid / NC; d0 < sd.n_data; d0 += 4 * dstep) {
                     cplx xd[4];
                     uint32_t tw[4], em[4];
@@ -1082,7 +1082,9 @@ __global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
                         const int d = d0 + u * dstep;
                         if (d < sd.n_data) {
                             sd.xD[csi][colbase + d] = xd[u];
-                            uint32_t diff = (uint32_t)demap_word(cd, xd[u]) ^ tw[u];
+                            const int word = demap_word(cd, xd[u]);
+                            if (next_pre) zbuf[(sd.P + d) * NC + c] = cd.symbol[word];
+                            uint32_t diff = (uint32_t)word ^ tw[u];
                             e_all += __popc(diff);
                             e_edge += __popc(diff & em[u]);
                         }
@@ -1091,7 +1093,7 @@ __global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
             }
             if (e_all) atomicAdd(&sh.cnt[c][0], e_all);
             if (e_edge) atomicAdd(&sh.cnt[c][1], e_edge);
-            __syncthreads();
+            __syncthreads();                                   // also: phase E readers of vbuf done, z complete
             if (tid < 2 * NC) {
                 int cc = tid >> 1, e = tid & 1;
                 if (cc < cta.n_cols && sh.c_rep[cc] >= 0) {
@@ -1100,8 +1102,63 @@ __global__ void __launch_bounds__(256, IC_MIN_BLOCKS) k_ic(IcParams p) {
                 }
             }
         }
+        if (!next_pre) continue;
+        // ---- phase A of iteration it+1: v = C z   (DS.m:482-484, 541-543)
+        {   // rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread
+            const int c = tid % NC;
+            const bool okc = sh.c_rep[c] >= 0;
+            const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            const int istep = nthr / NC;
+            for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
+                int col[8]; cplx val[8], zz[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * istep;
+                    col[u] = (okc && i < K) ? sd.row_col0[i] : -1;
+                    val[u] = (okc && i < K) ? sd.row_val0[i] : cmake(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) zz[u] = col[u] >= 0 ? zbuf[col[u] * NC + c] : cmake(0.0, 0.0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * istep;
+                    if (i < K && col[u] != -2) vbuf[i * NC + c] = cmul(val[u], zz[u]);
+                }
+            }
+        }
+        // long rows (auxiliary symbols, spread symbols): one warp per row, lane = 16*h + c handles column c
+        // and every second entry (h = 0/1), eight independent loads in flight; halves combined by shuffle.
+        {
+            const int c = lane & 15, h = lane >> 4;
+            const bool okc = sh.c_rep[c] >= 0;
+            const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            const int* __restrict__ rp = sd.c_rowptr;
+            const int* __restrict__ cc = sd.c_col;
+            const cplx* __restrict__ cv = sd.c_val;
+            int nl = 0;
+            for (int q = 0; q < cta.n_cols; ++q) nl = max(nl, p.sch[sh.c_scheme[q]].n_long_rows);
+            for (int r = warp; r < nl; r += nwarp) {
+                const bool okr = okc && r < sd.n_long_rows;
+                const int i = okr ? sd.long_rows[r] : 0;
+                cplx acc = cmake(0.0, 0.0);
+                if (okr) {
+                    const int e1 = rp[i + 1];
+                    int e = rp[i] + h;
+                    for (; e + 14 < e1; e += 16) {
+                        cplx cvv[8], zz[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { cvv[u] = cv[e + 2 * u]; zz[u] = zbuf[cc[e + 2 * u] * NC + c]; }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) cfma(acc, cvv[u], zz[u]);
+                    }
+                    for (; e < e1; e += 2) cfma(acc, cv[e], zbuf[cc[e] * NC + c]);
+                }
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+                if (okr && h == 0) vbuf[i * NC + c] = acc;
+            }
+        }
     }
-    IC_TRACE(5, gtime());
 }
 
 // ============================================================================ FP64 peak probes
