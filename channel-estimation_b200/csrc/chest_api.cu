@@ -390,8 +390,9 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     const int ic_threads = IC_THREADS;
     ip.ring_cplx = (EST_WSRC == 0) ? EST_RING * (ip.pilot_rows / 4) * 32 : 0;   // EST_RING tiles of P4 fragments x 32 lanes
     // main: pilot tables (2) + max(v-chunk stages of a PERF unit, W-fragment rings of an EST unit)
-    const size_t main_smem = (size_t)2 * ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx)
-                             + std::max((size_t)2 * PERF_STAGE_CPLX, (size_t)(ic_threads / 32) * ip.ring_cplx) * sizeof(cplx);
+    ip.stage_cplx = (int)((std::max((size_t)2 * PERF_STAGE_CPLX, (size_t)(ic_threads / 32) * ip.ring_cplx) + 7) / 8 * 8);
+    const size_t main_smem = ((size_t)ip.stage_cplx + (size_t)2 * ip.pilot_rows * (NC_MAX + 2)) * sizeof(cplx)
+                             + (size_t)ip.pilot_rows * EST_H1S * sizeof(double);
     // light: new pilot estimates + constellation tables
     const size_t light_smem = (size_t)ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx) + cst_smem;
     if (c->ic_grid == 0 || c->ic_smem != main_smem) {              // persistent main grid: one wave of resident CTAs
@@ -399,7 +400,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         CK(cudaFuncSetAttribute(k_ic_light, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         int per_sm = 0, per_sm_light = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ic_main, ic_threads, main_smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, k_ic_light, ic_threads, light_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, k_ic_light, IC_LIGHT_THREADS, light_smem));
         if (per_sm < 1 || per_sm_light < 1)
             return fail(CHEST_ERR_STATE, "the IC kernels do not fit on an SM (too many pilots for the shared tables)");
         c->ic_grid = per_sm * c->n_sm; c->ic_light_grid = per_sm_light * c->n_sm; c->ic_smem = main_smem;
@@ -423,7 +424,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
             ip.trace = nullptr;
         }
         // phases C, D, E of iteration it (+ phase A of iteration it+1)
-        k_ic_light<<<std::min(c->ic_light_grid * IC_LIGHT_WAVES, n_units), ic_threads, light_smem, st>>>(ip);
+        k_ic_light<<<std::min(c->ic_light_grid * IC_LIGHT_WAVES, n_units), IC_LIGHT_THREADS, light_smem, st>>>(ip);
         c->launches++;
         CK(cudaGetLastError());
         if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev[5], st));

@@ -436,6 +436,7 @@ struct IcCta { int mode, scheme_or_wf, snr, first, n_cols; };   // mode 0 EST, 1
 struct IcParams {
     int it, n_iter, n_rep, n_snr, K_max, pilot_rows;      // pilot_rows: rows of the shared pilot tables (4 * max P4)
     int ring_cplx;                                        // complex elements of one warp's W-fragment ring
+    int stage_cplx;                                       // complex elements of the main kernel's staging area
     const IcCta* ctas;
     SchemeDev sch[3];
     ConstDev cst[2];
@@ -478,6 +479,11 @@ __device__ __forceinline__ cplx ld_stream(const cplx* ptr) {
     return r;
 }
 
+// two adjacent complex values (32 bytes, 32-byte aligned) with one 256-bit load
+__device__ __forceinline__ void ld_cplx2(const cplx* ptr, cplx& a, cplx& b) {
+    asm("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(ptr));
+}
+
 // ---- phase B, estimated CSI: acc[i, c] = sum_{delta} ( sum_p W[i, i+delta, p] hP[p, c] ) * v[i+delta, c]
 // One warp owns 8 rows (a row tile) at a time and walks its diagonal tiles.  Per tile the P4 pilot
 // quads are DMMA k-steps with the hP fragments as B operand (shared by every tile), followed by an
@@ -490,6 +496,7 @@ __device__ __forceinline__ cplx ld_stream(const cplx* ptr) {
 //   measured (profiles/r01_kic_variant_sweep.txt): 0 is best in the mixed EST+PERF main stage
 //   EST_VPRE  1: next tile's v rows prefetched into registers
 //   EST_HPREG 1: the hP B-fragments live in registers for the whole row tile (P4 <= 4 only)
+#define EST_H1S 20           // row stride (doubles) of the real-part plane of the pilot estimates
 #ifndef EST_VPRE
 #define EST_VPRE 0
 #endif
@@ -501,11 +508,14 @@ __device__ __forceinline__ cplx ld_stream(const cplx* ptr) {
 #endif
 template <int P4T>
 __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
-                                                 const int* __restrict__ tdel, const cplx* hPs, const cplx* hP3, const cplx* vbuf,
+                                                 const int* __restrict__ tdel, const cplx* hPs, const cplx* hP3, const double* hP1,
+                                                 const cplx* vbuf,
                                                  cplx* ybuf, const cplx* const* ycolp, cplx* ring, int K, int warp,
                                                  int nwarp, int lane) {
     constexpr int NC = NC_MAX, HS = NC + 2, ST = EST_RING;
     constexpr bool HPREG = EST_HPREG && P4T <= 4;
+    // hP1: real parts of the pilot estimates as a plane of doubles, row stride 20 -> the 8-byte fragment loads
+    // are conflict-free (the 16-byte stride of the complex table would give 2-way conflicts)
     const int g = lane >> 2, t4 = lane & 3;
     const int RT = (K + 7) / 8;
     cplx* slot = ring + lane;                                  // [stage][pq][32 lanes]
@@ -541,9 +551,7 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
             int j = i + tdel[t];
             j = j < 0 ? 0 : (j > K - 1 ? K - 1 : j);
 #pragma unroll
-            for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) dst[ct][e] = vbuf[j * NC + ct * 8 + 2 * t4 + e];
+            for (int ct = 0; ct < 2; ++ct) ld_cplx2(vbuf + j * NC + ct * 8 + 2 * t4, dst[ct][0], dst[ct][1]);
         };
         if (EST_WSRC == 0) {
 #pragma unroll
@@ -585,7 +593,7 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
                 const double as = cur[pq].x + cur[pq].y;
 #pragma unroll
                 for (int ct = 0; ct < 2; ++ct) {
-                    const double b1 = HPREG ? hb[HPREG ? pq : 0][ct].x : hPs[(pq * 4 + t4) * HS + ct * 8 + g].x;
+                    const double b1 = HPREG ? hb[HPREG ? pq : 0][ct].x : hP1[(pq * 4 + t4) * EST_H1S + ct * 8 + g];
                     const cplx b23 = HPREG ? hb3[HPREG ? pq : 0][ct] : hP3[(pq * 4 + t4) * HS + ct * 8 + g];
                     dmma884(t1[ct][0], t1[ct][1], as, b1);
                     dmma884(tr[ct][0], tr[ct][1], cur[pq].y, b23.x);
@@ -692,7 +700,9 @@ __device__ __forceinline__ void est_interference_generic(const cplx* __restrict_
 #define PERF_CHUNK 32          // v rows staged per barrier
 #define PERF_DSUB 16           // D columns prefetched in registers at a time
 #define PERF_V1S 20            // row stride (doubles) of the b1 plane
+#ifndef IC_THREADS
 #define IC_THREADS 256
+#endif
 #define PERF_STAGE_CPLX (PERF_CHUNK * (NC_MAX + 2) + PERF_CHUNK * PERF_V1S / 2)   // one stage, in complex elements
 template <int NCT>
 __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
@@ -849,12 +859,13 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
     constexpr int NC = NC_MAX, HS = NC + 2;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int it = p.it;
-    extern __shared__ cplx ic_smem[];
-    cplx* hPs = ic_smem;                                    // previous pilot estimates [p][col]
-    cplx* hP3 = ic_smem + p.pilot_rows * HS;                // their three-multiplication operands (-(re+im), im-re)
-    // staging area, one unit at a time: the v chunks of a PERF unit (2 stages) or the per-warp W-fragment
-    // rings of an EST unit -- never both
-    cplx* vstage = ic_smem + 2 * p.pilot_rows * HS;
+    extern __shared__ __align__(128) cplx ic_smem[];
+    // staging area (first, 128-byte aligned), one unit at a time: the v chunks of a PERF unit (2 stages) or
+    // the per-warp W-fragment rings of an EST unit -- never both; then the pilot tables of an EST unit
+    cplx* vstage = ic_smem;
+    cplx* hPs = ic_smem + p.stage_cplx;                     // previous pilot estimates [p][col]
+    cplx* hP3 = hPs + p.pilot_rows * HS;                    // their three-multiplication operands (-(re+im), im-re)
+    double* hP1 = reinterpret_cast<double*>(hP3 + p.pilot_rows * HS);   // real parts, [p][EST_H1S]
     cplx* ring = vstage + warp * p.ring_cplx;
     __shared__ IcShared sh;
     IC_TRACE(0, smid()); IC_TRACE(1, gtime());
@@ -881,15 +892,16 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
                                    ? sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] : cmake(0.0, 0.0);
                 hPs[pp * HS + c] = b;
                 hP3[pp * HS + c] = cmake(-(b.x + b.y), b.y - b.x);
+                hP1[pp * EST_H1S + c] = b.x;
             }
             __syncthreads();
             // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
             const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
             if (sd.P4 == 4)
-                est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3,
+                est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3, hP1,
                                     vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
             else if (sd.P4 == 8)
-                est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3,
+                est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3, hP1,
                                     vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
             else
                 est_interference_generic(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev],
@@ -909,7 +921,8 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
 #ifndef IC_LIGHT_WAVES
 #define IC_LIGHT_WAVES 64      // grid of the light kernel in units of one resident wave (i.e. one CTA per unit)
 #endif
-__global__ void __launch_bounds__(IC_THREADS, IC_LIGHT_BLOCKS) k_ic_light(IcParams p) {
+#define IC_LIGHT_THREADS 256
+__global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(IcParams p) {
     constexpr int NC = NC_MAX, HS = NC + 2;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int it = p.it;

@@ -1,12 +1,6 @@
 #!/bin/bash
-# development: time k_ic stage durations for every build/lib_*.so variant
-for lib in build/lib_*.so; do
-  for mode in est_fbmc all; do
-    if [ "$mode" = all ]; then unset CHEST_DEBUG_ONLY; else export CHEST_DEBUG_ONLY=$mode; fi
-    CHEST_LIB=$PWD/$lib CHEST_IC_TRACE=gpurun_out/tr.bin python bench.py --steps 2 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys,numpy as np
-d=json.loads(sys.stdin.read())
-t=np.fromfile('gpurun_out/tr.bin',dtype=np.uint64).reshape(-1,8); t=t[t[:,1]>0]; ts=(t[:,1:6].astype(np.int64)-t[:,1].min())/1e3
-print('%-28s %-9s value %8.0f  ic/iter %6.2f ms | pre %5.2f main %6.2f post %5.2f ms' % ('$lib','$mode',d['value'],d['stage_ms_per_step']['ic_iterations']/4, ts[:,1].max()/1e3,(ts[:,3].max()-ts[:,1].max())/1e3,(ts[:,4].max()-ts[:,3].max())/1e3))"
-  done
+# development: stage times of the loop body for every variants/*.so build (CHEST_LIB override)
+for lib in variants/*.so; do
+  printf "%-22s " $lib
+  CHEST_LIB=$PWD/$lib python tests/gpu_quick_timing.py ${1:-1024} 3 2>&1 | grep "^batch" | tail -1 | sed 's/.*realizations.s \([0-9.]*\).*k2_transmission_matrix.: \([0-9.]*\).*one_tap.: \([0-9.]*\).*ic_iterations.: \([0-9.]*\).*total.: \([0-9.]*\).*/real\/s \1  k2 \2  one_tap \3  ic \4  total \5/'
 done
