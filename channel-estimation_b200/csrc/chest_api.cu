@@ -52,13 +52,16 @@ struct Waveform {
     bool set = false;
     int K = 0;
     DevBuf<cplx> G, Q, Gt;
+    DevBuf<cplx> Q1; DevBuf<double> Q2;                // three-multiplication planes of Q^H: (re, re - im), im; row stride Np
+    DevBuf<cplx> HG1; DevBuf<double> HG2;              // H*G planes: (re, re + im), im - re; [rep][K][Np]
     DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi, d_jlo, d_jhi;
+    DevBuf<int> q8_klo, q8_khi, hg8_klo, hg8_khi;      // per 8 columns of Q / of H*G (warp-level clipping in K2 / K3a)
     double d_struct_pairs = 0;   // (i,j) pairs of D inside the structural support
     std::vector<int> g_lo, g_hi, q_lo, q_hi;
     std::vector<double> hg_rows;   // per column: rows of H*G written by k_apply_hg
     int nsch = 0; int sch[2] = {0, 0};
     // batch state
-    DevBuf<cplx> x, s, r0, y, D, htrue, HG;
+    DevBuf<cplx> x, s, r0, y, D, htrue;
     int tile = 64;              // CTA tile size of the GEMMs on this waveform (48 or 64)
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
 };
@@ -157,7 +160,7 @@ void tile_ranges(const std::vector<int>& lo, const std::vector<int>& hi, int til
 template <int MODE, int WM, int WN, int TMW>
 cudaError_t launch_gemm_geo(Ctx* c, const GemmParams& p, int n_z) {
     constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
-    constexpr int smem = 2 * (TM + TN) * 20 * (int)sizeof(cplx);     // 2 stages x (A + B) rows x (16+4) complex
+    constexpr int smem = 3 * (TM + TN) * 20 * (int)sizeof(cplx);     // 2 stages x (A + B) rows x (16+4) x (complex + double plane)
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm<MODE, WM, WN, TMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -220,14 +223,16 @@ int stage_channel(Ctx* c, int n_rep, const double* du, const double* pu) {
 int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     Waveform& w = c->wf[wfi];
     GemmParams p{};
-    p.M = w.K; p.Kc = c->N; p.n_cols = w.K; p.lda = c->N; p.ldc = w.K; p.conj_a = 1;
-    p.At = w.Q.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.D.p;
-    p.bsrc = w.HG.p; p.ldb = c->N; p.N = c->N;
+    const int Np = (c->N + 1) & ~1;                                 // even row stride of the operand planes
+    p.M = w.K; p.Kc = c->N; p.n_cols = w.K; p.lda = Np; p.ldc = w.K; p.conj_a = 1;
+    p.At1 = w.Q1.p; p.At2 = w.Q2.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.D.p;
+    p.b1src = w.HG1.p; p.b2src = w.HG2.p; p.ldb = Np; p.N = c->N;
     p.nt_klo = w.hg_klo.p; p.nt_khi = w.hg_khi.p; p.hdiag = w.htrue.p; p.rep0 = rep0;
-    dim3 ghg(2, w.K, n_rep);
+    p.m8_klo = w.q8_klo.p; p.m8_khi = w.q8_khi.p; p.n8_klo = w.hg8_klo.p; p.n8_khi = w.hg8_khi.p;
+    dim3 ghg((w.K + HG_COLS - 1) / HG_COLS, n_rep);
     if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_hg[2 * wfi], c->stream));
-    k_apply_hg<<<ghg, 128, 0, c->stream>>>(w.HG.p, w.G.p, c->h.p, c->d_tap_delay.p, w.hg_klo.p, w.hg_khi.p,
-                                           c->N, w.K, c->T, rep0, w.tile);
+    k_apply_hg<<<ghg, 128, 0, c->stream>>>(w.HG1.p, w.HG2.p, w.G.p, c->h.p, c->d_tap_delay.p, w.hg_klo.p, w.hg_khi.p,
+                                           c->N, Np, w.K, c->T, rep0, w.tile);
     c->launches++;
     CK(cudaGetLastError());
     if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_hg[2 * wfi + 1], c->stream));
@@ -362,8 +367,9 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch) continue;
         GemmParams p{};
-        p.M = w.K; p.Kc = N; p.n_cols = w.nsch * S * n_rep; p.lda = N; p.ldc = w.K; p.conj_a = 1;
-        p.At = w.Q.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.y.p;
+        p.M = w.K; p.Kc = N; p.n_cols = w.nsch * S * n_rep; p.lda = (N + 1) & ~1; p.ldc = w.K; p.conj_a = 1;
+        p.At1 = w.Q1.p; p.At2 = w.Q2.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.y.p;
+        p.m8_klo = w.q8_klo.p; p.m8_khi = w.q8_khi.p;
         p.r0 = w.r0.p; p.noise = noise; p.noise_scale = c->d_noise_scale.p; p.n_snr = S; p.n_rep = n_rep; p.N = N;
         CK(launch_gemm<GEMM_DEMOD>(c, p, 1, w.tile));
     }
@@ -499,8 +505,8 @@ int chest_destroy(uint64_t handle) {
     // DevBuf has no destructor on purpose (plain members); release explicitly
     auto relw = [](Waveform& w) {
         w.G.release(); w.Q.release(); w.Gt.release(); w.q_klo.release(); w.q_khi.release(); w.gt_klo.release();
-        w.gt_khi.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
-        w.y.release(); w.D.release(); w.htrue.release(); w.HG.release();
+        w.gt_khi.release(); w.q8_klo.release(); w.q8_khi.release(); w.hg8_klo.release(); w.hg8_khi.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
+        w.y.release(); w.D.release(); w.htrue.release(); w.HG1.release(); w.HG2.release(); w.Q1.release(); w.Q2.release();
     };
     relw(c->wf[0]); relw(c->wf[1]);
     for (auto& k : c->cst) { k.symbol.release(); k.pilot.release(); k.level.release(); k.word_of_grid.release(); }
@@ -556,6 +562,19 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
     w.K = K;
     CK(w.G.upload(reinterpret_cast<const cplx*>(G), (size_t)N * K, c->stream));
     CK(w.Q.upload(reinterpret_cast<const cplx*>(Q), (size_t)N * K, c->stream));
+    {   // operand planes of Q^H for the three-multiplication GEMMs (K2, K3a): conj(q) = (re, -im)
+        const int Np = (N + 1) & ~1;
+        const cplx* q = reinterpret_cast<const cplx*>(Q);
+        std::vector<cplx> q1((size_t)Np * K, cmake(0.0, 0.0));
+        std::vector<double> q2((size_t)Np * K, 0.0);
+        for (int i = 0; i < K; ++i)
+            for (int n = 0; n < N; ++n) {
+                const cplx v = q[(size_t)n + (size_t)N * i];
+                q1[(size_t)n + (size_t)Np * i] = cmake(v.x, v.x - v.y);
+                q2[(size_t)n + (size_t)Np * i] = v.y;
+            }
+        CK(w.Q1.upload(q1, c->stream)); CK(w.Q2.upload(q2, c->stream));
+    }
     std::vector<cplx> gt((size_t)N * K);
     const cplx* g = reinterpret_cast<const cplx*>(G);
     for (int j = 0; j < K; ++j)
@@ -582,6 +601,8 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
     }
     tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, lo, hi);
     CK(w.q_klo.upload(lo, c->stream)); CK(w.q_khi.upload(hi, c->stream));
+    tile_ranges(w.q_lo, w.q_hi, 8, 0, N, lo, hi);
+    CK(w.q8_klo.upload(lo, c->stream)); CK(w.q8_khi.upload(hi, c->stream));
     // row supports of G (which symbols j touch sample n) for s = G x
     std::vector<int> rlo(N, K), rhi(N, 0);
     for (int j = 0; j < K; ++j)
@@ -813,6 +834,8 @@ int chest_finalize(uint64_t handle, int max_batch) {
         CK(w.hg_klo.upload(lo, c->stream)); CK(w.hg_khi.upload(hi, c->stream));
         w.hg_rows.assign(K, 0.0);
         for (int j = 0; j < K; ++j) w.hg_rows[j] = std::max(0, hi[j / w.tile] - lo[j / w.tile]);
+        tile_ranges(w.g_lo, w.g_hi, 8, max_delay, N, lo, hi);
+        CK(w.hg8_klo.upload(lo, c->stream)); CK(w.hg8_khi.upload(hi, c->stream));
         // support-aware work model: 8 T supp_G K  +  8 sum |supp(Q_i) ^ supp((HG)_j)|
         double f = 0;
         for (int j = 0; j < K; ++j) f += 8.0 * c->T * (w.g_hi[j] - w.g_lo[j]);
@@ -861,7 +884,12 @@ int chest_finalize(uint64_t handle, int max_batch) {
         int ns = std::max(w.nsch, 1);
         CK(w.x.alloc((size_t)ns * B * w.K)); CK(w.s.alloc((size_t)ns * B * N)); CK(w.r0.alloc((size_t)ns * B * N));
         CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.D.alloc((size_t)B * (((w.K + 7) / 8) * 8) * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
-        CK(w.HG.alloc((size_t)B * w.K * N));
+        {
+            const size_t n_hg = (size_t)B * w.K * ((N + 1) & ~1);
+            CK(w.HG1.alloc(n_hg)); CK(w.HG2.alloc(n_hg));
+            CK(cudaMemsetAsync(w.HG1.p, 0, n_hg * sizeof(cplx), c->stream));      // pad element of odd N stays zero
+            CK(cudaMemsetAsync(w.HG2.p, 0, n_hg * sizeof(double), c->stream));
+        }
         if (w.nsch) CK(c->pilot_idx[wfi].alloc((size_t)B * c->sch[w.sch[0]].P));
     }
     CK(c->doppler_u.alloc((size_t)B * c->T * c->paths)); CK(c->phase_u.alloc((size_t)B * c->T * c->paths));

@@ -120,22 +120,32 @@ __global__ void k_apply_h(cplx* __restrict__ r, const cplx* __restrict__ s, cons
 
 // HG[rep][j][n] = sum_tap h[rep][tap][n] * G[n - delay_tap, j] for n inside the k-range of j's column
 // tile (zero elsewhere in that range because G is zero outside its support).  K2 then reads H*G as a
-// plain k-contiguous operand with cp.async.
-__global__ void k_apply_hg(cplx* __restrict__ HG, const cplx* __restrict__ G, const cplx* __restrict__ h,
-                           const int* __restrict__ tap_delay, const int* __restrict__ nt_klo,
-                           const int* __restrict__ nt_khi, int N, int K, int T, int rep0, int tile) {
-    const int j = blockIdx.y, rep = blockIdx.z + rep0;
-    const int lo = nt_klo[j / tile], hi = nt_khi[j / tile];
-    const cplx* gc = G + (int64_t)N * j;
+// plain k-contiguous operand with cp.async.  The values are stored as the three-multiplication operands of
+// K2: plane 1 (complex) = (re, re + im), plane 2 (double) = im - re.  One block handles HG_COLS columns of
+// one realization (the channel taps stay in L1 across them).
+#define HG_COLS 8
+__global__ void k_apply_hg(cplx* __restrict__ HG1, double* __restrict__ HG2, const cplx* __restrict__ G,
+                           const cplx* __restrict__ h, const int* __restrict__ tap_delay,
+                           const int* __restrict__ nt_klo, const int* __restrict__ nt_khi, int N, int Np, int K, int T,
+                           int rep0, int tile) {
+    const int rep = blockIdx.y + rep0;
     const cplx* hr = h + (int64_t)rep * T * N;
-    cplx* out = HG + ((int64_t)rep * K + j) * N;
-    for (int n = lo + blockIdx.x * blockDim.x + threadIdx.x; n < hi; n += gridDim.x * blockDim.x) {
-        cplx acc = cmake(0.0, 0.0);
-        for (int t = 0; t < T; ++t) {
-            int d = tap_delay[t];
-            if (n >= d) cfma(acc, hr[(int64_t)t * N + n], gc[n - d]);
+    for (int jj = 0; jj < HG_COLS; ++jj) {
+        const int j = blockIdx.x * HG_COLS + jj;
+        if (j >= K) break;
+        // K2 copies the planes in aligned pairs: cover the range rounded out to even bounds (exact zeros there)
+        const int lo = nt_klo[j / tile] & ~1, hi = min(N, (nt_khi[j / tile] + 1) & ~1);
+        const cplx* gc = G + (int64_t)N * j;
+        const int64_t o = ((int64_t)rep * K + j) * Np;
+        for (int n = lo + threadIdx.x; n < hi; n += blockDim.x) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int t = 0; t < T; ++t) {
+                int d = tap_delay[t];
+                if (n >= d) cfma(acc, hr[(int64_t)t * N + n], gc[n - d]);
+            }
+            HG1[o + n] = cmake(acc.x, acc.x + acc.y);
+            HG2[o + n] = acc.y - acc.x;
         }
-        out[n] = acc;
     }
 }
 
@@ -235,14 +245,20 @@ enum { GEMM_PLAIN = 0, GEMM_DEMOD = 1, GEMM_D = 2 };
 struct GemmParams {
     int M, Kc, n_cols, lda, ldc, conj_a;
     const cplx* At;
-    const int* mt_klo; const int* mt_khi;      // per 64-row tile k support range
+    // GEMM_DEMOD / GEMM_D (A = Q^H): three-multiplication planes of the conjugated operand, same indexing as At:
+    // At1 = (re, re - im), At2 = im
+    const cplx* At1; const double* At2;
+    const int* mt_klo; const int* mt_khi;      // per CTA row tile: k support range
+    const int* m8_klo; const int* m8_khi;      // per 8 rows: k support range (warp-level clipping; may be null)
+    const int* n8_klo; const int* n8_khi;      // GEMM_D, per 8 columns: k support range of H*G (may be null)
     cplx* out;                                  // [col][ldc]
     // PLAIN: B[k,col] = bsrc[col*ldb + k]
     const cplx* bsrc; int ldb;
     // DEMOD: col = (g*n_snr + snr)*n_rep + rep ; B = r0[(g*n_rep+rep)*N + k] + sqrt(pn[snr]/2)*noise[(rep*n_snr+snr)*N + k]
     const cplx* r0; const cplx* noise; const double* noise_scale; int n_snr, n_rep;
-    // D: per realization (blockIdx.z): B[k=n, col=j] = HG[rep][j][n] (k_apply_hg) = bsrc[(rep*n_cols+col)*ldb + k];
-    // out += rep*ldc*n_cols
+    // D: per realization (blockIdx.z): B[k=n, col=j] = HG[rep][j][n] (k_apply_hg), stored as the planes
+    // b1src = (re, re + im), b2src = im - re at [(rep*n_cols+col)*ldb + k]; out += rep*ldc*n_cols
+    const cplx* b1src; const double* b2src;
     int N;
     const int* nt_klo; const int* nt_khi;      // per 64-col tile k support range of H*G
     cplx* hdiag;                                // [rep][K] diagonal of D (may be null)
@@ -258,19 +274,28 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Tiles live in shared memory as interleaved complex [row][k] with a row stride of KT+4 elements, so a
 // lane's (re, im) fragment pair is one conflict-free LDS.128.  Two stages: while the tensor pipe works
-// on stage s, cp.async (A, and B when it is a plain copy) and the computed B values (noise add / banded
-// H applied to G on the fly) fill stage s^1; one barrier per k-tile.
+// on stage s, cp.async (A, and B when it is a plain copy) and the computed B values (noise add) fill
+// stage s^1; one barrier per k-tile.
 // Geometry: WM x WN warps, each owning TMW x 2 DMMA tiles -> CTA tile (8*TMW*WM) x (16*WN).
-//   <2,4,4>: 64 x 64, 8 warps, 2 CTAs/SM        <2,3,3>: 48 x 48, 6 warps, 3 CTAs/SM
+//   <2,4,4>: 64 x 64, 8 warps        <2,3,3>: 48 x 48, 6 warps, 2 CTAs/SM
 // The host picks, per waveform, the geometry whose tiles waste the fewest flops on padding (48 divides the
 // 720 / 336 symbols of the reference's grids and follows the 24-subcarrier support structure more closely).
+// Complex products use the three-multiplication form (CHEST_3M, common.cuh): per 8x8 tile the partial sums
+// c1 = (ar+ai) br, cr = -ai (br+bi), ci = ar (bi-br); the epilogue forms re = c1 + cr, im = c1 + ci.
+// GEMM_DEMOD / GEMM_D (PRE3) read the operand sums ready-made: A from the planes the host builds once per
+// waveform, B from the planes k_apply_hg writes (or computed while adding the noise), so the inner loop is
+// LDS + DMMA only; a second, double-valued smem plane per operand holds the third value (row stride 20
+// doubles: conflict-free 8-byte fragment loads).  GEMM_PLAIN forms the sums in registers.
 template <int MODE, int WM, int WN, int TMW>
 __global__ void __launch_bounds__(32 * WM * WN, CHEST_3M ? ((WM * WN == 8) ? 1 : 2) : ((WM * WN == 8) ? 2 : 3))
 k_gemm(GemmParams p) {
     constexpr int TM = 8 * TMW * WM, TN = 16 * WN, KT = 16, LDS = KT + 4, NTHR = 32 * WM * WN;
-    extern __shared__ double smem[];
+    constexpr bool PRE3 = CHEST_3M && MODE != GEMM_PLAIN;
+    extern __shared__ __align__(128) double smem[];
     cplx (*As)[TM][LDS] = reinterpret_cast<cplx (*)[TM][LDS]>(smem);
     cplx (*Bs)[TN][LDS] = reinterpret_cast<cplx (*)[TN][LDS]>(smem + 2 * 2 * TM * LDS);
+    double (*As2)[TM][LDS] = reinterpret_cast<double (*)[TM][LDS]>(smem + 2 * 2 * (TM + TN) * LDS);
+    double (*Bs2)[TN][LDS] = reinterpret_cast<double (*)[TN][LDS]>(smem + 2 * 2 * (TM + TN) * LDS + 2 * TM * LDS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t4 = lane & 3;
@@ -279,14 +304,13 @@ k_gemm(GemmParams p) {
     const int rep = (MODE == GEMM_D) ? (int)blockIdx.z + p.rep0 : 0;
     int klo = p.mt_klo ? p.mt_klo[mt] : 0, khi = p.mt_khi ? p.mt_khi[mt] : p.Kc;
     if (MODE == GEMM_D) { klo = max(klo, p.nt_klo[nt]); khi = min(khi, p.nt_khi[nt]); }
+    if (PRE3) klo &= ~1;                                  // the double planes are copied in aligned pairs
     // GEMM_D writes D row-tile-major: D[rep][rt = m/8][col][m%8], so that the perfect-CSI interference pass
     // streams the 8 rows of a DMMA row tile as one contiguous block (K*128 bytes)
     const int RT8 = ((p.M + 7) / 8) * 8;
     cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * RT8 * p.n_cols : 0);
     const bool conj_a = p.conj_a != 0;
 
-    // Complex products use the three-multiplication form (CHEST_3M, common.cuh): per 8x8 tile the partial sums
-    // c1 = (ar+ai) br, cr = -ai (br+bi), ci = ar (bi-br); the epilogue forms re = c1 + cr, im = c1 + ci.
     double cr[TMW][2][2], ci[TMW][2][2], c1[CHEST_3M ? TMW : 1][2][2];
 #pragma unroll
     for (int a = 0; a < TMW; ++a)
@@ -302,7 +326,16 @@ k_gemm(GemmParams p) {
             int idx = tid + e * NTHR, kk = idx & (KT - 1), r = idx / KT;
             int gk = k0 + kk, gm = m0 + r;
             bool ok = gm < p.M && gk < khi;
-            cp_async16(&As[stage][r][kk], p.At + (ok ? (int64_t)gk + (int64_t)p.lda * gm : 0), ok);
+            cp_async16(&As[stage][r][kk], (PRE3 ? p.At1 : p.At) + (ok ? (int64_t)gk + (int64_t)p.lda * gm : 0), ok);
+        }
+        if (PRE3) {
+#pragma unroll
+            for (int e = 0; e < (TM * KT / 2) / NTHR; ++e) { // third A value: pairs of doubles
+                int idx = tid + e * NTHR, kk = (idx & (KT / 2 - 1)) * 2, r = idx / (KT / 2);
+                int gk = k0 + kk, gm = m0 + r;
+                bool ok = gm < p.M && gk < khi;
+                cp_async16(&As2[stage][r][kk], p.At2 + (ok ? (int64_t)gk + (int64_t)p.lda * gm : 0), ok);
+            }
         }
 #pragma unroll
         for (int e = 0; e < (TN * KT) / NTHR; ++e) {         // B tile: TN cols x 16 k
@@ -312,7 +345,7 @@ k_gemm(GemmParams p) {
             if (MODE == GEMM_PLAIN) {
                 cp_async16(&Bs[stage][c][kk], p.bsrc + (ok ? (int64_t)col * p.ldb + gk : 0), ok);
             } else if (MODE == GEMM_D) {
-                cp_async16(&Bs[stage][c][kk], p.bsrc + (ok ? ((int64_t)rep * p.n_cols + col) * p.ldb + gk : 0), ok);
+                cp_async16(&Bs[stage][c][kk], (PRE3 ? p.b1src : p.bsrc) + (ok ? ((int64_t)rep * p.n_cols + col) * p.ldb + gk : 0), ok);
             } else {
                 cplx v = cmake(0.0, 0.0);
                 if (ok) {
@@ -322,11 +355,42 @@ k_gemm(GemmParams p) {
                     double sc = p.noise_scale[snr];
                     v = cmake(a.x + sc * nz.x, a.y + sc * nz.y);
                 }
-                Bs[stage][c][kk] = v;
+                if (PRE3) { Bs[stage][c][kk] = cmake(v.x, v.x + v.y); Bs2[stage][c][kk] = v.y - v.x; }
+                else Bs[stage][c][kk] = v;
+            }
+        }
+        if (PRE3 && MODE == GEMM_D) {
+#pragma unroll
+            for (int e = 0; e < (TN * KT / 2) / NTHR; ++e) {
+                int idx = tid + e * NTHR, kk = (idx & (KT / 2 - 1)) * 2, c = idx / (KT / 2);
+                int gk = k0 + kk, col = n0 + c;
+                bool ok = col < p.n_cols && gk < khi;
+                cp_async16(&Bs2[stage][c][kk], p.b2src + (ok ? ((int64_t)rep * p.n_cols + col) * p.ldb + gk : 0), ok);
             }
         }
     };
 
+    // warp-level clipping: a warp skips the k-steps outside the support of its own rows / columns (the CTA range
+    // is the union over 2 x 3 warp tiles; for the FBMC grid a warp's 24 rows are one time position)
+    int wlo = klo, whi = khi;
+    if (p.m8_klo) {
+        int lo = 0x7fffffff, hi = 0;
+#pragma unroll
+        for (int x = 0; x < TMW; ++x) {
+            const int r = m0 + wm * 8 * TMW + x * 8;
+            if (r < p.M) { lo = min(lo, p.m8_klo[r >> 3]); hi = max(hi, p.m8_khi[r >> 3]); }
+        }
+        wlo = max(wlo, lo); whi = min(whi, hi);
+    }
+    if (MODE == GEMM_D && p.n8_klo) {
+        int lo = 0x7fffffff, hi = 0;
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+            const int cc = n0 + wn * 16 + y * 8;
+            if (cc < p.n_cols) { lo = min(lo, p.n8_klo[cc >> 3]); hi = max(hi, p.n8_khi[cc >> 3]); }
+        }
+        wlo = max(wlo, lo); whi = min(whi, hi);
+    }
     const int nk = (khi - klo + KT - 1) / KT;
     if (nk > 0) {
         fill(0, klo);
@@ -336,43 +400,59 @@ k_gemm(GemmParams p) {
     for (int kt = 0; kt < nk; ++kt) {
         const int st = kt & 1;
         if (kt + 1 < nk) fill(st ^ 1, klo + (kt + 1) * KT);
+        const int kbase = klo + kt * KT;
 #pragma unroll
         for (int kk = 0; kk < KT; kk += 4) {
+            if (kbase + kk + 4 <= wlo || kbase + kk >= whi) continue;     // warp-uniform
             cplx a[TMW], b[2];
 #pragma unroll
             for (int x = 0; x < TMW; ++x) a[x] = As[st][wm * 8 * TMW + x * 8 + g][kk + t4];
 #pragma unroll
             for (int y = 0; y < 2; ++y) b[y] = Bs[st][wn * 16 + y * 8 + g][kk + t4];
-#if CHEST_3M
-            double bs[2], bd[2];
+            if (PRE3) {
+                double a2[TMW], b2[2];
 #pragma unroll
-            for (int y = 0; y < 2; ++y) { bs[y] = b[y].x + b[y].y; bd[y] = b[y].y - b[y].x; }
+                for (int x = 0; x < TMW; ++x) a2[x] = As2[st][wm * 8 * TMW + x * 8 + g][kk + t4];
 #pragma unroll
-            for (int x = 0; x < TMW; ++x) {
-                const double ai = conj_a ? dneg(a[x].y) : a[x].y;
-                const double nai = conj_a ? a[x].y : dneg(a[x].y);
-                const double as = a[x].x + ai;
+                for (int y = 0; y < 2; ++y) b2[y] = Bs2[st][wn * 16 + y * 8 + g][kk + t4];
 #pragma unroll
-                for (int y = 0; y < 2; ++y) {
-                    dmma884(c1[x][y][0], c1[x][y][1], as, b[y].x);
-                    dmma884(cr[x][y][0], cr[x][y][1], nai, bs[y]);
-                    dmma884(ci[x][y][0], ci[x][y][1], a[x].x, bd[y]);
+                for (int x = 0; x < TMW; ++x)
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        dmma884(c1[CHEST_3M ? x : 0][y][0], c1[CHEST_3M ? x : 0][y][1], a[x].y, b[y].x);   // (ar+ai') br
+                        dmma884(cr[x][y][0], cr[x][y][1], a2[x], b[y].y);                                  // -ai' (br+bi)
+                        dmma884(ci[x][y][0], ci[x][y][1], a[x].x, b2[y]);                                  // ar (bi-br)
+                    }
+            } else if (CHEST_3M) {
+                double bs[2], bd[2];
+#pragma unroll
+                for (int y = 0; y < 2; ++y) { bs[y] = b[y].x + b[y].y; bd[y] = b[y].y - b[y].x; }
+#pragma unroll
+                for (int x = 0; x < TMW; ++x) {
+                    const double ai = conj_a ? dneg(a[x].y) : a[x].y;
+                    const double nai = conj_a ? a[x].y : dneg(a[x].y);
+                    const double as = a[x].x + ai;
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        dmma884(c1[CHEST_3M ? x : 0][y][0], c1[CHEST_3M ? x : 0][y][1], as, b[y].x);
+                        dmma884(cr[x][y][0], cr[x][y][1], nai, bs[y]);
+                        dmma884(ci[x][y][0], ci[x][y][1], a[x].x, bd[y]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < TMW; ++x) {
+                    const double ai = conj_a ? dneg(a[x].y) : a[x].y;
+                    const double nai = conj_a ? a[x].y : dneg(a[x].y);
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        dmma884(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
+                        dmma884(cr[x][y][0], cr[x][y][1], nai, b[y].y);
+                        dmma884(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
+                        dmma884(ci[x][y][0], ci[x][y][1], ai, b[y].x);
+                    }
                 }
             }
-#else
-#pragma unroll
-            for (int x = 0; x < TMW; ++x) {
-                const double ai = conj_a ? dneg(a[x].y) : a[x].y;
-                const double nai = conj_a ? a[x].y : dneg(a[x].y);
-#pragma unroll
-                for (int y = 0; y < 2; ++y) {
-                    dmma884(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
-                    dmma884(cr[x][y][0], cr[x][y][1], nai, b[y].y);
-                    dmma884(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
-                    dmma884(ci[x][y][0], ci[x][y][1], ai, b[y].x);
-                }
-            }
-#endif
         }
         cp_async_wait_all();
         __syncthreads();
