@@ -84,7 +84,7 @@ struct Scheme {
     bool set = false;
     int waveform = 0, K = 0, K_in = 0, P = 0, n_data = 0, detect = 0, constellation = 0, n_bits = 0;
     double kappa = 1, dpr = 1;
-    DevBuf<int> c_rowptr, c_col, ct_colptr, ct_row, pilot_pos, data_pos, row_col0, long_rows;
+    DevBuf<int> c_rowptr, c_col, ct_colptr, ct_row, pilot_pos, data_pos, pos2data, row_col0, long_rows;
     DevBuf<cplx> row_val0; int n_long_rows = 0;
     DevBuf<cplx> c_val, ct_val;
     DevBuf<uint32_t> edge_mask;
@@ -189,7 +189,7 @@ SchemeDev scheme_dev(Ctx* c, int si) {
     d.sqrt_kappa = std::sqrt(s.kappa); d.dpr = s.dpr; d.sqrt_dpr = std::sqrt(s.dpr);
     d.c_rowptr = s.c_rowptr.p; d.c_col = s.c_col.p; d.c_val = s.c_val.p;
     d.ct_colptr = s.ct_colptr.p; d.ct_row = s.ct_row.p; d.ct_val = s.ct_val.p;
-    d.pilot_pos = s.pilot_pos.p; d.data_pos = s.data_pos.p; d.edge_mask = s.edge_mask.p;
+    d.pilot_pos = s.pilot_pos.p; d.data_pos = s.data_pos.p; d.pos2data = s.pos2data.p; d.edge_mask = s.edge_mask.p;
     d.row_col0 = s.row_col0.p; d.row_val0 = s.row_val0.p; d.long_rows = s.long_rows.p; d.n_long_rows = s.n_long_rows;
     d.wdiag_frag[0] = s.mm[0].diag_frag.p; d.wdiag_frag[1] = s.mm[1].diag_frag.p;
     for (int v = 0; v < 2; ++v) {
@@ -400,7 +400,8 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     const size_t main_smem = ((size_t)ip.stage_cplx + (size_t)2 * ip.pilot_rows * (NC_MAX + 2)) * sizeof(cplx)
                              + (size_t)ip.pilot_rows * EST_H1S * sizeof(double);
     // light: new pilot estimates + constellation tables
-    const size_t light_smem = (size_t)ip.pilot_rows * (NC_MAX + 2) * sizeof(cplx) + cst_smem;
+    // light: new pilot estimates, transmitted pilots, constellation tables, decided words (one byte per symbol)
+    const size_t light_smem = (size_t)ip.pilot_rows * (2 * NC_MAX + 2) * sizeof(cplx) + cst_smem + (size_t)c->K_max * NC_MAX;
     if (c->ic_grid == 0 || c->ic_smem != main_smem) {              // persistent main grid: one wave of resident CTAs
         CK(cudaFuncSetAttribute(k_ic_main, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CK(cudaFuncSetAttribute(k_ic_light, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -512,7 +513,7 @@ int chest_destroy(uint64_t handle) {
     for (auto& k : c->cst) { k.symbol.release(); k.pilot.release(); k.level.release(); k.word_of_grid.release(); }
     for (auto& s : c->sch) {
         s.c_rowptr.release(); s.c_col.release(); s.ct_colptr.release(); s.ct_row.release(); s.pilot_pos.release();
-        s.data_pos.release(); s.row_col0.release(); s.long_rows.release(); s.row_val0.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
+        s.data_pos.release(); s.pos2data.release(); s.row_col0.release(); s.long_rows.release(); s.row_val0.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
         s.hP.release(); s.hdiag.release(); s.xD[0].release(); s.xD[1].release(); s.txword.release(); s.bits.release();
         for (auto& m : s.mm) {
             m.tile_ptr.release(); m.tile_delta.release(); m.table.release(); m.diag_frag.release();
@@ -715,10 +716,18 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
     std::vector<int> pp(pilot_pos, pilot_pos + P);
     for (int x : pp) ARG(x >= 0 && x < K);
     CK(s.pilot_pos.upload(pp, c->stream));
-    if (data_pos) {
-        std::vector<int> dp(data_pos, data_pos + n_data);
-        for (int x : dp) ARG(x >= 0 && x < K);
-        CK(s.data_pos.upload(dp, c->stream));
+    {
+        std::vector<int> p2d(K, -1);                       // position -> data symbol read off it (select schemes)
+        if (data_pos) {
+            std::vector<int> dp(data_pos, data_pos + n_data);
+            for (int d = 0; d < n_data; ++d) {
+                ARG(dp[d] >= 0 && dp[d] < K);
+                if (p2d[dp[d]] >= 0) return fail(CHEST_ERR_ARG, "two data symbols are read off the same position");
+                p2d[dp[d]] = d;
+            }
+            CK(s.data_pos.upload(dp, c->stream));
+        }
+        CK(s.pos2data.upload(p2d, c->stream));
     }
     std::vector<uint32_t> mask(n_data, 0);
     s.considered.assign(considered, considered + (size_t)n_data * nb);

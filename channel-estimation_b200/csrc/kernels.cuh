@@ -189,6 +189,7 @@ struct SchemeDev {
     const int* c_rowptr; const int* c_col; const cplx* c_val;      // precoder C, CSR (K rows)
     const int* ct_colptr; const int* ct_row; const cplx* ct_val;   // precoder C, CSC (K_in cols)
     const int* pilot_pos; const int* data_pos; const uint32_t* edge_mask;   // per data symbol bit mask
+    const int* pos2data;           // [K] data-symbol index read off position i (select schemes), -1 otherwise
     // precoder rows with a single entry (ELL-1): column (-1: empty row, -2: long row) and value; long rows listed
     const int* row_col0; const cplx* row_val0; const int* long_rows; int n_long_rows;
     const cplx* wdiag_frag[2];     // [snr][rt][pq][32 lanes]: W[i,i,p] in DMMA A-fragment order (phase D)
@@ -1002,15 +1003,26 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
 #define IC_LIGHT_WAVES 64      // grid of the light kernel in units of one resident wave (i.e. one CTA per unit)
 #endif
 #define IC_LIGHT_THREADS 256
+// Hard decision of one data-symbol estimate: bit errors against the transmitted word, and the decided word
+// (the quantised symbol of the next iteration's cancellation, DS.m:482-484).
+__device__ __forceinline__ int ic_decide(const ConstDev& cd, cplx xd, uint32_t tw, uint32_t em, unsigned& e_all, unsigned& e_edge) {
+    const int word = demap_word(cd, xd);
+    const uint32_t diff = (uint32_t)word ^ tw;
+    e_all += __popc(diff);
+    e_edge += __popc(diff & em);
+    return word;
+}
 __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(IcParams p) {
     constexpr int NC = NC_MAX, HS = NC + 2;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int it = p.it;
-    extern __shared__ cplx ic_smem[];
-    cplx* hPn = ic_smem;                                    // new pilot estimates [p][col]
+    extern __shared__ __align__(128) cplx ic_smem[];
+    cplx* hPn = ic_smem;                                    // new pilot estimates [p][col] (zero padded to 4*P4 rows)
+    cplx* xPs = hPn + p.pilot_rows * HS;                    // transmitted pilots of the unit's columns [p][col]
     __shared__ IcShared sh;
+    uint8_t* zw;                                            // decided words of the data symbols [d][col]
     {   // constellation tables (levels, grid -> word, word -> symbol) in shared memory
-        cplx* q = ic_smem + p.pilot_rows * HS;
+        cplx* q = xPs + p.pilot_rows * NC;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const ConstDev& cg = p.cst[k];
@@ -1021,16 +1033,17 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
             for (int e = tid; e < cg.n_axis; e += nthr) lev[e] = cg.level[e];
             if (tid == 0) { sh.cst[k] = cg; sh.cst[k].symbol = sym; sh.cst[k].level = lev; sh.cst[k].word_of_grid = gr; }
         }
+        zw = reinterpret_cast<uint8_t*>(q);
     }
-    const bool next_pre = it < p.n_iter;                    // build z and v of iteration it+1
+    const bool last = it == p.n_iter;                       // the last iteration leaves the state chest_get_state reads
+    const bool next_pre = !last;                            // otherwise build v of iteration it+1
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         const IcCta cta = p.ctas[unit];
         ic_load_unit(p, cta, sh);
         const int csi = cta.mode;
         const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
         const int K = p.sch[p.wf_scheme[wf][0]].K;
-        cplx* zbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC;
-        cplx* vbuf = zbuf + (int64_t)p.K_max * NC;
+        cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
         const cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
         // y_ic of this unit: the cancelled symbols, or y itself in the one-tap stage
         auto yic = [&](int i, int c) -> cplx {
@@ -1038,6 +1051,16 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
             const cplx* yp = sh.ycolp[c];
             return yp ? yp[i] : cmake(1.0, 0.0);
         };
+        bool any_despread = false;
+        for (int c = 0; c < cta.n_cols; ++c) any_despread |= p.sch[sh.c_scheme[c]].detect_mode == 1;
+        {   // transmitted pilots of the columns (phase C divides by them, phase A re-inserts them)
+            const int Pw = p.sch[p.wf_scheme[wf][0]].P;
+            for (int idx = tid; idx < Pw * NC; idx += nthr) {
+                const int c = idx % NC, pp = idx / NC;
+                xPs[pp * NC + c] = sh.c_rep[c] >= 0 ? p.sch[sh.c_scheme[c]].xP[(int64_t)sh.c_rep[c] * Pw + pp] : cmake(1.0, 0.0);
+            }
+            __syncthreads();
+        }
         // ---- phase C: LS pilot estimates from the (cancelled) symbols   (DS.m:412-414, 487-489)
         if (csi == 0) {
             const SchemeDev& sd = p.sch[cta.scheme_or_wf];
@@ -1045,7 +1068,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 int c = idx % NC, pp = idx / NC;
                 cplx hp = cmake(0.0, 0.0);
                 if (sh.c_rep[c] >= 0 && pp < sd.P) {
-                    cplx q = cdiv(yic(sd.pilot_pos[pp], c), sd.xP[(int64_t)sh.c_rep[c] * sd.P + pp]);
+                    cplx q = cdiv(yic(sd.pilot_pos[pp], c), xPs[pp * NC + c]);
                     hp = cmake(q.x / sd.sqrt_kappa, q.y / sd.sqrt_kappa);
                     sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] = hp;
                 }
@@ -1053,15 +1076,20 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
             }
             __syncthreads();
         }
-        // ---- phase D: one-tap channel + equalisation                  (DS.m:428-429, 515-521)
+        // ---- phases D + E: one-tap channel, equalisation (DS.m:428-429, 515-521) and, for the schemes whose data
+        //      symbols are read off single positions, the decision right away (DS.m:430-433): bit errors and the
+        //      decided word.  De-spread schemes write the equalised symbols to vbuf and are decided below.
         {
             const int var_cur = (it == 0 || it <= p.n_iter / 2) ? 0 : 1;
             if (csi == 0) {
                 // h_est = W_diag * hP as a small DMMA product per row tile (A = W[i,i,p] fragments, B = hP_new),
                 // then x_hat = y_ic / h_est on the C fragment
                 const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+                const ConstDev& cd = sh.cst[sd.constellation];
                 const int g = lane >> 2, t4 = lane & 3, RT = (K + 7) / 8, P4 = sd.P4;
+                const bool select = sd.detect_mode != 1;
                 const cplx* __restrict__ wf_ = sd.wdiag_frag[var_cur] + (int64_t)cta.snr * RT * P4 * 32;
+                unsigned e_all[2][2] = {{0, 0}, {0, 0}}, e_edge[2][2] = {{0, 0}, {0, 0}};
                 for (int rt = warp; rt < RT; rt += nwarp) {
                     double hr[2][2] = {{0, 0}, {0, 0}}, hi[2][2] = {{0, 0}, {0, 0}};
                     const int i = rt * 8 + g;
@@ -1070,6 +1098,8 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                     for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) yv[ct][e] = i < K ? yic(i, ct * 8 + 2 * t4 + e) : cmake(0.0, 0.0);
+                    const int d = (select && i < K) ? sd.pos2data[i] : -1;
+                    const uint32_t em = d >= 0 ? sd.edge_mask[d] : 0;
                     for (int pq = 0; pq < P4; ++pq) {
                         const cplx a = ld_stream(wf_ + ((int64_t)rt * P4 + pq) * 32 + lane);
                         const double nai = dneg(a.y);
@@ -1088,122 +1118,144 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int c = ct * 8 + 2 * t4 + e;
-                                cplx xh = cmake(0.0, 0.0);
-                                if (sh.c_rep[c] >= 0) {
-                                    const cplx hh = cmake(hr[ct][e], hi[ct][e]);
-                                    sd.hdiag[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * K + i] = hh;
-                                    xh = cdiv(yv[ct][e], hh);
-                                }
-                                vbuf[i * NC + c] = xh;
+                                if (sh.c_rep[c] < 0) continue;
+                                const int64_t col = (int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c];
+                                const cplx hh = cmake(hr[ct][e], hi[ct][e]);
+                                if (last) sd.hdiag[col * K + i] = hh;
+                                const cplx xh = cdiv(yv[ct][e], hh);
+                                if (!select) { vbuf[i * NC + c] = xh; continue; }
+                                if (d < 0) continue;
+                                const cplx xd = cmake(xh.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y / sd.sqrt_dpr);
+                                const int word = ic_decide(cd, xd, sd.txword[(int64_t)sh.c_rep[c] * sd.n_data + d], em, e_all[ct][e], e_edge[ct][e]);
+                                if (last) sd.xD[0][col * sd.n_data + d] = xd;
+                                if (next_pre) zw[d * NC + c] = (uint8_t)word;
                             }
                     }
+                }
+                if (select) {                                  // lanes with the same t4 hold the same four columns
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            unsigned a = e_all[ct][e], b = e_edge[ct][e];
+#pragma unroll
+                            for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                            if (g == 0) {
+                                if (a) atomicAdd(&sh.cnt[ct * 8 + 2 * t4 + e][0], a);
+                                if (b) atomicAdd(&sh.cnt[ct * 8 + 2 * t4 + e][1], b);
+                            }
+                        }
                 }
             } else {
                 const int c = tid % NC;
                 const bool okc = sh.c_rep[c] >= 0;
+                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                const ConstDev& cd = sh.cst[sd.constellation];
+                const bool select = sd.detect_mode != 1;
                 const cplx* __restrict__ ht = p.htrue[wf] + (int64_t)(okc ? sh.c_rep[c] : 0) * K;
+                const int64_t colbase = ((int64_t)sh.c_snr[c] * p.n_rep + (okc ? sh.c_rep[c] : 0)) * sd.n_data;
+                const uint32_t* __restrict__ txw = sd.txword + (int64_t)(okc ? sh.c_rep[c] : 0) * sd.n_data;
+                unsigned e_all = 0, e_edge = 0;
                 const int istep = nthr / NC;
                 for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
                     cplx yv[8], hv[8];
+                    int dd[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int i = i0 + u * istep;
                         yv[u] = (okc && i < K) ? yic(i, c) : cmake(0.0, 0.0);
                         hv[u] = (okc && i < K) ? ht[i] : cmake(1.0, 0.0);
+                        dd[u] = (okc && select && i < K) ? sd.pos2data[i] : -1;
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int i = i0 + u * istep;
-                        if (i < K) vbuf[i * NC + c] = okc ? cdiv(yv[u], hv[u]) : cmake(0.0, 0.0);
+                        if (i >= K || !okc) continue;
+                        const cplx xh = cdiv(yv[u], hv[u]);
+                        if (!select) { vbuf[i * NC + c] = xh; continue; }
+                        const int d = dd[u];
+                        if (d < 0) continue;
+                        const cplx xd = cmake(xh.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y / sd.sqrt_dpr);
+                        const int word = ic_decide(cd, xd, txw[d], sd.edge_mask[d], e_all, e_edge);
+                        if (last) sd.xD[1][colbase + d] = xd;
+                        if (next_pre) zw[d * NC + c] = (uint8_t)word;
                     }
                 }
+                if (e_all) atomicAdd(&sh.cnt[c][0], e_all);
+                if (e_edge) atomicAdd(&sh.cnt[c][1], e_edge);
             }
             __syncthreads();
         }
-        // ---- phase E: data-symbol estimates, demap, bit errors         (DS.m:430-433 ...); the hard decisions
-        //      are also the quantised symbols of the next iteration's cancellation (DS.m:482-484): z = [xP; Q(xD)]
-        {
+        // ---- phase E for de-spread schemes: x_d = C_d^H x_hat / dpr over the spreading set   (DS.m:430-433 ...)
+        if (any_despread) {
             // the block size is a multiple of 16, so a thread keeps its column: counters stay in registers
             const int c = tid % NC;
-            unsigned int e_all = 0, e_edge = 0;
-            if (sh.c_rep[c] >= 0) {
-                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            unsigned e_all = 0, e_edge = 0;
+            const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            if (sh.c_rep[c] >= 0 && sd.detect_mode == 1) {
                 const ConstDev& cd = sh.cst[sd.constellation];
                 const int64_t colbase = ((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.n_data;
                 const uint32_t* __restrict__ txw = sd.txword + (int64_t)sh.c_rep[c] * sd.n_data;
                 const int dstep = nthr / NC;
-                if (next_pre) {
-                    const cplx* __restrict__ xpp = sd.xP + (int64_t)sh.c_rep[c] * sd.P;
-                    for (int k = tid / NC; k < sd.P; k += dstep) zbuf[k * NC + c] = xpp[k];
-                }
                 for (int d0 = tid / NC; d0 < sd.n_data; d0 += 4 * dstep) {
                     cplx xd[4];
-                    uint32_t tw[4], em[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {                      // four data symbols in flight per thread
                         const int d = d0 + u * dstep;
-                        xd[u] = cmake(0.0, 0.0); tw[u] = 0; em[u] = 0;
+                        xd[u] = cmake(0.0, 0.0);
                         if (d < sd.n_data) {
-                            tw[u] = txw[d]; em[u] = sd.edge_mask[d];
-                            if (sd.detect_mode == 1) {
-                                cplx acc = cmake(0.0, 0.0);
-                                const int k = sd.P + d;
-                                const int e1 = sd.ct_colptr[k + 1];
-                                for (int e = sd.ct_colptr[k]; e < e1; e += 8) {
-                                    cplx cvv[8], xx[8];
+                            cplx acc = cmake(0.0, 0.0);
+                            const int k = sd.P + d;
+                            const int e1 = sd.ct_colptr[k + 1];
+                            for (int e = sd.ct_colptr[k]; e < e1; e += 8) {
+                                cplx cvv[8], xx[8];
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const bool in = e + q < e1;
-                                        cvv[q] = in ? sd.ct_val[e + q] : cmake(0.0, 0.0);
-                                        xx[q] = in ? vbuf[sd.ct_row[e + q] * NC + c] : cmake(0.0, 0.0);
-                                    }
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        cplx t = cmulc(cvv[q], xx[q]);
-                                        acc.x += t.x; acc.y += t.y;
-                                    }
+                                for (int q = 0; q < 8; ++q) {
+                                    const bool in = e + q < e1;
+                                    cvv[q] = in ? sd.ct_val[e + q] : cmake(0.0, 0.0);
+                                    xx[q] = in ? vbuf[sd.ct_row[e + q] * NC + c] : cmake(0.0, 0.0);
                                 }
-                                xd[u] = cmake(acc.x / sd.dpr, 0.0);
-                            } else {
-                                cplx v = vbuf[sd.data_pos[d] * NC + c];
-                                xd[u] = cmake(v.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : v.y / sd.sqrt_dpr);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    cplx t = cmulc(cvv[q], xx[q]);
+                                    acc.x += t.x; acc.y += t.y;
+                                }
                             }
+                            xd[u] = cmake(acc.x / sd.dpr, 0.0);
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int d = d0 + u * dstep;
                         if (d < sd.n_data) {
-                            sd.xD[csi][colbase + d] = xd[u];
-                            const int word = demap_word(cd, xd[u]);
-                            if (next_pre) zbuf[(sd.P + d) * NC + c] = cd.symbol[word];
-                            uint32_t diff = (uint32_t)word ^ tw[u];
-                            e_all += __popc(diff);
-                            e_edge += __popc(diff & em[u]);
+                            const int word = ic_decide(cd, xd[u], txw[d], sd.edge_mask[d], e_all, e_edge);
+                            if (last) sd.xD[csi][colbase + d] = xd[u];
+                            if (next_pre) zw[d * NC + c] = (uint8_t)word;
                         }
                     }
                 }
             }
             if (e_all) atomicAdd(&sh.cnt[c][0], e_all);
             if (e_edge) atomicAdd(&sh.cnt[c][1], e_edge);
-            __syncthreads();                                   // also: phase E readers of vbuf done, z complete
-            if (tid < 2 * NC) {
-                int cc = tid >> 1, e = tid & 1;
-                if (cc < cta.n_cols && sh.c_rep[cc] >= 0) {
-                    int64_t o = ((((int64_t)sh.c_rep[cc] * p.n_snr + sh.c_snr[cc]) * (p.n_iter + 1) + it) * 3 + sh.c_scheme[cc]) * 4 + csi * 2 + e;
-                    p.err[o] = sh.cnt[cc][e];
-                }
+            __syncthreads();                                   // readers of vbuf done, decided words complete
+        }
+        if (tid < 2 * NC) {
+            int cc = tid >> 1, e = tid & 1;
+            if (cc < cta.n_cols && sh.c_rep[cc] >= 0) {
+                int64_t o = ((((int64_t)sh.c_rep[cc] * p.n_snr + sh.c_snr[cc]) * (p.n_iter + 1) + it) * 3 + sh.c_scheme[cc]) * 4 + csi * 2 + e;
+                p.err[o] = sh.cnt[cc][e];
             }
         }
         if (!next_pre) continue;
-        // ---- phase A of iteration it+1: v = C z   (DS.m:482-484, 541-543)
+        // ---- phase A of iteration it+1: v = C z with z = [xP; decided symbols]   (DS.m:482-484, 541-543)
         {   // rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread
             const int c = tid % NC;
             const bool okc = sh.c_rep[c] >= 0;
             const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            const cplx* sym = sh.cst[sd.constellation].symbol;
             const int istep = nthr / NC;
             for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
-                int col[8]; cplx val[8], zz[8];
+                int col[8]; cplx val[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = i0 + u * istep;
@@ -1211,20 +1263,23 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                     val[u] = (okc && i < K) ? sd.row_val0[i] : cmake(0.0, 0.0);
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) zz[u] = col[u] >= 0 ? zbuf[col[u] * NC + c] : cmake(0.0, 0.0);
-#pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = i0 + u * istep;
-                    if (i < K && col[u] != -2) vbuf[i * NC + c] = cmul(val[u], zz[u]);
+                    if (i < K && col[u] != -2) {
+                        const cplx zz = col[u] < 0 ? cmake(0.0, 0.0)
+                                       : (col[u] < sd.P ? xPs[col[u] * NC + c] : sym[zw[(col[u] - sd.P) * NC + c]]);
+                        vbuf[i * NC + c] = cmul(val[u], zz);
+                    }
                 }
             }
         }
         // long rows (auxiliary symbols, spread symbols): one warp per row, lane = 16*h + c handles column c
-        // and every second entry (h = 0/1), eight independent loads in flight; halves combined by shuffle.
+        // and every second entry (h = 0/1); halves combined by shuffle.
         {
             const int c = lane & 15, h = lane >> 4;
             const bool okc = sh.c_rep[c] >= 0;
             const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            const cplx* sym = sh.cst[sd.constellation].symbol;
             const int* __restrict__ rp = sd.c_rowptr;
             const int* __restrict__ cc = sd.c_col;
             const cplx* __restrict__ cv = sd.c_val;
@@ -1236,15 +1291,10 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 cplx acc = cmake(0.0, 0.0);
                 if (okr) {
                     const int e1 = rp[i + 1];
-                    int e = rp[i] + h;
-                    for (; e + 14 < e1; e += 16) {
-                        cplx cvv[8], zz[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) { cvv[u] = cv[e + 2 * u]; zz[u] = zbuf[cc[e + 2 * u] * NC + c]; }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) cfma(acc, cvv[u], zz[u]);
+                    for (int e = rp[i] + h; e < e1; e += 2) {
+                        const int k = cc[e];
+                        cfma(acc, cv[e], k < sd.P ? xPs[k * NC + c] : sym[zw[(k - sd.P) * NC + c]]);
                     }
-                    for (; e < e1; e += 2) cfma(acc, cv[e], zbuf[cc[e] * NC + c]);
                 }
                 acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
                 acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
