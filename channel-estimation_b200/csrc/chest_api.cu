@@ -84,7 +84,8 @@ struct Scheme {
     bool set = false;
     int waveform = 0, K = 0, K_in = 0, P = 0, n_data = 0, detect = 0, constellation = 0, n_bits = 0;
     double kappa = 1, dpr = 1;
-    DevBuf<int> c_rowptr, c_col, ct_colptr, ct_row, pilot_pos, data_pos, pos2data, row_col0, long_rows;
+    DevBuf<int> c_rowptr, c_col, ct_colptr, ct_row, pilot_pos, data_pos, pos2data, row_col0, long_rows, lr_ptr, lr_kcol;
+    DevBuf<cplx> lr_frag; int n_lr_tiles = 0;
     DevBuf<cplx> row_val0; int n_long_rows = 0;
     DevBuf<cplx> c_val, ct_val;
     DevBuf<uint32_t> edge_mask;
@@ -191,6 +192,7 @@ SchemeDev scheme_dev(Ctx* c, int si) {
     d.ct_colptr = s.ct_colptr.p; d.ct_row = s.ct_row.p; d.ct_val = s.ct_val.p;
     d.pilot_pos = s.pilot_pos.p; d.data_pos = s.data_pos.p; d.pos2data = s.pos2data.p; d.edge_mask = s.edge_mask.p;
     d.row_col0 = s.row_col0.p; d.row_val0 = s.row_val0.p; d.long_rows = s.long_rows.p; d.n_long_rows = s.n_long_rows;
+    d.n_lr_tiles = s.n_lr_tiles; d.lr_ptr = s.lr_ptr.p; d.lr_kcol = s.lr_kcol.p; d.lr_frag = s.lr_frag.p;
     d.wdiag_frag[0] = s.mm[0].diag_frag.p; d.wdiag_frag[1] = s.mm[1].diag_frag.p;
     for (int v = 0; v < 2; ++v) {
         d.tile_ptr[v] = s.mm[v].tile_ptr.p; d.tile_delta[v] = s.mm[v].tile_delta.p; d.w[v] = s.mm[v].table.p;
@@ -251,9 +253,10 @@ int build_ctas(Ctx* c, int n_rep) {
     auto perf = [&](int wfi) {
         Waveform& w = c->wf[wfi];
         if (!w.set || w.nsch == 0) return;
-        int tot = w.nsch * c->S;
+        // columns: 8 * (scheme slot) + (SNR point - first); one unit per block of 8 SNR points
         for (int b = 0; b < n_rep; ++b)
-            for (int q0 = 0; q0 < tot; q0 += NC_MAX) v.push_back({1, wfi, b, q0, std::min(NC_MAX, tot - q0)});
+            for (int s0 = 0; s0 < c->S; s0 += 8)
+                v.push_back({1, wfi, b, s0, w.nsch == 2 ? 16 : std::min(8, c->S - s0)});
     };
     // heavy work first; compute-bound EST CTAs and memory-heavy PERF CTAs are interleaved so that both the
     // FP64 tensor pipe and HBM stay busy
@@ -513,7 +516,7 @@ int chest_destroy(uint64_t handle) {
     for (auto& k : c->cst) { k.symbol.release(); k.pilot.release(); k.level.release(); k.word_of_grid.release(); }
     for (auto& s : c->sch) {
         s.c_rowptr.release(); s.c_col.release(); s.ct_colptr.release(); s.ct_row.release(); s.pilot_pos.release();
-        s.data_pos.release(); s.pos2data.release(); s.row_col0.release(); s.long_rows.release(); s.row_val0.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
+        s.data_pos.release(); s.pos2data.release(); s.lr_ptr.release(); s.lr_kcol.release(); s.lr_frag.release(); s.row_col0.release(); s.long_rows.release(); s.row_val0.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
         s.hP.release(); s.hdiag.release(); s.xD[0].release(); s.xD[1].release(); s.txword.release(); s.bits.release();
         for (auto& m : s.mm) {
             m.tile_ptr.release(); m.tile_delta.release(); m.table.release(); m.diag_frag.release();
@@ -666,6 +669,7 @@ int chest_set_constellation(uint64_t handle, int which, int order, const double*
     CK(k.level.upload(lev, c->stream)); CK(k.word_of_grid.upload(grid, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     k.dev.order = order; k.dev.nbits = nb; k.dev.n_axis = k.n_axis; k.dev.is_qam = k.is_qam;
+    k.dev.inv_step = (double)(k.n_axis - 1) / (lev.back() - lev.front());
     k.dev.symbol = k.symbol.p; k.dev.pilot = k.pilot.p; k.dev.level = k.level.p; k.dev.word_of_grid = k.word_of_grid.p;
     k.set = true; c->finalized = false;
     return CHEST_OK;
@@ -709,6 +713,38 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
             else if (n > 1) { col0[i] = -2; longr.push_back(i); }
         }
         s.n_long_rows = (int)longr.size();
+        {   // long rows as DMMA tiles: 8 rows per tile, the union of their columns packed four per k-step
+            const int nt = ((int)longr.size() + 7) / 8;
+            std::vector<int> lptr(1, 0), kcol;
+            std::vector<cplx> frag;
+            for (int t = 0; t < nt; ++t) {
+                std::vector<int> u;
+                for (int g = 0; g < 8 && t * 8 + g < (int)longr.size(); ++g) {
+                    int i = longr[t * 8 + g];
+                    u.insert(u.end(), cols.begin() + rowptr[i], cols.begin() + rowptr[i + 1]);
+                }
+                std::sort(u.begin(), u.end());
+                u.erase(std::unique(u.begin(), u.end()), u.end());
+                const int n_real = (int)u.size();
+                while (u.size() % 4) u.push_back(u[0]);               // padding columns carry zero coefficients
+                for (size_t st = 0; st < u.size() / 4; ++st) {
+                    for (int q = 0; q < 4; ++q) kcol.push_back(u[st * 4 + q]);
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, q = lane & 3;
+                        cplx a = cmake(0.0, 0.0);
+                        if (t * 8 + g < (int)longr.size() && (int)(st * 4 + q) < n_real) {
+                            const int i = longr[t * 8 + g], col = u[st * 4 + q];
+                            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) if (cols[e] == col) { a.x += vcsr[e].x; a.y += vcsr[e].y; }
+                        }
+                        frag.push_back(a);
+                    }
+                }
+                lptr.push_back((int)kcol.size() / 4);
+            }
+            s.n_lr_tiles = nt;
+            if (kcol.empty()) { kcol.assign(4, 0); frag.assign(32, cmake(0.0, 0.0)); }
+            CK(s.lr_ptr.upload(lptr, c->stream)); CK(s.lr_kcol.upload(kcol, c->stream)); CK(s.lr_frag.upload(frag, c->stream));
+        }
         if (longr.empty()) longr.push_back(0);
         CK(s.row_col0.upload(col0, c->stream)); CK(s.row_val0.upload(val0, c->stream)); CK(s.long_rows.upload(longr, c->stream));
     }

@@ -156,14 +156,14 @@ struct ConstDev {
     const cplx* symbol;                 // SymbolMapping[word]
     const cplx* pilot;                  // SymbolMapping[word] / |.|
     const double* level;                // axis levels, ascending (n_axis)
+    double inv_step;                    // (n_axis - 1) / (level[n_axis-1] - level[0])
     const int* word_of_grid;            // PAM: [t] ; QAM: [ti * n_axis + tq] -> word
 };
 
 // nearest axis level, decided by the same |x - level| comparison the reference's argmin uses
-__device__ __forceinline__ int nearest_level(const double* lev, int n, double x) {
+__device__ __forceinline__ int nearest_level(const double* lev, int n, double inv_step, double x) {
     // first guess from the uniform grid (reciprocal multiply: the guess only has to be within one level,
     // the decision itself is made by the |x - level| comparisons below)
-    double inv_step = (double)(n - 1) / (lev[n - 1] - lev[0]);
     int t = (int)floor((x - lev[0]) * inv_step + 0.5);
     t = t < 0 ? 0 : (t > n - 1 ? n - 1 : t);
     double best = fabs(x - lev[t]);
@@ -172,9 +172,9 @@ __device__ __forceinline__ int nearest_level(const double* lev, int n, double x)
     return t;
 }
 __device__ __forceinline__ int demap_word(const ConstDev& cd, cplx x) {
-    if (!cd.is_qam) return cd.word_of_grid[nearest_level(cd.level, cd.n_axis, x.x)];
-    int ti = nearest_level(cd.level, cd.n_axis, x.x);
-    int tq = nearest_level(cd.level, cd.n_axis, x.y);
+    if (!cd.is_qam) return cd.word_of_grid[nearest_level(cd.level, cd.n_axis, cd.inv_step, x.x)];
+    int ti = nearest_level(cd.level, cd.n_axis, cd.inv_step, x.x);
+    int tq = nearest_level(cd.level, cd.n_axis, cd.inv_step, x.y);
     return cd.word_of_grid[ti * cd.n_axis + tq];
 }
 
@@ -192,6 +192,9 @@ struct SchemeDev {
     const int* pos2data;           // [K] data-symbol index read off position i (select schemes), -1 otherwise
     // precoder rows with a single entry (ELL-1): column (-1: empty row, -2: long row) and value; long rows listed
     const int* row_col0; const cplx* row_val0; const int* long_rows; int n_long_rows;
+    // long rows as DMMA tiles: 8 long rows per tile, the union of their columns packed four per k-step;
+    // lr_ptr [n_lr_tiles+1] -> steps, lr_kcol [step][4] column of z, lr_frag [step][32 lanes] A fragments
+    int n_lr_tiles; const int* lr_ptr; const int* lr_kcol; const cplx* lr_frag;
     const cplx* wdiag_frag[2];     // [snr][rt][pq][32 lanes]: W[i,i,p] in DMMA A-fragment order (phase D)
     // MMSE matrices: tile lists per variant, fragments per (variant, snr)
     const int* tile_ptr[2];        // [RT+1]
@@ -532,9 +535,15 @@ struct IcParams {
     unsigned long long* trace; // development: per CTA {smid, t0, t_pre, t_main_own, t_main_all, t_end, B busy ns, units}
 };
 
-__device__ __forceinline__ void ic_col(const IcParams& p, const IcCta& c, int col, int& scheme, int& snr, int& rep) {
-    if (c.mode == 0) { scheme = c.scheme_or_wf; snr = c.snr; rep = c.first + col; }
-    else { int q = c.first + col; scheme = p.wf_scheme[c.scheme_or_wf][q / p.n_snr]; snr = q % p.n_snr; rep = c.snr; }
+// Column -> (scheme, SNR point, realization); false for an unused slot.  PERF units keep each 8-column half
+// (one DMMA n-tile) on one scheme: column c = 8 * (scheme slot on the waveform) + (SNR point - first).
+__device__ __forceinline__ bool ic_col(const IcParams& p, const IcCta& c, int col, int& scheme, int& snr, int& rep) {
+    if (c.mode == 0) { scheme = c.scheme_or_wf; snr = c.snr; rep = c.first + col; return rep < p.n_rep; }
+    const int slot = col >> 3;
+    snr = c.first + (col & 7); rep = c.snr;
+    if (slot >= p.wf_nscheme[c.scheme_or_wf] || snr >= p.n_snr) { scheme = p.wf_scheme[c.scheme_or_wf][0]; snr = 0; return false; }
+    scheme = p.wf_scheme[c.scheme_or_wf][slot];
+    return true;
 }
 
 #define IC_PILOT_MAX 128
@@ -924,8 +933,7 @@ __device__ __forceinline__ void ic_load_unit(const IcParams& p, const IcCta& cta
     __syncthreads();                                   // previous unit's readers are done
     if (tid < NC_MAX) {
         int s_ = 0, n_ = 0, r_ = 0;
-        if (tid < cta.n_cols) ic_col(p, cta, tid, s_, n_, r_);
-        const bool ok = tid < cta.n_cols && r_ < p.n_rep;
+        const bool ok = tid < cta.n_cols && ic_col(p, cta, tid, s_, n_, r_);
         sh.c_scheme[tid] = s_; sh.c_snr[tid] = n_; sh.c_rep[tid] = ok ? r_ : -1;
         sh.ycolp[tid] = ok ? p.sch[s_].y + ((int64_t)n_ * p.n_rep + r_) * p.sch[s_].K : nullptr;
         sh.cnt[tid][0] = sh.cnt[tid][1] = 0;
@@ -1199,30 +1207,28 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 const int dstep = nthr / NC;
                 for (int d0 = tid / NC; d0 < sd.n_data; d0 += 4 * dstep) {
                     cplx xd[4];
+                    int e0[4], e1[4];
+                    cplx cv0[4], x0[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {                      // four data symbols in flight per thread
                         const int d = d0 + u * dstep;
-                        xd[u] = cmake(0.0, 0.0);
-                        if (d < sd.n_data) {
-                            cplx acc = cmake(0.0, 0.0);
-                            const int k = sd.P + d;
-                            const int e1 = sd.ct_colptr[k + 1];
-                            for (int e = sd.ct_colptr[k]; e < e1; e += 8) {
-                                cplx cvv[8], xx[8];
+                        e0[u] = e1[u] = 0;
+                        if (d < sd.n_data) { e0[u] = sd.ct_colptr[sd.P + d]; e1[u] = sd.ct_colptr[sd.P + d + 1]; }
+                    }
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const bool in = e + q < e1;
-                                    cvv[q] = in ? sd.ct_val[e + q] : cmake(0.0, 0.0);
-                                    xx[q] = in ? vbuf[sd.ct_row[e + q] * NC + c] : cmake(0.0, 0.0);
-                                }
+                    for (int u = 0; u < 4; ++u) {                      // first entry of each spreading set (most have one)
+                        const bool in = e0[u] < e1[u];
+                        cv0[u] = in ? sd.ct_val[e0[u]] : cmake(0.0, 0.0);
+                        x0[u] = in ? vbuf[sd.ct_row[e0[u]] * NC + c] : cmake(0.0, 0.0);
+                    }
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    cplx t = cmulc(cvv[q], xx[q]);
-                                    acc.x += t.x; acc.y += t.y;
-                                }
-                            }
-                            xd[u] = cmake(acc.x / sd.dpr, 0.0);
+                    for (int u = 0; u < 4; ++u) {
+                        cplx acc = cmulc(cv0[u], x0[u]);
+                        for (int e = e0[u] + 1; e < e1[u]; ++e) {
+                            const cplx t = cmulc(sd.ct_val[e], vbuf[sd.ct_row[e] * NC + c]);
+                            acc.x += t.x; acc.y += t.y;
                         }
+                        xd[u] = cmake(acc.x / sd.dpr, 0.0);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -1273,32 +1279,51 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 }
             }
         }
-        // long rows (auxiliary symbols, spread symbols): one warp per row, lane = 16*h + c handles column c
-        // and every second entry (h = 0/1); halves combined by shuffle.
+        // long rows (auxiliary symbols, spread symbols) on the FP64 tensor pipe: a warp takes a tile of 8 long
+        // rows; per k-step the A fragment holds their coefficients for four z rows (the tile's column union,
+        // packed by the host), the B fragment the z values of those rows for the 8 columns of an n-tile.
+        // An n-tile (8 columns) is always on one scheme; the two halves of an EST unit share the A fragments.
         {
-            const int c = lane & 15, h = lane >> 4;
-            const bool okc = sh.c_rep[c] >= 0;
-            const SchemeDev& sd = p.sch[sh.c_scheme[c]];
-            const cplx* sym = sh.cst[sd.constellation].symbol;
-            const int* __restrict__ rp = sd.c_rowptr;
-            const int* __restrict__ cc = sd.c_col;
-            const cplx* __restrict__ cv = sd.c_val;
-            int nl = 0;
-            for (int q = 0; q < cta.n_cols; ++q) nl = max(nl, p.sch[sh.c_scheme[q]].n_long_rows);
-            for (int r = warp; r < nl; r += nwarp) {
-                const bool okr = okc && r < sd.n_long_rows;
-                const int i = okr ? sd.long_rows[r] : 0;
-                cplx acc = cmake(0.0, 0.0);
-                if (okr) {
-                    const int e1 = rp[i + 1];
-                    for (int e = rp[i] + h; e < e1; e += 2) {
-                        const int k = cc[e];
-                        cfma(acc, cv[e], k < sd.P ? xPs[k * NC + c] : sym[zw[(k - sd.P) * NC + c]]);
+            const int g = lane >> 2, t4 = lane & 3;
+            const int s0 = sh.c_scheme[0], s1 = cta.n_cols > 8 ? sh.c_scheme[8] : -1;
+            for (int pass = 0; pass < 2; ++pass) {
+                // pass 0: the scheme of half 0, on both halves if they agree; pass 1: half 1 when its scheme differs
+                if (pass == 1 && (s1 < 0 || s1 == s0)) break;
+                const int si = pass == 0 ? s0 : s1;
+                const int ct0 = pass, ct1 = (pass == 0 && s1 == s0) ? 2 : pass + 1;
+                const SchemeDev& sd = p.sch[si];
+                const cplx* sym = sh.cst[sd.constellation].symbol;
+                const int P = sd.P;
+                for (int tl = warp; tl < sd.n_lr_tiles; tl += nwarp) {
+                    double cr[2][2] = {{0, 0}, {0, 0}}, ci[2][2] = {{0, 0}, {0, 0}};
+                    const int st1 = sd.lr_ptr[tl + 1];
+                    for (int st = sd.lr_ptr[tl]; st < st1; ++st) {
+                        const cplx a = ld_stream(sd.lr_frag + (int64_t)st * 32 + lane);
+                        const int kc = sd.lr_kcol[st * 4 + t4];
+                        const double nai = dneg(a.y);
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct) {
+                            if (ct < ct0 || ct >= ct1) continue;
+                            const int c = ct * 8 + g;
+                            const cplx b = kc < P ? xPs[kc * NC + c] : sym[zw[(kc - P) * NC + c]];
+                            dmma884(cr[ct][0], cr[ct][1], a.x, b.x);
+                            dmma884(cr[ct][0], cr[ct][1], nai, b.y);
+                            dmma884(ci[ct][0], ci[ct][1], a.x, b.y);
+                            dmma884(ci[ct][0], ci[ct][1], a.y, b.x);
+                        }
+                    }
+                    const int r = tl * 8 + g;
+                    if (r < sd.n_long_rows) {
+                        const int i = sd.long_rows[r];
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = ct * 8 + 2 * t4 + e;
+                                if (ct >= ct0 && ct < ct1 && sh.c_rep[c] >= 0) vbuf[i * NC + c] = cmake(cr[ct][e], ci[ct][e]);
+                            }
                     }
                 }
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-                if (okr && h == 0) vbuf[i * NC + c] = acc;
             }
         }
     }
