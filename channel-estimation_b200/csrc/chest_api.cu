@@ -55,7 +55,8 @@ struct Waveform {
     DevBuf<cplx> Q1; DevBuf<double> Q2;                // three-multiplication planes of Q^H: (re, re - im), im; row stride Np
     DevBuf<cplx> HG1; DevBuf<double> HG2;              // H*G planes: (re, re + im), im - re; [rep][K][Np]
     DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi, d_jlo, d_jhi;
-    DevBuf<int> q8_klo, q8_khi, hg8_klo, hg8_khi;      // per 8 columns of Q / of H*G (warp-level clipping in K2 / K3a)
+    DevBuf<int> q8_klo, q8_khi, hg8_klo, hg8_khi;
+    DevBuf<int2> pairs; int n_pairs = 0;               // (row tile, column tile) pairs of D with overlapping supports      // per 8 columns of Q / of H*G (warp-level clipping in K2 / K3a)
     double d_struct_pairs = 0;   // (i,j) pairs of D inside the structural support
     std::vector<int> g_lo, g_hi, q_lo, q_hi;
     std::vector<double> hg_rows;   // per column: rows of H*G written by k_apply_hg
@@ -173,6 +174,27 @@ cudaError_t launch_gemm_geo(Ctx* c, const GemmParams& p, int n_z) {
     c->launches++;
     return cudaGetLastError();
 }
+template <int WM, int WN, int TMW>
+cudaError_t launch_gemm_d_geo(Ctx* c, const GemmDParams& p) {
+    constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
+    constexpr int smem = GEMMD_STAGES * 3 * (TM + TN) * (GEMMD_KT + 4) * (int)sizeof(double);   // stages x rows x (KT+4) x (complex + double plane)
+    static int grid = 0;
+    if (!grid) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_d<WM, WN, TMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gemm_d<WM, WN, TMW>, 32 * WM * WN, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        grid = per_sm * c->n_sm;                                    // persistent: one resident wave
+    }
+    const long long total = (long long)p.n_pairs * p.n_rep;
+    if (total == 0) return cudaSuccess;
+    if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+    k_gemm_d<WM, WN, TMW><<<(int)std::min<long long>(grid, total), 32 * WM * WN, smem, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
+}
 // tile = 64 or 48 (square CTA tiles); the per-tile k-range tables must have been built for the same size
 template <int MODE>
 cudaError_t launch_gemm(Ctx* c, const GemmParams& p, int n_z, int tile) {
@@ -224,13 +246,14 @@ int stage_channel(Ctx* c, int n_rep, const double* du, const double* pu) {
 
 int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     Waveform& w = c->wf[wfi];
-    GemmParams p{};
+    GemmDParams p{};
     const int Np = (c->N + 1) & ~1;                                 // even row stride of the operand planes
-    p.M = w.K; p.Kc = c->N; p.n_cols = w.K; p.lda = Np; p.ldc = w.K; p.conj_a = 1;
-    p.At1 = w.Q1.p; p.At2 = w.Q2.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.D.p;
-    p.b1src = w.HG1.p; p.b2src = w.HG2.p; p.ldb = Np; p.N = c->N;
-    p.nt_klo = w.hg_klo.p; p.nt_khi = w.hg_khi.p; p.hdiag = w.htrue.p; p.rep0 = rep0;
+    p.M = w.K; p.n_cols = w.K; p.lda = Np; p.ldb = Np; p.n_rep = n_rep; p.rep0 = rep0;
+    p.n_pairs = w.n_pairs; p.pairs = w.pairs.p;
+    p.At1 = w.Q1.p; p.At2 = w.Q2.p; p.b1 = w.HG1.p; p.b2 = w.HG2.p;
+    p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.nt_klo = w.hg_klo.p; p.nt_khi = w.hg_khi.p;
     p.m8_klo = w.q8_klo.p; p.m8_khi = w.q8_khi.p; p.n8_klo = w.hg8_klo.p; p.n8_khi = w.hg8_khi.p;
+    p.out = w.D.p; p.hdiag = w.htrue.p;
     dim3 ghg((w.K + HG_COLS - 1) / HG_COLS, n_rep);
     if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_hg[2 * wfi], c->stream));
     k_apply_hg<<<ghg, 128, 0, c->stream>>>(w.HG1.p, w.HG2.p, w.G.p, c->h.p, c->d_tap_delay.p, w.hg_klo.p, w.hg_khi.p,
@@ -238,7 +261,8 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     c->launches++;
     CK(cudaGetLastError());
     if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_hg[2 * wfi + 1], c->stream));
-    CK(launch_gemm<GEMM_D>(c, p, n_rep, w.tile));
+    if (w.tile == 48) CK((launch_gemm_d_geo<2, 3, 3>(c, p)));
+    else CK((launch_gemm_d_geo<2, 4, 4>(c, p)));
     return CHEST_OK;
 }
 
@@ -509,7 +533,7 @@ int chest_destroy(uint64_t handle) {
     // DevBuf has no destructor on purpose (plain members); release explicitly
     auto relw = [](Waveform& w) {
         w.G.release(); w.Q.release(); w.Gt.release(); w.q_klo.release(); w.q_khi.release(); w.gt_klo.release();
-        w.gt_khi.release(); w.q8_klo.release(); w.q8_khi.release(); w.hg8_klo.release(); w.hg8_khi.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
+        w.gt_khi.release(); w.q8_klo.release(); w.q8_khi.release(); w.hg8_klo.release(); w.hg8_khi.release(); w.pairs.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
         w.y.release(); w.D.release(); w.htrue.release(); w.HG1.release(); w.HG2.release(); w.Q1.release(); w.Q2.release();
     };
     relw(c->wf[0]); relw(c->wf[1]);
@@ -881,6 +905,18 @@ int chest_finalize(uint64_t handle, int max_batch) {
         for (int j = 0; j < K; ++j) w.hg_rows[j] = std::max(0, hi[j / w.tile] - lo[j / w.tile]);
         tile_ranges(w.g_lo, w.g_hi, 8, max_delay, N, lo, hi);
         CK(w.hg8_klo.upload(lo, c->stream)); CK(w.hg8_khi.upload(hi, c->stream));
+        {   // work list of K2: tile pairs of D whose Q / H*G supports overlap (the rest of D is structurally zero)
+            std::vector<int> ql, qh, gl, gh;
+            tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, ql, qh);
+            tile_ranges(w.g_lo, w.g_hi, w.tile, max_delay, N, gl, gh);
+            std::vector<int2> pairs;
+            for (int b = 0; b < (int)gl.size(); ++b)
+                for (int a = 0; a < (int)ql.size(); ++a)
+                    if (std::min(qh[a], gh[b]) > std::max(ql[a], gl[b])) pairs.push_back(make_int2(a, b));
+            w.n_pairs = (int)pairs.size();
+            if (pairs.empty()) pairs.push_back(make_int2(0, 0));
+            CK(w.pairs.upload(pairs, c->stream));
+        }
         // support-aware work model: 8 T supp_G K  +  8 sum |supp(Q_i) ^ supp((HG)_j)|
         double f = 0;
         for (int j = 0; j < K; ++j) f += 8.0 * c->T * (w.g_hi[j] - w.g_lo[j]);
@@ -929,6 +965,8 @@ int chest_finalize(uint64_t handle, int max_batch) {
         int ns = std::max(w.nsch, 1);
         CK(w.x.alloc((size_t)ns * B * w.K)); CK(w.s.alloc((size_t)ns * B * N)); CK(w.r0.alloc((size_t)ns * B * N));
         CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.D.alloc((size_t)B * (((w.K + 7) / 8) * 8) * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
+        // tiles of D without support overlap are never written by K2: they stay at this zero
+        CK(cudaMemsetAsync(w.D.p, 0, sizeof(cplx) * (size_t)B * (((w.K + 7) / 8) * 8) * w.K, c->stream));
         {
             const size_t n_hg = (size_t)B * w.K * ((N + 1) & ~1);
             CK(w.HG1.alloc(n_hg)); CK(w.HG2.alloc(n_hg));

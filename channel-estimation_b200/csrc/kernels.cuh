@@ -482,6 +482,220 @@ k_gemm(GemmParams p) {
             }
 }
 
+// ============================================================================ K2: D = Q^H (H G), persistent
+// The transmission-matrix GEMM as a persistent kernel: every CTA walks a list of (realization, row tile,
+// column tile) work items -- only the tile pairs whose supports overlap (the others are structural zeros of D
+// and were cleared once at allocation) -- and streams their k-tiles through ONE shared-memory ring that runs
+// across tile boundaries: the first operands of the next tile are in flight while the current one finishes, so
+// there is no per-tile prologue.  Stages are handed over with mbarriers instead of block barriers:
+//   full[s]   every thread's cp.async group for stage s has landed (cp.async.mbarrier.arrive.noinc)
+//   empty[s]  every warp has finished reading stage s (one arrive per warp)
+// so a warp only ever waits for the data it needs, not for the slowest warp of the previous k-tile.  Operands
+// are the three-multiplication planes (see k_gemm): the inner loop is LDS + DMMA.
+struct GemmDParams {
+    int M, n_cols, lda, ldb, n_rep, rep0, n_pairs;
+    const int2* pairs;                           // (row tile, column tile) with overlapping supports
+    const cplx* At1; const double* At2;          // Q^H planes [m][lda]
+    const cplx* b1; const double* b2;            // H*G planes [rep][col][ldb]
+    const int* mt_klo; const int* mt_khi; const int* nt_klo; const int* nt_khi;
+    const int* m8_klo; const int* m8_khi; const int* n8_klo; const int* n8_khi;
+    cplx* out;                                   // D, row-tile-major [rep][M/8][n_cols][8]
+    cplx* hdiag;                                 // [rep][M]
+};
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared.b64 st, [%0]; }" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t* bar) {   // arrives when this thread's prior cp.async ops are done
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n .reg .pred p;\nWAIT_%=:\n mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\nDONE_%=:\n}"
+                 :: "r"(a), "r"(parity) : "memory");
+}
+
+#ifndef GEMMD_STAGES
+#define GEMMD_STAGES 2
+#endif
+#ifndef GEMMD_KT
+#define GEMMD_KT 16            // k-tile per stage (8 or 16)
+#endif
+template <int WM, int WN, int TMW>
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 1 : 2) k_gemm_d(GemmDParams p) {
+    constexpr int TM = 8 * TMW * WM, TN = 16 * WN, KT = GEMMD_KT, LDS = KT + 4, NTHR = 32 * WM * WN, NS = GEMMD_STAGES;
+    extern __shared__ __align__(128) double smem[];
+    cplx (*As)[TM][LDS] = reinterpret_cast<cplx (*)[TM][LDS]>(smem);
+    cplx (*Bs)[TN][LDS] = reinterpret_cast<cplx (*)[TN][LDS]>(smem + NS * 2 * TM * LDS);
+    double (*As2)[TM][LDS] = reinterpret_cast<double (*)[TM][LDS]>(smem + NS * 2 * (TM + TN) * LDS);
+    double (*Bs2)[TN][LDS] = reinterpret_cast<double (*)[TN][LDS]>(smem + NS * 2 * (TM + TN) * LDS + NS * TM * LDS);
+    __shared__ uint64_t full[NS], empty[NS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t4 = lane & 3;
+    if (tid == 0) {
+        for (int s_ = 0; s_ < NS; ++s_) { mbar_init(&full[s_], NTHR); mbar_init(&empty[s_], WM * WN); }
+    }
+    __syncthreads();
+    const int total = p.n_pairs * p.n_rep;                     // work items (host checks the product fits an int)
+    const int RT8 = ((p.M + 7) / 8) * 8;
+
+    // ---- consumer cursor: the item whose k-tiles the warps multiply
+    struct Cursor { int t, kt, nk, klo, khi, m0, n0, rep; };
+    auto load_item = [&](Cursor& c) {
+        if (c.t >= total) { c.nk = 0; return; }
+        c.rep = c.t / p.n_pairs;
+        const int2 mn = p.pairs[c.t - c.rep * p.n_pairs];
+        c.rep += p.rep0;
+        c.klo = max(p.mt_klo[mn.x], p.nt_klo[mn.y]) & ~1;      // the double planes are copied in aligned pairs
+        c.khi = min(p.mt_khi[mn.x], p.nt_khi[mn.y]);
+        c.nk = (c.khi - c.klo + KT - 1) / KT;
+        c.m0 = mn.x * TM; c.n0 = mn.y * TN; c.kt = 0;
+    };
+    Cursor cc;
+    cc.t = blockIdx.x;
+    load_item(cc);
+
+    // ---- producer: every thread copies fixed (row, k) slots of each stage; per item it keeps four source
+    //      pointers (advanced by KT per job) and the row-validity flags, so a job costs a handful of instructions
+    constexpr int EA = (TM * KT) / NTHR, EB = (TN * KT) / NTHR, EA2 = (TM * KT / 2) / NTHR, EB2 = (TN * KT / 2) / NTHR;
+    static_assert(EA * NTHR == TM * KT && EB * NTHR == TN * KT && EA2 * NTHR == TM * KT / 2 && EB2 * NTHR == TN * KT / 2, "tile / thread mismatch");
+    constexpr int RSTEP = NTHR / KT, RSTEP2 = NTHR / (KT / 2);         // row distance between a thread's slots
+    const int kk1 = tid & (KT - 1), r1 = tid / KT, kk2 = (tid & (KT / 2 - 1)) * 2, r2 = tid / (KT / 2);
+    const unsigned sA1 = (unsigned)__cvta_generic_to_shared(&As[0][r1][kk1]), sB1 = (unsigned)__cvta_generic_to_shared(&Bs[0][r1][kk1]);
+    const unsigned sA2 = (unsigned)__cvta_generic_to_shared(&As2[0][r2][kk2]), sB2 = (unsigned)__cvta_generic_to_shared(&Bs2[0][r2][kk2]);
+    constexpr unsigned STG_A1 = TM * LDS * 16, STG_B1 = TN * LDS * 16, STG_A2 = TM * LDS * 8, STG_B2 = TN * LDS * 8;
+    int pt = blockIdx.x, pkt = 0, pnk = 0, prem = 0;           // producer item, k-tile, k-tiles of the item, valid k left
+    const cplx* ga1 = nullptr; const cplx* gb1 = nullptr; const double* ga2 = nullptr; const double* gb2 = nullptr;
+    unsigned okA1 = 0, okB1 = 0, okA2 = 0, okB2 = 0;           // bit e: slot e of this thread is inside the matrix
+    auto producer_item = [&]() {
+        if (pt >= total) { pnk = 0; return; }
+        int rep = pt / p.n_pairs;
+        const int2 mn = p.pairs[pt - rep * p.n_pairs];
+        rep += p.rep0;
+        const int klo = max(p.mt_klo[mn.x], p.nt_klo[mn.y]) & ~1, khi = min(p.mt_khi[mn.x], p.nt_khi[mn.y]);
+        pnk = (khi - klo + KT - 1) / KT; pkt = 0; prem = khi - klo;
+        const int m0 = mn.x * TM, n0 = mn.y * TN;
+        ga1 = p.At1 + (int64_t)(m0 + r1) * p.lda + klo + kk1;
+        ga2 = p.At2 + (int64_t)(m0 + r2) * p.lda + klo + kk2;
+        gb1 = p.b1 + ((int64_t)rep * p.n_cols + n0 + r1) * p.ldb + klo + kk1;
+        gb2 = p.b2 + ((int64_t)rep * p.n_cols + n0 + r2) * p.ldb + klo + kk2;
+        okA1 = okB1 = okA2 = okB2 = 0;
+#pragma unroll
+        for (int e = 0; e < EA; ++e) okA1 |= (unsigned)(m0 + r1 + e * RSTEP < p.M) << e;
+#pragma unroll
+        for (int e = 0; e < EB; ++e) okB1 |= (unsigned)(n0 + r1 + e * RSTEP < p.n_cols) << e;
+#pragma unroll
+        for (int e = 0; e < EA2; ++e) okA2 |= (unsigned)(m0 + r2 + e * RSTEP2 < p.M) << e;
+#pragma unroll
+        for (int e = 0; e < EB2; ++e) okB2 |= (unsigned)(n0 + r2 + e * RSTEP2 < p.n_cols) << e;
+    };
+    auto cp16 = [](unsigned dst, const void* src, bool ok) {   // !ok: no read, the 16 bytes are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 16 : 0));
+    };
+    unsigned pj = 0, cj = 0;                                   // k-tile jobs produced / consumed by this thread
+    auto produce = [&]() {
+        if (pnk == 0) return;
+        const unsigned st = pj % NS;
+        if (pj >= NS) mbar_wait(&empty[st], ((pj / NS) - 1) & 1);     // every warp is done with the stage's previous job
+        const bool k1 = kk1 < prem, k2 = kk2 < prem;
+        const int64_t lda = p.lda, ldb = p.ldb;
+#pragma unroll
+        for (int e = 0; e < EA; ++e) { const bool ok = k1 && ((okA1 >> e) & 1); cp16(sA1 + st * STG_A1 + e * RSTEP * LDS * 16, ok ? ga1 + e * RSTEP * lda : p.At1, ok); }
+#pragma unroll
+        for (int e = 0; e < EA2; ++e) { const bool ok = k2 && ((okA2 >> e) & 1); cp16(sA2 + st * STG_A2 + e * RSTEP2 * LDS * 8, ok ? ga2 + e * RSTEP2 * lda : p.At2, ok); }
+#pragma unroll
+        for (int e = 0; e < EB; ++e) { const bool ok = k1 && ((okB1 >> e) & 1); cp16(sB1 + st * STG_B1 + e * RSTEP * LDS * 16, ok ? gb1 + e * RSTEP * ldb : p.b1, ok); }
+#pragma unroll
+        for (int e = 0; e < EB2; ++e) { const bool ok = k2 && ((okB2 >> e) & 1); cp16(sB2 + st * STG_B2 + e * RSTEP2 * LDS * 8, ok ? gb2 + e * RSTEP2 * ldb : p.b2, ok); }
+        mbar_arrive_cp_async(&full[st]);
+        ++pj;
+        ga1 += KT; ga2 += KT; gb1 += KT; gb2 += KT; prem -= KT;
+        if (++pkt == pnk) { pt += gridDim.x; producer_item(); }
+    };
+    producer_item();
+
+    double cr[TMW][2][2], ci[TMW][2][2], c1[TMW][2][2];
+    auto clear_acc = [&]() {
+#pragma unroll
+        for (int a = 0; a < TMW; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) { cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = c1[a][b][0] = c1[a][b][1] = 0.0; }
+    };
+    int wlo = 0, whi = 0;
+    auto warp_range = [&]() {                                  // k-steps outside the support of this warp's rows / columns are skipped
+        wlo = cc.klo; whi = cc.khi;
+        int lo = 0x7fffffff, hi = 0;
+#pragma unroll
+        for (int x = 0; x < TMW; ++x) {
+            const int r = cc.m0 + wm * 8 * TMW + x * 8;
+            if (r < p.M) { lo = min(lo, p.m8_klo[r >> 3]); hi = max(hi, p.m8_khi[r >> 3]); }
+        }
+        wlo = max(wlo, lo); whi = min(whi, hi);
+        lo = 0x7fffffff; hi = 0;
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+            const int c = cc.n0 + wn * 16 + y * 8;
+            if (c < p.n_cols) { lo = min(lo, p.n8_klo[c >> 3]); hi = max(hi, p.n8_khi[c >> 3]); }
+        }
+        wlo = max(wlo, lo); whi = min(whi, hi);
+    };
+    clear_acc();
+    if (cc.t < total) warp_range();
+#pragma unroll 1
+    for (int i = 0; i < NS - 1; ++i) produce();
+#pragma unroll 1
+    while (cc.t < total) {
+        produce();
+        const int st = cj % NS;
+        mbar_wait(&full[st], (cj / NS) & 1);
+        const int kbase = cc.klo + cc.kt * KT;
+#pragma unroll
+        for (int kk = 0; kk < KT; kk += 4) {
+            if (kbase + kk + 4 <= wlo || kbase + kk >= whi) continue;     // warp-uniform
+            cplx a[TMW], b[2];
+            double a2[TMW], b2[2];
+#pragma unroll
+            for (int x = 0; x < TMW; ++x) { a[x] = As[st][wm * 8 * TMW + x * 8 + g][kk + t4]; a2[x] = As2[st][wm * 8 * TMW + x * 8 + g][kk + t4]; }
+#pragma unroll
+            for (int y = 0; y < 2; ++y) { b[y] = Bs[st][wn * 16 + y * 8 + g][kk + t4]; b2[y] = Bs2[st][wn * 16 + y * 8 + g][kk + t4]; }
+#pragma unroll
+            for (int x = 0; x < TMW; ++x)
+#pragma unroll
+                for (int y = 0; y < 2; ++y) {
+                    dmma884(c1[x][y][0], c1[x][y][1], a[x].y, b[y].x);     // (ar+ai') br
+                    dmma884(cr[x][y][0], cr[x][y][1], a2[x], b[y].y);      // -ai' (br+bi)
+                    dmma884(ci[x][y][0], ci[x][y][1], a[x].x, b2[y]);      // ar (bi-br)
+                }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        ++cj;
+        if (++cc.kt == cc.nk) {
+            // ---- epilogue of this tile: D row-tile-major, diagonal to hdiag
+            cplx* out = p.out + (int64_t)cc.rep * RT8 * p.n_cols;
+#pragma unroll
+            for (int a = 0; a < TMW; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int m = cc.m0 + wm * 8 * TMW + a * 8 + g, col = cc.n0 + wn * 16 + b * 8 + 2 * t4 + e;
+                        if (m < p.M && col < p.n_cols) {
+                            const cplx v = cmake(c1[a][b][e] + cr[a][b][e], c1[a][b][e] + ci[a][b][e]);
+                            out[((int64_t)(m >> 3) * p.n_cols + col) * 8 + (m & 7)] = v;
+                            if (p.hdiag && m == col) p.hdiag[(int64_t)cc.rep * p.M + m] = v;
+                        }
+                    }
+            clear_acc();
+            cc.t += gridDim.x; load_item(cc);
+            if (cc.t < total) warp_range();
+        }
+    }
+}
+
 // ============================================================================ explicit D-hat (API)
 // Dhat[i, i+delta] = sum_p W[i, i+delta, p] hP[p]  scattered into a zeroed dense K x K; diag from W.diag.
 __global__ void k_estimate(cplx* __restrict__ Dhat, cplx* __restrict__ hdiag, WTiles w,
