@@ -180,12 +180,15 @@ def run_b200(args):
     ctx.event_record(0)
     t_wall = time.perf_counter()
     hg_ms, hg_bytes = 0.0, 0.0
+    kern_sum = {}
     for _ in range(K):
         step_resident()
         for k, v in ctx.stage_times().items():
             stage_sum[k] = stage_sum.get(k, 0.0) + v
         a, b = ctx.banded_apply_stats()
         hg_ms, hg_bytes = hg_ms + a, hg_bytes + b
+        for k, v in ctx.kernel_times().items():
+            kern_sum[k] = kern_sum.get(k, 0.0) + v
     ctx.event_record(1)
     dev_ms = ctx.event_elapsed_ms(0, 1)
     barrier()
@@ -239,9 +242,9 @@ def run_b200(args):
     dev_ms, e2e_wall_ms, wall_ms = [float(x) for x in t_max.cpu()]
     if rank == 0:
         wm = ctx.work_model(I)
-        ic_ms = stage_sum["ic_iterations"] / (K * I)                       # average duration of one k_ic launch
-        ic_flops = B * (wm["est_flops"] + wm["perf_flops"] + wm["precode_flops"]) / I
-        k2_ms = stage_sum["k2_transmission_matrix"] / K
+        ic_ms = kern_sum["k_ic_main"] / (K * I)                            # average duration of one k_ic_main launch
+        ic_flops = B * (wm["est_main_flops"] + wm["perf_flops"]) / I       # algorithmic flops of one launch
+        k2_ms = kern_sum["k_gemm_d"] / K                                   # both waveforms' k_gemm_d launches of a step
         nb = ctx.bit_counts()
         ber40 = {name: float(tot[-1, -1, sid * 4].item()) / float(nb[sid, 0] * B * world)
                  for name, sid in chest_b200.context.SCHEME_ID.items() if name in sim.sch}
@@ -254,7 +257,7 @@ def run_b200(args):
         try:                                                       # ncu --set full capture, scaled to this batch size
             tj = json.load(open(os.path.join(ROOT, "profiles", "kic_traffic.json")))
             traffic = tj["dram_bytes_per_launch"] * B / tj["batch"]
-            traffic_note = "dram__bytes_read+write per k_ic launch from %s, scaled x%.2f to batch %d" % (
+            traffic_note = "dram__bytes_read+write per k_ic_main launch from %s, scaled x%.2f to batch %d" % (
                 tj["source"], B / tj["batch"], B)
         except Exception:
             pass
@@ -274,7 +277,7 @@ def run_b200(args):
                     "api": "chest_run_batch (C ABI) with pinned host buffers: explicit draws in, error counts out"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_ic (one persistent launch per IC iteration: W(hP) v and (D - diag h) v on FP64 DMMA)",
+            "roofline": {"kernel": "k_ic_main (one persistent launch per IC iteration: W_off(hP) v and (D - diag h) v on FP64 DMMA)",
                          "bound": "tensor", "achieved": ic_flops / (ic_ms * 1e-3) / 1e12, "peak": peak_dmma,
                          "unit": "TFLOP/s", "frac": ic_flops / (ic_ms * 1e-3) / 1e12 / peak_dmma, "traffic": traffic,
                          "traffic_note": traffic_note,
@@ -282,7 +285,7 @@ def run_b200(args):
                                         "(chest_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; DFMA probe %.1f TFLOP/s"
                                         % peak_dfma,
                          "algorithmic_flops_per_launch": ic_flops, "avg_launch_ms": ic_ms},
-            "roofline_k2": {"kernel": "k_gemm<GEMM_D> (D = Q^H H G, support-aware)", "bound": "tensor",
+            "roofline_k2": {"kernel": "k_gemm_d (D = Q^H H G, persistent, support-aware)", "bound": "tensor",
                             "achieved": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12, "peak": peak_dmma, "unit": "TFLOP/s",
                             "frac": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12 / peak_dmma,
                             "algorithmic_flops_per_launch": B * wm["k2_flops"], "avg_launch_ms": k2_ms},
@@ -291,6 +294,7 @@ def run_b200(args):
                             "unit": "GB/s", "frac": hg_bytes / (hg_ms * 1e-3) / 1e9 / hbm_peak if hg_ms > 0 else None,
                             "peak_source": hbm_src, "algorithmic_bytes_per_step": hg_bytes / K, "ms_per_step": hg_ms / K},
             "stage_ms_per_step": {k: v / K for k, v in stage_sum.items()},
+            "kernel_ms_per_step": {k: v / K for k, v in kern_sum.items()},
             "wall_ms_per_step": wall_ms / K, "launches_per_step": launches_per_step, "setup_s": setup_s,
             "sanity_ber_40dB_last_iteration": ber40,
         }

@@ -284,11 +284,17 @@ class DeviceContext:
         self._check(self.lib.chest_event_elapsed(self._h, a, b, C.byref(ms)))
         return float(ms.value)
 
+    def kernel_times(self):
+        """Device ms of k_apply_hg, k_gemm_d, k_ic_main (sum), k_ic_light (sum) in the last profiled batch."""
+        out = (C.c_float * 4)()
+        self._check(self.lib.chest_kernel_times(self._h, out))
+        return dict(k_apply_hg=out[0], k_gemm_d=out[1], k_ic_main=out[2], k_ic_light=out[3])
+
     def work_model(self, n_iter):
         out = (C.c_double * 8)()
         self._check(self.lib.chest_work_model(self._h, n_iter, out))
         return dict(k2_flops=out[0], est_flops=out[1], perf_flops=out[2], txdemod_flops=out[3],
-                    w_bytes_per_ic_launch=out[4], precode_flops=out[5])
+                    w_bytes_per_ic_launch=out[4], precode_flops=out[5], est_main_flops=out[6])
 
     def fp64_peak(self, mode="dmma", iters=20000):
         t = C.c_double(0)

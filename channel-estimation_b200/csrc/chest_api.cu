@@ -125,6 +125,9 @@ struct Ctx {
     bool profiling = false;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_hg[4] = {};   // k_apply_hg of the two waveforms (profiling)
+    cudaEvent_t ev_gd[2] = {};   // end of k_gemm_d of the two waveforms
+    cudaEvent_t ev_ic[36] = {};  // after every k_ic_main / k_ic_light launch
+    float kernel_ms[4] = {0, 0, 0, 0};   // k_apply_hg, k_gemm_d, k_ic_main, k_ic_light of the last profiled batch
     float hg_ms = 0; double hg_bytes = 0;
     cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -263,6 +266,7 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_hg[2 * wfi + 1], c->stream));
     if (w.tile == 48) CK((launch_gemm_d_geo<2, 3, 3>(c, p)));
     else CK((launch_gemm_d_geo<2, 4, 4>(c, p)));
+    if (c->profiling && n_rep > 1) CK(cudaEventRecord(c->ev_gd[wfi], c->stream));
     return CHEST_OK;
 }
 
@@ -456,11 +460,13 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
             k_ic_main<<<std::min(c->ic_grid, n_units), ic_threads, main_smem, st>>>(ip);
             c->launches++;
             ip.trace = nullptr;
+            if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
         }
         // phases C, D, E of iteration it (+ phase A of iteration it+1)
         k_ic_light<<<std::min(c->ic_light_grid * IC_LIGHT_WAVES, n_units), IC_LIGHT_THREADS, light_smem, st>>>(ip);
         c->launches++;
         CK(cudaGetLastError());
+        if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it + 1], st));
         if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev[5], st));
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[6], st));
@@ -474,6 +480,22 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     if (c->profiling) {
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&c->stage_ms[6], c->ev[0], c->ev[6]);
+        // per-kernel times: events after every IC launch (main of iteration it: 2 it, light: 2 it + 1; ev[4] precedes)
+        c->kernel_ms[2] = c->kernel_ms[3] = 0;
+        for (int it = 0; it <= n_iter; ++it) {
+            float t = 0;
+            if (it > 0) { cudaEventElapsedTime(&t, c->ev_ic[2 * it - 1], c->ev_ic[2 * it]); c->kernel_ms[2] += t; }
+            cudaEventElapsedTime(&t, it > 0 ? c->ev_ic[2 * it] : c->ev[4], c->ev_ic[2 * it + 1]);
+            c->kernel_ms[3] += t;
+        }
+        c->kernel_ms[0] = c->kernel_ms[1] = 0;
+        if (n_rep > 1)
+            for (int wfi = 0; wfi < 2; ++wfi)
+                if (c->wf[wfi].set && c->wf[wfi].nsch) {
+                    float t = 0;
+                    cudaEventElapsedTime(&t, c->ev_hg[2 * wfi + 1], c->ev_gd[wfi]);
+                    c->kernel_ms[1] += t;
+                }
         c->hg_ms = 0; c->hg_bytes = 0;
         for (int wfi = 0; wfi < 2; ++wfi) {
             Waveform& w = c->wf[wfi];
@@ -521,6 +543,8 @@ int chest_create(int device, uint64_t* handle) {
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     for (auto& e : c->user_ev) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_hg) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_gd) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_ic) CK(cudaEventCreate(&e));
     *handle = (uint64_t)(uintptr_t)c;
     return CHEST_OK;
 }
@@ -554,6 +578,8 @@ int chest_destroy(uint64_t handle) {
     for (auto& e : c->ev) cudaEventDestroy(e);
     for (auto& e : c->user_ev) cudaEventDestroy(e);
     for (auto& e : c->ev_hg) cudaEventDestroy(e);
+    for (auto& e : c->ev_gd) cudaEventDestroy(e);
+    for (auto& e : c->ev_ic) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return CHEST_OK;
@@ -1295,6 +1321,14 @@ int chest_banded_apply_stats(uint64_t handle, float* ms, double* bytes) {
     return CHEST_OK;
 }
 
+int chest_kernel_times(uint64_t handle, float* ms) {
+    Ctx* c = from(handle);
+    ARG(c && ms);
+    c->kernel_ms[0] = c->hg_ms;
+    for (int i = 0; i < 4; ++i) ms[i] = c->kernel_ms[i];
+    return CHEST_OK;
+}
+
 int chest_work_model(uint64_t handle, int n_iter, double* out) {
     Ctx* c = from(handle);
     ARG(c && out);
@@ -1317,6 +1351,7 @@ int chest_work_model(uint64_t handle, int n_iter, double* out) {
             off += 8.0 * s.mm[var_prev].nnz_offdiag_pairs * (s.P + 1);
         }
         out[1] += S * (off + 8.0 * s.K * s.P * (n_iter + 1));
+        out[6] += S * off;                                                     // of which in k_ic_main (off-diagonal products)
         out[4] += (double)S * s.mm[0].n_tiles * ((s.P + 3) / 4) * 32 * 16;     // W bytes streamed per IC launch
         out[5] += S * n_iter * (8.0 * s.c_nnz);                                // precoding C z, x2 (est + perfect)
     }

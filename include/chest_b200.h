@@ -193,9 +193,13 @@ int chest_stage_times(uint64_t handle, float* ms /* [7] */);
 /* K1 banded operator applied to G (k_apply_hg) in the last profiled chest_run_batch: device time (ms) and
  * algorithmic bytes (H*G rows written + h read), for the HBM roofline of the banded path. */
 int chest_banded_apply_stats(uint64_t handle, float* ms, double* bytes);
+/* Device time (ms, CUDA events on the context's stream) of the hot kernels in the last profiled chest_run_batch:
+ * [0] k_apply_hg, [1] k_gemm_d (K2), [2] k_ic_main summed over the iterations, [3] k_ic_light summed. */
+int chest_kernel_times(uint64_t handle, float* ms /* [4] */);
 /* Algorithmic work of one realization for the roofline:
  * [0] K2 support-aware flops, [1] K3/K4 estimated-CSI flops per iteration-evaluation set,
- * [2] perfect-CSI flops, [3] demod/TX flops, [4] bytes of W streamed per IC kernel launch. */
+ * [2] perfect-CSI flops, [3] demod/TX flops, [4] bytes of W streamed per IC kernel launch,
+ * [5] precoding flops, [6] the part of [1] executed by k_ic_main (off-diagonal products). */
 int chest_work_model(uint64_t handle, int n_iter, double* out /* [8] */);
 
 /* Device-timeline timing for callers that cannot see the context's stream: record event `slot`
