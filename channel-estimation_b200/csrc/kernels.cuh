@@ -1,10 +1,9 @@
 // kernels.cuh -- the device side of the Monte-Carlo hot path (DS.m:350-565).
 //   K1  k_synth_h / k_apply_h      channel synthesis + banded, never-materialised H
-//   K2  k_gemm<GEMM_D>             D = Q^H (H G) on FP64 tensor cores (DMMA), support-aware tiles
+//   K2  k_apply_hg, k_gemm_d       D = Q^H (H G) on FP64 tensor cores (DMMA): persistent, support-aware tiles
 //   K3  k_gemm<GEMM_DEMOD>, k_estimate   demodulation GEMM over realizations, explicit D-hat
-//   K4  k_ic                       one launch per interference-cancellation iteration
+//   K4  k_ic_main, k_ic_light      tensor phase / scalar phases of one interference-cancellation iteration
 #pragma once
-#include <cooperative_groups.h>
 #include "common.cuh"
 
 #define NC_MAX 16          // columns (realizations x SNR points) one IC CTA carries
@@ -245,28 +244,21 @@ __global__ void k_tx_symbols(SchemeDev sd, ConstDev cd, const uint8_t* __restric
 //   A is given "k-contiguous": At[k + lda*m]; conj flag folds Q^H.
 //   B[k, col] comes from a mode-specific loader; C is written as out[col*ldc + m].
 // 64x64 CTA tile, 8 warps (2x4), warp tile 32x16 = 4x2 DMMA tiles, KT = 32.
-enum { GEMM_PLAIN = 0, GEMM_DEMOD = 1, GEMM_D = 2 };
+enum { GEMM_PLAIN = 0, GEMM_DEMOD = 1 };
 struct GemmParams {
     int M, Kc, n_cols, lda, ldc, conj_a;
     const cplx* At;
-    // GEMM_DEMOD / GEMM_D (A = Q^H): three-multiplication planes of the conjugated operand, same indexing as At:
+    // GEMM_DEMOD (A = Q^H): three-multiplication planes of the conjugated operand, same indexing as At:
     // At1 = (re, re - im), At2 = im
     const cplx* At1; const double* At2;
     const int* mt_klo; const int* mt_khi;      // per CTA row tile: k support range
     const int* m8_klo; const int* m8_khi;      // per 8 rows: k support range (warp-level clipping; may be null)
-    const int* n8_klo; const int* n8_khi;      // GEMM_D, per 8 columns: k support range of H*G (may be null)
     cplx* out;                                  // [col][ldc]
     // PLAIN: B[k,col] = bsrc[col*ldb + k]
     const cplx* bsrc; int ldb;
     // DEMOD: col = (g*n_snr + snr)*n_rep + rep ; B = r0[(g*n_rep+rep)*N + k] + sqrt(pn[snr]/2)*noise[(rep*n_snr+snr)*N + k]
     const cplx* r0; const cplx* noise; const double* noise_scale; int n_snr, n_rep;
-    // D: per realization (blockIdx.z): B[k=n, col=j] = HG[rep][j][n] (k_apply_hg), stored as the planes
-    // b1src = (re, re + im), b2src = im - re at [(rep*n_cols+col)*ldb + k]; out += rep*ldc*n_cols
-    const cplx* b1src; const double* b2src;
     int N;
-    const int* nt_klo; const int* nt_khi;      // per 64-col tile k support range of H*G
-    cplx* hdiag;                                // [rep][K] diagonal of D (may be null)
-    int rep0;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -282,13 +274,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // stage s^1; one barrier per k-tile.
 // Geometry: WM x WN warps, each owning TMW x 2 DMMA tiles -> CTA tile (8*TMW*WM) x (16*WN).
 //   <2,4,4>: 64 x 64, 8 warps        <2,3,3>: 48 x 48, 6 warps, 2 CTAs/SM
-// The host picks, per waveform, the geometry whose tiles waste the fewest flops on padding (48 divides the
-// 720 / 336 symbols of the reference's grids and follows the 24-subcarrier support structure more closely).
+// The host picks, per waveform, the geometry whose tiles waste the fewest flops on padding of D = Q^H (H G)
+// (48 divides the 720 / 336 symbols of the reference's grids and follows the 24-subcarrier support structure
+// more closely); K2 itself runs in k_gemm_d below, this kernel serves s = G x (PLAIN) and the demodulation.
 // Complex products use the three-multiplication form (CHEST_3M, common.cuh): per 8x8 tile the partial sums
 // c1 = (ar+ai) br, cr = -ai (br+bi), ci = ar (bi-br); the epilogue forms re = c1 + cr, im = c1 + ci.
-// GEMM_DEMOD / GEMM_D (PRE3) read the operand sums ready-made: A from the planes the host builds once per
-// waveform, B from the planes k_apply_hg writes (or computed while adding the noise), so the inner loop is
-// LDS + DMMA only; a second, double-valued smem plane per operand holds the third value (row stride 20
+// GEMM_DEMOD (PRE3) reads the operand sums ready-made: A from the planes the host builds once per waveform,
+// B computed while adding the noise, so the inner loop is LDS + DMMA only; a second, double-valued smem plane per operand holds the third value (row stride 20
 // doubles: conflict-free 8-byte fragment loads).  GEMM_PLAIN forms the sums in registers.
 template <int MODE, int WM, int WN, int TMW>
 __global__ void __launch_bounds__(32 * WM * WN, CHEST_3M ? ((WM * WN == 8) ? 1 : 2) : ((WM * WN == 8) ? 2 : 3))
@@ -305,14 +297,9 @@ k_gemm(GemmParams p) {
     const int g = lane >> 2, t4 = lane & 3;
     const int mt = blockIdx.x, nt = blockIdx.y;
     const int m0 = mt * TM, n0 = nt * TN;
-    const int rep = (MODE == GEMM_D) ? (int)blockIdx.z + p.rep0 : 0;
     int klo = p.mt_klo ? p.mt_klo[mt] : 0, khi = p.mt_khi ? p.mt_khi[mt] : p.Kc;
-    if (MODE == GEMM_D) { klo = max(klo, p.nt_klo[nt]); khi = min(khi, p.nt_khi[nt]); }
     if (PRE3) klo &= ~1;                                  // the double planes are copied in aligned pairs
-    // GEMM_D writes D row-tile-major: D[rep][rt = m/8][col][m%8], so that the perfect-CSI interference pass
-    // streams the 8 rows of a DMMA row tile as one contiguous block (K*128 bytes)
-    const int RT8 = ((p.M + 7) / 8) * 8;
-    cplx* out = p.out + ((MODE == GEMM_D) ? (int64_t)rep * RT8 * p.n_cols : 0);
+    cplx* out = p.out;
     const bool conj_a = p.conj_a != 0;
 
     double cr[TMW][2][2], ci[TMW][2][2], c1[CHEST_3M ? TMW : 1][2][2];
@@ -348,8 +335,6 @@ k_gemm(GemmParams p) {
             bool ok = col < p.n_cols && gk < khi;
             if (MODE == GEMM_PLAIN) {
                 cp_async16(&Bs[stage][c][kk], p.bsrc + (ok ? (int64_t)col * p.ldb + gk : 0), ok);
-            } else if (MODE == GEMM_D) {
-                cp_async16(&Bs[stage][c][kk], (PRE3 ? p.b1src : p.bsrc) + (ok ? ((int64_t)rep * p.n_cols + col) * p.ldb + gk : 0), ok);
             } else {
                 cplx v = cmake(0.0, 0.0);
                 if (ok) {
@@ -363,15 +348,6 @@ k_gemm(GemmParams p) {
                 else Bs[stage][c][kk] = v;
             }
         }
-        if (PRE3 && MODE == GEMM_D) {
-#pragma unroll
-            for (int e = 0; e < (TN * KT / 2) / NTHR; ++e) {
-                int idx = tid + e * NTHR, kk = (idx & (KT / 2 - 1)) * 2, c = idx / (KT / 2);
-                int gk = k0 + kk, col = n0 + c;
-                bool ok = col < p.n_cols && gk < khi;
-                cp_async16(&Bs2[stage][c][kk], p.b2src + (ok ? ((int64_t)rep * p.n_cols + col) * p.ldb + gk : 0), ok);
-            }
-        }
     };
 
     // warp-level clipping: a warp skips the k-steps outside the support of its own rows / columns (the CTA range
@@ -383,15 +359,6 @@ k_gemm(GemmParams p) {
         for (int x = 0; x < TMW; ++x) {
             const int r = m0 + wm * 8 * TMW + x * 8;
             if (r < p.M) { lo = min(lo, p.m8_klo[r >> 3]); hi = max(hi, p.m8_khi[r >> 3]); }
-        }
-        wlo = max(wlo, lo); whi = min(whi, hi);
-    }
-    if (MODE == GEMM_D && p.n8_klo) {
-        int lo = 0x7fffffff, hi = 0;
-#pragma unroll
-        for (int y = 0; y < 2; ++y) {
-            const int cc = n0 + wn * 16 + y * 8;
-            if (cc < p.n_cols) { lo = min(lo, p.n8_klo[cc >> 3]); hi = max(hi, p.n8_khi[cc >> 3]); }
         }
         wlo = max(wlo, lo); whi = min(whi, hi);
     }
@@ -472,12 +439,7 @@ k_gemm(GemmParams p) {
                 if (m < p.M && col < p.n_cols) {
                     cplx v = CHEST_3M ? cmake(c1[CHEST_3M ? a : 0][b][e] + cr[a][b][e], c1[CHEST_3M ? a : 0][b][e] + ci[a][b][e])
                                       : cmake(cr[a][b][e], ci[a][b][e]);
-                    if (MODE == GEMM_D) {
-                        out[((int64_t)(m >> 3) * p.n_cols + col) * 8 + (m & 7)] = v;
-                        if (p.hdiag && m == col) p.hdiag[(int64_t)rep * p.M + m] = v;
-                    } else {
-                        out[(int64_t)col * p.ldc + m] = v;
-                    }
+                    out[(int64_t)col * p.ldc + m] = v;
                 }
             }
 }
