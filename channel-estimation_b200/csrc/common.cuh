@@ -41,6 +41,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 #ifndef CHEST_3M
 #define CHEST_3M 1
 #endif
+// D = A * B + C with separate accumulator input (starts a new chain from another tile's partial sums)
+__device__ __forceinline__ void dmma884c(double& d0, double& d1, double a, double b, double c0, double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+                 : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
 // complex tile update: (cr + j ci) += (ar + j ai) * (br + j bi), nbi = -bi
 __device__ __forceinline__ void zmma884(double (&cr)[2], double (&ci)[2], double ar, double ai,
                                         double br, double bi, double nbi) {

@@ -852,7 +852,9 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
             }
             double tr[2][2] = {{0, 0}, {0, 0}}, ti[2][2] = {{0, 0}, {0, 0}};
 #if CHEST_3M
-            // three-multiplication complex product: hP3 holds (-(br+bi), bi-br) of the pilot estimates
+            // three-multiplication complex product: hP3 holds (-(br+bi), bi-br) of the pilot estimates.  The common
+            // term t1 = sum_p (ar+ai) br is accumulated first; the re and im chains then START from it (accumulator
+            // input of their first DMMA), so no separate additions are needed
             double t1[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll
             for (int pq = 0; pq < P4T; ++pq) {
@@ -860,16 +862,23 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
 #pragma unroll
                 for (int ct = 0; ct < 2; ++ct) {
                     const double b1 = HPREG ? hb[HPREG ? pq : 0][ct].x : hP1[(pq * 4 + t4) * EST_H1S + ct * 8 + g];
-                    const cplx b23 = HPREG ? hb3[HPREG ? pq : 0][ct] : hP3[(pq * 4 + t4) * HS + ct * 8 + g];
                     dmma884(t1[ct][0], t1[ct][1], as, b1);
-                    dmma884(tr[ct][0], tr[ct][1], cur[pq].y, b23.x);
-                    dmma884(ti[ct][0], ti[ct][1], cur[pq].x, b23.y);
                 }
             }
 #pragma unroll
-            for (int ct = 0; ct < 2; ++ct)
+            for (int pq = 0; pq < P4T; ++pq) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) { tr[ct][e] += t1[ct][e]; ti[ct][e] += t1[ct][e]; }
+                for (int ct = 0; ct < 2; ++ct) {
+                    const cplx b23 = HPREG ? hb3[HPREG ? pq : 0][ct] : hP3[(pq * 4 + t4) * HS + ct * 8 + g];
+                    if (pq == 0) {
+                        dmma884c(tr[ct][0], tr[ct][1], cur[pq].y, b23.x, t1[ct][0], t1[ct][1]);
+                        dmma884c(ti[ct][0], ti[ct][1], cur[pq].x, b23.y, t1[ct][0], t1[ct][1]);
+                    } else {
+                        dmma884(tr[ct][0], tr[ct][1], cur[pq].y, b23.x);
+                        dmma884(ti[ct][0], ti[ct][1], cur[pq].x, b23.y);
+                    }
+                }
+            }
 #else
 #pragma unroll
             for (int pq = 0; pq < P4T; ++pq) {
