@@ -2,8 +2,10 @@
 
 The constructor (power-delay-profile tables, resampling to the sampling rate) is host-side
 table work, as in the reference; `NewRealization`, `Convolution`, `GetConvolutionMatrix` run on the
-GPU through the C ABI.  Supported here: 1x1 antennas, 'Jakes' and 'Uniform' Doppler models with a
-positive maximum Doppler shift (the branch both reference scripts use, FF.m:223-239)."""
+GPU through the C ABI.  Supported here: 1x1 antennas; 'Jakes' and 'Uniform' Doppler models (the branch both
+reference scripts use, FF.m:223-239, synthesised on the GPU); block fading (f_D = 0, FF.m:241-248) and 'AWGN'
+(FF.m:197-198), whose few draws are made on the host and applied by the same device operator.  The
+'Discrete-*' IFFT synthesis raises NotImplementedError."""
 import numpy as np
 from scipy.special import j0
 
@@ -47,10 +49,10 @@ class FastFading:
                  create_device=True):
         if nTxAntennas != 1 or nRxAntennas != 1:
             raise NotImplementedError("only 1x1 antennas are supported by this build")
-        if DopplerModel not in ("Jakes", "Uniform"):
+        if DopplerModel not in ("Jakes", "Uniform") and MaximumDopplerShift > 0:
             raise NotImplementedError("Doppler spectrum not supported by this build: %s" % DopplerModel)
-        if not MaximumDopplerShift > 0:
-            raise NotImplementedError("time-invariant (block fading / AWGN) channels are not on the GPU path")
+        if str(DopplerModel).startswith("Discrete"):
+            raise NotImplementedError("Doppler spectrum not supported by this build: %s" % DopplerModel)
         self.PHY = {"SamplingRate": float(SamplingRate), "MaximumDopplerShift": float(MaximumDopplerShift),
                     "dt": 1.0 / SamplingRate, "DopplerModel": DopplerModel}
         self.Nr = {"SamplesTotal": int(SamplesTotal), "txAntennas": 1, "rxAntennas": 1, "Paths": int(Paths)}
@@ -87,16 +89,36 @@ class FastFading:
     def _device(self):
         if self._ctx is None:
             self._ctx = DeviceContext()
+            # a time-invariant channel (f_D = 0, AWGN) is uploaded as an impulse response; the sum-of-sinusoids
+            # parameters are then unused
+            model = self.PHY["DopplerModel"] if self.PHY["DopplerModel"] in ("Jakes", "Uniform") else "Jakes"
             self._ctx.set_channel(self.Nr["SamplesTotal"], self.Implementation["PowerDelayProfileNormalized"],
-                                  self.PHY["MaximumDopplerShift"], self.PHY["dt"], self.Nr["Paths"],
-                                  self.PHY["DopplerModel"])
+                                  self.PHY["MaximumDopplerShift"], self.PHY["dt"], self.Nr["Paths"], model)
             self._ctx.finalize(1)
         return self._ctx
 
-    def NewRealization(self, doppler_u=None, phase_u=None):
+    def NewRealization(self, doppler_u=None, phase_u=None, gauss=None):
         """FF.m:194-250.  Without arguments the uniforms come from the device generator keyed by
         (seed, call count); explicit (T x Paths) uniforms reproduce exported draws."""
         ctx = self._device()
+        N, pdp = self.Nr["SamplesTotal"], self.Implementation["PowerDelayProfileNormalized"]
+        if self.Implementation["PowerDelayProfile"] == "AWGN" if isinstance(self.Implementation["PowerDelayProfile"], str) else False:
+            h = np.ones((1, 1), dtype=complex)                                            # FF.m:197-198
+            ctx.set_impulse_response(np.broadcast_to(h, (N, len(pdp)))[None].copy())
+            self._count += 1
+            self.ImpulseResponse = h
+            return
+        if not self.PHY["MaximumDopplerShift"] > 0:
+            # block fading, FF.m:241-248: one complex normal per tap, constant over the block; `gauss` (Lt complex
+            # standard normals) reproduces exported draws, otherwise a NumPy generator keyed by (seed, call count)
+            if gauss is None:
+                rng = np.random.default_rng([self._seed, self._count])
+                gauss = rng.standard_normal(len(pdp)) + 1j * rng.standard_normal(len(pdp))
+            h = (np.sqrt(pdp) / np.sqrt(2) * np.asarray(gauss).reshape(-1))[None, :]
+            ctx.set_impulse_response(np.broadcast_to(h, (N, len(pdp)))[None].copy())      # H applied on the GPU as for f_D > 0
+            self._count += 1
+            self.ImpulseResponse = h
+            return
         if doppler_u is None:
             ctx.new_realization_seeded(1, self._seed, self._count)
         else:

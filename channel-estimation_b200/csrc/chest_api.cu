@@ -329,6 +329,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     ARG(n_rep >= 1 && n_rep <= c->max_batch);
     ARG(n_iter >= 0 && n_iter <= 16);
     ARG(c->S >= 1);
+    if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "the batched loop body synthesises Jakes / Uniform realizations: f_D must be positive");
     const int S = c->S, N = c->N, TP = c->T * c->paths;
     c->cur_batch = n_rep; c->last_iter = n_iter;
     cudaStream_t st = c->stream;
@@ -588,7 +589,7 @@ int chest_destroy(uint64_t handle) {
 int chest_set_channel(uint64_t handle, int n_samples, int n_taps, const double* pdp, double fd, double dt,
                       int n_paths, int model) {
     Ctx* c = from(handle);
-    ARG(c && n_samples > 0 && n_taps > 0 && pdp && n_paths > 0 && dt > 0 && fd > 0);
+    ARG(c && n_samples > 0 && n_taps > 0 && pdp && n_paths > 0 && dt > 0 && fd >= 0);   // fd = 0: time-invariant, see chest_set_impulse_response
     ARG(model == CHEST_DOPPLER_JAKES || model == CHEST_DOPPLER_UNIFORM);
     if (c->N && c->N != n_samples) return fail(CHEST_ERR_ARG, "Total number of samples must be the same for the channel and every waveform");
     CK(cudaSetDevice(c->device));
@@ -1014,6 +1015,7 @@ int chest_new_realization(uint64_t handle, int batch, const double* du, const do
     Ctx* c = from(handle);
     int rc = check_ready(c); if (rc) return rc;
     ARG(batch >= 1 && batch <= c->max_batch && du && pu);
+    if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "time-invariant channel (f_D = 0): upload the impulse response with chest_set_impulse_response");
     CK(cudaSetDevice(c->device));
     size_t n = (size_t)batch * c->T * c->paths;
     CK(cudaMemcpyAsync(c->doppler_u.p, du, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1028,6 +1030,7 @@ int chest_new_realization_seeded(uint64_t handle, int batch, uint64_t seed, int6
     Ctx* c = from(handle);
     int rc = check_ready(c); if (rc) return rc;
     ARG(batch >= 1 && batch <= c->max_batch);
+    if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "time-invariant channel (f_D = 0): upload the impulse response with chest_set_impulse_response");
     CK(cudaSetDevice(c->device));
     int n = c->T * c->paths;
     dim3 grid((n / 2 + 1 + 127) / 128, batch);

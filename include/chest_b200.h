@@ -66,7 +66,10 @@ int chest_destroy(uint64_t handle);
  * (the outputs of DS.m:50-313, which stay on the host)            */
 
 /* Channel.FastFading constructor state (FF.m:25-192): N samples, the normalised power delay
- * profile over ALL Lt taps (zeros allowed, FF.m:129), maximum Doppler shift, dt, paths. */
+ * profile over ALL Lt taps (zeros allowed, FF.m:129), maximum Doppler shift, dt, paths.
+ * max_doppler_hz = 0 declares a time-invariant channel (block fading FF.m:241-248, AWGN FF.m:197-198):
+ * realizations are then uploaded with chest_set_impulse_response and applied by the same banded operator;
+ * chest_new_realization* and chest_run_batch require a positive Doppler shift. */
 int chest_set_channel(uint64_t handle, int n_samples, int n_taps, const double* pdp_normalized,
                       double max_doppler_hz, double dt, int n_paths, int doppler_model);
 

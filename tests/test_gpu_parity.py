@@ -373,3 +373,31 @@ def test_simple_version_doubly_flat_chain():
     ber_fp, ber_op = errs["fbmc_perfect"] / bits_tot["fbmc"], errs["ofdm_perfect"] / bits_tot["ofdm"]
     assert abs(ber_op - theory) < 0.6 * theory and abs(ber_fp - theory) < 0.6 * theory      # 60 fading draws: wide MC band
     assert errs["cod"] >= errs["fbmc_perfect"] * 0.5 and errs["aux"] < 0.5 * aux.NrDataSymbols * 2 * reps
+
+
+def test_time_invariant_channel_branches():
+    """FastFading with f_D = 0 (block fading, FF.m:241-248) and 'AWGN' (FF.m:197-198): the impulse response is
+    drawn on the host, the convolution (FF.m:265-274: conv(s, h)(1:N)) and the convolution matrix (FF.m:288-293)
+    come from the same device operator as the time-variant case."""
+    import chest_b200
+    from oracle.fast_fading import FastFading as RefFF
+    rng = np.random.default_rng(3)
+    N = 540
+    s = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    ch = chest_b200.Channel.FastFading(360e3, "VehicularA", N, 0, "Jakes", 200, 1, 1, 0, create_device=False)
+    ref = RefFF(360e3, "VehicularA", N, 0, "Jakes", 200, 1, 1, False)
+    Lt = len(ch.Implementation["PowerDelayProfileNormalized"])
+    g = rng.standard_normal(Lt) + 1j * rng.standard_normal(Lt)
+    ch.NewRealization(gauss=g)
+    ref.NewRealization(gauss=g)
+    assert ch.ImpulseResponse.shape == (1, Lt) and rel(ch.ImpulseResponse, ref.ImpulseResponse) < 1e-15
+    assert rel(np.asarray(ch.Convolution(s)).reshape(-1), ref.Convolution(s)) < 1e-13
+    H = ch.GetConvolutionMatrix()[0][0].toarray()
+    assert rel(H, ref.GetConvolutionMatrix().toarray()) < 1e-15
+    ch.NewRealization()                                       # keyed host generator: new taps, unit average power
+    assert not np.allclose(ch.ImpulseResponse, ref.ImpulseResponse)
+    awgn = chest_b200.Channel.FastFading(360e3, "AWGN", N, 0, "Jakes", 200, 1, 1, 0)
+    assert awgn.ImpulseResponse.shape == (1, 1) and awgn.ImpulseResponse[0, 0] == 1
+    assert rel(np.asarray(awgn.Convolution(s)).reshape(-1), s) < 1e-15
+    with pytest.raises(NotImplementedError):
+        chest_b200.Channel.FastFading(360e3, "VehicularA", N, 1158.18, "Discrete-Jakes", 200, 1, 1, 0)
