@@ -213,6 +213,12 @@ class DeviceContext:
         dptr = C.byref(draws) if draws is not None else None
         self._check(self.lib.chest_run_batch_device(self._h, n_rep, n_iter, dptr, seed, first_rep, err_dev_ptr))
 
+    def prefetch_draws(self, n_rep, host_draws):
+        """Start the asynchronous upload of host draws; returns the device-side ChestDraws to pass to run_batch*."""
+        dev = _lib.ChestDraws()
+        self._check(self.lib.chest_prefetch_draws(self._h, n_rep, C.byref(host_draws), C.byref(dev)))
+        return dev
+
     def generate_draws(self, n_rep, seed, first_rep=0):
         st = _lib.ChestDraws()
         self._check(self.lib.chest_generate_draws(self._h, n_rep, seed, first_rep, C.byref(st)))

@@ -117,6 +117,13 @@ struct Ctx {
     int max_batch = 0, cur_batch = 0, last_iter = 0;
     DevBuf<double> doppler_u, phase_u; DevBuf<cplx> noise, h;
     DevBuf<int32_t> pilot_idx[2];
+    // chest_prefetch_draws: two library-owned copies of the draw buffers filled on a copy stream
+    struct Prefetch {
+        DevBuf<double> du, pu; DevBuf<cplx> noise; DevBuf<uint8_t> bits[3]; DevBuf<int32_t> pidx[2];
+        cudaEvent_t landed = nullptr, released = nullptr; bool used = false;
+    } pf[2];
+    int pf_next = 0;
+    cudaStream_t copy_stream = nullptr;
     DevBuf<uint32_t> err;
     DevBuf<cplx> scratch, tmp_a, tmp_b;
     DevBuf<IcCta> ctas; int n_ctas = 0, ctas_for_batch = -1;
@@ -339,7 +346,10 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     const cplx* noise = c->noise.p;
     const uint8_t* bits[3] = {c->sch[0].bits.p, c->sch[1].bits.p, c->sch[2].bits.p};
     const int32_t* pidx[2] = {c->pilot_idx[0].p, c->pilot_idx[1].p};
+    int pf_used = -1;
     if (draws && draws->on_device) {
+        for (int q = 0; q < 2; ++q)
+            if (c->pf[q].used && draws->doppler_u == c->pf[q].du.p) { pf_used = q; CK(cudaStreamWaitEvent(st, c->pf[q].landed, 0)); }
         du = draws->doppler_u; pu = draws->phase_u; noise = reinterpret_cast<const cplx*>(draws->noise);
         for (int i = 0; i < 3; ++i) bits[i] = draws->bits[i];
         for (int i = 0; i < 2; ++i) pidx[i] = draws->pilot_idx[i];
@@ -471,6 +481,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev[5], st));
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[6], st));
+    if (pf_used >= 0) CK(cudaEventRecord(c->pf[pf_used].released, st));        // the set may be refilled after this point
     if (err_host) CK(cudaMemcpyAsync(err_host, err, n_err * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (trace_path) {
@@ -541,6 +552,8 @@ int chest_create(int device, uint64_t* handle) {
     Ctx* c = new Ctx();
     c->device = device; c->n_sm = sm;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& q : c->pf) { CK(cudaEventCreateWithFlags(&q.landed, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&q.released, cudaEventDisableTiming)); }
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     for (auto& e : c->user_ev) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_hg) CK(cudaEventCreate(&e));
@@ -582,6 +595,13 @@ int chest_destroy(uint64_t handle) {
     for (auto& e : c->ev_gd) cudaEventDestroy(e);
     for (auto& e : c->ev_ic) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    for (auto& q : c->pf) {
+        cudaEventDestroy(q.landed); cudaEventDestroy(q.released);
+        q.du.release(); q.pu.release(); q.noise.release();
+        for (auto& b : q.bits) b.release();
+        for (auto& b : q.pidx) b.release();
+    }
     delete c;
     return CHEST_OK;
 }
@@ -1188,6 +1208,44 @@ int chest_estimate(uint64_t handle, int si, int variant, int i_snr, const double
 }
 
 // ---------------------------------------------------------------- tier 2
+int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, chest_draws* dev) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(n_rep >= 1 && n_rep <= c->max_batch && host && dev && !host->on_device);
+    ARG(host->doppler_u && host->phase_u && host->noise);
+    CK(cudaSetDevice(c->device));
+    const int S = c->S, N = c->N, TP = c->T * c->paths, B = c->max_batch;
+    Ctx::Prefetch& q = c->pf[c->pf_next];
+    c->pf_next ^= 1;
+    cudaStream_t cs = c->copy_stream;
+    if (q.used) CK(cudaStreamWaitEvent(cs, q.released, 0));       // the batch that read this set has finished with it
+    CK(q.du.alloc((size_t)B * TP)); CK(q.pu.alloc((size_t)B * TP)); CK(q.noise.alloc((size_t)B * S * N));
+    CK(cudaMemcpyAsync(q.du.p, host->doppler_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(q.pu.p, host->phase_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(q.noise.p, host->noise, sizeof(cplx) * (size_t)n_rep * S * N, cudaMemcpyHostToDevice, cs));
+    *dev = chest_draws{};
+    for (int i = 0; i < 3; ++i)
+        if (c->sch[i].set) {
+            ARG(host->bits[i]);
+            CK(q.bits[i].alloc((size_t)B * c->sch[i].n_bits));
+            CK(cudaMemcpyAsync(q.bits[i].p, host->bits[i], (size_t)n_rep * c->sch[i].n_bits, cudaMemcpyHostToDevice, cs));
+            dev->bits[i] = q.bits[i].p;
+        }
+    for (int i = 0; i < 2; ++i)
+        if (c->wf[i].set && c->wf[i].nsch) {
+            ARG(host->pilot_idx[i]);
+            const int P = c->sch[c->wf[i].sch[0]].P;
+            CK(q.pidx[i].alloc((size_t)B * P));
+            CK(cudaMemcpyAsync(q.pidx[i].p, host->pilot_idx[i], sizeof(int32_t) * n_rep * P, cudaMemcpyHostToDevice, cs));
+            dev->pilot_idx[i] = q.pidx[i].p;
+        }
+    CK(cudaEventRecord(q.landed, cs));
+    q.used = true;
+    dev->doppler_u = q.du.p; dev->phase_u = q.pu.p; dev->noise = reinterpret_cast<const double*>(q.noise.p);
+    dev->on_device = 1;
+    return CHEST_OK;
+}
+
 int64_t chest_draws_bytes(uint64_t handle, int n_rep) {
     Ctx* c = from(handle);
     if (!c) return 0;

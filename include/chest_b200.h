@@ -154,6 +154,12 @@ typedef struct chest_draws {
     int            on_device;
 } chest_draws;
 
+/* Asynchronous upload of host draws into one of two library-owned device buffer sets (a dedicated copy
+ * stream): returns at once with `dev` pointing at the device copies (on_device = 1).  The chest_run_batch*
+ * call that receives `dev` waits for the copy; the draws of batch i+1 can therefore travel while batch i runs
+ * (call order: prefetch(i+1), run(i)).  A set is reused by every second call, after the batch that read it. */
+int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, chest_draws* dev);
+
 /* Bytes a host->device upload of `n_rep` realizations' draws moves (for reporting). */
 int64_t chest_draws_bytes(uint64_t handle, int n_rep);
 

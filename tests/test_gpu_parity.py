@@ -401,3 +401,20 @@ def test_time_invariant_channel_branches():
     assert rel(np.asarray(awgn.Convolution(s)).reshape(-1), s) < 1e-15
     with pytest.raises(NotImplementedError):
         chest_b200.Channel.FastFading(360e3, "VehicularA", N, 1158.18, "Discrete-Jakes", 200, 1, 1, 0)
+
+
+def test_prefetched_draws_equal_direct_upload(gpu_ctx, ds_default):
+    """chest_prefetch_draws (asynchronous, double-buffered upload) feeds chest_run_batch the same draws as the
+    direct host-pointer path: identical error counts, also when two uploads are in flight."""
+    from oracle.ds import new_draws
+    ctx = gpu_ctx
+    rng = np.random.default_rng(11)
+    sets = [[new_draws(ds_default, rng) for _ in range(3)] for _ in range(3)]
+    packed = [ctx.pack_draws(d) for d in sets]
+    direct = [ctx.run_batch(3, 2, st) for st, _ in packed]
+    dev = ctx.prefetch_draws(3, packed[0][0])
+    for i in range(3):
+        nxt = ctx.prefetch_draws(3, packed[i + 1][0]) if i + 1 < 3 else None
+        got = ctx.run_batch(3, 2, dev)
+        assert np.array_equal(got, direct[i])
+        dev = nxt
