@@ -226,7 +226,7 @@ def run_b200(args):
             ctx._check(rc)
             dev = nxt
 
-    run_e2e(max(1, W // 2))
+    run_e2e(max(2, W // 2))
     barrier()
     ctx.event_record(2)
     t_e = time.perf_counter()

@@ -1215,11 +1215,15 @@ int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, ch
     ARG(host->doppler_u && host->phase_u && host->noise);
     CK(cudaSetDevice(c->device));
     const int S = c->S, N = c->N, TP = c->T * c->paths, B = c->max_batch;
+    for (auto& a : c->pf) {                                        // both sets are allocated by the first call
+        CK(a.du.alloc((size_t)B * TP)); CK(a.pu.alloc((size_t)B * TP)); CK(a.noise.alloc((size_t)B * S * N));
+        for (int i = 0; i < 3; ++i) if (c->sch[i].set) CK(a.bits[i].alloc((size_t)B * c->sch[i].n_bits));
+        for (int i = 0; i < 2; ++i) if (c->wf[i].set && c->wf[i].nsch) CK(a.pidx[i].alloc((size_t)B * c->sch[c->wf[i].sch[0]].P));
+    }
     Ctx::Prefetch& q = c->pf[c->pf_next];
     c->pf_next ^= 1;
     cudaStream_t cs = c->copy_stream;
     if (q.used) CK(cudaStreamWaitEvent(cs, q.released, 0));       // the batch that read this set has finished with it
-    CK(q.du.alloc((size_t)B * TP)); CK(q.pu.alloc((size_t)B * TP)); CK(q.noise.alloc((size_t)B * S * N));
     CK(cudaMemcpyAsync(q.du.p, host->doppler_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(q.pu.p, host->phase_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(q.noise.p, host->noise, sizeof(cplx) * (size_t)n_rep * S * N, cudaMemcpyHostToDevice, cs));
@@ -1227,7 +1231,6 @@ int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, ch
     for (int i = 0; i < 3; ++i)
         if (c->sch[i].set) {
             ARG(host->bits[i]);
-            CK(q.bits[i].alloc((size_t)B * c->sch[i].n_bits));
             CK(cudaMemcpyAsync(q.bits[i].p, host->bits[i], (size_t)n_rep * c->sch[i].n_bits, cudaMemcpyHostToDevice, cs));
             dev->bits[i] = q.bits[i].p;
         }
@@ -1235,7 +1238,6 @@ int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, ch
         if (c->wf[i].set && c->wf[i].nsch) {
             ARG(host->pilot_idx[i]);
             const int P = c->sch[c->wf[i].sch[0]].P;
-            CK(q.pidx[i].alloc((size_t)B * P));
             CK(cudaMemcpyAsync(q.pidx[i].p, host->pilot_idx[i], sizeof(int32_t) * n_rep * P, cudaMemcpyHostToDevice, cs));
             dev->pilot_idx[i] = q.pidx[i].p;
         }
