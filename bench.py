@@ -321,7 +321,17 @@ def run_b200(args):
     sim.close()
 
 
+def _one_json_line_stdout():
+    """Libraries (NCCL's version banner, ...) write to file descriptor 1 behind Python's back; the contract is ONE
+    JSON line on stdout.  Point fd 1 at stderr for the whole run and keep the real stdout for that line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 if __name__ == "__main__":
+    _one_json_line_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)
