@@ -480,10 +480,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 }
 
 #ifndef GEMMD_STAGES
-#define GEMMD_STAGES 2
+#define GEMMD_STAGES 4
 #endif
 #ifndef GEMMD_KT
-#define GEMMD_KT 16            // k-tile per stage (8 or 16)
+#define GEMMD_KT 8             // k-tile per stage (8 or 16)
+#endif
+#ifndef GEMMD_DEPTH
+#define GEMMD_DEPTH (GEMMD_STAGES > 2 ? GEMMD_STAGES - 2 : 1)
 #endif
 template <int WM, int WN, int TMW>
 __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 1 : 2) k_gemm_d(GemmDParams p) {
@@ -607,7 +610,9 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 1 : 2) k_gemm_d
     clear_acc();
     if (cc.t < total) warp_range();
 #pragma unroll 1
-    for (int i = 0; i < NS - 1; ++i) produce();
+    // the producer runs GEMMD_DEPTH jobs ahead; with DEPTH < NS - 1 the stage it refills was freed NS - DEPTH jobs ago,
+    // so a warp is not held up by warps that are still on the previous job (DEPTH = NS - 1 is a barrier per job)
+    for (int i = 0; i < GEMMD_DEPTH; ++i) produce();
 #pragma unroll 1
     while (cc.t < total) {
         produce();
