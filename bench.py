@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="realizations per step per GPU")
     ap.add_argument("--schemes", default="aux,cod,ofdm")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="realizations timed for cpu_baseline")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="realizations timed for cpu_baseline (about 13 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -107,7 +107,7 @@ def run_reference(args):
         return
     import numpy as np  # noqa: F401  (loads BLAS so that threadpool_info sees it)
     schemes = args.schemes.split(",")
-    n = max(1, args.cpu_sample // 2)
+    n = max(1, args.cpu_sample // 4)                      # a bounded sample per step: ~3 s of CPU work
     vals = []
     for _ in range(args.warmup):
         cpu_realizations_per_s(1, schemes)
