@@ -289,7 +289,10 @@ def run_b200(args):
                          "peak_source": "measured in this run: register-resident FP64 DMMA (m8n8k4) loop on every SM "
                                         "(chest_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; DFMA probe %.1f TFLOP/s"
                                         % peak_dfma,
-                         "algorithmic_flops_per_launch": ic_flops, "avg_launch_ms": ic_ms},
+                         "algorithmic_flops_per_launch": ic_flops, "avg_launch_ms": ic_ms,
+                         "flops_note": "algorithmic flops: 8 per complex multiply-add (SURVEY.md 8d); the kernel executes "
+                                       "the three-multiplication form (6 per complex multiply-add), so the tensor-pipe "
+                                       "busy fraction (ncu, profiles/r01_kic_main_summary.txt) is lower than frac"},
             "roofline_k2": {"kernel": "k_gemm_d (D = Q^H H G, persistent, support-aware)", "bound": "tensor",
                             "achieved": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12, "peak": peak_dmma, "unit": "TFLOP/s",
                             "frac": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12 / peak_dmma,
