@@ -69,6 +69,7 @@ struct Waveform {
 struct Constellation {
     bool set = false;
     int order = 0, nbits = 0, n_axis = 0, is_qam = 0;
+    bool real = false;           // every symbol (hence every unit-modulus pilot) is exactly real
     DevBuf<cplx> symbol, pilot; DevBuf<double> level; DevBuf<int> word_of_grid;
     ConstDev dev{};
 };
@@ -97,6 +98,7 @@ struct Scheme {
     DevBuf<uint8_t> bits;
     int64_t n_bits_edge = 0;
     int64_t c_nnz = 0;
+    bool c_real = false;
 };
 
 struct Ctx {
@@ -139,7 +141,7 @@ struct Ctx {
     cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     DevBuf<double> probe;
-    DevBuf<unsigned int> queue; int ic_grid = 0, ic_light_grid = 0; size_t ic_smem = 0;
+    DevBuf<unsigned int> queue; int ic_grid = 0, ic_light_grid = 0, ic_cfg = -1; size_t ic_smem = 0;
     DevBuf<unsigned long long> trace;
 };
 
@@ -220,6 +222,10 @@ SchemeDev scheme_dev(Ctx* c, int si) {
     d.n_data = s.n_data; d.nbits = c->cst[s.constellation].nbits; d.detect_mode = s.detect;
     d.constellation = s.constellation; d.n_bits_total = s.n_bits;
     d.sqrt_kappa = std::sqrt(s.kappa); d.dpr = s.dpr; d.sqrt_dpr = std::sqrt(s.dpr);
+#ifndef CHEST_VREAL
+#define CHEST_VREAL 1
+#endif
+    d.v_real = (CHEST_VREAL && s.c_real && c->cst[s.constellation].real) ? 1 : 0;
     d.c_rowptr = s.c_rowptr.p; d.c_col = s.c_col.p; d.c_val = s.c_val.p;
     d.ct_colptr = s.ct_colptr.p; d.ct_row = s.ct_row.p; d.ct_val = s.ct_val.p;
     d.pilot_pos = s.pilot_pos.p; d.data_pos = s.data_pos.p; d.pos2data = s.pos2data.p; d.edge_mask = s.edge_mask.p;
@@ -444,11 +450,32 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     // light: new pilot estimates + constellation tables
     // light: new pilot estimates, transmitted pilots, constellation tables, decided words (one byte per symbol)
     const size_t light_smem = (size_t)ip.pilot_rows * (2 * NC_MAX + 2) * sizeof(cplx) + cst_smem + (size_t)c->K_max * NC_MAX;
-    if (c->ic_grid == 0 || c->ic_smem != main_smem) {              // persistent main grid: one wave of resident CTAs
-        CK(cudaFuncSetAttribute(k_ic_main, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    // which loop bodies the main kernel carries: the pilot-quad count most EST units have, and the real-v masks
+    // every perfect-CSI unit of this configuration satisfies (16-column units: both schemes of a waveform)
+    int p4s = 4, m2 = 3, m1 = 1;
+    {
+        int n4 = 0, n8 = 0;
+        for (int si = 0; si < 3; ++si) if (c->sch[si].set) { int q = (c->sch[si].P + 3) / 4; n4 += q == 4; n8 += q == 8; }
+        p4s = n8 > n4 ? 8 : 4;
+        for (int wfi = 0; wfi < 2; ++wfi) {
+            Waveform& w = c->wf[wfi];
+            if (!w.set || !w.nsch) continue;
+            int mask = 0;
+            for (int q = 0; q < w.nsch; ++q) mask |= ip.sch[w.sch[q]].v_real << q;
+            if (w.nsch == 2) m2 &= mask; else m1 &= mask;
+        }
+        if (!((m2 == 0 && m1 == 0) || (m2 == 2 && m1 == 0) || (m2 == 3 && m1 == 1))) { m2 = 0; m1 = 0; }   // compiled combinations
+    }
+    void (*main_kernel)(IcParams) =
+        p4s == 4 ? (m2 == 2 ? k_ic_main<4, 2, 0> : (m2 == 3 ? k_ic_main<4, 3, 1> : k_ic_main<4, 0, 0>))
+                 : (m2 == 2 ? k_ic_main<8, 2, 0> : (m2 == 3 ? k_ic_main<8, 3, 1> : k_ic_main<8, 0, 0>));
+    const int cfg_id = p4s * 100 + m2 * 10 + m1;
+    if (c->ic_grid == 0 || c->ic_smem != main_smem || c->ic_cfg != cfg_id) {    // persistent main grid: one wave of resident CTAs
+        c->ic_cfg = cfg_id;
+        CK(cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CK(cudaFuncSetAttribute(k_ic_light, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         int per_sm = 0, per_sm_light = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ic_main, ic_threads, main_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, main_kernel, ic_threads, main_smem));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, k_ic_light, IC_LIGHT_THREADS, light_smem));
         if (per_sm < 1 || per_sm_light < 1)
             return fail(CHEST_ERR_STATE, "the IC kernels do not fit on an SM (too many pilots for the shared tables)");
@@ -468,7 +495,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         ip.it = it;
         if (it > 0) {                                              // phase B of iteration it
             ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
-            k_ic_main<<<std::min(c->ic_grid, n_units), ic_threads, main_smem, st>>>(ip);
+            main_kernel<<<std::min(c->ic_grid, n_units), ic_threads, main_smem, st>>>(ip);
             c->launches++;
             ip.trace = nullptr;
             if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
@@ -710,6 +737,8 @@ int chest_set_constellation(uint64_t handle, int which, int order, const double*
         double a = std::hypot(s[m].x, s[m].y);
         pil[m] = cmake(s[m].x / a, s[m].y / a);                       // xP./abs(xP), DS.m:366,368
     }
+    k.real = true;
+    for (int m = 0; m < order; ++m) if (s[m].y != 0.0 || pil[m].y != 0.0) k.real = false;
     std::vector<double> lev;
     for (int m = 0; m < order; ++m) lev.push_back(s[m].x);
     std::sort(lev.begin(), lev.end());
@@ -765,6 +794,8 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
     const int64_t nnz = jc[k_in];
     s.c_nnz = nnz;
     const cplx* v = reinterpret_cast<const cplx*>(val);
+    s.c_real = true;                                       // exactly real precoder: v = C z is real for a real constellation
+    for (int64_t e = 0; e < nnz; ++e) if (v[e].y != 0.0) { s.c_real = false; break; }
     // CSC (columns of C) for the de-spreading C' x, CSR (rows of C) for the precoding C z
     std::vector<int> colptr(k_in + 1), rows(nnz), rowptr(K + 1, 0), cols(nnz);
     std::vector<cplx> vcsc(nnz), vcsr(nnz);

@@ -6,6 +6,9 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef IC_INLINE
+#define IC_INLINE __forceinline__
+#endif
 #define NC_MAX 16          // columns (realizations x SNR points) one IC CTA carries
 
 // ============================================================================ RNG kernels
@@ -184,6 +187,7 @@ struct WTiles {                    // one (variant, snr) MMSE matrix in diagonal
 };
 struct SchemeDev {
     int waveform, K, K_in, P, P4, n_data, nbits, detect_mode, constellation, n_bits_total;
+    int v_real;                    // precoder and constellation are exactly real: v = C z has a zero imaginary part
     double sqrt_kappa, dpr, sqrt_dpr;
     const int* c_rowptr; const int* c_col; const cplx* c_val;      // precoder C, CSR (K rows)
     const int* ct_colptr; const int* ct_row; const cplx* ct_val;   // precoder C, CSC (K_in cols)
@@ -777,8 +781,8 @@ __device__ __forceinline__ void ld_cplx2(const cplx* ptr, cplx& a, cplx& b) {
 #ifndef EST_RING
 #define EST_RING 2
 #endif
-template <int P4T>
-__device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
+template <int P4T, bool VREAL>
+__device__ IC_INLINE void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
                                                  const int* __restrict__ tdel, const cplx* hPs, const cplx* hP3, const double* hP1,
                                                  const cplx* vbuf,
                                                  cplx* ybuf, const cplx* const* ycolp, cplx* ring, int K, int warp,
@@ -902,8 +906,13 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
             for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    accr[ct][e] = fma(tr[ct][e], v[ct][e].x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v[ct][e].y, accr[ct][e]);
-                    acci[ct][e] = fma(tr[ct][e], v[ct][e].y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v[ct][e].x, acci[ct][e]);
+                    if (VREAL) {                               // v exactly real: T o v needs half the multiply-adds
+                        accr[ct][e] = fma(tr[ct][e], v[ct][e].x, accr[ct][e]);
+                        acci[ct][e] = fma(ti[ct][e], v[ct][e].x, acci[ct][e]);
+                    } else {
+                        accr[ct][e] = fma(tr[ct][e], v[ct][e].x, accr[ct][e]); accr[ct][e] = fma(-ti[ct][e], v[ct][e].y, accr[ct][e]);
+                        acci[ct][e] = fma(tr[ct][e], v[ct][e].y, acci[ct][e]); acci[ct][e] = fma(ti[ct][e], v[ct][e].x, acci[ct][e]);
+                    }
                 }
             if (EST_WSRC == 0) load_w(t + ST, s);              // refill the slot just consumed
         }
@@ -923,7 +932,7 @@ __device__ __forceinline__ void est_interference(const cplx* __restrict__ frag, 
 }
 
 // generic pilot count (P4 not 4 or 8): direct fragment loads, no staging
-__device__ __forceinline__ void est_interference_generic(const cplx* __restrict__ frag, const int* __restrict__ tptr,
+__device__ IC_INLINE void est_interference_generic(const cplx* __restrict__ frag, const int* __restrict__ tptr,
                                                          const int* __restrict__ tdel, const cplx* hPs,
                                                          const cplx* vbuf, cplx* ybuf, const cplx* const* ycolp, int K,
                                                          int P4, int warp, int nwarp, int lane) {
@@ -984,8 +993,10 @@ __device__ __forceinline__ void est_interference_generic(const cplx* __restrict_
 #define IC_THREADS 256
 #endif
 #define PERF_STAGE_CPLX (PERF_CHUNK * (NC_MAX + 2) + PERF_CHUNK * PERF_V1S / 2)   // one stage, in complex elements
-template <int NCT>
-__device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
+// REALMASK bit ct: the v values of n-tile ct are exactly real (real precoder and constellation, e.g. the
+// data-spreading scheme): the complex x real product needs two DMMAs (ar v, ai v) instead of three.
+template <int NCT, int REALMASK>
+__device__ IC_INLINE void perf_interference(const cplx* __restrict__ Dm, const cplx* vbuf, cplx* ybuf,
                                                   const cplx* const* ycolp, cplx* vs, const int* __restrict__ rt_jlo,
                                                   const int* __restrict__ rt_jhi, int K, int warp, int nwarp,
                                                   int lane, int tid) {
@@ -1055,14 +1066,19 @@ __device__ __forceinline__ void perf_interference(const cplx* __restrict__ Dm, c
                     if (i >= K || j >= K || i == j) a[u] = cmake(0.0, 0.0);
                     const int row = s * PERF_CHUNK + sub * PERF_DSUB + 4 * u + t4;
 #if CHEST_3M
-                    const double as = a[u].x + a[u].y;
+                    const double as = a[u].x + a[u].y;       // dead code when every n-tile is real
 #pragma unroll
                     for (int ct = 0; ct < NCT; ++ct) {
                         const double b1 = v1[row * PERF_V1S + ct * 8 + g];
-                        const cplx b23 = v23[row * VS + ct * 8 + g];
-                        dmma884(acc1[ct][0], acc1[ct][1], as, b1);
-                        dmma884(accr[ct][0], accr[ct][1], a[u].y, b23.x);
-                        dmma884(acci[ct][0], acci[ct][1], a[u].x, b23.y);
+                        if ((REALMASK >> ct) & 1) {
+                            dmma884(accr[ct][0], accr[ct][1], a[u].x, b1);
+                            dmma884(acci[ct][0], acci[ct][1], a[u].y, b1);
+                        } else {
+                            const cplx b23 = v23[row * VS + ct * 8 + g];
+                            dmma884(acc1[ct][0], acc1[ct][1], as, b1);
+                            dmma884(accr[ct][0], accr[ct][1], a[u].y, b23.x);
+                            dmma884(acci[ct][0], acci[ct][1], a[u].x, b23.y);
+                        }
                     }
 #else
                     const double nai = dneg(a[u].y);
@@ -1134,6 +1150,11 @@ __device__ __forceinline__ void ic_load_unit(const IcParams& p, const IcCta& cta
 #ifndef IC_MIN_BLOCKS
 #define IC_MIN_BLOCKS 2
 #endif
+// The loop bodies compiled into one instance are chosen by the host for the configuration at hand (more
+// bodies in one kernel cost registers in all of them): P4S = pilot-quad count of the specialised estimated-CSI
+// loop (other schemes take the generic loop), M2 / M1 = real-v mask every 16-column / 8-column perfect-CSI unit
+// of the configuration satisfies (0 is always valid).
+template <int P4S, int M2, int M1>
 __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams p) {
     constexpr int NC = NC_MAX, HS = NC + 2;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -1176,19 +1197,20 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
             __syncthreads();
             // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
             const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
-            if (sd.P4 == 4)
-                est_interference<4>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3, hP1,
-                                    vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
-            else if (sd.P4 == 8)
-                est_interference<8>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], hPs, hP3, hP1,
-                                    vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane);
+#define EST_CALL(P4T_, VR_) est_interference<P4T_, VR_>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], \
+                                                        hPs, hP3, hP1, vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane)
+            if (sd.P4 == P4S) { if (sd.v_real) EST_CALL(P4S, true); else EST_CALL(P4S, false); }
             else
                 est_interference_generic(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev],
                                          hPs, vbuf, ybuf, sh.ycolp, K, sd.P4, warp, nwarp, lane);
         } else {
             const cplx* Dm = p.D[wf] + (int64_t)cta.snr * (((K + 7) / 8) * 8) * K;     // cta.snr holds the realization
-            if (cta.n_cols <= 8) perf_interference<1>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid);
-            else perf_interference<2>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid);
+            // each 8-column half is on one scheme: real v of a half -> two DMMAs per product instead of three
+            // (the masks M2 / M1 hold for every unit of this configuration, see the host)
+#define PERF_CALL(NCT_, MASK_) perf_interference<NCT_, MASK_>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid)
+            if (cta.n_cols <= 8) PERF_CALL(1, M1);
+            else PERF_CALL(2, M2);
+#undef PERF_CALL
         }
     }
     IC_TRACE(3, gtime()); IC_TRACE(7, n_done);
