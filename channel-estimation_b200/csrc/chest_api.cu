@@ -1432,7 +1432,13 @@ int chest_work_model(uint64_t handle, int n_iter, double* out) {
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch) continue;
         out[0] += w.flops_d;                                                   // K2
-        out[2] += 8.0 * w.d_struct_pairs * w.nsch * S * n_iter;              // perfect CSI (D - diag h) v over D's structural support
+        // perfect CSI (D - diag h) v over D's structural support: 8 flops per complex multiply-add, 4 where v is
+        // exactly real (real precoder and constellation)
+        for (int q = 0; q < w.nsch; ++q) {
+            const Scheme& sq = c->sch[w.sch[q]];
+            const bool vr = sq.c_real && c->cst[sq.constellation].real;
+            out[2] += (vr ? 4.0 : 8.0) * w.d_struct_pairs * S * n_iter;
+        }
         out[3] += w.nsch * (w.flops_mod + 8.0 * c->T * c->N) + w.nsch * S * w.flops_demod;   // TX + demod
     }
     for (int si = 0; si < 3; ++si) {
@@ -1442,7 +1448,7 @@ int chest_work_model(uint64_t handle, int n_iter, double* out) {
         double off = 0;
         for (int it = 1; it <= n_iter; ++it) {
             int var_prev = (it - 1 == 0 || (it - 1) <= n_iter / 2) ? 0 : 1;
-            off += 8.0 * s.mm[var_prev].nnz_offdiag_pairs * (s.P + 1);
+            off += s.mm[var_prev].nnz_offdiag_pairs * (8.0 * s.P + (s.c_real && c->cst[s.constellation].real ? 4.0 : 8.0));
         }
         out[1] += S * (off + 8.0 * s.K * s.P * (n_iter + 1));
         out[6] += S * off;                                                     // of which in k_ic_main (off-diagonal products)
