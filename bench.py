@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="realizations per step per GPU")
     ap.add_argument("--schemes", default="aux,cod,ofdm")
+    ap.add_argument("--no-ofdm-only", action="store_true", help="skip the extra OFDM-chain-only measurement")
     ap.add_argument("--cpu-sample", type=int, default=48, help="realizations timed for cpu_baseline (about 13 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -91,6 +92,34 @@ def cpu_realizations_per_s(n_sample, schemes, faithful=False):
     for d in draws[:n_sample]:
         ds_realization(S, d, faithful=faithful)
     return n_sample / (time.perf_counter() - t)
+
+
+def ofdm_only_line(torch, Simulation, device, K, W, cpu_sample):
+    """realizations/s of the DS.m loop body with only the OFDM scheme enabled (K = 336), B = 4096 per step."""
+    B, I = 4096, 4
+    sim = Simulation(schemes=("ofdm",), max_batch=B, device=device, seed=1234)
+    ctx = sim.ctx
+    err_dev = torch.zeros(B * len(sim.Pn) * (I + 1) * 12, dtype=torch.int32, device="cuda")
+    step = [0]
+
+    def run():
+        ctx.run_batch_device(B, I, None, seed=sim.seed, first_rep=step[0] * B, err_dev_ptr=err_dev.data_ptr())
+        step[0] += 1
+    for _ in range(W):
+        run()
+    torch.cuda.synchronize()
+    ctx.event_record(0)
+    for _ in range(K):
+        run()
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    line = {"value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "realizations_per_step": B,
+            "workload": "DS.m default parameters with the OFDM chain only: N=540, K=336, P=16, 7 SNR points, 4 IC iterations"}
+    sim.close()
+    if cpu_sample:
+        line["cpu_baseline"] = {"value": cpu_realizations_per_s(max(8, cpu_sample), ["ofdm"]), "unit": UNIT,
+                                "cores": blas_threads(), "kind": "port"}
+    return line
 
 
 def blas_threads():
@@ -306,6 +335,14 @@ def run_b200(args):
             "wall_ms_per_step": wall_ms / K, "launches_per_step": launches_per_step, "setup_s": setup_s,
             "sanity_ber_40dB_last_iteration": ber40,
         }
+        if world == 1 and set(schemes) != {"ofdm"} and not args.no_ofdm_only:
+            # the same loop body with the OFDM chain alone (the narrow reading of "default params: OFDM"), for
+            # comparison: resident value only, same timing rules; never fatal for the main line
+            try:
+                out["ofdm_chain_only"] = ofdm_only_line(torch, DoublySelectiveSimulation, local, K, W,
+                                                        None if args.no_cpu_baseline else args.cpu_sample)
+            except Exception as e:                              # noqa: BLE001
+                out["ofdm_chain_only"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_sample
             v = cpu_realizations_per_s(n, schemes)
