@@ -418,3 +418,25 @@ def test_prefetched_draws_equal_direct_upload(gpu_ctx, ds_default):
         got = ctx.run_batch(3, 2, dev)
         assert np.array_equal(got, direct[i])
         dev = nxt
+
+
+def test_more_than_eight_snr_points_and_ragged_batch():
+    """Perfect-CSI units hold at most 8 SNR points per scheme (one DMMA n-tile per scheme): with 11 points a
+    realization is split into two units; 19 realizations leave the last estimated-CSI unit ragged (3 of 16 columns).
+    Error counts must equal the oracle's on the same draws."""
+    from oracle.ds import DSConfig, ds_setup, ds_realization, new_draws
+    from tests.helpers import context_from_oracle
+    S = ds_setup(DSConfig(M_SNR_dB=tuple(range(10, 41, 3)), NrIterations=2))
+    assert len(S["Pn"]) == 11
+    ctx = context_from_oracle(S, max_batch=19)
+    rng = np.random.default_rng(2024)
+    draws = [new_draws(S, rng) for _ in range(19)]
+    st, keep = ctx.pack_draws(draws)
+    err = ctx.run_batch(19, 2, st)
+    for r in (0, 7, 15, 16, 18):
+        assert np.array_equal(err[r], err_from_oracle(ds_realization(S, draws[r]), 2)), r
+    # the same realizations one at a time give the same counts
+    for r in (3, 18):
+        st1, keep1 = ctx.pack_draws([draws[r]])
+        assert np.array_equal(ctx.run_batch(1, 2, st1)[0], err[r])
+    ctx.close()
