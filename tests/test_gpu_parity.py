@@ -440,3 +440,41 @@ def test_more_than_eight_snr_points_and_ragged_batch():
         st1, keep1 = ctx.pack_draws([draws[r]])
         assert np.array_equal(ctx.run_batch(1, 2, st1)[0], err[r])
     ctx.close()
+
+
+@pytest.mark.parametrize("N,K,taps", [(61, 20, (0, 2, 3)), (96, 50, (0, 1)), (131, 72, (0, 4))])
+def test_k2_synthetic_shapes(N, K, taps):
+    """K1 + K2 + modem on synthetic waveforms through the bare C ABI: odd sample counts (padded operand planes),
+    symbol counts that are not multiples of the 8-row / 48-column tiles, gaps in the power delay profile, columns
+    with ragged supports.  Reference: NumPy on the same impulse response."""
+    import chest_b200
+    rng = np.random.default_rng(N * 1000 + K)
+    pdp = np.zeros(max(taps) + 1); pdp[list(taps)] = rng.random(len(taps)) + 0.1; pdp /= pdp.sum()
+
+    def waveform():
+        M = rng.standard_normal((N, K)) + 1j * rng.standard_normal((N, K))
+        for j in range(K):                                    # compact, ragged supports (exact zeros outside)
+            lo = int(rng.integers(0, N // 2)); hi = int(rng.integers(lo + 3, N + 1))
+            M[:lo, j] = 0; M[hi:, j] = 0
+        return M
+    G, Q = waveform(), waveform()
+    ctx = chest_b200.DeviceContext()
+    ctx.set_channel(N, pdp, 900.0, 1.0 / 360e3, 40, "Jakes")
+    ctx.set_waveform("F", G, Q)
+    ctx.finalize(3)
+    ctx.new_realization_seeded(3, 9, 0)
+    for b in (0, 2):
+        h = ctx.impulse_response(b)                           # N x Lt
+        H = np.zeros((N, N), dtype=complex)
+        for m in taps:
+            r = np.arange(m, N)
+            H[r, r - m] = h[r, m]
+        assert rel(ctx.convolution_matrix(b).toarray(), H) < 1e-15
+        D_ref = Q.conj().T @ H @ G
+        D, hd = ctx.transmission_matrix("F", b)
+        assert rel(D, D_ref) < TOL and rel(hd, np.diag(D_ref)) < TOL
+    x = rng.standard_normal((K, 2)) + 1j * rng.standard_normal((K, 2))
+    assert rel(ctx.modulate("F", x), G @ x) < 1e-12
+    r = rng.standard_normal((N, 2)) + 1j * rng.standard_normal((N, 2))
+    assert rel(ctx.demodulate("F", r), Q.conj().T @ r) < 1e-12
+    ctx.close()
