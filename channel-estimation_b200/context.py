@@ -290,6 +290,10 @@ class DeviceContext:
         self._check(self.lib.chest_event_elapsed(self._h, a, b, C.byref(ms)))
         return float(ms.value)
 
+    def set_perfect_csi_mode(self, mode):
+        """'factored' (default): D never formed; 'dense': D = Q^H H G materialised per realization (K2)."""
+        self._check(self.lib.chest_set_perfect_csi_mode(self._h, {"dense": 0, "factored": 1}[mode]))
+
     def kernel_times(self):
         """Device ms of k_apply_hg, k_gemm_d, k_ic_main (sum), k_ic_light (sum) in the last profiled batch."""
         out = (C.c_float * 4)()

@@ -63,6 +63,12 @@ struct Waveform {
     int nsch = 0; int sch[2] = {0, 0};
     // batch state
     DevBuf<cplx> x, s, r0, y, D, htrue;
+    // factored perfect-CSI pass (perf_mode 1): column tables of the units' v / y_ic slots, and the two vector sets
+    DevBuf<int> q_lo_d, q_hi_d;
+    DevBuf<cplx> Pd; DevBuf<int> pd_klo, pd_khi;        // diag(D) operand: P[i][t*N + n] = conj(Q[n,i]) G[n - tau_t, i]
+    std::vector<cplx> Gh, Qh;                           // host copies of G, Q (finalize builds Pd from them)
+    DevBuf<int64_t> f_voff, f_yoff; DevBuf<int> f_rep; DevBuf<cplx> f_s, f_r;
+    int f_cols = 0, perf_base = 0, perf_nblk = 0;
     int tile = 64;              // CTA tile size of the GEMMs on this waveform (48 or 64)
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
 };
@@ -125,6 +131,8 @@ struct Ctx {
         cudaEvent_t landed = nullptr, released = nullptr; bool used = false;
     } pf[2];
     int pf_next = 0;
+    int perf_mode = 1;           // 1 (default): factored, y - Q^H H (G v) + h v, D never formed; 0: D materialised (K2) and applied densely
+    int n_est_units = 0;
     cudaStream_t copy_stream = nullptr;
     DevBuf<uint32_t> err;
     DevBuf<cplx> scratch, tmp_a, tmp_b;
@@ -283,6 +291,35 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     return CHEST_OK;
 }
 
+// Perfect-CSI cancellation without D: y_ic = y - Q^H (H (G v)) + h v for every (realization, scheme, SNR) column
+// (DS.m:541-543 with D = Q^H H G, h = diag D).  Two support-aware GEMMs over all columns of the batch with the banded
+// channel between them; the second GEMM's epilogue writes y_ic into the units' scratch.
+int stage_factored_perfect_csi(Ctx* c, int n_rep) {
+    const int N = c->N;
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set || !w.nsch || !w.f_cols) continue;
+        GemmParams p{};
+        p.M = N; p.Kc = w.K; p.n_cols = w.f_cols; p.lda = w.K; p.ldc = N; p.conj_a = 0;
+        p.At = w.Gt.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.out = w.f_s.p;
+        p.bsrc = c->scratch.p; p.b_off = w.f_voff.p; p.b_kstride = NC_MAX;
+        CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));                                   // s = G v
+        dim3 grid((N + 127) / 128, w.f_cols);
+        k_apply_h_cols<<<grid, 128, 0, c->stream>>>(w.f_r.p, w.f_s.p, c->h.p, c->d_tap_delay.p, w.f_rep.p, N, c->T);   // r = H s
+        c->launches++;
+        CK(cudaGetLastError());
+        GemmParams q{};
+        q.M = w.K; q.Kc = N; q.n_cols = w.f_cols; q.lda = N; q.ldc = w.K; q.conj_a = 1;
+        q.At = w.Q.p; q.mt_klo = w.q_klo.p; q.mt_khi = w.q_khi.p; q.out = w.f_s.p;
+        q.bsrc = w.f_r.p; q.ldb = N;
+        q.e_out = c->scratch.p + (size_t)c->K_max * NC_MAX; q.e_off = w.f_voff.p;       // y_ic sits one buffer behind v
+        q.e_y = w.y.p; q.e_yoff = w.f_yoff.p; q.e_h = w.htrue.p; q.e_rep = w.f_rep.p;
+        q.e_v = c->scratch.p; q.e_voff = w.f_voff.p;
+        CK(launch_gemm<GEMM_PLAIN>(c, q, 1, w.tile));                                   // y_ic = y - Q^H r + h v
+    }
+    return CHEST_OK;
+}
+
 int build_ctas(Ctx* c, int n_rep) {
     if (c->ctas_for_batch == n_rep) return CHEST_OK;
     std::vector<IcCta> v;
@@ -320,7 +357,12 @@ int build_ctas(Ctx* c, int n_rep) {
         if (!strcmp(dbg, "est_fbmc")) { p1.clear(); p2.clear(); e2.clear(); }
         if (!strcmp(dbg, "perf_fbmc")) { e1.clear(); e2.clear(); p2.clear(); }
     }
-    if (getenv("CHEST_IC_WEAVE")) {                            // development: interleave compute- and memory-heavy units
+    if (c->perf_mode == 1) {                                   // factored mode: k_ic_main runs the EST units only (listed first)
+        v.insert(v.end(), e1.begin(), e1.end()); v.insert(v.end(), e2.begin(), e2.end());
+        c->n_est_units = (int)v.size();
+        c->wf[CHEST_WF_FBMC].perf_base = (int)v.size(); v.insert(v.end(), p1.begin(), p1.end());
+        c->wf[CHEST_WF_OFDM].perf_base = (int)v.size(); v.insert(v.end(), p2.begin(), p2.end());
+    } else if (getenv("CHEST_IC_WEAVE")) {                     // development: interleave compute- and memory-heavy units
         weave(e1, p1);
         weave(e2, p2);
     } else {                                                   // longest units first: the short ones fill the tail of the queue
@@ -328,8 +370,32 @@ int build_ctas(Ctx* c, int n_rep) {
         v.insert(v.end(), e2.begin(), e2.end()); v.insert(v.end(), p2.begin(), p2.end());
     }
     c->n_ctas = (int)v.size();
+    if (c->perf_mode != 1) c->n_est_units = c->n_ctas;
     CK(c->ctas.upload(v, c->stream));
     CK(c->scratch.alloc((size_t)c->n_ctas * 3 * c->K_max * NC_MAX));
+    if (c->perf_mode == 1) {
+        // column tables: perfect-CSI column (rep, scheme slot, snr) -> its v / y_ic slot in the unit scratch, its y
+        const int S = c->S, nblk = (S + 7) / 8;
+        for (int wfi = 0; wfi < 2; ++wfi) {
+            Waveform& w = c->wf[wfi];
+            if (!w.set || !w.nsch) { w.f_cols = 0; continue; }
+            const int nv = w.nsch * S;
+            w.perf_nblk = nblk; w.f_cols = nv * n_rep;
+            std::vector<int64_t> voff(w.f_cols), yoff(w.f_cols);
+            std::vector<int> rep(w.f_cols);
+            for (int r = 0; r < n_rep; ++r)
+                for (int slot = 0; slot < w.nsch; ++slot)
+                    for (int snr = 0; snr < S; ++snr) {
+                        const int col = r * nv + slot * S + snr;
+                        const int64_t unit = w.perf_base + (int64_t)r * nblk + snr / 8;
+                        voff[col] = (unit * 3 + 1) * c->K_max * NC_MAX + slot * 8 + snr % 8;
+                        yoff[col] = ((int64_t)slot * S * n_rep + (int64_t)snr * n_rep + r) * w.K;
+                        rep[col] = r;
+                    }
+            CK(w.f_voff.upload(voff, c->stream)); CK(w.f_yoff.upload(yoff, c->stream)); CK(w.f_rep.upload(rep, c->stream));
+            CK(w.f_s.alloc((size_t)w.f_cols * c->N)); CK(w.f_r.alloc((size_t)w.f_cols * c->N));
+        }
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->ctas_for_batch = n_rep;
     return CHEST_OK;
@@ -407,8 +473,17 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
     // ---- stage 2 (K2): D = Q^H H G, h = diag(D)
-    for (int wfi = 0; wfi < 2; ++wfi)
-        if (c->wf[wfi].set && c->wf[wfi].nsch) { rc = stage_transmission_matrix(c, wfi, n_rep, 0); if (rc) return rc; }
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.set || !w.nsch) continue;
+        if (c->perf_mode == 1) {                               // factored mode needs only h = diag(D)
+            GemmParams p{};                                    // htrue[rep][i] = P[i][:] . h[rep][:]
+            p.M = w.K; p.Kc = c->T * N; p.n_cols = n_rep; p.lda = c->T * N; p.ldc = w.K; p.conj_a = 0;
+            p.At = w.Pd.p; p.mt_klo = w.pd_klo.p; p.mt_khi = w.pd_khi.p; p.out = w.htrue.p;
+            p.bsrc = c->h.p; p.ldb = c->T * N;
+            CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));
+        } else { rc = stage_transmission_matrix(c, wfi, n_rep, 0); if (rc) return rc; }
+    }
     if (c->profiling) CK(cudaEventRecord(c->ev[3], st));
     // ---- stage 3 (K3a): y = Q^H (r0 + noise) for every (scheme, SNR, realization)
     for (int wfi = 0; wfi < 2; ++wfi) {
@@ -483,7 +558,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     }
     CK(c->queue.alloc(32));
     CK(cudaMemsetAsync(c->queue.p, 0, 32 * sizeof(unsigned int), st));
-    ip.queue = c->queue.p; ip.n_units = c->n_ctas;
+    ip.queue = c->queue.p; ip.n_units = c->n_ctas; ip.n_units_main = c->n_est_units;
     size_t n_err = (size_t)n_rep * S * (n_iter + 1) * 12;
     uint32_t* err = err_dev ? err_dev : c->err.p;
     CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
@@ -495,9 +570,10 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         ip.it = it;
         if (it > 0) {                                              // phase B of iteration it
             ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
-            main_kernel<<<std::min(c->ic_grid, n_units), ic_threads, main_smem, st>>>(ip);
+            main_kernel<<<std::min(c->ic_grid, std::max(c->n_est_units, 1)), ic_threads, main_smem, st>>>(ip);
             c->launches++;
             ip.trace = nullptr;
+            if (c->perf_mode == 1) { rc = stage_factored_perfect_csi(c, n_rep); if (rc) return rc; }
             if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
         }
         // phases C, D, E of iteration it (+ phase A of iteration it+1)
@@ -528,7 +604,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
             c->kernel_ms[3] += t;
         }
         c->kernel_ms[0] = c->kernel_ms[1] = 0;
-        if (n_rep > 1)
+        if (n_rep > 1 && c->perf_mode != 1)
             for (int wfi = 0; wfi < 2; ++wfi)
                 if (c->wf[wfi].set && c->wf[wfi].nsch) {
                     float t = 0;
@@ -538,7 +614,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         c->hg_ms = 0; c->hg_bytes = 0;
         for (int wfi = 0; wfi < 2; ++wfi) {
             Waveform& w = c->wf[wfi];
-            if (!w.set || !w.nsch) continue;
+            if (!w.set || !w.nsch || c->perf_mode == 1 || n_rep <= 1) continue;
             float t = 0;
             cudaEventElapsedTime(&t, c->ev_hg[2 * wfi], c->ev_hg[2 * wfi + 1]);
             c->hg_ms += t;
@@ -577,6 +653,7 @@ int chest_create(int device, uint64_t* handle) {
     if (maj != 10) return fail(CHEST_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200); no fallback path exists");
     CK(cudaSetDevice(device));
     Ctx* c = new Ctx();
+    if (const char* e = getenv("CHEST_PERF_MODE")) c->perf_mode = (!strcmp(e, "dense") || !strcmp(e, "0")) ? 0 : 1;
     c->device = device; c->n_sm = sm;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -663,6 +740,8 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
     c->N = N;
     w.K = K;
     CK(w.G.upload(reinterpret_cast<const cplx*>(G), (size_t)N * K, c->stream));
+    w.Gh.assign(reinterpret_cast<const cplx*>(G), reinterpret_cast<const cplx*>(G) + (size_t)N * K);
+    w.Qh.assign(reinterpret_cast<const cplx*>(Q), reinterpret_cast<const cplx*>(Q) + (size_t)N * K);
     CK(w.Q.upload(reinterpret_cast<const cplx*>(Q), (size_t)N * K, c->stream));
     {   // operand planes of Q^H for the three-multiplication GEMMs (K2, K3a): conj(q) = (re, -im)
         const int Np = (N + 1) & ~1;
@@ -705,6 +784,7 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
     CK(w.q_klo.upload(lo, c->stream)); CK(w.q_khi.upload(hi, c->stream));
     tile_ranges(w.q_lo, w.q_hi, 8, 0, N, lo, hi);
     CK(w.q8_klo.upload(lo, c->stream)); CK(w.q8_khi.upload(hi, c->stream));
+    CK(w.q_lo_d.upload(w.q_lo, c->stream)); CK(w.q_hi_d.upload(w.q_hi, c->stream));
     // row supports of G (which symbols j touch sample n) for s = G x
     std::vector<int> rlo(N, K), rhi(N, 0);
     for (int j = 0; j < K; ++j)
@@ -983,6 +1063,23 @@ int chest_finalize(uint64_t handle, int max_batch) {
         for (int j = 0; j < K; ++j) w.hg_rows[j] = std::max(0, hi[j / w.tile] - lo[j / w.tile]);
         tile_ranges(w.g_lo, w.g_hi, 8, max_delay, N, lo, hi);
         CK(w.hg8_klo.upload(lo, c->stream)); CK(w.hg8_khi.upload(hi, c->stream));
+        {   // diag(D) as a GEMM over realizations: h[rep][i] = sum_{t,n} P[i][t*N + n] h[rep][t][n]
+            const int T = c->T;
+            std::vector<cplx> P((size_t)K * T * N, cmake(0.0, 0.0));
+            for (int i = 0; i < K; ++i)
+                for (int t = 0; t < T; ++t) {
+                    const int d = c->tap_delay[t];
+                    for (int n = std::max(w.q_lo[i], d); n < w.q_hi[i]; ++n) {
+                        const cplx q = w.Qh[(size_t)n + (size_t)N * i], g = w.Gh[(size_t)(n - d) + (size_t)N * i];
+                        P[((size_t)i * T + t) * N + n] = cmake(q.x * g.x + q.y * g.y, q.x * g.y - q.y * g.x);
+                    }
+                }
+            CK(w.Pd.upload(P, c->stream));
+            std::vector<int> ql, qh;
+            tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, ql, qh);
+            for (size_t a = 0; a < ql.size(); ++a) if (qh[a] > ql[a]) qh[a] += (T - 1) * N;   // the range spans all tap segments
+            CK(w.pd_klo.upload(ql, c->stream)); CK(w.pd_khi.upload(qh, c->stream));
+        }
         {   // work list of K2: tile pairs of D whose Q / H*G supports overlap (the rest of D is structurally zero)
             std::vector<int> ql, qh, gl, gh;
             tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, ql, qh);
@@ -1412,6 +1509,14 @@ int chest_banded_apply_stats(uint64_t handle, float* ms, double* bytes) {
     Ctx* c = from(handle);
     ARG(c && ms && bytes);
     *ms = c->hg_ms; *bytes = c->hg_bytes;
+    return CHEST_OK;
+}
+
+int chest_set_perfect_csi_mode(uint64_t handle, int mode) {
+    Ctx* c = from(handle);
+    ARG(c && (mode == 0 || mode == 1));
+    c->perf_mode = mode;
+    c->ctas_for_batch = -1;                                    // unit order and column tables depend on the mode
     return CHEST_OK;
 }
 

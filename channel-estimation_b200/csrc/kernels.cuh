@@ -151,6 +151,21 @@ __global__ void k_apply_hg(cplx* __restrict__ HG1, double* __restrict__ HG2, con
     }
 }
 
+// r[col][n] = sum_tap h[rep_of_col[col]][tap][n] * s[col][n - delay_tap]: the banded H applied to a list of columns
+__global__ void k_apply_h_cols(cplx* __restrict__ r, const cplx* __restrict__ s, const cplx* __restrict__ h,
+                               const int* __restrict__ tap_delay, const int* __restrict__ rep_of_col, int N, int T) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (n >= N) return;
+    const int rep = rep_of_col[col];
+    const cplx* sc = s + (int64_t)col * N;
+    cplx acc = cmake(0.0, 0.0);
+    for (int t = 0; t < T; ++t) {
+        const int d = tap_delay[t];
+        if (n >= d) cfma(acc, h[((int64_t)rep * T + t) * N + n], sc[n - d]);
+    }
+    r[(int64_t)col * N + n] = acc;
+}
+
 // ============================================================================ constellations
 struct ConstDev {
     int order, nbits, n_axis;           // n_axis = order (PAM) or sqrt(order) (QAM)
@@ -258,8 +273,14 @@ struct GemmParams {
     const int* mt_klo; const int* mt_khi;      // per CTA row tile: k support range
     const int* m8_klo; const int* m8_khi;      // per 8 rows: k support range (warp-level clipping; may be null)
     cplx* out;                                  // [col][ldc]
-    // PLAIN: B[k,col] = bsrc[col*ldb + k]
+    // PLAIN: B[k,col] = bsrc[col*ldb + k], or with a column table bsrc[b_off[col] + k*b_kstride]
+    // (the unit-interleaved v of the IC scratch: k stride 16)
     const cplx* bsrc; int ldb;
+    const int64_t* b_off; int b_kstride;
+    // PLAIN, cancellation epilogue (factored perfect-CSI pass): instead of out[col][m] = U the kernel writes
+    // e_out[e_off[col] + m*16] = e_y[e_yoff[col] + m] - U + e_h[e_rep[col]*M + m] * bsrc2[e_off2[col] + m*16]
+    cplx* e_out; const int64_t* e_off; const cplx* e_y; const int64_t* e_yoff; const cplx* e_h; const int* e_rep;
+    const cplx* e_v; const int64_t* e_voff;
     // DEMOD: col = (g*n_snr + snr)*n_rep + rep ; B = r0[(g*n_rep+rep)*N + k] + sqrt(pn[snr]/2)*noise[(rep*n_snr+snr)*N + k]
     const cplx* r0; const cplx* noise; const double* noise_scale; int n_snr, n_rep;
     int N;
@@ -338,7 +359,8 @@ k_gemm(GemmParams p) {
             int gk = k0 + kk, col = n0 + c;
             bool ok = col < p.n_cols && gk < khi;
             if (MODE == GEMM_PLAIN) {
-                cp_async16(&Bs[stage][c][kk], p.bsrc + (ok ? (int64_t)col * p.ldb + gk : 0), ok);
+                const int64_t o = !ok ? 0 : (p.b_off ? p.b_off[col] + (int64_t)gk * p.b_kstride : (int64_t)col * p.ldb + gk);
+                cp_async16(&Bs[stage][c][kk], p.bsrc + o, ok);
             } else {
                 cplx v = cmake(0.0, 0.0);
                 if (ok) {
@@ -443,6 +465,12 @@ k_gemm(GemmParams p) {
                 if (m < p.M && col < p.n_cols) {
                     cplx v = CHEST_3M ? cmake(c1[CHEST_3M ? a : 0][b][e] + cr[a][b][e], c1[CHEST_3M ? a : 0][b][e] + ci[a][b][e])
                                       : cmake(cr[a][b][e], ci[a][b][e]);
+                    if (MODE == GEMM_PLAIN && p.e_out) {       // y_ic = y - U + h v  (DS.m:541-543 with U = Q^H H G v)
+                        const cplx yv = p.e_y[p.e_yoff[col] + m], hv = p.e_h[(int64_t)p.e_rep[col] * p.M + m];
+                        const cplx vv = p.e_v[p.e_voff[col] + (int64_t)m * 16];
+                        const cplx hvv = cmul(hv, vv);
+                        p.e_out[p.e_off[col] + (int64_t)m * 16] = cmake(yv.x - v.x + hvv.x, yv.y - v.y + hvv.y);
+                    } else
                     out[(int64_t)col * p.ldc + m] = v;
                 }
             }
@@ -717,6 +745,7 @@ struct IcParams {
     uint32_t* err;             // [rep][snr][it][scheme][csi][edge]
     unsigned int* queue;       // [n_iter+1] unit counters of the main stage (zeroed per batch)
     int n_units;
+    int n_units_main;          // units k_ic_main processes (all of them, or only the EST units in factored mode)
     unsigned long long* trace; // development: per CTA {smid, t0, t_pre, t_main_own, t_main_all, t_end, B busy ns, units}
 };
 
@@ -1175,7 +1204,7 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
         if (tid == 0) sh.unit = (int)atomicAdd(p.queue + it, 1u);
         __syncthreads();
         const int unit = sh.unit;
-        if (unit >= p.n_units) break;
+        if (unit >= p.n_units_main) break;
         ++n_done;
         const IcCta cta = p.ctas[unit];
         ic_load_unit(p, cta, sh);

@@ -171,6 +171,14 @@ int64_t chest_draws_bytes(uint64_t handle, int n_rep);
  * Either draws (explicit) or, if draws == NULL, the device generator keyed by (seed, first_rep+r). */
 int chest_run_batch(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws,
                     uint64_t seed, int64_t first_rep, uint32_t* err_out);
+/* How the perfect-CSI twin of the loop body applies the true channel (DS.m:541-543, y - (D - diag h) v):
+ * CHEST_PERFECT_FACTORED (default): y - Q^H (H (G v)) + h v with h = diag(D) from a small GEMM -- D itself is never
+ * formed (exactly as D-hat never is);  CHEST_PERFECT_DENSE: D = Q^H H G is materialised per realization (K2) and
+ * applied.  Same results; chest_transmission_matrix returns D in either mode. */
+#define CHEST_PERFECT_DENSE     0
+#define CHEST_PERFECT_FACTORED  1
+int chest_set_perfect_csi_mode(uint64_t handle, int mode);
+
 /* Same with the result left on the device: err_dev is a device pointer (used by bench `value`). */
 int chest_run_batch_device(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws,
                            uint64_t seed, int64_t first_rep, uint32_t* err_dev);

@@ -478,3 +478,24 @@ def test_k2_synthetic_shapes(N, K, taps):
     r = rng.standard_normal((N, 2)) + 1j * rng.standard_normal((N, 2))
     assert rel(ctx.demodulate("F", r), Q.conj().T @ r) < 1e-12
     ctx.close()
+
+
+def test_dense_and_factored_perfect_csi_agree(ds_default):
+    """The perfect-CSI twin in its two modes -- D = Q^H H G materialised (K2) and applied, or y - Q^H H (G v) + h v
+    with D never formed (default) -- gives the same error counts as the oracle, and the same one-tap channel."""
+    from oracle.ds import ds_realization, new_draws
+    from tests.helpers import context_from_oracle
+    S = ds_default
+    rng = np.random.default_rng(31)
+    draws = [new_draws(S, rng) for _ in range(5)]
+    ref = [err_from_oracle(ds_realization(S, d), 4) for d in draws[:2]]
+    errs = {}
+    for mode in ("factored", "dense"):
+        ctx = context_from_oracle(S, max_batch=5)
+        ctx.set_perfect_csi_mode(mode)
+        st, keep = ctx.pack_draws(draws)
+        errs[mode] = ctx.run_batch(5, 4, st)
+        for r in range(2):
+            assert np.array_equal(errs[mode][r], ref[r]), (mode, r)
+        ctx.close()
+    assert np.array_equal(errs["dense"], errs["factored"])
