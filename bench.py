@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="realizations per step per GPU")
     ap.add_argument("--schemes", default="aux,cod,ofdm")
     ap.add_argument("--no-ofdm-only", action="store_true", help="skip the extra OFDM-chain-only measurement")
+    ap.add_argument("--no-dense-leg", action="store_true", help="skip the extra leg with D materialised (K2 rooflines)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="realizations timed for cpu_baseline (about 13 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -92,6 +93,52 @@ def cpu_realizations_per_s(n_sample, schemes, faithful=False):
     for d in draws[:n_sample]:
         ds_realization(S, d, faithful=faithful)
     return n_sample / (time.perf_counter() - t)
+
+
+def dense_mode_line(torch, Simulation, schemes, device, B, K, W, I, peak_dmma, hbm_peak, hbm_src):
+    """Same workload, perfect-CSI pass in dense mode (chest_set_perfect_csi_mode(DENSE)): K2 on the timed path."""
+    sim = Simulation(schemes=tuple(schemes), max_batch=B, device=device, seed=1234)
+    ctx = sim.ctx
+    ctx.set_perfect_csi_mode("dense")
+    ctx.set_profiling(True)
+    err_dev = torch.zeros(B * len(sim.Pn) * (I + 1) * 12, dtype=torch.int32, device="cuda")
+    step = [0]
+
+    def run():
+        ctx.run_batch_device(B, I, None, seed=sim.seed, first_rep=step[0] * B, err_dev_ptr=err_dev.data_ptr())
+        step[0] += 1
+    for _ in range(W):
+        run()
+    torch.cuda.synchronize()
+    ctx.event_record(0)
+    kern, hg_ms, hg_bytes = {}, 0.0, 0.0
+    for _ in range(K):
+        run()
+        for k, v in ctx.kernel_times().items():
+            kern[k] = kern.get(k, 0.0) + v
+        a, b = ctx.banded_apply_stats()
+        hg_ms, hg_bytes = hg_ms + a, hg_bytes + b
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    wm = ctx.work_model(I)
+    k2_ms = kern["k_gemm_d"] / K
+    ic_ms = kern["k_ic_main"] / (K * I)
+    ic_flops = B * (wm["est_main_flops"] + wm["perf_flops"]) / I
+    line = {"value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+            "kernel_ms_per_step": {k: v / K for k, v in kern.items()},
+            "roofline_k_ic_main": {"bound": "tensor", "achieved": ic_flops / (ic_ms * 1e-3) / 1e12, "peak": peak_dmma,
+                                   "unit": "TFLOP/s", "frac": ic_flops / (ic_ms * 1e-3) / 1e12 / peak_dmma,
+                                   "avg_launch_ms": ic_ms},
+            "roofline_k2": {"kernel": "k_gemm_d (D = Q^H H G, persistent, support-aware)", "bound": "tensor",
+                            "achieved": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12, "peak": peak_dmma, "unit": "TFLOP/s",
+                            "frac": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12 / peak_dmma,
+                            "algorithmic_flops_per_launch": B * wm["k2_flops"], "avg_launch_ms": k2_ms},
+            "roofline_k1": {"kernel": "k_apply_hg (banded, never-materialised H applied to G)", "bound": "hbm",
+                            "achieved": hg_bytes / (hg_ms * 1e-3) / 1e9 if hg_ms > 0 else None, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": hg_bytes / (hg_ms * 1e-3) / 1e9 / hbm_peak if hg_ms > 0 else None,
+                            "peak_source": hbm_src, "algorithmic_bytes_per_step": hg_bytes / K, "ms_per_step": hg_ms / K}}
+    sim.close()
+    return line
 
 
 def ofdm_only_line(torch, Simulation, device, K, W, cpu_sample):
@@ -276,8 +323,8 @@ def run_b200(args):
     if rank == 0:
         wm = ctx.work_model(I)
         ic_ms = kern_sum["k_ic_main"] / (K * I)                            # average duration of one k_ic_main launch
-        ic_flops = B * (wm["est_main_flops"] + wm["perf_flops"]) / I       # algorithmic flops of one launch
-        k2_ms = kern_sum["k_gemm_d"] / K                                   # both waveforms' k_gemm_d launches of a step
+        ic_flops = B * wm["est_main_flops"] / I                            # algorithmic flops of one launch (estimated-CSI units)
+        chain_ms = kern_sum["perfect_csi_chain"] / (K * I)                 # G v, H, Q^H of one iteration, both waveforms
         nb = ctx.bit_counts()
         ber40 = {name: float(tot[-1, -1, sid * 4].item()) / float(nb[sid, 0] * B * world)
                  for name, sid in chest_b200.context.SCHEME_ID.items() if name in sim.sch}
@@ -300,8 +347,9 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "schemes": schemes, "realizations_per_step_per_gpu": B,
                        "parallelism": "realizations sharded over %d GPU(s), no data-path collective" % world,
-                       "l2": "inputs larger than L2 (per step %.1f GB of D matrices + %.2f GB of MMSE tiles vs 126 MB L2)"
-                             % (B * (720 * 720 + 336 * 336) * 16 / 1e9, wm["w_bytes_per_ic_launch"] / 1e9),
+                       "l2": "working set larger than L2 (per IC launch %.2f GB of MMSE tiles + %.1f GB of per-unit v / y_ic "
+                             "columns vs 126 MB L2)" % (wm["w_bytes_per_ic_launch"] / 1e9, ctx.n_units() * 2 * 720 * 16 * 16 / 1e9),
+                       "perfect_csi_mode": "factored (D never formed); dense_d_mode holds the leg with D materialised",
                        "timing": "CUDA events on the library's stream around all K steps; max over ranks",
                        "seed": sim.seed},
             "e2e": {"value": world * B * K / (e2e_wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -311,7 +359,7 @@ def run_b200(args):
                            "step, uploaded under the previous step's kernels), error counts out"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_ic_main (one persistent launch per IC iteration: W_off(hP) v and (D - diag h) v on FP64 DMMA)",
+            "roofline": {"kernel": "k_ic_main (one persistent launch per IC iteration: y - W_off(hP) v of every (scheme, SNR, realization) on FP64 DMMA)",
                          "bound": "tensor", "achieved": ic_flops / (ic_ms * 1e-3) / 1e12, "peak": peak_dmma,
                          "unit": "TFLOP/s", "frac": ic_flops / (ic_ms * 1e-3) / 1e12 / peak_dmma, "traffic": traffic,
                          "traffic_note": traffic_note,
@@ -322,19 +370,25 @@ def run_b200(args):
                          "flops_note": "algorithmic flops: 8 per complex multiply-add (SURVEY.md 8d); the kernel executes "
                                        "the three-multiplication form (6 per complex multiply-add), so the tensor-pipe "
                                        "busy fraction (ncu, profiles/r01_kic_main_summary.txt) is lower than frac"},
-            "roofline_k2": {"kernel": "k_gemm_d (D = Q^H H G, persistent, support-aware)", "bound": "tensor",
-                            "achieved": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12, "peak": peak_dmma, "unit": "TFLOP/s",
-                            "frac": B * wm["k2_flops"] / (k2_ms * 1e-3) / 1e12 / peak_dmma,
-                            "algorithmic_flops_per_launch": B * wm["k2_flops"], "avg_launch_ms": k2_ms},
-            "roofline_k1": {"kernel": "k_apply_hg (banded, never-materialised H applied to G)", "bound": "hbm",
-                            "achieved": hg_bytes / (hg_ms * 1e-3) / 1e9 if hg_ms > 0 else None, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": hg_bytes / (hg_ms * 1e-3) / 1e9 / hbm_peak if hg_ms > 0 else None,
-                            "peak_source": hbm_src, "algorithmic_bytes_per_step": hg_bytes / K, "ms_per_step": hg_ms / K},
+            "roofline_perfect_csi": {"kernel": "k_gemm<PLAIN> x2 + k_apply_h_cols (perfect-CSI pass, factored: y - Q^H H (G v) + h v)",
+                                     "bound": "tensor", "achieved": B * wm["factored_perf_flops"] / I / (chain_ms * 1e-3) / 1e12,
+                                     "peak": peak_dmma, "unit": "TFLOP/s",
+                                     "frac": B * wm["factored_perf_flops"] / I / (chain_ms * 1e-3) / 1e12 / peak_dmma,
+                                     "algorithmic_flops_per_iteration": B * wm["factored_perf_flops"] / I,
+                                     "avg_iteration_ms": chain_ms},
             "stage_ms_per_step": {k: v / K for k, v in stage_sum.items()},
             "kernel_ms_per_step": {k: v / K for k, v in kern_sum.items()},
             "wall_ms_per_step": wall_ms / K, "launches_per_step": launches_per_step, "setup_s": setup_s,
             "sanity_ber_40dB_last_iteration": ber40,
         }
+        if world == 1 and not args.no_dense_leg:
+            # the same workload with D = Q^H H G materialised per realization (K2) and applied densely: the rooflines
+            # of k_gemm_d (FP64 tensor) and k_apply_hg (HBM) come from this leg; never fatal for the main line
+            try:
+                out["dense_d_mode"] = dense_mode_line(torch, DoublySelectiveSimulation, schemes, local, B, K, W, I,
+                                                      peak_dmma, hbm_peak, hbm_src)
+            except Exception as e:                              # noqa: BLE001
+                out["dense_d_mode"] = {"error": repr(e)[:200]}
         if world == 1 and set(schemes) != {"ofdm"} and not args.no_ofdm_only:
             # the same loop body with the OFDM chain alone (the narrow reading of "default params: OFDM"), for
             # comparison: resident value only, same timing rules; never fatal for the main line

@@ -290,21 +290,29 @@ class DeviceContext:
         self._check(self.lib.chest_event_elapsed(self._h, a, b, C.byref(ms)))
         return float(ms.value)
 
+    def n_units(self):
+        """IC work units of the current batch size (3392 at the default configuration, B = 1024)."""
+        n = C.c_int(0)
+        self._check(self.lib.chest_unit_count(self._h, C.byref(n)))
+        return n.value
+
     def set_perfect_csi_mode(self, mode):
         """'factored' (default): D never formed; 'dense': D = Q^H H G materialised per realization (K2)."""
         self._check(self.lib.chest_set_perfect_csi_mode(self._h, {"dense": 0, "factored": 1}[mode]))
 
     def kernel_times(self):
         """Device ms of k_apply_hg, k_gemm_d, k_ic_main (sum), k_ic_light (sum) in the last profiled batch."""
-        out = (C.c_float * 4)()
+        out = (C.c_float * 6)()
         self._check(self.lib.chest_kernel_times(self._h, out))
-        return dict(k_apply_hg=out[0], k_gemm_d=out[1], k_ic_main=out[2], k_ic_light=out[3])
+        return dict(k_apply_hg=out[0], k_gemm_d=out[1], k_ic_main=out[2], k_ic_light=out[3],
+                    perfect_csi_chain=out[4], diag_d_gemm=out[5])
 
     def work_model(self, n_iter):
         out = (C.c_double * 8)()
         self._check(self.lib.chest_work_model(self._h, n_iter, out))
         return dict(k2_flops=out[0], est_flops=out[1], perf_flops=out[2], txdemod_flops=out[3],
-                    w_bytes_per_ic_launch=out[4], precode_flops=out[5], est_main_flops=out[6])
+                    w_bytes_per_ic_launch=out[4], precode_flops=out[5], est_main_flops=out[6],
+                    factored_perf_flops=out[7])
 
     def fp64_peak(self, mode="dmma", iters=20000):
         t = C.c_double(0)

@@ -143,8 +143,9 @@ struct Ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_hg[4] = {};   // k_apply_hg of the two waveforms (profiling)
     cudaEvent_t ev_gd[2] = {};   // end of k_gemm_d of the two waveforms
-    cudaEvent_t ev_ic[36] = {};  // after every k_ic_main / k_ic_light launch
-    float kernel_ms[4] = {0, 0, 0, 0};   // k_apply_hg, k_gemm_d, k_ic_main, k_ic_light of the last profiled batch
+    cudaEvent_t ev_ic[36] = {};  // after every k_ic_main (+ factored chain) / k_ic_light launch
+    cudaEvent_t ev_mn[18] = {};  // after k_ic_main alone (before the factored perfect-CSI chain)
+    float kernel_ms[6] = {0, 0, 0, 0, 0, 0};   // k_apply_hg, k_gemm_d, k_ic_main, k_ic_light, factored perfect-CSI chain, diag(D) GEMM
     float hg_ms = 0; double hg_bytes = 0;
     cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -573,6 +574,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
             main_kernel<<<std::min(c->ic_grid, std::max(c->n_est_units, 1)), ic_threads, main_smem, st>>>(ip);
             c->launches++;
             ip.trace = nullptr;
+            if (c->profiling) CK(cudaEventRecord(c->ev_mn[it], st));
             if (c->perf_mode == 1) { rc = stage_factored_perfect_csi(c, n_rep); if (rc) return rc; }
             if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
         }
@@ -596,14 +598,18 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&c->stage_ms[6], c->ev[0], c->ev[6]);
         // per-kernel times: events after every IC launch (main of iteration it: 2 it, light: 2 it + 1; ev[4] precedes)
-        c->kernel_ms[2] = c->kernel_ms[3] = 0;
+        c->kernel_ms[2] = c->kernel_ms[3] = c->kernel_ms[4] = 0;
         for (int it = 0; it <= n_iter; ++it) {
             float t = 0;
-            if (it > 0) { cudaEventElapsedTime(&t, c->ev_ic[2 * it - 1], c->ev_ic[2 * it]); c->kernel_ms[2] += t; }
+            if (it > 0) {
+                cudaEventElapsedTime(&t, c->ev_ic[2 * it - 1], c->ev_mn[it]); c->kernel_ms[2] += t;
+                cudaEventElapsedTime(&t, c->ev_mn[it], c->ev_ic[2 * it]); c->kernel_ms[4] += t;
+            }
             cudaEventElapsedTime(&t, it > 0 ? c->ev_ic[2 * it] : c->ev[4], c->ev_ic[2 * it + 1]);
             c->kernel_ms[3] += t;
         }
         c->kernel_ms[0] = c->kernel_ms[1] = 0;
+        c->kernel_ms[5] = c->perf_mode == 1 ? c->stage_ms[2] : 0;              // factored mode: stage 2 is the diag(D) GEMM
         if (n_rep > 1 && c->perf_mode != 1)
             for (int wfi = 0; wfi < 2; ++wfi)
                 if (c->wf[wfi].set && c->wf[wfi].nsch) {
@@ -663,6 +669,7 @@ int chest_create(int device, uint64_t* handle) {
     for (auto& e : c->ev_hg) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_gd) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_ic) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_mn) CK(cudaEventCreate(&e));
     *handle = (uint64_t)(uintptr_t)c;
     return CHEST_OK;
 }
@@ -698,6 +705,7 @@ int chest_destroy(uint64_t handle) {
     for (auto& e : c->ev_hg) cudaEventDestroy(e);
     for (auto& e : c->ev_gd) cudaEventDestroy(e);
     for (auto& e : c->ev_ic) cudaEventDestroy(e);
+    for (auto& e : c->ev_mn) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     for (auto& q : c->pf) {
@@ -1520,11 +1528,18 @@ int chest_set_perfect_csi_mode(uint64_t handle, int mode) {
     return CHEST_OK;
 }
 
+int chest_unit_count(uint64_t handle, int* n_units) {
+    Ctx* c = from(handle);
+    ARG(c && n_units);
+    *n_units = c->n_ctas;
+    return CHEST_OK;
+}
+
 int chest_kernel_times(uint64_t handle, float* ms) {
     Ctx* c = from(handle);
     ARG(c && ms);
     c->kernel_ms[0] = c->hg_ms;
-    for (int i = 0; i < 4; ++i) ms[i] = c->kernel_ms[i];
+    for (int i = 0; i < 6; ++i) ms[i] = c->kernel_ms[i];
     return CHEST_OK;
 }
 
@@ -1545,6 +1560,8 @@ int chest_work_model(uint64_t handle, int n_iter, double* out) {
             out[2] += (vr ? 4.0 : 8.0) * w.d_struct_pairs * S * n_iter;
         }
         out[3] += w.nsch * (w.flops_mod + 8.0 * c->T * c->N) + w.nsch * S * w.flops_demod;   // TX + demod
+        // factored perfect CSI: per column G v, H (.), Q^H (.) over the supports, per iteration
+        out[7] += (double)w.nsch * S * n_iter * (w.flops_mod + 8.0 * c->T * c->N + w.flops_demod);
     }
     for (int si = 0; si < 3; ++si) {
         Scheme& s = c->sch[si];

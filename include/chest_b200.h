@@ -178,6 +178,8 @@ int chest_run_batch(uint64_t handle, int n_rep, int n_iter, const chest_draws* d
 #define CHEST_PERFECT_DENSE     0
 #define CHEST_PERFECT_FACTORED  1
 int chest_set_perfect_csi_mode(uint64_t handle, int mode);
+/* Work units (up to 16 columns x all K rows each) the IC kernels processed in the last batch. */
+int chest_unit_count(uint64_t handle, int* n_units);
 
 /* Same with the result left on the device: err_dev is a device pointer (used by bench `value`). */
 int chest_run_batch_device(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws,
@@ -211,12 +213,14 @@ int chest_stage_times(uint64_t handle, float* ms /* [7] */);
  * algorithmic bytes (H*G rows written + h read), for the HBM roofline of the banded path. */
 int chest_banded_apply_stats(uint64_t handle, float* ms, double* bytes);
 /* Device time (ms, CUDA events on the context's stream) of the hot kernels in the last profiled chest_run_batch:
- * [0] k_apply_hg, [1] k_gemm_d (K2), [2] k_ic_main summed over the iterations, [3] k_ic_light summed. */
-int chest_kernel_times(uint64_t handle, float* ms /* [4] */);
+ * [0] k_apply_hg, [1] k_gemm_d (K2; both zero in factored mode), [2] k_ic_main summed over the iterations,
+ * [3] k_ic_light summed, [4] the factored perfect-CSI chain summed, [5] the diag(D) GEMM. */
+int chest_kernel_times(uint64_t handle, float* ms /* [6] */);
 /* Algorithmic work of one realization for the roofline:
  * [0] K2 support-aware flops, [1] K3/K4 estimated-CSI flops per iteration-evaluation set,
  * [2] perfect-CSI flops, [3] demod/TX flops, [4] bytes of W streamed per IC kernel launch,
- * [5] precoding flops, [6] the part of [1] executed by k_ic_main (off-diagonal products). */
+ * [5] precoding flops, [6] the part of [1] executed by k_ic_main (off-diagonal products),
+ * [7] flops of the factored perfect-CSI chain (G v, H, Q^H over the supports, all iterations). */
 int chest_work_model(uint64_t handle, int n_iter, double* out /* [8] */);
 
 /* Device-timeline timing for callers that cannot see the context's stream: record event `slot`
