@@ -542,10 +542,12 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         }
         if (!((m2 == 0 && m1 == 0) || (m2 == 2 && m1 == 0) || (m2 == 3 && m1 == 1))) { m2 = 0; m1 = 0; }   // compiled combinations
     }
+    if (c->perf_mode == 1) { m2 = -1; m1 = -1; }                 // factored mode: the main kernel runs EST units only
     void (*main_kernel)(IcParams) =
-        p4s == 4 ? (m2 == 2 ? k_ic_main<4, 2, 0> : (m2 == 3 ? k_ic_main<4, 3, 1> : k_ic_main<4, 0, 0>))
-                 : (m2 == 2 ? k_ic_main<8, 2, 0> : (m2 == 3 ? k_ic_main<8, 3, 1> : k_ic_main<8, 0, 0>));
-    const int cfg_id = p4s * 100 + m2 * 10 + m1;
+        m2 < 0 ? (p4s == 4 ? k_ic_main<4, -1, -1> : k_ic_main<8, -1, -1>)
+               : p4s == 4 ? (m2 == 2 ? k_ic_main<4, 2, 0> : (m2 == 3 ? k_ic_main<4, 3, 1> : k_ic_main<4, 0, 0>))
+                          : (m2 == 2 ? k_ic_main<8, 2, 0> : (m2 == 3 ? k_ic_main<8, 3, 1> : k_ic_main<8, 0, 0>));
+    const int cfg_id = p4s * 100 + (m2 + 1) * 10 + (m1 + 1);
     if (c->ic_grid == 0 || c->ic_smem != main_smem || c->ic_cfg != cfg_id) {    // persistent main grid: one wave of resident CTAs
         c->ic_cfg = cfg_id;
         CK(cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

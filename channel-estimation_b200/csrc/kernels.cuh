@@ -799,7 +799,8 @@ __device__ __forceinline__ void ld_cplx2(const cplx* ptr, cplx& a, cplx& b) {
 //             2: this tile's fragments loaded where they are used
 //   measured (profiles/r01_kic_variant_sweep.txt): 0 is best in the mixed EST+PERF main stage
 //   EST_VPRE  1: next tile's v rows prefetched into registers
-//   EST_HPREG 1: the hP B-fragments live in registers for the whole row tile (P4 <= 4 only)
+//   EST_HPREG 1: the hP B-fragments live in registers for the whole row tile (P4 <= 4 only); always on in the
+//             EST-only kernel instance of the factored mode (template flag HPR), where they fit without spills
 #define EST_H1S 20           // row stride (doubles) of the real-part plane of the pilot estimates
 #ifndef EST_VPRE
 #define EST_VPRE 0
@@ -810,14 +811,14 @@ __device__ __forceinline__ void ld_cplx2(const cplx* ptr, cplx& a, cplx& b) {
 #ifndef EST_RING
 #define EST_RING 2
 #endif
-template <int P4T, bool VREAL>
+template <int P4T, bool VREAL, bool HPR>
 __device__ IC_INLINE void est_interference(const cplx* __restrict__ frag, const int* __restrict__ tptr,
                                                  const int* __restrict__ tdel, const cplx* hPs, const cplx* hP3, const double* hP1,
                                                  const cplx* vbuf,
                                                  cplx* ybuf, const cplx* const* ycolp, cplx* ring, int K, int warp,
                                                  int nwarp, int lane) {
     constexpr int NC = NC_MAX, HS = NC + 2, ST = EST_RING;
-    constexpr bool HPREG = EST_HPREG && P4T <= 4;
+    constexpr bool HPREG = (EST_HPREG || HPR) && P4T <= 4;
     // hP1: real parts of the pilot estimates as a plane of doubles, row stride 20 -> the 8-byte fragment loads
     // are conflict-free (the 16-byte stride of the complex table would give 2-way conflicts)
     const int g = lane >> 2, t4 = lane & 3;
@@ -1226,7 +1227,8 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
             __syncthreads();
             // the D-hat being cancelled is the one estimated in iteration it-1 (DS.m:475,492)
             const int var_prev = (it - 1 == 0 || (it - 1) <= p.n_iter / 2) ? 0 : 1;
-#define EST_CALL(P4T_, VR_) est_interference<P4T_, VR_>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], \
+            // the EST-only instance (factored mode) has the registers to keep the pilot operands resident
+#define EST_CALL(P4T_, VR_) est_interference<P4T_, VR_, (M2 < 0)>(sd.w[var_prev][cta.snr].frag, sd.tile_ptr[var_prev], sd.tile_delta[var_prev], \
                                                         hPs, hP3, hP1, vbuf, ybuf, sh.ycolp, ring, K, warp, nwarp, lane)
             if (sd.P4 == P4S) { if (sd.v_real) EST_CALL(P4S, true); else EST_CALL(P4S, false); }
             else
@@ -1237,8 +1239,9 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
             // each 8-column half is on one scheme: real v of a half -> two DMMAs per product instead of three
             // (the masks M2 / M1 hold for every unit of this configuration, see the host)
 #define PERF_CALL(NCT_, MASK_) perf_interference<NCT_, MASK_>(Dm, vbuf, ybuf, sh.ycolp, vstage, p.d_jlo[wf], p.d_jhi[wf], K, warp, nwarp, lane, tid)
-            if (cta.n_cols <= 8) PERF_CALL(1, M1);
-            else PERF_CALL(2, M2);
+            if (M2 < 0) {}                                     // EST-only instance (factored mode): no perfect-CSI bodies
+            else if (cta.n_cols <= 8) PERF_CALL(1, (M1 < 0 ? 0 : M1));
+            else PERF_CALL(2, (M2 < 0 ? 0 : M2));
 #undef PERF_CALL
         }
     }
