@@ -55,7 +55,7 @@ struct Waveform {
     DevBuf<cplx> Q1; DevBuf<double> Q2;                // three-multiplication planes of Q^H: (re, re - im), im; row stride Np
     DevBuf<cplx> HG1; DevBuf<double> HG2;              // H*G planes: (re, re + im), im - re; [rep][K][Np]
     DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi, d_jlo, d_jhi;
-    DevBuf<int> q8_klo, q8_khi, hg8_klo, hg8_khi;
+    DevBuf<int> q8_klo, q8_khi, hg8_klo, hg8_khi, gt8_klo, gt8_khi;
     DevBuf<int2> pairs; int n_pairs = 0;               // (row tile, column tile) pairs of D with overlapping supports      // per 8 columns of Q / of H*G (warp-level clipping in K2 / K3a)
     double d_struct_pairs = 0;   // (i,j) pairs of D inside the structural support
     std::vector<int> g_lo, g_hi, q_lo, q_hi;
@@ -303,6 +303,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep) {
         GemmParams p{};
         p.M = N; p.Kc = w.K; p.n_cols = w.f_cols; p.lda = w.K; p.ldc = N; p.conj_a = 0;
         p.At = w.Gt.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.out = w.f_s.p;
+        p.m8_klo = w.gt8_klo.p; p.m8_khi = w.gt8_khi.p;
         p.bsrc = c->scratch.p; p.b_off = w.f_voff.p; p.b_kstride = NC_MAX;
         CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));                                   // s = G v
         dim3 grid((N + 127) / 128, w.f_cols);
@@ -312,6 +313,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep) {
         GemmParams q{};
         q.M = w.K; q.Kc = N; q.n_cols = w.f_cols; q.lda = N; q.ldc = w.K; q.conj_a = 1;
         q.At = w.Q.p; q.mt_klo = w.q_klo.p; q.mt_khi = w.q_khi.p; q.out = w.f_s.p;
+        q.m8_klo = w.q8_klo.p; q.m8_khi = w.q8_khi.p;
         q.bsrc = w.f_r.p; q.ldb = N;
         q.e_out = c->scratch.p + (size_t)c->K_max * NC_MAX; q.e_off = w.f_voff.p;       // y_ic sits one buffer behind v
         q.e_y = w.y.p; q.e_yoff = w.f_yoff.p; q.e_h = w.htrue.p; q.e_rep = w.f_rep.p;
@@ -684,7 +686,7 @@ int chest_destroy(uint64_t handle) {
     // DevBuf has no destructor on purpose (plain members); release explicitly
     auto relw = [](Waveform& w) {
         w.G.release(); w.Q.release(); w.Gt.release(); w.q_klo.release(); w.q_khi.release(); w.gt_klo.release();
-        w.gt_khi.release(); w.q8_klo.release(); w.q8_khi.release(); w.hg8_klo.release(); w.hg8_khi.release(); w.pairs.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
+        w.gt_khi.release(); w.q8_klo.release(); w.q8_khi.release(); w.hg8_klo.release(); w.hg8_khi.release(); w.gt8_klo.release(); w.gt8_khi.release(); w.pairs.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
         w.y.release(); w.D.release(); w.htrue.release(); w.HG1.release(); w.HG2.release(); w.Q1.release(); w.Q2.release();
     };
     relw(c->wf[0]); relw(c->wf[1]);
@@ -801,6 +803,8 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
         for (int n = w.g_lo[j]; n < w.g_hi[j]; ++n) { rlo[n] = std::min(rlo[n], j); rhi[n] = std::max(rhi[n], j + 1); }
     tile_ranges(rlo, rhi, w.tile, 0, K, lo, hi);
     CK(w.gt_klo.upload(lo, c->stream)); CK(w.gt_khi.upload(hi, c->stream));
+    tile_ranges(rlo, rhi, 8, 0, K, lo, hi);
+    CK(w.gt8_klo.upload(lo, c->stream)); CK(w.gt8_khi.upload(hi, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     w.set = true; c->finalized = false;
     return CHEST_OK;
