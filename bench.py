@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="realizations per step per GPU")
+    ap.add_argument("--batch", type=int, default=4096, help="realizations per step per GPU")
     ap.add_argument("--schemes", default="aux,cod,ofdm")
     ap.add_argument("--no-ofdm-only", action="store_true", help="skip the extra OFDM-chain-only measurement")
     ap.add_argument("--no-dense-leg", action="store_true", help="skip the extra leg with D materialised (K2 rooflines)")
@@ -124,7 +124,7 @@ def dense_mode_line(torch, Simulation, schemes, device, B, K, W, I, peak_dmma, h
     k2_ms = kern["k_gemm_d"] / K
     ic_ms = kern["k_ic_main"] / (K * I)
     ic_flops = B * (wm["est_main_flops"] + wm["perf_flops"]) / I
-    line = {"value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+    line = {"value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "realizations_per_step": B,
             "kernel_ms_per_step": {k: v / K for k, v in kern.items()},
             "roofline_k_ic_main": {"bound": "tensor", "achieved": ic_flops / (ic_ms * 1e-3) / 1e12, "peak": peak_dmma,
                                    "unit": "TFLOP/s", "frac": ic_flops / (ic_ms * 1e-3) / 1e12 / peak_dmma,
@@ -367,9 +367,11 @@ def run_b200(args):
                                         "(chest_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; DFMA probe %.1f TFLOP/s"
                                         % peak_dfma,
                          "algorithmic_flops_per_launch": ic_flops, "avg_launch_ms": ic_ms,
+                         "frac_executed": 0.75 * ic_flops / (ic_ms * 1e-3) / 1e12 / peak_dmma,
                          "flops_note": "algorithmic flops: 8 per complex multiply-add (SURVEY.md 8d); the kernel executes "
-                                       "the three-multiplication form (6 per complex multiply-add), so the tensor-pipe "
-                                       "busy fraction (ncu, profiles/r01_kic_main_summary.txt) is lower than frac"},
+                                       "the three-multiplication form (6 per complex multiply-add): frac can exceed 1, "
+                                       "frac_executed = 0.75 frac is the share of the DMMA peak the executed products take "
+                                       "(ncu pipe-busy fraction: profiles/r01_kic_main_summary.txt)"},
             "roofline_perfect_csi": {"kernel": "k_gemm<PLAIN> x2 + k_apply_h_cols (perfect-CSI pass, factored: y - Q^H H (G v) + h v)",
                                      "bound": "tensor", "achieved": B * wm["factored_perf_flops"] / I / (chain_ms * 1e-3) / 1e12,
                                      "peak": peak_dmma, "unit": "TFLOP/s",
@@ -385,7 +387,7 @@ def run_b200(args):
             # the same workload with D = Q^H H G materialised per realization (K2) and applied densely: the rooflines
             # of k_gemm_d (FP64 tensor) and k_apply_hg (HBM) come from this leg; never fatal for the main line
             try:
-                out["dense_d_mode"] = dense_mode_line(torch, DoublySelectiveSimulation, schemes, local, B, K, W, I,
+                out["dense_d_mode"] = dense_mode_line(torch, DoublySelectiveSimulation, schemes, local, min(B, 1024), K, W, I,
                                                       peak_dmma, hbm_peak, hbm_src)
             except Exception as e:                              # noqa: BLE001
                 out["dense_d_mode"] = {"error": repr(e)[:200]}

@@ -69,6 +69,7 @@ struct Waveform {
     std::vector<cplx> Gh, Qh;                           // host copies of G, Q (finalize builds Pd from them)
     DevBuf<int64_t> f_voff, f_yoff; DevBuf<int> f_rep; DevBuf<cplx> f_s, f_r;
     int f_cols = 0, perf_base = 0, perf_nblk = 0;
+    int d_alloc_batch = 0;      // batch size D / HG1 / HG2 are allocated for (0: not yet)
     int tile = 64;              // CTA tile size of the GEMMs on this waveform (48 or 64)
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
 };
@@ -269,8 +270,24 @@ int stage_channel(Ctx* c, int n_rep, const double* du, const double* pu) {
     return CHEST_OK;
 }
 
+// D (row-tile-major) and the H*G operand planes for the whole batch; allocated by the first call that needs them
+// (dense mode, chest_transmission_matrix) -- the factored loop body never does.
+int ensure_d_buffers(Ctx* c, Waveform& w) {
+    const int B = c->max_batch, N = c->N;
+    if (w.d_alloc_batch == B) return CHEST_OK;
+    const size_t n_d = (size_t)B * (((w.K + 7) / 8) * 8) * w.K, n_hg = (size_t)B * w.K * ((N + 1) & ~1);
+    CK(w.D.alloc(n_d)); CK(w.HG1.alloc(n_hg)); CK(w.HG2.alloc(n_hg));
+    // tiles of D without support overlap are never written by K2: they stay at this zero
+    CK(cudaMemsetAsync(w.D.p, 0, n_d * sizeof(cplx), c->stream));
+    CK(cudaMemsetAsync(w.HG1.p, 0, n_hg * sizeof(cplx), c->stream));          // pad element of odd N stays zero
+    CK(cudaMemsetAsync(w.HG2.p, 0, n_hg * sizeof(double), c->stream));
+    w.d_alloc_batch = B;
+    return CHEST_OK;
+}
+
 int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
     Waveform& w = c->wf[wfi];
+    { int rc_ = ensure_d_buffers(c, w); if (rc_) return rc_; }
     GemmDParams p{};
     const int Np = (c->N + 1) & ~1;                                 // even row stride of the operand planes
     p.M = w.K; p.n_cols = w.K; p.lda = Np; p.ldb = Np; p.n_rep = n_rep; p.rep0 = rep0;
@@ -1153,15 +1170,9 @@ int chest_finalize(uint64_t handle, int max_batch) {
         c->K_max = std::max(c->K_max, w.K);
         int ns = std::max(w.nsch, 1);
         CK(w.x.alloc((size_t)ns * B * w.K)); CK(w.s.alloc((size_t)ns * B * N)); CK(w.r0.alloc((size_t)ns * B * N));
-        CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.D.alloc((size_t)B * (((w.K + 7) / 8) * 8) * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
-        // tiles of D without support overlap are never written by K2: they stay at this zero
-        CK(cudaMemsetAsync(w.D.p, 0, sizeof(cplx) * (size_t)B * (((w.K + 7) / 8) * 8) * w.K, c->stream));
-        {
-            const size_t n_hg = (size_t)B * w.K * ((N + 1) & ~1);
-            CK(w.HG1.alloc(n_hg)); CK(w.HG2.alloc(n_hg));
-            CK(cudaMemsetAsync(w.HG1.p, 0, n_hg * sizeof(cplx), c->stream));      // pad element of odd N stays zero
-            CK(cudaMemsetAsync(w.HG2.p, 0, n_hg * sizeof(double), c->stream));
-        }
+        CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
+        // D and the H*G planes (dense mode, chest_transmission_matrix) are allocated on first use: ensure_d_buffers
+        w.d_alloc_batch = 0;
         if (w.nsch) CK(c->pilot_idx[wfi].alloc((size_t)B * c->sch[w.sch[0]].P));
     }
     CK(c->doppler_u.alloc((size_t)B * c->T * c->paths)); CK(c->phase_u.alloc((size_t)B * c->T * c->paths));
