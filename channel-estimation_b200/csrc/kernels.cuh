@@ -1254,7 +1254,9 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
 #ifndef IC_LIGHT_WAVES
 #define IC_LIGHT_WAVES 64      // grid of the light kernel in units of one resident wave (i.e. one CTA per unit)
 #endif
+#ifndef IC_LIGHT_THREADS
 #define IC_LIGHT_THREADS 256
+#endif
 // Hard decision of one data-symbol estimate: bit errors against the transmitted word, and the decided word
 // (the quantised symbol of the next iteration's cancellation, DS.m:482-484).
 __device__ __forceinline__ int ic_decide(const ConstDev& cd, cplx xd, uint32_t tw, uint32_t em, unsigned& e_all, unsigned& e_edge) {
