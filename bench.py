@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-dense-leg", action="store_true", help="skip the extra leg with D materialised (K2 rooflines)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="realizations timed for cpu_baseline (about 13 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-sample", action="store_true", help="skip the oracle check of sampled realizations")
     return ap.parse_args()
 
 
@@ -177,11 +178,41 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_cores():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core it
+    can (the launcher's setting would halve its value and inflate the ratio).  Returns the BLAS thread count in use."""
+    import numpy as np  # noqa: F401  (loads BLAS so that threadpoolctl sees it)
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return blas_threads()
+
+
+def parity_sample(schemes, seed, first, err_batch, n_iter, reps):
+    """The checker, not the thing measured: realizations `reps` of the batch that the timed region processed last
+    (counter-based draws keyed by (seed, first + r)) are re-run by the CPU oracle with ITS OWN setup; the GPU's error
+    counts -- produced by the product's setup and kernels -- must equal the oracle's."""
+    import numpy as np
+    from oracle.ds import DSConfig, ds_setup, ds_realization
+    from oracle import rng as orng
+    from tests.helpers import err_from_oracle
+    S = ds_setup(DSConfig(schemes=tuple(schemes), NrIterations=n_iter))
+    bad = []
+    for r in reps:
+        ref = err_from_oracle(ds_realization(S, orng.draws_for(S, seed, first + r)), n_iter)
+        if not np.array_equal(err_batch[r], ref):
+            bad.append(int(first + r))
+    return "ok" if not bad else "MISMATCH at realizations %s" % bad
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np  # noqa: F401  (loads BLAS so that threadpool_info sees it)
+    cores = use_all_host_cores()
     schemes = args.schemes.split(",")
     n = max(1, args.cpu_sample // 4)                      # a bounded sample per step: ~3 s of CPU work
     vals = []
@@ -191,7 +222,6 @@ def run_reference(args):
     for _ in range(args.steps):
         vals.append(cpu_realizations_per_s(n, schemes))
     value = float(sum(vals) / len(vals))
-    cores = blas_threads()
     sample = ("oracle port (NumPy/OpenBLAS restatement of DS.m:350-565, support-aware D-hat as a GEMV; NOT MATLAB), "
               "%d realizations per step, %d steps" % (n, args.steps))
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -200,7 +230,8 @@ def run_reference(args):
            "config": {"workload": WORKLOAD, "schemes": schemes, "realizations_per_step": n},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "wall_s": time.perf_counter() - t0}
+           "wall_s": time.perf_counter() - t0, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+           "host_cores": os.cpu_count()}
     print(json.dumps(out), flush=True)
 
 
@@ -222,6 +253,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     schemes = args.schemes.split(",")
     B, K, W, I = args.batch, args.steps, args.warmup, 4
+    parity_failed = False
     t0 = time.perf_counter()
     sim = DoublySelectiveSimulation(schemes=tuple(schemes), max_batch=B, device=local, seed=1234)
     setup_s = time.perf_counter() - t0
@@ -271,6 +303,8 @@ def run_b200(args):
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     launches = ctx.launch_count() - launches0
     clk = clocks.stop()
+    last_first = ((step_id[0] - 1) * world + rank) * B           # first realization index of the last timed batch
+    err_last = err_dev.view(B, n_snr, I + 1, 3, 2, 2).cpu().numpy().astype(np.uint32)
 
     # ---- end-to-end leg: host draws (pinned) -> device, counts -> host, every step
     ctx.generate_draws(B, sim.seed, 10 ** 9)
@@ -399,6 +433,12 @@ def run_b200(args):
                                                         None if args.no_cpu_baseline else args.cpu_sample)
             except Exception as e:                              # noqa: BLE001
                 out["ofdm_chain_only"] = {"error": repr(e)[:200]}
+        if not args.no_parity_sample:
+            use_all_host_cores()
+            reps = sorted({0, 17, B // 2 + 1, B - 1})
+            out["parity_sample"] = parity_sample(schemes, sim.seed, last_first, err_last, I, reps)
+            out["parity_sample_note"] = ("GPU error counts of realizations %s of the last timed batch (seed %d, first index %d) "
+                                         "equal the CPU oracle's (own setup, same counter-based draws)" % (reps, sim.seed, last_first))
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_sample
             v = cpu_realizations_per_s(n, schemes)
@@ -411,10 +451,15 @@ def run_b200(args):
                 "reference_faithful_note": "same port with the reference's own formulation (dense Q'HG, full()+bsxfun "
                                            "D-hat, DS.m:388-389,417-425), 1 realization"}
         print(json.dumps(out), flush=True)
+        if str(out.get("parity_sample", "ok")).startswith("MISMATCH"):
+            sys.stderr.write("bench.py: parity sample failed: %s\n" % out["parity_sample"])
+            parity_failed = True
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     sim.close()
+    if parity_failed:
+        raise SystemExit(3)
 
 
 def _one_json_line_stdout():

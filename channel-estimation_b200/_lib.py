@@ -50,6 +50,11 @@ SIGNATURES = {
     "chest_draws_bytes": (c_i64, [c_u64, c_int]),
     "chest_run_batch": (c_int, [c_u64, c_int, c_int, C.POINTER(ChestDraws), c_u64, c_i64, vp]),
     "chest_run_batch_device": (c_int, [c_u64, c_int, c_int, C.POINTER(ChestDraws), c_u64, c_i64, vp]),
+    "chest_run_batch_async": (c_int, [c_u64, c_int, c_int, C.POINTER(ChestDraws), c_u64, c_i64]),
+    "chest_wait": (c_int, [c_u64, vp]),
+    "chest_multi_create": (c_int, [C.POINTER(c_u64), c_int, C.POINTER(c_u64)]),
+    "chest_multi_run": (c_int, [c_u64, c_i64, c_int, c_u64, c_i64, vp, vp, p_f]),
+    "chest_multi_destroy": (c_int, [c_u64]),
     "chest_bit_counts": (c_int, [c_u64, p_i64]),
     "chest_generate_draws": (c_int, [c_u64, c_int, c_u64, c_i64, C.POINTER(ChestDraws)]),
     "chest_download_draws": (c_int, [c_u64, c_int, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -213,6 +213,17 @@ class DeviceContext:
         dptr = C.byref(draws) if draws is not None else None
         self._check(self.lib.chest_run_batch_device(self._h, n_rep, n_iter, dptr, seed, first_rep, err_dev_ptr))
 
+    def run_batch_async(self, n_rep, n_iter, draws=None, seed=0, first_rep=0):
+        """Enqueue the loop body and return; `wait()` collects the counts (one host thread, several contexts)."""
+        dptr = C.byref(draws) if draws is not None else None
+        self._check(self.lib.chest_run_batch_async(self._h, n_rep, n_iter, dptr, seed, first_rep))
+        self._pending_shape = (n_rep, self.n_snr, n_iter + 1, 3, 2, 2)
+
+    def wait(self):
+        err = np.zeros(self._pending_shape, dtype=np.uint32)
+        self._check(self.lib.chest_wait(self._h, _ptr(err)))
+        return err
+
     def prefetch_draws(self, n_rep, host_draws):
         """Start the asynchronous upload of host draws; returns the device-side ChestDraws to pass to run_batch*."""
         dev = _lib.ChestDraws()
@@ -318,3 +329,37 @@ class DeviceContext:
         t = C.c_double(0)
         self._check(self.lib.chest_fp64_peak(self._h, {"dmma": 0, "dfma": 1, "mix": 2}[mode], iters, C.byref(t)))
         return t.value
+
+
+class MultiDevice:
+    """chest_multi_*: one host thread driving one finalized, identically configured context per GPU."""
+
+    def __init__(self, contexts):
+        self.ctxs = list(contexts)
+        self.lib = self.ctxs[0].lib
+        hs = (C.c_uint64 * len(self.ctxs))(*[c._h.value for c in self.ctxs])
+        m = C.c_uint64(0)
+        self._m = None
+        self.ctxs[0]._check(self.lib.chest_multi_create(hs, len(self.ctxs), C.byref(m)))
+        self._m = m
+
+    def run(self, n_rep_total, n_iter, seed=0, first_rep=0, want_err=True):
+        """Returns (err[rep, snr, it, scheme, csi, edge] or None, totals[snr, it, scheme, csi, edge] uint64,
+        device ms of the final NCCL all-reduce)."""
+        c0 = self.ctxs[0]
+        err = np.zeros((n_rep_total, c0.n_snr, n_iter + 1, 3, 2, 2), dtype=np.uint32) if want_err else None
+        tot = np.zeros((c0.n_snr, n_iter + 1, 3, 2, 2), dtype=np.uint64)
+        ms = C.c_float(0)
+        c0._check(self.lib.chest_multi_run(self._m, n_rep_total, n_iter, seed, first_rep, _ptr(err), _ptr(tot), C.byref(ms)))
+        return err, tot, float(ms.value)
+
+    def close(self):
+        if self._m is not None:
+            self.lib.chest_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

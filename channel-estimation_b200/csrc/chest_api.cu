@@ -4,6 +4,9 @@
 #include "../../include/chest_b200.h"
 #include "kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -28,9 +31,17 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 namespace {
 
+// Owning device buffer: move-only, freed by its destructor (so every DevBuf member of Ctx / Waveform / Scheme is
+// released by `delete ctx` -- nothing to list by hand, nothing to forget).
 template <class T>
 struct DevBuf {
     T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
     cudaError_t alloc(size_t count) {
         if (count <= n && p) return cudaSuccess;
         if (p) cudaFree(p);
@@ -153,6 +164,10 @@ struct Ctx {
     DevBuf<double> probe;
     DevBuf<unsigned int> queue; int ic_grid = 0, ic_light_grid = 0, ic_cfg = -1; size_t ic_smem = 0;
     DevBuf<unsigned long long> trace;
+    // asynchronous runs (chest_run_batch_async / chest_wait): pinned host copy of the counters, pending-run state
+    uint32_t* err_pinned = nullptr; size_t err_pinned_n = 0;
+    bool pending = false; size_t pending_n_err = 0; bool trace_on = false; int pending_iter = 0, pending_rep = 0;
+    DevBuf<unsigned long long> totals;    // [snr][it][12] sums over realizations (chest_multi_run)
 };
 
 Ctx* from(uint64_t h) { return reinterpret_cast<Ctx*>(static_cast<uintptr_t>(h)); }
@@ -421,10 +436,15 @@ int build_ctas(Ctx* c, int n_rep) {
     return CHEST_OK;
 }
 
+int finish_pipeline(Ctx* c);
+
+// Enqueues the whole loop body on c->stream.  wait = false leaves the run pending (chest_wait collects it): nothing
+// in here blocks the host once the per-batch-size tables exist, so one host thread can drive several devices.
 int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64_t seed, int64_t first_rep,
-                 uint32_t* err_host, uint32_t* err_dev) {
+                 uint32_t* err_host, uint32_t* err_dev, bool wait = true) {
     int rc = check_ready(c);
     if (rc) return rc;
+    if (c->pending) return fail(CHEST_ERR_STATE, "an asynchronous run is pending on this context: call chest_wait first");
     ARG(n_rep >= 1 && n_rep <= c->max_batch);
     ARG(n_iter >= 0 && n_iter <= 16);
     ARG(c->S >= 1);
@@ -440,6 +460,9 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     const int32_t* pidx[2] = {c->pilot_idx[0].p, c->pilot_idx[1].p};
     int pf_used = -1;
     if (draws && draws->on_device) {
+        ARG(draws->doppler_u && draws->phase_u && draws->noise);
+        for (int i = 0; i < 3; ++i) if (c->sch[i].set) ARG(draws->bits[i]);
+        for (int i = 0; i < 2; ++i) if (c->wf[i].set && c->wf[i].nsch) ARG(draws->pilot_idx[i]);
         for (int q = 0; q < 2; ++q)
             if (c->pf[q].used && draws->doppler_u == c->pf[q].du.p) { pf_used = q; CK(cudaStreamWaitEvent(st, c->pf[q].landed, 0)); }
         du = draws->doppler_u; pu = draws->phase_u; noise = reinterpret_cast<const cplx*>(draws->noise);
@@ -588,11 +611,17 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     const char* trace_path = getenv("CHEST_IC_TRACE");             // development: per-CTA timestamps of the last main launch
     if (trace_path) { CK(c->trace.alloc((size_t)c->ic_grid * 8)); CK(cudaMemsetAsync(c->trace.p, 0, (size_t)c->ic_grid * 64, st)); }
     const int n_units = std::max(c->n_ctas, 1);
+    // test knobs: cap the grids so that a small batch still makes every persistent CTA of k_ic_main pull several
+    // units from the queue and every k_ic_light CTA walk its grid-stride loop (tests/test_gpu_parity.py)
+    int main_grid = std::min(c->ic_grid, std::max(c->n_est_units, 1));
+    int light_grid = std::min(c->ic_light_grid * IC_LIGHT_WAVES, n_units);
+    if (const char* e = getenv("CHEST_IC_MAIN_GRID")) main_grid = std::max(1, std::min(main_grid, atoi(e)));
+    if (const char* e = getenv("CHEST_IC_LIGHT_GRID")) light_grid = std::max(1, std::min(light_grid, atoi(e)));
     for (int it = 0; it <= n_iter; ++it) {
         ip.it = it;
         if (it > 0) {                                              // phase B of iteration it
             ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
-            main_kernel<<<std::min(c->ic_grid, std::max(c->n_est_units, 1)), ic_threads, main_smem, st>>>(ip);
+            main_kernel<<<main_grid, ic_threads, main_smem, st>>>(ip);
             c->launches++;
             ip.trace = nullptr;
             if (c->profiling) CK(cudaEventRecord(c->ev_mn[it], st));
@@ -600,7 +629,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
             if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
         }
         // phases C, D, E of iteration it (+ phase A of iteration it+1)
-        k_ic_light<<<std::min(c->ic_light_grid * IC_LIGHT_WAVES, n_units), IC_LIGHT_THREADS, light_smem, st>>>(ip);
+        k_ic_light<<<light_grid, IC_LIGHT_THREADS, light_smem, st>>>(ip);
         c->launches++;
         CK(cudaGetLastError());
         if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it + 1], st));
@@ -609,11 +638,33 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     if (c->profiling) CK(cudaEventRecord(c->ev[6], st));
     if (pf_used >= 0) CK(cudaEventRecord(c->pf[pf_used].released, st));        // the set may be refilled after this point
     if (err_host) CK(cudaMemcpyAsync(err_host, err, n_err * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    c->trace_on = trace_path != nullptr; c->pending_iter = n_iter; c->pending_rep = n_rep; c->pending_n_err = n_err;
+    if (!wait) {
+        if (!err_dev) {                                            // counters travel to a pinned buffer the context owns
+            if (c->err_pinned_n < n_err) {
+                if (c->err_pinned) cudaFreeHost(c->err_pinned);
+                c->err_pinned = nullptr; c->err_pinned_n = 0;
+                CK(cudaHostAlloc((void**)&c->err_pinned, n_err * sizeof(uint32_t), cudaHostAllocDefault));
+                c->err_pinned_n = n_err;
+            }
+            CK(cudaMemcpyAsync(c->err_pinned, err, n_err * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        c->pending = true;
+        return CHEST_OK;
+    }
+    return finish_pipeline(c);
+}
+
+int finish_pipeline(Ctx* c) {
+    cudaStream_t st = c->stream;
+    const int n_iter = c->pending_iter, n_rep = c->pending_rep, N = c->N;
+    c->pending = false;
     CK(cudaStreamSynchronize(st));
-    if (trace_path) {
+    if (c->trace_on) {
+        const char* trace_path = getenv("CHEST_IC_TRACE");
         std::vector<unsigned long long> th((size_t)c->ic_grid * 8);
         CK(cudaMemcpy(th.data(), c->trace.p, th.size() * 8, cudaMemcpyDeviceToHost));
-        if (FILE* f = fopen(trace_path, "wb")) { fwrite(th.data(), 8, th.size(), f); fclose(f); }
+        if (trace_path) if (FILE* f = fopen(trace_path, "wb")) { fwrite(th.data(), 8, th.size(), f); fclose(f); }
     }
     if (c->profiling) {
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
@@ -700,42 +751,19 @@ int chest_destroy(uint64_t handle) {
     if (!c) return CHEST_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    // DevBuf has no destructor on purpose (plain members); release explicitly
-    auto relw = [](Waveform& w) {
-        w.G.release(); w.Q.release(); w.Gt.release(); w.q_klo.release(); w.q_khi.release(); w.gt_klo.release();
-        w.gt_khi.release(); w.q8_klo.release(); w.q8_khi.release(); w.hg8_klo.release(); w.hg8_khi.release(); w.gt8_klo.release(); w.gt8_khi.release(); w.pairs.release(); w.hg_klo.release(); w.hg_khi.release(); w.d_jlo.release(); w.d_jhi.release(); w.x.release(); w.s.release(); w.r0.release();
-        w.y.release(); w.D.release(); w.htrue.release(); w.HG1.release(); w.HG2.release(); w.Q1.release(); w.Q2.release();
-    };
-    relw(c->wf[0]); relw(c->wf[1]);
-    for (auto& k : c->cst) { k.symbol.release(); k.pilot.release(); k.level.release(); k.word_of_grid.release(); }
-    for (auto& s : c->sch) {
-        s.c_rowptr.release(); s.c_col.release(); s.ct_colptr.release(); s.ct_row.release(); s.pilot_pos.release();
-        s.data_pos.release(); s.pos2data.release(); s.lr_ptr.release(); s.lr_kcol.release(); s.lr_frag.release(); s.row_col0.release(); s.long_rows.release(); s.row_val0.release(); s.c_val.release(); s.ct_val.release(); s.edge_mask.release(); s.xP.release();
-        s.hP.release(); s.hdiag.release(); s.xD[0].release(); s.xD[1].release(); s.txword.release(); s.bits.release();
-        for (auto& m : s.mm) {
-            m.tile_ptr.release(); m.tile_delta.release(); m.table.release(); m.diag_frag.release();
-            for (auto& f : m.frag) f.release();
-            for (auto& f : m.diag) f.release();
-        }
-    }
-    c->d_tap_delay.release(); c->d_tap_amp.release(); c->d_noise_scale.release(); c->doppler_u.release();
-    c->phase_u.release(); c->noise.release(); c->h.release(); c->pilot_idx[0].release(); c->pilot_idx[1].release();
-    c->err.release(); c->scratch.release(); c->tmp_a.release(); c->tmp_b.release(); c->ctas.release(); c->probe.release(); c->queue.release();
     for (auto& e : c->ev) cudaEventDestroy(e);
     for (auto& e : c->user_ev) cudaEventDestroy(e);
     for (auto& e : c->ev_hg) cudaEventDestroy(e);
     for (auto& e : c->ev_gd) cudaEventDestroy(e);
     for (auto& e : c->ev_ic) cudaEventDestroy(e);
     for (auto& e : c->ev_mn) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->copy_stream);
-    for (auto& q : c->pf) {
-        cudaEventDestroy(q.landed); cudaEventDestroy(q.released);
-        q.du.release(); q.pu.release(); q.noise.release();
-        for (auto& b : q.bits) b.release();
-        for (auto& b : q.pidx) b.release();
-    }
-    delete c;
+    for (auto& q : c->pf) { cudaEventDestroy(q.landed); cudaEventDestroy(q.released); }
+    cudaStreamSynchronize(c->copy_stream);
+    if (c->err_pinned) cudaFreeHost(c->err_pinned);
+    cudaStream_t s0 = c->stream, s1 = c->copy_stream;
+    delete c;                                              // every DevBuf member frees its device memory here
+    cudaStreamDestroy(s0);
+    cudaStreamDestroy(s1);
     return CHEST_OK;
 }
 
@@ -830,6 +858,8 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
 int chest_set_constellation(uint64_t handle, int which, int order, const double* sym, const uint8_t* bitmap) {
     Ctx* c = from(handle);
     ARG(c && (which == 0 || which == 1) && order >= 2 && sym && bitmap);
+    // decided words travel as one byte per data symbol inside the IC kernels (k_ic_light, zw[])
+    if (order > 256) return fail(CHEST_ERR_ARG, "constellation order > 256 is not supported (decided words are stored as bytes)");
     CK(cudaSetDevice(c->device));
     Constellation& k = c->cst[which];
     int nb = 0;
@@ -891,7 +921,8 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
                      double kappa, double dpr, int detect, int constellation, const uint8_t* considered) {
     Ctx* c = from(handle);
     ARG(c && si >= 0 && si < 3 && (wfi == 0 || wfi == 1) && jc && ir && val && pilot_pos && considered);
-    ARG(c->wf[wfi].set && c->cst[constellation & 1].set);
+    ARG(constellation == CHEST_CONST_PAM || constellation == CHEST_CONST_QAM);
+    ARG(c->wf[wfi].set && c->cst[constellation].set);
     ARG(detect >= 0 && detect <= 2 && (detect == CHEST_DETECT_DESPREAD_REAL || data_pos));
     ARG(P > 0 && P <= 128 && n_data > 0 && k_in >= P + n_data && kappa > 0 && dpr > 0);
     CK(cudaSetDevice(c->device));
@@ -1032,9 +1063,8 @@ int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_
     m.n_tiles = (int)tdel.size();
     CK(m.tile_ptr.upload(tptr, c->stream));
     CK(m.tile_delta.upload(tdel.empty() ? std::vector<int>(1, 0) : tdel, c->stream));
-    for (auto& f : m.frag) f.release();
-    for (auto& f : m.diag) f.release();
-    m.frag.assign(n_snr, DevBuf<cplx>()); m.diag.assign(n_snr, DevBuf<cplx>());
+    m.frag.clear(); m.diag.clear();
+    m.frag.resize(n_snr); m.diag.resize(n_snr);
     std::vector<WTiles> table(n_snr);
     std::vector<cplx> frag((size_t)std::max(m.n_tiles, 1) * P4 * 32), dg((size_t)K * P);
     std::vector<cplx> dfrag((size_t)n_snr * RT * P4 * 32, cmake(0.0, 0.0));
@@ -1482,6 +1512,172 @@ int chest_run_batch_device(uint64_t handle, int n_rep, int n_iter, const chest_d
     ARG(c);
     CK(cudaSetDevice(c->device));
     return run_pipeline(c, n_rep, n_iter, draws, seed, first_rep, nullptr, err_dev);
+}
+
+// ---------------------------------------------------------------- asynchronous run / wait, several devices
+int chest_run_batch_async(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws, uint64_t seed,
+                          int64_t first_rep) {
+    Ctx* c = from(handle);
+    ARG(c);
+    CK(cudaSetDevice(c->device));
+    return run_pipeline(c, n_rep, n_iter, draws, seed, first_rep, nullptr, nullptr, false);
+}
+
+int chest_wait(uint64_t handle, uint32_t* err_out) {
+    Ctx* c = from(handle);
+    ARG(c);
+    if (!c->pending) return fail(CHEST_ERR_STATE, "no asynchronous run is pending on this context");
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->pending_n_err;
+    int rc = finish_pipeline(c);
+    if (rc) return rc;
+    if (err_out) std::memcpy(err_out, c->err_pinned, n * sizeof(uint32_t));
+    return CHEST_OK;
+}
+
+namespace {
+// NCCL is bound at run time (dlopen): the library has no link-time dependency on it, and inside a process that has
+// already loaded an NCCL (PyTorch's) the same soname resolves to that copy.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& why) {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { why = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        bool ok = true;
+        auto sym = [&](const char* n) { void* f = dlsym(lib, n); if (!f) { ok = false; why = std::string("NCCL symbol missing: ") + n; } return f; };
+        CommInitAll = (decltype(CommInitAll))sym("ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!ok) { dlclose(lib); lib = nullptr; }
+        return ok;
+    }
+};
+NcclApi g_nccl;
+#define NCK(call)                                                                                  \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess)                                                                     \
+            return fail(CHEST_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r_));    \
+    } while (0)
+
+struct Multi {
+    std::vector<Ctx*> ctx;
+    std::vector<ncclComm_t> comm;                  // empty for a single device
+    std::vector<cudaEvent_t> ev0, ev1;             // around the all-reduce, per device
+};
+Multi* multi_from(uint64_t h) { return reinterpret_cast<Multi*>(static_cast<uintptr_t>(h)); }
+}  // namespace
+
+int chest_multi_create(const uint64_t* handles, int n_devices, uint64_t* multi) {
+    ARG(handles && multi && n_devices >= 1 && n_devices <= 64);
+    Multi* m = new Multi();
+    std::vector<int> devs;
+    for (int i = 0; i < n_devices; ++i) {
+        Ctx* c = from(handles[i]);
+        if (!c || !c->finalized) { delete m; return fail(CHEST_ERR_STATE, "chest_multi_create: every context must be finalized"); }
+        for (int d : devs) if (d == c->device) { delete m; return fail(CHEST_ERR_ARG, "chest_multi_create: two contexts on one device"); }
+        if (i > 0 && (c->S != m->ctx[0]->S || c->N != m->ctx[0]->N)) { delete m; return fail(CHEST_ERR_ARG, "chest_multi_create: contexts differ in configuration"); }
+        m->ctx.push_back(c); devs.push_back(c->device);
+    }
+    if (n_devices > 1) {
+        std::string why;
+        if (!g_nccl.load(why)) { delete m; return fail(CHEST_ERR_STATE, why); }
+        m->comm.resize(n_devices);
+        ncclResult_t r = g_nccl.CommInitAll(m->comm.data(), n_devices, devs.data());
+        if (r != ncclSuccess) { delete m; return fail(CHEST_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r)); }
+    }
+    m->ev0.resize(n_devices); m->ev1.resize(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        CK(cudaSetDevice(devs[i]));
+        CK(cudaEventCreate(&m->ev0[i])); CK(cudaEventCreate(&m->ev1[i]));
+    }
+    *multi = (uint64_t)(uintptr_t)m;
+    return CHEST_OK;
+}
+
+int chest_multi_destroy(uint64_t multi) {
+    Multi* m = multi_from(multi);
+    if (!m) return CHEST_OK;
+    for (size_t i = 0; i < m->ctx.size(); ++i) {
+        cudaSetDevice(m->ctx[i]->device);
+        cudaEventDestroy(m->ev0[i]); cudaEventDestroy(m->ev1[i]);
+    }
+    for (auto& q : m->comm) g_nccl.CommDestroy(q);
+    delete m;
+    return CHEST_OK;
+}
+
+int chest_multi_run(uint64_t multi, int64_t n_rep_total, int n_iter, uint64_t seed, int64_t first_rep,
+                    uint32_t* err_out, uint64_t* totals_out, float* reduce_ms) {
+    Multi* m = multi_from(multi);
+    ARG(m && n_rep_total >= 1 && n_iter >= 0 && n_iter <= 16);
+    const int nd = (int)m->ctx.size(), S = m->ctx[0]->S;
+    const size_t per_rep = (size_t)S * (n_iter + 1) * 12;
+    for (Ctx* c : m->ctx) {
+        CK(cudaSetDevice(c->device));
+        CK(c->totals.alloc(per_rep));
+        CK(cudaMemsetAsync(c->totals.p, 0, per_rep * sizeof(unsigned long long), c->stream));
+    }
+    // contiguous blocks of realizations per device, handed out in rounds of at most max_batch each; all devices of a
+    // round are enqueued before any is waited for (the host thread never blocks between them)
+    int64_t done = 0;
+    std::vector<int64_t> off(nd); std::vector<int> cnt(nd);
+    while (done < n_rep_total) {
+        for (int i = 0; i < nd; ++i) {
+            Ctx* c = m->ctx[i];
+            cnt[i] = (int)std::min<int64_t>(c->max_batch, n_rep_total - done);
+            off[i] = done; done += cnt[i];
+            if (cnt[i] == 0) continue;
+            CK(cudaSetDevice(c->device));
+            int rc = run_pipeline(c, cnt[i], n_iter, nullptr, seed, first_rep + off[i], nullptr, nullptr, false);
+            if (rc) return rc;
+            k_sum_counters<<<(unsigned)per_rep, 128, 0, c->stream>>>(c->totals.p, c->err.p, cnt[i], (int)per_rep);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+        for (int i = 0; i < nd; ++i) {
+            if (cnt[i] == 0) continue;
+            Ctx* c = m->ctx[i];
+            CK(cudaSetDevice(c->device));
+            const size_t n = c->pending_n_err;
+            int rc = finish_pipeline(c);
+            if (rc) return rc;
+            if (err_out) std::memcpy(err_out + (size_t)off[i] * per_rep, c->err_pinned, n * sizeof(uint32_t));
+        }
+    }
+    // the one collective of the path: sum of the per-GPU counter totals
+    for (int i = 0; i < nd; ++i) { CK(cudaSetDevice(m->ctx[i]->device)); CK(cudaEventRecord(m->ev0[i], m->ctx[i]->stream)); }
+    if (nd > 1) {
+        NCK(g_nccl.GroupStart());
+        for (int i = 0; i < nd; ++i)
+            NCK(g_nccl.AllReduce(m->ctx[i]->totals.p, m->ctx[i]->totals.p, per_rep, ncclUint64, ncclSum, m->comm[i], m->ctx[i]->stream));
+        NCK(g_nccl.GroupEnd());
+    }
+    float worst = 0;
+    for (int i = 0; i < nd; ++i) {
+        CK(cudaSetDevice(m->ctx[i]->device));
+        CK(cudaEventRecord(m->ev1[i], m->ctx[i]->stream));
+        CK(cudaStreamSynchronize(m->ctx[i]->stream));
+        float t = 0; CK(cudaEventElapsedTime(&t, m->ev0[i], m->ev1[i]));
+        worst = std::max(worst, t);
+    }
+    if (reduce_ms) *reduce_ms = worst;
+    if (totals_out) {
+        CK(cudaSetDevice(m->ctx[0]->device));
+        CK(cudaMemcpy(totals_out, m->ctx[0]->totals.p, per_rep * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    return CHEST_OK;
 }
 
 int chest_bit_counts(uint64_t handle, int64_t* n_bits) {

@@ -1575,6 +1575,24 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
     }
 }
 
+// ============================================================================ counter totals
+// tot[e] += sum_rep err[rep][e]  (e = (snr, it, scheme, csi, edge)): the per-GPU partial sums of the final reduce.
+// One block per counter; 64-bit totals (4096 realizations x 5504 bits already exceed 2^24 per batch).
+__global__ void k_sum_counters(unsigned long long* __restrict__ tot, const uint32_t* __restrict__ err, int n_rep, int per_rep) {
+    const int e = blockIdx.x;
+    unsigned long long a = 0;
+    for (int r = threadIdx.x; r < n_rep; r += blockDim.x) a += err[(int64_t)r * per_rep + e];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    __shared__ unsigned long long part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += part[w];
+        tot[e] += t;
+    }
+}
+
 // ============================================================================ FP64 peak probes
 __global__ void k_peak_dmma(double* out, int iters) {
     double c[8][2];

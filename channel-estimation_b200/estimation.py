@@ -18,7 +18,13 @@ class ImaginaryInterferenceCancellationAtPilotPosition:
     """ChannelEstimation.ImaginaryInterferenceCancellationAtPilotPosition(Method, PilotMatrix,
     FBMCMatrix, NrCanceledInterferersPerPilot, PilotToDataPowerOffset)  (IIC.m:37-229)."""
 
-    def __init__(self, Method, PilotMatrix, FBMCMatrix, NrCanceledInterferersPerPilot, PilotToDataPowerOffset):
+    # Relative width of a tie group around the selection threshold (see _tags).  0 = the reference's literal >=.
+    TieTolerance = 1e-9
+
+    def __init__(self, Method, PilotMatrix, FBMCMatrix, NrCanceledInterferersPerPilot, PilotToDataPowerOffset,
+                 TieTolerance=None):
+        if TieTolerance is not None:
+            self.TieTolerance = float(TieTolerance)
         pm2 = np.asarray(PilotMatrix)
         D0 = np.asarray(FBMCMatrix)
         L, K = pm2.shape
@@ -40,7 +46,7 @@ class ImaginaryInterferenceCancellationAtPilotPosition:
             C[pil, np.arange(P)] = np.sqrt(PilotToDataPowerOffset)                       # IIC.m:68
             C[dat, P + np.arange(nD)] = 1.0                                              # IIC.m:69
             if n_cancel > 0:                                                             # IIC.m:71-82
-                tags = self._tags(D0, pm2, pil, n_cancel)[1]
+                tags = self._tags(D0, pm2, pil, n_cancel, self.TieTolerance)[1]
                 keep = np.concatenate([tags[pil], tags[dat]]) != 0
                 C[np.ix_(aux, np.flatnonzero(~keep))] = 0
                 self.ConsideredInterferenceMatrix = tags.reshape(L, K, order="F")
@@ -49,7 +55,7 @@ class ImaginaryInterferenceCancellationAtPilotPosition:
             self.NrDataSymbols, self.NrAuxiliarySymbols = nD, nA
             self.PostCodingChannelMatrix = np.nan
         elif Method == "Coding":
-            mask, tags = self._tags(D0, pm2, pil, n_cancel)
+            mask, tags = self._tags(D0, pm2, pil, n_cancel, self.TieTolerance)
             if np.any(mask.sum(axis=0) > 1):                                             # IIC.m:116-118
                 raise ValueError("Coding symbols must not overlap: The pilot-spacing is too small!")
             free = np.flatnonzero(tags == 0)
@@ -81,18 +87,20 @@ class ImaginaryInterferenceCancellationAtPilotPosition:
         self.NrTransmittedSymbols = LK
 
     @staticmethod
-    def _tags(D0, pm2, pil, n_cancel):
+    def _tags(D0, pm2, pil, n_cancel, tie=0.0):
         """IIC.m:47-51,72-76,113-122: positions whose interference weight towards pilot p is among
         the n_cancel largest weights of the interference pattern get tag -p, pilots get +p.
-        As in the reference, nominally equal weights are compared with a plain >=, so which members
-        of a tie group straddling the threshold are taken depends on their last bits."""
+        The reference compares nominally equal weights with a plain >=; when the threshold falls inside
+        a group of weights that are equal in exact arithmetic (FFT size = subcarrier count: offsets +l
+        and L-l alias), which members pass depends on their last bits, i.e. on the FFT library.  `tie`
+        > 0 takes the exact-arithmetic reading instead: the whole group passes."""
         L, K = pm2.shape
         LK = L * K
         corner = lambda c: np.abs(D0[:, c]).reshape(L, K, order="F")
         i11, iE1, i1E, iEE = corner(0), corner(L - 1), corner(LK - L), corner(LK - 1)
         pattern = np.hstack([np.vstack([iEE, i1E[1:, :]]), np.vstack([iE1[:, 1:], i11[1:, 1:]])])
         thr = np.sort(pattern.reshape(-1))[::-1][n_cancel]
-        mask = np.abs(D0[pil, :]) >= thr
+        mask = np.abs(D0[pil, :]) >= thr * (1.0 - tie)
         tags = -(mask * np.arange(1, len(pil) + 1)[:, None]).sum(axis=0).astype(np.int64)
         tags[pil] = np.arange(1, len(pil) + 1)
         return mask, tags

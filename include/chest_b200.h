@@ -2,7 +2,7 @@
  * chest_b200.h -- C ABI of the B200-native Monte-Carlo hot path of rnissel/Channel-Estimation.
  *
  * This is the drop-in boundary: a MATLAB MEX gateway (matlab/chest_mex.c), the Python host mirror
- * (channel-estimation_b200/host.py, ctypes) or any other FFI binds exactly these entry points.
+ * (channel-estimation_b200/context.py + _lib.py, ctypes) or any other FFI binds exactly these entry points.
  * The reference has no native interface of its own (it is 100 % MATLAB); each entry point cites
  * the reference method / script lines it replaces.  `DS.m` = DoublySelectiveChannelEstimation.m,
  * `FF.m` = +Channel/FastFading.m, `FBMC.m`/`OFDM.m`/`SC.m` live in +Modulation.
@@ -184,6 +184,31 @@ int chest_unit_count(uint64_t handle, int* n_units);
 /* Same with the result left on the device: err_dev is a device pointer (used by bench `value`). */
 int chest_run_batch_device(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws,
                            uint64_t seed, int64_t first_rep, uint32_t* err_dev);
+
+/* ------------------------------------------------------------------ one host thread, several GPUs
+ * (SURVEY.md 8b "Threading", 8e: a MEX host is single-threaded; realizations are independent, DS.m:350-368)
+ *
+ * chest_run_batch_async enqueues the loop body for n_rep realizations on the context's stream and returns without
+ * waiting; chest_wait blocks until it has finished and copies the error counts (layout of chest_run_batch) from a
+ * pinned buffer the context owns into err_out (may be NULL).  A caller with one context per device enqueues on all
+ * of them, then waits for all of them.  Seeded draws (draws == NULL) or device-resident draws never block the host;
+ * explicit host draws are staged by the CUDA runtime unless they live in pinned memory. */
+int chest_run_batch_async(uint64_t handle, int n_rep, int n_iter, const chest_draws* draws, uint64_t seed,
+                          int64_t first_rep);
+int chest_wait(uint64_t handle, uint32_t* err_out);
+
+/* A group of finalized contexts, one per device, configured identically (the caller runs the same setters on each).
+ * chest_multi_run shards n_rep_total seeded realizations [first_rep, first_rep + n_rep_total) over the devices in
+ * contiguous blocks (rounds of at most max_batch per device, all devices of a round enqueued before any wait; no
+ * inter-GPU traffic during the loop), sums each device's counters on that device (64-bit), and finishes with the one
+ * collective of the path: an NCCL all-reduce (ncclUint64, sum; NCCL bound with dlopen, ncclCommInitAll) of the
+ * S x (n_iter+1) x 12 totals.  err_out (may be NULL): per-realization counts [n_rep_total][snr][it][12];
+ * totals_out (may be NULL): [snr][it][scheme][csi][edge] uint64; reduce_ms (may be NULL): device time of the
+ * all-reduce, maximum over the devices.  The contexts stay owned by the caller. */
+int chest_multi_create(const uint64_t* handles, int n_devices, uint64_t* multi);
+int chest_multi_run(uint64_t multi, int64_t n_rep_total, int n_iter, uint64_t seed, int64_t first_rep,
+                    uint32_t* err_out, uint64_t* totals_out, float* reduce_ms);
+int chest_multi_destroy(uint64_t multi);
 
 /* n_bits[scheme][edge] used as BER denominators. */
 int chest_bit_counts(uint64_t handle, int64_t* n_bits /* [CHEST_N_SCHEMES][2] */);

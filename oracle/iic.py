@@ -18,14 +18,28 @@ def _interference_matrix(FBMCMatrix, L, K):
     return np.hstack([left, right])
 
 
-def _considered(FBMCMatrix, PilotMatrix, n_cancel, IM):
+# Tie rule of the interferer selection (IIC.m:72-73, 113-114).  The reference compares
+#     abs(FBMCMatrix(pilot,:)) >= SortedInterferenceValues(N+1)
+# with a plain >=.  When the FFT size equals the subcarrier count (DS.m default: fs = 24*15 kHz) the interference
+# pattern holds groups of weights that are EQUAL in exact arithmetic (subcarrier offsets +l and L-l alias) and the
+# (N+1)-th value falls inside such a group for the data-spreading scheme (N = 20: the 16th..31st largest values are all 0.036858; so does the 29th of the auxiliary scheme).
+# In exact arithmetic >= takes the whole group; in floating point the members differ in their last bits (FFT and
+# exp() rounding), so the literal comparison picks a rounding-noise-dependent subset -- a different one in MATLAB,
+# in this NumPy restatement (12 of 16) and in the product's host mirror (14-16), i.e. the reference's behaviour
+# is not defined beyond "some subset of the tie group".  TIE_RTOL > 0 restates the exact-arithmetic reading:
+# values within TIE_RTOL (relative) below the threshold count as equal to it.  tie_rtol = 0 is the literal >=.
+# At the paper geometry (DS.m:42-46) the threshold is the smallest member of its group and both readings agree.
+TIE_RTOL = 1e-9
+
+
+def _considered(FBMCMatrix, PilotMatrix, n_cancel, IM, tie_rtol=TIE_RTOL):
     """IIC.m:72-76 / 113-122: per-position pilot tags (-p for interferers of pilot p, +p at pilots)."""
     L, K = PilotMatrix.shape
     pm = PilotMatrix.reshape(-1, order="F")
     pil = np.flatnonzero(pm == 1)
     P = len(pil)
     srt = np.sort(np.abs(IM.reshape(-1)))[::-1]                                   # sort(...,'descend')
-    tmp = np.abs(FBMCMatrix[pil, :]) >= srt[n_cancel]                             # (NrCanceled+1)-th value
+    tmp = np.abs(FBMCMatrix[pil, :]) >= srt[n_cancel] * (1.0 - tie_rtol)          # (NrCanceled+1)-th value
     ci = -(tmp * np.arange(1, P + 1)[:, None]).sum(axis=0).astype(np.int64)       # sum_p -(p) * mask_p
     ci[pil] = np.arange(1, P + 1)
     return tmp, ci
@@ -35,7 +49,7 @@ class ImaginaryInterferenceCancellationAtPilotPosition:
     """IIC.m:37-229."""
 
     def __init__(self, Method, PilotMatrix, FBMCMatrix, NrCanceledInterferersPerPilot,
-                 PilotToDataPowerOffset):
+                 PilotToDataPowerOffset, tie_rtol=TIE_RTOL):
         PilotMatrix = np.asarray(PilotMatrix)
         L, K = PilotMatrix.shape
         LK = L * K
@@ -57,7 +71,7 @@ class ImaginaryInterferenceCancellationAtPilotPosition:
             C[pil, np.arange(P)] = np.sqrt(PilotToDataPowerOffset)                # :68
             C[dat, P + np.arange(nD)] = 1.0                                       # :69
             if NrCanceledInterferersPerPilot > 0:                                 # :71-82
-                _, ci = _considered(D0, PilotMatrix, NrCanceledInterferersPerPilot, IM)
+                _, ci = _considered(D0, PilotMatrix, NrCanceledInterferersPerPilot, IM, tie_rtol)
                 idx = np.concatenate([ci[pil], ci[dat]])
                 C[np.ix_(aux, np.flatnonzero(idx == 0))] = 0                      # :82
                 considered = ci.reshape(L, K, order="F")
@@ -71,7 +85,7 @@ class ImaginaryInterferenceCancellationAtPilotPosition:
         elif Method == "Coding":                                                  # :106-210
             nD, nA = LK - 2 * P, 0
             self.AuxiliaryToDataPowerOffset = 0
-            tmp, ci = _considered(D0, PilotMatrix, NrCanceledInterferersPerPilot, IM)
+            tmp, ci = _considered(D0, PilotMatrix, NrCanceledInterferersPerPilot, IM, tie_rtol)
             if np.sum(tmp.sum(axis=0) > 1):                                       # :116-118
                 raise ValueError("Coding symbols must not overlap: The pilot-spacing is too small!")
             unc = np.flatnonzero(ci == 0)

@@ -1,0 +1,188 @@
+"""GPU parity at bench scale: persistent CTAs that process many work units, grid-stride loops, the
+double-buffered draw upload at full size, context life-cycle, and the product's own setup feeding the loop.
+Everything goes through the C ABI; the checker is the CPU oracle on the same seeded draws."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.helpers import err_from_oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_counts(S, seed, rep, n_iter=4):
+    from oracle import rng
+    from oracle.ds import ds_realization
+    return err_from_oracle(ds_realization(S, rng.draws_for(S, seed, rep)), n_iter)
+
+
+@pytest.mark.parametrize("mode", ["factored", "dense"])
+def test_large_batch_sampled_against_oracle(ds_default, mode):
+    """B = 1047 realizations (65 full 16-column units + a ragged tail of 7), 4 iterations: every persistent CTA of
+    k_ic_main pulls about five units from the queue (kernels.cuh, `for (;;)` loop of k_ic_main; `ic_load_unit` reuses
+    the shared tables).  Eleven realizations -- first, last, both sides of unit boundaries, the ragged tail -- are
+    compared with the oracle run on the same counter-based draws: identical counts."""
+    from tests.helpers import context_from_oracle
+    S = ds_default
+    B, seed, first = 1047, 99, 5000
+    ctx = context_from_oracle(S, max_batch=B)
+    ctx.set_perfect_csi_mode(mode)
+    err = ctx.run_batch(B, 4, None, seed=seed, first_rep=first)
+    assert ctx.n_units() > 4 * 296
+    for r in (0, 15, 16, 17, 511, 512, 1023, 1024, 1039, 1040, 1046):
+        assert np.array_equal(err[r], _oracle_counts(S, seed, first + r)), (mode, r)
+    # a second batch through the same context (queue counters, scratch and tables are reused)
+    err2 = ctx.run_batch(40, 4, None, seed=seed, first_rep=first + 1000)
+    assert np.array_equal(err2, err[1000:1040])
+    ctx.close()
+
+
+def test_capped_grids_walk_the_unit_loops(ds_default):
+    """With the grids capped (CHEST_IC_MAIN_GRID / CHEST_IC_LIGHT_GRID) 7 CTAs of k_ic_main and 5 of k_ic_light
+    share 66 + 38 units: the queue loop and the grid-stride loop (kernels.cuh: `for (int unit = blockIdx.x; ...`)
+    run many times per CTA.  Counts must equal the uncapped run and the oracle."""
+    from tests.helpers import context_from_oracle
+    S = ds_default
+    seed, first, B = 4, 70, 19
+    ctx = context_from_oracle(S, max_batch=B)
+    base = ctx.run_batch(B, 4, None, seed=seed, first_rep=first)
+    for mode in ("factored", "dense"):
+        ctx.set_perfect_csi_mode(mode)
+        os.environ["CHEST_IC_MAIN_GRID"], os.environ["CHEST_IC_LIGHT_GRID"] = "7", "5"
+        try:
+            capped = ctx.run_batch(B, 4, None, seed=seed, first_rep=first)
+        finally:
+            del os.environ["CHEST_IC_MAIN_GRID"], os.environ["CHEST_IC_LIGHT_GRID"]
+        assert np.array_equal(capped, base), mode
+    for r in (0, 16, 18):
+        assert np.array_equal(base[r], _oracle_counts(S, seed, first + r))
+    ctx.close()
+
+
+def test_prefetch_double_buffer_at_full_size(ds_default):
+    """chest_prefetch_draws with bench-sized batches: three uploads of 512 realizations (38 MB each) alternate between
+    the two library-owned buffer sets while batches run; counts equal the direct path and the oracle."""
+    from tests.helpers import context_from_oracle
+    S = ds_default
+    B, seed = 512, 31
+    ctx = context_from_oracle(S, max_batch=B)
+    sets = []
+    for k in range(3):
+        ctx.generate_draws(B, seed, k * B)
+        sets.append(ctx.pack_draws(ctx.download_draws(B)))
+    seeded = [ctx.run_batch(B, 2, None, seed=seed, first_rep=k * B) for k in range(3)]
+    dev = ctx.prefetch_draws(B, sets[0][0])
+    for k in range(3):
+        nxt = ctx.prefetch_draws(B, sets[k + 1][0]) if k + 1 < 3 else None
+        got = ctx.run_batch(B, 2, dev)
+        assert np.array_equal(got, seeded[k]), k
+        dev = nxt
+    assert np.array_equal(seeded[2][B - 1], _oracle_counts(S, seed, 3 * B - 1, 2))
+    ctx.close()
+
+
+def test_create_destroy_releases_device_memory(ds_default):
+    """chest_destroy frees everything the context allocated (the factored-mode buffers leaked)."""
+    import torch
+    from tests.helpers import context_from_oracle
+    S = ds_default
+
+    def cycle():
+        ctx = context_from_oracle(S, max_batch=256)
+        ctx.run_batch(256, 1, None, seed=1, first_rep=0)
+        ctx.close()
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 << 20, "device memory not released: %.1f MB per cycle" % ((free0 - free1) / 3 / 2 ** 20)
+
+
+def test_argument_checks():
+    """constellation order above the byte-wide decided words is rejected; the constellation id of a scheme is
+    validated before use; device-resident draws with a missing member are refused before any launch."""
+    import ctypes as C
+    import chest_b200
+    from chest_b200 import _lib
+    from oracle.signal_constellation import SignalConstellation
+    ctx = chest_b200.DeviceContext()
+    q = SignalConstellation(1024, "QAM")
+    with pytest.raises(chest_b200.ChestError, match="order > 256"):
+        ctx.set_constellation("QAM", q.SymbolMapping, q.BitMapping)
+    q = SignalConstellation(256, "QAM")
+    ctx.set_constellation("QAM", q.SymbolMapping, q.BitMapping)
+    G = np.eye(8, 4, dtype=complex)
+    ctx.set_waveform("O", G, G)
+    jc = np.arange(5, dtype=np.int64); ir = np.arange(4, dtype=np.int32); val = np.ones(4, dtype=complex)
+    pp = np.zeros(1, dtype=np.int32); dp = np.arange(1, 4, dtype=np.int32); cb = np.ones(3 * 8, dtype=np.uint8)
+    rc = ctx.lib.chest_set_scheme(ctx._h, 2, 1, 4, 1, 3, jc.ctypes.data, ir.ctypes.data, val.ctypes.data, pp.ctypes.data,
+                                  dp.ctypes.data, 1.0, 1.0, 2, 7, cb.ctypes.data)
+    assert rc == -1 and b"constellation" in ctx.lib.chest_last_error()
+    ctx.close()
+
+
+def test_device_draws_null_members_rejected(gpu_ctx):
+    from chest_b200 import _lib
+    import ctypes as C
+    ctx = gpu_ctx
+    st = ctx.generate_draws(2, 1, 0)
+    bad = _lib.ChestDraws()
+    C.memmove(C.byref(bad), C.byref(st), C.sizeof(st))
+    bad.noise = None
+    err = np.zeros((2, ctx.n_snr, 2, 3, 2, 2), dtype=np.uint32)
+    rc = ctx.lib.chest_run_batch(ctx._h, 2, 1, C.byref(bad), 0, 0, err.ctypes.data)
+    assert rc == -1
+    C.memmove(C.byref(bad), C.byref(st), C.sizeof(st))
+    bad.bits[1] = None
+    rc = ctx.lib.chest_run_batch(ctx._h, 2, 1, C.byref(bad), 0, 0, err.ctypes.data)
+    assert rc == -1
+    assert ctx.run_batch(2, 1, st).shape == err.shape          # the context is still healthy
+
+
+def test_product_setup_fbmc_counts_match_oracle(ds_default):
+    """The benched path end to end: the PRODUCT's setup (its own modem matrices, precoders with the tie rule, pilot
+    correlations through K2 on the GPU, MMSE matrices) feeding the GPU loop, against the oracle's setup + loop on
+    the same draws -- all three schemes at the default configuration, count-level."""
+    from chest_b200.simulation import DoublySelectiveSimulation
+    S = ds_default
+    sim = DoublySelectiveSimulation(max_batch=16, seed=11)
+    for name in ("aux", "cod"):
+        assert np.array_equal(sim.sch[name]["C"] != 0, S["schemes"][name]["C"] != 0)
+        assert np.max(np.abs(sim.sch[name]["C"] - S["schemes"][name]["C"])) < 1e-13
+    ber, err = sim.run(NrRepetitions=6, seed=11, first_rep=300)
+    for r in range(6):
+        assert np.array_equal(err[r], _oracle_counts(S, 11, 300 + r)), r
+    assert ber["BER_FBMC_Aux_InterferenceCancellation"].shape == (7, 6, 4)
+    sim.close()
+
+
+def test_two_gpus_sharded_counters_equal_single_gpu(ds_default):
+    """SURVEY section 4 pyramid item 3: the same realization indices give the same counters whether one GPU runs
+    them all or two GPUs run half each (one host thread, chest_multi_*), and the NCCL-reduced totals are their sum."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from chest_b200.context import MultiDevice
+    from tests.helpers import context_from_oracle
+    S = ds_default
+    n, seed, first = 96, 17, 1000
+    one = context_from_oracle(S, max_batch=64, device=0)
+    ref = np.concatenate([one.run_batch(64, 4, None, seed=seed, first_rep=first),
+                          one.run_batch(32, 4, None, seed=seed, first_rep=first + 64)])
+    one.close()
+    ctxs = [context_from_oracle(S, max_batch=32, device=d) for d in (0, 1)]
+    multi = MultiDevice(ctxs)
+    err, totals, reduce_ms = multi.run(n, 4, seed=seed, first_rep=first)
+    assert np.array_equal(err, ref)
+    assert np.array_equal(totals, ref.astype(np.uint64).sum(axis=0))
+    assert reduce_ms >= 0
+    multi.close()
+    for c in ctxs:
+        c.close()

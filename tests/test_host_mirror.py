@@ -112,3 +112,43 @@ def test_product_fails_loudly_without_gpu():
         chest_b200.DeviceContext(0)
     with pytest.raises(chest_b200.ChestError):
         FBMC().Modulation(np.zeros((12, 30)))
+
+
+def test_iic_tie_group_rule(ds_default):
+    """IIC.m:72-73,113-114 at the default geometry: the (N+1)-th largest interference weight of the data-spreading
+    scheme falls inside a group of 20 weights that are equal in exact arithmetic.  The literal >= picks a subset that
+    depends on the last bits of the FBMC matrix (the oracle's FFT-built D0 and the product's closed-form D0 differ by
+    1e-14 and already disagree); the exact-arithmetic reading (whole group, `TieTolerance`) makes oracle and product
+    build the SAME precoder, bit for bit in its sparsity pattern."""
+    from oracle.iic import ImaginaryInterferenceCancellationAtPilotPosition as RefIIC, TIE_RTOL
+    S = ds_default
+    pm_o, pm_f, pm_aux = DoublySelectiveSimulation._pilot_matrices(24, 1)
+    D0_prod = FBMC(24, 30, 15e3, 15e3 * 24, 0, False, "Hermite-OQAM", 8, 0, True).GetFBMCMatrix()
+    assert 0 < np.max(np.abs(D0_prod - S["D0"])) < 1e-12
+    # the tie group: values 16..31 (1-based) of the sorted pattern are one weight (0.036858); both thresholds, the
+    # 21st (Coding) and the 29th (Auxiliary) value, are inside it
+    from oracle.iic import _interference_matrix
+    srt = np.sort(np.abs(_interference_matrix(S["D0"], 24, 30)).reshape(-1))[::-1]
+    assert np.ptp(srt[15:31]) < 1e-12 and srt[31] < 0.3 * srt[30] and srt[14] > 5 * srt[15]
+    assert IIC.TieTolerance == TIE_RTOL == 1e-9
+    for method, pm, n, off in (("Auxiliary", pm_aux, 28, 4.685), ("Coding", pm_f, 20, 4)):
+        a = RefIIC(method, pm, S["D0"], n, off)
+        b = IIC(method, pm, D0_prod, n, off)
+        assert np.array_equal(a.PrecodingMatrix != 0, b.PrecodingMatrix != 0)
+        assert np.max(np.abs(a.PrecodingMatrix - b.PrecodingMatrix)) < 1e-13
+        tags = np.asarray(b.ConsideredInterferenceMatrix).reshape(-1, order="F")
+        assert all(np.sum(tags == -p) == 16 for p in range(1, 17))           # the whole group: 16 interferers per pilot
+    # literal comparison: rounding-noise dependent (documented, DESIGN.md section 2)
+    lit_ref = RefIIC("Coding", pm_f, S["D0"], 20, 4, tie_rtol=0.0)
+    lit_prod = IIC("Coding", pm_f, D0_prod, 20, 4, TieTolerance=0.0)
+    n_ref = np.count_nonzero(lit_ref.PrecodingMatrix)
+    n_prod = np.count_nonzero(lit_prod.PrecodingMatrix)
+    assert n_ref != n_prod or not np.array_equal(lit_ref.PrecodingMatrix != 0, lit_prod.PrecodingMatrix != 0)
+    # paper geometry (DS.m:42-46): the threshold is the smallest member of its group, both readings agree
+    fb = FBMC(24, 60, 15e3, 15e3 * 14 * 14, 0, False, "Hermite-OQAM", 8, 0, True)
+    D0p = fb.GetFBMCMatrix()
+    _, pm_f2, pm_aux2 = DoublySelectiveSimulation._pilot_matrices(24, 2)
+    for method, pm, n, off in (("Auxiliary", pm_aux2, 28, 4.685), ("Coding", pm_f2, 20, 4)):
+        x = IIC(method, pm, D0p, n, off, TieTolerance=0.0)
+        y = IIC(method, pm, D0p, n, off)
+        assert np.array_equal(x.PrecodingMatrix, y.PrecodingMatrix)
