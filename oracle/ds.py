@@ -46,8 +46,9 @@ class DSConfig:
 
     @staticmethod
     def paper(**kw):
-        return DSConfig(M_SNR_dB=tuple(range(10, 41, 2)), NrRepetitions=1000,
-                        SamplingRate=15e3 * 14 * 14, NrSubframes=2, **kw)
+        base = dict(M_SNR_dB=tuple(range(10, 41, 2)), NrRepetitions=1000, SamplingRate=15e3 * 14 * 14, NrSubframes=2)
+        base.update(kw)
+        return DSConfig(**base)
 
 
 def pilot_matrices(L, NrSubframes):

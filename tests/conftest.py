@@ -26,3 +26,11 @@ def gpu_ctx(ds_default):
     ctx = context_from_oracle(ds_default, max_batch=32)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="session")
+def ds_paper():
+    """Paper geometry (DS.m:42-46: fs = 2.94 MHz, 2 subframes -> N = 7350, K = 1440 / 672, 32 pilots, 6 taps) with two
+    SNR points (20 dB and the 32 dB of png/Figure5.png) to keep the oracle setup around a minute."""
+    from oracle.ds import DSConfig, ds_setup
+    return ds_setup(DSConfig.paper(M_SNR_dB=(20, 32)))

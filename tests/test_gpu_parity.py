@@ -248,14 +248,6 @@ def test_golden_error_counts(gpu_ctx):
     assert np.array_equal(err, np.array(g["err"], dtype=np.uint32))
 
 
-@pytest.fixture(scope="module")
-def ds_paper():
-    """Paper geometry (DS.m:42-46: fs = 2.94 MHz, 2 subframes -> N = 7350, K = 1440 / 672, 32 pilots, 6 taps) with two
-    SNR points to keep the oracle setup around a minute."""
-    from oracle.ds import DSConfig, ds_setup
-    return ds_setup(DSConfig(M_SNR_dB=(20, 36), SamplingRate=15e3 * 14 * 14, NrSubframes=2))
-
-
 def test_paper_geometry_parity(ds_paper):
     """BASELINE.json config 3 geometry: P = 32 (eight pilot quads per tile), 6 non-zero taps with gaps, K = 1440."""
     from oracle.ds import ds_realization, new_draws

@@ -124,3 +124,51 @@ def test_doubly_flat_simulation_matches_theory():
         tot += len(bits)
     theory = bep([snr_db], qam.SymbolMapping, qam.BitMapping)[0]
     assert abs(errs / tot - theory) < 0.25 * theory
+
+
+def _bundle_draws(B, S, reps):
+    """Rebuild per-repetition draws from the three replay streams of a reference bundle (consumption order of
+    FF.m:227-233, DS.m:355-367, DS.m:399 -- see oracle/export_reference_bundle.py)."""
+    u, i, g = (np.asarray(B["stream_" + k]).reshape(-1) for k in ("rand", "randi", "randn"))
+    T, paths, N, nS = len(S["chan"].Implementation["IndexDelayTaps"]), S["cfg"].Paths, S["N"], len(S["Pn"])
+    nb = {sc: len(S["schemes"][sc]["considered_bits"]) for sc in ("aux", "cod", "ofdm")}
+    P = S["P"]
+    out, pu, pi, pg = [], 0, 0, 0
+    for _ in range(reps):
+        d = {}
+        d["doppler_u"] = u[pu:pu + T * paths].reshape(T, paths, order="F"); pu += T * paths
+        d["phase_u"] = u[pu:pu + T * paths].reshape(T, paths, order="F"); pu += T * paths
+        for sc in ("aux", "cod", "ofdm"):
+            d["bits_" + sc] = i[pi:pi + nb[sc]].astype(np.uint8); pi += nb[sc]
+        d["pil_idx_fbmc"] = i[pi:pi + P].astype(np.int64) - 1; pi += P
+        d["pil_idx_ofdm"] = i[pi:pi + P].astype(np.int64) - 1; pi += P
+        nz = np.zeros((nS, N), dtype=complex)
+        for s_ in range(nS):
+            nz[s_] = g[pg:pg + N] + 1j * g[pg + N:pg + 2 * N]; pg += 2 * N
+        d["noise"] = nz
+        out.append(d)
+    assert (pu, pi, pg) == (len(u), len(i), len(g))            # the streams are consumed exactly
+    return out
+
+
+def test_reference_bundle_default_replays(ds_default):
+    """tests/golden/reference_bundle_default.mat (for matlab/verify_oracle.m): the committed replay streams, read back in
+    the reference's consumption order, reproduce the committed 24 BER arrays and end-of-script vectors."""
+    import os
+    import scipy.io
+    from oracle.ds import ds_realization, ber_arrays
+    S = ds_default
+    B = scipy.io.loadmat(os.path.join(os.path.dirname(__file__), "golden", "reference_bundle_default.mat"),
+                         squeeze_me=True, struct_as_record=False)
+    reps = int(B["overrides"].NrRepetitions)
+    assert list(B["overrides"].M_SNR_dB) == list(S["cfg"].M_SNR_dB) and B["overrides"].paper_block == 0
+    draws = _bundle_draws(B, S, reps)
+    res = [ds_realization(S, d, keep=(r == reps - 1)) for r, d in enumerate(draws)]
+    ber = ber_arrays(res, S)
+    assert len(ber) == 24
+    for name, arr in ber.items():
+        assert np.array_equal(arr, getattr(B["ber"], name).reshape(arr.shape)), name
+    last = res[-1]["inter"]
+    assert np.max(np.abs(last["hP_aux"][-1][-1] - B["last"].hP_est_FBMC_Aux_Temp)) < 1e-12
+    assert np.max(np.abs(np.diag(last["D_O"]) - B["last"].h_OFDM)) < 1e-12
+    assert np.max(np.abs(S["cod"].SIR_dB - B["setup"].SIR_dB_Cod)) < 1e-9
