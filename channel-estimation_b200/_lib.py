@@ -36,6 +36,9 @@ SIGNATURES = {
                                  C.c_double, C.c_double, c_int, c_int, vp]),
     "chest_set_snr": (c_int, [c_u64, c_int, vp]),
     "chest_set_mmse": (c_int, [c_u64, c_int, c_int, c_int, vp, vp, vp]),
+    "chest_setup_correlations": (c_int, [c_u64, c_int, c_int, vp, vp, C.c_double, vp, p_i64]),
+    "chest_build_mmse": (c_int, [c_u64, c_int, c_int, c_int, vp, C.c_double]),
+    "chest_release_setup": (c_int, [c_u64]),
     "chest_finalize": (c_int, [c_u64, c_int]),
     "chest_new_realization": (c_int, [c_u64, c_int, vp, vp]),
     "chest_new_realization_seeded": (c_int, [c_u64, c_int, c_u64, c_i64]),

@@ -113,6 +113,27 @@ class DeviceContext:
         val = _c(val)
         self._check(self.lib.chest_set_mmse(self._h, SCHEME_ID[name], variant, len(jc) - 1, _ptr(jc), _ptr(ir), _ptr(val)))
 
+    def setup_correlations(self, wf, pilot_pos, time_correlation, zero_threshold):
+        """DS.m:208-268 on the device: returns (R_hP, number of (i,j) with a non-zero row of R_Dij_hP); R_Dij_hP stays
+        on the device for build_mmse."""
+        pp = np.ascontiguousarray(pilot_pos, dtype=np.int32)
+        rt = np.ascontiguousarray(time_correlation, dtype=np.float64)
+        assert rt.shape == (2 * self.N - 1,)
+        R = np.zeros((len(pp), len(pp)), dtype=np.complex128)
+        n = C.c_int64(0)
+        self._check(self.lib.chest_setup_correlations(self._h, WF_ID[wf], len(pp), _ptr(pp), _ptr(rt), zero_threshold,
+                                                      _ptr(R), C.byref(n)))
+        return R.T.copy(), int(n.value)          # library writes column-major
+
+    def build_mmse(self, name, variant, R_inv, zero_threshold):
+        """W = R_Dij_hP * R_inv[snr] for every SNR point, thresholded, written as device tiles (DS.m:283-313).
+        R_inv: (n_snr, P, P) complex."""
+        Ri = _c(np.transpose(np.asarray(R_inv), (0, 2, 1)))      # per SNR column-major P x P
+        self._check(self.lib.chest_build_mmse(self._h, SCHEME_ID[name], variant, Ri.shape[0], _ptr(Ri), zero_threshold))
+
+    def release_setup(self):
+        self._check(self.lib.chest_release_setup(self._h))
+
     def finalize(self, max_batch):
         self._check(self.lib.chest_finalize(self._h, max_batch))
         self.max_batch = max_batch

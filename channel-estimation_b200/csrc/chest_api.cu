@@ -81,6 +81,9 @@ struct Waveform {
     DevBuf<int64_t> f_voff, f_yoff; DevBuf<int> f_rep; DevBuf<cplx> f_s, f_r;
     int f_cols = 0, perf_base = 0, perf_nblk = 0;
     int d_alloc_batch = 0;      // batch size D / HG1 / HG2 are allocated for (0: not yet)
+    // device-side setup (chest_setup_correlations): thresholded R_Dij_hP of all pilots, row-tile-major like D
+    DevBuf<cplx> Rsup; int rsup_P = 0; double rsup_thr = 0;
+    DevBuf<int> g_lo_d, g_hi_d;
     int tile = 64;              // CTA tile size of the GEMMs on this waveform (48 or 64)
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
 };
@@ -1103,6 +1106,135 @@ int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_
     CK(m.diag_frag.upload(dfrag, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     m.set = true; c->finalized = false;
+    return CHEST_OK;
+}
+
+// ---------------------------------------------------------------- setup on the device (DS.m:208-313)
+int chest_setup_correlations(uint64_t handle, int wfi, int n_pilots, const int32_t* pilot_pos, const double* time_corr,
+                             double zero_threshold, double* R_hP_out, int64_t* n_support) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG((wfi == 0 || wfi == 1) && c->wf[wfi].set && n_pilots >= 1 && n_pilots <= c->max_batch && pilot_pos && time_corr && R_hP_out);
+    CK(cudaSetDevice(c->device));
+    Waveform& w = c->wf[wfi];
+    const int N = c->N, K = w.K, T = c->T, P = n_pilots, max_delay = std::max(1, c->tap_delay.back());
+    const size_t RT8 = ((size_t)(K + 7) / 8) * 8, n_e = RT8 * K;
+    std::vector<int> pil(pilot_pos, pilot_pos + P);
+    for (int x : pil) ARG(x >= 0 && x < K);
+    std::vector<double> tp(T);
+    for (int t = 0; t < T; ++t) tp[t] = c->tap_amp[t] * c->tap_amp[t];
+    DevBuf<int> d_pil; DevBuf<double> d_rt, d_tp; DevBuf<cplx> corner, rhp;
+    cudaStream_t st = c->stream;
+    CK(d_pil.upload(pil, st)); CK(d_rt.upload(time_corr, (size_t)2 * N - 1, st)); CK(d_tp.upload(tp, st));
+    CK(w.g_lo_d.upload(w.g_lo, st)); CK(w.g_hi_d.upload(w.g_hi, st));
+    CK(corner.alloc((size_t)P * T * max_delay)); CK(rhp.alloc((size_t)P * P));
+    CK(cudaMemsetAsync(corner.p, 0, sizeof(cplx) * P * T * max_delay, st));
+    dim3 g1((N + 127) / 128, T, P);
+    k_pseudo_channel<<<g1, 128, 0, st>>>(c->h.p, corner.p, w.G.p, w.Q.p, d_pil.p, w.g_lo_d.p, w.g_hi_d.p, d_rt.p,
+                                         c->d_tap_delay.p, d_tp.p, N, T, max_delay);
+    c->launches++;
+    CK(cudaGetLastError());
+    c->cur_batch = P;
+    rc = stage_transmission_matrix(c, wfi, P, 0);                   // D_p = Q^H M_p G for every pilot: K1 + K2
+    if (rc) return rc;
+    CK(w.Rsup.alloc((size_t)P * n_e));
+    dim3 g2((unsigned)((n_e + 255) / 256), P);
+    k_rsup_finish<<<g2, 256, 0, st>>>(w.Rsup.p, w.D.p, corner.p, w.G.p, w.Q.p, c->d_tap_delay.p, N, K, T, max_delay, 0.0);
+    k_rhp_gather<<<P, ((P + 31) / 32) * 32, 0, st>>>(rhp.p, w.Rsup.p, d_pil.p, K, P);
+    k_rsup_finish<<<g2, 256, 0, st>>>(w.Rsup.p, w.Rsup.p, corner.p, w.G.p, w.Q.p, c->d_tap_delay.p, N, K, 0, max_delay, zero_threshold);
+    c->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(R_hP_out, rhp.p, sizeof(cplx) * P * P, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    w.rsup_P = P; w.rsup_thr = zero_threshold;
+    if (n_support) {                                                // entries of the K x K grid with any non-zero pilot weight
+        DevBuf<int> mask; DevBuf<cplx> eye;
+        CK(mask.alloc(n_e)); CK(cudaMemsetAsync(mask.p, 0, n_e * sizeof(int), st));
+        std::vector<cplx> id((size_t)P * P, cmake(0.0, 0.0));
+        for (int p = 0; p < P; ++p) id[(size_t)p * P + p] = cmake(1.0, 0.0);
+        CK(eye.upload(id, st));
+        dim3 g3((unsigned)((n_e * P + 255) / 256), 1);
+        k_w_mask<<<g3, 256, 0, st>>>(mask.p, w.Rsup.p, eye.p, K, P, 1e-300);
+        c->launches++;
+        std::vector<int> hm(n_e);
+        CK(cudaMemcpyAsync(hm.data(), mask.p, n_e * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int64_t cnt = 0;
+        for (int v : hm) cnt += v;
+        *n_support = cnt;
+    }
+    return CHEST_OK;
+}
+
+int chest_build_mmse(uint64_t handle, int si, int variant, int n_snr, const double* R_inv, double zero_threshold) {
+    Ctx* c = from(handle);
+    ARG(c && si >= 0 && si < 3 && (variant == 0 || variant == 1) && R_inv);
+    ARG(c->sch[si].set && n_snr == c->S);
+    CK(cudaSetDevice(c->device));
+    Scheme& s = c->sch[si];
+    Waveform& w = c->wf[s.waveform];
+    if (!w.Rsup.p || w.rsup_P != s.P) return fail(CHEST_ERR_STATE, "chest_build_mmse: call chest_setup_correlations for this waveform first");
+    MmseVariant& m = s.mm[variant];
+    const int K = s.K, P = s.P, P4 = (P + 3) / 4, RT = (K + 7) / 8, ND = 2 * K - 1;
+    const size_t n_e = (size_t)RT * 8 * K;
+    cudaStream_t st = c->stream;
+    DevBuf<cplx> rinv; DevBuf<int> mask;
+    CK(rinv.upload(reinterpret_cast<const cplx*>(R_inv), (size_t)n_snr * P * P, st));
+    CK(mask.alloc(n_e)); CK(cudaMemsetAsync(mask.p, 0, n_e * sizeof(int), st));
+    dim3 g1((unsigned)((n_e * P + 255) / 256), n_snr);
+    k_w_mask<<<g1, 256, 0, st>>>(mask.p, w.Rsup.p, rinv.p, K, P, zero_threshold);
+    c->launches++;
+    CK(cudaGetLastError());
+    std::vector<int> hm(n_e);
+    CK(cudaMemcpyAsync(hm.data(), mask.p, n_e * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // tile list: (row tile, diagonal offset) pairs with any surviving off-diagonal entry, offsets ascending per row tile
+    std::vector<char> lut((size_t)RT * ND, 0);
+    int64_t pairs = 0;
+    for (int rt = 0; rt < RT; ++rt)
+        for (int j = 0; j < K; ++j)
+            for (int r = 0; r < 8; ++r) {
+                const int i = rt * 8 + r;
+                if (i >= K || i == j || !hm[((size_t)rt * K + j) * 8 + r]) continue;
+                lut[(size_t)rt * ND + (j - i + K - 1)] = 1; ++pairs;
+            }
+    std::vector<int> tptr(RT + 1, 0), tdel, trt;
+    for (int rt = 0; rt < RT; ++rt) {
+        for (int d = 0; d < ND; ++d) if (lut[(size_t)rt * ND + d]) { tdel.push_back(d - (K - 1)); trt.push_back(rt); }
+        tptr[rt + 1] = (int)tdel.size();
+    }
+    m.n_tiles = (int)tdel.size(); m.nnz_offdiag_pairs = pairs;
+    if (tdel.empty()) { tdel.push_back(0); trt.push_back(0); }
+    DevBuf<int> d_trt;
+    CK(m.tile_ptr.upload(tptr, st)); CK(m.tile_delta.upload(tdel, st)); CK(d_trt.upload(trt, st));
+    m.frag.clear(); m.diag.clear(); m.frag.resize(n_snr); m.diag.resize(n_snr);
+    std::vector<WTiles> table(n_snr);
+    const size_t n_frag = (size_t)std::max(m.n_tiles, 1) * P4 * 32, n_dfrag = (size_t)RT * P4 * 32;
+    CK(m.diag_frag.alloc((size_t)n_snr * n_dfrag));
+    CK(cudaMemsetAsync(m.diag_frag.p, 0, sizeof(cplx) * n_snr * n_dfrag, st));
+    const int64_t n_thr = ((int64_t)m.n_tiles + RT) * 8 * P;
+    for (int snr = 0; snr < n_snr; ++snr) {
+        CK(m.frag[snr].alloc(n_frag)); CK(m.diag[snr].alloc((size_t)K * P));
+        CK(cudaMemsetAsync(m.frag[snr].p, 0, sizeof(cplx) * n_frag, st));
+        CK(cudaMemsetAsync(m.diag[snr].p, 0, sizeof(cplx) * K * P, st));
+        k_w_fill<<<(unsigned)((n_thr + 255) / 256), 256, 0, st>>>(m.frag[snr].p, m.diag[snr].p, m.diag_frag.p + (size_t)snr * n_dfrag,
+                                                                  w.Rsup.p, rinv.p + (size_t)snr * P * P, d_trt.p, m.tile_delta.p,
+                                                                  m.n_tiles, K, P, P4, zero_threshold);
+        c->launches++;
+        table[snr].frag = m.frag[snr].p; table[snr].diag = m.diag[snr].p;
+    }
+    CK(cudaGetLastError());
+    CK(m.table.upload(table, st));
+    CK(cudaStreamSynchronize(st));
+    m.set = true; c->finalized = false;
+    return CHEST_OK;
+}
+
+int chest_release_setup(uint64_t handle) {
+    Ctx* c = from(handle);
+    ARG(c);
+    CK(cudaSetDevice(c->device));
+    for (auto& w : c->wf) { w.Rsup.release(); w.rsup_P = 0; }
     return CHEST_OK;
 }
 

@@ -1575,6 +1575,123 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
     }
 }
 
+// ============================================================================ setup on the device (DS.m:208-313)
+// Pseudo-channel of pilot p (DS.m:213,260): M_p = reshape(R_vecH * kron(g_p.', q_p')', N, N) is banded like H, with
+//   M_p[a + m, a] = pdp_m * sum_a' rt[a - a'] * zeta_m[a'],   zeta_m[a'] = q_p[row(a')] * conj(g_p[col(a')])
+// where (row, col) = position of entry a'(N+1) + m of H(:) (FF.m:377: regular entries row = a' + m, col = a'; entries
+// running past the bottom of a column wrap to (a' + m - N, a' + 1), those beyond N^2 are cropped, FF.m:406).  Regular
+// entries go to h[p][tap][a + m] (the layout K1 / K2 read), wrapped ones to corner[p][tap][a + m - N].
+__global__ void k_pseudo_channel(cplx* __restrict__ h, cplx* __restrict__ corner, const cplx* __restrict__ G,
+                                 const cplx* __restrict__ Q, const int* __restrict__ pil, const int* __restrict__ g_lo,
+                                 const int* __restrict__ g_hi, const double* __restrict__ rt, const int* __restrict__ tap_delay,
+                                 const double* __restrict__ tap_pow, int N, int T, int max_delay) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, tap = blockIdx.y, p = blockIdx.z;
+    if (a >= N) return;
+    const int m = tap_delay[tap], sym = pil[p];
+    const cplx* q = Q + (int64_t)N * sym;
+    const cplx* g = G + (int64_t)N * sym;
+    const double* r0 = rt + (N - 1) + a;                       // rt[(N-1) + a - a']
+    cplx acc = cmake(0.0, 0.0);
+    const int lo = g_lo[sym], hi = min(g_hi[sym], N - m);       // regular a': a' + m < N, g[a'] != 0
+    for (int ap = lo; ap < hi; ++ap) {
+        const cplx z = cmulc(g[ap], q[ap + m]);                 // q * conj(g)
+        const double w = r0[-ap];
+        acc.x = fma(w, z.x, acc.x); acc.y = fma(w, z.y, acc.y);
+    }
+    for (int ap = max(N - m, 0); ap <= N - 2; ++ap) {           // wrapped a': row = a' + m - N, col = a' + 1
+        const cplx z = cmulc(g[ap + 1], q[ap + m - N]);
+        const double w = r0[-ap];
+        acc.x = fma(w, z.x, acc.x); acc.y = fma(w, z.y, acc.y);
+    }
+    const double pw = tap_pow[tap];
+    acc.x *= pw; acc.y *= pw;
+    if (a + m < N) h[((int64_t)p * T + tap) * N + a + m] = acc;
+    else if (a <= N - 2) corner[((int64_t)p * T + tap) * max_delay + (a + m - N)] = acc;
+    if (a < m) h[((int64_t)p * T + tap) * N + a] = cmake(0.0, 0.0);      // rows above the band start
+}
+
+// R[p][e] = D_p[e] + wrapped-entry contributions  v * conj(Q[r, i]) * G[c, j]  (exactness of FF.m:377), then the
+// |.| < thr -> 0 rule of DS.m:263-264.  Layout of D and R: row-tile-major [p][K/8][K][8].
+__global__ void k_rsup_finish(cplx* __restrict__ R, const cplx* __restrict__ D, const cplx* __restrict__ corner,
+                              const cplx* __restrict__ G, const cplx* __restrict__ Q, const int* __restrict__ tap_delay,
+                              int N, int K, int T, int max_delay, double thr) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    const int RT8 = ((K + 7) / 8) * 8;
+    if (e >= (int64_t)RT8 * K) return;
+    const int r8 = (int)(e & 7), j = (int)((e >> 3) % K), i = (int)((e >> 3) / K) * 8 + r8;
+    cplx v = D[(int64_t)p * RT8 * K + e];
+    if (i < K) {
+        for (int t = 0; t < T; ++t) {
+            const int m = tap_delay[t];
+            for (int r = 0; r + 2 <= m; ++r) {
+                const cplx cv = corner[((int64_t)p * T + t) * max_delay + r];
+                if (cv.x == 0.0 && cv.y == 0.0) continue;
+                const cplx qv = Q[(int64_t)N * i + r];
+                if (qv.x == 0.0 && qv.y == 0.0) continue;
+                const cplx gv = G[(int64_t)N * j + (N - m + r + 1)];
+                cfma(v, cmul(cv, cmake(qv.x, -qv.y)), gv);
+            }
+        }
+        if (hypot(v.x, v.y) < thr) v = cmake(0.0, 0.0);
+    } else v = cmake(0.0, 0.0);
+    R[(int64_t)p * RT8 * K + e] = v;
+}
+
+// R_hP[p'][p] = D_p[pil[p'], pil[p']] (DS.m:213), column-major P x P; before thresholding
+__global__ void k_rhp_gather(cplx* __restrict__ out, const cplx* __restrict__ R, const int* __restrict__ pil, int K, int P) {
+    const int pp = threadIdx.x, p = blockIdx.x;
+    if (pp >= P) return;
+    const int RT8 = ((K + 7) / 8) * 8, i = pil[pp];
+    out[pp + (int64_t)P * p] = R[(int64_t)p * RT8 * K + ((int64_t)(i >> 3) * K + i) * 8 + (i & 7)];
+}
+
+// W[(i,j), p'] = sum_p R_p[(i,j)] Rinv[p, p']  (DS.m:283-313: W = R_Dij_hP * pinv(R_hP_est)), |.| < thr -> 0.
+// pass A: mask[e] = 1 where any (snr, p') entry survives.  One thread per (entry e, p'), snr = blockIdx.y.
+__global__ void k_w_mask(int* __restrict__ mask, const cplx* __restrict__ R, const cplx* __restrict__ Rinv, int K, int P, double thr) {
+    const int RT8 = ((K + 7) / 8) * 8;
+    const int64_t n_e = (int64_t)RT8 * K;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pp = (int)(idx % P);
+    const int64_t e = idx / P;
+    if (e >= n_e) return;
+    const cplx* ri = Rinv + (int64_t)blockIdx.y * P * P + (int64_t)P * pp;
+    cplx w = cmake(0.0, 0.0);
+    bool any = false;
+    for (int p = 0; p < P; ++p) {
+        const cplx a = R[(int64_t)p * n_e + e];
+        if (a.x != 0.0 || a.y != 0.0) { any = true; cfma(w, a, ri[p]); }
+    }
+    if (any && !(hypot(w.x, w.y) < thr)) mask[e] = 1;
+}
+// pass B: fragments of one SNR point.  One thread per (tile t, row r, p'); the diagonal goes to dg / dfrag.
+__global__ void k_w_fill(cplx* __restrict__ frag, cplx* __restrict__ dg, cplx* __restrict__ dfrag, const cplx* __restrict__ R,
+                         const cplx* __restrict__ Rinv, const int* __restrict__ tile_rt, const int* __restrict__ tile_delta,
+                         int n_tiles, int K, int P, int P4, double thr) {
+    const int RT8 = ((K + 7) / 8) * 8;
+    const int64_t n_e = (int64_t)RT8 * K;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pp = (int)(idx % P), r = (int)((idx / P) & 7);
+    const int64_t t = idx / P / 8;
+    if (t >= n_tiles + (K + 7) / 8) return;
+    const bool diag = t >= n_tiles;                               // the last RT "tiles" are the diagonal
+    const int rt = diag ? (int)(t - n_tiles) : tile_rt[t];
+    const int i = rt * 8 + r, j = diag ? i : i + tile_delta[t];
+    if (i >= K || j < 0 || j >= K) return;
+    const int64_t e = ((int64_t)rt * K + j) * 8 + r;
+    const cplx* ri = Rinv + (int64_t)P * pp;
+    cplx w = cmake(0.0, 0.0);
+    for (int p = 0; p < P; ++p) {
+        const cplx a = R[(int64_t)p * n_e + e];
+        if (a.x != 0.0 || a.y != 0.0) cfma(w, a, ri[p]);
+    }
+    if (hypot(w.x, w.y) < thr) w = cmake(0.0, 0.0);
+    if (diag) {
+        dg[(int64_t)i * P + pp] = w;
+        dfrag[((int64_t)rt * P4 + (pp >> 2)) * 32 + r * 4 + (pp & 3)] = w;
+    } else frag[((int64_t)t * P4 + (pp >> 2)) * 32 + r * 4 + (pp & 3)] = w;
+}
+
 // ============================================================================ counter totals
 // tot[e] += sum_rep err[rep][e]  (e = (snr, it, scheme, csi, edge)): the per-GPU partial sums of the final reduce.
 // One block per counter; 64-bit totals (4096 realizations x 5504 bits already exceed 2^24 per batch).

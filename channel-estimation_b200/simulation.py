@@ -8,7 +8,10 @@ DS.m:322-345.  The setup's dominant contraction  R_Dij_hP(:,p) = vec(Q' M_p G)  
 same banded-operator GEMM as the hot path's D = Q' H G, so it runs through K2 on the GPU with the
 pseudo-channel M_p uploaded as an impulse response; everything else in the setup is small host
 linear algebra, as in the reference."""
+import time
+
 import numpy as np
+import scipy.sparse as sp
 
 from .channel import FastFading
 from .context import DeviceContext, SCHEME_ID
@@ -23,7 +26,11 @@ class DoublySelectiveSimulation:
                  L=24, F=15e3, SamplingRate=15e3 * 24, NrSubframes=1, QAM_ModulationOrder=256,
                  PilotToDataPowerOffset=2, PilotToDataPowerOffsetAux=4.685, NrIterations=4,
                  Velocity_kmh=500, PowerDelayProfile="VehicularA", DopplerModel="Jakes", Paths=200,
-                 schemes=("aux", "cod", "ofdm"), max_batch=256, device=0, seed=0, verbose=False):
+                 schemes=("aux", "cod", "ofdm"), max_batch=256, device=0, seed=0, verbose=False, setup="device"):
+        if setup not in ("device", "host"):
+            raise ValueError("setup must be 'device' (DS.m:208-313 on the GPU) or 'host' (NumPy, cross-check)")
+        self.setup_mode = setup
+        self.setup_times = {}
         self.p = dict(M_SNR_dB=tuple(M_SNR_dB), NrRepetitions=NrRepetitions, ZeroThresholdSparse=ZeroThresholdSparse,
                       L=L, F=F, SamplingRate=SamplingRate, NrSubframes=NrSubframes,
                       QAM_ModulationOrder=QAM_ModulationOrder, PilotToDataPowerOffset=PilotToDataPowerOffset,
@@ -47,8 +54,13 @@ class DoublySelectiveSimulation:
             print(*a, flush=True)
 
     # ------------------------------------------------------------------ DS.m:50-313
+    def _tick(self, key, t0):
+        self.setup_times[key] = self.setup_times.get(key, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     def _setup(self, max_batch):
         p, ctx = self.p, self.ctx
+        t0 = time.perf_counter()
         L, F, fs, nsf = p["L"], p["F"], p["SamplingRate"], p["NrSubframes"]
         self.FBMC = FBMC(L, 30 * nsf, F, fs, 0, False, "Hermite-OQAM", 8, 0, True)            # DS.m:51-62
         zg = ((self.FBMC.Nr["SamplesTotal"] - (_round_half_away((1 / 15e3 / 14) * fs) + _round_half_away(fs / 15e3))
@@ -106,6 +118,7 @@ class DoublySelectiveSimulation:
             s["considered_bits"] = np.repeat(cons, nb[s["const"]]).astype(np.uint8)
             s["nbits"] = nb[s["const"]]
         self.sch = sch
+        t0 = self._tick("modem_and_precoders_host", t0)
         # ---- channel, DS.m:176-186
         fD = p["Velocity_kmh"] / 3.6 * 2.5e9 / 2.998e8
         self.ChannelModel = chan = FastFading(fs, p["PowerDelayProfile"], N, fD, p["DopplerModel"], p["Paths"],
@@ -125,42 +138,82 @@ class DoublySelectiveSimulation:
         ctx.set_constellation("QAM", self.QAM.SymbolMapping, self.QAM.BitMapping)
         ctx.set_snr(self.Pn)
         ctx.finalize(max(P, 1))
-        # ---- correlation matrices (DS.m:208-268) and MMSE matrices (DS.m:277-313)
-        thr = 10.0 ** (-p["ZeroThresholdSparse"])
-        rt = chan.GetTimeCorrelation()[0]
-        taps = np.flatnonzero(pdp)
-        for w, d in wfs.items():
-            self._log("correlation matrices, waveform", w)
-            d["R_hP"], d["sup"], d["R_sup"] = self._pilot_correlations(d, pdp, taps, rt, thr, w)
+        t0 = self._tick("device_static_operands", t0)
         self.wfs = wfs
+        self._pdp, self._power_cache = pdp, {}
         for name, s in sch.items():
             d = wfs[s["wf"]]
             ctx.set_scheme(name, s["wf"], s["C"], d["pil"], s["data_pos"], s["kappa"], s["dpr"], s["detect"],
                            s["const"], s["considered_bits"])
-            GA = d["G"] @ s["C"]                                                               # DS.m:203-205
+        t0 = self._tick("device_schemes", t0)
+        self._estimator_setup(max_batch)
+
+    def set_velocity(self, Velocity_kmh):
+        """BASELINE.json config 4 (high-mobility sweep): only the time correlation R_t depends on the velocity
+        (FF.m:333), so modem matrices, precoders and every static device operand are kept; the correlation and MMSE
+        matrices (DS.m:208-313) are rebuilt on the device and the channel's Doppler shift is updated."""
+        p = self.p
+        p["Velocity_kmh"] = Velocity_kmh
+        fD = Velocity_kmh / 3.6 * 2.5e9 / 2.998e8
+        self.ChannelModel = FastFading(p["SamplingRate"], p["PowerDelayProfile"], self.N, fD, p["DopplerModel"],
+                                       p["Paths"], 1, 1, False, create_device=False)
+        self.ctx.set_channel(self.N, self._pdp, fD, self.ChannelModel.PHY["dt"], p["Paths"], p["DopplerModel"])
+        self.ctx.finalize(max(self.NrPilotSymbols, 1))
+        self.setup_times = {}
+        self._estimator_setup(self.max_batch_requested)
+
+    def _estimator_setup(self, max_batch):
+        """Correlation matrices (DS.m:208-268) and MMSE matrices (DS.m:277-313)."""
+        p, ctx, sch, wfs, pdp, P = self.p, self.ctx, self.sch, self.wfs, self._pdp, self.NrPilotSymbols
+        self.max_batch_requested = max_batch
+        t0 = time.perf_counter()
+        thr = 10.0 ** (-p["ZeroThresholdSparse"])
+        rt = self.ChannelModel.GetTimeCorrelation()[0]
+        taps = np.flatnonzero(pdp)
+        for w, d in wfs.items():
+            self._log("correlation matrices, waveform", w)
+            if self.setup_mode == "device":
+                d["R_hP"], d["n_sup"] = ctx.setup_correlations(w, d["pil"], rt, thr)
+            else:
+                d["R_hP"], d["sup"], d["R_sup"] = self._pilot_correlations(d, pdp, taps, rt, thr, w)
+        t0 = self._tick("correlations_%s" % self.setup_mode, t0)
+        for name, s in sch.items():
+            d = wfs[s["wf"]]
             R_nn = d["R_hP"].copy()
             qn = np.zeros(P)
             for ip in range(P):                                                                # DS.m:222-234
                 q = d["Q"][:, d["pil"][ip]]
-                R_nn[ip, ip] = self._pilot_power(q, GA, s["kappa"], pdp, taps, rt)
+                R_nn[ip, ip] = self._pilot_power(name, ip, q, s, d, pdp, taps, rt)
                 qn[ip] = np.real(np.vdot(q, q))
+            t0 = self._tick("pilot_power_host", t0)
             K2 = d["G"].shape[1] ** 2
             for variant in (0, 1):
-                jc, ir, val = [0], [], []
-                for pn in self.Pn:                                                             # DS.m:238-253,282-313
+                Rs = []
+                for pn in self.Pn:                                                             # DS.m:238-253,282-285
                     R = R_nn.copy()
                     R[np.arange(P), np.arange(P)] = np.diag(R_nn) + pn * qn / s["kappa"]
                     if variant == 1:
                         R = R - (R_nn - d["R_hP"])
-                    Wv = d["R_sup"] @ np.linalg.pinv(R)
-                    Wv[np.abs(Wv) < thr] = 0
-                    pi, ai = np.nonzero(Wv.T)
-                    ir.append(d["sup"][ai].astype(np.int64) + K2 * pi.astype(np.int64))
-                    val.append(Wv.T[pi, ai])
-                    jc.append(jc[-1] + len(ai))
-                ctx.set_mmse_arrays(name, variant, np.array(jc), np.concatenate(ir), np.concatenate(val))
+                    Rs.append(np.linalg.pinv(R))
+                t0 = self._tick("pinv_host", t0)
+                if self.setup_mode == "device":
+                    ctx.build_mmse(name, variant, np.stack(Rs), thr)                          # DS.m:283-313 on the GPU
+                else:
+                    jc, ir, val = [0], [], []
+                    for Ri in Rs:
+                        Wv = d["R_sup"] @ Ri
+                        Wv[np.abs(Wv) < thr] = 0
+                        pi, ai = np.nonzero(Wv.T)
+                        ir.append(d["sup"][ai].astype(np.int64) + K2 * pi.astype(np.int64))
+                        val.append(Wv.T[pi, ai])
+                        jc.append(jc[-1] + len(ai))
+                    ctx.set_mmse_arrays(name, variant, np.array(jc), np.concatenate(ir), np.concatenate(val))
+                t0 = self._tick("mmse_%s" % self.setup_mode, t0)
             s["R_hP_est_noNoise"] = R_nn
+        if self.setup_mode == "device":
+            ctx.release_setup()
         ctx.finalize(max_batch)
+        self._tick("finalize", t0)
         self.max_batch = max_batch
 
     @staticmethod
@@ -224,17 +277,36 @@ class DoublySelectiveSimulation:
         R_sup = np.stack([v[sup] for v in cols], axis=1)
         return R_hP, sup, R_sup
 
-    def _pilot_power(self, q, GA, kappa, pdp, taps, rt):
-        """abs(sum(sum((GA.'*(Temp*R_vecH*Temp')).*GA',2))) with Temp = kron(I, q')/sqrt(kappa), DS.m:224-233:
-        the total power received at one pilot position from all precoded unit-power symbols."""
+    def _pilot_power(self, name, ip, q, s, d, pdp, taps, rt):
+        """abs(sum(sum((GA.'*(Temp*R_vecH*Temp')).*GA',2))) with Temp = kron(I, q')/sqrt(kappa), GA = G*C, DS.m:203-205,
+        224-233: the total power received at one pilot position from all precoded unit-power symbols,
+            sum_m pdp_m / kappa * sum_{a,a'} R_t[a-a'] q[r_a] conj(q[r_a']) B[c_a', c_a],   B = GA GA^H.
+        B over the pilot's sample window depends on neither tap nor velocity: it is built once per (scheme, pilot) from
+        the sparse precoder and cached (a velocity sweep re-uses it)."""
         N = self.N
-        tot = 0.0
+        per_tap = []
+        X = []
         for m in taps:
             row, col, ok = self._positions(m)
             sel = np.flatnonzero(ok & (q[row] != 0))
-            U = np.conj(q[row[sel]])[:, None] * GA[col[sel], :]
+            per_tap.append((m, sel, row[sel], col[sel]))
+            X.append(col[sel])
+        key = (name, ip)
+        if key not in self._power_cache:
+            rows = np.unique(np.concatenate(X))
+            if "GA_sparse" not in s:
+                s["GA_sparse"] = sp.csr_matrix(sp.csr_matrix(d["G"]) @ sp.csc_matrix(s["C"]))   # DS.m:203-205
+            GAx = s["GA_sparse"][rows, :]
+            GAx = GAx[:, np.flatnonzero(np.diff(GAx.tocsc().indptr))].toarray()
+            self._power_cache[key] = (rows, GAx @ GAx.conj().T)
+        rows, B = self._power_cache[key]
+        pos = np.full(N, -1); pos[rows] = np.arange(len(rows))
+        tot = 0.0
+        for m, sel, r, c in per_tap:
+            qq = q[r]
             T = rt[(N - 1) + sel[:, None] - sel[None, :]]
-            tot = tot + pdp[m] / kappa * np.sum(np.conj(U) * (T @ U))
+            Bc = B[np.ix_(pos[c], pos[c])].T                                   # B[c_a', c_a] indexed [a, a']
+            tot = tot + pdp[m] / s["kappa"] * np.sum(T * (qq[:, None] * np.conj(qq)[None, :]) * Bc)
         return abs(tot)
 
     # ------------------------------------------------------------------ DS.m:350-565

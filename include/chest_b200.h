@@ -102,6 +102,21 @@ int chest_set_snr(uint64_t handle, int n_snr, const double* pn_time);
 int chest_set_mmse(uint64_t handle, int scheme, int variant, int n_snr,
                    const int64_t* jc, const int64_t* ir, const double* val);
 
+/* The same setup on the device (DS.m:208-313).  chest_setup_correlations needs a context finalized for at least
+ * n_pilots realizations: it synthesises the banded pseudo-channels M_p = reshape(R_vecH*kron(g_p.',q_p')',N,N) of all
+ * pilots from the time correlation (FF.m:321-340: 2N-1 real values, lag 0 at index N-1) and the power delay profile
+ * (FF.m:366-407, including the wrapped entries of FF.m:377), runs them through K1 + K2 (D_p = Q' M_p G, DS.m:260), returns
+ * R_hP = D_p(pilot, pilot) (DS.m:213; P x P complex, column-major) and keeps R_Dij_hP -- with the zero_threshold rule of
+ * DS.m:263-264 applied -- on the device.  n_support (may be NULL): number of (i,j) with a non-zero row of R_Dij_hP.
+ * chest_build_mmse then forms W = R_Dij_hP * R_inv for every SNR point (R_inv: n_snr matrices pinv(R_hP_est), P x P complex
+ * column-major, DS.m:283-285: P x P host work), applies the second threshold (DS.m:287-289) and writes the diagonal-tile
+ * format directly -- the (K^2 P) x n_snr sparse matrix never exists on the host.  It replaces chest_set_mmse.
+ * chest_release_setup frees R_Dij_hP (P x K^2 complex) once every scheme has its matrices. */
+int chest_setup_correlations(uint64_t handle, int waveform, int n_pilots, const int32_t* pilot_pos,
+                             const double* time_correlation, double zero_threshold, double* R_hP_out, int64_t* n_support);
+int chest_build_mmse(uint64_t handle, int scheme, int variant, int n_snr, const double* R_inv, double zero_threshold);
+int chest_release_setup(uint64_t handle);
+
 /* Allocate device state for batches of up to max_batch realizations.  Must follow the setters. */
 int chest_finalize(uint64_t handle, int max_batch);
 

@@ -198,7 +198,7 @@ def test_product_setup_and_loop_ofdm(ds_default, draws3):
     from chest_b200.simulation import DoublySelectiveSimulation
     from oracle.ds import ds_realization
     S = ds_default
-    sim = DoublySelectiveSimulation(schemes=("ofdm",), max_batch=8)
+    sim = DoublySelectiveSimulation(schemes=("ofdm",), max_batch=8, setup="host")
     w, wr = sim.wfs["O"], S["wf"]["O"]
     assert rel(w["R_hP"], wr["R_hP"]) < TOL
     assert np.array_equal(w["sup"], wr["sup"]) and rel(w["R_sup"], wr["R_sup"]) < TOL
@@ -218,7 +218,7 @@ def test_product_setup_fbmc_correlations(ds_default):
     (the reference's interferer selection is rounding-noise dependent at the default geometry)."""
     from chest_b200.simulation import DoublySelectiveSimulation
     S = ds_default
-    sim = DoublySelectiveSimulation(schemes=("aux", "cod"), max_batch=4, M_SNR_dB=(10, 40))
+    sim = DoublySelectiveSimulation(schemes=("aux", "cod"), max_batch=4, M_SNR_dB=(10, 40), setup="host")
     w, wr = sim.wfs["F"], S["wf"]["F"]
     assert rel(w["R_hP"], wr["R_hP"]) < TOL
     common = np.intersect1d(w["sup"], wr["sup"])

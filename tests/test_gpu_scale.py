@@ -252,3 +252,64 @@ def test_figure5_statistical_pin():
     assert min(min(v) for v in report.values()) > 0.0130
     print("figure 5 read-offs vs this run:", report)
     sim.close()
+
+
+def test_device_setup_equals_host_setup(ds_default):
+    """DS.m:208-313 on the device (chest_setup_correlations + chest_build_mmse: pseudo-channels,
+    K1 + K2 for all pilots, both 1e-8 thresholds, W written straight into the diagonal-tile format) against the NumPy
+    setup feeding chest_set_mmse, and against the oracle: same R_hP, same support size, same tiles (bytes streamed per
+    launch), D-hat within 1e-11 for random pilot estimates, identical error counts."""
+    from chest_b200.simulation import DoublySelectiveSimulation
+    S = ds_default
+    dev = DoublySelectiveSimulation(max_batch=16, M_SNR_dB=(10, 25, 40), seed=2)
+    host = DoublySelectiveSimulation(max_batch=16, M_SNR_dB=(10, 25, 40), seed=2, setup="host")
+    for wf in ("F", "O"):
+        assert np.max(np.abs(dev.wfs[wf]["R_hP"] - S["wf"][wf]["R_hP"])) < 1e-11
+        assert np.max(np.abs(dev.wfs[wf]["R_hP"] - host.wfs[wf]["R_hP"])) < 1e-12
+        assert dev.wfs[wf]["n_sup"] == len(host.wfs[wf]["sup"])
+    assert dev.wfs["F"]["n_sup"] == len(S["wf"]["F"]["sup"]) or abs(dev.wfs["F"]["n_sup"] - len(S["wf"]["F"]["sup"])) < 50
+    wd, wh = dev.ctx.work_model(4), host.ctx.work_model(4)
+    assert wd["w_bytes_per_ic_launch"] == wh["w_bytes_per_ic_launch"] and wd["est_main_flops"] == wh["est_main_flops"]
+    rng = np.random.default_rng(1)
+    for name in ("aux", "cod", "ofdm"):
+        for variant in (0, 1):
+            for isnr in (0, 2):
+                hP = rng.standard_normal(16) + 1j * rng.standard_normal(16)
+                Da, ha = dev.ctx.estimate(name, variant, isnr, hP)
+                Db, hb = host.ctx.estimate(name, variant, isnr, hP)
+                assert np.max(np.abs(Da - Db)) < 1e-11 * np.max(np.abs(Db)) and np.max(np.abs(ha - hb)) < 1e-11
+    _, ea = dev.run(NrRepetitions=5, seed=2, first_rep=40)
+    _, eb = host.run(NrRepetitions=5, seed=2, first_rep=40)
+    assert np.array_equal(ea, eb)
+    print("setup times, device path:", {k: round(v, 3) for k, v in dev.setup_times.items()})
+    print("setup times, host path  :", {k: round(v, 3) for k, v in host.setup_times.items()})
+    # velocity change (BASELINE.json config 4): only R_t changes; the device re-setup equals a fresh simulation
+    dev.set_velocity(120)
+    fresh = DoublySelectiveSimulation(max_batch=16, M_SNR_dB=(10, 25, 40), seed=2, Velocity_kmh=120)
+    _, ea = dev.run(NrRepetitions=3, seed=2, first_rep=7)
+    _, eb = fresh.run(NrRepetitions=3, seed=2, first_rep=7)
+    assert np.array_equal(ea, eb)
+    print("re-setup after a velocity change:", {k: round(v, 3) for k, v in dev.setup_times.items()})
+    for s in (dev, host, fresh):
+        s.close()
+
+
+def test_device_setup_paper_geometry_wrapped_entries(ds_paper):
+    """Paper geometry: taps at delays 0,1,2,3,5,7 -> R_vecH has wrapped entries (FF.m:377,406) that fall outside the band
+    of the pseudo-channels; the device adds them as rank-one terms.  R_hP and W-hat (through chest_estimate) against the
+    oracle's setup."""
+    from chest_b200.simulation import DoublySelectiveSimulation
+    from oracle.ds import _dhat
+    S = ds_paper
+    sim = DoublySelectiveSimulation.paper(M_SNR_dB=(20, 32), schemes=("ofdm",), max_batch=4)
+    assert np.max(np.abs(sim.wfs["O"]["R_hP"] - S["wf"]["O"]["R_hP"])) < 1e-10
+    rng = np.random.default_rng(2)
+    m, w = S["schemes"]["ofdm"], S["wf"]["O"]
+    for variant, key in ((0, "W"), (1, "W_noInt")):
+        hP = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+        D_ref, h_ref = _dhat(w, m[key][1], hP, faithful=False)
+        D, hd = sim.ctx.estimate("ofdm", variant, 1, hP)
+        assert np.max(np.abs(D - D_ref.toarray())) < 1e-9 * np.max(np.abs(h_ref))
+        assert np.max(np.abs(hd - h_ref)) < 1e-9 * np.max(np.abs(h_ref))
+    print("paper geometry (OFDM only) setup times:", {k: round(v, 3) for k, v in sim.setup_times.items()})
+    sim.close()
