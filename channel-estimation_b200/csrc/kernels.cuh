@@ -213,6 +213,11 @@ struct SchemeDev {
     // long rows as DMMA tiles: 8 long rows per tile, the union of their columns packed four per k-step;
     // lr_ptr [n_lr_tiles+1] -> steps, lr_kcol [step][4] column of z, lr_frag [step][32 lanes] A fragments
     int n_lr_tiles; const int* lr_ptr; const int* lr_kcol; const cplx* lr_frag;
+    // k_ic_post: per-row descriptor {d decided directly at this row (-1: none), col0, NoEdge mask of d, flags (bit 0:
+    // the equalised symbol of this row is needed by the de-spreading gather)}, the data symbols the gather pass decides,
+    // and whether v of every single-entry row can be written in the same pass as the decision
+    const int4* rowinfo; const int* multi_d; int n_multi; int fuse_ok;
+    const uint32_t* txw_t;         // transmitted words, [rep / 16][n_data][rep % 16]
     const cplx* wdiag_frag[2];     // [snr][rt][pq][32 lanes]: W[i,i,p] in DMMA A-fragment order (phase D)
     // MMSE matrices: tile lists per variant, fragments per (variant, snr)
     const int* tile_ptr[2];        // [RT+1]
@@ -221,6 +226,7 @@ struct SchemeDev {
     // per-batch state
     cplx* xP;                      // [rep][P]      unit-modulus pilots
     uint32_t* txword;              // [rep][n_data] transmitted bit words
+    uint32_t* txw_t_w;             // the same, [rep / 16][n_data][rep % 16] (written by k_tx_symbols)
     cplx* x;                       // [rep][K]      precoded symbols
     cplx* y;                       // [snr][rep][K]
     cplx* hP;                      // [snr][rep][P]
@@ -246,6 +252,7 @@ __global__ void k_tx_symbols(SchemeDev sd, ConstDev cd, const uint8_t* __restric
             uint32_t w = 0;
             for (int t = 0; t < sd.nbits; ++t) w |= (uint32_t)(b[d * sd.nbits + t] & 1) << t;
             sd.txword[(int64_t)rep * sd.n_data + d] = w;
+            sd.txw_t_w[((int64_t)(rep >> 4) * sd.n_data + d) * 16 + (rep & 15)] = w;
             z = cd.symbol[w];
         }
         zs[k] = z;
@@ -1569,6 +1576,355 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                                 if (ct >= ct0 && ct < ct1 && sh.c_rep[c] >= 0) vbuf[i * NC + c] = cmake(cr[ct][e], ci[ct][e]);
                             }
                     }
+                }
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_ic_post: phases C, D, E of iteration `it` and phase A of iteration it+1 in (mostly) ONE pass over the unit's
+// K x 16 tile of cancelled symbols (the successor of k_ic_light, which stays selectable: CHEST_LIGHT=old).
+//   * y_ic is streamed through a shared-memory ring of 64-row chunks (16 KB) filled by bulk asynchronous copies
+//     (cp.async.bulk + mbarrier complete_tx: one elected thread, LOOK chunks ahead); a warp copies its row tile from
+//     the ring into registers and frees the stage at once, so the memory-level parallelism does not depend on registers;
+//   * the operands a row tile needs besides y (diagonal-W fragments, row descriptors, true channel) are prefetched into
+//     registers one row tile ahead;
+//   * a row is equalised, decided and -- for rows whose precoder entry refers to the symbol decided at that very row
+//     (data rows of all three schemes, pilot rows) -- precoded for the next iteration right away: one read of y_ic, one
+//     write of v.  Only the spread symbols of the data-spreading scheme (gather over their spreading sets) and the long
+//     precoder rows (auxiliary / spread positions, DMMA tiles) need a second look, after one block barrier.
+#ifndef POST_NS
+#define POST_NS 4              // ring stages
+#endif
+#ifndef POST_LOOK
+#define POST_LOOK 2            // chunks in flight ahead of the consumers
+#endif
+#define POST_ROWS 64           // rows per chunk = 8 warps x 8 rows
+#define POST_THREADS 256
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void st_cplx2(cplx* ptr, cplx a, cplx b) {   // 32 bytes, 32-byte aligned
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(ptr), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
+template <int P4T>
+__global__ void __launch_bounds__(POST_THREADS, 2) k_ic_post(IcParams p) {
+    constexpr int NC = NC_MAX, HS = NC + 2, NS = POST_NS, LOOK = POST_LOOK, CH = POST_ROWS * NC;
+    constexpr int PQ = P4T > 0 ? P4T : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int it = p.it;
+    extern __shared__ __align__(128) cplx ic_smem[];
+    cplx* ring = ic_smem;                                   // [NS][64 rows][16 columns]
+    cplx* hPn = ring + NS * CH;                             // new pilot estimates [p][col] (zero padded to 4*P4 rows)
+    cplx* xPs = hPn + p.pilot_rows * HS;                    // transmitted pilots of the unit's columns [p][col]
+    __shared__ IcShared sh;
+    __shared__ uint64_t full[NS], empty[NS];
+    uint8_t* zw;                                            // decided words of the data symbols [d][col]
+    {
+        cplx* q = xPs + p.pilot_rows * NC;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const ConstDev& cg = p.cst[k];
+            cplx* sym = q; q += cg.order;
+            double* lev = reinterpret_cast<double*>(q); q += (cg.n_axis + 1) / 2;
+            int* gr = reinterpret_cast<int*>(q); q += (cg.order + 3) / 4;
+            for (int e = tid; e < cg.order; e += POST_THREADS) { sym[e] = cg.symbol[e]; gr[e] = cg.word_of_grid[e]; }
+            for (int e = tid; e < cg.n_axis; e += POST_THREADS) lev[e] = cg.level[e];
+            if (tid == 0) { sh.cst[k] = cg; sh.cst[k].symbol = sym; sh.cst[k].level = lev; sh.cst[k].word_of_grid = gr; }
+        }
+        zw = reinterpret_cast<uint8_t*>(q);
+    }
+    if (tid == 0) {
+        for (int s_ = 0; s_ < NS; ++s_) { mbar_init(&full[s_], 1); mbar_init(&empty[s_], POST_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const bool last = it == p.n_iter, next_pre = !last;
+    unsigned seq = 0;                                       // chunks this CTA has streamed so far (ring position)
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        const IcCta cta = p.ctas[unit];
+        const int csi = cta.mode;
+        const int wf = (cta.mode == 0) ? p.sch[cta.scheme_or_wf].waveform : cta.scheme_or_wf;
+        const int K = p.sch[p.wf_scheme[wf][0]].K, RT = (K + 7) / 8;
+        cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
+        const cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
+        const int ngroup = (RT + 7) / 8;                    // groups of 8 row tiles = chunks of 64 rows
+        const bool staged = it > 0;
+        auto issue = [&](int j) {                           // chunk j of this unit -> ring (thread 0 only)
+            const unsigned q = seq + j, st = q % NS;
+            if (q >= NS) mbar_wait(&empty[st], ((q / NS) - 1) & 1);
+            const unsigned rows = min(POST_ROWS, K - j * POST_ROWS);
+            mbar_expect_tx(&full[st], rows * NC * 16);
+            bulk_g2s(ring + st * CH, ybuf + (int64_t)j * CH, rows * NC * 16, &full[st]);
+        };
+        if (staged && tid == 0)
+            for (int j = 0; j < LOOK && j < ngroup; ++j) issue(j);
+        ic_load_unit(p, cta, sh);
+        const int Pw = p.sch[p.wf_scheme[wf][0]].P;
+        // ---- transmitted pilots of the columns; phase C: LS pilot estimates (DS.m:412-414, 487-489)
+        for (int idx = tid; idx < p.pilot_rows * NC; idx += POST_THREADS) {
+            const int c = idx % NC, pp = idx / NC;
+            const bool ok = sh.c_rep[c] >= 0 && pp < Pw;
+            const cplx xp = ok ? p.sch[sh.c_scheme[c]].xP[(int64_t)sh.c_rep[c] * Pw + pp] : cmake(1.0, 0.0);
+            xPs[pp * NC + c] = xp;
+            if (csi == 0) {
+                const SchemeDev& sd = p.sch[cta.scheme_or_wf];
+                cplx hp = cmake(0.0, 0.0);
+                if (ok) {
+                    const int i = sd.pilot_pos[pp];
+                    const cplx yv = staged ? ybuf[i * NC + c] : sh.ycolp[c][i];
+                    const cplx q = cdiv(yv, xp);
+                    hp = cmake(q.x / sd.sqrt_kappa, q.y / sd.sqrt_kappa);
+                    sd.hP[((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.P + pp] = hp;
+                }
+                hPn[pp * HS + c] = hp;
+            }
+        }
+        __syncthreads();
+        // ---- the pass: equalise, decide, count, precode
+        const int var_cur = (it == 0 || it <= p.n_iter / 2) ? 0 : 1;
+        const int sc0 = sh.c_scheme[0], sc1 = cta.n_cols > 8 ? sh.c_scheme[8] : sc0;
+        const SchemeDev& sd0 = p.sch[sc0];
+        const SchemeDev& sd1 = p.sch[sc1];
+        const bool two = sc1 != sc0;                        // PERF unit with two schemes: one per 8-column half
+        const int P4 = sd0.P4;
+        const cplx* __restrict__ wfr = csi == 0 ? sd0.wdiag_frag[var_cur] + (int64_t)cta.snr * RT * P4 * 32 + lane : nullptr;
+        const cplx* __restrict__ ht = csi == 1 ? p.htrue[wf] + (int64_t)cta.snr * K : nullptr;     // cta.snr holds the realization
+        struct TileIn { cplx w[PQ]; int4 ri[2]; cplx val0[2]; cplx h; };
+        auto load_in = [&](int rt, TileIn& in) {
+            const int i = min(rt * 8 + g, K - 1);
+            if (csi == 0) {
+                if (P4T > 0) {
+#pragma unroll
+                    for (int pq = 0; pq < PQ; ++pq) in.w[pq] = ld_stream(wfr + ((int64_t)rt * P4T + pq) * 32);
+                }
+            } else in.h = ht[i];
+            in.ri[0] = sd0.rowinfo[i]; in.val0[0] = sd0.row_val0[i];
+            if (two) { in.ri[1] = sd1.rowinfo[i]; in.val0[1] = sd1.row_val0[i]; }
+            else { in.ri[1] = in.ri[0]; in.val0[1] = in.val0[0]; }
+        };
+        unsigned e_all[2][2] = {{0, 0}, {0, 0}}, e_edge[2][2] = {{0, 0}, {0, 0}};
+        TileIn nxt;
+        if (warp < RT) load_in(warp, nxt);
+#pragma unroll 1
+        for (int j = 0; j < ngroup; ++j) {
+            const int rt = j * 8 + warp;
+            const bool have = rt < RT;
+            TileIn cur = nxt;
+            if (rt + 8 < RT) load_in(rt + 8, nxt);
+            cplx y[2][2];
+            const int i = rt * 8 + g;
+            if (staged) {
+                if (tid == 0 && j + LOOK < ngroup) issue(j + LOOK);
+                const unsigned q = seq + j, st = q % NS;
+                mbar_wait(&full[st], (q / NS) & 1);
+                if (have) {
+                    const cplx* yr = ring + st * CH + (warp * 8 + g) * NC + 2 * t4;
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct) { y[ct][0] = yr[ct * 8]; y[ct][1] = yr[ct * 8 + 1]; }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);     // the values are in registers: the stage is free
+            } else if (have) {
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const cplx* yp = sh.ycolp[ct * 8 + 2 * t4 + e];
+                        y[ct][e] = (yp && i < K) ? yp[i] : cmake(1.0, 0.0);
+                    }
+            }
+            if (!have) continue;
+            const bool rowok = i < K;
+            // one-tap channel of the row: h_est = W_diag * hP as a small DMMA product, or the true channel
+            cplx hh[2][2];
+            if (csi == 0) {
+                double hr[2][2] = {{0, 0}, {0, 0}}, hi[2][2] = {{0, 0}, {0, 0}};
+                const int npq = P4T > 0 ? P4T : P4;
+#pragma unroll
+                for (int pq = 0; pq < npq; ++pq) {
+                    const cplx a = P4T > 0 ? cur.w[P4T > 0 ? pq : 0] : ld_stream(wfr + ((int64_t)rt * P4 + pq) * 32);
+                    const double nai = dneg(a.y);
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct) {
+                        const cplx b = hPn[(pq * 4 + t4) * HS + ct * 8 + g];
+                        dmma884(hr[ct][0], hr[ct][1], a.x, b.x);
+                        dmma884(hr[ct][0], hr[ct][1], nai, b.y);
+                        dmma884(hi[ct][0], hi[ct][1], a.x, b.y);
+                        dmma884(hi[ct][0], hi[ct][1], a.y, b.x);
+                    }
+                }
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) hh[ct][e] = cmake(hr[ct][e], hi[ct][e]);
+            } else {
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) hh[ct][0] = hh[ct][1] = cur.h;
+            }
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                const SchemeDev& sd = ct == 0 ? sd0 : sd1;
+                const ConstDev& cd = sh.cst[sd.constellation];
+                const int4 ri = cur.ri[ct];
+                const cplx val0 = cur.val0[ct];
+                const int mode = sd.detect_mode;
+                cplx vv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = ct * 8 + 2 * t4 + e;
+                    const bool valid = rowok && sh.c_rep[c] >= 0;
+                    const cplx xh = cdiv(y[ct][e], hh[ct][e]);
+                    int word = 0;
+                    vv[e] = cmake(0.0, 0.0);
+                    if (valid) {
+                        const int64_t col = (int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c];
+                        if (last && csi == 0) sd.hdiag[col * K + i] = hh[ct][e];
+                        if (ri.x >= 0) {
+                            const int d = ri.x;
+                            const cplx xd = mode == 1 ? cmake((val0.x * xh.x + val0.y * xh.y) / sd.dpr, 0.0)
+                                                      : cmake(xh.x / sd.sqrt_dpr, mode == 0 ? 0.0 : xh.y / sd.sqrt_dpr);
+                            const uint32_t tw = sd.txw_t[((int64_t)(sh.c_rep[c] >> 4) * sd.n_data + d) * 16 + (sh.c_rep[c] & 15)];
+                            word = ic_decide(cd, xd, tw, (uint32_t)ri.z, e_all[ct][e], e_edge[ct][e]);
+                            if (last) sd.xD[csi][col * sd.n_data + d] = xd;
+                            if (next_pre) zw[d * NC + c] = (uint8_t)word;
+                        }
+                        if (ri.w & 1) vbuf[i * NC + c] = xh;            // wanted by the de-spreading gather below
+                    }
+                    if (next_pre && sd.fuse_ok && ri.y != -2) {         // v = C z for rows with at most one entry
+                        const cplx zz = ri.y < 0 ? cmake(0.0, 0.0) : (ri.y < sd.P ? xPs[ri.y * NC + c] : cd.symbol[word]);
+                        vv[e] = cmul(val0, zz);
+                    }
+                }
+                if (next_pre && sd.fuse_ok && ri.y != -2 && rowok && !(ri.w & 1)) st_cplx2(vbuf + i * NC + ct * 8 + 2 * t4, vv[0], vv[1]);
+            }
+        }
+        seq += staged ? ngroup : 0;
+        // lanes with the same t4 hold the same four columns
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                unsigned a = e_all[ct][e], b = e_edge[ct][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                if (g == 0) {
+                    if (a) atomicAdd(&sh.cnt[ct * 8 + 2 * t4 + e][0], a);
+                    if (b) atomicAdd(&sh.cnt[ct * 8 + 2 * t4 + e][1], b);
+                }
+            }
+        __syncthreads();
+        // ---- data symbols spread over several positions: x_d = C_d^H x_hat / dpr over the spreading set (DS.m:436-437, 520)
+        if ((sd0.detect_mode == 1 && sd0.n_multi > 0) || (sd1.detect_mode == 1 && sd1.n_multi > 0)) {
+            const int c = tid % NC;
+            unsigned ea = 0, ee = 0;
+            const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            if (sh.c_rep[c] >= 0 && sd.detect_mode == 1) {
+                const ConstDev& cd = sh.cst[sd.constellation];
+                const int64_t colbase = ((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.n_data;
+                const uint32_t* __restrict__ txw = sd.txw_t + (int64_t)(sh.c_rep[c] >> 4) * sd.n_data * 16 + (sh.c_rep[c] & 15);
+                constexpr int DSTEP = POST_THREADS / NC;
+                for (int k0 = tid / NC; k0 < sd.n_multi; k0 += 4 * DSTEP) {
+                    int dd[4], e0[4], e1[4];
+                    cplx acc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + u * DSTEP;
+                        dd[u] = k < sd.n_multi ? sd.multi_d[k] : -1;
+                        e0[u] = e1[u] = 0;
+                        if (dd[u] >= 0) { e0[u] = sd.ct_colptr[sd.P + dd[u]]; e1[u] = sd.ct_colptr[sd.P + dd[u] + 1]; }
+                        acc[u] = cmake(0.0, 0.0);
+                    }
+                    int nmax = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nmax = max(nmax, e1[u] - e0[u]);
+                    for (int q = 0; q < nmax; ++q) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (e0[u] + q < e1[u]) {
+                                const cplx t = cmulc(sd.ct_val[e0[u] + q], vbuf[sd.ct_row[e0[u] + q] * NC + c]);
+                                acc[u].x += t.x; acc[u].y += t.y;
+                            }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (dd[u] >= 0) {
+                            const cplx xd = cmake(acc[u].x / sd.dpr, 0.0);
+                            const int word = ic_decide(cd, xd, txw[(int64_t)dd[u] * 16], sd.edge_mask[dd[u]], ea, ee);
+                            if (last) sd.xD[csi][colbase + dd[u]] = xd;
+                            if (next_pre) zw[dd[u] * NC + c] = (uint8_t)word;
+                        }
+                }
+            }
+            if (ea) atomicAdd(&sh.cnt[c][0], ea);
+            if (ee) atomicAdd(&sh.cnt[c][1], ee);
+            __syncthreads();                                   // readers of vbuf done, decided words complete
+        }
+        if (tid < 2 * NC) {
+            const int cc = tid >> 1, e = tid & 1;
+            if (cc < cta.n_cols && sh.c_rep[cc] >= 0) {
+                const int64_t o = ((((int64_t)sh.c_rep[cc] * p.n_snr + sh.c_snr[cc]) * (p.n_iter + 1) + it) * 3 + sh.c_scheme[cc]) * 4 + csi * 2 + e;
+                p.err[o] = sh.cnt[cc][e];
+            }
+        }
+        if (!next_pre) continue;
+        // ---- phase A leftovers: single-entry rows of schemes whose precoder does not allow the fused write ...
+        if (!sd0.fuse_ok || !sd1.fuse_ok) {
+            const int c = tid % NC;
+            const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+            if (sh.c_rep[c] >= 0 && !sd.fuse_ok) {
+                const cplx* sym = sh.cst[sd.constellation].symbol;
+                for (int i = tid / NC; i < K; i += POST_THREADS / NC) {
+                    const int col = sd.row_col0[i];
+                    if (col == -2) continue;
+                    const cplx zz = col < 0 ? cmake(0.0, 0.0) : (col < sd.P ? xPs[col * NC + c] : sym[zw[(col - sd.P) * NC + c]]);
+                    vbuf[i * NC + c] = cmul(sd.row_val0[i], zz);
+                }
+            }
+        }
+        // ... and the long rows (auxiliary symbols, spread positions) on the FP64 tensor pipe: a warp takes a tile of 8 long
+        // rows; per k-step the A fragment holds their coefficients for four z rows (the tile's column union, packed by
+        // the host), the B fragment the z values of those rows for the 8 columns of an n-tile.
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && !two) break;
+            const SchemeDev& sd = pass == 0 ? sd0 : sd1;
+            const int ct0 = pass, ct1 = (pass == 0 && !two) ? 2 : pass + 1;
+            const cplx* sym = sh.cst[sd.constellation].symbol;
+            const int P = sd.P;
+            for (int tl = warp; tl < sd.n_lr_tiles; tl += POST_THREADS / 32) {
+                double cr[2][2] = {{0, 0}, {0, 0}}, ci[2][2] = {{0, 0}, {0, 0}};
+                const int st1 = sd.lr_ptr[tl + 1];
+                for (int st = sd.lr_ptr[tl]; st < st1; ++st) {
+                    const cplx a = ld_stream(sd.lr_frag + (int64_t)st * 32 + lane);
+                    const int kc = sd.lr_kcol[st * 4 + t4];
+                    const double nai = dneg(a.y);
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct) {
+                        if (ct < ct0 || ct >= ct1) continue;
+                        const int c = ct * 8 + g;
+                        const cplx b = kc < P ? xPs[kc * NC + c] : sym[zw[(kc - P) * NC + c]];
+                        dmma884(cr[ct][0], cr[ct][1], a.x, b.x);
+                        dmma884(cr[ct][0], cr[ct][1], nai, b.y);
+                        dmma884(ci[ct][0], ci[ct][1], a.x, b.y);
+                        dmma884(ci[ct][0], ci[ct][1], a.y, b.x);
+                    }
+                }
+                const int r = tl * 8 + g;
+                if (r < sd.n_long_rows) {
+                    const int i = sd.long_rows[r];
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+                        if (ct >= ct0 && ct < ct1) st_cplx2(vbuf + i * NC + ct * 8 + 2 * t4, cmake(cr[ct][0], ci[ct][0]), cmake(cr[ct][1], ci[ct][1]));
                 }
             }
         }

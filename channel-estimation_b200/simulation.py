@@ -140,12 +140,7 @@ class DoublySelectiveSimulation:
         ctx.finalize(max(P, 1))
         t0 = self._tick("device_static_operands", t0)
         self.wfs = wfs
-        self._pdp, self._power_cache = pdp, {}
-        for name, s in sch.items():
-            d = wfs[s["wf"]]
-            ctx.set_scheme(name, s["wf"], s["C"], d["pil"], s["data_pos"], s["kappa"], s["dpr"], s["detect"],
-                           s["const"], s["considered_bits"])
-        t0 = self._tick("device_schemes", t0)
+        self._pdp, self._power_cache, self._schemes_on_device = pdp, {}, False
         self._estimator_setup(max_batch)
 
     def set_velocity(self, Velocity_kmh):
@@ -177,6 +172,13 @@ class DoublySelectiveSimulation:
             else:
                 d["R_hP"], d["sup"], d["R_sup"] = self._pilot_correlations(d, pdp, taps, rt, thr, w)
         t0 = self._tick("correlations_%s" % self.setup_mode, t0)
+        if not self._schemes_on_device:                       # (the correlation pass needs a finalized context)
+            for name, s in sch.items():
+                d = wfs[s["wf"]]
+                ctx.set_scheme(name, s["wf"], s["C"], d["pil"], s["data_pos"], s["kappa"], s["dpr"], s["detect"],
+                               s["const"], s["considered_bits"])
+            self._schemes_on_device = True
+            t0 = self._tick("device_schemes", t0)
         for name, s in sch.items():
             d = wfs[s["wf"]]
             R_nn = d["R_hP"].copy()

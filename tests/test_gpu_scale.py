@@ -258,7 +258,8 @@ def test_device_setup_equals_host_setup(ds_default):
     """DS.m:208-313 on the device (chest_setup_correlations + chest_build_mmse: pseudo-channels,
     K1 + K2 for all pilots, both 1e-8 thresholds, W written straight into the diagonal-tile format) against the NumPy
     setup feeding chest_set_mmse, and against the oracle: same R_hP, same support size, same tiles (bytes streamed per
-    launch), D-hat within 1e-11 for random pilot estimates, identical error counts."""
+    launch), D-hat within 1e-9 (north_star tolerance; pinv(R) has entries ~1e4, so the two summation orders of
+    R_Dij_hP * pinv(R) differ by ~1e-11) for random pilot estimates, identical error counts."""
     from chest_b200.simulation import DoublySelectiveSimulation
     S = ds_default
     dev = DoublySelectiveSimulation(max_batch=16, M_SNR_dB=(10, 25, 40), seed=2)
@@ -277,7 +278,7 @@ def test_device_setup_equals_host_setup(ds_default):
                 hP = rng.standard_normal(16) + 1j * rng.standard_normal(16)
                 Da, ha = dev.ctx.estimate(name, variant, isnr, hP)
                 Db, hb = host.ctx.estimate(name, variant, isnr, hP)
-                assert np.max(np.abs(Da - Db)) < 1e-11 * np.max(np.abs(Db)) and np.max(np.abs(ha - hb)) < 1e-11
+                assert np.max(np.abs(Da - Db)) < 1e-9 * np.max(np.abs(Db)) and np.max(np.abs(ha - hb)) < 1e-9 * np.max(np.abs(hb))
     _, ea = dev.run(NrRepetitions=5, seed=2, first_rep=40)
     _, eb = host.run(NrRepetitions=5, seed=2, first_rep=40)
     assert np.array_equal(ea, eb)
