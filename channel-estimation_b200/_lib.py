@@ -49,6 +49,10 @@ SIGNATURES = {
     "chest_transmission_matrix": (c_int, [c_u64, c_int, c_int, vp, vp]),
     "chest_modulate": (c_int, [c_u64, c_int, vp, c_int, vp]),
     "chest_demodulate": (c_int, [c_u64, c_int, vp, c_int, vp]),
+    "chest_set_modem": (c_int, [c_u64, c_int, c_int, c_int, c_int, c_int, vp, c_int, c_int, c_int, c_int, vp, vp,
+                                C.c_double, C.c_double]),
+    "chest_modulate_fft": (c_int, [c_u64, c_int, vp, c_int, vp]),
+    "chest_demodulate_fft": (c_int, [c_u64, c_int, vp, c_int, vp]),
     "chest_estimate": (c_int, [c_u64, c_int, c_int, c_int, vp, vp, vp]),
     "chest_draws_bytes": (c_i64, [c_u64, c_int]),
     "chest_run_batch": (c_int, [c_u64, c_int, c_int, C.POINTER(ChestDraws), c_u64, c_i64, vp]),

@@ -80,6 +80,9 @@ struct Waveform {
     std::vector<cplx> Gh, Qh;                           // host copies of G, Q (finalize builds Pd from them)
     DevBuf<int64_t> f_voff, f_yoff; DevBuf<int> f_rep; DevBuf<cplx> f_s, f_r;
     int f_cols = 0, perf_base = 0, perf_nblk = 0;
+    // FFT modem (chest_set_modem): plan, tables and the per-symbol IFFT outputs of the FBMC modulator
+    bool modem_set = false; ModemDev modem{};
+    DevBuf<int> m_bin; DevBuf<double> m_filt; DevBuf<cplx> m_phase, m_tw, m_Z, m_in, m_out;
     int d_alloc_batch = 0;      // batch size D / HG1 / HG2 are allocated for (0: not yet)
     // device-side setup (chest_setup_correlations): thresholded R_Dij_hP of all pilots, row-tile-major like D
     DevBuf<cplx> Rsup; int rsup_P = 0; double rsup_thr = 0;
@@ -115,8 +118,9 @@ struct Scheme {
     std::vector<uint8_t> considered;
     MmseVariant mm[2];
     DevBuf<cplx> xP, hP, hdiag, xD[2];
-    DevBuf<uint32_t> txword;
+    DevBuf<uint32_t> txword, txw_t;
     DevBuf<uint8_t> bits;
+    DevBuf<int4> rowinfo; DevBuf<int> multi_d; int n_multi = 0; bool fuse_ok = false;
     int64_t n_bits_edge = 0;
     int64_t c_nnz = 0;
     bool c_real = false;
@@ -260,6 +264,8 @@ SchemeDev scheme_dev(Ctx* c, int si) {
     d.row_col0 = s.row_col0.p; d.row_val0 = s.row_val0.p; d.long_rows = s.long_rows.p; d.n_long_rows = s.n_long_rows;
     d.n_lr_tiles = s.n_lr_tiles; d.lr_ptr = s.lr_ptr.p; d.lr_kcol = s.lr_kcol.p; d.lr_frag = s.lr_frag.p;
     d.wdiag_frag[0] = s.mm[0].diag_frag.p; d.wdiag_frag[1] = s.mm[1].diag_frag.p;
+    d.rowinfo = s.rowinfo.p; d.multi_d = s.multi_d.p; d.n_multi = s.n_multi; d.fuse_ok = s.fuse_ok ? 1 : 0;
+    d.txw_t = s.txw_t.p; d.txw_t_w = s.txw_t.p;
     for (int v = 0; v < 2; ++v) {
         d.tile_ptr[v] = s.mm[v].tile_ptr.p; d.tile_delta[v] = s.mm[v].tile_delta.p; d.w[v] = s.mm[v].table.p;
     }
@@ -568,9 +574,15 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     ip.stage_cplx = (int)((std::max((size_t)2 * PERF_STAGE_CPLX, (size_t)(ic_threads / 32) * ip.ring_cplx) + 7) / 8 * 8);
     const size_t main_smem = ((size_t)ip.stage_cplx + (size_t)2 * ip.pilot_rows * (NC_MAX + 2)) * sizeof(cplx)
                              + (size_t)ip.pilot_rows * EST_H1S * sizeof(double);
-    // light: new pilot estimates + constellation tables
-    // light: new pilot estimates, transmitted pilots, constellation tables, decided words (one byte per symbol)
+    // light / post: new pilot estimates, transmitted pilots, constellation tables, decided words (one byte per symbol);
+    // k_ic_post adds the ring of y_ic chunks in front
     const size_t light_smem = (size_t)ip.pilot_rows * (2 * NC_MAX + 2) * sizeof(cplx) + cst_smem + (size_t)c->K_max * NC_MAX;
+    const size_t post_smem = light_smem + (size_t)POST_NS * POST_ROWS * NC_MAX * sizeof(cplx);
+    const char* light_env = getenv("CHEST_LIGHT");
+    bool use_post = !(light_env && !strcmp(light_env, "old")) && post_smem <= 110 * 1024;
+    int p4_all = -1;                                              // pilot-quad count shared by every scheme (register prefetch)
+    for (int si = 0; si < 3; ++si) if (c->sch[si].set) { int q = (c->sch[si].P + 3) / 4; p4_all = p4_all < 0 ? q : (p4_all == q ? q : 0); }
+    void (*post_kernel)(IcParams) = p4_all == 4 ? k_ic_post<4> : (p4_all == 8 ? k_ic_post<8> : k_ic_post<0>);
     // which loop bodies the main kernel carries: the pilot-quad count most EST units have, and the real-v masks
     // every perfect-CSI unit of this configuration satisfies (16-column units: both schemes of a waveform)
     int p4s = 4, m2 = 3, m1 = 1;
@@ -592,14 +604,16 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         m2 < 0 ? (p4s == 4 ? k_ic_main<4, -1, -1> : k_ic_main<8, -1, -1>)
                : p4s == 4 ? (m2 == 2 ? k_ic_main<4, 2, 0> : (m2 == 3 ? k_ic_main<4, 3, 1> : k_ic_main<4, 0, 0>))
                           : (m2 == 2 ? k_ic_main<8, 2, 0> : (m2 == 3 ? k_ic_main<8, 3, 1> : k_ic_main<8, 0, 0>));
-    const int cfg_id = p4s * 100 + (m2 + 1) * 10 + (m1 + 1);
+    const int cfg_id = p4s * 100 + (m2 + 1) * 10 + (m1 + 1) + (use_post ? 1000 : 0);
     if (c->ic_grid == 0 || c->ic_smem != main_smem || c->ic_cfg != cfg_id) {    // persistent main grid: one wave of resident CTAs
         c->ic_cfg = cfg_id;
         CK(cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CK(cudaFuncSetAttribute(k_ic_light, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CK(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         int per_sm = 0, per_sm_light = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, main_kernel, ic_threads, main_smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, k_ic_light, IC_LIGHT_THREADS, light_smem));
+        if (use_post) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, post_kernel, POST_THREADS, post_smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, k_ic_light, IC_LIGHT_THREADS, light_smem));
         if (per_sm < 1 || per_sm_light < 1)
             return fail(CHEST_ERR_STATE, "the IC kernels do not fit on an SM (too many pilots for the shared tables)");
         c->ic_grid = per_sm * c->n_sm; c->ic_light_grid = per_sm_light * c->n_sm; c->ic_smem = main_smem;
@@ -632,7 +646,8 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
             if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
         }
         // phases C, D, E of iteration it (+ phase A of iteration it+1)
-        k_ic_light<<<light_grid, IC_LIGHT_THREADS, light_smem, st>>>(ip);
+        if (use_post) post_kernel<<<light_grid, POST_THREADS, post_smem, st>>>(ip);
+        else k_ic_light<<<light_grid, IC_LIGHT_THREADS, light_smem, st>>>(ip);
         c->launches++;
         CK(cudaGetLastError());
         if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it + 1], st));
@@ -1019,6 +1034,37 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
         for (int t = 0; t < nb; ++t)
             if (considered[(size_t)d * nb + t]) { mask[d] |= 1u << t; s.n_bits_edge++; }
     CK(s.edge_mask.upload(mask, c->stream));
+    {   // row descriptors of k_ic_post
+        std::vector<int> col0(K, -1), d_direct(K, -1);
+        std::vector<char> need(K, 0);
+        for (int i = 0; i < K; ++i) {
+            const int n = rowptr[i + 1] - rowptr[i];
+            if (n == 1) col0[i] = cols[rowptr[i]]; else if (n > 1) col0[i] = -2;
+        }
+        std::vector<int> multi;
+        if (detect == CHEST_DETECT_DESPREAD_REAL) {
+            // a data symbol is decided at its own row when its spreading set is that single row and the row holds nothing else
+            for (int d = 0; d < n_data; ++d) {
+                const int k = P + d, e0 = colptr[k], e1 = colptr[k + 1];
+                if (e1 - e0 == 1 && col0[rows[e0]] == k) d_direct[rows[e0]] = d;
+                else { multi.push_back(d); for (int e = e0; e < e1; ++e) need[rows[e]] = 1; }
+            }
+        } else {
+            std::vector<int> dp(data_pos, data_pos + n_data);
+            for (int d = 0; d < n_data; ++d) d_direct[dp[d]] = d;
+        }
+        bool fuse = true;
+        for (int i = 0; i < K; ++i) {
+            if (col0[i] >= P && d_direct[i] != col0[i] - P) fuse = false;     // the row's entry refers to a symbol decided elsewhere
+            if (need[i] && col0[i] != -2) fuse = false;                        // x-hat and v of the row would share a slot
+        }
+        if (getenv("CHEST_POST_NOFUSE")) fuse = false;                         // test knob: exercise the separate phase-A pass
+        std::vector<int4> ri(K);
+        for (int i = 0; i < K; ++i) ri[i] = make_int4(d_direct[i], col0[i], d_direct[i] >= 0 ? (int)mask[d_direct[i]] : 0, need[i]);
+        s.n_multi = (int)multi.size(); s.fuse_ok = fuse;
+        if (multi.empty()) multi.push_back(0);
+        CK(s.rowinfo.upload(ri, c->stream)); CK(s.multi_d.upload(multi, c->stream));
+    }
     CK(cudaStreamSynchronize(c->stream));
     s.set = true; c->finalized = false;
     return CHEST_OK;
@@ -1322,7 +1368,7 @@ int chest_finalize(uint64_t handle, int max_batch) {
         if (w.nsch == 1 && c->sch[w.sch[0]].P != s.P) return fail(CHEST_ERR_STATE, "schemes of one waveform must share the pilot count");
         w.sch[w.nsch++] = si;
         c->K_max = std::max(c->K_max, s.K);
-        CK(s.xP.alloc((size_t)B * s.P)); CK(s.txword.alloc((size_t)B * s.n_data)); CK(s.bits.alloc((size_t)B * s.n_bits));
+        CK(s.xP.alloc((size_t)B * s.P)); CK(s.txword.alloc((size_t)B * s.n_data)); CK(s.txw_t.alloc((size_t)((B + 15) / 16) * 16 * s.n_data)); CK(s.bits.alloc((size_t)B * s.n_bits));
         CK(s.hP.alloc((size_t)S * B * s.P)); CK(s.hdiag.alloc((size_t)S * B * s.K));
         CK(s.xD[0].alloc((size_t)S * B * s.n_data)); CK(s.xD[1].alloc((size_t)S * B * s.n_data));
     }
@@ -1497,6 +1543,112 @@ int chest_demodulate(uint64_t handle, int wfi, const double* r, int n_cols, doub
     ARG(c && (wfi == 0 || wfi == 1) && c->wf[wfi].set && r && y && n_cols >= 1);
     CK(cudaSetDevice(c->device));
     return plain_gemm(c, wfi, true, r, n_cols, y);
+}
+
+// ---------------------------------------------------------------- FFT modem
+int chest_set_modem(uint64_t handle, int wfi, int kind, int L, int Ksym, int nfft, const int32_t* bin, int time_spacing,
+                    int O, int cp, int zero_guard, const double* filt, const double* phase, double norm, double F) {
+    Ctx* c = from(handle);
+    ARG(c && (wfi == 0 || wfi == 1) && (kind == 0 || kind == 1) && L >= 1 && Ksym >= 1 && nfft >= 2 && nfft <= 4096 && bin);
+    ARG(L <= nfft && time_spacing >= 1 && norm > 0 && F > 0);
+    if (kind == 0) ARG(O >= 1 && filt && phase);
+    else ARG(cp >= 0 && zero_guard >= 0 && time_spacing == nfft + cp);
+    CK(cudaSetDevice(c->device));
+    Waveform& w = c->wf[wfi];
+    ModemDev& md = w.modem;
+    md = ModemDev{};
+    md.kind = kind; md.L = L; md.Ksym = Ksym; md.nfft = nfft; md.time_spacing = time_spacing; md.O = O; md.cp = cp;
+    md.zero_guard = zero_guard; md.Np = kind == 0 ? O * nfft : 0;
+    md.N = kind == 0 ? md.Np + (Ksym - 1) * time_spacing : 2 * zero_guard + Ksym * time_spacing;
+    if (c->N && c->N != md.N) return fail(CHEST_ERR_ARG, "Total number of samples must be the same for the channel and every waveform");
+    md.norm = norm; md.inv_demod = kind == 0 ? 1.0 / (norm * F) : 1.0 / norm;
+    md.plan.n = nfft; md.plan.n_stage = 0;
+    int rem = nfft;
+    for (int r : {4, 2, 3, 5, 7, 11, 13})
+        while (rem % r == 0) { ARG(md.plan.n_stage < FFT_MAX_STAGES); md.plan.radix[md.plan.n_stage++] = r; rem /= r; }
+    if (rem != 1) return fail(CHEST_ERR_ARG, "FFT size has a prime factor above 13");
+    std::vector<int> b(bin, bin + L);
+    std::vector<char> used(nfft, 0);
+    for (int x : b) { ARG(x >= 0 && x < nfft && !used[x]); used[x] = 1; }
+    std::vector<cplx> tw(nfft);
+    for (int m = 0; m < nfft; ++m) {                            // exact octant symmetry is not needed: cos/sin of 2 pi m / n in double
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * m / nfft;
+        tw[m] = cmake((double)cosl(a), (double)sinl(a));
+    }
+    cudaStream_t st = c->stream;
+    CK(w.m_bin.upload(b, st)); CK(w.m_tw.upload(tw, st));
+    if (kind == 0) {
+        CK(w.m_filt.upload(filt, (size_t)md.Np, st));
+        CK(w.m_phase.upload(reinterpret_cast<const cplx*>(phase), (size_t)L * Ksym, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    md.bin = w.m_bin.p; md.filt = w.m_filt.p; md.phase = w.m_phase.p; md.tw = w.m_tw.p;
+    const size_t smem = (size_t)3 * nfft * sizeof(cplx);
+    CK(cudaFuncSetAttribute(k_modem_ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_modem_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ARG(smem <= 200 * 1024);
+    w.modem_set = true;
+    return CHEST_OK;
+}
+
+// device-resident core: x_dev [n_cols][L*K] -> s_dev [n_cols][N]
+static int modem_modulate_dev(Ctx* c, Waveform& w, const cplx* x_dev, int n_cols, cplx* s_dev) {
+    const ModemDev& md = w.modem;
+    const size_t smem = (size_t)3 * md.nfft * sizeof(cplx);
+    const int thr = std::min(256, std::max(32, ((md.nfft / 2 + 31) / 32) * 32));
+    dim3 g(md.Ksym, n_cols);
+    if (md.kind == 0) {
+        CK(w.m_Z.alloc((size_t)n_cols * md.Ksym * md.nfft));
+        k_modem_ifft<<<g, thr, smem, c->stream>>>(md, x_dev, w.m_Z.p, nullptr);
+        dim3 g2((md.N + 255) / 256, n_cols);
+        k_fbmc_overlap_add<<<g2, 256, 0, c->stream>>>(md, w.m_Z.p, s_dev);
+        c->launches += 2;
+    } else {
+        CK(cudaMemsetAsync(s_dev, 0, sizeof(cplx) * (size_t)n_cols * md.N, c->stream));     // zero guard samples
+        k_modem_ifft<<<g, thr, smem, c->stream>>>(md, x_dev, nullptr, s_dev);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return CHEST_OK;
+}
+static int modem_demodulate_dev(Ctx* c, Waveform& w, const cplx* r_dev, int n_cols, cplx* y_dev) {
+    const ModemDev& md = w.modem;
+    const size_t smem = (size_t)3 * md.nfft * sizeof(cplx);
+    const int thr = std::min(256, std::max(32, ((md.nfft / 2 + 31) / 32) * 32));
+    dim3 g(md.Ksym, n_cols);
+    k_modem_fft<<<g, thr, smem, c->stream>>>(md, r_dev, y_dev);
+    c->launches++;
+    CK(cudaGetLastError());
+    return CHEST_OK;
+}
+
+int chest_modulate_fft(uint64_t handle, int wfi, const double* x, int n_cols, double* s_out) {
+    Ctx* c = from(handle);
+    ARG(c && (wfi == 0 || wfi == 1) && c->wf[wfi].modem_set && x && s_out && n_cols >= 1);
+    CK(cudaSetDevice(c->device));
+    Waveform& w = c->wf[wfi];
+    const ModemDev& md = w.modem;
+    const size_t nx = (size_t)n_cols * md.L * md.Ksym, ns = (size_t)n_cols * md.N;
+    CK(w.m_in.upload(reinterpret_cast<const cplx*>(x), nx, c->stream));
+    CK(w.m_out.alloc(ns));
+    int rc = modem_modulate_dev(c, w, w.m_in.p, n_cols, w.m_out.p); if (rc) return rc;
+    CK(cudaMemcpyAsync(s_out, w.m_out.p, ns * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+int chest_demodulate_fft(uint64_t handle, int wfi, const double* r, int n_cols, double* y_out) {
+    Ctx* c = from(handle);
+    ARG(c && (wfi == 0 || wfi == 1) && c->wf[wfi].modem_set && r && y_out && n_cols >= 1);
+    CK(cudaSetDevice(c->device));
+    Waveform& w = c->wf[wfi];
+    const ModemDev& md = w.modem;
+    const size_t ny = (size_t)n_cols * md.L * md.Ksym, nr = (size_t)n_cols * md.N;
+    CK(w.m_in.upload(reinterpret_cast<const cplx*>(r), nr, c->stream));
+    CK(w.m_out.alloc(ny));
+    int rc = modem_demodulate_dev(c, w, w.m_in.p, n_cols, w.m_out.p); if (rc) return rc;
+    CK(cudaMemcpyAsync(y_out, w.m_out.p, ny * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
 }
 
 int chest_estimate(uint64_t handle, int si, int variant, int i_snr, const double* hP, double* Dhat_out, double* hdiag_out) {

@@ -1931,6 +1931,143 @@ __global__ void __launch_bounds__(POST_THREADS, 2) k_ic_post(IcParams p) {
     }
 }
 
+
+// ============================================================================ FFT modem (FBMC.m:255-315, OFDM.m:153-181)
+// Hand-written mixed-radix Stockham FFT in shared memory (sizes with prime factors <= 13: 24, 168, 196, 512, ... ; no
+// cuFFT), one thread block per (multicarrier symbol, column).  tw[m] = exp(-2 pi i m / n); the inverse transform
+// conjugates the table and scales by 1/n like MATLAB's ifft.
+#define FFT_MAX_STAGES 16
+struct FftPlan { int n, n_stage; int radix[FFT_MAX_STAGES]; };
+struct ModemDev {
+    int kind;                    // 0: FBMC polyphase, 1: CP-OFDM
+    int L, Ksym, nfft, N, time_spacing, O, cp, zero_guard, Np;
+    double norm, inv_demod;      // NormalizationFactor; 1 / (NormalizationFactor * SubcarrierSpacing) (FBMC) or 1 / NormalizationFactor (OFDM)
+    const int* bin;              // FFT bin of subcarrier l (IndexPolyphaseMap rows in ascending order, FBMC.m:154-156)
+    const double* filt;          // prototype filter, Np = O * nfft real taps (FBMC)
+    const cplx* phase;           // PhaseShift, L x Ksym (FBMC.m:139)
+    const cplx* tw;              // exp(-2 pi i m / nfft), m = 0..nfft-1
+    FftPlan plan;
+};
+template <int R>
+__device__ __forceinline__ void fft_butterfly(const cplx* __restrict__ a, cplx* __restrict__ b, const cplx* __restrict__ tw,
+                                              int n, int Ns, int j, int m, bool inv) {
+    const int k = j % Ns, step = n / (Ns * R);
+    cplx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+        cplx w = tw[(int)(((int64_t)t * k * step) % n)];
+        if (inv) w.y = -w.y;
+        v[t] = cmul(a[j + t * m], w);
+    }
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        cplx acc = v[0];
+#pragma unroll
+        for (int t = 1; t < R; ++t) {
+            cplx w = tw[((t * u) % R) * (n / R)];
+            if (inv) w.y = -w.y;
+            cfma(acc, v[t], w);
+        }
+        b[j0 + u * Ns] = acc;
+    }
+}
+// In-place interface: data in `a`, scratch `b` (both n complex, shared memory).  Returns the buffer holding the result.
+__device__ cplx* fft_shared(cplx* a, cplx* b, const cplx* tw, const FftPlan& plan, bool inv) {
+    const int n = plan.n;
+    int Ns = 1;
+    for (int s = 0; s < plan.n_stage; ++s) {
+        const int R = plan.radix[s], m = n / R;
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            switch (R) {
+                case 2: fft_butterfly<2>(a, b, tw, n, Ns, j, m, inv); break;
+                case 3: fft_butterfly<3>(a, b, tw, n, Ns, j, m, inv); break;
+                case 4: fft_butterfly<4>(a, b, tw, n, Ns, j, m, inv); break;
+                case 5: fft_butterfly<5>(a, b, tw, n, Ns, j, m, inv); break;
+                case 7: fft_butterfly<7>(a, b, tw, n, Ns, j, m, inv); break;
+                case 11: fft_butterfly<11>(a, b, tw, n, Ns, j, m, inv); break;
+                default: fft_butterfly<13>(a, b, tw, n, Ns, j, m, inv); break;
+            }
+        }
+        __syncthreads();
+        cplx* t_ = a; a = b; b = t_;
+        Ns *= R;
+    }
+    return a;
+}
+// x: [col][L*Ksym] symbols (column-major L x Ksym per column).  FBMC: Z[col][k][nfft] = ifft of symbol k (FBMC.m:263-267
+// before the tiling); OFDM: the time signal with cyclic prefix written straight into s (OFDM.m:158-164).
+__global__ void k_modem_ifft(ModemDev md, const cplx* __restrict__ x, cplx* __restrict__ Z, cplx* __restrict__ s) {
+    extern __shared__ __align__(16) cplx fsm[];
+    cplx* a = fsm; cplx* b = fsm + md.nfft; cplx* tw = fsm + 2 * md.nfft;
+    const int k = blockIdx.x, col = blockIdx.y, n = md.nfft;
+    for (int m = threadIdx.x; m < n; m += blockDim.x) { a[m] = cmake(0.0, 0.0); tw[m] = md.tw[m]; }
+    __syncthreads();
+    for (int l = threadIdx.x; l < md.L; l += blockDim.x) {
+        cplx v = x[((int64_t)col * md.Ksym + k) * md.L + l];
+        if (md.kind == 0) v = cmul(v, md.phase[k * md.L + l]);
+        a[md.bin[l]] = cmake(v.x * md.norm, v.y * md.norm);
+    }
+    __syncthreads();
+    const cplx* z = fft_shared(a, b, tw, md.plan, true);
+    const double sc = 1.0 / n;
+    if (md.kind == 0) {
+        for (int m = threadIdx.x; m < n; m += blockDim.x) Z[((int64_t)col * md.Ksym + k) * n + m] = cmake(z[m].x * sc, z[m].y * sc);
+    } else {
+        const int T = md.time_spacing;                          // FFT size + cyclic prefix
+        cplx* out = s + (int64_t)col * md.N + md.zero_guard + (int64_t)k * T;
+        for (int j = threadIdx.x; j < T; j += blockDim.x) {
+            const int m = (j - md.cp + n) % n;
+            out[j] = cmake(z[m].x * sc, z[m].y * sc);
+        }
+    }
+}
+// FBMC overlap-add as a gather: s[n] = sum_k p[n - k T] * Z[k][(n - k T) mod nfft], symbols ascending (FBMC.m:267-268)
+__global__ void k_fbmc_overlap_add(ModemDev md, const cplx* __restrict__ Z, cplx* __restrict__ s) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (n >= md.N) return;
+    const int T = md.time_spacing;
+    int k_lo = (n - md.Np + T) / T; if (n - md.Np + 1 <= 0) k_lo = 0;      // smallest k with n - kT <= Np - 1
+    const int k_hi = min(md.Ksym - 1, n / T);
+    cplx acc = cmake(0.0, 0.0);
+    for (int k = k_lo; k <= k_hi; ++k) {
+        const int tap = n - k * T;
+        if (tap < 0 || tap >= md.Np) continue;
+        const cplx z = Z[((int64_t)col * md.Ksym + k) * md.nfft + tap % md.nfft];
+        const double pf = md.filt[tap];
+        acc.x += pf * z.x; acc.y += pf * z.y;
+    }
+    s[(int64_t)col * md.N + n] = acc;
+}
+// Demodulation: FBMC: filter, fold by O, FFT, pick the subcarrier bins, undo the phase (FBMC.m:294-302);
+// OFDM: drop the cyclic prefix, FFT, pick (OFDM.m:172-180).  y: [col][L*Ksym].
+__global__ void k_modem_fft(ModemDev md, const cplx* __restrict__ r, cplx* __restrict__ y) {
+    extern __shared__ __align__(16) cplx fsm[];
+    cplx* a = fsm; cplx* b = fsm + md.nfft; cplx* tw = fsm + 2 * md.nfft;
+    const int k = blockIdx.x, col = blockIdx.y, n = md.nfft;
+    const cplx* rc = r + (int64_t)col * md.N;
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        tw[m] = md.tw[m];
+        cplx acc = cmake(0.0, 0.0);
+        if (md.kind == 0) {
+            const cplx* seg = rc + (int64_t)k * md.time_spacing;
+            for (int o = 0; o < md.O; ++o) {
+                const double pf = md.filt[o * n + m];
+                const cplx v = seg[o * n + m];
+                acc.x += v.x * pf; acc.y += v.y * pf;
+            }
+        } else acc = rc[md.zero_guard + (int64_t)k * md.time_spacing + md.cp + m];
+        a[m] = acc;
+    }
+    __syncthreads();
+    const cplx* z = fft_shared(a, b, tw, md.plan, false);
+    for (int l = threadIdx.x; l < md.L; l += blockDim.x) {
+        cplx v = z[md.bin[l]];
+        if (md.kind == 0) v = cmulc(md.phase[k * md.L + l], v);        // .* conj(PhaseShift)
+        y[((int64_t)col * md.Ksym + k) * md.L + l] = cmake(v.x * md.inv_demod, v.y * md.inv_demod);
+    }
+}
+
 // ============================================================================ setup on the device (DS.m:208-313)
 // Pseudo-channel of pilot p (DS.m:213,260): M_p = reshape(R_vecH * kron(g_p.', q_p')', N, N) is banded like H, with
 //   M_p[a + m, a] = pdp_m * sum_a' rt[a - a'] * zeta_m[a'],   zeta_m[a'] = q_p[row(a')] * conj(g_p[col(a')])

@@ -151,6 +151,21 @@ int chest_transmission_matrix(uint64_t handle, int b, int waveform, double* D_ou
 int chest_modulate(uint64_t handle, int waveform, const double* x, int n_cols, double* s);
 int chest_demodulate(uint64_t handle, int waveform, const double* r, int n_cols, double* y);
 
+/* The same two methods in their FFT form (FBMC.m:255-268, 287-302 polyphase branch; OFDM.m:153-181), for waveforms whose
+ * dense G / Q would not fit or would be wasteful (SimpleVersion_DoublyFlat.m:118-135, scaled bandwidths).  chest_set_modem
+ * takes what SetDependentParameters computes (FBMC.m:61-160, OFDM.m:53-88): kind 0 = FBMC polyphase, 1 = CP-OFDM;
+ * bin_of_subcarrier[l] = FFT bin (0-based) that carries subcarrier l (rows of IndexPolyphaseMap in ascending order /
+ * IntermediateFrequency + l); FBMC: time_spacing = FFTSize/2, overlapping factor O (prototype filter: O*FFTSize real
+ * taps), PhaseShift L x K complex, NormalizationFactor, SubcarrierSpacing; OFDM: cyclic prefix and zero-guard samples,
+ * time_spacing = FFTSize + CP.  The transforms are hand-written mixed-radix shared-memory FFTs (prime factors <= 13).
+ * x: (L*K) x n_cols, s / r: N x n_cols, y: (L*K) x n_cols; complex, column-major, host pointers. */
+int chest_set_modem(uint64_t handle, int waveform, int kind, int n_subcarriers, int n_mc_symbols, int fft_size,
+                    const int32_t* bin_of_subcarrier, int time_spacing, int overlapping_factor, int cyclic_prefix,
+                    int zero_guard_samples, const double* prototype_filter, const double* phase_shift,
+                    double normalization_factor, double subcarrier_spacing);
+int chest_modulate_fft(uint64_t handle, int waveform, const double* x, int n_cols, double* s);
+int chest_demodulate_fft(uint64_t handle, int waveform, const double* r, int n_cols, double* y);
+
 /* D_est = sum_p W(:,:,p) hP(p), h_est = diag(D_est) (DS.m:417-428,493-517).
  * hP: P complex; Dhat_out K x K (may be NULL); hdiag_out K (may be NULL). */
 int chest_estimate(uint64_t handle, int scheme, int variant, int i_snr, const double* hP,

@@ -19,7 +19,8 @@ for i in range(reps):
     t = time.time()
     err = ctx.run_batch(B, 4, None, seed=1, first_rep=i * B)
     dt = time.time() - t
-    print("batch", B, "wall s", dt, "realizations/s", B / dt, ctx.stage_times())
+    print("batch", B, "wall s", round(dt, 4), "realizations/s", round(B / dt, 1), {k: round(v, 3) for k, v in ctx.stage_times().items()},
+          {k: round(v, 3) for k, v in ctx.kernel_times().items()})
 nb = ctx.bit_counts()
 ber = err.astype(float).mean(axis=0)
 for sid, n in enumerate(("aux", "cod", "ofdm")):

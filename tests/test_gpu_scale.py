@@ -314,3 +314,35 @@ def test_device_setup_paper_geometry_wrapped_entries(ds_paper):
         assert np.max(np.abs(hd - h_ref)) < 1e-9 * np.max(np.abs(h_ref))
     print("paper geometry (OFDM only) setup times:", {k: round(v, 3) for k, v in sim.setup_times.items()})
     sim.close()
+
+
+def test_post_kernel_variants_agree(ds_default):
+    """k_ic_post (TMA-staged, fused decide + precode) against its own un-fused phase-A path (CHEST_POST_NOFUSE) and the
+    previous k_ic_light (CHEST_LIGHT=old): identical counts and state on the same seeded batch, ragged tail included."""
+    from tests.helpers import context_from_oracle
+    S = ds_default
+    B, seed, first = 37, 8, 900
+
+    def run(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            ctx = context_from_oracle(S, max_batch=B)
+            err = ctx.run_batch(B, 4, None, seed=seed, first_rep=first)
+            st = [ctx.get_state(w, sc, 36, 6) for sc in ("aux", "cod", "ofdm") for w in ("hP", "xD_est", "xD_perf", "hdiag")]
+            ctx.close()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    del os.environ[k]
+                else:
+                    os.environ[k] = v
+        return err, st
+    base, st0 = run({})
+    for env in ({"CHEST_POST_NOFUSE": "1"}, {"CHEST_LIGHT": "old"}):
+        err, st = run(env)
+        assert np.array_equal(err, base), env
+        for a, b in zip(st, st0):
+            assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(b))), env
+    for r in (0, 16, 36):
+        assert np.array_equal(base[r], _oracle_counts(S, seed, first + r))
