@@ -194,6 +194,35 @@ class DeviceContext:
         self._check(self.lib.chest_demodulate(self._h, WF_ID[wf], _ptr(r2), r2.shape[0], _ptr(y)))
         return y[0] if np.ndim(r) == 1 else y.T.copy()
 
+    # ------------------------------------------------------------------ FFT modem
+    def set_modem(self, wf, kind, L, Ksym, nfft, bins, time_spacing, O=1, cp=0, zero_guard=0, prototype_filter=None,
+                  phase_shift=None, normalization=1.0, subcarrier_spacing=1.0):
+        """kind: 'fbmc' (polyphase, FBMC.m:255-302) or 'ofdm' (OFDM.m:153-181)."""
+        b = np.ascontiguousarray(bins, dtype=np.int32)
+        pf = np.ascontiguousarray(prototype_filter, dtype=np.float64) if prototype_filter is not None else None
+        ph = _c(np.asfortranarray(phase_shift).reshape(-1, order="F")) if phase_shift is not None else None
+        self._check(self.lib.chest_set_modem(self._h, WF_ID[wf], {"fbmc": 0, "ofdm": 1}[kind], L, Ksym, nfft, _ptr(b),
+                                             time_spacing, O, cp, zero_guard, _ptr(pf), _ptr(ph), normalization,
+                                             subcarrier_spacing))
+        n = O * nfft + (Ksym - 1) * time_spacing if kind == "fbmc" else 2 * zero_guard + Ksym * time_spacing
+        self._modem = getattr(self, "_modem", {})
+        self._modem[wf] = (L * Ksym, n)
+
+    def modulate_fft(self, wf, x):
+        """x: (L*K,) or (L*K, n_cols) -> (N,) or (N, n_cols)."""
+        lk, n = self._modem[wf]
+        x2 = _c(np.atleast_2d(np.asarray(x).T) if np.ndim(x) == 1 else np.asarray(x).T)
+        s = np.zeros((x2.shape[0], n), dtype=np.complex128)
+        self._check(self.lib.chest_modulate_fft(self._h, WF_ID[wf], _ptr(x2), x2.shape[0], _ptr(s)))
+        return s[0] if np.ndim(x) == 1 else s.T.copy()
+
+    def demodulate_fft(self, wf, r):
+        lk, n = self._modem[wf]
+        r2 = _c(np.atleast_2d(np.asarray(r).T) if np.ndim(r) == 1 else np.asarray(r).T)
+        y = np.zeros((r2.shape[0], lk), dtype=np.complex128)
+        self._check(self.lib.chest_demodulate_fft(self._h, WF_ID[wf], _ptr(r2), r2.shape[0], _ptr(y)))
+        return y[0] if np.ndim(r) == 1 else y.T.copy()
+
     def estimate(self, name, variant, i_snr, hP, want_D=True):
         K = self.schemes[name]["K"]
         hP = _c(hP)

@@ -3,8 +3,10 @@
 `Modulation.FBMC`, `Modulation.OFDM`: the constructors reproduce SetDependentParameters
 (FBMC.m:61-160, OFDM.m:53-88); the transmit / receive matrices are written in closed form (the
 reference obtains them by calling its IFFT modulator once per subcarrier, FBMC.m:330-337);
-`Modulation` / `Demodulation` run on the GPU in their matrix form s = G x(:), y = Q' r
-(FBMC.m:319-320,344-345; OFDM.m:185-186,206-207) through the C ABI.
+`Modulation` / `Demodulation` run on the GPU in their FFT form (polyphase IFFT + prototype filter + overlap-add,
+FBMC.m:255-302; CP-OFDM, OFDM.m:153-181: hand-written mixed-radix FFT kernels, chest_set_modem /
+chest_modulate_fft / chest_demodulate_fft); `ModulationMatrix` / `DemodulationMatrix` keep the matrix form
+s = G x(:), y = Q' r (FBMC.m:319-320,344-345; OFDM.m:185-186,206-207), the form the DS.m loop body uses.
 `Modulation.SignalConstellation`: tables of SC.m:24-74; the nearest-neighbour demapping used on
 the hot path lives in the CUDA library (kernels.cuh, demap_word)."""
 import sys
@@ -92,27 +94,52 @@ class _Modem:
     _wf = "F"
 
     def _device(self):
+        """Context with the dense G / Q uploaded (matrix-form modem)."""
         if getattr(self, "_ctx", None) is None:
             self._ctx = DeviceContext()
             self._ctx.set_waveform(self._wf, self.GetTXMatrix(), self.GetRXMatrix().conj().T)
         return self._ctx
 
-    def Modulation(self, DataSymbols):
-        """s = G*x(:) on the GPU.  DataSymbols: L x K (or several stacked along a 3rd axis)."""
+    def _device_fft(self):
+        """Context with only the FFT modem's tables (no N x LK matrices)."""
+        if getattr(self, "_ctx_fft", None) is None:
+            self._ctx_fft = DeviceContext()
+            self._set_modem(self._ctx_fft)
+        return self._ctx_fft
+
+    def _check_x(self, DataSymbols):
         x = np.asarray(DataSymbols)
         L, K = self.Nr["Subcarriers"], self.Nr["MCSymbols"]
         if x.shape[:2] != (L, K):
             raise ValueError("DataSymbols must be Subcarriers x MCSymbols")
-        flat = x.reshape(L * K, -1, order="F")
-        s = self._device().modulate(self._wf, flat)
+        return x, x.reshape(L * K, -1, order="F")
+
+    def Modulation(self, DataSymbols):
+        """FBMC.m:255-268 / OFDM.m:153-165 on the GPU (FFT form).  DataSymbols: L x K (or several stacked along a
+        3rd axis, as SimpleVersion_DoublyFlat.m:118 does)."""
+        x, flat = self._check_x(DataSymbols)
+        s = self._device_fft().modulate_fft(self._wf, flat)
         return s[:, 0] if x.ndim == 2 else s
 
     def Demodulation(self, ReceivedSignal):
-        """reshape(Q'*r, L, K) on the GPU."""
+        """FBMC.m:287-302 / OFDM.m:167-181 on the GPU (FFT form)."""
         r = np.asarray(ReceivedSignal)
         L, K = self.Nr["Subcarriers"], self.Nr["MCSymbols"]
         if r.shape[0] != self.Nr["SamplesTotal"]:
             raise ValueError("ReceivedSignal must have Nr.SamplesTotal rows")
+        y = self._device_fft().demodulate_fft(self._wf, r.reshape(r.shape[0], -1))
+        return y[:, 0].reshape(L, K, order="F") if r.ndim == 1 else y.reshape(L, K, -1, order="F")
+
+    def ModulationMatrix(self, DataSymbols):
+        """s = G*x(:) on the GPU (the identity the reference states at FBMC.m:319-320 / OFDM.m:185-186)."""
+        x, flat = self._check_x(DataSymbols)
+        s = self._device().modulate(self._wf, flat)
+        return s[:, 0] if x.ndim == 2 else s
+
+    def DemodulationMatrix(self, ReceivedSignal):
+        """reshape(Q'*r, L, K) on the GPU (FBMC.m:344-345 / OFDM.m:206-207)."""
+        r = np.asarray(ReceivedSignal)
+        L, K = self.Nr["Subcarriers"], self.Nr["MCSymbols"]
         y = self._device().demodulate(self._wf, r.reshape(r.shape[0], -1))
         return y[:, 0].reshape(L, K, order="F") if r.ndim == 1 else y.reshape(L, K, -1, order="F")
 
@@ -194,6 +221,16 @@ class FBMC(_Modem):
         Imp["NormalizationFactor"] = np.sqrt(fs ** 2 / F ** 2 * PHY["TimeSpacing"] / Nr["Subcarriers"])
         self._ctx = None
         self._G = None
+
+    def _set_modem(self, ctx):
+        Nr, Imp = self.Nr, self.Implementation
+        L, K, nfft = Nr["Subcarriers"], Nr["MCSymbols"], Imp["FFTSize"]
+        bins = np.sort((Imp["IntermediateFrequency"] + np.arange(L)) % nfft)          # FBMC.m:154-156: ascending rows
+        k, l = np.meshgrid(np.arange(K), np.arange(L))
+        phase = np.exp(1j * np.pi / 2 * (l + k)) * np.exp(1j * Imp["InitialPhaseShift"])          # FBMC.m:139
+        ctx.set_modem(self._wf, "fbmc", L, K, nfft, bins, Imp["TimeSpacing"], O=Imp["FrequencySpacing"],
+                      prototype_filter=self.PrototypeFilter["TimeDomain"], phase_shift=phase,
+                      normalization=Imp["NormalizationFactor"], subcarrier_spacing=self.PHY["SubcarrierSpacing"])
 
     def GetTXMatrix(self):
         """G (N x L*K): column (l,k) = shifted, modulated prototype filter.  Closed form of
@@ -290,7 +327,15 @@ class OFDM(_Modem):
         PHY["TimeSpacing"] = Imp["TimeSpacing"] * PHY["dt"]
         Nr["SamplesTotal"] = Nr["MCSymbols"] * Imp["TimeSpacing"] + 2 * Imp["ZeroGuardSamples"]
         self._ctx = None
+        self._ctx_fft = None
         self._G = None
+
+    def _set_modem(self, ctx):
+        Nr, Imp = self.Nr, self.Implementation
+        ctx.set_modem(self._wf, "ofdm", Nr["Subcarriers"], Nr["MCSymbols"], Imp["FFTSize"],
+                      Imp["IntermediateFrequency"] + np.arange(Nr["Subcarriers"]), Imp["TimeSpacing"],
+                      cp=Imp["CyclicPrefix"], zero_guard=Imp["ZeroGuardSamples"],
+                      normalization=Imp["NormalizationFactor"], subcarrier_spacing=self.PHY["SubcarrierSpacing"])
 
     def GetTXMatrix(self):
         """G (N x L*K), closed form of OFDM.m:184-203: subcarrier l of symbol k is a complex

@@ -346,3 +346,44 @@ def test_post_kernel_variants_agree(ds_default):
             assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(b))), env
     for r in (0, 16, 36):
         assert np.array_equal(base[r], _oracle_counts(S, seed, first + r))
+
+
+@pytest.mark.parametrize("cfg", ["sv", "ds_default", "paper", "lte5"])
+def test_fft_modem_equals_oracle_fft_modem(cfg):
+    """Modulation and Demodulation in their FFT form on the device (hand-written
+    mixed-radix FFT: 168 = 8*3*7, 24, 196 = 4*7*7 and 512 points; polyphase filter + overlap-add; cyclic prefix) against
+    the oracle's FFT modem (FBMC.m:255-302, OFDM.m:153-181), several symbol matrices per call, and against the matrix
+    form G*x / Q'*r where the matrices are small enough."""
+    import chest_b200
+    from oracle.fbmc import FBMC as RefFBMC
+    from oracle.ofdm import OFDM as RefOFDM
+    M = chest_b200.Modulation
+    args = {"sv": ((12, 30, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, "Hermite-OQAM", 8, 0, True),
+                   (12, 15, 15e3, 15e3 * 14 * 12, 15e3 * 20, False, 0, (8 - 1 / 2) * 1 / 15e3 * 1 / 2)),
+            "ds_default": ((24, 30, 15e3, 15e3 * 24, 0, False, "Hermite-OQAM", 8, 0, True),
+                           (24, 14, 15e3, 15e3 * 24, 0, False, 1 / 15e3 / 14, 88 / (15e3 * 24))),
+            "paper": ((24, 60, 15e3, 15e3 * 14 * 14, 0, False, "Hermite-OQAM", 8, 0, True),
+                      (24, 28, 15e3, 15e3 * 14 * 14, 0, False, 1 / 15e3 / 14, 735 / (15e3 * 14 * 14))),
+            "lte5": ((300, 30, 15e3, 15e3 * 512, 15e3 * 106, False, "Hermite-OQAM", 4, 0, True),
+                     (300, 14, 15e3, 15e3 * 512, 15e3 * 106, False, 36 / (15e3 * 512), 0))}[cfg]
+    rng = np.random.default_rng(5)
+    for cls, ref_cls, a in ((M.FBMC, RefFBMC, args[0]), (M.OFDM, RefOFDM, args[1])):
+        dev, ref = cls(*a), ref_cls(*a)
+        L, K, N = dev.Nr["Subcarriers"], dev.Nr["MCSymbols"], dev.Nr["SamplesTotal"]
+        assert N == ref.Nr["SamplesTotal"] and dev.Implementation["FFTSize"] == ref.Implementation["FFTSize"]
+        x = rng.standard_normal((L, K, 3)) + 1j * rng.standard_normal((L, K, 3))
+        s = dev.Modulation(x)
+        for q in range(3):
+            assert rel(s[:, q], ref.Modulation(x[:, :, q])) < 1e-12
+        assert rel(dev.Modulation(x[:, :, 1]), s[:, 1]) < 1e-15
+        r = rng.standard_normal((N, 2)) + 1j * rng.standard_normal((N, 2))
+        y = dev.Demodulation(r)
+        for q in range(2):
+            assert rel(y[:, :, q], ref.Demodulation(r[:, q])) < 1e-12
+        if cfg != "lte5":                                           # identities stated at FBMC.m:319-320,344-345
+            assert rel(dev.ModulationMatrix(x[:, :, 0]), s[:, 0]) < 1e-12
+            assert rel(dev.DemodulationMatrix(r[:, 0]), y[:, :, 0]) < 1e-12
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b))
