@@ -20,7 +20,7 @@ vp = C.c_void_p
 class ChestDraws(C.Structure):
     """struct chest_draws (chest_b200.h)."""
     _fields_ = [("doppler_u", vp), ("phase_u", vp), ("bits", vp * 3), ("pilot_idx", vp * 2),
-                ("noise", vp), ("on_device", c_int)]
+                ("noise", vp), ("on_device", c_int), ("channel_gauss", vp)]
 
 
 # name -> (restype, argtypes); every symbol include/chest_b200.h declares
@@ -42,6 +42,8 @@ SIGNATURES = {
     "chest_finalize": (c_int, [c_u64, c_int]),
     "chest_new_realization": (c_int, [c_u64, c_int, vp, vp]),
     "chest_new_realization_seeded": (c_int, [c_u64, c_int, c_u64, c_i64]),
+    "chest_new_realization_gauss": (c_int, [c_u64, c_int, vp]),
+    "chest_channel_info": (c_int, [c_u64, C.POINTER(c_int), p_d, C.POINTER(c_int)]),
     "chest_set_impulse_response": (c_int, [c_u64, c_int, vp]),
     "chest_get_impulse_response": (c_int, [c_u64, c_int, vp]),
     "chest_get_convolution_csc": (c_int, [c_u64, c_int, p_i64, vp, vp, vp]),

@@ -2,10 +2,11 @@
 
 The constructor (power-delay-profile tables, resampling to the sampling rate) is host-side
 table work, as in the reference; `NewRealization`, `Convolution`, `GetConvolutionMatrix` run on the
-GPU through the C ABI.  Supported here: 1x1 antennas; 'Jakes' and 'Uniform' Doppler models (the branch both
-reference scripts use, FF.m:223-239, synthesised on the GPU); block fading (f_D = 0, FF.m:241-248) and 'AWGN'
-(FF.m:197-198), whose few draws are made on the host and applied by the same device operator.  The
-'Discrete-*' IFFT synthesis raises NotImplementedError."""
+GPU through the C ABI: 'Jakes' and 'Uniform' sum-of-sinusoids synthesis (the branch both reference scripts use,
+FF.m:223-239), the 'Discrete-Jakes' / 'Discrete-Uniform' IFFT synthesis (FF.m:151-182, 203-221: a pruned inverse DFT
+over the 2 n_shift + 1 Doppler bins), block fading (f_D = 0, FF.m:241-248) and 'AWGN' (FF.m:197-198), whose few
+draws are made on the host and applied by the same device operator.  nTx x nRx antennas (FF.m:205-206, 223-224,
+258-262, 279-285) are a batch of nRx * nTx independent realizations on the device (index rx + nRx * tx)."""
 import numpy as np
 from scipy.special import j0
 
@@ -47,15 +48,13 @@ class FastFading:
     def __init__(self, SamplingRate, PowerDelayProfile, SamplesTotal, MaximumDopplerShift, DopplerModel,
                  Paths, nTxAntennas=1, nRxAntennas=1, WarningIfSampleRateDoesNotMatch=False, seed=0,
                  create_device=True):
-        if nTxAntennas != 1 or nRxAntennas != 1:
-            raise NotImplementedError("only 1x1 antennas are supported by this build")
-        if DopplerModel not in ("Jakes", "Uniform") and MaximumDopplerShift > 0:
-            raise NotImplementedError("Doppler spectrum not supported by this build: %s" % DopplerModel)
-        if str(DopplerModel).startswith("Discrete"):
-            raise NotImplementedError("Doppler spectrum not supported by this build: %s" % DopplerModel)
+        if DopplerModel not in ("Jakes", "Uniform", "Discrete-Jakes", "Discrete-Uniform") and MaximumDopplerShift > 0:
+            raise ValueError("Doppler spectrum not supported")                           # FF.m:230,171
         self.PHY = {"SamplingRate": float(SamplingRate), "MaximumDopplerShift": float(MaximumDopplerShift),
                     "dt": 1.0 / SamplingRate, "DopplerModel": DopplerModel}
-        self.Nr = {"SamplesTotal": int(SamplesTotal), "txAntennas": 1, "rxAntennas": 1, "Paths": int(Paths)}
+        self.Nr = {"SamplesTotal": int(SamplesTotal), "txAntennas": int(nTxAntennas), "rxAntennas": int(nRxAntennas),
+                   "Paths": int(Paths)}
+        discrete = str(DopplerModel).startswith("Discrete")
         self.Implementation = {"PowerDelayProfile": PowerDelayProfile, "UseDiscreteDopplerSpectrum": False}
         dt = self.PHY["dt"]
         if isinstance(PowerDelayProfile, str):
@@ -79,6 +78,18 @@ class FastFading:
         self.PHY["PowerDelayProfile"] = pdp
         self.Implementation["PowerDelayProfileNormalized"] = pdp / pdp.sum()              # FF.m:129
         self.Implementation["IndexDelayTaps"] = np.flatnonzero(pdp)                       # FF.m:131
+        fD, N = self.PHY["MaximumDopplerShift"], self.Nr["SamplesTotal"]
+        if discrete and fD > 0 and fD / (SamplingRate / N) <= 0.5:                        # FF.m:146-149
+            import sys; print('Discrete Doppler spectrum: The velocity is so low, that it is set to zero.', file=sys.stderr)
+            self.PHY["MaximumDopplerShift"] = fD = 0.0
+        if discrete and fD > 0:                                                           # FF.m:153-175
+            self.Implementation["UseDiscreteDopplerSpectrum"] = True
+            df = SamplingRate / N
+            ns = int(np.ceil(fD / df))
+            pts = np.clip(df * (np.arange(-ns - 1, ns + 1) + 0.5), -fD, fD)
+            spec = (np.arcsin(pts[1:] / fD) - np.arcsin(pts[:-1] / fD)) if DopplerModel == "Discrete-Jakes" else (pts[1:] - pts[:-1])
+            spec = spec / spec.sum()
+            self.Implementation["DiscreteDopplerSpectrum"] = np.repeat(spec[:, None], len(self.Implementation["IndexDelayTaps"]), axis=1)
         self._seed, self._count = int(seed), 0
         self._ctx = None
         self.ImpulseResponse = None
@@ -86,61 +97,92 @@ class FastFading:
             self.NewRealization()                                                         # FF.m:184
 
     # ------------------------------------------------------------------ device
+    def _n_links(self):
+        return self.Nr["txAntennas"] * self.Nr["rxAntennas"]
+
     def _device(self):
         if self._ctx is None:
             self._ctx = DeviceContext()
-            # a time-invariant channel (f_D = 0, AWGN) is uploaded as an impulse response; the sum-of-sinusoids
-            # parameters are then unused
-            model = self.PHY["DopplerModel"] if self.PHY["DopplerModel"] in ("Jakes", "Uniform") else "Jakes"
+            # a time-invariant channel (f_D = 0, AWGN) is uploaded as an impulse response; the synthesis parameters are
+            # then unused
+            model = self.PHY["DopplerModel"] if self.PHY["MaximumDopplerShift"] > 0 else "Jakes"
             self._ctx.set_channel(self.Nr["SamplesTotal"], self.Implementation["PowerDelayProfileNormalized"],
                                   self.PHY["MaximumDopplerShift"], self.PHY["dt"], self.Nr["Paths"], model)
-            self._ctx.finalize(1)
+            self._ctx.finalize(self._n_links())
         return self._ctx
 
+    def _as_cells(self, per_link):
+        """list over links (rx + nRx * tx) -> array [..., nRx, nTx] like obj.ImpulseResponse(:,:,iRx,iTx)."""
+        nT, nR = self.Nr["txAntennas"], self.Nr["rxAntennas"]
+        a = np.stack(per_link, axis=-1)
+        return a.reshape(a.shape[:-1] + (nT, nR)).swapaxes(-1, -2)
+
     def NewRealization(self, doppler_u=None, phase_u=None, gauss=None):
-        """FF.m:194-250.  Without arguments the uniforms come from the device generator keyed by
-        (seed, call count); explicit (T x Paths) uniforms reproduce exported draws."""
+        """FF.m:194-250.  Without arguments the draws come from the device generator keyed by (seed, call count);
+        explicit draws reproduce exported ones: (T x Paths) uniforms per link for 'Jakes'/'Uniform', (2 n_shift + 1, T)
+        complex normals per link for 'Discrete-*', Lt complex normals per link for block fading.  With several antennas the
+        leading axis of the explicit draws runs over the links in the reference's loop order (tx outer, rx inner)."""
         ctx = self._device()
         N, pdp = self.Nr["SamplesTotal"], self.Implementation["PowerDelayProfileNormalized"]
-        if self.Implementation["PowerDelayProfile"] == "AWGN" if isinstance(self.Implementation["PowerDelayProfile"], str) else False:
-            h = np.ones((1, 1), dtype=complex)                                            # FF.m:197-198
-            ctx.set_impulse_response(np.broadcast_to(h, (N, len(pdp)))[None].copy())
+        nl = self._n_links()
+        siso = nl == 1
+        is_awgn = isinstance(self.Implementation["PowerDelayProfile"], str) and self.Implementation["PowerDelayProfile"] == "AWGN"
+        if is_awgn:
+            h = np.ones((nl, 1, 1), dtype=complex)                                        # FF.m:197-198
+            ctx.set_impulse_response(np.broadcast_to(h, (nl, N, len(pdp))).copy())
             self._count += 1
-            self.ImpulseResponse = h
+            self.ImpulseResponse = h[0] if siso else self._as_cells(list(h))
             return
         if not self.PHY["MaximumDopplerShift"] > 0:
-            # block fading, FF.m:241-248: one complex normal per tap, constant over the block; `gauss` (Lt complex
-            # standard normals) reproduces exported draws, otherwise a NumPy generator keyed by (seed, call count)
+            # block fading, FF.m:241-248: one complex normal per tap and link, constant over the block
             if gauss is None:
                 rng = np.random.default_rng([self._seed, self._count])
-                gauss = rng.standard_normal(len(pdp)) + 1j * rng.standard_normal(len(pdp))
-            h = (np.sqrt(pdp) / np.sqrt(2) * np.asarray(gauss).reshape(-1))[None, :]
-            ctx.set_impulse_response(np.broadcast_to(h, (N, len(pdp)))[None].copy())      # H applied on the GPU as for f_D > 0
+                gauss = rng.standard_normal((nl, len(pdp))) + 1j * rng.standard_normal((nl, len(pdp)))
+            g = np.asarray(gauss).reshape(nl, len(pdp))
+            h = (np.sqrt(pdp) / np.sqrt(2))[None, :] * g
+            ctx.set_impulse_response(np.broadcast_to(h[:, None, :], (nl, N, len(pdp))).copy())   # H applied on the GPU as for f_D > 0
             self._count += 1
-            self.ImpulseResponse = h
+            self.ImpulseResponse = h[0][None, :] if siso else self._as_cells([x[None, :] for x in h])
             return
-        if doppler_u is None:
-            ctx.new_realization_seeded(1, self._seed, self._count)
+        if self.Implementation["UseDiscreteDopplerSpectrum"]:
+            if gauss is None:
+                ctx.new_realization_seeded(nl, self._seed, self._count * nl)
+            else:
+                ctx.new_realization_gauss(np.asarray(gauss).reshape(nl, 2 * ctx.n_doppler_shifts + 1, ctx.T))
+        elif doppler_u is None:
+            ctx.new_realization_seeded(nl, self._seed, self._count * nl)
         else:
-            ctx.new_realization(np.asarray(doppler_u).reshape(1, -1, order="F"),
-                                np.asarray(phase_u).reshape(1, -1, order="F"))
+            du = np.asarray(doppler_u).reshape(nl, ctx.T, self.Nr["Paths"])
+            pu = np.asarray(phase_u).reshape(nl, ctx.T, self.Nr["Paths"])
+            ctx.new_realization(np.stack([x.reshape(-1, order="F") for x in du]), np.stack([x.reshape(-1, order="F") for x in pu]))
         self._count += 1
-        self.ImpulseResponse = ctx.impulse_response(0)
+        hs = [ctx.impulse_response(b) for b in range(nl)]
+        self.ImpulseResponse = hs[0] if siso else self._as_cells(hs)
 
     def Convolution(self, signal):
-        """FF.m:253-264: r = H*s with the time-variant, banded H applied on the GPU."""
-        return self._device().convolve(np.asarray(signal), 0)
+        """FF.m:253-274: r(:,iRx) = sum_iTx H{iRx,iTx} * s(:,iTx) with the banded H applied on the GPU."""
+        s = np.asarray(signal)
+        nT, nR = self.Nr["txAntennas"], self.Nr["rxAntennas"]
+        if nT == 1 and nR == 1:
+            return self._device().convolve(s, 0)
+        s = s.reshape(s.shape[0], nT)
+        out = np.zeros((s.shape[0], nR), dtype=complex)
+        for tx in range(nT):
+            for rx in range(nR):
+                out[:, rx] += self._device().convolve(s[:, tx], rx + nR * tx)
+        return out
 
     def GetConvolutionMatrix(self):
-        """FF.m:276-295: 1x1 cell holding the sparse N x N convolution matrix."""
-        return [[self._device().convolution_matrix(0)]]
+        """FF.m:276-295: nRx x nTx cell of sparse N x N convolution matrices."""
+        nT, nR = self.Nr["txAntennas"], self.Nr["rxAntennas"]
+        return [[self._device().convolution_matrix(rx + nR * tx) for tx in range(nT)] for rx in range(nR)]
 
     # ------------------------------------------------------------------ statistics (host, setup-time)
     def GetTimeCorrelation(self):
         """FF.m:321-340."""
         N, dt, fD = self.Nr["SamplesTotal"], self.PHY["dt"], self.PHY["MaximumDopplerShift"]
         time = (np.arange(2 * N - 1) - (N - 1)) * dt
-        if self.PHY["DopplerModel"] == "Jakes":
+        if self.PHY["DopplerModel"] in ("Jakes", "Discrete-Jakes"):                      # FF.m:332-336
             return j0(np.pi * 2 * fD * time), time
         return np.sinc(2 * fD * time), time
 

@@ -61,10 +61,13 @@ class DeviceContext:
     def set_channel(self, n_samples, pdp_normalized, max_doppler, dt, paths, model="Jakes"):
         pdp = np.ascontiguousarray(pdp_normalized, dtype=np.float64)
         self._check(self.lib.chest_set_channel(self._h, n_samples, len(pdp), _ptr(pdp), max_doppler, dt, paths,
-                                               {"Jakes": 0, "Uniform": 1}[model]))
+                                               {"Jakes": 0, "Uniform": 1, "Discrete-Jakes": 2, "Discrete-Uniform": 3}[model]))
         self.N, self.Lt = n_samples, len(pdp)
         self.T = int(np.count_nonzero(pdp))
         self.paths = paths
+        ns, fd = C.c_int(0), C.c_double(0)
+        self._check(self.lib.chest_channel_info(self._h, C.byref(ns), C.byref(fd), None))
+        self.n_doppler_shifts, self.max_doppler = ns.value, fd.value
 
     def set_waveform(self, wf, G, Q):
         G, Q = np.asfortranarray(G, dtype=np.complex128), np.asfortranarray(Q, dtype=np.complex128)
@@ -144,6 +147,12 @@ class DeviceContext:
         pu = np.ascontiguousarray(phase_u, dtype=np.float64)
         batch = du.size // (self.T * self.paths)
         self._check(self.lib.chest_new_realization(self._h, batch, _ptr(du), _ptr(pu)))
+
+    def new_realization_gauss(self, gauss):
+        """'Discrete-*' Doppler models: gauss (batch, 2 n_shift + 1, T) complex standard normals (FF.m:208-209)."""
+        g = _c(gauss)
+        assert g.shape[1:] == (2 * self.n_doppler_shifts + 1, self.T)
+        self._check(self.lib.chest_new_realization_gauss(self._h, g.shape[0], _ptr(g)))
 
     def new_realization_seeded(self, batch, seed, first_rep=0):
         self._check(self.lib.chest_new_realization_seeded(self._h, batch, seed, first_rep))
@@ -236,11 +245,16 @@ class DeviceContext:
         """list of per-realization dicts (doppler_u, phase_u, bits_<scheme>, pil_idx_fbmc, pil_idx_ofdm,
         noise) -> (ChestDraws struct, keep-alive arrays)."""
         keep = {}
-        keep["du"] = np.ascontiguousarray(np.stack([d["doppler_u"].reshape(-1, order="F") for d in draws_list]))
-        keep["pu"] = np.ascontiguousarray(np.stack([d["phase_u"].reshape(-1, order="F") for d in draws_list]))
-        keep["noise"] = _c(np.stack([d["noise"] for d in draws_list]))
         st = _lib.ChestDraws()
-        st.doppler_u, st.phase_u, st.noise = _ptr(keep["du"]), _ptr(keep["pu"]), _ptr(keep["noise"])
+        if getattr(self, "n_doppler_shifts", 0) > 0:                 # 'Discrete-*': complex normals instead of uniforms
+            keep["cg"] = _c(np.stack([d["gauss"] for d in draws_list]))
+            st.channel_gauss = _ptr(keep["cg"])
+        else:
+            keep["du"] = np.ascontiguousarray(np.stack([d["doppler_u"].reshape(-1, order="F") for d in draws_list]))
+            keep["pu"] = np.ascontiguousarray(np.stack([d["phase_u"].reshape(-1, order="F") for d in draws_list]))
+            st.doppler_u, st.phase_u = _ptr(keep["du"]), _ptr(keep["pu"])
+        keep["noise"] = _c(np.stack([d["noise"] for d in draws_list]))
+        st.noise = _ptr(keep["noise"])
         for name, sid in SCHEME_ID.items():
             if name in self.schemes:
                 keep["b" + name] = np.ascontiguousarray(np.stack([d["bits_" + name] for d in draws_list]), dtype=np.uint8)

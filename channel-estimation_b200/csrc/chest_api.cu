@@ -135,6 +135,8 @@ struct Ctx {
     double fD = 0, dt = 0;
     std::vector<int> tap_delay; std::vector<double> tap_amp;
     DevBuf<int> d_tap_delay; DevBuf<double> d_tap_amp;
+    // discrete Doppler spectrum (FF.m:151-178): shifts -n_shift..n_shift, coefficient sqrt(spectrum * pdp / 2) per (bin, tap)
+    int n_shift = 0; std::vector<double> dspec; DevBuf<double> d_dcoef; DevBuf<cplx> chan_gauss;
     Waveform wf[2];
     Constellation cst[2];
     Scheme sch[3];
@@ -146,7 +148,7 @@ struct Ctx {
     DevBuf<int32_t> pilot_idx[2];
     // chest_prefetch_draws: two library-owned copies of the draw buffers filled on a copy stream
     struct Prefetch {
-        DevBuf<double> du, pu; DevBuf<cplx> noise; DevBuf<uint8_t> bits[3]; DevBuf<int32_t> pidx[2];
+        DevBuf<double> du, pu; DevBuf<cplx> noise, cg; DevBuf<uint8_t> bits[3]; DevBuf<int32_t> pidx[2];
         cudaEvent_t landed = nullptr, released = nullptr; bool used = false;
     } pf[2];
     int pf_next = 0;
@@ -285,6 +287,22 @@ int check_ready(Ctx* c) {
 }
 
 // ---------------------------------------------------------------- pipeline stages (all async on c->stream)
+int stage_channel_discrete(Ctx* c, int n_rep, const cplx* gauss_dev) {
+    dim3 grid((c->N + 127) / 128, c->T, n_rep);
+    k_synth_h_discrete<<<grid, 128, 0, c->stream>>>(c->h.p, gauss_dev, c->d_dcoef.p, c->N, c->T, c->n_shift);
+    c->launches++;
+    CK(cudaGetLastError());
+    return CHEST_OK;
+}
+int gen_chan_gauss(Ctx* c, int n_rep, uint64_t seed, int64_t first_rep) {
+    const int n = (2 * c->n_shift + 1) * c->T;
+    dim3 g((n + 63) / 64, n_rep);
+    k_rng_cnormal<<<g, 64, 0, c->stream>>>(c->chan_gauss.p, n, n_rep, RS_CHAN_GAUSS, seed, first_rep);
+    c->launches++;
+    CK(cudaGetLastError());
+    return CHEST_OK;
+}
+
 int stage_channel(Ctx* c, int n_rep, const double* du, const double* pu) {
     dim3 grid((c->N + 127) / 128, c->T, n_rep);
     k_synth_h<<<grid, 128, 2 * c->paths * sizeof(double), c->stream>>>(
@@ -457,7 +475,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     ARG(n_rep >= 1 && n_rep <= c->max_batch);
     ARG(n_iter >= 0 && n_iter <= 16);
     ARG(c->S >= 1);
-    if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "the batched loop body synthesises Jakes / Uniform realizations: f_D must be positive");
+    if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "the batched loop body synthesises time-variant realizations: f_D must be positive");
     const int S = c->S, N = c->N, TP = c->T * c->paths;
     c->cur_batch = n_rep; c->last_iter = n_iter;
     cudaStream_t st = c->stream;
@@ -468,7 +486,24 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     const uint8_t* bits[3] = {c->sch[0].bits.p, c->sch[1].bits.p, c->sch[2].bits.p};
     const int32_t* pidx[2] = {c->pilot_idx[0].p, c->pilot_idx[1].p};
     int pf_used = -1;
-    if (draws && draws->on_device) {
+    const bool discrete = c->n_shift > 0;
+    const cplx* cgauss = c->chan_gauss.p;
+    const size_t n_cg = (size_t)(2 * c->n_shift + 1) * c->T;
+    if (draws && discrete) {                                   // the discrete spectrum draws normals, not uniforms (FF.m:208-209)
+        ARG(draws->channel_gauss && draws->noise);
+        if (draws->on_device) {
+            for (int q = 0; q < 2; ++q)
+                if (c->pf[q].used && draws->channel_gauss == reinterpret_cast<const double*>(c->pf[q].cg.p)) { pf_used = q; CK(cudaStreamWaitEvent(st, c->pf[q].landed, 0)); }
+            cgauss = reinterpret_cast<const cplx*>(draws->channel_gauss);
+        } else CK(cudaMemcpyAsync(c->chan_gauss.p, draws->channel_gauss, sizeof(cplx) * n_rep * n_cg, cudaMemcpyHostToDevice, st));
+    }
+    if (draws && draws->on_device && discrete) {
+        for (int i = 0; i < 3; ++i) if (c->sch[i].set) ARG(draws->bits[i]);
+        for (int i = 0; i < 2; ++i) if (c->wf[i].set && c->wf[i].nsch) ARG(draws->pilot_idx[i]);
+        noise = reinterpret_cast<const cplx*>(draws->noise);
+        for (int i = 0; i < 3; ++i) bits[i] = draws->bits[i];
+        for (int i = 0; i < 2; ++i) pidx[i] = draws->pilot_idx[i];
+    } else if (draws && draws->on_device) {
         ARG(draws->doppler_u && draws->phase_u && draws->noise);
         for (int i = 0; i < 3; ++i) if (c->sch[i].set) ARG(draws->bits[i]);
         for (int i = 0; i < 2; ++i) if (c->wf[i].set && c->wf[i].nsch) ARG(draws->pilot_idx[i]);
@@ -478,9 +513,11 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         for (int i = 0; i < 3; ++i) bits[i] = draws->bits[i];
         for (int i = 0; i < 2; ++i) pidx[i] = draws->pilot_idx[i];
     } else if (draws) {
-        ARG(draws->doppler_u && draws->phase_u && draws->noise);
-        CK(cudaMemcpyAsync(c->doppler_u.p, draws->doppler_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->phase_u.p, draws->phase_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, st));
+        ARG(draws->noise && (discrete || (draws->doppler_u && draws->phase_u)));
+        if (!discrete) {
+            CK(cudaMemcpyAsync(c->doppler_u.p, draws->doppler_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->phase_u.p, draws->phase_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, st));
+        }
         CK(cudaMemcpyAsync(c->noise.p, draws->noise, sizeof(cplx) * (size_t)n_rep * S * N, cudaMemcpyHostToDevice, st));
         for (int i = 0; i < 3; ++i)
             if (c->sch[i].set) {
@@ -500,7 +537,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[1], st));
     // ---- stage 1 (K1): channel realization, TX symbols, s = G x, r0 = H s
-    rc = stage_channel(c, n_rep, du, pu);
+    rc = discrete ? stage_channel_discrete(c, n_rep, cgauss) : stage_channel(c, n_rep, du, pu);
     if (rc) return rc;
     for (int si = 0; si < 3; ++si) {
         if (!c->sch[si].set) continue;
@@ -579,7 +616,9 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     const size_t light_smem = (size_t)ip.pilot_rows * (2 * NC_MAX + 2) * sizeof(cplx) + cst_smem + (size_t)c->K_max * NC_MAX;
     const size_t post_smem = light_smem + (size_t)POST_NS * POST_ROWS * NC_MAX * sizeof(cplx);
     const char* light_env = getenv("CHEST_LIGHT");
-    bool use_post = !(light_env && !strcmp(light_env, "old")) && post_smem <= 110 * 1024;
+    // k_ic_light is the default: on B200 it is the faster of the two (17.3 vs 22.1 ms per 4096-realization step,
+    // profiles/r02_kic_post_vs_light.txt); CHEST_LIGHT=post selects the bulk-copy staged k_ic_post
+    bool use_post = light_env && !strcmp(light_env, "post") && post_smem <= 110 * 1024;
     int p4_all = -1;                                              // pilot-quad count shared by every scheme (register prefetch)
     for (int si = 0; si < 3; ++si) if (c->sch[si].set) { int q = (c->sch[si].P + 3) / 4; p4_all = p4_all < 0 ? q : (p4_all == q ? q : 0); }
     void (*post_kernel)(IcParams) = p4_all == 4 ? k_ic_post<4> : (p4_all == 8 ? k_ic_post<8> : k_ic_post<0>);
@@ -605,7 +644,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
                : p4s == 4 ? (m2 == 2 ? k_ic_main<4, 2, 0> : (m2 == 3 ? k_ic_main<4, 3, 1> : k_ic_main<4, 0, 0>))
                           : (m2 == 2 ? k_ic_main<8, 2, 0> : (m2 == 3 ? k_ic_main<8, 3, 1> : k_ic_main<8, 0, 0>));
     const int cfg_id = p4s * 100 + (m2 + 1) * 10 + (m1 + 1) + (use_post ? 1000 : 0);
-    if (c->ic_grid == 0 || c->ic_smem != main_smem || c->ic_cfg != cfg_id) {    // persistent main grid: one wave of resident CTAs
+    if (c->ic_grid == 0 || c->ic_smem != main_smem + post_smem || c->ic_cfg != cfg_id) {    // persistent main grid: one wave of resident CTAs
         c->ic_cfg = cfg_id;
         CK(cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CK(cudaFuncSetAttribute(k_ic_light, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -616,7 +655,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_light, k_ic_light, IC_LIGHT_THREADS, light_smem));
         if (per_sm < 1 || per_sm_light < 1)
             return fail(CHEST_ERR_STATE, "the IC kernels do not fit on an SM (too many pilots for the shared tables)");
-        c->ic_grid = per_sm * c->n_sm; c->ic_light_grid = per_sm_light * c->n_sm; c->ic_smem = main_smem;
+        c->ic_grid = per_sm * c->n_sm; c->ic_light_grid = per_sm_light * c->n_sm; c->ic_smem = main_smem + post_smem;
     }
     CK(c->queue.alloc(32));
     CK(cudaMemsetAsync(c->queue.p, 0, 32 * sizeof(unsigned int), st));
@@ -789,10 +828,27 @@ int chest_set_channel(uint64_t handle, int n_samples, int n_taps, const double* 
                       int n_paths, int model) {
     Ctx* c = from(handle);
     ARG(c && n_samples > 0 && n_taps > 0 && pdp && n_paths > 0 && dt > 0 && fd >= 0);   // fd = 0: time-invariant, see chest_set_impulse_response
-    ARG(model == CHEST_DOPPLER_JAKES || model == CHEST_DOPPLER_UNIFORM);
+    ARG(model >= CHEST_DOPPLER_JAKES && model <= CHEST_DOPPLER_DISCRETE_UNIFORM);
     if (c->N && c->N != n_samples) return fail(CHEST_ERR_ARG, "Total number of samples must be the same for the channel and every waveform");
     CK(cudaSetDevice(c->device));
+    const bool discrete = model >= CHEST_DOPPLER_DISCRETE_JAKES;
+    if (discrete && fd > 0 && fd / ((1.0 / dt) / n_samples) <= 0.5) fd = 0;        // FF.m:146-149: velocity too low for a discrete spectrum
     c->N = n_samples; c->Lt = n_taps; c->fD = fd; c->dt = dt; c->paths = n_paths; c->model = model;
+    c->n_shift = 0; c->dspec.clear();
+    if (discrete && fd > 0) {                                                      // FF.m:151-175
+        const double df = (1.0 / dt) / n_samples;
+        const int ns = (int)std::ceil(fd / df);
+        std::vector<double> pts(2 * ns + 2);
+        for (int q = 0; q < 2 * ns + 2; ++q) pts[q] = std::min(fd, std::max(-fd, df * ((q - ns - 1) + 0.5)));
+        std::vector<double> sp(2 * ns + 1);
+        double tot = 0;
+        for (int q = 0; q < 2 * ns + 1; ++q) {
+            sp[q] = model == CHEST_DOPPLER_DISCRETE_JAKES ? std::asin(pts[q + 1] / fd) - std::asin(pts[q] / fd) : pts[q + 1] - pts[q];
+            tot += sp[q];
+        }
+        for (double& x : sp) x /= tot;
+        c->n_shift = ns; c->dspec = sp;                                            // sp[q]: shift q - ns
+    }
     c->tap_delay.clear(); c->tap_amp.clear();
     for (int m = 0; m < n_taps; ++m)
         if (pdp[m] != 0.0) { c->tap_delay.push_back(m); c->tap_amp.push_back(std::sqrt(pdp[m])); }   // FF.m:131,237
@@ -800,6 +856,15 @@ int chest_set_channel(uint64_t handle, int n_samples, int n_taps, const double* 
     ARG(c->T > 0);
     CK(c->d_tap_delay.upload(c->tap_delay, c->stream));
     CK(c->d_tap_amp.upload(c->tap_amp, c->stream));
+    if (c->n_shift > 0) {      // rows in the reference's order: shifts 0..ns (GaussUncorr1), then -ns..-1 (GaussUncorr2), FF.m:214-217
+        const int ns = c->n_shift, nb = 2 * ns + 1;
+        std::vector<double> coef((size_t)nb * c->T);
+        for (int b = 0; b < nb; ++b) {
+            const int shift = b <= ns ? b : b - nb;
+            for (int t = 0; t < c->T; ++t) coef[(size_t)b * c->T + t] = std::sqrt(c->dspec[shift + ns]) * c->tap_amp[t] / std::sqrt(2.0);
+        }
+        CK(c->d_dcoef.upload(coef, c->stream));
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->chan_set = true; c->finalized = false;
     return CHEST_OK;
@@ -1056,6 +1121,7 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
         bool fuse = true;
         for (int i = 0; i < K; ++i) {
             if (col0[i] >= P && d_direct[i] != col0[i] - P) fuse = false;     // the row's entry refers to a symbol decided elsewhere
+            if (d_direct[i] >= 0 && col0[i] >= 0 && col0[i] < P) fuse = false; // a decided row whose entry refers to a pilot
             if (need[i] && col0[i] != -2) fuse = false;                        // x-hat and v of the row would share a slot
         }
         if (getenv("CHEST_POST_NOFUSE")) fuse = false;                         // test knob: exercise the separate phase-A pass
@@ -1384,6 +1450,7 @@ int chest_finalize(uint64_t handle, int max_batch) {
         if (w.nsch) CK(c->pilot_idx[wfi].alloc((size_t)B * c->sch[w.sch[0]].P));
     }
     CK(c->doppler_u.alloc((size_t)B * c->T * c->paths)); CK(c->phase_u.alloc((size_t)B * c->T * c->paths));
+    CK(c->chan_gauss.alloc((size_t)B * (2 * c->n_shift + 1) * c->T));
     CK(c->noise.alloc((size_t)B * std::max(S, 1) * N)); CK(c->h.alloc((size_t)B * c->T * N));
     CK(c->err.alloc((size_t)B * std::max(S, 1) * 17 * 12));
     c->max_batch = B; c->cur_batch = B; c->ctas_for_batch = -1;
@@ -1397,6 +1464,7 @@ int chest_new_realization(uint64_t handle, int batch, const double* du, const do
     int rc = check_ready(c); if (rc) return rc;
     ARG(batch >= 1 && batch <= c->max_batch && du && pu);
     if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "time-invariant channel (f_D = 0): upload the impulse response with chest_set_impulse_response");
+    if (c->n_shift > 0) return fail(CHEST_ERR_STATE, "discrete Doppler spectrum: realizations are drawn from normals (chest_new_realization_gauss)");
     CK(cudaSetDevice(c->device));
     size_t n = (size_t)batch * c->T * c->paths;
     CK(cudaMemcpyAsync(c->doppler_u.p, du, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1413,6 +1481,13 @@ int chest_new_realization_seeded(uint64_t handle, int batch, uint64_t seed, int6
     ARG(batch >= 1 && batch <= c->max_batch);
     if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "time-invariant channel (f_D = 0): upload the impulse response with chest_set_impulse_response");
     CK(cudaSetDevice(c->device));
+    if (c->n_shift > 0) {
+        c->cur_batch = batch;
+        rc = gen_chan_gauss(c, batch, seed, first_rep); if (rc) return rc;
+        rc = stage_channel_discrete(c, batch, c->chan_gauss.p); if (rc) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+        return CHEST_OK;
+    }
     int n = c->T * c->paths;
     dim3 grid((n / 2 + 1 + 127) / 128, batch);
     k_rng_uniform<<<grid, 128, 0, c->stream>>>(c->doppler_u.p, n, batch, RS_DOPPLER, seed, first_rep);
@@ -1421,6 +1496,28 @@ int chest_new_realization_seeded(uint64_t handle, int batch, uint64_t seed, int6
     c->cur_batch = batch;
     rc = stage_channel(c, batch, c->doppler_u.p, c->phase_u.p); if (rc) return rc;
     CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+int chest_new_realization_gauss(uint64_t handle, int batch, const double* gauss) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(batch >= 1 && batch <= c->max_batch && gauss);
+    if (c->n_shift <= 0) return fail(CHEST_ERR_STATE, "chest_new_realization_gauss needs a 'Discrete-*' Doppler model with f_D > 0");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->chan_gauss.p, gauss, sizeof(cplx) * (size_t)batch * (2 * c->n_shift + 1) * c->T, cudaMemcpyHostToDevice, c->stream));
+    c->cur_batch = batch;
+    rc = stage_channel_discrete(c, batch, c->chan_gauss.p); if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+int chest_channel_info(uint64_t handle, int* n_doppler_shifts, double* max_doppler_hz, int* n_nonzero_taps) {
+    Ctx* c = from(handle);
+    ARG(c && c->chan_set);
+    if (n_doppler_shifts) *n_doppler_shifts = c->n_shift;
+    if (max_doppler_hz) *max_doppler_hz = c->fD;
+    if (n_nonzero_taps) *n_nonzero_taps = c->T;
     return CHEST_OK;
 }
 
@@ -1679,11 +1776,14 @@ int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, ch
     Ctx* c = from(handle);
     int rc = check_ready(c); if (rc) return rc;
     ARG(n_rep >= 1 && n_rep <= c->max_batch && host && dev && !host->on_device);
-    ARG(host->doppler_u && host->phase_u && host->noise);
+    const bool discrete = c->n_shift > 0;
+    const size_t n_cg = (size_t)(2 * c->n_shift + 1) * c->T;
+    ARG(host->noise && (discrete ? host->channel_gauss != nullptr : (host->doppler_u && host->phase_u)));
     CK(cudaSetDevice(c->device));
     const int S = c->S, N = c->N, TP = c->T * c->paths, B = c->max_batch;
     for (auto& a : c->pf) {                                        // both sets are allocated by the first call
         CK(a.du.alloc((size_t)B * TP)); CK(a.pu.alloc((size_t)B * TP)); CK(a.noise.alloc((size_t)B * S * N));
+        CK(a.cg.alloc((size_t)B * n_cg));
         for (int i = 0; i < 3; ++i) if (c->sch[i].set) CK(a.bits[i].alloc((size_t)B * c->sch[i].n_bits));
         for (int i = 0; i < 2; ++i) if (c->wf[i].set && c->wf[i].nsch) CK(a.pidx[i].alloc((size_t)B * c->sch[c->wf[i].sch[0]].P));
     }
@@ -1691,10 +1791,14 @@ int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, ch
     c->pf_next ^= 1;
     cudaStream_t cs = c->copy_stream;
     if (q.used) CK(cudaStreamWaitEvent(cs, q.released, 0));       // the batch that read this set has finished with it
-    CK(cudaMemcpyAsync(q.du.p, host->doppler_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(q.pu.p, host->phase_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
+    if (discrete) CK(cudaMemcpyAsync(q.cg.p, host->channel_gauss, sizeof(cplx) * n_rep * n_cg, cudaMemcpyHostToDevice, cs));
+    else {
+        CK(cudaMemcpyAsync(q.du.p, host->doppler_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(q.pu.p, host->phase_u, sizeof(double) * n_rep * TP, cudaMemcpyHostToDevice, cs));
+    }
     CK(cudaMemcpyAsync(q.noise.p, host->noise, sizeof(cplx) * (size_t)n_rep * S * N, cudaMemcpyHostToDevice, cs));
     *dev = chest_draws{};
+    dev->channel_gauss = discrete ? reinterpret_cast<const double*>(q.cg.p) : nullptr;
     for (int i = 0; i < 3; ++i)
         if (c->sch[i].set) {
             ARG(host->bits[i]);
@@ -1718,7 +1822,7 @@ int chest_prefetch_draws(uint64_t handle, int n_rep, const chest_draws* host, ch
 int64_t chest_draws_bytes(uint64_t handle, int n_rep) {
     Ctx* c = from(handle);
     if (!c) return 0;
-    int64_t per = 2 * (int64_t)c->T * c->paths * 8 + (int64_t)c->S * c->N * 16;
+    int64_t per = (c->n_shift > 0 ? (int64_t)(2 * c->n_shift + 1) * c->T * 16 : 2 * (int64_t)c->T * c->paths * 8) + (int64_t)c->S * c->N * 16;
     for (int si = 0; si < 3; ++si) if (c->sch[si].set) per += c->sch[si].n_bits;
     for (int wfi = 0; wfi < 2; ++wfi) if (c->wf[wfi].set && c->wf[wfi].nsch) per += 4 * c->sch[c->wf[wfi].sch[0]].P;
     return per * n_rep;
@@ -1731,11 +1835,15 @@ int chest_generate_draws(uint64_t handle, int n_rep, uint64_t seed, int64_t firs
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     int n = c->T * c->paths;
-    dim3 gu((n / 2 + 1 + 127) / 128, n_rep);
-    k_rng_uniform<<<gu, 128, 0, st>>>(c->doppler_u.p, n, n_rep, RS_DOPPLER, seed, first_rep);
-    k_rng_uniform<<<gu, 128, 0, st>>>(c->phase_u.p, n, n_rep, RS_PHASE, seed, first_rep);
-    c->launches += 2;
+    if (c->n_shift > 0) { int rc2 = gen_chan_gauss(c, n_rep, seed, first_rep); if (rc2) return rc2; }
+    else {
+        dim3 gu((n / 2 + 1 + 127) / 128, n_rep);
+        k_rng_uniform<<<gu, 128, 0, st>>>(c->doppler_u.p, n, n_rep, RS_DOPPLER, seed, first_rep);
+        k_rng_uniform<<<gu, 128, 0, st>>>(c->phase_u.p, n, n_rep, RS_PHASE, seed, first_rep);
+        c->launches += 2;
+    }
     std::memset(out, 0, sizeof(*out));
+    out->channel_gauss = c->n_shift > 0 ? reinterpret_cast<const double*>(c->chan_gauss.p) : nullptr;
     for (int si = 0; si < 3; ++si) {
         Scheme& s = c->sch[si];
         if (!s.set) continue;

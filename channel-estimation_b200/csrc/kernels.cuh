@@ -103,6 +103,41 @@ __global__ void k_synth_h(cplx* __restrict__ h, const double* __restrict__ doppl
     h[((int64_t)rep * T + tap) * N + n] = cmake(a * (sr / inv), a * (si / inv));
 }
 
+// 'Discrete-Jakes' / 'Discrete-Uniform' (FF.m:203-221): the impulse response of a tap is the inverse DFT of a spectrum with
+// 2 n_shift + 1 non-zero bins (Doppler shifts -n_shift .. n_shift times fs/N), i.e. a pruned inverse DFT:
+//   h[n] = sum_b coef[b] * gauss[b] * exp(j 2 pi f_b n / N),   coef[b] = sqrt(spectrum_b * pdp_tap / 2)
+// gauss: [rep][2 n_shift + 1][T] complex standard normals in the reference's order: rows 0..n_shift are GaussUncorr1
+// (shifts 0..n_shift), rows n_shift+1 .. 2 n_shift are GaussUncorr2 (shifts -n_shift .. -1).
+__global__ void k_synth_h_discrete(cplx* __restrict__ h, const cplx* __restrict__ gauss, const double* __restrict__ coef,
+                                   int N, int T, int n_shift) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, tap = blockIdx.y, rep = blockIdx.z;
+    if (n >= N) return;
+    const int nb = 2 * n_shift + 1;
+    const cplx* gz = gauss + (int64_t)rep * nb * T;
+    cplx acc = cmake(0.0, 0.0);
+    for (int b = 0; b < nb; ++b) {
+        const int f = b <= n_shift ? b : b - nb;                  // Doppler bin: 0..n_shift, -n_shift..-1
+        const int64_t m = (((int64_t)f * n) % N + N) % N;
+        double s_, c_;
+        sincospi(2.0 * (double)m / (double)N, &s_, &c_);
+        const cplx a = gz[b * T + tap];
+        const double w = coef[b * T + tap];
+        cfma(acc, cmake(a.x * w, a.y * w), cmake(c_, s_));
+    }
+    h[((int64_t)rep * T + tap) * N + n] = acc;
+}
+// complex standard normals: out[rep][n_per_rep]
+__global__ void k_rng_cnormal(cplx* __restrict__ out, int n_per_rep, int n_rep, int stream, uint64_t seed, int64_t first_rep) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, rep = blockIdx.y;
+    if (rep >= n_rep || e >= n_per_rep) return;
+    const uint64_t r = (uint64_t)(first_rep + rep);
+    Philox4 p = philox4x32_10((uint32_t)e, (uint32_t)r, (uint32_t)stream, (uint32_t)(r >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = u53(p.v[0], p.v[1]), u2 = u53(p.v[2], p.v[3]);
+    double rad = sqrt(-2.0 * log(u1)), s_, c_;
+    sincospi(2.0 * u2, &s_, &c_);
+    out[(int64_t)rep * n_per_rep + e] = cmake(rad * c_, rad * s_);
+}
+
 // r[col][n] = sum_tap h[rep(col)][tap][n] * s[col][n - delay_tap]   (banded H, never materialised)
 // cols are laid out [group][rep]: rep = col % n_rep.
 __global__ void k_apply_h(cplx* __restrict__ r, const cplx* __restrict__ s, const cplx* __restrict__ h,

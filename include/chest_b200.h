@@ -49,6 +49,10 @@ extern "C" {
 /* Doppler models of Channel.FastFading.NewRealization (FF.m:225-232) */
 #define CHEST_DOPPLER_JAKES    0
 #define CHEST_DOPPLER_UNIFORM  1
+/* 'Discrete-Jakes' / 'Discrete-Uniform' (FF.m:151-182, 203-221): 2 n_shift + 1 discrete Doppler shifts spaced fs/N, the
+ * realization is the inverse DFT of their weighted complex normals (a pruned inverse DFT on the device) */
+#define CHEST_DOPPLER_DISCRETE_JAKES    2
+#define CHEST_DOPPLER_DISCRETE_UNIFORM  3
 /* MMSE matrix variants (DS.m:492): W_MMSE / W_MMSE_noInterference */
 #define CHEST_W_WITH_INTERFERENCE  0
 #define CHEST_W_NO_INTERFERENCE    1
@@ -130,6 +134,12 @@ int chest_new_realization(uint64_t handle, int batch, const double* doppler_u, c
  * (seed, first_rep + b) -- see DESIGN.md "Random numbers". */
 int chest_new_realization_seeded(uint64_t handle, int batch, uint64_t seed, int64_t first_rep);
 
+/* NewRealization of a 'Discrete-*' channel from explicit normals (layout of chest_draws.channel_gauss). */
+int chest_new_realization_gauss(uint64_t handle, int batch, const double* gauss);
+/* What the channel constructor derived: number of discrete Doppler shifts per side (0 unless 'Discrete-*'), the maximum
+ * Doppler shift in use (FF.m:146-149 sets it to 0 when too low for a discrete spectrum), non-zero taps.  Any may be NULL. */
+int chest_channel_info(uint64_t handle, int* n_doppler_shifts, double* max_doppler_hz, int* n_nonzero_taps);
+
 /* Load `batch` time-variant impulse responses computed elsewhere (channel realizations exported
  * from the reference, or the banded pseudo-channels of the correlation setup, DS.m:213,260):
  * h is batch x (N x Lt) complex, column-major per realization; only the non-zero taps are used. */
@@ -182,6 +192,9 @@ typedef struct chest_draws {
     const int32_t* pilot_idx[CHEST_N_WF];  /* n_rep x P, 0-based SymbolMapping idx DS.m:365,367 */
     const double*  noise;          /* n_rep x n_snr x N complex, randn+1j*randn    DS.m:399 */
     int            on_device;
+    /* 'Discrete-*' Doppler models only (doppler_u / phase_u are then unused): n_rep x (2 n_shift + 1) x T complex standard
+     * normals, rows 0..n_shift = GaussUncorr1 / sqrt(N^2/2), rows n_shift+1..2 n_shift = GaussUncorr2   FF.m:208-209 */
+    const double*  channel_gauss;
 } chest_draws;
 
 /* Asynchronous upload of host draws into one of two library-owned device buffer sets (a dedicated copy

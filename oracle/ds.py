@@ -239,7 +239,11 @@ def new_draws(S, rng):
     """One realization's random draws in the order DS.m:352-368,399 consumes them."""
     cfg = S["cfg"]
     T = len(S["chan"].Implementation["IndexDelayTaps"])
-    d = dict(doppler_u=rng.random((T, cfg.Paths)), phase_u=rng.random((T, cfg.Paths)))
+    if S["chan"].Implementation.get("UseDiscreteDopplerSpectrum"):         # FF.m:208-209: normals, not uniforms
+        nb = S["chan"].Implementation["DiscreteDopplerSpectrum"].shape[0]
+        d = dict(gauss=rng.standard_normal((nb, T)) + 1j * rng.standard_normal((nb, T)))
+    else:
+        d = dict(doppler_u=rng.random((T, cfg.Paths)), phase_u=rng.random((T, cfg.Paths)))
     for sc in ("aux", "cod", "ofdm"):
         if sc in S["schemes"]:
             m = S["schemes"][sc]
@@ -280,7 +284,7 @@ def ds_realization(S, draws, faithful=False, keep=False):
     cfg, P, N = S["cfg"], S["P"], S["N"]
     nS, nI = len(cfg.M_SNR_dB), cfg.NrIterations
     chan = S["chan"]
-    chan.NewRealization(draws["doppler_u"], draws["phase_u"])                               # :352
+    chan.NewRealization(draws.get("doppler_u"), draws.get("phase_u"), draws.get("gauss"))   # :352
     H = chan.GetConvolutionMatrix()                                                         # :381
     const = {"PAM": S["PAM"], "QAM": S["QAM"]}
     out = {"err": {}, "nbits": {}, "nbits_noedge": {}}

@@ -391,8 +391,8 @@ def test_time_invariant_channel_branches():
     awgn = chest_b200.Channel.FastFading(360e3, "AWGN", N, 0, "Jakes", 200, 1, 1, 0)
     assert awgn.ImpulseResponse.shape == (1, 1) and awgn.ImpulseResponse[0, 0] == 1
     assert rel(np.asarray(awgn.Convolution(s)).reshape(-1), s) < 1e-15
-    with pytest.raises(NotImplementedError):
-        chest_b200.Channel.FastFading(360e3, "VehicularA", N, 1158.18, "Discrete-Jakes", 200, 1, 1, 0)
+    with pytest.raises(ValueError):
+        chest_b200.Channel.FastFading(360e3, "VehicularA", N, 1158.18, "Gaussian", 200, 1, 1, 0)
 
 
 def test_prefetched_draws_equal_direct_upload(gpu_ctx, ds_default):

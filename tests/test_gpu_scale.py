@@ -317,8 +317,9 @@ def test_device_setup_paper_geometry_wrapped_entries(ds_paper):
 
 
 def test_post_kernel_variants_agree(ds_default):
-    """k_ic_post (TMA-staged, fused decide + precode) against its own un-fused phase-A path (CHEST_POST_NOFUSE) and the
-    previous k_ic_light (CHEST_LIGHT=old): identical counts and state on the same seeded batch, ragged tail included."""
+    """k_ic_light (default) against k_ic_post (CHEST_LIGHT=post: y_ic staged by cp.async.bulk through an mbarrier ring,
+    fused decide + precode) and k_ic_post's un-fused phase-A path (CHEST_POST_NOFUSE): identical counts and state on the
+    same seeded batch, ragged tail included."""
     from tests.helpers import context_from_oracle
     S = ds_default
     B, seed, first = 37, 8, 900
@@ -339,7 +340,7 @@ def test_post_kernel_variants_agree(ds_default):
                     os.environ[k] = v
         return err, st
     base, st0 = run({})
-    for env in ({"CHEST_POST_NOFUSE": "1"}, {"CHEST_LIGHT": "old"}):
+    for env in ({"CHEST_LIGHT": "post"}, {"CHEST_LIGHT": "post", "CHEST_POST_NOFUSE": "1"}):
         err, st = run(env)
         assert np.array_equal(err, base), env
         for a, b in zip(st, st0):
@@ -387,3 +388,73 @@ def test_fft_modem_equals_oracle_fft_modem(cfg):
 
 def rel(a, b):
     return np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b))
+
+
+def test_discrete_doppler_and_mimo_cells():
+    """the 'Discrete-Jakes' / 'Discrete-Uniform' NewRealization branch (FF.m:151-182, 203-221: IFFT
+    synthesis = pruned inverse DFT on the device) against the oracle on the same normals, and nTx x nRx antennas
+    (FF.m:223-224, 258-262, 279-285): cell {nRx, nTx} of convolution matrices, Convolution summing over the transmit
+    antennas -- each link against a 1x1 oracle object fed with that link's draws."""
+    import chest_b200
+    from oracle.fast_fading import FastFading as RefFF
+    rng = np.random.default_rng(9)
+    N = 540
+    for model in ("Discrete-Jakes", "Discrete-Uniform"):
+        ch = chest_b200.Channel.FastFading(15e3 * 14 * 14, "VehicularA", N, 1158.18 * 8, model, 200, 1, 1, 0, create_device=False)
+        ref = RefFF(15e3 * 14 * 14, "VehicularA", N, 1158.18 * 8, model, 200, 1, 1, False)
+        nb, T = ref.Implementation["DiscreteDopplerSpectrum"].shape[0], len(ref.Implementation["IndexDelayTaps"])
+        g = rng.standard_normal((nb, T)) + 1j * rng.standard_normal((nb, T))
+        ch.NewRealization(gauss=g); ref.NewRealization(gauss=g)
+        assert ch.ImpulseResponse.shape == ref.ImpulseResponse.shape and rel(ch.ImpulseResponse, ref.ImpulseResponse) < 1e-12
+        s = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+        assert rel(np.asarray(ch.Convolution(s)).reshape(-1), ref.Convolution(s)) < 1e-12
+        assert rel(ch.GetConvolutionMatrix()[0][0].toarray(), ref.GetConvolutionMatrix().toarray()) < 1e-12
+        ch.NewRealization()                                          # device generator: unit average power per realization
+        assert 0.05 < np.mean(np.sum(np.abs(ch.ImpulseResponse) ** 2, axis=1)) < 8
+    # 2 x 3 MIMO, Jakes: links in the reference's loop order (tx outer, rx inner)
+    nT, nR, paths = 2, 3, 50
+    mimo = chest_b200.Channel.FastFading(360e3, "VehicularA", N, 1158.18, "Jakes", paths, nT, nR, 0, create_device=False)
+    du = rng.random((nT * nR, 2, paths)); pu = rng.random((nT * nR, 2, paths))
+    mimo.NewRealization(du, pu)
+    assert mimo.ImpulseResponse.shape == (N, 2, nR, nT)
+    s = rng.standard_normal((N, nT)) + 1j * rng.standard_normal((N, nT))
+    out = mimo.Convolution(s)
+    cells = mimo.GetConvolutionMatrix()
+    assert out.shape == (N, nR) and len(cells) == nR and len(cells[0]) == nT
+    expect = np.zeros((N, nR), dtype=complex)
+    for tx in range(nT):
+        for rx in range(nR):
+            ref = RefFF(360e3, "VehicularA", N, 1158.18, "Jakes", paths, 1, 1, False)
+            ref.NewRealization(du[rx + nR * tx], pu[rx + nR * tx])
+            assert rel(mimo.ImpulseResponse[:, :, rx, tx], ref.ImpulseResponse) < 1e-12
+            assert rel(cells[rx][tx].toarray(), ref.GetConvolutionMatrix().toarray()) < 1e-12
+            expect[:, rx] += ref.Convolution(s[:, tx])
+    assert rel(out, expect) < 1e-12
+    # block fading with antennas: one normal per tap and link (FF.m:241-248)
+    bf = chest_b200.Channel.FastFading(360e3, "VehicularA", N, 0, "Jakes", paths, 2, 2, 0, create_device=False)
+    g = rng.standard_normal((4, 2)) + 1j * rng.standard_normal((4, 2))
+    bf.NewRealization(gauss=g)
+    assert bf.ImpulseResponse.shape == (1, 2, 2, 2)
+    pdp = bf.Implementation["PowerDelayProfileNormalized"]
+    assert rel(bf.ImpulseResponse[0, :, 1, 0], np.sqrt(pdp / 2) * g[1]) < 1e-15
+
+
+def test_loop_body_with_discrete_doppler_channel():
+    """DS.m:350-565 with DopplerModel = 'Discrete-Jakes' (the reference's constructor accepts it, FF.m:151): explicit
+    normals for the channel, same counts as the oracle; the seeded run is reproducible and batch-independent."""
+    from oracle.ds import DSConfig, ds_setup, ds_realization, new_draws
+    from tests.helpers import context_from_oracle
+    S = ds_setup(DSConfig(DopplerModel="Discrete-Jakes", M_SNR_dB=(15, 35), NrIterations=2))
+    ctx = context_from_oracle(S, max_batch=5)
+    assert ctx.n_doppler_shifts == 2
+    rng = np.random.default_rng(3)
+    draws = [new_draws(S, rng) for _ in range(3)]
+    assert draws[0]["gauss"].shape == (5, 2)
+    st, keep = ctx.pack_draws(draws)
+    err = ctx.run_batch(3, 2, st)
+    for r in range(3):
+        assert np.array_equal(err[r], err_from_oracle(ds_realization(S, draws[r]), 2))
+    a = ctx.run_batch(5, 2, None, seed=4, first_rep=10)
+    b = ctx.run_batch(2, 2, None, seed=4, first_rep=13)
+    assert np.array_equal(a[3:], b) and a.sum() > 0
+    ctx.close()

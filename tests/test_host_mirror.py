@@ -99,8 +99,14 @@ def test_fast_fading_constructor_tables():
         assert np.allclose(a.Implementation["PowerDelayProfileNormalized"], b.Implementation["PowerDelayProfileNormalized"])
     with pytest.raises(ValueError):
         FastFading(1e6, "NoSuchModel", 10, 10.0, "Jakes", 4, create_device=False)
-    with pytest.raises(NotImplementedError):
-        FastFading(1e6, "Flat", 10, 10.0, "Discrete-Jakes", 4, create_device=False)
+    d = FastFading(360e3, "VehicularA", 540, 1158.18, "Discrete-Jakes", 4, 2, 2, create_device=False)   # FF.m:151-175
+    r = Ref(360e3, "VehicularA", 540, 1158.18, "Discrete-Jakes", 4)
+    assert np.allclose(d.Implementation["DiscreteDopplerSpectrum"], r.Implementation["DiscreteDopplerSpectrum"], atol=1e-15)
+    assert d.Nr["txAntennas"] == 2 and d.Nr["rxAntennas"] == 2
+    slow = FastFading(360e3, "VehicularA", 540, 100.0, "Discrete-Uniform", 4, create_device=False)      # FF.m:146-149
+    assert slow.PHY["MaximumDopplerShift"] == 0
+    with pytest.raises(ValueError):
+        FastFading(1e6, "Flat", 10, 10.0, "Gaussian", 4, create_device=False)
 
 
 def test_product_fails_loudly_without_gpu():
