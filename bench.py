@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "channel realizations/sec (est+IC+BER)"
 UNIT = "realizations/s"
+WORKLOAD_PAPER = ("DoublySelectiveChannelEstimation.m with the paper block DS.m:42-46 enabled: N=7350, OFDM K=672 + FBMC-Aux + "
+                  "FBMC-Cod K=1440, P=32, 6 taps, 16 SNR points (10:2:40 dB), 4 IC iterations, estimated + perfect CSI")
 WORKLOAD = ("DoublySelectiveChannelEstimation.m default parameters (DS.m:16-37): N=540, OFDM K=336 + FBMC-Aux + "
             "FBMC-Cod K=720, P=16, 7 SNR points, 4 IC iterations, estimated + perfect CSI, 24 BER outputs")
 
@@ -44,6 +46,11 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=48, help="realizations timed for cpu_baseline (about 13 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-sample", action="store_true", help="skip the oracle check of sampled realizations")
+    ap.add_argument("--workload", default="default", choices=["default", "paper", "sweep", "sv"],
+                    help="default: DS.m default parameters (BASELINE.json configs[1], the headline); paper: DS.m:42-46 "
+                         "(configs[2]); sweep: velocity sweep, 1e5 realizations over all GPUs including setup (configs[3]); "
+                         "sv: SimpleVersion_DoublyFlat.m chain with the FFT modem on the device (configs[0])")
+    ap.add_argument("--sweep-realizations", type=int, default=100000)
     return ap.parse_args()
 
 
@@ -254,8 +261,17 @@ def run_b200(args):
     schemes = args.schemes.split(",")
     B, K, W, I = args.batch, args.steps, args.warmup, 4
     parity_failed = False
+    paper = args.workload == "paper"
+    workload = WORKLOAD
+    if paper:
+        if args.batch == 4096:
+            B = 512
+        workload = WORKLOAD_PAPER
     t0 = time.perf_counter()
-    sim = DoublySelectiveSimulation(schemes=tuple(schemes), max_batch=B, device=local, seed=1234)
+    if paper:
+        sim = DoublySelectiveSimulation.paper(schemes=tuple(schemes), max_batch=B, device=local, seed=1234)
+    else:
+        sim = DoublySelectiveSimulation(schemes=tuple(schemes), max_batch=B, device=local, seed=1234)
     setup_s = time.perf_counter() - t0
     ctx = sim.ctx
     n_snr = len(sim.Pn)
@@ -379,7 +395,7 @@ def run_b200(args):
             "metric": METRIC, "value": world * B * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "schemes": schemes, "realizations_per_step_per_gpu": B,
+            "config": {"workload": workload, "schemes": schemes, "realizations_per_step_per_gpu": B,
                        "parallelism": "realizations sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "working set larger than L2 (per IC launch %.2f GB of MMSE tiles + %.1f GB of per-unit v / y_ic "
                              "columns vs 126 MB L2)" % (wm["w_bytes_per_ic_launch"] / 1e9, ctx.n_units() * 2 * 720 * 16 * 16 / 1e9),
@@ -417,7 +433,31 @@ def run_b200(args):
             "wall_ms_per_step": wall_ms / K, "launches_per_step": launches_per_step, "setup_s": setup_s,
             "sanity_ber_40dB_last_iteration": ber40,
         }
-        if world == 1 and not args.no_dense_leg:
+        # small kernels of the step (sincos/s of the synthesis, GB/s of the banded apply)
+        T_taps, paths, N_s = ctx.T, ctx.paths, sim.N
+        n_vec = sum(1 for n_ in sim.sch)                                   # transmit vectors per realization
+        synth_ms, apply_ms = kern_sum["k_synth_h"] / K, kern_sum["k_apply_h"] / K
+        demod_ms = stage_sum["k3_demod"] / K
+        out["roofline_small_kernels"] = {
+            "k_synth_h": {"bound": "fp64 alu (sincos)", "sincos_per_s": B * T_taps * paths * N_s / (synth_ms * 1e-3) if synth_ms > 0 else None,
+                          "ms_per_step": synth_ms, "note": "T * paths * N complex exponentials per realization (FF.m:235); writes 16 T N bytes"},
+            "k_apply_h": {"bound": "hbm", "achieved": B * n_vec * 16.0 * N_s * (T_taps + 2) / (apply_ms * 1e-3) / 1e9 if apply_ms > 0 else None,
+                          "peak": hbm_peak, "unit": "GB/s",
+                          "frac": B * n_vec * 16.0 * N_s * (T_taps + 2) / (apply_ms * 1e-3) / 1e9 / hbm_peak if apply_ms > 0 else None,
+                          "ms_per_step": apply_ms, "note": "16 N (T + 2) algorithmic bytes per vector (read h, read s, write r), SURVEY.md 8d"},
+            "k_gemm_demod": {"bound": "tensor", "achieved": B * wm["txdemod_flops"] / (demod_ms * 1e-3) / 1e12 if demod_ms > 0 else None,
+                             "peak": peak_dmma, "unit": "TFLOP/s", "ms_per_step": demod_ms,
+                             "note": "y = Q^H (r0 + noise) for every (scheme, SNR, realization); flops include the TX GEMM s = G x"},
+            "k_tx_symbols": {"ms_per_step": kern_sum["k_tx_symbols"] / K}, "modulate_gemm": {"ms_per_step": kern_sum["modulate_gemm"] / K}}
+        light_ms = kern_sum["k_ic_light"] / (K * (I + 1))
+        light_bytes = ctx.n_units() * 2.0 * 16 * 16 * (sum(s_["K"] for s_ in ctx.schemes.values()) / max(1, len(ctx.schemes)))
+        out["roofline_k_ic_light"] = {"kernel": "k_ic_light (LS pilots, W_diag x hP, equalise, decide, count, precode v)", "bound": "hbm",
+                                      "achieved": light_bytes / (light_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": light_bytes / (light_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": light_ms,
+                                      "algorithmic_bytes_per_launch": light_bytes,
+                                      "note": "y_ic read + v written once per unit (16 columns x K rows x 16 B each way); the kernel is "
+                                              "instruction bound, not bandwidth bound: profiles/r02_kic_post_vs_light.txt"}
+        if world == 1 and not args.no_dense_leg and not paper:
             # the same workload with D = Q^H H G materialised per realization (K2) and applied densely: the rooflines
             # of k_gemm_d (FP64 tensor) and k_apply_hg (HBM) come from this leg; never fatal for the main line
             try:
@@ -425,7 +465,7 @@ def run_b200(args):
                                                       peak_dmma, hbm_peak, hbm_src)
             except Exception as e:                              # noqa: BLE001
                 out["dense_d_mode"] = {"error": repr(e)[:200]}
-        if world == 1 and set(schemes) != {"ofdm"} and not args.no_ofdm_only:
+        if world == 1 and set(schemes) != {"ofdm"} and not args.no_ofdm_only and not paper:
             # the same loop body with the OFDM chain alone (the narrow reading of "default params: OFDM"), for
             # comparison: resident value only, same timing rules; never fatal for the main line
             try:
@@ -433,13 +473,18 @@ def run_b200(args):
                                                         None if args.no_cpu_baseline else args.cpu_sample)
             except Exception as e:                              # noqa: BLE001
                 out["ofdm_chain_only"] = {"error": repr(e)[:200]}
-        if not args.no_parity_sample:
+        if paper:
+            out["parity_sample"] = "not run (the oracle's setup at the paper geometry takes minutes; parity at this geometry: tests/test_gpu_parity.py::test_paper_geometry_parity, tests/test_gpu_scale.py::test_reference_bundle_on_gpu[paper], ::test_figure5_statistical_pin)"
+        elif not args.no_parity_sample:
             use_all_host_cores()
             reps = sorted({0, 17, B // 2 + 1, B - 1})
             out["parity_sample"] = parity_sample(schemes, sim.seed, last_first, err_last, I, reps)
             out["parity_sample_note"] = ("GPU error counts of realizations %s of the last timed batch (seed %d, first index %d) "
                                          "equal the CPU oracle's (own setup, same counter-based draws)" % (reps, sim.seed, last_first))
-        if world == 1 and not args.no_cpu_baseline:
+        if paper:
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                                   "sample": "not timed at the paper geometry (oracle setup alone takes minutes); see the default workload"}
+        elif world == 1 and not args.no_cpu_baseline:
             n = args.cpu_sample
             v = cpu_realizations_per_s(n, schemes)
             vf = cpu_realizations_per_s(1, schemes, faithful=True)
@@ -462,6 +507,79 @@ def run_b200(args):
         raise SystemExit(3)
 
 
+def run_sweep(args):
+    """BASELINE.json configs[3]: high-mobility sweep.  `--sweep-realizations` (1e5) realizations in total, split evenly over the
+    velocities 50..500 km/h and over the GPUs, VehicularA, 4 IC iterations, default geometry, all three schemes -- timed
+    INCLUDING the per-velocity setup (correlation + MMSE matrices rebuilt on the device, DS.m:208-313) and the final counter
+    reduce; only the velocity-independent one-time setup (modem matrices, precoders) is outside.  Strong scaling."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from chest_b200.simulation import DoublySelectiveSimulation
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    velocities = list(range(50, 501, 50))
+    I, B = 4, min(args.batch, 2048)
+    per_v = args.sweep_realizations // len(velocities)
+    t0 = time.perf_counter()
+    sim = DoublySelectiveSimulation(max_batch=B, device=local, seed=77, Velocity_kmh=velocities[0])
+    one_time_s = time.perf_counter() - t0
+    sim.run(NrRepetitions=min(B, 256), NrIterations=I)                  # warm-up: allocations, first-launch costs
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    setup_s, loop_s = 0.0, 0.0
+    t_all = time.perf_counter()
+    totals = []
+    n_snr = len(sim.Pn)
+    for v in velocities:
+        t = time.perf_counter()
+        sim.set_velocity(v)
+        setup_s += time.perf_counter() - t
+        t = time.perf_counter()
+        lo = per_v * rank // world; hi = per_v * (rank + 1) // world     # this rank's contiguous block of the velocity's realizations
+        tot = sim.run_totals(hi - lo, NrIterations=I, first_rep=lo)
+        totals.append(tot)
+        loop_s += time.perf_counter() - t
+    tt = torch.from_numpy(np.stack(totals).astype(np.int64)).cuda()
+    t_red = time.perf_counter()
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)                       # the one collective: counters of all velocities
+    torch.cuda.synchronize()
+    reduce_ms = 1e3 * (time.perf_counter() - t_red)
+    wall = time.perf_counter() - t_all
+    times = torch.tensor([wall, setup_s, loop_s, reduce_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    wall, setup_s, loop_s, reduce_ms = [float(x) for x in times.cpu()]
+    if rank == 0:
+        nb = sim.ctx.bit_counts()
+        tt = tt.cpu().numpy().reshape(len(velocities), n_snr, I + 1, 3, 2, 2)
+        n_total = per_v * len(velocities)
+        ber = {str(v): float(tt[k, -1, I, 2, 0, 0]) / (nb[2, 0] * per_v) for k, v in enumerate(velocities)}
+        out = {"metric": METRIC, "value": n_total / wall, "unit": UNIT, "n_gpus": world, "steps": len(velocities), "warmup": 1,
+               "ms_per_step": 1e3 * wall / len(velocities), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "high-mobility sweep (BASELINE.json configs[3]): velocities %s km/h, VehicularA, DS.m default geometry, "
+                                      "3 schemes, 7 SNR points, 4 IC iterations, %d realizations in total over %d GPU(s), per-velocity "
+                                      "setup (DS.m:208-313 on the device) inside the timed region" % (velocities, n_total, world),
+                          "realizations_per_velocity": per_v, "batch": B, "timing": "host wall clock around the whole sweep (setup + loop + reduce), max over ranks"},
+               "setup_s_per_velocity": setup_s / len(velocities), "loop_s": loop_s, "reduce_ms": reduce_ms, "one_time_setup_s": one_time_s,
+               "loop_only_value": n_total / loop_s, "sanity_ber_ofdm_40dB_iteration4_by_velocity": ber}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sim.close()
+
+
+def run_sv(args):
+    raise SystemExit("bench.py --workload sv: not built yet")
+
+
 def _one_json_line_stdout():
     """Libraries (NCCL's version banner, ...) write to file descriptor 1 behind Python's back; the contract is ONE
     JSON line on stdout.  Point fd 1 at stderr for the whole run and keep the real stdout for that line."""
@@ -476,5 +594,9 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "sweep":
+        run_sweep(a)
+    elif a.workload == "sv":
+        run_sv(a)
     else:
         run_b200(a)

@@ -377,10 +377,11 @@ class DeviceContext:
 
     def kernel_times(self):
         """Device ms of k_apply_hg, k_gemm_d, k_ic_main (sum), k_ic_light (sum) in the last profiled batch."""
-        out = (C.c_float * 6)()
+        out = (C.c_float * 10)()
         self._check(self.lib.chest_kernel_times(self._h, out))
         return dict(k_apply_hg=out[0], k_gemm_d=out[1], k_ic_main=out[2], k_ic_light=out[3],
-                    perfect_csi_chain=out[4], diag_d_gemm=out[5])
+                    perfect_csi_chain=out[4], diag_d_gemm=out[5], k_synth_h=out[6], k_tx_symbols=out[7],
+                    modulate_gemm=out[8], k_apply_h=out[9])
 
     def work_model(self, n_iter):
         out = (C.c_double * 8)()

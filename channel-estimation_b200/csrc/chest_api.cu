@@ -76,7 +76,7 @@ struct Waveform {
     DevBuf<cplx> x, s, r0, y, D, htrue;
     // factored perfect-CSI pass (perf_mode 1): column tables of the units' v / y_ic slots, and the two vector sets
     DevBuf<int> q_lo_d, q_hi_d;
-    DevBuf<cplx> Pd; DevBuf<int> pd_klo, pd_khi;        // diag(D) operand: P[i][t*N + n] = conj(Q[n,i]) G[n - tau_t, i]
+    DevBuf<cplx> Pd; DevBuf<int> pd_klo, pd_khi; bool pd_built = false;   // diag(D) operand: P[i][t*N + n] = conj(Q[n,i]) G[n - tau_t, i]
     std::vector<cplx> Gh, Qh;                           // host copies of G, Q (finalize builds Pd from them)
     DevBuf<int64_t> f_voff, f_yoff; DevBuf<int> f_rep; DevBuf<cplx> f_s, f_r;
     int f_cols = 0, perf_base = 0, perf_nblk = 0;
@@ -166,7 +166,8 @@ struct Ctx {
     cudaEvent_t ev_gd[2] = {};   // end of k_gemm_d of the two waveforms
     cudaEvent_t ev_ic[36] = {};  // after every k_ic_main (+ factored chain) / k_ic_light launch
     cudaEvent_t ev_mn[18] = {};  // after k_ic_main alone (before the factored perfect-CSI chain)
-    float kernel_ms[6] = {0, 0, 0, 0, 0, 0};   // k_apply_hg, k_gemm_d, k_ic_main, k_ic_light, factored perfect-CSI chain, diag(D) GEMM
+    cudaEvent_t ev_k1[8] = {};   // inside stage 1: after k_synth_h, k_tx_symbols, per waveform after s = G x and after r0 = H s
+    float kernel_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // k_apply_hg, k_gemm_d, k_ic_main, k_ic_light, factored perfect-CSI chain, diag(D) GEMM, k_synth_h, k_tx_symbols, s = G x, k_apply_h
     float hg_ms = 0; double hg_bytes = 0;
     cudaEvent_t user_ev[4] = {};
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -324,6 +325,30 @@ int ensure_d_buffers(Ctx* c, Waveform& w) {
     CK(cudaMemsetAsync(w.HG1.p, 0, n_hg * sizeof(cplx), c->stream));          // pad element of odd N stays zero
     CK(cudaMemsetAsync(w.HG2.p, 0, n_hg * sizeof(double), c->stream));
     w.d_alloc_batch = B;
+    return CHEST_OK;
+}
+
+// diag(D) as a GEMM over realizations: h[rep][i] = sum_{t,n} P[i][t*N + n] h[rep][t][n], P = conj(Q) shift_t(G).
+// K x T x N complex: built on the first factored-mode run only (a waveform used for K1 / K2 alone never needs it).
+int ensure_pd(Ctx* c, Waveform& w) {
+    if (w.pd_built) return CHEST_OK;
+    const int N = c->N, K = w.K, T = c->T;
+    std::vector<cplx> P((size_t)K * T * N, cmake(0.0, 0.0));
+    for (int i = 0; i < K; ++i)
+        for (int t = 0; t < T; ++t) {
+            const int d = c->tap_delay[t];
+            for (int n = std::max(w.q_lo[i], d); n < w.q_hi[i]; ++n) {
+                const cplx q = w.Qh[(size_t)n + (size_t)N * i], g = w.Gh[(size_t)(n - d) + (size_t)N * i];
+                P[((size_t)i * T + t) * N + n] = cmake(q.x * g.x + q.y * g.y, q.x * g.y - q.y * g.x);
+            }
+        }
+    CK(w.Pd.upload(P, c->stream));
+    std::vector<int> ql, qh;
+    tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, ql, qh);
+    for (size_t a = 0; a < ql.size(); ++a) if (qh[a] > ql[a]) qh[a] += (T - 1) * N;   // the range spans all tap segments
+    CK(w.pd_klo.upload(ql, c->stream)); CK(w.pd_khi.upload(qh, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    w.pd_built = true;
     return CHEST_OK;
 }
 
@@ -539,6 +564,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     // ---- stage 1 (K1): channel realization, TX symbols, s = G x, r0 = H s
     rc = discrete ? stage_channel_discrete(c, n_rep, cgauss) : stage_channel(c, n_rep, du, pu);
     if (rc) return rc;
+    if (c->profiling) CK(cudaEventRecord(c->ev_k1[0], st));
     for (int si = 0; si < 3; ++si) {
         if (!c->sch[si].set) continue;
         SchemeDev sd = scheme_dev(c, si);
@@ -547,18 +573,25 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         c->launches++;
         CK(cudaGetLastError());
     }
+    if (c->profiling) CK(cudaEventRecord(c->ev_k1[1], st));
     for (int wfi = 0; wfi < 2; ++wfi) {
         Waveform& w = c->wf[wfi];
-        if (!w.set || !w.nsch) continue;
-        GemmParams p{};
-        p.M = N; p.Kc = w.K; p.n_cols = w.nsch * n_rep; p.lda = w.K; p.ldc = N; p.conj_a = 0;
-        p.At = w.Gt.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.out = w.s.p;
-        p.bsrc = w.x.p; p.ldb = w.K;
-        CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));
-        dim3 grid((N + 127) / 128, w.nsch * n_rep);
-        k_apply_h<<<grid, 128, 0, st>>>(w.r0.p, w.s.p, c->h.p, c->d_tap_delay.p, N, c->T, n_rep, -1);
-        c->launches++;
-        CK(cudaGetLastError());
+        if (c->profiling) CK(cudaEventRecord(c->ev_k1[2 + 3 * wfi], st));
+        if (w.set && w.nsch) {
+            GemmParams p{};
+            p.M = N; p.Kc = w.K; p.n_cols = w.nsch * n_rep; p.lda = w.K; p.ldc = N; p.conj_a = 0;
+            p.At = w.Gt.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.out = w.s.p;
+            p.bsrc = w.x.p; p.ldb = w.K;
+            CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));
+        }
+        if (c->profiling) CK(cudaEventRecord(c->ev_k1[3 + 3 * wfi], st));
+        if (w.set && w.nsch) {
+            dim3 grid((N + 127) / 128, w.nsch * n_rep);
+            k_apply_h<<<grid, 128, 0, st>>>(w.r0.p, w.s.p, c->h.p, c->d_tap_delay.p, N, c->T, n_rep, -1);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+        if (c->profiling) CK(cudaEventRecord(c->ev_k1[4 + 3 * wfi], st));
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
     // ---- stage 2 (K2): D = Q^H H G, h = diag(D)
@@ -566,6 +599,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch) continue;
         if (c->perf_mode == 1) {                               // factored mode needs only h = diag(D)
+            rc = ensure_pd(c, w); if (rc) return rc;
             GemmParams p{};                                    // htrue[rep][i] = P[i][:] . h[rep][:]
             p.M = w.K; p.Kc = c->T * N; p.n_cols = n_rep; p.lda = c->T * N; p.ldc = w.K; p.conj_a = 0;
             p.At = w.Pd.p; p.mt_klo = w.pd_klo.p; p.mt_khi = w.pd_khi.p; p.out = w.htrue.p;
@@ -739,6 +773,14 @@ int finish_pipeline(Ctx* c) {
         }
         c->kernel_ms[0] = c->kernel_ms[1] = 0;
         c->kernel_ms[5] = c->perf_mode == 1 ? c->stage_ms[2] : 0;              // factored mode: stage 2 is the diag(D) GEMM
+        cudaEventElapsedTime(&c->kernel_ms[6], c->ev[1], c->ev_k1[0]);         // k_synth_h
+        cudaEventElapsedTime(&c->kernel_ms[7], c->ev_k1[0], c->ev_k1[1]);      // k_tx_symbols
+        c->kernel_ms[8] = c->kernel_ms[9] = 0;
+        for (int wfi = 0; wfi < 2; ++wfi) {
+            float t = 0;
+            cudaEventElapsedTime(&t, c->ev_k1[2 + 3 * wfi], c->ev_k1[3 + 3 * wfi]); c->kernel_ms[8] += t;   // s = G x
+            cudaEventElapsedTime(&t, c->ev_k1[3 + 3 * wfi], c->ev_k1[4 + 3 * wfi]); c->kernel_ms[9] += t;   // r0 = H s
+        }
         if (n_rep > 1 && c->perf_mode != 1)
             for (int wfi = 0; wfi < 2; ++wfi)
                 if (c->wf[wfi].set && c->wf[wfi].nsch) {
@@ -799,6 +841,7 @@ int chest_create(int device, uint64_t* handle) {
     for (auto& e : c->ev_gd) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_ic) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_mn) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_k1) CK(cudaEventCreate(&e));
     *handle = (uint64_t)(uintptr_t)c;
     return CHEST_OK;
 }
@@ -814,6 +857,7 @@ int chest_destroy(uint64_t handle) {
     for (auto& e : c->ev_gd) cudaEventDestroy(e);
     for (auto& e : c->ev_ic) cudaEventDestroy(e);
     for (auto& e : c->ev_mn) cudaEventDestroy(e);
+    for (auto& e : c->ev_k1) cudaEventDestroy(e);
     for (auto& q : c->pf) { cudaEventDestroy(q.landed); cudaEventDestroy(q.released); }
     cudaStreamSynchronize(c->copy_stream);
     if (c->err_pinned) cudaFreeHost(c->err_pinned);
@@ -1368,23 +1412,7 @@ int chest_finalize(uint64_t handle, int max_batch) {
         for (int j = 0; j < K; ++j) w.hg_rows[j] = std::max(0, hi[j / w.tile] - lo[j / w.tile]);
         tile_ranges(w.g_lo, w.g_hi, 8, max_delay, N, lo, hi);
         CK(w.hg8_klo.upload(lo, c->stream)); CK(w.hg8_khi.upload(hi, c->stream));
-        {   // diag(D) as a GEMM over realizations: h[rep][i] = sum_{t,n} P[i][t*N + n] h[rep][t][n]
-            const int T = c->T;
-            std::vector<cplx> P((size_t)K * T * N, cmake(0.0, 0.0));
-            for (int i = 0; i < K; ++i)
-                for (int t = 0; t < T; ++t) {
-                    const int d = c->tap_delay[t];
-                    for (int n = std::max(w.q_lo[i], d); n < w.q_hi[i]; ++n) {
-                        const cplx q = w.Qh[(size_t)n + (size_t)N * i], g = w.Gh[(size_t)(n - d) + (size_t)N * i];
-                        P[((size_t)i * T + t) * N + n] = cmake(q.x * g.x + q.y * g.y, q.x * g.y - q.y * g.x);
-                    }
-                }
-            CK(w.Pd.upload(P, c->stream));
-            std::vector<int> ql, qh;
-            tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, ql, qh);
-            for (size_t a = 0; a < ql.size(); ++a) if (qh[a] > ql[a]) qh[a] += (T - 1) * N;   // the range spans all tap segments
-            CK(w.pd_klo.upload(ql, c->stream)); CK(w.pd_khi.upload(qh, c->stream));
-        }
+        w.pd_built = false;                                    // diag(D) operand: built by the first factored run (ensure_pd)
         {   // work list of K2: tile pairs of D whose Q / H*G supports overlap (the rest of D is structurally zero)
             std::vector<int> ql, qh, gl, gh;
             tile_ranges(w.q_lo, w.q_hi, w.tile, 0, N, ql, qh);
@@ -2144,7 +2172,7 @@ int chest_kernel_times(uint64_t handle, float* ms) {
     Ctx* c = from(handle);
     ARG(c && ms);
     c->kernel_ms[0] = c->hg_ms;
-    for (int i = 0; i < 6; ++i) ms[i] = c->kernel_ms[i];
+    for (int i = 0; i < 10; ++i) ms[i] = c->kernel_ms[i];
     return CHEST_OK;
 }
 

@@ -329,6 +329,19 @@ class DoublySelectiveSimulation:
                 err[r0:r0 + n] = self.ctx.run_batch(n, I, None, seed=seed, first_rep=first_rep + r0)
         return self.ber_arrays(err), err
 
+    def run_totals(self, NrRepetitions, NrIterations=None, seed=None, first_rep=0):
+        """The loop for `NrRepetitions` seeded realizations with the per-realization counters left on the device and
+        summed there (chest_multi_run over this simulation's one context): returns the 64-bit totals
+        [snr, it, scheme, csi, edge] -- what a sharded run reduces over the GPUs."""
+        from .context import MultiDevice
+        I = self.p["NrIterations"] if NrIterations is None else NrIterations
+        if getattr(self, "_multi", None) is None:
+            self._multi = MultiDevice([self.ctx])
+        if NrRepetitions <= 0:
+            return np.zeros((len(self.Pn), I + 1, 3, 2, 2), dtype=np.uint64)
+        _, tot, _ = self._multi.run(NrRepetitions, I, seed=self.seed if seed is None else seed, first_rep=first_rep, want_err=False)
+        return tot
+
     def ber_arrays(self, err):
         nb = self.ctx.bit_counts()
         out = {}
@@ -344,4 +357,7 @@ class DoublySelectiveSimulation:
         return out
 
     def close(self):
+        if getattr(self, "_multi", None) is not None:
+            self._multi.close()
+            self._multi = None
         self.ctx.close()

@@ -282,8 +282,9 @@ int chest_stage_times(uint64_t handle, float* ms /* [7] */);
 int chest_banded_apply_stats(uint64_t handle, float* ms, double* bytes);
 /* Device time (ms, CUDA events on the context's stream) of the hot kernels in the last profiled chest_run_batch:
  * [0] k_apply_hg, [1] k_gemm_d (K2; both zero in factored mode), [2] k_ic_main summed over the iterations,
- * [3] k_ic_light summed, [4] the factored perfect-CSI chain summed, [5] the diag(D) GEMM. */
-int chest_kernel_times(uint64_t handle, float* ms /* [6] */);
+ * [3] k_ic_light summed, [4] the factored perfect-CSI chain summed, [5] the diag(D) GEMM, [6] k_synth_h (channel
+ * synthesis), [7] k_tx_symbols, [8] s = G x (both waveforms), [9] k_apply_h (r0 = H s, both waveforms). */
+int chest_kernel_times(uint64_t handle, float* ms /* [10] */);
 /* Algorithmic work of one realization for the roofline:
  * [0] K2 support-aware flops, [1] K3/K4 estimated-CSI flops per iteration-evaluation set,
  * [2] perfect-CSI flops, [3] demod/TX flops, [4] bytes of W streamed per IC kernel launch,
