@@ -568,7 +568,8 @@ def run_sweep(args):
                                       "setup (DS.m:208-313 on the device) inside the timed region" % (velocities, n_total, world),
                           "realizations_per_velocity": per_v, "batch": B, "timing": "host wall clock around the whole sweep (setup + loop + reduce), max over ranks"},
                "setup_s_per_velocity": setup_s / len(velocities), "loop_s": loop_s, "reduce_ms": reduce_ms, "one_time_setup_s": one_time_s,
-               "loop_only_value": n_total / loop_s, "sanity_ber_ofdm_40dB_iteration4_by_velocity": ber}
+               "loop_only_value": n_total / loop_s, "sanity_ber_ofdm_40dB_iteration4_by_velocity": ber,
+               "setup_breakdown_last_velocity_s": {k: round(v, 4) for k, v in sim.setup_times.items()}}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

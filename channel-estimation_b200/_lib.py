@@ -23,6 +23,11 @@ class ChestDraws(C.Structure):
                 ("noise", vp), ("on_device", c_int), ("channel_gauss", vp)]
 
 
+class ChestSvDraws(C.Structure):
+    """struct chest_sv_draws (chest_b200.h)."""
+    _fields_ = [("bits", vp * 3), ("pilot_idx", vp * 2), ("h", vp), ("noise", vp * 2), ("on_device", c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/chest_b200.h declares
 SIGNATURES = {
     "chest_last_error": (C.c_char_p, []),
@@ -55,6 +60,8 @@ SIGNATURES = {
                                 C.c_double, C.c_double]),
     "chest_modulate_fft": (c_int, [c_u64, c_int, vp, c_int, vp]),
     "chest_demodulate_fft": (c_int, [c_u64, c_int, vp, c_int, vp]),
+    "chest_set_interpolation": (c_int, [c_u64, c_int, vp]),
+    "chest_sv_run_batch": (c_int, [c_u64, c_int, vp, C.POINTER(ChestSvDraws), c_u64, c_i64, vp]),
     "chest_estimate": (c_int, [c_u64, c_int, c_int, c_int, vp, vp, vp]),
     "chest_draws_bytes": (c_i64, [c_u64, c_int]),
     "chest_run_batch": (c_int, [c_u64, c_int, c_int, C.POINTER(ChestDraws), c_u64, c_i64, vp]),

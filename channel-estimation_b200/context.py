@@ -232,6 +232,37 @@ class DeviceContext:
         self._check(self.lib.chest_demodulate_fft(self._h, WF_ID[wf], _ptr(r2), r2.shape[0], _ptr(y)))
         return y[0] if np.ndim(r) == 1 else y.T.copy()
 
+    # ------------------------------------------------------------------ SimpleVersion_DoublyFlat.m chain
+    def set_interpolation(self, name, M):
+        """M: K x P interpolation matrix (PSACE.m:171-184)."""
+        Mf = _c(np.asfortranarray(np.asarray(M, dtype=np.complex128)).reshape(-1, order="F"))
+        self._check(self.lib.chest_set_interpolation(self._h, SCHEME_ID[name], _ptr(Mf)))
+
+    def sv_run_batch(self, pn_time, draws=None, seed=0, first_body=0):
+        """SV.m:89-176 for len(pn_time) bodies.  draws: list of per-body dicts (oracle.sv.sv_new_draws layout) or None
+        (device generator).  Returns err[body, 5] (aux, cod, FBMC perfect, OFDM, OFDM perfect)."""
+        pn = np.ascontiguousarray(pn_time, dtype=np.float64)
+        n = len(pn)
+        err = np.zeros((n, 5), dtype=np.uint32)
+        dptr, keep = None, {}
+        if draws is not None:
+            st = _lib.ChestSvDraws()
+            for name, sid in SCHEME_ID.items():
+                keep["b" + name] = np.ascontiguousarray(np.stack([d["bits_" + name] for d in draws]), dtype=np.uint8)
+                st.bits[sid] = keep["b" + name].ctypes.data
+            for key, wid in (("pil_idx_fbmc", 0), ("pil_idx_ofdm", 1)):
+                keep[key] = np.ascontiguousarray(np.stack([d[key] for d in draws]), dtype=np.int32)
+                st.pilot_idx[wid] = keep[key].ctypes.data
+            keep["h"] = _c(np.array([d["h"] for d in draws]))
+            st.h = _ptr(keep["h"])
+            for key, wid in (("noise_fbmc", 0), ("noise_ofdm", 1)):
+                keep[key] = _c(np.stack([d[key] for d in draws]))
+                st.noise[wid] = keep[key].ctypes.data
+            st.on_device = 0
+            dptr = C.byref(st)
+        self._check(self.lib.chest_sv_run_batch(self._h, n, _ptr(pn), dptr, seed, first_body, _ptr(err)))
+        return err
+
     def estimate(self, name, variant, i_snr, hP, want_D=True):
         K = self.schemes[name]["K"]
         hP = _c(hP)

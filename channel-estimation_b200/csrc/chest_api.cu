@@ -121,6 +121,7 @@ struct Scheme {
     DevBuf<uint32_t> txword, txw_t;
     DevBuf<uint8_t> bits;
     DevBuf<int4> rowinfo; DevBuf<int> multi_d; int n_multi = 0; bool fuse_ok = false;
+    DevBuf<cplx> interp;           // SV.m chain: interpolation matrix K x P, row-major (chest_set_interpolation)
     int64_t n_bits_edge = 0;
     int64_t c_nnz = 0;
     bool c_real = false;
@@ -178,6 +179,7 @@ struct Ctx {
     uint32_t* err_pinned = nullptr; size_t err_pinned_n = 0;
     bool pending = false; size_t pending_n_err = 0; bool trace_on = false; int pending_iter = 0, pending_rep = 0;
     DevBuf<unsigned long long> totals;    // [snr][it][12] sums over realizations (chest_multi_run)
+    DevBuf<cplx> sv_h, sv_noise; DevBuf<double> sv_pn; DevBuf<uint32_t> sv_err;   // chest_sv_run_batch
 };
 
 Ctx* from(uint64_t h) { return reinterpret_cast<Ctx*>(static_cast<uintptr_t>(h)); }
@@ -500,6 +502,8 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     ARG(n_rep >= 1 && n_rep <= c->max_batch);
     ARG(n_iter >= 0 && n_iter <= 16);
     ARG(c->S >= 1);
+    for (int si = 0; si < 3; ++si)
+        if (c->sch[si].set && (!c->sch[si].mm[0].set || !c->sch[si].mm[1].set)) return fail(CHEST_ERR_STATE, "scheme without both MMSE variants");
     if (!(c->fD > 0)) return fail(CHEST_ERR_STATE, "the batched loop body synthesises time-variant realizations: f_D must be positive");
     const int S = c->S, N = c->N, TP = c->T * c->paths;
     c->cur_batch = n_rep; c->last_iter = n_iter;
@@ -1049,7 +1053,7 @@ int chest_set_scheme(uint64_t handle, int si, int wfi, int k_in, int P, int n_da
     Ctx* c = from(handle);
     ARG(c && si >= 0 && si < 3 && (wfi == 0 || wfi == 1) && jc && ir && val && pilot_pos && considered);
     ARG(constellation == CHEST_CONST_PAM || constellation == CHEST_CONST_QAM);
-    ARG(c->wf[wfi].set && c->cst[constellation].set);
+    ARG((c->wf[wfi].set || c->wf[wfi].modem_set) && c->cst[constellation].set);
     ARG(detect >= 0 && detect <= 2 && (detect == CHEST_DETECT_DESPREAD_REAL || data_pos));
     ARG(P > 0 && P <= 128 && n_data > 0 && k_in >= P + n_data && kappa > 0 && dpr > 0);
     CK(cudaSetDevice(c->device));
@@ -1397,7 +1401,8 @@ int chest_release_setup(uint64_t handle) {
 int chest_finalize(uint64_t handle, int max_batch) {
     Ctx* c = from(handle);
     ARG(c && max_batch >= 1);
-    if (!c->chan_set) return fail(CHEST_ERR_STATE, "channel not set");
+    const bool modem_only = !c->chan_set && (c->wf[0].modem_set || c->wf[1].modem_set) && !c->wf[0].set && !c->wf[1].set;
+    if (!c->chan_set && !modem_only) return fail(CHEST_ERR_STATE, "channel not set");
     CK(cudaSetDevice(c->device));
     const int B = max_batch, S = c->S, N = c->N;
     c->K_max = 0;
@@ -1456,23 +1461,24 @@ int chest_finalize(uint64_t handle, int max_batch) {
     for (int si = 0; si < 3; ++si) {
         Scheme& s = c->sch[si];
         if (!s.set) continue;
-        if (!s.mm[0].set || !s.mm[1].set) return fail(CHEST_ERR_STATE, "scheme without both MMSE variants");
+        if ((!s.mm[0].set || !s.mm[1].set) && !modem_only) return fail(CHEST_ERR_STATE, "scheme without both MMSE variants");
         Waveform& w = c->wf[s.waveform];
         if (w.nsch >= 2) return fail(CHEST_ERR_STATE, "more than two schemes on one waveform");
         if (w.nsch == 1 && c->sch[w.sch[0]].P != s.P) return fail(CHEST_ERR_STATE, "schemes of one waveform must share the pilot count");
         w.sch[w.nsch++] = si;
         c->K_max = std::max(c->K_max, s.K);
         CK(s.xP.alloc((size_t)B * s.P)); CK(s.txword.alloc((size_t)B * s.n_data)); CK(s.txw_t.alloc((size_t)((B + 15) / 16) * 16 * s.n_data)); CK(s.bits.alloc((size_t)B * s.n_bits));
-        CK(s.hP.alloc((size_t)S * B * s.P)); CK(s.hdiag.alloc((size_t)S * B * s.K));
-        CK(s.xD[0].alloc((size_t)S * B * s.n_data)); CK(s.xD[1].alloc((size_t)S * B * s.n_data));
+        const size_t S1 = (size_t)std::max(S, 1);
+        CK(s.hP.alloc(S1 * B * s.P)); CK(s.hdiag.alloc(S1 * B * s.K));
+        CK(s.xD[0].alloc(S1 * B * s.n_data)); CK(s.xD[1].alloc(S1 * B * s.n_data));
     }
     for (int wfi = 0; wfi < 2; ++wfi) {
         Waveform& w = c->wf[wfi];
-        if (!w.set) continue;
+        if (!w.set && !w.modem_set) continue;
         c->K_max = std::max(c->K_max, w.K);
         int ns = std::max(w.nsch, 1);
         CK(w.x.alloc((size_t)ns * B * w.K)); CK(w.s.alloc((size_t)ns * B * N)); CK(w.r0.alloc((size_t)ns * B * N));
-        CK(w.y.alloc((size_t)ns * S * B * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
+        CK(w.y.alloc((size_t)ns * std::max(S, 1) * B * w.K)); CK(w.htrue.alloc((size_t)B * w.K));
         // D and the H*G planes (dense mode, chest_transmission_matrix) are allocated on first use: ensure_d_buffers
         w.d_alloc_batch = 0;
         if (w.nsch) CK(c->pilot_idx[wfi].alloc((size_t)B * c->sch[w.sch[0]].P));
@@ -1712,6 +1718,7 @@ int chest_set_modem(uint64_t handle, int wfi, int kind, int L, int Ksym, int nff
     CK(cudaFuncSetAttribute(k_modem_ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_modem_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ARG(smem <= 200 * 1024);
+    if (!w.set) { w.K = L * Ksym; c->N = md.N; c->finalized = false; }       // modem-only waveform (no dense G / Q)
     w.modem_set = true;
     return CHEST_OK;
 }
@@ -1773,6 +1780,105 @@ int chest_demodulate_fft(uint64_t handle, int wfi, const double* r, int n_cols, 
     int rc = modem_demodulate_dev(c, w, w.m_in.p, n_cols, w.m_out.p); if (rc) return rc;
     CK(cudaMemcpyAsync(y_out, w.m_out.p, ny * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+// ---------------------------------------------------------------- SimpleVersion_DoublyFlat.m chain
+int chest_set_interpolation(uint64_t handle, int si, const double* M) {
+    Ctx* c = from(handle);
+    ARG(c && si >= 0 && si < 3 && c->sch[si].set && M);
+    CK(cudaSetDevice(c->device));
+    Scheme& s = c->sch[si];
+    const cplx* m = reinterpret_cast<const cplx*>(M);          // K x P column-major -> row-major
+    std::vector<cplx> rm((size_t)s.K * s.P);
+    for (int i = 0; i < s.K; ++i) for (int p = 0; p < s.P; ++p) rm[(size_t)i * s.P + p] = m[(size_t)i + (size_t)s.K * p];
+    CK(s.interp.upload(rm, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
+int chest_sv_run_batch(uint64_t handle, int n_body, const double* pn_time, const chest_sv_draws* draws, uint64_t seed,
+                       int64_t first_body, uint32_t* err_out) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(n_body >= 1 && n_body <= c->max_batch && pn_time && err_out);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int N = c->N;
+    for (int wfi = 0; wfi < 2; ++wfi) if (c->wf[wfi].nsch && !c->wf[wfi].modem_set) return fail(CHEST_ERR_STATE, "chest_sv_run_batch needs chest_set_modem for every waveform in use");
+    for (int si = 0; si < 3; ++si) if (c->sch[si].set && !c->sch[si].interp.p) return fail(CHEST_ERR_STATE, "chest_sv_run_batch needs chest_set_interpolation for every scheme");
+    c->cur_batch = n_body;
+    CK(c->sv_h.alloc(c->max_batch)); CK(c->sv_noise.alloc((size_t)c->max_batch * 2 * N)); CK(c->sv_pn.alloc(c->max_batch));
+    CK(c->sv_err.alloc((size_t)c->max_batch * 5));
+    CK(cudaMemcpyAsync(c->sv_pn.p, pn_time, sizeof(double) * n_body, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->sv_err.p, 0, sizeof(uint32_t) * n_body * 5, st));
+    const uint8_t* bits[3] = {c->sch[0].bits.p, c->sch[1].bits.p, c->sch[2].bits.p};
+    const int32_t* pidx[2] = {c->pilot_idx[0].p, c->pilot_idx[1].p};
+    if (draws) {                                                   // explicit draws (host pointers), SV.m:95-128 order
+        ARG(!draws->on_device && draws->h && draws->noise[0] && draws->noise[1]);
+        CK(cudaMemcpyAsync(c->sv_h.p, draws->h, sizeof(cplx) * n_body, cudaMemcpyHostToDevice, st));
+        for (int wfi = 0; wfi < 2; ++wfi)                          // host layout per waveform [body][N] -> device [body][wf][N]
+            CK(cudaMemcpy2DAsync(c->sv_noise.p + (size_t)wfi * N, sizeof(cplx) * 2 * N, draws->noise[wfi], sizeof(cplx) * N,
+                                 sizeof(cplx) * N, n_body, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < 3; ++i)
+            if (c->sch[i].set) { ARG(draws->bits[i]); CK(cudaMemcpyAsync(c->sch[i].bits.p, draws->bits[i], (size_t)n_body * c->sch[i].n_bits, cudaMemcpyHostToDevice, st)); }
+        for (int i = 0; i < 2; ++i)
+            if (c->wf[i].nsch) { ARG(draws->pilot_idx[i]); CK(cudaMemcpyAsync(c->pilot_idx[i].p, draws->pilot_idx[i], sizeof(int32_t) * n_body * c->sch[c->wf[i].sch[0]].P, cudaMemcpyHostToDevice, st)); }
+    } else {
+        for (int si = 0; si < 3; ++si) {
+            Scheme& s = c->sch[si];
+            if (!s.set) continue;
+            dim3 gb(((s.n_bits + 127) / 128 + 127) / 128, n_body);
+            k_rng_bits<<<gb, 128, 0, st>>>(s.bits.p, s.n_bits, n_body, RS_BITS0 + si, seed, first_body);
+            c->launches++;
+        }
+        for (int wfi = 0; wfi < 2; ++wfi) {
+            Waveform& w = c->wf[wfi];
+            if (!w.nsch) continue;
+            Scheme& s = c->sch[w.sch[0]];
+            dim3 gp((s.P + 63) / 64, n_body);
+            k_rng_index<<<gp, 64, 0, st>>>(c->pilot_idx[wfi].p, s.P, n_body, c->cst[s.constellation].order, RS_PILOT0 + wfi, seed, first_body);
+            c->launches++;
+        }
+        dim3 gh(1, n_body);
+        k_rng_cnormal<<<gh, 32, 0, st>>>(c->sv_h.p, 1, n_body, RS_SV_H, seed, first_body, 0.70710678118654752440);   // h ~ CN(0,1), SV.m:123
+        dim3 gn((N + 127) / 128, 2, n_body);
+        k_rng_normal<<<gn, 128, 0, st>>>(c->sv_noise.p, N, 2, n_body, seed, first_body);
+        c->launches += 2;
+        CK(cudaGetLastError());
+    }
+    for (int si = 0; si < 3; ++si) {
+        if (!c->sch[si].set) continue;
+        SchemeDev sd = scheme_dev(c, si);
+        k_tx_symbols<<<n_body, 256, sd.K_in * sizeof(cplx), st>>>(sd, c->cst[sd.constellation].dev, bits[si], pidx[sd.waveform], n_body);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.nsch) continue;
+        const int n_cols = w.nsch * n_body;
+        rc = modem_modulate_dev(c, w, w.x.p, n_cols, w.s.p); if (rc) return rc;                       // SV.m:118-120
+        dim3 g((N + 127) / 128, n_cols);
+        k_sv_channel<<<g, 128, 0, st>>>(w.r0.p, w.s.p, c->sv_h.p, c->sv_noise.p, c->sv_pn.p, N, n_body, wfi);   // SV.m:123-131
+        c->launches++;
+        CK(cudaGetLastError());
+        rc = modem_demodulate_dev(c, w, w.r0.p, n_cols, w.y.p); if (rc) return rc;                    // SV.m:133-135
+    }
+    // error slots: 0 aux, 1 cod, 2 FBMC perfect (data spreading with the true channel), 3 OFDM, 4 OFDM perfect (SV.m:165-169)
+    const int slot_est[3] = {0, 1, 3}, slot_perf[3] = {-1, 2, 4};
+    for (int si = 0; si < 3; ++si) {
+        if (!c->sch[si].set) continue;
+        SchemeDev sd = scheme_dev(c, si);
+        sd.y = c->wf[sd.waveform].y.p + (size_t)((c->wf[sd.waveform].sch[0] == si) ? 0 : 1) * n_body * sd.K;   // one "SNR point": [g][body][K]
+        const size_t smem = ((size_t)sd.P + 2 * sd.K) * sizeof(cplx);
+        k_sv_detect<<<n_body, 256, smem, st>>>(sd, c->cst[sd.constellation].dev, sd.y, c->sch[si].interp.p, c->sv_h.p, c->sv_err.p,
+                                                 slot_est[si], slot_perf[si], n_body);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(err_out, c->sv_err.p, sizeof(uint32_t) * n_body * 5, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return CHEST_OK;
 }
 

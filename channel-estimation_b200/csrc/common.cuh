@@ -78,4 +78,4 @@ __host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
     return (double)(w >> 11) * (1.0 / 9007199254740992.0) + (0.5 / 9007199254740992.0);
 }
 // RNG streams (counter word c2 = stream | snr << 8)
-enum { RS_DOPPLER = 0, RS_PHASE = 1, RS_BITS0 = 2 /* +scheme */, RS_PILOT0 = 5 /* +waveform */, RS_NOISE = 7, RS_CHAN_GAUSS = 8 };
+enum { RS_DOPPLER = 0, RS_PHASE = 1, RS_BITS0 = 2 /* +scheme */, RS_PILOT0 = 5 /* +waveform */, RS_NOISE = 7, RS_CHAN_GAUSS = 8, RS_SV_H = 9 };

@@ -127,7 +127,8 @@ __global__ void k_synth_h_discrete(cplx* __restrict__ h, const cplx* __restrict_
     h[((int64_t)rep * T + tap) * N + n] = acc;
 }
 // complex standard normals: out[rep][n_per_rep]
-__global__ void k_rng_cnormal(cplx* __restrict__ out, int n_per_rep, int n_rep, int stream, uint64_t seed, int64_t first_rep) {
+__global__ void k_rng_cnormal(cplx* __restrict__ out, int n_per_rep, int n_rep, int stream, uint64_t seed, int64_t first_rep,
+                              double scale = 1.0) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x, rep = blockIdx.y;
     if (rep >= n_rep || e >= n_per_rep) return;
     const uint64_t r = (uint64_t)(first_rep + rep);
@@ -135,7 +136,7 @@ __global__ void k_rng_cnormal(cplx* __restrict__ out, int n_per_rep, int n_rep, 
     const double u1 = u53(p.v[0], p.v[1]), u2 = u53(p.v[2], p.v[3]);
     double rad = sqrt(-2.0 * log(u1)), s_, c_;
     sincospi(2.0 * u2, &s_, &c_);
-    out[(int64_t)rep * n_per_rep + e] = cmake(rad * c_, rad * s_);
+    out[(int64_t)rep * n_per_rep + e] = cmake(scale * rad * c_, scale * rad * s_);
 }
 
 // r[col][n] = sum_tap h[rep(col)][tap][n] * s[col][n - delay_tap]   (banded H, never materialised)
@@ -2100,6 +2101,75 @@ __global__ void k_modem_fft(ModemDev md, const cplx* __restrict__ r, cplx* __res
         cplx v = z[md.bin[l]];
         if (md.kind == 0) v = cmulc(md.phase[k * md.L + l], v);        // .* conj(PhaseShift)
         y[((int64_t)col * md.Ksym + k) * md.L + l] = cmake(v.x * md.inv_demod, v.y * md.inv_demod);
+    }
+}
+
+
+// ============================================================================ SimpleVersion_DoublyFlat.m:89-176, batched
+// One "body" = one (repetition, SNR point) pass of the script's loop: doubly-flat channel h (one complex scalar), AWGN.
+// r[col][n] = h[body] * s[col][n] + sqrt(Pn[body] / 2) * noise[body][wf][n]   (SV.m:123-131), col = g * n_body + body
+__global__ void k_sv_channel(cplx* __restrict__ r, const cplx* __restrict__ s, const cplx* __restrict__ h,
+                             const cplx* __restrict__ noise, const double* __restrict__ pn, int N, int n_body, int wf) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (n >= N) return;
+    const int body = col % n_body;
+    const double sc = sqrt(pn[body] / 2.0);
+    const cplx nz = noise[((int64_t)body * 2 + wf) * N + n];
+    cplx v = cmul(h[body], s[(int64_t)col * N + n]);
+    r[(int64_t)col * N + n] = cmake(v.x + sc * nz.x, v.y + sc * nz.y);
+}
+// LS pilot estimates, interpolation h = M hP (M given: K x P, row-major here), one-tap equalisation, de-spreading / selection,
+// hard decisions and bit-error counts of one scheme (SV.m:138-169).  One block per body.  err[body][slot] counts; a slot < 0
+// is skipped (the script has no perfect-CSI auxiliary branch).
+__global__ void k_sv_detect(SchemeDev sd, ConstDev cd, const cplx* __restrict__ y, const cplx* __restrict__ interp,
+                            const cplx* __restrict__ htrue, uint32_t* __restrict__ err, int slot_est, int slot_perf, int n_body) {
+    extern __shared__ cplx svs[];
+    cplx* hP = svs;                    // [P]
+    cplx* xe = svs + sd.P;             // [K] equalised with the interpolated channel
+    cplx* xp = xe + sd.K;              // [K] equalised with the true channel
+    __shared__ unsigned cnt[2];
+    const int body = blockIdx.x, tid = threadIdx.x;
+    if (body >= n_body) return;
+    const cplx* yb = y + (int64_t)body * sd.K;
+    if (tid < 2) cnt[tid] = 0;
+    for (int p = tid; p < sd.P; p += blockDim.x) {
+        const cplx q = cdiv(yb[sd.pilot_pos[p]], sd.xP[(int64_t)body * sd.P + p]);
+        hP[p] = cmake(q.x / sd.sqrt_kappa, q.y / sd.sqrt_kappa);
+    }
+    __syncthreads();
+    const cplx ht = htrue[body];
+    for (int i = tid; i < sd.K; i += blockDim.x) {
+        cplx hh = cmake(0.0, 0.0);
+        for (int p = 0; p < sd.P; ++p) cfma(hh, interp[(int64_t)i * sd.P + p], hP[p]);
+        xe[i] = cdiv(yb[i], hh);
+        xp[i] = cdiv(yb[i], ht);
+    }
+    __syncthreads();
+    unsigned e_est = 0, e_perf = 0, dummy = 0;
+    for (int d = tid; d < sd.n_data; d += blockDim.x) {
+        cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
+        if (sd.detect_mode == 1) {
+            for (int e = sd.ct_colptr[sd.P + d]; e < sd.ct_colptr[sd.P + d + 1]; ++e) {
+                const cplx cv = sd.ct_val[e];
+                const cplx t1 = cmulc(cv, xe[sd.ct_row[e]]), t2 = cmulc(cv, xp[sd.ct_row[e]]);
+                a.x += t1.x; a.y += t1.y; b.x += t2.x; b.y += t2.y;
+            }
+            a = cmake(a.x / sd.dpr, 0.0); b = cmake(b.x / sd.dpr, 0.0);
+        } else {
+            const int i = sd.data_pos[d];
+            a = cmake(xe[i].x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xe[i].y / sd.sqrt_dpr);
+            b = cmake(xp[i].x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xp[i].y / sd.sqrt_dpr);
+        }
+        const uint32_t tw = sd.txword[(int64_t)body * sd.n_data + d];
+        ic_decide(cd, a, tw, 0u, e_est, dummy);
+        ic_decide(cd, b, tw, 0u, e_perf, dummy);
+    }
+    if (e_est) atomicAdd(&cnt[0], e_est);
+    if (e_perf) atomicAdd(&cnt[1], e_perf);
+    __syncthreads();
+    if (tid == 0) {
+        if (slot_est >= 0) err[(int64_t)body * 5 + slot_est] = cnt[0];
+        if (slot_perf >= 0) err[(int64_t)body * 5 + slot_perf] = cnt[1];
     }
 }
 

@@ -152,9 +152,11 @@ class DoublySelectiveSimulation:
         fD = Velocity_kmh / 3.6 * 2.5e9 / 2.998e8
         self.ChannelModel = FastFading(p["SamplingRate"], p["PowerDelayProfile"], self.N, fD, p["DopplerModel"],
                                        p["Paths"], 1, 1, False, create_device=False)
+        self.setup_times = {}
+        t0 = time.perf_counter()
         self.ctx.set_channel(self.N, self._pdp, fD, self.ChannelModel.PHY["dt"], p["Paths"], p["DopplerModel"])
         self.ctx.finalize(max(self.NrPilotSymbols, 1))
-        self.setup_times = {}
+        self._tick("set_channel_and_finalize", t0)
         self._estimator_setup(self.max_batch_requested)
 
     def _estimator_setup(self, max_batch):
@@ -360,4 +362,72 @@ class DoublySelectiveSimulation:
         if getattr(self, "_multi", None) is not None:
             self._multi.close()
             self._multi = None
+        self.ctx.close()
+
+
+class SimpleVersionSimulation:
+    """SimpleVersion_DoublyFlat.m with its double loop (SV.m:89-176) replaced by batched device launches
+    (chest_sv_run_batch): FFT-form FBMC / OFDM modem, doubly-flat Rayleigh channel, LS pilot estimates, interpolation,
+    one-tap equalisation, BER.  The parameter block is SV.m:12-82."""
+
+    def __init__(self, M_SNR_OFDM_dB=tuple(range(0, 31, 5)), NrRepetitions=1000, QAM_ModulationOrder=16,
+                 NrSubcarriers=12, max_batch=4096, device=0, seed=0):
+        from .estimation import PilotSymbolAidedChannelEstimation as PSACE
+        self.M_SNR_OFDM_dB, self.NrRepetitions, self.seed = tuple(M_SNR_OFDM_dB), NrRepetitions, seed
+        L = NrSubcarriers
+        fs = 15e3 * 14 * 12
+        self.FBMC = FBMC(L, 30, 15e3, fs, 15e3 * 20, False, "Hermite-OQAM", 8, 0, True)                       # SV.m:17-28
+        self.OFDM = OFDM(L, 15, 15e3, fs, 15e3 * 20, False, 0, (8 - 1 / 2) * 1 / 15e3 * 1 / 2)                # SV.m:31-40
+        self.PAM = SignalConstellation(int(round(np.sqrt(QAM_ModulationOrder))), "PAM")                       # SV.m:43-44
+        self.QAM = SignalConstellation(QAM_ModulationOrder, "QAM")
+        self.ChannelEstimation_FBMC = ce_f = PSACE("Diamond", [[L, 6], [30, 8]], "linear")                    # SV.m:47-56
+        self.ChannelEstimation_OFDM = ce_o = PSACE("Diamond", [[L, 6], [15, 4]], "linear")                    # SV.m:57-66
+        D0 = self.FBMC.GetFBMCMatrix()
+        self.AuxiliaryMethod = aux = _IIC("Auxiliary", ce_f.GetAuxiliaryMatrix(1), D0, 16, 2)                 # SV.m:71-75
+        self.CodingMethod = cod = _IIC("Coding", ce_f.PilotMatrix, D0, 16, 2)                                 # SV.m:76-80
+        pmf = ce_f.PilotMatrix.reshape(-1, order="F"); pmo = ce_o.PilotMatrix.reshape(-1, order="F")
+        pma = aux.PilotMatrix.reshape(-1, order="F")
+        Pf, Po, Ko = ce_f.NrPilotSymbols, ce_o.NrPilotSymbols, pmo.size
+        map_o = np.zeros((Ko, Ko))                                                                             # SV.m:113-115
+        map_o[np.flatnonzero(pmo == 1), np.arange(Po)] = 1.0
+        map_o[np.flatnonzero(pmo == 0), Po + np.arange(Ko - Po)] = 1.0
+        self.interp_f, self.interp_o = ce_f.GetInterpolationMatrix(), ce_o.GetInterpolationMatrix()            # PSACE.m:171-184
+        ctx = self.ctx = DeviceContext(device)
+        self.FBMC._set_modem(ctx); self.OFDM._set_modem(ctx)
+        ctx.set_constellation("PAM", self.PAM.SymbolMapping, self.PAM.BitMapping)
+        ctx.set_constellation("QAM", self.QAM.SymbolMapping, self.QAM.BitMapping)
+        nbp, nbq = self.PAM.BitMapping.shape[1], self.QAM.BitMapping.shape[1]
+        ctx.K["F"], ctx.K["O"] = pmf.size, Ko
+        ctx.set_scheme("aux", "F", aux.PrecodingMatrix, np.flatnonzero(pmf == 1), np.flatnonzero(pma == 0),
+                       aux.PilotToDataPowerOffset * aux.DataPowerReduction, aux.DataPowerReduction, "select_real", "PAM",
+                       np.ones(aux.NrDataSymbols * nbp, dtype=np.uint8))                                        # SV.m:138,148
+        ctx.set_scheme("cod", "F", cod.PrecodingMatrix, np.flatnonzero(pmf == 1), None, cod.PilotToDataPowerOffset, 1.0,
+                       "despread_real", "PAM", np.ones(cod.NrDataSymbols * nbp, dtype=np.uint8))                # SV.m:139,149
+        ctx.set_scheme("ofdm", "O", map_o.astype(np.complex128), np.flatnonzero(pmo == 1), np.flatnonzero(pmo == 0), 1.0, 1.0,
+                       "select_complex", "QAM", np.ones((Ko - Po) * nbq, dtype=np.uint8))                       # SV.m:140,152
+        ctx.set_interpolation("aux", self.interp_f); ctx.set_interpolation("cod", self.interp_f)
+        ctx.set_interpolation("ofdm", self.interp_o)
+        ctx.finalize(max_batch)
+        self.max_batch = max_batch
+        self.n_bits = np.array([aux.NrDataSymbols * nbp, cod.NrDataSymbols * nbp, cod.NrDataSymbols * nbp,
+                                (Ko - Po) * nbq, (Ko - Po) * nbq], dtype=np.float64)
+
+    def noise_power(self, snr_db):
+        o = self.OFDM
+        return o.PHY["SamplingRate"] / (o.PHY["SubcarrierSpacing"] * o.Nr["Subcarriers"]) * 10 ** (-np.asarray(snr_db, dtype=float) / 10)   # SV.m:92
+
+    def run(self, NrRepetitions=None, seed=None):
+        """Returns the five BER arrays of SV.m:84-88 (n_SNR x NrRepetitions each) keyed by the script's variable names."""
+        R = self.NrRepetitions if NrRepetitions is None else NrRepetitions
+        nS = len(self.M_SNR_OFDM_dB)
+        pn = np.tile(self.noise_power(self.M_SNR_OFDM_dB), R)                 # body = rep * nS + snr (the script's loop order)
+        err = np.zeros((R * nS, 5), dtype=np.uint32)
+        for b0 in range(0, R * nS, self.max_batch):
+            n = min(self.max_batch, R * nS - b0)
+            err[b0:b0 + n] = self.ctx.sv_run_batch(pn[b0:b0 + n], None, seed=self.seed if seed is None else seed, first_body=b0)
+        ber = err.reshape(R, nS, 5).transpose(1, 0, 2) / self.n_bits[None, None, :]
+        names = ("BER_FBMC_Aux", "BER_FBMC_Cod", "BER_FBMC_perfect", "BER_OFDM", "BER_OFDM_perfect")
+        return {n: ber[:, :, k] for k, n in enumerate(names)}, err
+
+    def close(self):
         self.ctx.close()

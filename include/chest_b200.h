@@ -176,6 +176,28 @@ int chest_set_modem(uint64_t handle, int waveform, int kind, int n_subcarriers, 
 int chest_modulate_fft(uint64_t handle, int waveform, const double* x, int n_cols, double* s);
 int chest_demodulate_fft(uint64_t handle, int waveform, const double* r, int n_cols, double* y);
 
+/* ------------------------------------------------------------------ SimpleVersion_DoublyFlat.m:89-176 as a batched launch
+ * One "body" = one (repetition, SNR point) pass of the script's double loop: bits -> symbols -> precoding (SV.m:95-115),
+ * FFT-form Modulation (SV.m:118-120), doubly-flat channel h ~ CN(0,1) plus noise of power Pn_time (SV.m:123-131),
+ * Demodulation (SV.m:133-135), LS pilot estimates (SV.m:138-140), interpolation (SV.m:143-145: the interpolation MATRIX
+ * of PilotSymbolAidedChannelEstimation.GetInterpolationMatrix, PSACE.m:171-184, is an input -- MATLAB's scatteredInterpolant
+ * is closed source), one-tap equalisation, de-spreading / selection, hard decisions and bit-error counts (SV.m:148-169).
+ * The context needs chest_set_modem for both waveforms (no dense G / Q, no channel), the constellations and the three
+ * schemes (chest_set_scheme; kappa = the LS scaling of SV.m:138-140, dpr = AuxiliaryMethod.DataPowerReduction for the
+ * auxiliary scheme and 1 otherwise), chest_set_interpolation per scheme (K x P complex, column-major) and chest_finalize.
+ * err_out[body][5]: bit errors of FBMC-Aux, FBMC-Cod, FBMC perfect CSI, OFDM, OFDM perfect CSI (BER_* of SV.m:165-169 =
+ * err / n_bits).  draws == NULL: counter-based generator keyed by (seed, first_body + b). */
+typedef struct chest_sv_draws {
+    const uint8_t* bits[CHEST_N_SCHEMES];  /* n_body x n_bits(scheme)                       SV.m:95-97   */
+    const int32_t* pilot_idx[CHEST_N_WF];  /* n_body x P, 0-based                            SV.m:105,107 */
+    const double*  h;                      /* n_body complex: the channel h = sqrt(1/2)*(randn+1j*randn) itself  SV.m:123 */
+    const double*  noise[CHEST_N_WF];      /* per waveform n_body x N complex standard normals SV.m:125-126 */
+    int            on_device;              /* must be 0 */
+} chest_sv_draws;
+int chest_set_interpolation(uint64_t handle, int scheme, const double* interpolation_matrix);
+int chest_sv_run_batch(uint64_t handle, int n_body, const double* pn_time, const chest_sv_draws* draws, uint64_t seed,
+                       int64_t first_body, uint32_t* err_out);
+
 /* D_est = sum_p W(:,:,p) hP(p), h_est = diag(D_est) (DS.m:417-428,493-517).
  * hP: P complex; Dhat_out K x K (may be NULL); hdiag_out K (may be NULL). */
 int chest_estimate(uint64_t handle, int scheme, int variant, int i_snr, const double* hP,

@@ -458,3 +458,38 @@ def test_loop_body_with_discrete_doppler_channel():
     b = ctx.run_batch(2, 2, None, seed=4, first_rep=13)
     assert np.array_equal(a[3:], b) and a.sum() > 0
     ctx.close()
+
+
+def test_simple_version_chain_on_device():
+    """BASELINE.json configs[0]: the loop body of SimpleVersion_DoublyFlat.m (SV.m:89-176) as batched device launches
+    (chest_sv_run_batch: FFT modem, doubly-flat channel, LS + interpolation matrix, equalisation, BER) against the oracle's
+    restatement of the same lines on identical draws -- identical error counts for all five BER outputs -- and the seeded
+    Monte-Carlo run against the closed-form theory curve (SV.m:181, Theory/BitErrorProbabilityDoublyFlatRayleigh.m)."""
+    from chest_b200.simulation import SimpleVersionSimulation
+    from oracle.sv import sv_setup, sv_new_draws, sv_body, sv_pn
+    from oracle.bep import bit_error_probability_doubly_flat_rayleigh as bep
+    sim = SimpleVersionSimulation(max_batch=2048, seed=3)
+    S = sv_setup(sim.ChannelEstimation_FBMC.PilotMatrix, sim.AuxiliaryMethod.PilotMatrix, sim.ChannelEstimation_OFDM.PilotMatrix,
+                 sim.interp_f, sim.interp_o)
+    assert np.max(np.abs(S["aux"].PrecodingMatrix - sim.AuxiliaryMethod.PrecodingMatrix)) < 1e-13
+    assert np.max(np.abs(S["cod"].PrecodingMatrix - sim.CodingMethod.PrecodingMatrix)) < 1e-13
+    rng = np.random.default_rng(21)
+    snrs = [0.0, 10.0, 20.0, 30.0, 15.0, 25.0]
+    draws = [sv_new_draws(S, rng) for _ in snrs]
+    pn = np.array([sv_pn(S, x) for x in snrs])
+    assert np.allclose(pn, sim.noise_power(snrs))
+    err = sim.ctx.sv_run_batch(pn, draws)
+    for b, d in enumerate(draws):
+        assert np.array_equal(err[b], sv_body(S, d, pn[b])), b
+    ber, raw = sim.run(NrRepetitions=600)
+    assert ber["BER_OFDM"].shape == (7, 600)
+    theory = bep(np.array(sim.M_SNR_OFDM_dB, dtype=float), sim.QAM.SymbolMapping, sim.QAM.BitMapping)
+    for name in ("BER_OFDM_perfect", "BER_FBMC_perfect"):
+        got = ber[name].mean(axis=1)
+        assert np.all(np.abs(got - theory) < 0.2 * theory + 2e-4), (name, got, theory)
+    assert np.all(ber["BER_FBMC_Cod"].mean(axis=1) >= ber["BER_FBMC_perfect"].mean(axis=1) * 0.9)
+    # the seeded run does not depend on the batch size
+    sim2 = SimpleVersionSimulation(max_batch=100, seed=3)
+    _, raw2 = sim2.run(NrRepetitions=40)
+    assert np.array_equal(raw2, raw[:40 * 7])
+    sim.close(); sim2.close()
