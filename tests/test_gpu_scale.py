@@ -481,12 +481,16 @@ def test_simple_version_chain_on_device():
     err = sim.ctx.sv_run_batch(pn, draws)
     for b, d in enumerate(draws):
         assert np.array_equal(err[b], sv_body(S, d, pn[b])), b
-    ber, raw = sim.run(NrRepetitions=600)
-    assert ber["BER_OFDM"].shape == (7, 600)
+    n_rep = 8000
+    ber, raw = sim.run(NrRepetitions=n_rep)
+    assert ber["BER_OFDM"].shape == (7, n_rep)
     theory = bep(np.array(sim.M_SNR_OFDM_dB, dtype=float), sim.QAM.SymbolMapping, sim.QAM.BitMapping)
     for name in ("BER_OFDM_perfect", "BER_FBMC_perfect"):
         got = ber[name].mean(axis=1)
-        assert np.all(np.abs(got - theory) < 0.2 * theory + 2e-4), (name, got, theory)
+        # a doubly-flat repetition is one fade: the per-repetition BER is heavy-tailed at high SNR, so the tolerance is the
+        # sample's own standard error (5 sigma) and not a fraction of the mean
+        se = ber[name].std(axis=1) / np.sqrt(n_rep)
+        assert np.all(np.abs(got - theory) < 5.0 * se + 0.02 * theory), (name, got, theory, se)
     assert np.all(ber["BER_FBMC_Cod"].mean(axis=1) >= ber["BER_FBMC_perfect"].mean(axis=1) * 0.9)
     # the seeded run does not depend on the batch size
     sim2 = SimpleVersionSimulation(max_batch=100, seed=3)
