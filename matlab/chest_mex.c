@@ -3,7 +3,8 @@
  *   out = chest_mex('command', handle, args...)
  *
  * One gateway, dispatch on a command string; the uint64 context handle lives in the MATLAB
- * classdef wrappers (matlab/+Channel/FastFading.m, matlab/+ChestB200/Simulation.m).  The shim only
+ * classdef wrappers (matlab/+Channel/FastFading.m, matlab/+Modulation/FBMC.m, OFDM.m, matlab/+ChestB200/Simulation.m);
+ * every live context is also remembered here and released by the mexAtExit hook.  The shim only
  * converts between MATLAB's split-complex, 1-based, column-major arrays and the ABI's interleaved,
  * 0-based ones; launchers return codes and errors are raised AFTER temporaries are released
  * (mexErrMsgIdAndTxt does not return).  No gpuArray, no Parallel Computing Toolbox, no CPU path.
@@ -12,6 +13,26 @@
 #include <string.h>
 #include "mex.h"
 #include "chest_b200.h"
+
+/* Every live context is remembered so that 'clear mex' / MATLAB exit releases the device memory (mexAtExit). */
+#define CHEST_MEX_MAX_HANDLES 64
+static uint64_t g_handles[CHEST_MEX_MAX_HANDLES];
+static uint64_t g_multi[CHEST_MEX_MAX_HANDLES];
+static int g_at_exit_registered = 0;
+static void at_exit_cleanup(void) {
+    int i;
+    for (i = 0; i < CHEST_MEX_MAX_HANDLES; ++i) if (g_multi[i]) { chest_multi_destroy(g_multi[i]); g_multi[i] = 0; }
+    for (i = 0; i < CHEST_MEX_MAX_HANDLES; ++i) if (g_handles[i]) { chest_destroy(g_handles[i]); g_handles[i] = 0; }
+}
+static void remember(uint64_t* table, uint64_t h) {
+    int i;
+    if (!g_at_exit_registered) { mexAtExit(at_exit_cleanup); g_at_exit_registered = 1; }
+    for (i = 0; i < CHEST_MEX_MAX_HANDLES; ++i) if (!table[i]) { table[i] = h; return; }
+}
+static void forget(uint64_t* table, uint64_t h) {
+    int i;
+    for (i = 0; i < CHEST_MEX_MAX_HANDLES; ++i) if (table[i] == h) table[i] = 0;
+}
 
 static void fail_if(int rc) {
     if (rc != CHEST_OK) mexErrMsgIdAndTxt("chest:error", "%s", chest_last_error());
@@ -47,6 +68,18 @@ static uint8_t* to_u8(const mxArray* a) {
     for (i = 0; i < n; ++i) out[i] = p[i] != 0.0;
     return out;
 }
+static int32_t* to_i32(const mxArray* a, int offset) {      /* doubles -> int32 (offset -1 for 1-based indices) */
+    size_t n = mxGetNumberOfElements(a), i;
+    int32_t* out = (int32_t*)mxMalloc(n * sizeof(int32_t) + 4);
+    const double* p = mxGetPr(a);
+    for (i = 0; i < n; ++i) out[i] = (int32_t)p[i] + offset;
+    return out;
+}
+static mxArray* handle_array(uint64_t h) {
+    mxArray* a = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+    *(uint64_t*)mxGetData(a) = h;
+    return a;
+}
 /* sparse complex matrix -> CSC arrays of the ABI */
 static void sparse_parts(const mxArray* a, int64_t** jc, int64_t** ir, double** val) {
     mwSize ncol = mxGetN(a), c;
@@ -73,9 +106,11 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         fail_if(rc);
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
         *(uint64_t*)mxGetData(plhs[0]) = h;
+        remember(g_handles, h);
         mexLock();                                       /* device state must survive 'clear mex' */
     } else if (!strcmp(cmd, "destroy")) {
         rc = chest_destroy(handle_of(prhs[1]));
+        forget(g_handles, handle_of(prhs[1]));
         mexUnlock();
         fail_if(rc);
     } else if (!strcmp(cmd, "set_channel")) {            /* (h, N, pdp_normalized, fD, dt, paths, model) */
@@ -181,6 +216,130 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxCreateNumericMatrix(12 * (n_iter + 1) * n_snr, n_rep, mxUINT32_CLASS, mxREAL);
         rc = chest_run_batch(handle_of(prhs[1]), (int)n_rep, (int)n_iter, NULL, (uint64_t)mxGetScalar(prhs[4]),
                              (int64_t)mxGetScalar(prhs[5]), (uint32_t*)mxGetData(plhs[0]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "device_info")) {            /* [n_sm, cc] = (device) */
+        int n_sm = 0, maj = 0, min_ = 0;
+        rc = chest_device_info(nrhs > 1 ? (int)mxGetScalar(prhs[1]) : 0, &n_sm, &maj, &min_);
+        fail_if(rc);
+        plhs[0] = mxCreateDoubleScalar((double)n_sm);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(maj * 10.0 + min_);
+    } else if (!strcmp(cmd, "channel_info")) {           /* [n_shift, fD, T] = (h) */
+        int ns = 0, nt = 0; double fd = 0.0;
+        rc = chest_channel_info(handle_of(prhs[1]), &ns, &fd, &nt);
+        fail_if(rc);
+        plhs[0] = mxCreateDoubleScalar((double)ns);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(fd);
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar((double)nt);
+    } else if (!strcmp(cmd, "new_realization_draws")) {  /* (h, batch, doppler_u, phase_u): rand([T 1 Paths]) order per column */
+        rc = chest_new_realization(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetPr(prhs[3]), mxGetPr(prhs[4]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "new_realization_gauss")) {  /* (h, batch, gauss): 'Discrete-*' normals, (2 n_shift + 1) x T per column */
+        double* g = interleave(prhs[3]);
+        rc = chest_new_realization_gauss(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), g);
+        mxFree(g);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "set_impulse_response")) {   /* (h, batch, h_in): N x Lt x batch complex */
+        double* z = interleave(prhs[3]);
+        rc = chest_set_impulse_response(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), z);
+        mxFree(z);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "set_modem")) {
+        /* (h, wf, kind, L, K, FFTSize, bins(0-based), TimeSpacing, O, CP, ZeroGuard, PrototypeFilter|[], PhaseShift|[], NormalizationFactor, F) */
+        int32_t* bins = to_i32(prhs[7], 0);
+        double* ph = mxIsEmpty(prhs[13]) ? NULL : interleave(prhs[13]);
+        rc = chest_set_modem(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[4]),
+                             (int)mxGetScalar(prhs[5]), (int)mxGetScalar(prhs[6]), bins, (int)mxGetScalar(prhs[8]),
+                             (int)mxGetScalar(prhs[9]), (int)mxGetScalar(prhs[10]), (int)mxGetScalar(prhs[11]),
+                             mxIsEmpty(prhs[12]) ? NULL : mxGetPr(prhs[12]), ph, mxGetScalar(prhs[14]), mxGetScalar(prhs[15]));
+        mxFree(bins); if (ph) mxFree(ph);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "modulate_fft") || !strcmp(cmd, "demodulate_fft")) {   /* out = (h, wf, in, n_out_rows) */
+        double* in = interleave(prhs[3]);
+        mwSize ncol = mxGetN(prhs[3]), nout = (mwSize)mxGetScalar(prhs[4]);
+        double* out = (double*)mxMalloc(2 * nout * ncol * sizeof(double));
+        if (!strcmp(cmd, "modulate_fft")) rc = chest_modulate_fft(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), in, (int)ncol, out);
+        else rc = chest_demodulate_fft(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), in, (int)ncol, out);
+        if (rc == CHEST_OK) plhs[0] = deinterleave(out, nout, ncol);
+        mxFree(in); mxFree(out);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "setup_correlations")) {     /* [R_hP, n_support] = (h, wf, pilot_pos(1-based), TimeCorrelation, threshold) */
+        mwSize P = mxGetNumberOfElements(prhs[3]);
+        int32_t* pp = to_i32(prhs[3], -1);
+        double* R = (double*)mxMalloc(2 * P * P * sizeof(double));
+        int64_t nsup = 0;
+        rc = chest_setup_correlations(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), (int)P, pp, mxGetPr(prhs[4]), mxGetScalar(prhs[5]), R, &nsup);
+        if (rc == CHEST_OK) { plhs[0] = deinterleave(R, P, P); if (nlhs > 1) plhs[1] = mxCreateDoubleScalar((double)nsup); }
+        mxFree(pp); mxFree(R);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "build_mmse")) {             /* (h, scheme, variant, R_inv: P x P x n_snr complex, threshold) */
+        mwSize P = mxGetM(prhs[4]);
+        double* Ri = interleave(prhs[4]);
+        rc = chest_build_mmse(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]),
+                              (int)(mxGetNumberOfElements(prhs[4]) / (P * P)), Ri, mxGetScalar(prhs[5]));
+        mxFree(Ri);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "release_setup")) {
+        rc = chest_release_setup(handle_of(prhs[1]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "set_perfect_csi_mode")) {   /* (h, mode): 0 dense D, 1 factored */
+        rc = chest_set_perfect_csi_mode(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "run_batch_draws")) {
+        /* err = (h, n_rep, n_iter, n_snr, doppler_u, phase_u, bits_aux, bits_cod, bits_ofdm, pilot_idx_fbmc, pilot_idx_ofdm, noise)
+         * one column per realization, in the order DS.m:352-368,399 draws them; pilot indices 1-based; noise N x n_snr x n_rep */
+        mwSize n_rep = (mwSize)mxGetScalar(prhs[2]), n_iter = (mwSize)mxGetScalar(prhs[3]), n_snr = (mwSize)mxGetScalar(prhs[4]);
+        chest_draws d;
+        uint8_t* b[3] = {NULL, NULL, NULL}; int32_t* pi_[2] = {NULL, NULL}; double* nz; int k;
+        memset(&d, 0, sizeof(d));
+        d.doppler_u = mxGetPr(prhs[5]); d.phase_u = mxGetPr(prhs[6]);
+        for (k = 0; k < 3; ++k) if (!mxIsEmpty(prhs[7 + k])) { b[k] = to_u8(prhs[7 + k]); d.bits[k] = b[k]; }
+        for (k = 0; k < 2; ++k) if (!mxIsEmpty(prhs[10 + k])) { pi_[k] = to_i32(prhs[10 + k], -1); d.pilot_idx[k] = pi_[k]; }
+        nz = interleave(prhs[12]); d.noise = nz;
+        plhs[0] = mxCreateNumericMatrix(12 * (n_iter + 1) * n_snr, n_rep, mxUINT32_CLASS, mxREAL);
+        rc = chest_run_batch(handle_of(prhs[1]), (int)n_rep, (int)n_iter, &d, 0, 0, (uint32_t*)mxGetData(plhs[0]));
+        for (k = 0; k < 3; ++k) if (b[k]) mxFree(b[k]);
+        for (k = 0; k < 2; ++k) if (pi_[k]) mxFree(pi_[k]);
+        mxFree(nz);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "run_batch_async")) {        /* (h, n_rep, n_iter, seed, first_rep): returns at once */
+        rc = chest_run_batch_async(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), NULL,
+                                   (uint64_t)mxGetScalar(prhs[4]), (int64_t)mxGetScalar(prhs[5]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "wait")) {                   /* err = (h, n_rep, n_iter, n_snr) */
+        mwSize n_rep = (mwSize)mxGetScalar(prhs[2]), n_iter = (mwSize)mxGetScalar(prhs[3]), n_snr = (mwSize)mxGetScalar(prhs[4]);
+        plhs[0] = mxCreateNumericMatrix(12 * (n_iter + 1) * n_snr, n_rep, mxUINT32_CLASS, mxREAL);
+        rc = chest_wait(handle_of(prhs[1]), (uint32_t*)mxGetData(plhs[0]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "multi_create")) {           /* m = (handles: uint64 vector, one finalized context per device) */
+        uint64_t m = 0;
+        rc = chest_multi_create((const uint64_t*)mxGetData(prhs[1]), (int)mxGetNumberOfElements(prhs[1]), &m);
+        fail_if(rc);
+        plhs[0] = handle_array(m);
+        remember(g_multi, m);
+    } else if (!strcmp(cmd, "multi_run")) {              /* [err, totals, reduce_ms] = (m, n_rep_total, n_iter, seed, first_rep, n_snr) */
+        mwSize n_rep = (mwSize)mxGetScalar(prhs[2]), n_iter = (mwSize)mxGetScalar(prhs[3]), n_snr = (mwSize)mxGetScalar(prhs[6]);
+        float ms = 0.0f;
+        mxArray* tot = mxCreateNumericMatrix(12 * (n_iter + 1) * n_snr, 1, mxUINT64_CLASS, mxREAL);
+        plhs[0] = mxCreateNumericMatrix(12 * (n_iter + 1) * n_snr, n_rep, mxUINT32_CLASS, mxREAL);
+        rc = chest_multi_run(handle_of(prhs[1]), (int64_t)n_rep, (int)n_iter, (uint64_t)mxGetScalar(prhs[4]),
+                             (int64_t)mxGetScalar(prhs[5]), (uint32_t*)mxGetData(plhs[0]), (uint64_t*)mxGetData(tot), &ms);
+        fail_if(rc);
+        if (nlhs > 1) plhs[1] = tot;
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar((double)ms);
+    } else if (!strcmp(cmd, "multi_destroy")) {
+        rc = chest_multi_destroy(handle_of(prhs[1]));
+        forget(g_multi, handle_of(prhs[1]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "set_interpolation")) {      /* (h, scheme, InterpolationMatrix K x P) */
+        double* M = interleave(prhs[3]);
+        rc = chest_set_interpolation(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), M);
+        mxFree(M);
+        fail_if(rc);
+    } else if (!strcmp(cmd, "sv_run_batch")) {           /* err = (h, n_body, Pn_time vector (one per body), seed, first_body): 5 x n_body */
+        mwSize n_body = (mwSize)mxGetScalar(prhs[2]);
+        plhs[0] = mxCreateNumericMatrix(5, n_body, mxUINT32_CLASS, mxREAL);
+        rc = chest_sv_run_batch(handle_of(prhs[1]), (int)n_body, mxGetPr(prhs[3]), NULL, (uint64_t)mxGetScalar(prhs[4]),
+                                (int64_t)mxGetScalar(prhs[5]), (uint32_t*)mxGetData(plhs[0]));
         fail_if(rc);
     } else if (!strcmp(cmd, "bit_counts")) {             /* n = (h): 2 x 3 (edge x scheme) */
         int64_t nb[6]; int i;

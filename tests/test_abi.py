@@ -37,3 +37,27 @@ def test_mex_shim_compiles_against_stub():
     shim = os.path.join(ROOT, "matlab", "chest_mex.c")
     subprocess.run(["gcc", "-c", "-Wall", "-Werror", "-I", os.path.join(ROOT, "matlab", "stub"),
                     "-I", os.path.join(ROOT, "include"), "-o", "/tmp/chest_mex_test.o", shim], check=True)
+
+
+def test_matlab_wrappers_use_only_gateway_commands_that_exist():
+    """Static cross-check of the MATLAB side (it cannot be executed here): every chest_mex('command', ...) the classdef
+    wrappers issue is dispatched by matlab/chest_mex.c, and every wrapper class north_star names is present."""
+    import glob
+    import re
+    shim = open(os.path.join(ROOT, "matlab", "chest_mex.c")).read()
+    known = set(re.findall(r'strcmp\(cmd, "([a-z_]+)"\)', shim))
+    used = set()
+    files = glob.glob(os.path.join(ROOT, "matlab", "+*", "*.m"))
+    for f in files:
+        used |= set(re.findall(r"chest_mex\('([a-z_]+)'", open(f).read()))
+    assert used and used <= known, sorted(used - known)
+    names = {os.path.relpath(f, os.path.join(ROOT, "matlab")) for f in files}
+    for want in ("+Channel/FastFading.m", "+Modulation/FBMC.m", "+Modulation/OFDM.m", "+Modulation/SignalConstellation.m",
+                 "+ChannelEstimation/PilotSymbolAidedChannelEstimation.m",
+                 "+ChannelEstimation/ImaginaryInterferenceCancellationAtPilotPosition.m", "+ChestB200/Simulation.m"):
+        assert want in names, want
+    # every ABI entry point the MATLAB tier needs is reachable through the gateway
+    for sym in ("chest_set_modem", "chest_modulate_fft", "chest_demodulate_fft", "chest_setup_correlations", "chest_build_mmse",
+                "chest_multi_run", "chest_run_batch_async", "chest_wait", "chest_set_impulse_response", "chest_sv_run_batch",
+                "mexAtExit"):
+        assert sym in shim, sym
