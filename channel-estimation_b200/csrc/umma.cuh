@@ -1,0 +1,122 @@
+// umma.cuh -- Blackwell (sm_100a) 5th-generation tensor-core plumbing used by the split-precision mode:
+// tcgen05.mma issued by one thread with both operands in shared memory, accumulators in tensor memory (TMEM),
+// tcgen05.ld for the epilogue, tcgen05.commit -> mbarrier hand-over, 1-D bulk copies (the TMA engine's
+// cp.async.bulk) for the static operand.  Inline PTX only; no CUTLASS.
+//
+// Operand layout in shared memory ("K-major, no swizzle", the canonical interleaved form): a tile of R rows x KB
+// 16-bit elements is stored as [k-chunk of 8 elements][row][8 elements], i.e. 16 bytes per (row, chunk); the 8 x 16 B
+// core matrices of consecutive 8-row groups follow each other (SBO = 128 B) and consecutive k-chunks are R * 16 B
+// apart (LBO).  One tcgen05.mma of kind::f16 consumes K = 16 elements = two chunks.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarriers with a bail-out: a wait gives up when `*abort_flag` is set or after ~2^31 polls, sets the flag and
+// returns false; every role of a kernel then leaves its loop, so a protocol bug ends as an error code, never as a hang.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, volatile int* abort_flag) {
+    for (unsigned spin = 0; ; ++spin) {
+        if (mbar_try(bar, parity)) return true;
+        if ((spin & 1023u) == 1023u) {
+            if (*abort_flag) return false;
+            if (spin > (1u << 26)) { *abort_flag = 1; return false; }     // ~ seconds: something is wrong
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// writes made with ordinary stores become visible to the async proxy (tcgen05.mma operand reads, bulk copies)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- tensor memory
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t n_cols) {   // one full warp; n_cols = 2^k >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot_in_smem)), "r"(n_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t n_cols) {           // the warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(n_cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- descriptors
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE: start >> 4 in [0,14), LBO >> 4 in [16,30) (distance of the
+// two 16-byte k-chunks of one MMA), SBO >> 4 in [32,46) (distance of consecutive 8-row groups), version 1 in [46,48)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16)
+           | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor of kind::f16 with BF16 operands, FP32 accumulation, both operands K-major:
+// c_format F32 (1) at [4,6), a_format BF16 (1) at [7,10), b_format BF16 (1) at [10,13), N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: the warp reads its own 32 lanes (lane quarter = warp index % 4), 32 consecutive columns,
+// one 32-bit column per register
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- split of an FP32 value into two BF16 slices: x ~ hi + lo with |x - hi - lo| <= 2^-17 |x|
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {       // result: {hi_half : lo_half}
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+    return r;
+}
+__device__ __forceinline__ float bf16_lo_as_float(uint32_t pair) { return __uint_as_float(pair << 16); }
+__device__ __forceinline__ float bf16_hi_as_float(uint32_t pair) { return __uint_as_float(pair & 0xFFFF0000u); }
+// (a, b) -> packed high slices {b_hi : a_hi} and packed low slices {b_lo : a_lo}
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - bf16_lo_as_float(hi), b - bf16_hi_as_float(hi));
+}
+
+}  // namespace umma
