@@ -406,6 +406,17 @@ class DeviceContext:
         """'factored' (default): D never formed; 'dense': D = Q^H H G materialised per realization (K2)."""
         self._check(self.lib.chest_set_perfect_csi_mode(self._h, {"dense": 0, "factored": 1}[mode]))
 
+    def set_precision(self, mode):
+        """'fp64' (default): FP64 DMMA everywhere; 'split_bf16': the estimated-CSI cancellation on tcgen05 tensor cores with
+        split-BF16 operands and FP32 accumulation in TMEM (the stated reduced-precision mode, ~1e-5 of the interference)."""
+        self._check(self.lib.chest_set_precision(self._h, {"fp64": 0, "split_bf16": 1}[mode]))
+
+    def precision_info(self):
+        """(mode, dense BF16 flops one k_ic_est_tc launch executes, bytes of the packed W operand images)."""
+        m, f, b = C.c_int(0), C.c_double(0), C.c_int64(0)
+        self._check(self.lib.chest_precision_info(self._h, C.byref(m), C.byref(f), C.byref(b)))
+        return ("fp64", "split_bf16")[m.value], f.value, b.value
+
     def kernel_times(self):
         """Device ms of k_apply_hg, k_gemm_d, k_ic_main (sum), k_ic_light (sum) in the last profiled batch."""
         out = (C.c_float * 10)()

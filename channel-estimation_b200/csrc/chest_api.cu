@@ -3,6 +3,7 @@
 // runs in the kernels of kernels.cuh on the context's stream.  No CPU fallback.
 #include "../../include/chest_b200.h"
 #include "kernels.cuh"
+#include "kernels_tc.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -105,6 +106,9 @@ struct MmseVariant {
     DevBuf<cplx> diag_frag;        // [snr][rt][pq][32 lanes]
     DevBuf<WTiles> table;
     int64_t nnz_offdiag_pairs = 0;
+    // split-BF16 tensor-core mode (chest_set_precision): active columns per 128-row tile and the operand images
+    DevBuf<int> tc_jlist, tc_jptr; DevBuf<uint8_t> tc_img; int tc_entries = 0, tc_row_tiles = 0; bool tc_packed = false;
+    std::vector<int> tc_jptr_h;
 };
 struct Scheme {
     bool set = false;
@@ -153,6 +157,10 @@ struct Ctx {
         cudaEvent_t landed = nullptr, released = nullptr; bool used = false;
     } pf[2];
     int pf_next = 0;
+    int precision = 0;           // 0: FP64 DMMA everywhere (default); 1: estimated-CSI cancellation on tcgen05, split BF16 (kernels_tc.cuh)
+    int tc_p8 = 0;               // pilots per scheme padded to the k-chunking of the tensor-core mode (16 or 32)
+    DevBuf<TcItem> tc_items; DevBuf<int> tc_cta_ptr, tc_status; int tc_n_items = 0, tc_grid = 0;
+    double tc_mma_flops = 0;     // dense BF16 flops one launch of k_ic_est_tc executes (roofline of the reduced-precision mode)
     int perf_mode = 1;           // 1 (default): factored, y - Q^H H (G v) + h v, D never formed; 0: D materialised (K2) and applied densely
     int n_est_units = 0;
     cudaStream_t copy_stream = nullptr;
@@ -409,6 +417,96 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep) {
     return CHEST_OK;
 }
 
+// ---- split-BF16 tensor-core mode: operand images of W (kernels_tc.cuh).  Once per (scheme, variant); all SNR points.
+int ensure_tc_pack(Ctx* c) {
+    int p8 = 16;
+    for (int si = 0; si < 3; ++si) if (c->sch[si].set) p8 = std::max(p8, c->sch[si].P <= 16 ? 16 : 32);
+    for (int si = 0; si < 3; ++si)
+        if (c->sch[si].set && c->sch[si].P > 32) return fail(CHEST_ERR_STATE, "split-BF16 mode supports at most 32 pilots per scheme");
+    if (c->tc_p8 != p8) { for (auto& s : c->sch) for (auto& m : s.mm) m.tc_packed = false; c->tc_p8 = p8; }
+    const int NCH = p8 / 4;
+    const size_t a_bytes = (size_t)2 * NCH * TC_ROWS * 16;
+    cudaStream_t st = c->stream;
+    for (int si = 0; si < 3; ++si) {
+        Scheme& s = c->sch[si];
+        if (!s.set) continue;
+        const int K = s.K, P4 = (s.P + 3) / 4, RT8 = (K + 7) / 8, n_rt = (K + TC_ROWS - 1) / TC_ROWS;
+        for (int v = 0; v < 2; ++v) {
+            MmseVariant& m = s.mm[v];
+            if (!m.set || m.tc_packed) continue;
+            std::vector<int> tptr(RT8 + 1), tdel(std::max(m.n_tiles, 1));
+            CK(cudaMemcpyAsync(tptr.data(), m.tile_ptr.p, sizeof(int) * (RT8 + 1), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(tdel.data(), m.tile_delta.p, sizeof(int) * std::max(m.n_tiles, 1), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::vector<int> jlist, jptr(n_rt + 1, 0), a_tile;
+            std::vector<char> mark(K);
+            for (int t = 0; t < n_rt; ++t) {
+                std::fill(mark.begin(), mark.end(), 0);
+                for (int rt = t * (TC_ROWS / 8); rt < std::min(RT8, (t + 1) * (TC_ROWS / 8)); ++rt)
+                    for (int e = tptr[rt]; e < tptr[rt + 1]; ++e)
+                        for (int r = 0; r < 8; ++r) {
+                            const int i = rt * 8 + r, j = i + tdel[e];
+                            if (i < K && j >= 0 && j < K) mark[j] = 1;
+                        }
+                for (int j = 0; j < K; ++j) if (mark[j]) { jlist.push_back(j); a_tile.push_back(t); }
+                jptr[t + 1] = (int)jlist.size();
+            }
+            m.tc_entries = (int)jlist.size(); m.tc_row_tiles = n_rt; m.tc_jptr_h = jptr;
+            if (jlist.empty()) { jlist.push_back(0); a_tile.push_back(0); }
+            DevBuf<int> d_atile;
+            CK(m.tc_jlist.upload(jlist, st)); CK(m.tc_jptr.upload(jptr, st)); CK(d_atile.upload(a_tile, st));
+            CK(m.tc_img.alloc((size_t)c->S * std::max(m.tc_entries, 1) * a_bytes));
+            for (int snr = 0; snr < c->S && m.tc_entries > 0; ++snr) {
+                k_tc_pack_w<<<m.tc_entries, TC_ROWS, 0, st>>>(m.tc_img.p + (size_t)snr * m.tc_entries * a_bytes, m.frag[snr].p, m.tile_ptr.p,
+                                                              m.tile_delta.p, m.tc_jlist.p, d_atile.p, K, P4, NCH);
+                c->launches++;
+            }
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+            m.tc_packed = true;
+        }
+    }
+    return CHEST_OK;
+}
+
+// Work items of k_ic_est_tc: (scheme, SNR point, up to 8 consecutive EST units = 128 realization columns, one row tile),
+// balanced over one CTA per SM on the host (longest processing time first).
+int build_tc_items(Ctx* c, const std::vector<IcCta>& v, int n_est) {
+    struct Cost { TcItem it; int cost; };
+    std::vector<Cost> all;
+    const int NCH = c->tc_p8 / 4;
+    double flops = 0;
+    for (int u = 0; u < n_est;) {
+        int u1 = u + 1;
+        while (u1 < n_est && u1 - u < TC_COLS / NC_MAX && v[u1].mode == 0 && v[u1].scheme_or_wf == v[u].scheme_or_wf && v[u1].snr == v[u].snr) ++u1;
+        const MmseVariant& m = c->sch[v[u].scheme_or_wf].mm[0];
+        for (int t = 0; t < m.tc_row_tiles; ++t) {
+            const int cost = m.tc_jptr_h[t + 1] - m.tc_jptr_h[t];
+            all.push_back({{v[u].scheme_or_wf, v[u].snr, u, u1 - u, t, t + 1}, cost});
+            flops += (double)cost * 3 * (NCH / 2) * 2.0 * TC_ROWS * (2 * TC_COLS) * 16;
+        }
+        u = u1;
+    }
+    c->tc_mma_flops = flops;
+    std::stable_sort(all.begin(), all.end(), [](const Cost& a, const Cost& b) { return a.cost > b.cost; });
+    const int grid = std::max(1, std::min(c->n_sm, (int)all.size()));
+    std::vector<std::vector<TcItem>> per(grid);
+    std::vector<long long> load(grid, 0);
+    // longest first onto the least loaded CTA (a heap is not worth it for a few thousand items x 148 CTAs)
+    for (const Cost& x : all) {
+        int best = 0;
+        for (int b = 1; b < grid; ++b) if (load[b] < load[best]) best = b;
+        per[best].push_back(x.it); load[best] += x.cost + 8;
+    }
+    std::vector<TcItem> items; std::vector<int> ptr(grid + 1, 0);
+    for (int b = 0; b < grid; ++b) { items.insert(items.end(), per[b].begin(), per[b].end()); ptr[b + 1] = (int)items.size(); }
+    c->tc_n_items = (int)items.size(); c->tc_grid = grid;
+    if (items.empty()) items.push_back({0, 0, 0, 0, 0, 0});
+    CK(c->tc_items.upload(items, c->stream)); CK(c->tc_cta_ptr.upload(ptr, c->stream));
+    CK(c->tc_status.alloc(1)); CK(cudaMemsetAsync(c->tc_status.p, 0, sizeof(int), c->stream));
+    return CHEST_OK;
+}
+
 int build_ctas(Ctx* c, int n_rep) {
     if (c->ctas_for_batch == n_rep) return CHEST_OK;
     std::vector<IcCta> v;
@@ -460,6 +558,11 @@ int build_ctas(Ctx* c, int n_rep) {
     }
     c->n_ctas = (int)v.size();
     if (c->perf_mode != 1) c->n_est_units = c->n_ctas;
+    if (c->precision == 1) {
+        if (c->perf_mode != 1) return fail(CHEST_ERR_STATE, "the split-BF16 mode runs with the factored perfect-CSI pass (CHEST_PERFECT_FACTORED)");
+        int rc = ensure_tc_pack(c); if (rc) return rc;
+        rc = build_tc_items(c, v, c->n_est_units); if (rc) return rc;
+    }
     CK(c->ctas.upload(v, c->stream));
     CK(c->scratch.alloc((size_t)c->n_ctas * 3 * c->K_max * NC_MAX));
     if (c->perf_mode == 1) {
@@ -715,6 +818,30 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         ip.it = it;
         if (it > 0) {                                              // phase B of iteration it
             ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
+            if (c->precision == 1) {
+                TcParams tp{};
+                tp.it = it; tp.n_iter = n_iter; tp.n_rep = n_rep; tp.K_max = c->K_max; tp.n_items = c->tc_n_items;
+                tp.items = c->tc_items.p; tp.cta_ptr = c->tc_cta_ptr.p; tp.ctas = c->ctas.p; tp.scratch = c->scratch.p; tp.status = c->tc_status.p;
+                for (int si = 0; si < 3; ++si) {
+                    Scheme& s = c->sch[si];
+                    if (!s.set) continue;
+                    TcScheme& ts = tp.sch[si];
+                    ts.K = s.K; ts.P = s.P; ts.n_row_tiles = s.mm[0].tc_row_tiles; ts.y = ip.sch[si].y; ts.hP = ip.sch[si].hP;
+                    for (int v = 0; v < 2; ++v) {
+                        ts.jlist[v] = s.mm[v].tc_jlist.p; ts.jptr[v] = s.mm[v].tc_jptr.p; ts.a_img[v] = s.mm[v].tc_img.p;
+                        ts.a_snr_stride[v] = (long long)s.mm[v].tc_entries * 2 * (c->tc_p8 / 4) * TC_ROWS * 16;
+                    }
+                }
+                if (c->tc_p8 == 16) {
+                    static bool attr16 = false;
+                    if (!attr16) { CK(cudaFuncSetAttribute(k_ic_est_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<16>::SMEM)); attr16 = true; }
+                    k_ic_est_tc<16><<<c->tc_grid, TC_THREADS, TcGeo<16>::SMEM, st>>>(tp);
+                } else {
+                    static bool attr32 = false;
+                    if (!attr32) { CK(cudaFuncSetAttribute(k_ic_est_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<32>::SMEM)); attr32 = true; }
+                    k_ic_est_tc<32><<<c->tc_grid, TC_THREADS, TcGeo<32>::SMEM, st>>>(tp);
+                }
+            } else
             main_kernel<<<main_grid, ic_threads, main_smem, st>>>(ip);
             c->launches++;
             ip.trace = nullptr;
@@ -755,6 +882,11 @@ int finish_pipeline(Ctx* c) {
     const int n_iter = c->pending_iter, n_rep = c->pending_rep, N = c->N;
     c->pending = false;
     CK(cudaStreamSynchronize(st));
+    if (c->precision == 1 && c->tc_status.p) {
+        int flag = 0;
+        CK(cudaMemcpy(&flag, c->tc_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) { cudaMemset(c->tc_status.p, 0, sizeof(int)); return fail(CHEST_ERR_CUDA, "k_ic_est_tc: the tensor-core pipeline gave up on an mbarrier (protocol error)"); }
+    }
     if (c->trace_on) {
         const char* trace_path = getenv("CHEST_IC_TRACE");
         std::vector<unsigned long long> th((size_t)c->ic_grid * 8);
@@ -2264,6 +2396,28 @@ int chest_set_perfect_csi_mode(uint64_t handle, int mode) {
     ARG(c && (mode == 0 || mode == 1));
     c->perf_mode = mode;
     c->ctas_for_batch = -1;                                    // unit order and column tables depend on the mode
+    return CHEST_OK;
+}
+
+int chest_set_precision(uint64_t handle, int mode) {
+    Ctx* c = from(handle);
+    ARG(c && (mode == CHEST_PRECISION_FP64 || mode == CHEST_PRECISION_SPLIT_BF16));
+    if (c->pending) return fail(CHEST_ERR_STATE, "an asynchronous run is pending on this context");
+    c->precision = mode;
+    c->ctas_for_batch = -1;                                    // the work items of the tensor-core kernel are built with the unit list
+    return CHEST_OK;
+}
+
+int chest_precision_info(uint64_t handle, int* mode, double* mma_flops_per_launch, int64_t* operand_bytes) {
+    Ctx* c = from(handle);
+    ARG(c);
+    if (mode) *mode = c->precision;
+    if (mma_flops_per_launch) *mma_flops_per_launch = c->tc_mma_flops;
+    if (operand_bytes) {
+        int64_t b = 0;
+        for (auto& s : c->sch) for (auto& m : s.mm) b += (int64_t)m.tc_img.n;
+        *operand_bytes = b;
+    }
     return CHEST_OK;
 }
 

@@ -16,7 +16,7 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// ---- mbarriers with a bail-out: a wait gives up when `*abort_flag` is set or after ~2^31 polls, sets the flag and
+// ---- mbarriers with a bail-out: a wait gives up when `*abort_flag` is set or after ~2 s, sets the flag and
 // returns false; every role of a kernel then leaves its loop, so a protocol bug ends as an error code, never as a hang.
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
@@ -35,11 +35,13 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
     return ok != 0;
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, volatile int* abort_flag) {
-    for (unsigned spin = 0; ; ++spin) {
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (unsigned spin = 1; ; ++spin) {
         if (mbar_try(bar, parity)) return true;
-        if ((spin & 1023u) == 1023u) {
+        if ((spin & 255u) == 0u) {
             if (*abort_flag) return false;
-            if (spin > (1u << 26)) { *abort_flag = 1; return false; }     // ~ seconds: something is wrong
+            if (clock64() - t0 > 4000000000ll) { *abort_flag = 1; return false; }     // ~2 s: something is wrong
         }
     }
 }

@@ -243,6 +243,18 @@ int chest_run_batch(uint64_t handle, int n_rep, int n_iter, const chest_draws* d
 #define CHEST_PERFECT_DENSE     0
 #define CHEST_PERFECT_FACTORED  1
 int chest_set_perfect_csi_mode(uint64_t handle, int mode);
+/* Arithmetic of the estimated-CSI interference cancellation y - (D_est - diag h_est) v (DS.m:482-484, the dominant cost of
+ * the loop body).  CHEST_PRECISION_FP64 (default): FP64 tensor-core DMMA, results within 1e-9 of the reference arithmetic and
+ * identical hard decisions.  CHEST_PRECISION_SPLIT_BF16: the stated reduced-precision mode -- the same sum on the 5th-generation
+ * tensor cores (tcgen05.mma, FP32 accumulators in tensor memory, both operands split into two BF16 slices, three products):
+ * the cancelled symbols differ by ~1e-5 of the interference magnitude (within the 1e-4 the mode states); pilot estimates,
+ * W_diag h_P, equalisation, decisions, counters and the perfect-CSI twin stay FP64.  Needs CHEST_PERFECT_FACTORED and at most 32
+ * pilots per scheme; the operand images are packed at the next run.  chest_precision_info: mode, the dense BF16 flops one
+ * launch of the tensor-core kernel executes (roofline numerator) and the bytes of the packed operand images; any may be NULL. */
+#define CHEST_PRECISION_FP64        0
+#define CHEST_PRECISION_SPLIT_BF16  1
+int chest_set_precision(uint64_t handle, int mode);
+int chest_precision_info(uint64_t handle, int* mode, double* mma_flops_per_launch, int64_t* operand_bytes);
 /* Work units (up to 16 columns x all K rows each) the IC kernels processed in the last batch. */
 int chest_unit_count(uint64_t handle, int* n_units);
 

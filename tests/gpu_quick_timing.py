@@ -1,5 +1,5 @@
 """Development script (not a test): stage timings of the loop body on a B200 with oracle-built
-setup inputs.  python tests/gpu_quick_timing.py [batch] [reps]"""
+setup inputs.  python tests/gpu_quick_timing.py [batch] [reps] [fp64|split_bf16]"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,12 +8,14 @@ from tests.helpers import context_from_oracle
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+precision = sys.argv[3] if len(sys.argv) > 3 else "fp64"
 S = ds_setup(DSConfig())
 t = time.time()
 ctx = context_from_oracle(S, max_batch=B)
 print("context setup s", time.time() - t)
 print("fp64 peak dmma TF/s", ctx.fp64_peak("dmma"), "dfma TF/s", ctx.fp64_peak("dfma"))
 print("work model", ctx.work_model(4))
+ctx.set_precision(precision)
 ctx.set_profiling(True)
 for i in range(reps):
     t = time.time()
@@ -26,4 +28,4 @@ ber = err.astype(float).mean(axis=0)
 for sid, n in enumerate(("aux", "cod", "ofdm")):
     print(n, "BER est it0..4 @40dB", np.round(ber[-1, :, sid, 0, 0] / nb[sid, 0], 4),
           "perfect", np.round(ber[-1, :, sid, 1, 0] / nb[sid, 0], 4))
-print("launches", ctx.launch_count())
+print("launches", ctx.launch_count(), "precision", ctx.precision_info())
