@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="realizations per step per GPU")
     ap.add_argument("--schemes", default="aux,cod,ofdm")
     ap.add_argument("--no-ofdm-only", action="store_true", help="skip the extra OFDM-chain-only measurement")
+    ap.add_argument("--no-split-leg", action="store_true", help="skip the extra leg in the split-BF16 tensor-core mode")
     ap.add_argument("--no-dense-leg", action="store_true", help="skip the extra leg with D materialised (K2 rooflines)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="realizations timed for cpu_baseline (about 13 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -147,6 +148,63 @@ def dense_mode_line(torch, Simulation, schemes, device, B, K, W, I, peak_dmma, h
                             "peak_source": hbm_src, "algorithmic_bytes_per_step": hg_bytes / K, "ms_per_step": hg_ms / K}}
     sim.close()
     return line
+
+
+def split_bf16_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last_first, wm):
+    """The stated reduced-precision mode on the same context and workload (chest_set_precision(SPLIT_BF16)): the
+    estimated-CSI cancellation runs on tcgen05 tensor cores (k_ic_est_tc: split-BF16 operands, FP32 accumulators in TMEM),
+    everything else stays FP64.  Reports the step time, the tensor roofline of the kernel against the measured BF16 peak,
+    and how many hard decisions differ from the FP64 mode on the last timed batch."""
+    n_snr = len(sim.Pn)
+    ctx.set_precision("split_bf16")
+    err_dev = torch.zeros(B * n_snr * (I + 1) * 12, dtype=torch.int32, device="cuda")
+    step = [10 ** 6]
+
+    def run(first=None):
+        ctx.run_batch_device(B, I, None, seed=sim.seed, first_rep=step[0] * B if first is None else first,
+                             err_dev_ptr=err_dev.data_ptr())
+        step[0] += 1
+    for _ in range(W):
+        run()
+    torch.cuda.synchronize()
+    ctx.event_record(0)
+    kern = {}
+    for _ in range(K):
+        run()
+        for k, v in ctx.kernel_times().items():
+            kern[k] = kern.get(k, 0.0) + v
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    run(first=last_first)                                       # the batch the FP64 mode processed last
+    torch.cuda.synchronize()
+    got = err_dev.view(B, n_snr, I + 1, 3, 2, 2).cpu().numpy().astype(np.int64)
+    ref = err_fp64_last.astype(np.int64)
+    nb = ctx.bit_counts()
+    n_dec = B * n_snr * I * float(sum(nb[sid, 0] for sid in range(3)))
+    mode, mma_flops, img_bytes = ctx.precision_info()
+    ctx.set_precision("fp64")
+    tc_ms = kern["k_ic_main"] / (K * I)
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(pk["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; burst %.0f)" % pk["bf16_tflops"]
+    except Exception:
+        peak, peak_src = 1400.0, "B200_PROFILING.md fallback, sustained 1.4 PFLOP/s (MEASURED_PEAKS.json absent)"
+    alg = B * wm["est_main_flops"] / I
+    return {"value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "realizations_per_step": B, "dtype": "bf16x2 split operands, f32 accumulate (estimated-CSI cancellation only; the rest f64)",
+            "kernel_ms_per_step": {k: v / K for k, v in kern.items()},
+            "roofline": {"kernel": "k_ic_est_tc (tcgen05.mma kind::f16 BF16, 128 x 256 x 16, three products per k-step, TMEM accumulators, bulk-copied W images)",
+                         "bound": "tensor", "achieved": mma_flops / (tc_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": mma_flops / (tc_ms * 1e-3) / 1e12 / peak, "peak_source": peak_src, "avg_launch_ms": tc_ms,
+                         "executed_dense_bf16_flops_per_launch": mma_flops, "algorithmic_flops_per_launch": alg,
+                         "algorithmic_tflops": alg / (tc_ms * 1e-3) / 1e12,
+                         "note": "achieved counts the dense BF16 flops the MMAs execute: 3 split products x 4 real products per complex one x "
+                                 "the block-dense tiles (128 rows x the union of their active columns; about 27 % of those entries are "
+                                 "non-zero at the default geometry).  algorithmic_tflops is the 8-flop-per-complex-MAC count of the FP64 "
+                                 "roofline over the same launch time, for comparison with k_ic_main"},
+            "operand_image_bytes": int(img_bytes),
+            "vs_fp64_mode": {"bit_decisions_that_differ": int(np.abs(got - ref)[:, :, 1:, :, 0, 0].sum()), "of": int(n_dec),
+                             "perfect_csi_and_one_tap_counters_identical": bool(np.array_equal(got[:, :, :, :, 1], ref[:, :, :, :, 1]) and np.array_equal(got[:, :, 0], ref[:, :, 0])),
+                             "tolerance": "estimated channel within 1e-4 of the FP64 mode (tests/test_gpu_tc.py measures 3e-6 on the pilot estimates, 1e-5 on diag(D_est))"}}
 
 
 def ofdm_only_line(torch, Simulation, device, K, W, cpu_sample):
@@ -457,6 +515,15 @@ def run_b200(args):
                                       "algorithmic_bytes_per_launch": light_bytes,
                                       "note": "y_ic read + v written once per unit (16 columns x K rows x 16 B each way); the kernel is "
                                               "instruction bound, not bandwidth bound: profiles/r02_kic_post_vs_light.txt"}
+        if world == 1 and not args.no_split_leg:
+            try:
+                out["split_bf16_mode"] = split_bf16_line(torch, np, ctx, sim, B, K, W, I, err_last, last_first, wm)
+            except Exception as e:                              # noqa: BLE001
+                out["split_bf16_mode"] = {"error": repr(e)[:300]}
+                try:
+                    ctx.set_precision("fp64")
+                except Exception:                               # noqa: BLE001
+                    pass
         if world == 1 and not args.no_dense_leg and not paper:
             # the same workload with D = Q^H H G materialised per realization (K2) and applied densely: the rooflines
             # of k_gemm_d (FP64 tensor) and k_apply_hg (HBM) come from this leg; never fatal for the main line

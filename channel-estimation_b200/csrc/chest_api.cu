@@ -65,6 +65,8 @@ struct Waveform {
     int K = 0;
     DevBuf<cplx> G, Q, Gt;
     DevBuf<cplx> Q1; DevBuf<double> Q2;                // three-multiplication planes of Q^H: (re, re - im), im; row stride Np
+    DevBuf<cplx> Gt1; DevBuf<double> Gt2;              // planes of G (not conjugated), rows = samples: (re, re + im), -im; row stride Kp
+    DevBuf<cplx> f_r1; DevBuf<double> f_r2;            // planes of r = H s of the factored perfect-CSI pass: (re, re + im), im - re; [column][Np]
     DevBuf<cplx> HG1; DevBuf<double> HG2;              // H*G planes: (re, re + im), im - re; [rep][K][Np]
     DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi, d_jlo, d_jhi;
     DevBuf<int> q8_klo, q8_khi, hg8_klo, hg8_khi, gt8_klo, gt8_khi;
@@ -267,6 +269,7 @@ SchemeDev scheme_dev(Ctx* c, int si) {
     d.n_data = s.n_data; d.nbits = c->cst[s.constellation].nbits; d.detect_mode = s.detect;
     d.constellation = s.constellation; d.n_bits_total = s.n_bits;
     d.sqrt_kappa = std::sqrt(s.kappa); d.dpr = s.dpr; d.sqrt_dpr = std::sqrt(s.dpr);
+    d.inv_sqrt_dpr = 1.0 / d.sqrt_dpr; d.inv_dpr = 1.0 / s.dpr;
 #ifndef CHEST_VREAL
 #define CHEST_VREAL 1
 #endif
@@ -389,11 +392,59 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
 // Perfect-CSI cancellation without D: y_ic = y - Q^H (H (G v)) + h v for every (realization, scheme, SNR) column
 // (DS.m:541-543 with D = Q^H H G, h = diag D).  Two support-aware GEMMs over all columns of the batch with the banded
 // channel between them; the second GEMM's epilogue writes y_ic into the units' scratch.
+template <int WM, int WN, int TMW, bool BG, int EPI>
+cudaError_t launch_gemm_ring_geo(Ctx* c, GemmRingParams& p) {
+    constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
+    constexpr int smem = GEMMD_STAGES * 3 * (TM + TN) * (GEMMD_KT + 4) * (int)sizeof(double);
+    static int grid = 0;
+    if (!grid) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_ring<WM, WN, TMW, BG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gemm_ring<WM, WN, TMW, BG, EPI>, 32 * WM * WN, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        grid = per_sm * c->n_sm;
+    }
+    p.n_mt = (p.M + TM - 1) / TM; p.n_nt = (p.n_cols + TN - 1) / TN;
+    const long long total = (long long)p.n_mt * p.n_nt;
+    if (total == 0) return cudaSuccess;
+    if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+    k_gemm_ring<WM, WN, TMW, BG, EPI><<<(int)std::min<long long>(grid, total), 32 * WM * WN, smem, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
+}
+template <bool BG, int EPI>
+cudaError_t launch_gemm_ring(Ctx* c, GemmRingParams& p, int tile) {
+    if (tile == 48) return launch_gemm_ring_geo<2, 3, 3, BG, EPI>(c, p);
+    return launch_gemm_ring_geo<2, 4, 4, BG, EPI>(c, p);
+}
+
 int stage_factored_perfect_csi(Ctx* c, int n_rep) {
-    const int N = c->N;
+    const int N = c->N, Np = (N + 1) & ~1;
+    static const bool legacy = getenv("CHEST_CHAIN_LEGACY") != nullptr;      // development: the block-barrier k_gemm<PLAIN> chain
     for (int wfi = 0; wfi < 2; ++wfi) {
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch || !w.f_cols) continue;
+        if (!legacy) {
+            GemmRingParams p{};                                                             // s = G v
+            p.M = N; p.n_cols = w.f_cols; p.lda = (w.K + 1) & ~1; p.ldc = N;
+            p.At1 = w.Gt1.p; p.At2 = w.Gt2.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.m8_klo = w.gt8_klo.p; p.m8_khi = w.gt8_khi.p;
+            p.bsrc = c->scratch.p; p.b_off = w.f_voff.p; p.b_kstride = NC_MAX; p.out = w.f_s.p;
+            CK((launch_gemm_ring<true, 0>(c, p, w.tile)));
+            dim3 grid((N + 127) / 128, w.f_cols);                                           // r = H s, written as operand planes
+            k_apply_h_cols_planes<<<grid, 128, 0, c->stream>>>(w.f_r1.p, w.f_r2.p, w.f_s.p, c->h.p, c->d_tap_delay.p, w.f_rep.p, N, Np, c->T);
+            c->launches++;
+            CK(cudaGetLastError());
+            GemmRingParams q{};                                                             // y_ic = y - Q^H r + h v
+            q.M = w.K; q.n_cols = w.f_cols; q.lda = Np; q.ldb = Np; q.ldc = w.K;
+            q.At1 = w.Q1.p; q.At2 = w.Q2.p; q.mt_klo = w.q_klo.p; q.mt_khi = w.q_khi.p; q.m8_klo = w.q8_klo.p; q.m8_khi = w.q8_khi.p;
+            q.b1 = w.f_r1.p; q.b2 = w.f_r2.p;
+            q.e_out = c->scratch.p + (size_t)c->K_max * NC_MAX; q.e_off = w.f_voff.p;       // y_ic sits one buffer behind v
+            q.e_y = w.y.p; q.e_yoff = w.f_yoff.p; q.e_h = w.htrue.p; q.e_rep = w.f_rep.p; q.e_v = c->scratch.p;
+            CK((launch_gemm_ring<false, 1>(c, q, w.tile)));
+            continue;
+        }
         GemmParams p{};
         p.M = N; p.Kc = w.K; p.n_cols = w.f_cols; p.lda = w.K; p.ldc = N; p.conj_a = 0;
         p.At = w.Gt.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.out = w.f_s.p;
@@ -586,6 +637,15 @@ int build_ctas(Ctx* c, int n_rep) {
                     }
             CK(w.f_voff.upload(voff, c->stream)); CK(w.f_yoff.upload(yoff, c->stream)); CK(w.f_rep.upload(rep, c->stream));
             CK(w.f_s.alloc((size_t)w.f_cols * c->N)); CK(w.f_r.alloc((size_t)w.f_cols * c->N));
+            {
+                const size_t Np = (size_t)((c->N + 1) & ~1);
+                const bool fresh = w.f_r1.n < (size_t)w.f_cols * Np;
+                CK(w.f_r1.alloc((size_t)w.f_cols * Np)); CK(w.f_r2.alloc((size_t)w.f_cols * Np));
+                if (fresh) {                                    // the padding sample of an odd N is read by the 16-byte copies
+                    CK(cudaMemsetAsync(w.f_r1.p, 0, sizeof(cplx) * w.f_r1.n, c->stream));
+                    CK(cudaMemsetAsync(w.f_r2.p, 0, sizeof(double) * w.f_r2.n, c->stream));
+                }
+            }
         }
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -1081,6 +1141,18 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
     for (int j = 0; j < K; ++j)
         for (int n = 0; n < N; ++n) gt[(size_t)j + (size_t)K * n] = g[(size_t)n + (size_t)N * j];
     CK(w.Gt.upload(gt, c->stream));
+    {   // planes of G for the ring GEMM s = G v of the factored perfect-CSI pass
+        const int Kp = (K + 1) & ~1;
+        std::vector<cplx> g1((size_t)Kp * N, cmake(0.0, 0.0));
+        std::vector<double> g2((size_t)Kp * N, 0.0);
+        for (int j = 0; j < K; ++j)
+            for (int n = 0; n < N; ++n) {
+                const cplx v = g[(size_t)n + (size_t)N * j];
+                g1[(size_t)j + (size_t)Kp * n] = cmake(v.x, v.x + v.y);
+                g2[(size_t)j + (size_t)Kp * n] = -v.y;
+            }
+        CK(w.Gt1.upload(g1, c->stream)); CK(w.Gt2.upload(g2, c->stream));
+    }
     support_ranges(G, N, K, w.g_lo, w.g_hi);
     support_ranges(Q, N, K, w.q_lo, w.q_hi);
     std::vector<int> lo, hi;

@@ -202,6 +202,22 @@ __global__ void k_apply_h_cols(cplx* __restrict__ r, const cplx* __restrict__ s,
     r[(int64_t)col * N + n] = acc;
 }
 
+// the same, r written as the three-multiplication operand planes of the next GEMM: r1 = (re, re + im), r2 = im - re; row stride Np
+__global__ void k_apply_h_cols_planes(cplx* __restrict__ r1, double* __restrict__ r2, const cplx* __restrict__ s, const cplx* __restrict__ h,
+                                      const int* __restrict__ tap_delay, const int* __restrict__ rep_of_col, int N, int Np, int T) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (n >= N) return;
+    const int rep = rep_of_col[col];
+    const cplx* sc = s + (int64_t)col * N;
+    cplx acc = cmake(0.0, 0.0);
+    for (int t = 0; t < T; ++t) {
+        const int d = tap_delay[t];
+        if (n >= d) cfma(acc, h[((int64_t)rep * T + t) * N + n], sc[n - d]);
+    }
+    r1[(int64_t)col * Np + n] = cmake(acc.x, acc.x + acc.y);
+    r2[(int64_t)col * Np + n] = acc.y - acc.x;
+}
+
 // ============================================================================ constellations
 struct ConstDev {
     int order, nbits, n_axis;           // n_axis = order (PAM) or sqrt(order) (QAM)
@@ -239,7 +255,7 @@ struct WTiles {                    // one (variant, snr) MMSE matrix in diagonal
 struct SchemeDev {
     int waveform, K, K_in, P, P4, n_data, nbits, detect_mode, constellation, n_bits_total;
     int v_real;                    // precoder and constellation are exactly real: v = C z has a zero imaginary part
-    double sqrt_kappa, dpr, sqrt_dpr;
+    double sqrt_kappa, dpr, sqrt_dpr, inv_sqrt_dpr, inv_dpr;
     const int* c_rowptr; const int* c_col; const cplx* c_val;      // precoder C, CSR (K rows)
     const int* ct_colptr; const int* ct_row; const cplx* ct_val;   // precoder C, CSC (K_in cols)
     const int* pilot_pos; const int* data_pos; const uint32_t* edge_mask;   // per data symbol bit mask
@@ -729,6 +745,214 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 1 : 2) k_gemm_d
                             const cplx v = cmake(c1[a][b][e] + cr[a][b][e], c1[a][b][e] + ci[a][b][e]);
                             out[((int64_t)(m >> 3) * p.n_cols + col) * 8 + (m & 7)] = v;
                             if (p.hdiag && m == col) p.hdiag[(int64_t)cc.rep * p.M + m] = v;
+                        }
+                    }
+            clear_acc();
+            cc.t += gridDim.x; load_item(cc);
+            if (cc.t < total) warp_range();
+        }
+    }
+}
+
+// ============================================================================ persistent ring GEMM over a column list
+// The K2 design (one shared-memory ring of k-tiles running across work items, mbarrier hand-over, three-multiplication
+// operand planes, warp-level k clipping) for the two GEMMs of the factored perfect-CSI pass, whose columns are the
+// (realization, scheme, SNR) vectors of the whole batch:
+//   BGATHER = true   s = G v          A = planes of G (rows = samples), B gathered from the units' interleaved v scratch
+//                                      (16-byte cp.async per element, stride b_kstride; the operand sums are formed in registers)
+//   BGATHER = false  U = Q^H r        A = planes of Q^H, B = planes of r written by k_apply_h_cols
+// EPI = 0: out[col][m] = C;  EPI = 1: the cancellation epilogue y_ic = y - C + h v written into the unit scratch.
+// Work items: (row tile, column tile), row tile fastest, so CTAs that run side by side share their B columns in L2.
+struct GemmRingParams {
+    int M, n_cols, lda, ldb, ldc, n_mt, n_nt;
+    const cplx* At1; const double* At2;          // A planes [m][lda] (k-contiguous)
+    const cplx* b1; const double* b2;            // B planes [col][ldb]                 (BGATHER = false)
+    const cplx* bsrc; const int64_t* b_off; int b_kstride;                               // (BGATHER = true)
+    const int* mt_klo; const int* mt_khi; const int* m8_klo; const int* m8_khi;
+    cplx* out;
+    cplx* e_out; const int64_t* e_off; const cplx* e_y; const int64_t* e_yoff; const cplx* e_h; const int* e_rep;
+    const cplx* e_v;
+};
+template <int WM, int WN, int TMW, bool BGATHER, int EPI>
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 1 : 2) k_gemm_ring(GemmRingParams p) {
+    constexpr int TM = 8 * TMW * WM, TN = 16 * WN, KT = GEMMD_KT, LDS = KT + 4, NTHR = 32 * WM * WN, NS = GEMMD_STAGES;
+    extern __shared__ __align__(128) double smem[];
+    cplx (*As)[TM][LDS] = reinterpret_cast<cplx (*)[TM][LDS]>(smem);
+    cplx (*Bs)[TN][LDS] = reinterpret_cast<cplx (*)[TN][LDS]>(smem + NS * 2 * TM * LDS);
+    double (*As2)[TM][LDS] = reinterpret_cast<double (*)[TM][LDS]>(smem + NS * 2 * (TM + TN) * LDS);
+    double (*Bs2)[TN][LDS] = reinterpret_cast<double (*)[TN][LDS]>(smem + NS * 2 * (TM + TN) * LDS + NS * TM * LDS);
+    __shared__ uint64_t full[NS], empty[NS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t4 = lane & 3;
+    if (tid == 0) {
+        for (int s_ = 0; s_ < NS; ++s_) { mbar_init(&full[s_], NTHR); mbar_init(&empty[s_], WM * WN); }
+    }
+    __syncthreads();
+    const int total = p.n_mt * p.n_nt;
+
+    struct Cursor { int t, kt, nk, klo, khi, m0, n0; };
+    auto load_item = [&](Cursor& c) {
+        if (c.t >= total) { c.nk = 0; return; }
+        const int nt = c.t / p.n_mt, mt = c.t - nt * p.n_mt;
+        c.klo = p.mt_klo[mt] & ~1; c.khi = p.mt_khi[mt];
+        c.nk = c.khi > c.klo ? (c.khi - c.klo + KT - 1) / KT : 0;
+        c.m0 = mt * TM; c.n0 = nt * TN; c.kt = 0;
+    };
+    Cursor cc;
+    cc.t = blockIdx.x;
+    load_item(cc);
+
+    constexpr int EA = (TM * KT) / NTHR, EB = (TN * KT) / NTHR, EA2 = (TM * KT / 2) / NTHR, EB2 = (TN * KT / 2) / NTHR;
+    static_assert(EA * NTHR == TM * KT && EB * NTHR == TN * KT && EA2 * NTHR == TM * KT / 2 && EB2 * NTHR == TN * KT / 2, "tile / thread mismatch");
+    constexpr int RSTEP = NTHR / KT, RSTEP2 = NTHR / (KT / 2);
+    const int kk1 = tid & (KT - 1), r1 = tid / KT, kk2 = (tid & (KT / 2 - 1)) * 2, r2 = tid / (KT / 2);
+    const unsigned sA1 = (unsigned)__cvta_generic_to_shared(&As[0][r1][kk1]), sB1 = (unsigned)__cvta_generic_to_shared(&Bs[0][r1][kk1]);
+    const unsigned sA2 = (unsigned)__cvta_generic_to_shared(&As2[0][r2][kk2]), sB2 = (unsigned)__cvta_generic_to_shared(&Bs2[0][r2][kk2]);
+    constexpr unsigned STG_A1 = TM * LDS * 16, STG_B1 = TN * LDS * 16, STG_A2 = TM * LDS * 8, STG_B2 = TN * LDS * 8;
+    int pt = blockIdx.x, pkt = 0, pnk = 0, prem = 0;
+    const cplx* ga1 = nullptr; const double* ga2 = nullptr; const double* gb2 = nullptr;
+    const cplx* gb1[EB];
+    unsigned okA1 = 0, okB1 = 0, okA2 = 0, okB2 = 0;
+    auto producer_item = [&]() {
+        int nt = 0, mt = 0, klo = 0, khi = 0;
+        for (;;) {                                             // items with an empty k-range have no jobs
+            if (pt >= total) { pnk = 0; return; }
+            nt = pt / p.n_mt; mt = pt - nt * p.n_mt;
+            klo = p.mt_klo[mt] & ~1; khi = p.mt_khi[mt];
+            if (khi > klo) break;
+            pt += gridDim.x;
+        }
+        pnk = (khi - klo + KT - 1) / KT; pkt = 0; prem = khi - klo;
+        const int m0 = mt * TM, n0 = nt * TN;
+        ga1 = p.At1 + (int64_t)(m0 + r1) * p.lda + klo + kk1;
+        ga2 = p.At2 + (int64_t)(m0 + r2) * p.lda + klo + kk2;
+        okA1 = okB1 = okA2 = okB2 = 0;
+#pragma unroll
+        for (int e = 0; e < EA; ++e) okA1 |= (unsigned)(m0 + r1 + e * RSTEP < p.M) << e;
+#pragma unroll
+        for (int e = 0; e < EA2; ++e) okA2 |= (unsigned)(m0 + r2 + e * RSTEP2 < p.M) << e;
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const int col = n0 + r1 + e * RSTEP;
+            const bool ok = col < p.n_cols;
+            okB1 |= (unsigned)ok << e;
+            if (BGATHER) gb1[e] = p.bsrc + (ok ? p.b_off[col] + (int64_t)(klo + kk1) * p.b_kstride : 0);
+            else gb1[e] = p.b1 + (ok ? (int64_t)col * p.ldb + klo + kk1 : 0);
+        }
+        if (!BGATHER) {
+            gb2 = p.b2 + (int64_t)(n0 + r2) * p.ldb + klo + kk2;
+#pragma unroll
+            for (int e = 0; e < EB2; ++e) okB2 |= (unsigned)(n0 + r2 + e * RSTEP2 < p.n_cols) << e;
+        }
+    };
+    auto cp16 = [](unsigned dst, const void* src, bool ok) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 16 : 0));
+    };
+    unsigned pj = 0, cj = 0;
+    auto produce = [&]() {
+        if (pnk == 0) return;
+        const unsigned st = pj % NS;
+        if (pj >= NS) mbar_wait(&empty[st], ((pj / NS) - 1) & 1);
+        const bool k1 = kk1 < prem, k2 = kk2 < prem;
+        const int64_t lda = p.lda, ldb = p.ldb;
+#pragma unroll
+        for (int e = 0; e < EA; ++e) { const bool ok = k1 && ((okA1 >> e) & 1); cp16(sA1 + st * STG_A1 + e * RSTEP * LDS * 16, ok ? ga1 + e * RSTEP * lda : p.At1, ok); }
+#pragma unroll
+        for (int e = 0; e < EA2; ++e) { const bool ok = k2 && ((okA2 >> e) & 1); cp16(sA2 + st * STG_A2 + e * RSTEP2 * LDS * 8, ok ? ga2 + e * RSTEP2 * lda : p.At2, ok); }
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const bool ok = k1 && ((okB1 >> e) & 1);
+            cp16(sB1 + st * STG_B1 + e * RSTEP * LDS * 16, ok ? (const void*)gb1[e] : (const void*)p.At1, ok);
+            gb1[e] += BGATHER ? (int64_t)KT * p.b_kstride : KT;
+        }
+        if (!BGATHER) {
+#pragma unroll
+            for (int e = 0; e < EB2; ++e) { const bool ok = k2 && ((okB2 >> e) & 1); cp16(sB2 + st * STG_B2 + e * RSTEP2 * LDS * 8, ok ? gb2 + e * RSTEP2 * ldb : p.At2, ok); }
+            gb2 += KT;
+        }
+        mbar_arrive_cp_async(&full[st]);
+        ++pj;
+        ga1 += KT; ga2 += KT; prem -= KT;
+        if (++pkt == pnk) { pt += gridDim.x; producer_item(); }
+    };
+    producer_item();
+
+    double cr[TMW][2][2], ci[TMW][2][2], c1[TMW][2][2];
+    auto clear_acc = [&]() {
+#pragma unroll
+        for (int a = 0; a < TMW; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) { cr[a][b][0] = cr[a][b][1] = ci[a][b][0] = ci[a][b][1] = c1[a][b][0] = c1[a][b][1] = 0.0; }
+    };
+    int wlo = 0, whi = 0;
+    auto warp_range = [&]() {
+        wlo = cc.klo; whi = cc.khi;
+        if (p.m8_klo) {
+            int lo = 0x7fffffff, hi = 0;
+#pragma unroll
+            for (int x = 0; x < TMW; ++x) {
+                const int r = cc.m0 + wm * 8 * TMW + x * 8;
+                if (r < p.M) { lo = min(lo, p.m8_klo[r >> 3]); hi = max(hi, p.m8_khi[r >> 3]); }
+            }
+            wlo = max(wlo, lo); whi = min(whi, hi);
+        }
+    };
+    clear_acc();
+    if (cc.t < total) warp_range();
+#pragma unroll 1
+    for (int i = 0; i < GEMMD_DEPTH; ++i) produce();
+#pragma unroll 1
+    while (cc.t < total) {
+        produce();
+        if (cc.nk > 0) {
+            const int st = cj % NS;
+            mbar_wait(&full[st], (cj / NS) & 1);
+            const int kbase = cc.klo + cc.kt * KT;
+#pragma unroll
+            for (int kk = 0; kk < KT; kk += 4) {
+                if (kbase + kk + 4 <= wlo || kbase + kk >= whi) continue;     // warp-uniform
+                cplx a[TMW], b[2];
+                double a2[TMW], b2[2];
+#pragma unroll
+                for (int x = 0; x < TMW; ++x) { a[x] = As[st][wm * 8 * TMW + x * 8 + g][kk + t4]; a2[x] = As2[st][wm * 8 * TMW + x * 8 + g][kk + t4]; }
+#pragma unroll
+                for (int y = 0; y < 2; ++y) {
+                    b[y] = Bs[st][wn * 16 + y * 8 + g][kk + t4];
+                    if (BGATHER) { b2[y] = b[y].y - b[y].x; b[y].y = b[y].x + b[y].y; }      // (br, br+bi), bi-br
+                    else b2[y] = Bs2[st][wn * 16 + y * 8 + g][kk + t4];
+                }
+#pragma unroll
+                for (int x = 0; x < TMW; ++x)
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        dmma884(c1[x][y][0], c1[x][y][1], a[x].y, b[y].x);
+                        dmma884(cr[x][y][0], cr[x][y][1], a2[x], b[y].y);
+                        dmma884(ci[x][y][0], ci[x][y][1], a[x].x, b2[y]);
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+            ++cj;
+            ++cc.kt;
+        }
+        if (cc.kt >= cc.nk) {
+#pragma unroll
+            for (int a = 0; a < TMW; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int m = cc.m0 + wm * 8 * TMW + a * 8 + g, col = cc.n0 + wn * 16 + b * 8 + 2 * t4 + e;
+                        if (m < p.M && col < p.n_cols) {
+                            const cplx v = cmake(c1[a][b][e] + cr[a][b][e], c1[a][b][e] + ci[a][b][e]);
+                            if (EPI == 1) {        // y_ic = y - U + h v  (DS.m:541-543 with U = Q^H H G v)
+                                const cplx yv = p.e_y[p.e_yoff[col] + m], hv = p.e_h[(int64_t)p.e_rep[col] * p.M + m];
+                                const cplx vv = p.e_v[p.e_off[col] + (int64_t)m * 16];
+                                const cplx hvv = cmul(hv, vv);
+                                p.e_out[p.e_off[col] + (int64_t)m * 16] = cmake(yv.x - v.x + hvv.x, yv.y - v.y + hvv.y);
+                            } else
+                                p.out[(int64_t)col * p.ldc + m] = v;
                         }
                     }
             clear_acc();
@@ -1300,6 +1524,9 @@ __global__ void __launch_bounds__(IC_THREADS, IC_MIN_BLOCKS) k_ic_main(IcParams 
 #ifndef IC_LIGHT_THREADS
 #define IC_LIGHT_THREADS 256
 #endif
+#ifndef IC_LIGHT_UNROLL
+#define IC_LIGHT_UNROLL 4      // rows in flight per thread in the perfect-CSI equalisation pass (8 spills at 64 registers)
+#endif
 // Hard decision of one data-symbol estimate: bit errors against the transmitted word, and the decided word
 // (the quantised symbol of the next iteration's cancellation, DS.m:482-484).
 __device__ __forceinline__ int ic_decide(const ConstDev& cd, cplx xd, uint32_t tw, uint32_t em, unsigned& e_all, unsigned& e_edge) {
@@ -1419,11 +1646,11 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                                 const int64_t col = (int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c];
                                 const cplx hh = cmake(hr[ct][e], hi[ct][e]);
                                 if (last) sd.hdiag[col * K + i] = hh;
-                                const cplx xh = cdiv(yv[ct][e], hh);
+                                const cplx xh = cdiv_fast(yv[ct][e], hh);
                                 if (!select) { vbuf[i * NC + c] = xh; continue; }
                                 if (d < 0) continue;
-                                const cplx xd = cmake(xh.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y / sd.sqrt_dpr);
-                                const int word = ic_decide(cd, xd, sd.txword[(int64_t)sh.c_rep[c] * sd.n_data + d], em, e_all[ct][e], e_edge[ct][e]);
+                                const cplx xd = cmake(xh.x * sd.inv_sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y * sd.inv_sqrt_dpr);
+                                const int word = ic_decide(cd, xd, sd.txw_t[((int64_t)(sh.c_rep[c] >> 4) * sd.n_data + d) * 16 + (sh.c_rep[c] & 15)], em, e_all[ct][e], e_edge[ct][e]);
                                 if (last) sd.xD[0][col * sd.n_data + d] = xd;
                                 if (next_pre) zw[d * NC + c] = (uint8_t)word;
                             }
@@ -1454,25 +1681,25 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 const uint32_t* __restrict__ txw = sd.txword + (int64_t)(okc ? sh.c_rep[c] : 0) * sd.n_data;
                 unsigned e_all = 0, e_edge = 0;
                 const int istep = nthr / NC;
-                for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
-                    cplx yv[8], hv[8];
-                    int dd[8];
+                for (int i0 = tid / NC; i0 < K; i0 += IC_LIGHT_UNROLL * istep) {
+                    cplx yv[IC_LIGHT_UNROLL], hv[IC_LIGHT_UNROLL];
+                    int dd[IC_LIGHT_UNROLL];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < IC_LIGHT_UNROLL; ++u) {
                         const int i = i0 + u * istep;
                         yv[u] = (okc && i < K) ? yic(i, c) : cmake(0.0, 0.0);
                         hv[u] = (okc && i < K) ? ht[i] : cmake(1.0, 0.0);
                         dd[u] = (okc && select && i < K) ? sd.pos2data[i] : -1;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < IC_LIGHT_UNROLL; ++u) {
                         const int i = i0 + u * istep;
                         if (i >= K || !okc) continue;
-                        const cplx xh = cdiv(yv[u], hv[u]);
+                        const cplx xh = cdiv_fast(yv[u], hv[u]);
                         if (!select) { vbuf[i * NC + c] = xh; continue; }
                         const int d = dd[u];
                         if (d < 0) continue;
-                        const cplx xd = cmake(xh.x / sd.sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y / sd.sqrt_dpr);
+                        const cplx xd = cmake(xh.x * sd.inv_sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y * sd.inv_sqrt_dpr);
                         const int word = ic_decide(cd, xd, txw[d], sd.edge_mask[d], e_all, e_edge);
                         if (last) sd.xD[1][colbase + d] = xd;
                         if (next_pre) zw[d * NC + c] = (uint8_t)word;
@@ -1492,7 +1719,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
             if (sh.c_rep[c] >= 0 && sd.detect_mode == 1) {
                 const ConstDev& cd = sh.cst[sd.constellation];
                 const int64_t colbase = ((int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c]) * sd.n_data;
-                const uint32_t* __restrict__ txw = sd.txword + (int64_t)sh.c_rep[c] * sd.n_data;
+                const uint32_t* __restrict__ txw = sd.txw_t + (int64_t)(sh.c_rep[c] >> 4) * sd.n_data * 16 + (sh.c_rep[c] & 15);
                 const int dstep = nthr / NC;
                 for (int d0 = tid / NC; d0 < sd.n_data; d0 += 4 * dstep) {
                     cplx xd[4];
@@ -1517,13 +1744,13 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                             const cplx t = cmulc(sd.ct_val[e], vbuf[sd.ct_row[e] * NC + c]);
                             acc.x += t.x; acc.y += t.y;
                         }
-                        xd[u] = cmake(acc.x / sd.dpr, 0.0);
+                        xd[u] = cmake(acc.x * sd.inv_dpr, 0.0);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int d = d0 + u * dstep;
                         if (d < sd.n_data) {
-                            const int word = ic_decide(cd, xd[u], txw[d], sd.edge_mask[d], e_all, e_edge);
+                            const int word = ic_decide(cd, xd[u], txw[(int64_t)d * 16], sd.edge_mask[d], e_all, e_edge);
                             if (last) sd.xD[csi][colbase + d] = xd[u];
                             if (next_pre) zw[d * NC + c] = (uint8_t)word;
                         }
