@@ -904,8 +904,8 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 1 : 2) k_gemm_r
     for (int i = 0; i < GEMMD_DEPTH; ++i) produce();
 #pragma unroll 1
     while (cc.t < total) {
-        produce();
-        if (cc.nk > 0) {
+        if (cc.nk > 0) {                                       // (an item with an empty k-range -- e.g. rows inside the zero guard of
+            produce();                                         //  an OFDM frame -- has no jobs: the producer must not run further ahead)
             const int st = cj % NS;
             mbar_wait(&full[st], (cj / NS) & 1);
             const int kbase = cc.klo + cc.kt * KT;
