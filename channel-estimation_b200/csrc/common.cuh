@@ -39,6 +39,13 @@ __device__ __forceinline__ cplx cdiv_fast(cplx a, cplx b) {
     const double inv = rcp_pos(fma(b.x, b.x, b.y * b.y));
     return cmake(fma(a.x, b.x, a.y * b.y) * inv, fma(a.y, b.x, -(a.x * b.y)) * inv);
 }
+// 16-byte load through the read-only path (data no thread of the kernel writes); not volatile, so the compiler may batch
+// several of them ahead of the arithmetic and stores that follow
+__device__ __forceinline__ cplx ld_nc(const cplx* ptr) {
+    cplx r;
+    asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(ptr));
+    return r;
+}
 __device__ __forceinline__ double dneg(double x) {   // sign flip on the integer pipe
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
 }

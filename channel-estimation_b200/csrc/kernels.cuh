@@ -937,24 +937,53 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN == 8) ? 1 : 2) k_gemm_r
             ++cc.kt;
         }
         if (cc.kt >= cc.nk) {
-#pragma unroll
-            for (int a = 0; a < TMW; ++a)
+            if (EPI == 1) {
+                // y_ic = y - U + h v  (DS.m:541-543 with U = Q^H H G v).  The operands of a row tile's four columns are
+                // fetched first (read-only path, so the loads are not ordered behind the stores), then combined and stored.
+                int64_t off[2][2], yo[2][2]; int rp[2][2]; bool okc[2][2];
 #pragma unroll
                 for (int b = 0; b < 2; ++b)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int m = cc.m0 + wm * 8 * TMW + a * 8 + g, col = cc.n0 + wn * 16 + b * 8 + 2 * t4 + e;
-                        if (m < p.M && col < p.n_cols) {
-                            const cplx v = cmake(c1[a][b][e] + cr[a][b][e], c1[a][b][e] + ci[a][b][e]);
-                            if (EPI == 1) {        // y_ic = y - U + h v  (DS.m:541-543 with U = Q^H H G v)
-                                const cplx yv = p.e_y[p.e_yoff[col] + m], hv = p.e_h[(int64_t)p.e_rep[col] * p.M + m];
-                                const cplx vv = p.e_v[p.e_off[col] + (int64_t)m * 16];
-                                const cplx hvv = cmul(hv, vv);
-                                p.e_out[p.e_off[col] + (int64_t)m * 16] = cmake(yv.x - v.x + hvv.x, yv.y - v.y + hvv.y);
-                            } else
-                                p.out[(int64_t)col * p.ldc + m] = v;
-                        }
+                        const int col = cc.n0 + wn * 16 + b * 8 + 2 * t4 + e;
+                        okc[b][e] = col < p.n_cols;
+                        off[b][e] = okc[b][e] ? p.e_off[col] : 0; yo[b][e] = okc[b][e] ? p.e_yoff[col] : 0; rp[b][e] = okc[b][e] ? p.e_rep[col] : 0;
                     }
+#pragma unroll
+                for (int a = 0; a < TMW; ++a) {
+                    const int m = cc.m0 + wm * 8 * TMW + a * 8 + g;
+                    if (m >= p.M) continue;
+                    cplx yv[2][2], hv[2][2], vv[2][2];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            yv[b][e] = ld_nc(p.e_y + yo[b][e] + m);
+                            hv[b][e] = ld_nc(p.e_h + (int64_t)rp[b][e] * p.M + m);
+                            vv[b][e] = ld_nc(p.e_v + off[b][e] + (int64_t)m * 16);
+                        }
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            if (!okc[b][e]) continue;
+                            const cplx hvv = cmul(hv[b][e], vv[b][e]);
+                            p.e_out[off[b][e] + (int64_t)m * 16] = cmake(yv[b][e].x - (c1[a][b][e] + cr[a][b][e]) + hvv.x,
+                                                                          yv[b][e].y - (c1[a][b][e] + ci[a][b][e]) + hvv.y);
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < TMW; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int m = cc.m0 + wm * 8 * TMW + a * 8 + g, col = cc.n0 + wn * 16 + b * 8 + 2 * t4 + e;
+                            if (m < p.M && col < p.n_cols)
+                                p.out[(int64_t)col * p.ldc + m] = cmake(c1[a][b][e] + cr[a][b][e], c1[a][b][e] + ci[a][b][e]);
+                        }
+            }
             clear_acc();
             cc.t += gridDim.x; load_item(cc);
             if (cc.t < total) warp_range();

@@ -1,10 +1,11 @@
 """Development tool: key metrics, stall reasons and hot instructions of one kernel from an .ncu-rep.
-usage: python tools/ncu_report.py file.ncu-rep [n_hot]"""
+usage: python tools/ncu_report.py file.ncu-rep [n_hot] [kernel index in the report]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; n_hot = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(io.StringIO(raw)))
-h, u, v = r[0], r[1], r[2]
+h, u, v = r[0], r[1], r[2 + kidx]
 d = {h[i]: (v[i], u[i]) for i in range(len(h))}
 print(d.get("Kernel Name"), d.get("Grid Size"), d.get("Block Size"))
 for k in ["gpu__time_duration.sum", "launch__registers_per_thread", "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active",
@@ -18,7 +19,7 @@ for k in ["gpu__time_duration.sum", "launch__registers_per_thread", "sm__pipe_sh
 st = [(k, float(d[k][0].replace(",", ""))) for k in d if k.startswith("smsp__average_warp") and "issue_stalled" in k and "ratio" in k]
 print("stalls per issue:", ", ".join("%s %.2f" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), x)
                                       for k, x in sorted(st, key=lambda t: -t[1])[:8]))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(kidx), "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]; ix = {n: i for i, n in enumerate(hdr)}
 data = [x for x in rows[2:] if len(x) == len(hdr)]
