@@ -47,11 +47,12 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=48, help="realizations timed for cpu_baseline (about 13 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-sample", action="store_true", help="skip the oracle check of sampled realizations")
-    ap.add_argument("--workload", default="default", choices=["default", "paper", "sweep", "sv"],
+    ap.add_argument("--workload", default="default", choices=["default", "paper", "sweep", "sv", "scaled"],
                     help="default: DS.m default parameters (BASELINE.json configs[1], the headline); paper: DS.m:42-46 "
                          "(configs[2]); sweep: velocity sweep, 1e5 realizations over all GPUs including setup (configs[3]); "
                          "sv: SimpleVersion_DoublyFlat.m chain with the FFT modem on the device (configs[0])")
     ap.add_argument("--sweep-realizations", type=int, default=100000)
+    ap.add_argument("--scaled-subcarriers", type=int, default=300, help="--workload scaled: 300 / 600 / 1200 (5 / 10 / 20 MHz LTE grids)")
     return ap.parse_args()
 
 
@@ -645,7 +646,223 @@ def run_sweep(args):
 
 
 def run_sv(args):
-    raise SystemExit("bench.py --workload sv: not built yet")
+    """BASELINE.json configs[0]: SimpleVersion_DoublyFlat.m (L = 12, 30 FBMC / 15 OFDM symbols, 16-QAM / 4-PAM, SNR 0:5:30 dB,
+    8 Diamond pilots, doubly-flat Rayleigh channel).  A "realization" of this workload is one body of the script's double loop,
+    SV.m:91-170 (one repetition at one SNR point, all five BER outputs), run as batched device launches (chest_sv_run_batch)."""
+    import numpy as np
+    import torch
+    from chest_b200.simulation import SimpleVersionSimulation
+    from oracle.sv import sv_setup, sv_new_draws, sv_body, sv_pn
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(0)
+    B, K, W = (8192 if args.batch == 4096 else args.batch), args.steps, args.warmup
+    t0 = time.perf_counter()
+    sim = SimpleVersionSimulation(max_batch=B, seed=1234)
+    setup_s = time.perf_counter() - t0
+    ctx = sim.ctx
+    snrs = np.resize(np.asarray(sim.M_SNR_OFDM_dB, dtype=float), B)            # body = rep * nS + snr, as the script loops
+    pn = sim.noise_power(snrs)
+    step = [0]
+
+    def run():
+        err = ctx.sv_run_batch(pn, None, seed=sim.seed, first_body=step[0] * B)
+        step[0] += 1
+        return err
+    for _ in range(W):
+        run()
+    clocks = ClockSampler(0)
+    torch.cuda.synchronize()
+    clocks.start()
+    l0 = ctx.launch_count()
+    ctx.event_record(0)
+    t_w = time.perf_counter()
+    for _ in range(K):
+        err = run()
+    ctx.event_record(1)
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    wall_ms = 1e3 * (time.perf_counter() - t_w)
+    launches = ctx.launch_count() - l0
+    clk = clocks.stop()
+    # end to end: explicit host draws (bits, pilot indices, channel coefficient, noise of both waveforms) in, counts out
+    S = sv_setup(sim.ChannelEstimation_FBMC.PilotMatrix, sim.AuxiliaryMethod.PilotMatrix, sim.ChannelEstimation_OFDM.PilotMatrix,
+                 sim.interp_f, sim.interp_o)
+    rng = np.random.default_rng(3)
+    Be = min(B, 2048)
+    base = [sv_new_draws(S, rng) for _ in range(64)]
+    draws = [base[i % 64] for i in range(Be)]
+    h2d = sum(np.asarray(v).nbytes for v in base[0].values()) * Be
+    ctx.sv_run_batch(pn[:Be], draws)
+    t_e = time.perf_counter()
+    for _ in range(max(1, K // 2)):
+        err_e = ctx.sv_run_batch(pn[:Be], draws)
+    e2e_ms = 1e3 * (time.perf_counter() - t_e) / max(1, K // 2)
+    # parity on the explicit draws: identical error counts to the oracle's restatement of SV.m:95-169
+    bad = [b for b in range(0, 64, 7) if not np.array_equal(err_e[b], sv_body(S, draws[b], pn[b]))]
+    # CPU baseline: the oracle port of the loop body on the host cores
+    cores = use_all_host_cores()
+    t_c = time.perf_counter(); n_c = 0
+    while time.perf_counter() - t_c < 10.0:
+        sv_body(S, base[n_c % 64], pn[n_c % len(pn)]); n_c += 1
+    cpu = n_c / (time.perf_counter() - t_c)
+    ber = (err.reshape(-1, len(sim.M_SNR_OFDM_dB), 5).astype(float).mean(axis=0) / sim.n_bits[None, :])
+    N = sim.FBMC.Nr["SamplesTotal"]
+    bytes_per_body = 16.0 * N * 2 * 2                               # transmit + receive signal of both waveforms (the FFT modem's traffic)
+    out = {"metric": METRIC, "value": B * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "SimpleVersion_DoublyFlat.m default parameters (BASELINE.json configs[0]): L=12, 30 FBMC / 15 OFDM symbols, "
+                                  "N=%d, 16-QAM / 4-PAM, SNR 0:5:30 dB, 8 Diamond pilots; one realization = one (repetition, SNR) body SV.m:91-170" % N,
+                      "bodies_per_step": B, "timing": "CUDA events on the library's stream around all K steps", "seed": sim.seed,
+                      "l2": "working set per step %.1f GB (signals of %d bodies) vs 126 MB L2" % (B * bytes_per_body / 1e9, B)},
+           "e2e": {"value": Be / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(err_e.nbytes),
+                   "bodies_per_step": Be, "api": "chest_sv_run_batch (C ABI) with explicit host draws (pageable NumPy buffers): bits, pilot indices, h, noise in; error counts out"},
+           "gpu_launches": int(launches), "clocks": clk, "wall_ms_per_step": wall_ms / K, "setup_s": setup_s,
+           "roofline": {"kernel": "FFT modem + channel + detection chain (k_modem_ifft, k_fbmc_overlap_add, k_sv_channel, k_modem_fft, k_sv_detect)",
+                        "bound": "hbm", "achieved": B * K * bytes_per_body / (dev_ms * 1e-3) / 1e9, "peak": _hbm_peak()[0], "unit": "GB/s",
+                        "frac": B * K * bytes_per_body / (dev_ms * 1e-3) / 1e9 / _hbm_peak()[0], "traffic": None,
+                        "note": "algorithmic bytes: the time-domain signals written by the modulators and read by the demodulators "
+                                "(16 N bytes each way per waveform and body); the step is a chain of small launch-bound kernels, not one HBM-bound kernel",
+                        "peak_source": _hbm_peak()[1]},
+           "parity_sample": "ok" if not bad else "MISMATCH at bodies %s" % bad,
+           "sanity_ber_by_snr": {n: [round(float(x), 5) for x in ber[:, k]] for k, n in enumerate(("FBMC_Aux", "FBMC_Cod", "FBMC_perfect", "OFDM", "OFDM_perfect"))},
+           "cpu_baseline": {"value": cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "oracle port of SV.m:95-169 (NumPy FFT modem), %d bodies in 10 s" % n_c}}
+    print(json.dumps(out), flush=True)
+    sim.close()
+    if bad:
+        raise SystemExit(3)
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (MEASURED_PEAKS.json absent)"
+
+
+def run_scaled(args):
+    """BASELINE.json configs[4]: scaled bandwidth.  L = 300 subcarriers (5 MHz LTE grid), fs = 512 x 15 kHz = 7.68 MHz, 30 FBMC
+    symbols: N = 9472 samples, K = 9000 symbols -- the dense model of the reference (G, Q: 1.36 GB each; D: 1.3 GB per realization;
+    H: N x N) does not fit a workstation, the banded H and the support-aware, chunked D GEMM do.  A step = B realizations of rows
+    A-D of the hot path: NewRealization (sum of 200 sinusoids per tap), the banded H applied to G, D = Q^H (H G) with its diagonal."""
+    import numpy as np
+    import torch
+    import chest_b200
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(0)
+    L = args.scaled_subcarriers
+    B, K, W = (8 if args.batch == 4096 else args.batch), args.steps, args.warmup
+    nfft = 512 if L <= 300 else (1024 if L <= 600 else 2048)
+    fs = 15e3 * nfft
+    t0 = time.perf_counter()
+    fb = chest_b200.Modulation.FBMC(L, 30, 15e3, fs, 15e3 * ((nfft - L) // 2), False, "Hermite-OQAM", 4, 0, True)
+    N, Ksym = fb.Nr["SamplesTotal"], L * 30
+    G = fb.GetTXMatrix()
+    Q = fb.GetRXMatrix().conj().T
+    ch = chest_b200.Channel.FastFading(fs, "VehicularA", N, 500 / 3.6 * 2.5e9 / 2.998e8, "Jakes", 200, 1, 1, False, create_device=False)
+    ctx = chest_b200.DeviceContext(0)
+    pdp = ch.Implementation["PowerDelayProfileNormalized"]
+    ctx.set_channel(N, pdp, ch.PHY["MaximumDopplerShift"], ch.PHY["dt"], 200, "Jakes")
+    ctx.set_waveform("F", G, Q)
+    ctx.finalize(B)
+    setup_s = time.perf_counter() - t0
+    peak_dmma = ctx.fp64_peak("dmma", 20000)
+    hbm_peak, hbm_src = _hbm_peak()
+    T = ctx.T
+    step = [0]
+
+    def run():
+        ctx.new_realization_seeded(B, 1234, step[0] * B)
+        step[0] += 1
+        return ctx.transmission_matrix_batch("F", B)
+    for _ in range(W):
+        run()
+    clocks = ClockSampler(0)
+    torch.cuda.synchronize()
+    clocks.start()
+    l0 = ctx.launch_count()
+    ctx.event_record(0)
+    hg_ms = gd_ms = 0.0
+    for _ in range(K):
+        a, b, flops = run()
+        hg_ms += a; gd_ms += b
+    ctx.event_record(1)
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    launches = ctx.launch_count() - l0
+    clk = clocks.stop()
+    # parity: sampled entries of D of the first and last realization against the host product with the device's own h
+    rng = np.random.default_rng(1)
+    taps = np.flatnonzero(pdp)
+    worst = 0.0
+    for b in (0, B - 1):
+        h = ctx.impulse_response(b)                                  # N x Lt
+        rows = rng.integers(0, Ksym, 48); cols = np.clip(rows + rng.integers(-2 * L, 2 * L + 1, 48), 0, Ksym - 1)
+        rows[:8] = cols[:8]                                          # some diagonal entries
+        got = ctx.transmission_matrix_entries("F", b, rows, cols)
+        ref = np.zeros(48, dtype=complex)
+        for e, (i, j) in enumerate(zip(rows, cols)):
+            hg = np.zeros(N, dtype=complex)
+            for m in taps:
+                hg[m:] += h[m:, m] * G[:N - m, j]
+            ref[e] = np.vdot(Q[:, i], hg)
+        worst = max(worst, float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+    # end to end: explicit Doppler / phase draws from the host in, diag(D) of every realization out
+    du = rng.random((B, T * 200)); pu = rng.random((B, T * 200))
+    hd = torch.zeros((B, Ksym, 2), dtype=torch.float64).pin_memory()
+    ctx.new_realization(du, pu); ctx.transmission_matrix_batch("F", B, hd.data_ptr())
+    t_e = time.perf_counter()
+    for _ in range(max(1, K // 2)):
+        ctx.new_realization(du, pu); ctx.transmission_matrix_batch("F", B, hd.data_ptr())
+    e2e_ms = 1e3 * (time.perf_counter() - t_e) / max(1, K // 2)
+    # CPU baseline: the dense formulation of DS.m:388-389 on the host cores, on a slice of the columns of D
+    cores = use_all_host_cores()
+    import scipy.sparse as sp
+    h0 = ctx.impulse_response(0)
+    n_idx = np.arange(N)
+    Hs = sp.csc_matrix((N, N), dtype=complex)
+    for m in taps:
+        Hs = Hs + sp.csc_matrix((h0[m:, m], (n_idx[m:], n_idx[m:] - m)), shape=(N, N))
+    ncol = 300
+    t_c = time.perf_counter()
+    Dslice = Q.conj().T @ (Hs @ G[:, :ncol])
+    cpu_s = (time.perf_counter() - t_c) * Ksym / ncol
+    got = ctx.transmission_matrix_entries("F", 0, np.arange(0, 40), np.arange(0, 40))
+    worst = max(worst, float(np.max(np.abs(got - np.diag(Dslice)[:40])) / np.max(np.abs(Dslice))))
+    bytes_hg = 16.0 * sum(ctx_hg_rows(fb, taps, N)) * B            # H*G rows written per batch (algorithmic: 16 B per element)
+    out = {"metric": METRIC, "value": B * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "scaled bandwidth (BASELINE.json configs[4]): FBMC L=%d subcarriers x 30 symbols, fs=%.2f MHz, N=%d samples, "
+                                  "K=%d symbols, VehicularA (T=%d taps) at 500 km/h; per realization: NewRealization + banded H applied to G + "
+                                  "D = Q^H H G (%.1f GB) + diag(D)  [rows A-D of SURVEY.md 8a]; the MMSE / IC rows are not run at this size "
+                                  "(R_Dij_hP alone would be P x K^2 x 16 B = 259 GB for P = 200 pilots)" % (L, fs / 1e6, N, Ksym, T, 16.0 * Ksym * Ksym / 1e9),
+                      "realizations_per_step": B, "timing": "CUDA events on the library's stream around all K steps",
+                      "l2": "per realization 2.5 GB of H*G planes and 1.3 GB of D vs 126 MB L2"},
+           "e2e": {"value": B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(du.nbytes + pu.nbytes), "d2h_bytes_per_step": int(hd.numel() * 8),
+                   "api": "chest_new_realization (host draws) + chest_transmission_matrix_batch (C ABI): Doppler / phase uniforms in, diag(D) out; D stays in HBM"},
+           "gpu_launches": int(launches), "clocks": clk, "setup_s": setup_s,
+           "roofline": {"kernel": "k_gemm_d (D = Q^H (H G): persistent mbarrier-ring FP64 DMMA GEMM over the tile pairs whose supports overlap)",
+                        "bound": "tensor", "achieved": B * K * flops / (gd_ms * 1e-3) / 1e12, "peak": peak_dmma, "unit": "TFLOP/s",
+                        "frac": B * K * flops / (gd_ms * 1e-3) / 1e12 / peak_dmma, "traffic": None,
+                        "algorithmic_flops_per_realization": flops, "dense_model_flops_per_realization": 8.0 * Ksym * Ksym * N + 8.0 * T * N * Ksym,
+                        "avg_launch_ms": gd_ms / K, "peak_source": "FP64 DMMA loop measured in this run (chest_fp64_peak)"},
+           "roofline_k1": {"kernel": "k_apply_hg (banded, never-materialised H applied to the columns of G)", "bound": "hbm",
+                           "achieved": bytes_hg * K / (hg_ms * 1e-3) / 1e9 if hg_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": bytes_hg * K / (hg_ms * 1e-3) / 1e9 / hbm_peak if hg_ms > 0 else None, "peak_source": hbm_src, "ms_per_step": hg_ms / K},
+           "parity_sample": "ok (max deviation %.1e of max|D| over sampled entries)" % worst if worst < 1e-9 else "MISMATCH %.2e" % worst,
+           "cpu_baseline": {"value": 1.0 / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "Q' * (H * G) of DS.m:388-389 with sparse H and dense G, Q (NumPy/OpenBLAS + SciPy), %d of %d columns of D timed and scaled; "
+                                      "channel synthesis not included" % (ncol, Ksym)}}
+    print(json.dumps(out), flush=True)
+    ctx.close()
+    if worst >= 1e-9:
+        raise SystemExit(3)
+
+
+def ctx_hg_rows(fb, taps, N):
+    """Rows of H*G per column: the column's support widened by the largest delay (what k_apply_hg has to write)."""
+    Np, TS, Ksym, L = fb.Nr["SamplesPrototypeFilter"], fb.Implementation["TimeSpacing"], fb.Nr["MCSymbols"], fb.Nr["Subcarriers"]
+    return [min(N, k * TS + Np + int(taps[-1])) - k * TS for k in range(Ksym) for _ in range(L)]
 
 
 def _one_json_line_stdout():
@@ -666,5 +883,7 @@ if __name__ == "__main__":
         run_sweep(a)
     elif a.workload == "sv":
         run_sv(a)
+    elif a.workload == "scaled":
+        run_scaled(a)
     else:
         run_b200(a)

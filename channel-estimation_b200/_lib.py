@@ -58,6 +58,8 @@ SIGNATURES = {
     "chest_demodulate": (c_int, [c_u64, c_int, vp, c_int, vp]),
     "chest_set_modem": (c_int, [c_u64, c_int, c_int, c_int, c_int, c_int, vp, c_int, c_int, c_int, c_int, vp, vp,
                                 C.c_double, C.c_double]),
+    "chest_transmission_matrix_batch": (c_int, [c_u64, c_int, c_int, p_f, p_d, vp]),
+    "chest_transmission_matrix_entries": (c_int, [c_u64, c_int, c_int, c_int, vp, vp, vp]),
     "chest_modulate_fft": (c_int, [c_u64, c_int, vp, c_int, vp]),
     "chest_demodulate_fft": (c_int, [c_u64, c_int, vp, c_int, vp]),
     "chest_set_interpolation": (c_int, [c_u64, c_int, vp]),

@@ -191,6 +191,20 @@ class DeviceContext:
         self._check(self.lib.chest_transmission_matrix(self._h, b, WF_ID[wf], _ptr(D), _ptr(h)))
         return D.T.copy(), h        # library writes column-major
 
+    def transmission_matrix_batch(self, wf, n_rep, h_out_ptr=None):
+        """D = Q' H_b G for realizations 0..n_rep-1 on the device (left there).  Returns (ms of k_apply_hg, ms of k_gemm_d,
+        support-aware flops per realization); h_out_ptr: host address receiving diag(D) (n_rep x K complex)."""
+        ms = (C.c_float * 2)()
+        fl = C.c_double(0)
+        self._check(self.lib.chest_transmission_matrix_batch(self._h, n_rep, WF_ID[wf], ms, C.byref(fl), C.c_void_p(h_out_ptr)))
+        return float(ms[0]), float(ms[1]), fl.value
+
+    def transmission_matrix_entries(self, wf, b, rows, cols):
+        rows = np.ascontiguousarray(rows, dtype=np.int32); cols = np.ascontiguousarray(cols, dtype=np.int32)
+        out = np.zeros(len(rows), dtype=np.complex128)
+        self._check(self.lib.chest_transmission_matrix_entries(self._h, b, WF_ID[wf], len(rows), rows.ctypes.data, cols.ctypes.data, _ptr(out)))
+        return out
+
     def modulate(self, wf, x):
         x2 = _c(np.atleast_2d(np.asarray(x).T) if np.ndim(x) == 1 else np.asarray(x).T)
         s = np.zeros((x2.shape[0], self.N), dtype=np.complex128)

@@ -1851,6 +1851,45 @@ int chest_transmission_matrix(uint64_t handle, int b, int wfi, double* D_out, do
     return CHEST_OK;
 }
 
+int chest_transmission_matrix_batch(uint64_t handle, int n_rep, int wfi, float* ms, double* flops_per_realization, double* h_out) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(n_rep >= 1 && n_rep <= c->cur_batch && (wfi == 0 || wfi == 1) && c->wf[wfi].set);
+    CK(cudaSetDevice(c->device));
+    const bool prof = c->profiling;
+    c->profiling = true;                                        // the stage records its own events (k_apply_hg / k_gemm_d)
+    if (n_rep == 1) CK(cudaEventRecord(c->ev_hg[2 * wfi], c->stream));
+    rc = stage_transmission_matrix(c, wfi, n_rep, 0);
+    if (n_rep == 1) { CK(cudaEventRecord(c->ev_hg[2 * wfi + 1], c->stream)); CK(cudaEventRecord(c->ev_gd[wfi], c->stream)); }
+    c->profiling = prof;
+    if (rc) return rc;
+    if (h_out) CK(cudaMemcpyAsync(h_out, c->wf[wfi].htrue.p, sizeof(cplx) * (size_t)n_rep * c->wf[wfi].K, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (ms) {
+        if (n_rep > 1) { CK(cudaEventElapsedTime(&ms[0], c->ev_hg[2 * wfi], c->ev_hg[2 * wfi + 1])); CK(cudaEventElapsedTime(&ms[1], c->ev_hg[2 * wfi + 1], c->ev_gd[wfi])); }
+        else { CK(cudaEventElapsedTime(&ms[1], c->ev_hg[2 * wfi], c->ev_gd[wfi])); ms[0] = 0; }
+    }
+    if (flops_per_realization) *flops_per_realization = c->wf[wfi].flops_d;
+    return CHEST_OK;
+}
+
+int chest_transmission_matrix_entries(uint64_t handle, int b, int wfi, int n, const int32_t* rows, const int32_t* cols, double* out) {
+    Ctx* c = from(handle);
+    int rc = check_ready(c); if (rc) return rc;
+    ARG(b >= 0 && b < c->cur_batch && (wfi == 0 || wfi == 1) && c->wf[wfi].set && n >= 0 && rows && cols && out);
+    Waveform& w = c->wf[wfi];
+    if (!w.D.p) return fail(CHEST_ERR_STATE, "no transmission matrix on the device: call chest_transmission_matrix_batch first");
+    CK(cudaSetDevice(c->device));
+    const size_t K = w.K, RT8 = ((K + 7) / 8) * 8;
+    for (int e = 0; e < n; ++e) {
+        ARG(rows[e] >= 0 && rows[e] < (int)K && cols[e] >= 0 && cols[e] < (int)K);
+        const size_t i = rows[e], j = cols[e];
+        CK(cudaMemcpyAsync(out + 2 * e, w.D.p + (size_t)b * RT8 * K + ((i >> 3) * K + j) * 8 + (i & 7), sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return CHEST_OK;
+}
+
 static int plain_gemm(Ctx* c, int wfi, bool demod, const double* in, int n_cols, double* out) {
     Waveform& w = c->wf[wfi];
     const int N = c->N, K = w.K;

@@ -156,6 +156,16 @@ int chest_convolve(uint64_t handle, int b, const double* s, int n_cols, double* 
 /* D = Q'*H_b*G and h = diag(D) (DS.m:388-393) of realization b; D_out K x K, h_out K (may be NULL). */
 int chest_transmission_matrix(uint64_t handle, int b, int waveform, double* D_out, double* h_out);
 
+/* The same product for realizations 0 .. n_rep-1 of the current channel batch in one go, D left on the device (row-tile-major;
+ * the structural zeros are never touched): the "chunked D GEMM" of the scaled-bandwidth workloads, where one D is 1.3 GB
+ * (K = 9000).  ms (may be NULL): device time of the banded apply H*G (k_apply_hg) and of the GEMM (k_gemm_d);
+ * flops_per_realization (may be NULL): support-aware algorithmic flops; h_out (may be NULL): diag(D) of the
+ * n_rep realizations, n_rep x K complex (host pointer; DS.m:391-393).  chest_transmission_matrix_entries
+ * reads n entries D[rows[e], cols[e]] of realization b back (complex interleaved) without moving the whole matrix. */
+int chest_transmission_matrix_batch(uint64_t handle, int n_rep, int waveform, float* ms /* [2] */, double* flops_per_realization,
+                                    double* h_out);
+int chest_transmission_matrix_entries(uint64_t handle, int b, int waveform, int n, const int32_t* rows, const int32_t* cols, double* out);
+
 /* s = G*x (Modulation, FBMC.m:319-320 / OFDM.m:185-186) and y = Q'*r (Demodulation,
  * FBMC.m:344-345 / OFDM.m:206-207) in their matrix form for n_cols columns. */
 int chest_modulate(uint64_t handle, int waveform, const double* x, int n_cols, double* s);
