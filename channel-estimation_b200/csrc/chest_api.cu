@@ -190,6 +190,7 @@ struct Ctx {
     bool pending = false; size_t pending_n_err = 0; bool trace_on = false; int pending_iter = 0, pending_rep = 0;
     DevBuf<unsigned long long> totals;    // [snr][it][12] sums over realizations (chest_multi_run)
     DevBuf<cplx> sv_h, sv_noise; DevBuf<double> sv_pn; DevBuf<uint32_t> sv_err;   // chest_sv_run_batch
+    DevBuf<cplx> setup_rinv; DevBuf<int> setup_mask, setup_trt;   // chest_build_mmse scratch, kept across calls (a velocity sweep rebuilds W per velocity)
 };
 
 Ctx* from(uint64_t h) { return reinterpret_cast<Ctx*>(static_cast<uintptr_t>(h)); }
@@ -1428,6 +1429,7 @@ int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_
         tptr[rt + 1] = (int)tdel.size();
     }
     m.n_tiles = (int)tdel.size();
+    m.tc_packed = false;                                       // the split-BF16 operand images follow W
     CK(m.tile_ptr.upload(tptr, c->stream));
     CK(m.tile_delta.upload(tdel.empty() ? std::vector<int>(1, 0) : tdel, c->stream));
     m.frag.clear(); m.diag.clear();
@@ -1542,7 +1544,7 @@ int chest_build_mmse(uint64_t handle, int si, int variant, int n_snr, const doub
     const int K = s.K, P = s.P, P4 = (P + 3) / 4, RT = (K + 7) / 8, ND = 2 * K - 1;
     const size_t n_e = (size_t)RT * 8 * K;
     cudaStream_t st = c->stream;
-    DevBuf<cplx> rinv; DevBuf<int> mask;
+    DevBuf<cplx>& rinv = c->setup_rinv; DevBuf<int>& mask = c->setup_mask;
     CK(rinv.upload(reinterpret_cast<const cplx*>(R_inv), (size_t)n_snr * P * P, st));
     CK(mask.alloc(n_e)); CK(cudaMemsetAsync(mask.p, 0, n_e * sizeof(int), st));
     dim3 g1((unsigned)((n_e * P + 255) / 256), n_snr);
@@ -1569,16 +1571,20 @@ int chest_build_mmse(uint64_t handle, int si, int variant, int n_snr, const doub
     }
     m.n_tiles = (int)tdel.size(); m.nnz_offdiag_pairs = pairs;
     if (tdel.empty()) { tdel.push_back(0); trt.push_back(0); }
-    DevBuf<int> d_trt;
+    DevBuf<int>& d_trt = c->setup_trt;
     CK(m.tile_ptr.upload(tptr, st)); CK(m.tile_delta.upload(tdel, st)); CK(d_trt.upload(trt, st));
-    m.frag.clear(); m.diag.clear(); m.frag.resize(n_snr); m.diag.resize(n_snr);
+    // buffers are kept across rebuilds (cudaMalloc / cudaFree of ~100 buffers cost more than the kernels of a rebuild);
+    // a little headroom absorbs the small changes of the tile count from one velocity to the next
+    if ((int)m.frag.size() != n_snr) { m.frag.clear(); m.diag.clear(); m.frag.resize(n_snr); m.diag.resize(n_snr); }
+    m.tc_packed = false;                                       // the split-BF16 operand images follow W
     std::vector<WTiles> table(n_snr);
     const size_t n_frag = (size_t)std::max(m.n_tiles, 1) * P4 * 32, n_dfrag = (size_t)RT * P4 * 32;
     CK(m.diag_frag.alloc((size_t)n_snr * n_dfrag));
     CK(cudaMemsetAsync(m.diag_frag.p, 0, sizeof(cplx) * n_snr * n_dfrag, st));
     const int64_t n_thr = ((int64_t)m.n_tiles + RT) * 8 * P;
     for (int snr = 0; snr < n_snr; ++snr) {
-        CK(m.frag[snr].alloc(n_frag)); CK(m.diag[snr].alloc((size_t)K * P));
+        if (m.frag[snr].n < n_frag) CK(m.frag[snr].alloc(n_frag + n_frag / 8));
+        CK(m.diag[snr].alloc((size_t)K * P));
         CK(cudaMemsetAsync(m.frag[snr].p, 0, sizeof(cplx) * n_frag, st));
         CK(cudaMemsetAsync(m.diag[snr].p, 0, sizeof(cplx) * K * P, st));
         k_w_fill<<<(unsigned)((n_thr + 255) / 256), 256, 0, st>>>(m.frag[snr].p, m.diag[snr].p, m.diag_frag.p + (size_t)snr * n_dfrag,
