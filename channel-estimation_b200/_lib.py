@@ -79,6 +79,8 @@ SIGNATURES = {
     "chest_get_state": (c_int, [c_u64, c_int, c_int, c_int, c_int, vp]),
     "chest_kernel_times": (c_int, [c_u64, vp]),
     "chest_set_perfect_csi_mode": (c_int, [c_u64, c_int]),
+    "chest_set_mse_accumulation": (c_int, [c_u64, c_int]),
+    "chest_get_mse": (c_int, [c_u64, vp]),
     "chest_set_precision": (c_int, [c_u64, c_int]),
     "chest_precision_info": (c_int, [c_u64, C.POINTER(c_int), p_d, p_i64]),
     "chest_unit_count": (c_int, [c_u64, C.POINTER(c_int)]),

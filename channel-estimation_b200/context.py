@@ -420,6 +420,16 @@ class DeviceContext:
         """'factored' (default): D never formed; 'dense': D = Q^H H G materialised per realization (K2)."""
         self._check(self.lib.chest_set_perfect_csi_mode(self._h, {"dense": 0, "factored": 1}[mode]))
 
+    def set_mse_accumulation(self, on=True):
+        """Also accumulate sum_i |h_est(i) - h(i)|^2 per (realization, SNR, iteration, scheme) in the next runs."""
+        self._check(self.lib.chest_set_mse_accumulation(self._h, int(on)))
+
+    def get_mse(self, n_rep, n_iter):
+        """[rep, snr, it, scheme] sums of the last run_batch (scheme order aux, cod, ofdm)."""
+        out = np.zeros((n_rep, self.n_snr, n_iter + 1, 3), dtype=np.float64)
+        self._check(self.lib.chest_get_mse(self._h, out.ctypes.data))
+        return out
+
     def set_precision(self, mode):
         """'fp64' (default): FP64 DMMA everywhere; 'split_bf16': the estimated-CSI cancellation on tcgen05 tensor cores with
         split-BF16 operands and FP32 accumulation in TMEM (the stated reduced-precision mode, ~1e-5 of the interference)."""

@@ -190,6 +190,7 @@ struct Ctx {
     bool pending = false; size_t pending_n_err = 0; bool trace_on = false; int pending_iter = 0, pending_rep = 0;
     DevBuf<unsigned long long> totals;    // [snr][it][12] sums over realizations (chest_multi_run)
     DevBuf<cplx> sv_h, sv_noise; DevBuf<double> sv_pn; DevBuf<uint32_t> sv_err;   // chest_sv_run_batch
+    bool mse_on = false; DevBuf<double> mse;                      // chest_set_mse_accumulation: [rep][snr][it][scheme]
     DevBuf<cplx> setup_rinv; DevBuf<int> setup_mask, setup_trt;   // chest_build_mmse scratch, kept across calls (a velocity sweep rebuilds W per velocity)
 };
 
@@ -866,6 +867,14 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     uint32_t* err = err_dev ? err_dev : c->err.p;
     CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
     ip.err = err;
+    ip.mse = nullptr;
+    if (c->mse_on) {
+        if (use_post) return fail(CHEST_ERR_STATE, "MSE accumulation is implemented in k_ic_light (unset CHEST_LIGHT=post)");
+        const size_t n_mse = (size_t)n_rep * S * (n_iter + 1) * 3;
+        CK(c->mse.alloc(n_mse));
+        CK(cudaMemsetAsync(c->mse.p, 0, n_mse * sizeof(double), st));
+        ip.mse = c->mse.p;
+    }
     const char* trace_path = getenv("CHEST_IC_TRACE");             // development: per-CTA timestamps of the last main launch
     if (trace_path) { CK(c->trace.alloc((size_t)c->ic_grid * 8)); CK(cudaMemsetAsync(c->trace.p, 0, (size_t)c->ic_grid * 64, st)); }
     const int n_units = std::max(c->n_ctas, 1);
@@ -2513,6 +2522,23 @@ int chest_set_perfect_csi_mode(uint64_t handle, int mode) {
     ARG(c && (mode == 0 || mode == 1));
     c->perf_mode = mode;
     c->ctas_for_batch = -1;                                    // unit order and column tables depend on the mode
+    return CHEST_OK;
+}
+
+int chest_set_mse_accumulation(uint64_t handle, int enable) {
+    Ctx* c = from(handle);
+    ARG(c);
+    c->mse_on = enable != 0;
+    return CHEST_OK;
+}
+
+int chest_get_mse(uint64_t handle, double* out) {
+    Ctx* c = from(handle);
+    ARG(c && out);
+    if (!c->mse_on || !c->mse.p) return fail(CHEST_ERR_STATE, "no MSE sums: enable chest_set_mse_accumulation before the run");
+    if (c->pending) return fail(CHEST_ERR_STATE, "an asynchronous run is pending on this context: call chest_wait first");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(out, c->mse.p, sizeof(double) * (size_t)c->cur_batch * c->S * (c->last_iter + 1) * 3, cudaMemcpyDeviceToHost));
     return CHEST_OK;
 }
 

@@ -1043,6 +1043,7 @@ struct IcParams {
     int n_units;
     int n_units_main;          // units k_ic_main processes (all of them, or only the EST units in factored mode)
     unsigned long long* trace; // development: per CTA {smid, t0, t_pre, t_main_own, t_main_all, t_end, B busy ns, units}
+    double* mse;               // optional: sum_i |h_est[i] - h[i]|^2 per [rep][snr][it][scheme] (estimated-CSI columns); nullptr = off
 };
 
 // Column -> (scheme, SNR point, realization); false for an unused slot.  PERF units keep each 8-column half
@@ -1458,6 +1459,7 @@ struct IcShared {
     const cplx* ycolp[NC_MAX];
     ConstDev cst[2];
     int unit;
+    double mse[NC_MAX];
 };
 
 __device__ __forceinline__ void ic_load_unit(const IcParams& p, const IcCta& cta, IcShared& sh) {
@@ -1469,6 +1471,7 @@ __device__ __forceinline__ void ic_load_unit(const IcParams& p, const IcCta& cta
         sh.c_scheme[tid] = s_; sh.c_snr[tid] = n_; sh.c_rep[tid] = ok ? r_ : -1;
         sh.ycolp[tid] = ok ? p.sch[s_].y + ((int64_t)n_ * p.n_rep + r_) * p.sch[s_].K : nullptr;
         sh.cnt[tid][0] = sh.cnt[tid][1] = 0;
+        sh.mse[tid] = 0.0;
     }
     __syncthreads();
 }
@@ -1643,6 +1646,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 const bool select = sd.detect_mode != 1;
                 const cplx* __restrict__ wf_ = sd.wdiag_frag[var_cur] + (int64_t)cta.snr * RT * P4 * 32;
                 unsigned e_all[2][2] = {{0, 0}, {0, 0}}, e_edge[2][2] = {{0, 0}, {0, 0}};
+                double dm[2][2] = {{0, 0}, {0, 0}};                // channel-estimation error of this lane's columns (p.mse)
                 for (int rt = warp; rt < RT; rt += nwarp) {
                     double hr[2][2] = {{0, 0}, {0, 0}}, hi[2][2] = {{0, 0}, {0, 0}};
                     const int i = rt * 8 + g;
@@ -1675,6 +1679,10 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                                 const int64_t col = (int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c];
                                 const cplx hh = cmake(hr[ct][e], hi[ct][e]);
                                 if (last) sd.hdiag[col * K + i] = hh;
+                                if (p.mse) {
+                                    const cplx ht = p.htrue[wf][(int64_t)sh.c_rep[c] * K + i];
+                                    dm[ct][e] += (hh.x - ht.x) * (hh.x - ht.x) + (hh.y - ht.y) * (hh.y - ht.y);
+                                }
                                 const cplx xh = cdiv_fast(yv[ct][e], hh);
                                 if (!select) { vbuf[i * NC + c] = xh; continue; }
                                 if (d < 0) continue;
@@ -1684,6 +1692,17 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                                 if (next_pre) zw[d * NC + c] = (uint8_t)word;
                             }
                     }
+                }
+                if (p.mse) {
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            double a = dm[ct][e];
+#pragma unroll
+                            for (int o = 4; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                            if (g == 0) atomicAdd(&sh.mse[ct * 8 + 2 * t4 + e], a);
+                        }
                 }
                 if (select) {                                  // lanes with the same t4 hold the same four columns
 #pragma unroll
@@ -1797,6 +1816,8 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 p.err[o] = sh.cnt[cc][e];
             }
         }
+        if (p.mse && csi == 0 && tid < cta.n_cols && sh.c_rep[tid] >= 0)
+            p.mse[(((int64_t)sh.c_rep[tid] * p.n_snr + sh.c_snr[tid]) * (p.n_iter + 1) + it) * 3 + sh.c_scheme[tid]] = sh.mse[tid];
         if (!next_pre) continue;
         // ---- phase A of iteration it+1: v = C z with z = [xP; decided symbols]   (DS.m:482-484, 541-543)
         {   // rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread

@@ -265,6 +265,13 @@ int chest_set_perfect_csi_mode(uint64_t handle, int mode);
 #define CHEST_PRECISION_SPLIT_BF16  1
 int chest_set_precision(uint64_t handle, int mode);
 int chest_precision_info(uint64_t handle, int* mode, double* mma_flops_per_launch, int64_t* operand_bytes);
+/* Channel-estimation error sums next to the bit-error counters (north_star: "BER/MSE counters"; the reference itself keeps
+ * no MSE): with accumulation enabled every chest_run_batch* also leaves sum_i |h_est(i) - h(i)|^2 over the K positions of
+ * a scheme's grid -- h_est = diag(D_est) of DS.m:428/517, h = diag(Q'HG) of DS.m:392-393 -- for every realization, SNR
+ * point and iteration (0 = the one-tap stage).  chest_get_mse: out[rep][snr][it][scheme], n_rep x n_snr x (n_iter+1) x 3
+ * doubles of the last batch; divide by K for the mean.  Off by default (one extra load per estimated value). */
+int chest_set_mse_accumulation(uint64_t handle, int enable);
+int chest_get_mse(uint64_t handle, double* out);
 /* Work units (up to 16 columns x all K rows each) the IC kernels processed in the last batch. */
 int chest_unit_count(uint64_t handle, int* n_units);
 

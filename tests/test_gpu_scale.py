@@ -497,3 +497,33 @@ def test_simple_version_chain_on_device():
     _, raw2 = sim2.run(NrRepetitions=40)
     assert np.array_equal(raw2, raw[:40 * 7])
     sim.close(); sim2.close()
+
+
+def test_mse_sums_match_oracle(ds_default):
+    """north_star "BER/MSE counters": sum_i |h_est(i) - h(i)|^2 per (realization, SNR, iteration, scheme) accumulated by the
+    loop body (chest_set_mse_accumulation) against the oracle's h_est = diag(D_est) (DS.m:428,517) and h = diag(Q'HG)
+    (DS.m:392-393) of the same seeded realizations; the bit-error counters are unchanged by the extra accumulation."""
+    from oracle import rng
+    from oracle.ds import ds_realization
+    from tests.helpers import context_from_oracle
+    S = ds_default
+    B, seed, first, n_iter = 19, 8, 300, 4
+    ctx = context_from_oracle(S, max_batch=B)
+    base = ctx.run_batch(B, n_iter, None, seed=seed, first_rep=first)
+    ctx.set_mse_accumulation(True)
+    err = ctx.run_batch(B, n_iter, None, seed=seed, first_rep=first)
+    assert np.array_equal(err, base)
+    mse = ctx.get_mse(B, n_iter)
+    assert np.all(mse > 0)
+    for r in (0, 16, 18):
+        out = ds_realization(S, rng.draws_for(S, seed, first + r), keep=True)["inter"]
+        for sid, sc in enumerate(("aux", "cod", "ofdm")):
+            h = np.diag(out["D_" + S["schemes"][sc]["waveform"]])
+            for isnr in range(ctx.n_snr):
+                for it in range(n_iter + 1):
+                    ref = float(np.sum(np.abs(out["hdiag_" + sc][isnr][it] - h) ** 2))
+                    assert abs(mse[r, isnr, it, sid] - ref) < 1e-9 * ref, (r, sc, isnr, it, mse[r, isnr, it, sid], ref)
+    # iterations improve the estimate at high SNR (BASELINE.md: the point of the interference cancellation)
+    assert mse[:, -1, n_iter, :].mean() < mse[:, -1, 0, :].mean()
+    ctx.set_mse_accumulation(False)
+    ctx.close()
