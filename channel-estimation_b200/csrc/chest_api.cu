@@ -66,6 +66,8 @@ struct Waveform {
     DevBuf<cplx> G, Q, Gt;
     DevBuf<cplx> Q1; DevBuf<double> Q2;                // three-multiplication planes of Q^H: (re, re - im), im; row stride Np
     DevBuf<cplx> Gt1; DevBuf<double> Gt2;              // planes of G (not conjugated), rows = samples: (re, re + im), -im; row stride Kp
+    int pf_state = 0;                                  // polyphase perfect-CSI pass: 0 unchecked, 1 usable, -1 not (no modem description, mismatch, too large)
+    DevBuf<int2> pf_groups; int pf_n_groups = 0;
     DevBuf<cplx> f_r1; DevBuf<double> f_r2;            // planes of r = H s of the factored perfect-CSI pass: (re, re + im), im - re; [column][Np]
     DevBuf<cplx> HG1; DevBuf<double> HG2;              // H*G planes: (re, re + im), im - re; [rep][K][Np]
     DevBuf<int> q_klo, q_khi, gt_klo, gt_khi, hg_klo, hg_khi, d_jlo, d_jhi;
@@ -394,6 +396,82 @@ int stage_transmission_matrix(Ctx* c, int wfi, int n_rep, int rep0) {
 // Perfect-CSI cancellation without D: y_ic = y - Q^H (H (G v)) + h v for every (realization, scheme, SNR) column
 // (DS.m:541-543 with D = Q^H H G, h = diag D).  Two support-aware GEMMs over all columns of the batch with the banded
 // channel between them; the second GEMM's epilogue writes y_ic into the units' scratch.
+// device-resident core: x_dev [n_cols][L*K] -> s_dev [n_cols][N]
+int modem_modulate_dev(Ctx* c, Waveform& w, const cplx* x_dev, int n_cols, cplx* s_dev) {
+    const ModemDev& md = w.modem;
+    const size_t smem = (size_t)3 * md.nfft * sizeof(cplx);
+    const int thr = std::min(256, std::max(32, ((md.nfft / 2 + 31) / 32) * 32));
+    dim3 g(md.Ksym, n_cols);
+    if (md.kind == 0) {
+        CK(w.m_Z.alloc((size_t)n_cols * md.Ksym * md.nfft));
+        k_modem_ifft<<<g, thr, smem, c->stream>>>(md, x_dev, w.m_Z.p, nullptr);
+        dim3 g2(n_cols, (md.N + 255) / 256);
+        k_fbmc_overlap_add<<<g2, 256, 0, c->stream>>>(md, w.m_Z.p, s_dev);
+        c->launches += 2;
+    } else {
+        CK(cudaMemsetAsync(s_dev, 0, sizeof(cplx) * (size_t)n_cols * md.N, c->stream));     // zero guard samples
+        k_modem_ifft<<<g, thr, smem, c->stream>>>(md, x_dev, nullptr, s_dev);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return CHEST_OK;
+}
+int modem_demodulate_dev(Ctx* c, Waveform& w, const cplx* r_dev, int n_cols, cplx* y_dev) {
+    const ModemDev& md = w.modem;
+    const size_t smem = (size_t)3 * md.nfft * sizeof(cplx);
+    const int thr = std::min(256, std::max(32, ((md.nfft / 2 + 31) / 32) * 32));
+    dim3 g(md.Ksym, n_cols);
+    k_modem_fft<<<g, thr, smem, c->stream>>>(md, r_dev, y_dev);
+    c->launches++;
+    CK(cudaGetLastError());
+    return CHEST_OK;
+}
+
+#define PERF_FBMC_CW 4
+// Can the perfect-CSI pass of this waveform run through the polyphase modem (k_perfect_fbmc)?  Needs an FBMC description
+// from chest_set_modem next to the dense matrices, shared-memory room for CW columns, and -- since the two descriptions come
+// from the caller independently -- the modem must reproduce G and Q^H on probe vectors.
+int check_polyphase_pass(Ctx* c, Waveform& w) {
+    if (w.pf_state) return CHEST_OK;
+    w.pf_state = -1;
+    if (getenv("CHEST_CHAIN_GEMM")) return CHEST_OK;            // development: force the GEMM chain
+    const ModemDev& md = w.modem;
+    const int N = c->N, K = w.K;
+    if (!w.modem_set || !w.set || md.kind != 0 || md.L * md.Ksym != K || md.N != N || md.time_spacing * 2 != md.nfft) return CHEST_OK;
+    const size_t nx = (size_t)md.Ksym * md.nfft;
+    if ((size_t)N > nx) return CHEST_OK;
+    const size_t smem = ((size_t)2 * PERF_FBMC_CW * nx + (size_t)PERF_FBMC_CW * N + md.nfft) * sizeof(cplx);
+    if (smem > 200 * 1024) return CHEST_OK;
+    // probes: three unit symbol vectors through the modulator against the columns of G, three unit samples through the
+    // demodulator against the rows of Q^H
+    const int cols[3] = {0, K / 2 + 1 < K ? K / 2 + 1 : 0, K - 1}, rows[3] = {w.q_lo[K / 2], (w.q_lo[K / 2] + w.q_hi[K / 2]) / 2, std::max(0, w.q_hi[K - 1] - 1)};
+    std::vector<cplx> x((size_t)3 * K, cmake(0.0, 0.0)), e((size_t)3 * N, cmake(0.0, 0.0)), s_h((size_t)3 * N), y_h((size_t)3 * K);
+    for (int q = 0; q < 3; ++q) { x[(size_t)q * K + cols[q]] = cmake(1.0, 0.0); e[(size_t)q * N + rows[q]] = cmake(1.0, 0.0); }
+    DevBuf<cplx> dx, de, ds, dy;
+    CK(dx.upload(x, c->stream)); CK(de.upload(e, c->stream)); CK(ds.alloc((size_t)3 * N)); CK(dy.alloc((size_t)3 * K));
+    int rc = modem_modulate_dev(c, w, dx.p, 3, ds.p); if (rc) return rc;
+    rc = modem_demodulate_dev(c, w, de.p, 3, dy.p); if (rc) return rc;
+    CK(cudaMemcpyAsync(s_h.data(), ds.p, sizeof(cplx) * s_h.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(y_h.data(), dy.p, sizeof(cplx) * y_h.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double dev = 0, mag = 0;
+    for (int q = 0; q < 3; ++q) {
+        for (int n = 0; n < N; ++n) {
+            const cplx g = w.Gh[(size_t)n + (size_t)N * cols[q]], m = s_h[(size_t)q * N + n];
+            dev = std::max(dev, std::hypot(g.x - m.x, g.y - m.y)); mag = std::max(mag, std::hypot(g.x, g.y));
+        }
+        for (int i = 0; i < K; ++i) {                           // (Q^H e_n)[i] = conj(Q[n, i])
+            const cplx qv = w.Qh[(size_t)rows[q] + (size_t)N * i], m = y_h[(size_t)q * K + i];
+            dev = std::max(dev, std::hypot(qv.x - m.x, -qv.y - m.y)); mag = std::max(mag, std::hypot(qv.x, qv.y));
+        }
+    }
+    if (dev <= 1e-12 * mag) {
+        w.pf_state = 1;
+        CK(cudaFuncSetAttribute(k_perfect_fbmc<PERF_FBMC_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    return CHEST_OK;
+}
+
 template <int WM, int WN, int TMW, bool BG, int EPI>
 cudaError_t launch_gemm_ring_geo(Ctx* c, GemmRingParams& p) {
     constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
@@ -428,13 +506,26 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep) {
     for (int wfi = 0; wfi < 2; ++wfi) {
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch || !w.f_cols) continue;
+        if (!legacy && w.pf_state == 1 && w.pf_n_groups > 0) {                             // FBMC: the polyphase modem instead of the GEMMs
+            const ModemDev& md = w.modem;
+            PerfFbmcParams pp{};
+            pp.md = md; pp.n_groups = w.pf_n_groups; pp.T = c->T; pp.N = N; pp.K = w.K; pp.groups = w.pf_groups.p;
+            pp.voff = w.f_voff.p; pp.yoff = w.f_yoff.p; pp.rep = w.f_rep.p;
+            pp.v_base = c->scratch.p; pp.y_base = c->scratch.p + (size_t)c->K_max * NC_MAX;
+            pp.y = w.y.p; pp.htrue = w.htrue.p; pp.h = c->h.p; pp.tap_delay = c->d_tap_delay.p;
+            const size_t smem = ((size_t)2 * PERF_FBMC_CW * md.Ksym * md.nfft + (size_t)PERF_FBMC_CW * N + md.nfft) * sizeof(cplx);
+            k_perfect_fbmc<PERF_FBMC_CW><<<w.pf_n_groups, PERF_FBMC_THREADS, smem, c->stream>>>(pp);
+            c->launches++;
+            CK(cudaGetLastError());
+            continue;
+        }
         if (!legacy) {
             GemmRingParams p{};                                                             // s = G v
             p.M = N; p.n_cols = w.f_cols; p.lda = (w.K + 1) & ~1; p.ldc = N;
             p.At1 = w.Gt1.p; p.At2 = w.Gt2.p; p.mt_klo = w.gt_klo.p; p.mt_khi = w.gt_khi.p; p.m8_klo = w.gt8_klo.p; p.m8_khi = w.gt8_khi.p;
             p.bsrc = c->scratch.p; p.b_off = w.f_voff.p; p.b_kstride = NC_MAX; p.out = w.f_s.p;
             CK((launch_gemm_ring<true, 0>(c, p, w.tile)));
-            dim3 grid((N + 127) / 128, w.f_cols);                                           // r = H s, written as operand planes
+            dim3 grid(w.f_cols, (N + 127) / 128);                                           // r = H s, written as operand planes
             k_apply_h_cols_planes<<<grid, 128, 0, c->stream>>>(w.f_r1.p, w.f_r2.p, w.f_s.p, c->h.p, c->d_tap_delay.p, w.f_rep.p, N, Np, c->T);
             c->launches++;
             CK(cudaGetLastError());
@@ -453,7 +544,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep) {
         p.m8_klo = w.gt8_klo.p; p.m8_khi = w.gt8_khi.p;
         p.bsrc = c->scratch.p; p.b_off = w.f_voff.p; p.b_kstride = NC_MAX;
         CK(launch_gemm<GEMM_PLAIN>(c, p, 1, w.tile));                                   // s = G v
-        dim3 grid((N + 127) / 128, w.f_cols);
+        dim3 grid(w.f_cols, (N + 127) / 128);
         k_apply_h_cols<<<grid, 128, 0, c->stream>>>(w.f_r.p, w.f_s.p, c->h.p, c->d_tap_delay.p, w.f_rep.p, N, c->T);   // r = H s
         c->launches++;
         CK(cudaGetLastError());
@@ -638,6 +729,18 @@ int build_ctas(Ctx* c, int n_rep) {
                         rep[col] = r;
                     }
             CK(w.f_voff.upload(voff, c->stream)); CK(w.f_yoff.upload(yoff, c->stream)); CK(w.f_rep.upload(rep, c->stream));
+            {   // column groups of the polyphase pass: up to CW columns that are neighbours in one unit's scratch
+                int rc = check_polyphase_pass(c, w); if (rc) return rc;
+                std::vector<int2> groups;
+                if (w.pf_state == 1)
+                    for (int r = 0; r < n_rep; ++r)
+                        for (int slot = 0; slot < w.nsch; ++slot)
+                            for (int s0 = 0; s0 < S; s0 += 8)
+                                for (int q = s0; q < std::min(S, s0 + 8); q += PERF_FBMC_CW)
+                                    groups.push_back(make_int2(r * nv + slot * S + q, std::min(PERF_FBMC_CW, std::min(S, s0 + 8) - q)));
+                w.pf_n_groups = (int)groups.size();
+                if (!groups.empty()) CK(w.pf_groups.upload(groups, c->stream));
+            }
             CK(w.f_s.alloc((size_t)w.f_cols * c->N)); CK(w.f_r.alloc((size_t)w.f_cols * c->N));
             {
                 const size_t Np = (size_t)((c->N + 1) & ~1);
@@ -1196,7 +1299,7 @@ int chest_set_waveform(uint64_t handle, int wfi, int n_samples, int K, const dou
     tile_ranges(rlo, rhi, 8, 0, K, lo, hi);
     CK(w.gt8_klo.upload(lo, c->stream)); CK(w.gt8_khi.upload(hi, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    w.set = true; c->finalized = false;
+    w.set = true; c->finalized = false; w.pf_state = 0; c->ctas_for_batch = -1;
     return CHEST_OK;
 }
 
@@ -1977,38 +2080,7 @@ int chest_set_modem(uint64_t handle, int wfi, int kind, int L, int Ksym, int nff
     CK(cudaFuncSetAttribute(k_modem_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ARG(smem <= 200 * 1024);
     if (!w.set) { w.K = L * Ksym; c->N = md.N; c->finalized = false; }       // modem-only waveform (no dense G / Q)
-    w.modem_set = true;
-    return CHEST_OK;
-}
-
-// device-resident core: x_dev [n_cols][L*K] -> s_dev [n_cols][N]
-static int modem_modulate_dev(Ctx* c, Waveform& w, const cplx* x_dev, int n_cols, cplx* s_dev) {
-    const ModemDev& md = w.modem;
-    const size_t smem = (size_t)3 * md.nfft * sizeof(cplx);
-    const int thr = std::min(256, std::max(32, ((md.nfft / 2 + 31) / 32) * 32));
-    dim3 g(md.Ksym, n_cols);
-    if (md.kind == 0) {
-        CK(w.m_Z.alloc((size_t)n_cols * md.Ksym * md.nfft));
-        k_modem_ifft<<<g, thr, smem, c->stream>>>(md, x_dev, w.m_Z.p, nullptr);
-        dim3 g2((md.N + 255) / 256, n_cols);
-        k_fbmc_overlap_add<<<g2, 256, 0, c->stream>>>(md, w.m_Z.p, s_dev);
-        c->launches += 2;
-    } else {
-        CK(cudaMemsetAsync(s_dev, 0, sizeof(cplx) * (size_t)n_cols * md.N, c->stream));     // zero guard samples
-        k_modem_ifft<<<g, thr, smem, c->stream>>>(md, x_dev, nullptr, s_dev);
-        c->launches++;
-    }
-    CK(cudaGetLastError());
-    return CHEST_OK;
-}
-static int modem_demodulate_dev(Ctx* c, Waveform& w, const cplx* r_dev, int n_cols, cplx* y_dev) {
-    const ModemDev& md = w.modem;
-    const size_t smem = (size_t)3 * md.nfft * sizeof(cplx);
-    const int thr = std::min(256, std::max(32, ((md.nfft / 2 + 31) / 32) * 32));
-    dim3 g(md.Ksym, n_cols);
-    k_modem_fft<<<g, thr, smem, c->stream>>>(md, r_dev, y_dev);
-    c->launches++;
-    CK(cudaGetLastError());
+    w.modem_set = true; w.pf_state = 0; c->ctas_for_batch = -1;
     return CHEST_OK;
 }
 
@@ -2117,7 +2189,7 @@ int chest_sv_run_batch(uint64_t handle, int n_body, const double* pn_time, const
         if (!w.nsch) continue;
         const int n_cols = w.nsch * n_body;
         rc = modem_modulate_dev(c, w, w.x.p, n_cols, w.s.p); if (rc) return rc;                       // SV.m:118-120
-        dim3 g((N + 127) / 128, n_cols);
+        dim3 g(n_cols, (N + 127) / 128);
         k_sv_channel<<<g, 128, 0, st>>>(w.r0.p, w.s.p, c->sv_h.p, c->sv_noise.p, c->sv_pn.p, N, n_body, wfi);   // SV.m:123-131
         c->launches++;
         CK(cudaGetLastError());

@@ -190,7 +190,7 @@ __global__ void k_apply_hg(cplx* __restrict__ HG1, double* __restrict__ HG2, con
 // r[col][n] = sum_tap h[rep_of_col[col]][tap][n] * s[col][n - delay_tap]: the banded H applied to a list of columns
 __global__ void k_apply_h_cols(cplx* __restrict__ r, const cplx* __restrict__ s, const cplx* __restrict__ h,
                                const int* __restrict__ tap_delay, const int* __restrict__ rep_of_col, int N, int T) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    const int n = blockIdx.y * blockDim.x + threadIdx.x, col = blockIdx.x;      // columns on grid.x: up to 2^31 - 1 of them
     if (n >= N) return;
     const int rep = rep_of_col[col];
     const cplx* sc = s + (int64_t)col * N;
@@ -205,7 +205,7 @@ __global__ void k_apply_h_cols(cplx* __restrict__ r, const cplx* __restrict__ s,
 // the same, r written as the three-multiplication operand planes of the next GEMM: r1 = (re, re + im), r2 = im - re; row stride Np
 __global__ void k_apply_h_cols_planes(cplx* __restrict__ r1, double* __restrict__ r2, const cplx* __restrict__ s, const cplx* __restrict__ h,
                                       const int* __restrict__ tap_delay, const int* __restrict__ rep_of_col, int N, int Np, int T) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    const int n = blockIdx.y * blockDim.x + threadIdx.x, col = blockIdx.x;      // columns on grid.x: up to 2^31 - 1 of them
     if (n >= N) return;
     const int rep = rep_of_col[col];
     const cplx* sc = s + (int64_t)col * N;
@@ -2250,6 +2250,9 @@ __global__ void __launch_bounds__(POST_THREADS, 2) k_ic_post(IcParams p) {
 // cuFFT), one thread block per (multicarrier symbol, column).  tw[m] = exp(-2 pi i m / n); the inverse transform
 // conjugates the table and scales by 1/n like MATLAB's ifft.
 #define FFT_MAX_STAGES 16
+#ifndef PERF_FBMC_THREADS
+#define PERF_FBMC_THREADS 512
+#endif
 struct FftPlan { int n, n_stage; int radix[FFT_MAX_STAGES]; };
 struct ModemDev {
     int kind;                    // 0: FBMC polyphase, 1: CP-OFDM
@@ -2337,7 +2340,7 @@ __global__ void k_modem_ifft(ModemDev md, const cplx* __restrict__ x, cplx* __re
 }
 // FBMC overlap-add as a gather: s[n] = sum_k p[n - k T] * Z[k][(n - k T) mod nfft], symbols ascending (FBMC.m:267-268)
 __global__ void k_fbmc_overlap_add(ModemDev md, const cplx* __restrict__ Z, cplx* __restrict__ s) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    const int n = blockIdx.y * blockDim.x + threadIdx.x, col = blockIdx.x;      // columns on grid.x: up to 2^31 - 1 of them
     if (n >= md.N) return;
     const int T = md.time_spacing;
     int k_lo = (n - md.Np + T) / T; if (n - md.Np + 1 <= 0) k_lo = 0;      // smallest k with n - kT <= Np - 1
@@ -2382,12 +2385,166 @@ __global__ void k_modem_fft(ModemDev md, const cplx* __restrict__ r, cplx* __res
 }
 
 
+// ============================================================================ perfect-CSI pass through the polyphase modem
+// y_ic = y - Q^H H G v + h v  (DS.m:541-543 with D = Q^H H G never formed) for FBMC columns, with G and Q^H applied in
+// their FACTORED form -- G v = Modulation(v) (FBMC.m:255-268: phase, IFFT per symbol, prototype filter, overlap-add) and
+// Q^H r = Demodulation(r) (FBMC.m:287-302: filter, fold by O, FFT, conj phase) -- instead of as support-aware GEMMs:
+// about 1/13 of the flops (per column 2 x (Ksym FFTs of size nfft + 2 O nfft Ksym real-complex multiply-adds) against
+// 2 x 8 Np L Ksym) and no G / Q operand traffic at all.  One CTA takes CW columns that sit side by side in one unit's
+// interleaved scratch (16 CW contiguous bytes per symbol row) and keeps the whole chain
+//     v -> Z = IFFT -> s (overlap-add) -> r = H s (banded, the realization's taps) -> fold -> FFT -> y_ic
+// in shared memory; every step is FP64 on the scalar pipe.  Used when chest_set_modem described the waveform next to its
+// dense matrices, the description reproduces G / Q (checked at finalize) and the buffers fit; otherwise k_gemm_ring.
+struct PerfFbmcParams {
+    ModemDev md;
+    int n_groups, T, N, K;
+    const int2* groups;            // (first column, number of columns <= CW): columns of one (realization, scheme slot, SNR block)
+    const int64_t* voff; const int64_t* yoff; const int* rep;
+    const cplx* v_base; cplx* y_base;              // unit scratch: v and, one buffer behind, y_ic
+    const cplx* y; const cplx* htrue; const cplx* h; const int* tap_delay;
+};
+template <int R>
+__device__ __forceinline__ void fft_bfly(const cplx* __restrict__ a, cplx* __restrict__ b, const cplx* __restrict__ tw,
+                                         int n, int Ns, int j, int m, int step, bool inv) {
+    const int k = j % Ns;
+    cplx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+        cplx w = tw[t * k * step];                              // t k step < n: no reduction needed
+        if (inv) w.y = -w.y;
+        v[t] = cmul(a[j + t * m], w);
+    }
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        cplx acc = v[0];
+#pragma unroll
+        for (int t = 1; t < R; ++t) {
+            cplx w = tw[((t * u) % R) * (n / R)];
+            if (inv) w.y = -w.y;
+            cfma(acc, v[t], w);
+        }
+        b[j0 + u * Ns] = acc;
+    }
+}
+// n_batch independent transforms of size plan.n stored back to back in `a` (scratch `b`, same size); returns the result buffer
+__device__ cplx* fft_shared_batch(cplx* a, cplx* b, const cplx* tw, const FftPlan& plan, bool inv, int n_batch) {
+    const int n = plan.n;
+    int Ns = 1;
+    for (int s = 0; s < plan.n_stage; ++s) {
+        const int R = plan.radix[s], m = n / R, step = n / (Ns * R);
+        for (int idx = threadIdx.x; idx < n_batch * m; idx += blockDim.x) {
+            const int f = idx / m, j = idx - f * m;
+            const cplx* af = a + f * n; cplx* bf = b + f * n;
+            switch (R) {
+                case 2: fft_bfly<2>(af, bf, tw, n, Ns, j, m, step, inv); break;
+                case 3: fft_bfly<3>(af, bf, tw, n, Ns, j, m, step, inv); break;
+                case 4: fft_bfly<4>(af, bf, tw, n, Ns, j, m, step, inv); break;
+                case 5: fft_bfly<5>(af, bf, tw, n, Ns, j, m, step, inv); break;
+                case 7: fft_bfly<7>(af, bf, tw, n, Ns, j, m, step, inv); break;
+                case 11: fft_bfly<11>(af, bf, tw, n, Ns, j, m, step, inv); break;
+                default: fft_bfly<13>(af, bf, tw, n, Ns, j, m, step, inv); break;
+            }
+        }
+        __syncthreads();
+        cplx* t_ = a; a = b; b = t_;
+        Ns *= R;
+    }
+    return a;
+}
+template <int CW>
+__global__ void __launch_bounds__(PERF_FBMC_THREADS) k_perfect_fbmc(PerfFbmcParams p) {
+    extern __shared__ __align__(16) cplx pf_smem[];
+    const ModemDev& md = p.md;
+    const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
+    cplx* Xa = pf_smem;                    // [CW][Ksym][n]
+    cplx* Xb = Xa + CW * nx;               // [CW][Ksym][n]   (>= CW * N: also holds r)
+    cplx* Sg = Xb + CW * nx;               // [CW][N]
+    cplx* tw = Sg + CW * N;                // [n]
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int2 grp = p.groups[blockIdx.x];
+    const int c0 = grp.x, nc = grp.y;
+    for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
+    for (int idx = tid; idx < CW * nx; idx += nthr) Xa[idx] = cmake(0.0, 0.0);
+    __syncthreads();
+    // ---- load v (the columns are adjacent in the unit scratch: consecutive threads read consecutive 16-byte slots)
+    for (int idx = tid; idx < CW * K; idx += nthr) {
+        const int c = idx % CW, i = idx / CW;
+        if (c >= nc) continue;
+        const int l = i % L, k = i / L;
+        cplx v = p.v_base[p.voff[c0 + c] + (int64_t)i * NC_MAX];
+        v = cmul(v, md.phase[k * L + l]);
+        Xa[(c * Ksym + k) * n + md.bin[l]] = cmake(v.x * md.norm, v.y * md.norm);
+    }
+    __syncthreads();
+    cplx* Z = fft_shared_batch(Xa, Xb, tw, md.plan, true, CW * Ksym);              // un-normalised IFFT per symbol
+    cplx* Rb = (Z == Xa) ? Xb : Xa;                                                  // the other buffer: r, then FFT scratch
+    // ---- overlap-add: s[nn] = 1/n sum_k p[nn - k TS] Z_k[(nn - k TS) mod n]
+    const double inv_n = 1.0 / n;
+    for (int idx = tid; idx < CW * N; idx += nthr) {
+        const int c = idx / N, nn = idx - c * N;
+        int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+        const int k_hi = min(Ksym - 1, nn / TS);
+        cplx acc = cmake(0.0, 0.0);
+        int tap = nn - k_lo * TS, mm = tap % n;
+        for (int k = k_lo; k <= k_hi; ++k) {
+            if (tap >= 0 && tap < md.Np) {
+                const cplx z = Z[(c * Ksym + k) * n + mm];
+                const double pf = md.filt[tap];
+                acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+            }
+            tap -= TS; mm -= TS; if (mm < 0) mm += n; if (mm < 0) mm += n;
+        }
+        Sg[idx] = cmake(acc.x * inv_n, acc.y * inv_n);
+    }
+    __syncthreads();
+    // ---- r = H s with the realization's taps
+    for (int idx = tid; idx < CW * N; idx += nthr) {
+        const int c = idx / N, nn = idx - c * N;
+        cplx acc = cmake(0.0, 0.0);
+        if (c < nc) {
+            const cplx* hr = p.h + (int64_t)p.rep[c0 + c] * p.T * N;
+            for (int t = 0; t < p.T; ++t) {
+                const int d = p.tap_delay[t];
+                if (nn >= d) cfma(acc, hr[(int64_t)t * N + nn], Sg[c * N + nn - d]);
+            }
+        }
+        Rb[idx] = acc;
+    }
+    __syncthreads();
+    // ---- fold: a_k[m] = sum_o p[o n + m] r[k TS + o n + m]   (into the buffer that held Z)
+    for (int idx = tid; idx < CW * nx; idx += nthr) {
+        const int c = idx / nx, rem = idx - c * nx, k = rem / n, m = rem - k * n;
+        const cplx* seg = Rb + c * N + k * TS + m;
+        cplx acc = cmake(0.0, 0.0);
+        for (int o = 0; o < md.O; ++o) {
+            const double pf = md.filt[o * n + m];
+            const cplx v = seg[o * n];
+            acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+        }
+        Z[idx] = acc;
+    }
+    __syncthreads();
+    const cplx* Y = fft_shared_batch(Z, Rb, tw, md.plan, false, CW * Ksym);
+    // ---- epilogue: y_ic = y - conj(phase) Y[bin] / (norm F) + h v
+    for (int idx = tid; idx < CW * K; idx += nthr) {
+        const int c = idx % CW, i = idx / CW;
+        if (c >= nc) continue;
+        const int l = i % L, k = i / L, col = c0 + c;
+        const cplx u0 = cmulc(md.phase[k * L + l], Y[(c * Ksym + k) * n + md.bin[l]]);
+        const int64_t o = p.voff[col] + (int64_t)i * NC_MAX;
+        const cplx yv = p.y[p.yoff[col] + i], hv = p.htrue[(int64_t)p.rep[col] * K + i], vv = p.v_base[o];
+        const cplx hvv = cmul(hv, vv);
+        p.y_base[o] = cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y);
+    }
+}
+
 // ============================================================================ SimpleVersion_DoublyFlat.m:89-176, batched
 // One "body" = one (repetition, SNR point) pass of the script's loop: doubly-flat channel h (one complex scalar), AWGN.
 // r[col][n] = h[body] * s[col][n] + sqrt(Pn[body] / 2) * noise[body][wf][n]   (SV.m:123-131), col = g * n_body + body
 __global__ void k_sv_channel(cplx* __restrict__ r, const cplx* __restrict__ s, const cplx* __restrict__ h,
                              const cplx* __restrict__ noise, const double* __restrict__ pn, int N, int n_body, int wf) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    const int n = blockIdx.y * blockDim.x + threadIdx.x, col = blockIdx.x;      // columns on grid.x: up to 2^31 - 1 of them
     if (n >= N) return;
     const int body = col % n_body;
     const double sc = sqrt(pn[body] / 2.0);

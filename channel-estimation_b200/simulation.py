@@ -134,6 +134,10 @@ class DoublySelectiveSimulation:
             wfs["O"] = dict(G=G_O, Q=Q_O, pil=np.flatnonzero(pmo == 1))
         for w, d in wfs.items():
             ctx.set_waveform(w, d["G"], d["Q"])
+        if use_fbmc:
+            # the polyphase description of the same modem (FBMC.m:61-160): with it the perfect-CSI pass of the loop body applies
+            # G and Q' as Modulation / Demodulation (k_perfect_fbmc) instead of as GEMMs; the library checks that it reproduces G, Q
+            self.FBMC._set_modem(ctx)
         ctx.set_constellation("PAM", self.PAM.SymbolMapping, self.PAM.BitMapping)
         ctx.set_constellation("QAM", self.QAM.SymbolMapping, self.QAM.BitMapping)
         ctx.set_snr(self.Pn)
