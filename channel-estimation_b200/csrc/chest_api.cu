@@ -427,7 +427,9 @@ int modem_demodulate_dev(Ctx* c, Waveform& w, const cplx* r_dev, int n_cols, cpl
     return CHEST_OK;
 }
 
-#define PERF_FBMC_CW 4
+#ifndef PERF_FBMC_CW
+#define PERF_FBMC_CW 1
+#endif
 // Can the perfect-CSI pass of this waveform run through the polyphase modem (k_perfect_fbmc)?  Needs an FBMC description
 // from chest_set_modem next to the dense matrices, shared-memory room for CW columns, and -- since the two descriptions come
 // from the caller independently -- the modem must reproduce G and Q^H on probe vectors.
@@ -440,7 +442,8 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
     if (!w.modem_set || !w.set || md.kind != 0 || md.L * md.Ksym != K || md.N != N || md.time_spacing * 2 != md.nfft) return CHEST_OK;
     const size_t nx = (size_t)md.Ksym * md.nfft;
     if ((size_t)N > nx) return CHEST_OK;
-    const size_t smem = ((size_t)2 * PERF_FBMC_CW * nx + (size_t)PERF_FBMC_CW * N + md.nfft) * sizeof(cplx);
+    for (int q = 0; q < md.plan.n_stage; ++q) if (md.plan.radix[q] > 7) return CHEST_OK;     // the batched FFT carries radices 2, 3, 4, 5, 7
+    const size_t smem = ((size_t)2 * PERF_FBMC_CW * nx + md.nfft) * sizeof(cplx);
     if (smem > 200 * 1024) return CHEST_OK;
     // probes: three unit symbol vectors through the modulator against the columns of G, three unit samples through the
     // demodulator against the rows of Q^H
@@ -513,7 +516,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep) {
             pp.voff = w.f_voff.p; pp.yoff = w.f_yoff.p; pp.rep = w.f_rep.p;
             pp.v_base = c->scratch.p; pp.y_base = c->scratch.p + (size_t)c->K_max * NC_MAX;
             pp.y = w.y.p; pp.htrue = w.htrue.p; pp.h = c->h.p; pp.tap_delay = c->d_tap_delay.p;
-            const size_t smem = ((size_t)2 * PERF_FBMC_CW * md.Ksym * md.nfft + (size_t)PERF_FBMC_CW * N + md.nfft) * sizeof(cplx);
+            const size_t smem = ((size_t)2 * PERF_FBMC_CW * md.Ksym * md.nfft + md.nfft) * sizeof(cplx);
             k_perfect_fbmc<PERF_FBMC_CW><<<w.pf_n_groups, PERF_FBMC_THREADS, smem, c->stream>>>(pp);
             c->launches++;
             CK(cudaGetLastError());

@@ -2251,7 +2251,10 @@ __global__ void __launch_bounds__(POST_THREADS, 2) k_ic_post(IcParams p) {
 // conjugates the table and scales by 1/n like MATLAB's ifft.
 #define FFT_MAX_STAGES 16
 #ifndef PERF_FBMC_THREADS
-#define PERF_FBMC_THREADS 512
+#define PERF_FBMC_THREADS 128
+#endif
+#ifndef PERF_FBMC_MIN_CTAS
+#define PERF_FBMC_MIN_CTAS 8
 #endif
 struct FftPlan { int n, n_stage; int radix[FFT_MAX_STAGES]; };
 struct ModemDev {
@@ -2391,7 +2394,8 @@ __global__ void k_modem_fft(ModemDev md, const cplx* __restrict__ r, cplx* __res
 // Q^H r = Demodulation(r) (FBMC.m:287-302: filter, fold by O, FFT, conj phase) -- instead of as support-aware GEMMs:
 // about 1/13 of the flops (per column 2 x (Ksym FFTs of size nfft + 2 O nfft Ksym real-complex multiply-adds) against
 // 2 x 8 Np L Ksym) and no G / Q operand traffic at all.  One CTA takes CW columns that sit side by side in one unit's
-// interleaved scratch (16 CW contiguous bytes per symbol row) and keeps the whole chain
+// interleaved scratch (16 CW contiguous bytes per symbol row; CW = 1 measured best: more, smaller CTAs overlap their
+// phases) and keeps the whole chain
 //     v -> Z = IFFT -> s (overlap-add) -> r = H s (banded, the realization's taps) -> fold -> FFT -> y_ic
 // in shared memory; every step is FP64 on the scalar pipe.  Used when chest_set_modem described the waveform next to its
 // dense matrices, the description reproduces G / Q (checked at finalize) and the buffers fit; otherwise k_gemm_ring.
@@ -2441,9 +2445,7 @@ __device__ cplx* fft_shared_batch(cplx* a, cplx* b, const cplx* tw, const FftPla
                 case 3: fft_bfly<3>(af, bf, tw, n, Ns, j, m, step, inv); break;
                 case 4: fft_bfly<4>(af, bf, tw, n, Ns, j, m, step, inv); break;
                 case 5: fft_bfly<5>(af, bf, tw, n, Ns, j, m, step, inv); break;
-                case 7: fft_bfly<7>(af, bf, tw, n, Ns, j, m, step, inv); break;
-                case 11: fft_bfly<11>(af, bf, tw, n, Ns, j, m, step, inv); break;
-                default: fft_bfly<13>(af, bf, tw, n, Ns, j, m, step, inv); break;
+                default: fft_bfly<7>(af, bf, tw, n, Ns, j, m, step, inv); break;     // (radices 11, 13: the host keeps the GEMM chain)
             }
         }
         __syncthreads();
@@ -2453,85 +2455,88 @@ __device__ cplx* fft_shared_batch(cplx* a, cplx* b, const cplx* tw, const FftPla
     return a;
 }
 template <int CW>
-__global__ void __launch_bounds__(PERF_FBMC_THREADS) k_perfect_fbmc(PerfFbmcParams p) {
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfect_fbmc(PerfFbmcParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
-    cplx* Xa = pf_smem;                    // [CW][Ksym][n]
-    cplx* Xb = Xa + CW * nx;               // [CW][Ksym][n]   (>= CW * N: also holds r)
-    cplx* Sg = Xb + CW * nx;               // [CW][N]
-    cplx* tw = Sg + CW * N;                // [n]
+    // two buffers of CW x Ksym x n values (>= CW x N) ping-pong through the chain:
+    //   X0: padded symbols -> (IFFT) Z in Xz -> (overlap-add) s in Xo -> (H) r in Xz -> (fold) in Xo -> (FFT) Y
+    cplx* X0 = pf_smem;
+    cplx* X1 = X0 + CW * nx;
+    cplx* tw = X1 + CW * nx;               // [n]
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int2 grp = p.groups[blockIdx.x];
     const int c0 = grp.x, nc = grp.y;
     for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
-    for (int idx = tid; idx < CW * nx; idx += nthr) Xa[idx] = cmake(0.0, 0.0);
+    if (L < n) for (int idx = tid; idx < CW * nx; idx += nthr) X0[idx] = cmake(0.0, 0.0);      // bins without a subcarrier
     __syncthreads();
-    // ---- load v (the columns are adjacent in the unit scratch: consecutive threads read consecutive 16-byte slots)
-    for (int idx = tid; idx < CW * K; idx += nthr) {
-        const int c = idx % CW, i = idx / CW;
-        if (c >= nc) continue;
-        const int l = i % L, k = i / L;
-        cplx v = p.v_base[p.voff[c0 + c] + (int64_t)i * NC_MAX];
-        v = cmul(v, md.phase[k * L + l]);
-        Xa[(c * Ksym + k) * n + md.bin[l]] = cmake(v.x * md.norm, v.y * md.norm);
+    // ---- load v: the CW columns are neighbours in the unit scratch (consecutive threads, consecutive 16-byte slots)
+    for (int idx = tid; idx < CW * K; idx += nthr) {            // flat index: L may be far below the thread count
+        const int c = idx % CW, i = idx / CW, k = i / L, l = i - k * L;
+        cplx v = cmake(0.0, 0.0);
+        if (c < nc) {
+            v = cmul(p.v_base[p.voff[c0 + c] + (int64_t)i * NC_MAX], md.phase[i]);
+            v = cmake(v.x * md.norm, v.y * md.norm);
+        }
+        X0[(c * Ksym + k) * n + md.bin[l]] = v;
     }
     __syncthreads();
-    cplx* Z = fft_shared_batch(Xa, Xb, tw, md.plan, true, CW * Ksym);              // un-normalised IFFT per symbol
-    cplx* Rb = (Z == Xa) ? Xb : Xa;                                                  // the other buffer: r, then FFT scratch
+    cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, CW * Ksym);              // un-normalised IFFT per symbol
+    cplx* Xo = (Xz == X0) ? X1 : X0;
     // ---- overlap-add: s[nn] = 1/n sum_k p[nn - k TS] Z_k[(nn - k TS) mod n]
     const double inv_n = 1.0 / n;
-    for (int idx = tid; idx < CW * N; idx += nthr) {
-        const int c = idx / N, nn = idx - c * N;
-        int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
-        const int k_hi = min(Ksym - 1, nn / TS);
-        cplx acc = cmake(0.0, 0.0);
-        int tap = nn - k_lo * TS, mm = tap % n;
-        for (int k = k_lo; k <= k_hi; ++k) {
-            if (tap >= 0 && tap < md.Np) {
-                const cplx z = Z[(c * Ksym + k) * n + mm];
-                const double pf = md.filt[tap];
-                acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+    for (int c = 0; c < CW; ++c)
+        for (int nn = tid; nn < N; nn += nthr) {
+            int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+            const int k_hi = min(Ksym - 1, nn / TS);
+            cplx acc = cmake(0.0, 0.0);
+            int tap = nn - k_lo * TS, mm = tap % n;
+            const cplx* zc = Xz + (c * Ksym + k_lo) * n;
+            for (int k = k_lo; k <= k_hi; ++k) {
+                if (tap >= 0 && tap < md.Np) {
+                    const cplx z = zc[mm];
+                    const double pf = md.filt[tap];
+                    acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+                }
+                tap -= TS; mm -= TS; if (mm < 0) mm += n;
+                zc += n;
             }
-            tap -= TS; mm -= TS; if (mm < 0) mm += n; if (mm < 0) mm += n;
+            Xo[c * N + nn] = cmake(acc.x * inv_n, acc.y * inv_n);
         }
-        Sg[idx] = cmake(acc.x * inv_n, acc.y * inv_n);
-    }
     __syncthreads();
-    // ---- r = H s with the realization's taps
-    for (int idx = tid; idx < CW * N; idx += nthr) {
-        const int c = idx / N, nn = idx - c * N;
-        cplx acc = cmake(0.0, 0.0);
-        if (c < nc) {
-            const cplx* hr = p.h + (int64_t)p.rep[c0 + c] * p.T * N;
+    // ---- r = H s with the realization's taps (Z is dead: r goes into its buffer)
+    for (int c = 0; c < CW; ++c) {
+        const cplx* hr = p.h + (int64_t)p.rep[c0 + min(c, nc - 1)] * p.T * N;
+        for (int nn = tid; nn < N; nn += nthr) {
+            cplx acc = cmake(0.0, 0.0);
             for (int t = 0; t < p.T; ++t) {
                 const int d = p.tap_delay[t];
-                if (nn >= d) cfma(acc, hr[(int64_t)t * N + nn], Sg[c * N + nn - d]);
+                if (nn >= d) cfma(acc, hr[(int64_t)t * N + nn], Xo[c * N + nn - d]);
             }
+            Xz[c * N + nn] = acc;
         }
-        Rb[idx] = acc;
     }
     __syncthreads();
-    // ---- fold: a_k[m] = sum_o p[o n + m] r[k TS + o n + m]   (into the buffer that held Z)
+    // ---- fold: a_k[m] = sum_o p[o n + m] r[k TS + o n + m]   (s is dead: into its buffer)
     for (int idx = tid; idx < CW * nx; idx += nthr) {
         const int c = idx / nx, rem = idx - c * nx, k = rem / n, m = rem - k * n;
-        const cplx* seg = Rb + c * N + k * TS + m;
+        const cplx* seg = Xz + c * N + k * TS + m;
         cplx acc = cmake(0.0, 0.0);
         for (int o = 0; o < md.O; ++o) {
             const double pf = md.filt[o * n + m];
             const cplx v = seg[o * n];
             acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
         }
-        Z[idx] = acc;
+        Xo[idx] = acc;
     }
     __syncthreads();
-    const cplx* Y = fft_shared_batch(Z, Rb, tw, md.plan, false, CW * Ksym);
+    const cplx* Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, CW * Ksym);
     // ---- epilogue: y_ic = y - conj(phase) Y[bin] / (norm F) + h v
     for (int idx = tid; idx < CW * K; idx += nthr) {
         const int c = idx % CW, i = idx / CW;
         if (c >= nc) continue;
-        const int l = i % L, k = i / L, col = c0 + c;
-        const cplx u0 = cmulc(md.phase[k * L + l], Y[(c * Ksym + k) * n + md.bin[l]]);
+        const int k = i / L, l = i - k * L, col = c0 + c;
+        const cplx u0 = cmulc(md.phase[i], Y[(c * Ksym + k) * n + md.bin[l]]);
         const int64_t o = p.voff[col] + (int64_t)i * NC_MAX;
         const cplx yv = p.y[p.yoff[col] + i], hv = p.htrue[(int64_t)p.rep[col] * K + i], vv = p.v_base[o];
         const cplx hvv = cmul(hv, vv);

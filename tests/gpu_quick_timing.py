@@ -1,5 +1,5 @@
 """Development script (not a test): stage timings of the loop body on a B200 with oracle-built
-setup inputs.  python tests/gpu_quick_timing.py [batch] [reps] [fp64|split_bf16]"""
+setup inputs.  python tests/gpu_quick_timing.py [batch] [reps] [fp64|split_bf16] [product|oracle]"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,9 +9,15 @@ from tests.helpers import context_from_oracle
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 precision = sys.argv[3] if len(sys.argv) > 3 else "fp64"
-S = ds_setup(DSConfig())
+setup = sys.argv[4] if len(sys.argv) > 4 else "product"      # product: the library's own setup (modem description included)
 t = time.time()
-ctx = context_from_oracle(S, max_batch=B)
+if setup == "product":
+    from chest_b200.simulation import DoublySelectiveSimulation
+    sim = DoublySelectiveSimulation(max_batch=B, seed=1)
+    ctx = sim.ctx
+else:
+    S = ds_setup(DSConfig())
+    ctx = context_from_oracle(S, max_batch=B)
 print("context setup s", time.time() - t)
 print("fp64 peak dmma TF/s", ctx.fp64_peak("dmma"), "dfma TF/s", ctx.fp64_peak("dfma"))
 print("work model", ctx.work_model(4))
