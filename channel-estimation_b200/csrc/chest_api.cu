@@ -443,7 +443,7 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
     const size_t nx = (size_t)md.Ksym * md.nfft;
     if ((size_t)N > nx) return CHEST_OK;
     for (int q = 0; q < md.plan.n_stage; ++q) if (md.plan.radix[q] > 7) return CHEST_OK;     // the batched FFT carries radices 2, 3, 4, 5, 7
-    const size_t smem = ((size_t)2 * PERF_FBMC_CW * nx + md.nfft) * sizeof(cplx);
+    const size_t smem = ((size_t)2 * PERF_FBMC_CW * nx + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
     if (smem > 200 * 1024) return CHEST_OK;
     // probes: three unit symbol vectors through the modulator against the columns of G, three unit samples through the
     // demodulator against the rows of Q^H
@@ -516,7 +516,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep) {
             pp.voff = w.f_voff.p; pp.yoff = w.f_yoff.p; pp.rep = w.f_rep.p;
             pp.v_base = c->scratch.p; pp.y_base = c->scratch.p + (size_t)c->K_max * NC_MAX;
             pp.y = w.y.p; pp.htrue = w.htrue.p; pp.h = c->h.p; pp.tap_delay = c->d_tap_delay.p;
-            const size_t smem = ((size_t)2 * PERF_FBMC_CW * md.Ksym * md.nfft + md.nfft) * sizeof(cplx);
+            const size_t smem = ((size_t)2 * PERF_FBMC_CW * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
             k_perfect_fbmc<PERF_FBMC_CW><<<w.pf_n_groups, PERF_FBMC_THREADS, smem, c->stream>>>(pp);
             c->launches++;
             CK(cudaGetLastError());

@@ -2412,23 +2412,41 @@ __device__ __forceinline__ void fft_bfly(const cplx* __restrict__ a, cplx* __res
                                          int n, int Ns, int j, int m, int step, bool inv) {
     const int k = j % Ns;
     cplx v[R];
+    v[0] = a[j];
 #pragma unroll
-    for (int t = 0; t < R; ++t) {
-        cplx w = tw[t * k * step];                              // t k step < n: no reduction needed
-        if (inv) w.y = -w.y;
-        v[t] = cmul(a[j + t * m], w);
-    }
-    const int j0 = (j - k) * R + k;
-#pragma unroll
-    for (int u = 0; u < R; ++u) {
-        cplx acc = v[0];
-#pragma unroll
-        for (int t = 1; t < R; ++t) {
-            cplx w = tw[((t * u) % R) * (n / R)];
+    for (int t = 1; t < R; ++t) {
+        v[t] = a[j + t * m];
+        if (k) {                                                // first stage (Ns = 1): every input twiddle is 1
+            cplx w = tw[t * k * step];                          // t k step < n: no reduction needed
             if (inv) w.y = -w.y;
-            cfma(acc, v[t], w);
+            v[t] = cmul(v[t], w);
         }
-        b[j0 + u * Ns] = acc;
+    }
+    cplx* o = b + (j - k) * R + k;
+    if (R == 2) {
+        o[0] = cadd(v[0], v[1]); o[Ns] = csub(v[0], v[1]);
+    } else if (R == 4) {                                        // roots of unity 1, -+i, -1, +-i: additions only
+        const cplx s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]), s13 = cadd(v[1], v[3]), d13 = csub(v[1], v[3]);
+        const cplx r = inv ? cmake(-d13.y, d13.x) : cmake(d13.y, -d13.x);      // (+-i)^-1 ... forward: -i d13, inverse: +i d13
+        o[0] = cadd(s02, s13); o[Ns] = cadd(d02, r); o[2 * Ns] = csub(s02, s13); o[3 * Ns] = csub(d02, r);
+    } else if (R == 3) {                                        // w = -1/2 -+ i sqrt(3)/2
+        const double h3 = 0.86602540378443864676;
+        const cplx sm = cadd(v[1], v[2]), df = csub(v[1], v[2]);
+        const cplx base = cmake(v[0].x - 0.5 * sm.x, v[0].y - 0.5 * sm.y);
+        const cplx rot = inv ? cmake(-h3 * df.y, h3 * df.x) : cmake(h3 * df.y, -h3 * df.x);     // forward: -i h3 df
+        o[0] = cadd(v[0], sm); o[Ns] = cadd(base, rot); o[2 * Ns] = csub(base, rot);
+    } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            cplx acc = v[0];
+#pragma unroll
+            for (int t = 1; t < R; ++t) {
+                cplx w = tw[((t * u) % R) * (n / R)];
+                if (inv) w.y = -w.y;
+                cfma(acc, v[t], w);
+            }
+            o[u * Ns] = acc;
+        }
     }
 }
 // n_batch independent transforms of size plan.n stored back to back in `a` (scratch `b`, same size); returns the result buffer
@@ -2464,10 +2482,14 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
     cplx* X0 = pf_smem;
     cplx* X1 = X0 + CW * nx;
     cplx* tw = X1 + CW * nx;               // [n]
+    double* filt = reinterpret_cast<double*>(tw + n);          // [Np] prototype filter
+    int* bins = reinterpret_cast<int*>(filt + md.Np);          // [L]
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int2 grp = p.groups[blockIdx.x];
     const int c0 = grp.x, nc = grp.y;
     for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
+    for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+    for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
     if (L < n) for (int idx = tid; idx < CW * nx; idx += nthr) X0[idx] = cmake(0.0, 0.0);      // bins without a subcarrier
     __syncthreads();
     // ---- load v: the CW columns are neighbours in the unit scratch (consecutive threads, consecutive 16-byte slots)
@@ -2478,7 +2500,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
             v = cmul(p.v_base[p.voff[c0 + c] + (int64_t)i * NC_MAX], md.phase[i]);
             v = cmake(v.x * md.norm, v.y * md.norm);
         }
-        X0[(c * Ksym + k) * n + md.bin[l]] = v;
+        X0[(c * Ksym + k) * n + bins[l]] = v;
     }
     __syncthreads();
     cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, CW * Ksym);              // un-normalised IFFT per symbol
@@ -2495,7 +2517,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
             for (int k = k_lo; k <= k_hi; ++k) {
                 if (tap >= 0 && tap < md.Np) {
                     const cplx z = zc[mm];
-                    const double pf = md.filt[tap];
+                    const double pf = filt[tap];
                     acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
                 }
                 tap -= TS; mm -= TS; if (mm < 0) mm += n;
@@ -2523,7 +2545,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         const cplx* seg = Xz + c * N + k * TS + m;
         cplx acc = cmake(0.0, 0.0);
         for (int o = 0; o < md.O; ++o) {
-            const double pf = md.filt[o * n + m];
+            const double pf = filt[o * n + m];
             const cplx v = seg[o * n];
             acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
         }
@@ -2536,7 +2558,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         const int c = idx % CW, i = idx / CW;
         if (c >= nc) continue;
         const int k = i / L, l = i - k * L, col = c0 + c;
-        const cplx u0 = cmulc(md.phase[i], Y[(c * Ksym + k) * n + md.bin[l]]);
+        const cplx u0 = cmulc(md.phase[i], Y[(c * Ksym + k) * n + bins[l]]);
         const int64_t o = p.voff[col] + (int64_t)i * NC_MAX;
         const cplx yv = p.y[p.yoff[col] + i], hv = p.htrue[(int64_t)p.rep[col] * K + i], vv = p.v_base[o];
         const cplx hvv = cmul(hv, vv);
