@@ -208,6 +208,28 @@ def split_bf16_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last_first, 
                              "tolerance": "estimated channel within 1e-4 of the FP64 mode (tests/test_gpu_tc.py measures 3e-6 on the pilot estimates, 1e-5 on diag(D_est))"}}
 
 
+def perfect_csi_roofline(ctx, sim, B, I, wm, chain_ms, peak_dmma, hbm_peak):
+    """The perfect-CSI pass y - Q^H H G v + h v of one iteration.  FBMC columns go through the polyphase modem (k_perfect_fbmc:
+    G and Q^H applied as IFFT / filter / overlap-add and filter / fold / FFT, all in shared memory), OFDM columns through
+    the ring GEMMs: the pass is bound by memory traffic, not by the FP64 pipe, so its roofline is bytes, with the flops of the
+    GEMM formulation it replaces reported beside it."""
+    n_snr = len(sim.Pn)
+    cols = {name: B * n_snr for name in sim.sch}
+    k_of = {name: ctx.schemes[name]["K"] for name in sim.sch}
+    alg_bytes = sum(cols[n] * k_of[n] * 3 * 16.0 for n in sim.sch)           # v in, y in, y_ic out (16 B each per symbol)
+    gemm_flops = B * wm["factored_perf_flops"] / I
+    return {"kernel": "k_perfect_fbmc (FBMC columns: polyphase Modulation -> banded H -> Demodulation -> cancellation, one column per CTA in "
+                      "shared memory) + k_gemm_ring x2 + k_apply_h_cols_planes (OFDM columns)",
+            "bound": "hbm", "achieved": alg_bytes / (chain_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_bytes / (chain_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_iteration": alg_bytes, "avg_iteration_ms": chain_ms,
+            "gemm_formulation_flops_per_iteration": gemm_flops, "gemm_equivalent_tflops": gemm_flops / (chain_ms * 1e-3) / 1e12,
+            "gemm_equivalent_frac_of_dmma_peak": gemm_flops / (chain_ms * 1e-3) / 1e12 / peak_dmma,
+            "note": "algorithmic bytes: v and y read, y_ic written once per column (48 B per symbol); the kernel is bound by shared-memory / L1 "
+                    "throughput (ncu l1tex 86 %, profiles/r02_perfect_fbmc_summary.txt), not by HBM or the FP64 pipe (15 %).  The GEMM formulation "
+                    "of round 1 needed 13 x the flops; gemm_equivalent_* divides THOSE flops by the time of the pass (above 1 = faster than a "
+                    "perfect DMMA GEMM could be)"}
+
+
 def ofdm_only_line(torch, Simulation, device, K, W, cpu_sample):
     """realizations/s of the DS.m loop body with only the OFDM scheme enabled (K = 336), B = 4096 per step."""
     B, I = 4096, 4
@@ -481,12 +503,7 @@ def run_b200(args):
                                        "the three-multiplication form (6 per complex multiply-add): frac can exceed 1, "
                                        "frac_executed = 0.75 frac is the share of the DMMA peak the executed products take "
                                        "(ncu pipe-busy fraction: profiles/r01_kic_main_summary.txt)"},
-            "roofline_perfect_csi": {"kernel": "k_gemm<PLAIN> x2 + k_apply_h_cols (perfect-CSI pass, factored: y - Q^H H (G v) + h v)",
-                                     "bound": "tensor", "achieved": B * wm["factored_perf_flops"] / I / (chain_ms * 1e-3) / 1e12,
-                                     "peak": peak_dmma, "unit": "TFLOP/s",
-                                     "frac": B * wm["factored_perf_flops"] / I / (chain_ms * 1e-3) / 1e12 / peak_dmma,
-                                     "algorithmic_flops_per_iteration": B * wm["factored_perf_flops"] / I,
-                                     "avg_iteration_ms": chain_ms},
+            "roofline_perfect_csi": perfect_csi_roofline(ctx, sim, B, I, wm, chain_ms, peak_dmma, hbm_peak),
             "stage_ms_per_step": {k: v / K for k, v in stage_sum.items()},
             "kernel_ms_per_step": {k: v / K for k, v in kern_sum.items()},
             "wall_ms_per_step": wall_ms / K, "launches_per_step": launches_per_step, "setup_s": setup_s,
