@@ -322,8 +322,8 @@ int gen_chan_gauss(Ctx* c, int n_rep, uint64_t seed, int64_t first_rep) {
 }
 
 int stage_channel(Ctx* c, int n_rep, const double* du, const double* pu) {
-    dim3 grid((c->N + 127) / 128, c->T, n_rep);
-    k_synth_h<<<grid, 128, 2 * c->paths * sizeof(double), c->stream>>>(
+    dim3 grid((c->N + SYNTH_THREADS * SYNTH_SEG - 1) / (SYNTH_THREADS * SYNTH_SEG), c->T, n_rep);
+    k_synth_h<<<grid, SYNTH_THREADS, 4 * c->paths * sizeof(double), c->stream>>>(
         c->h.p, du, pu, c->d_tap_amp.p, c->N, c->T, c->paths, c->fD, c->dt, c->model);
     c->launches++;
     CK(cudaGetLastError());
@@ -471,6 +471,7 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
     if (dev <= 1e-12 * mag) {
         w.pf_state = 1;
         CK(cudaFuncSetAttribute(k_perfect_fbmc<PERF_FBMC_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_demod_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     return CHEST_OK;
 }
@@ -887,6 +888,18 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     for (int wfi = 0; wfi < 2; ++wfi) {
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch) continue;
+        { rc = check_polyphase_pass(c, w); if (rc) return rc; }
+        if (w.pf_state == 1 && !getenv("CHEST_CHAIN_LEGACY")) {          // FBMC: the polyphase demodulator instead of the GEMM
+            DemodFbmcParams dp{};
+            dp.md = w.modem; dp.N = N; dp.K = w.K; dp.n_snr = S; dp.n_rep = n_rep; dp.n_cols = w.nsch * S * n_rep;
+            dp.r0 = w.r0.p; dp.noise = noise; dp.noise_scale = c->d_noise_scale.p; dp.y = w.y.p;
+            const ModemDev& md = w.modem;
+            const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
+            k_demod_fbmc<<<dp.n_cols, PERF_FBMC_THREADS, smem, st>>>(dp);
+            c->launches++;
+            CK(cudaGetLastError());
+            continue;
+        }
         GemmParams p{};
         p.M = w.K; p.Kc = N; p.n_cols = w.nsch * S * n_rep; p.lda = (N + 1) & ~1; p.ldc = w.K; p.conj_a = 1;
         p.At1 = w.Q1.p; p.At2 = w.Q2.p; p.mt_klo = w.q_klo.p; p.mt_khi = w.q_khi.p; p.out = w.y.p;

@@ -71,36 +71,58 @@ __global__ void k_rng_normal(cplx* __restrict__ out, int n, int n_snr, int n_rep
 
 // ============================================================================ K1: channel
 // h[rep][tap][n] = sqrt(pdp_tap) / sqrt(paths) * sum_p exp(j 2 pi (phase_p + shift_p n dt))
-// (FF.m:227-237).  One thread per sample n, paths staged in shared memory.
-__global__ void k_synth_h(cplx* __restrict__ h, const double* __restrict__ doppler_u,
+// (FF.m:227-237).  A thread owns SYNTH_SEG consecutive samples: per path one sincos at the first sample, then the phasor
+// is advanced by the path's per-sample rotation exp(j 2 pi shift_p dt) (computed once per block, shared memory) -- a complex
+// multiplication per sample instead of a sincos.  The recurrence restarts every SYNTH_SEG samples, so its rounding error
+// stays below SYNTH_SEG ulp per term (parity with the oracle's exp() at 1e-12 holds with three digits to spare).
+#define SYNTH_SEG 16
+#define SYNTH_THREADS 64
+__global__ void __launch_bounds__(SYNTH_THREADS) k_synth_h(cplx* __restrict__ h, const double* __restrict__ doppler_u,
                           const double* __restrict__ phase_u, const double* __restrict__ tap_amp,
                           int N, int T, int paths, double fD, double dt, int model) {
     extern __shared__ double sm[];
     double* shift = sm;
     double* phase = sm + paths;
+    double* rot_c = sm + 2 * paths;
+    double* rot_s = sm + 3 * paths;
     int tap = blockIdx.y, rep = blockIdx.z;
     const double* du = doppler_u + (int64_t)rep * T * paths;
     const double* pu = phase_u + (int64_t)rep * T * paths;
     const double PI = 3.14159265358979323846;
     for (int p = threadIdx.x; p < paths; p += blockDim.x) {
         double u = du[tap + T * p];                       // rand([T 1 paths]): tap fastest
-        shift[p] = (model == 0) ? cos(u * 2.0 * PI) * fD : 2.0 * (u - 0.5) * fD;
+        const double sh = (model == 0) ? cos(u * 2.0 * PI) * fD : 2.0 * (u - 0.5) * fD;
+        shift[p] = sh;
         phase[p] = pu[tap + T * p];
+        double s_, c_;
+        sincos((2.0 * PI) * (sh * dt), &s_, &c_);
+        rot_c[p] = c_; rot_s[p] = s_;
     }
     __syncthreads();
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    double t = n * dt;
-    double sr = 0.0, si = 0.0;
+    const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * SYNTH_SEG;
+    if (n0 >= N) return;
+    const double t0 = n0 * dt;
+    double sr[SYNTH_SEG], si[SYNTH_SEG];
+#pragma unroll
+    for (int q = 0; q < SYNTH_SEG; ++q) { sr[q] = 0.0; si[q] = 0.0; }
     for (int p = 0; p < paths; ++p) {
-        double arg = phase[p] + shift[p] * t;
-        double s, c;
-        sincos((2.0 * PI) * arg, &s, &c);
-        sr += c; si += s;
+        double s_, c_;
+        sincos((2.0 * PI) * (phase[p] + shift[p] * t0), &s_, &c_);
+        const double rc = rot_c[p], rs = rot_s[p];
+#pragma unroll
+        for (int q = 0; q < SYNTH_SEG; ++q) {
+            sr[q] += c_; si[q] += s_;
+            const double cn = fma(c_, rc, -(s_ * rs));
+            s_ = fma(s_, rc, c_ * rs);
+            c_ = cn;
+        }
     }
-    double inv = sqrt((double)paths);
-    double a = tap_amp[tap];
-    h[((int64_t)rep * T + tap) * N + n] = cmake(a * (sr / inv), a * (si / inv));
+    const double inv = sqrt((double)paths);
+    const double a = tap_amp[tap];
+    cplx* out = h + ((int64_t)rep * T + tap) * N + n0;
+#pragma unroll
+    for (int q = 0; q < SYNTH_SEG; ++q)
+        if (n0 + q < N) out[q] = cmake(a * (sr[q] / inv), a * (si[q] / inv));
 }
 
 // 'Discrete-Jakes' / 'Discrete-Uniform' (FF.m:203-221): the impulse response of a tap is the inverse DFT of a spectrum with
@@ -2563,6 +2585,57 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         const cplx yv = p.y[p.yoff[col] + i], hv = p.htrue[(int64_t)p.rep[col] * K + i], vv = p.v_base[o];
         const cplx hvv = cmul(hv, vv);
         p.y_base[o] = cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y);
+    }
+}
+
+// y = Q^H (r0 + sqrt(Pn/2) noise) of FBMC columns through the polyphase demodulator (DS.m:401-409 with Q^H r = Demodulation(r),
+// FBMC.m:287-302): column = (scheme slot g, SNR point, realization) as in k_gemm<GEMM_DEMOD>; one column per CTA, the received
+// samples, the folded symbols and the FFT ping-pong in two shared-memory buffers.
+struct DemodFbmcParams {
+    ModemDev md;
+    int N, K, n_snr, n_rep, n_cols;
+    const cplx* r0; const cplx* noise; const double* noise_scale;
+    cplx* y;                       // [col][K]
+};
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod_fbmc(DemodFbmcParams p) {
+    extern __shared__ __align__(16) cplx pf_smem[];
+    const ModemDev& md = p.md;
+    const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
+    cplx* X0 = pf_smem;
+    cplx* X1 = X0 + nx;
+    cplx* tw = X1 + nx;
+    double* filt = reinterpret_cast<double*>(tw + n);
+    int* bins = reinterpret_cast<int*>(filt + md.Np);
+    const int tid = threadIdx.x, nthr = blockDim.x, col = blockIdx.x;
+    for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
+    for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+    for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
+    {   // received samples of this column
+        const int rep = col % p.n_rep, q = col / p.n_rep, snr = q % p.n_snr, grp = q / p.n_snr;
+        const cplx* a = p.r0 + ((int64_t)grp * p.n_rep + rep) * N;
+        const cplx* nz = p.noise + ((int64_t)rep * p.n_snr + snr) * N;
+        const double sc = p.noise_scale[snr];
+        for (int nn = tid; nn < N; nn += nthr) { const cplx x = a[nn], z = nz[nn]; X1[nn] = cmake(x.x + sc * z.x, x.y + sc * z.y); }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nx; idx += nthr) {               // fold: a_k[m] = sum_o p[o n + m] r[k TS + o n + m]
+        const int k = idx / n, m = idx - k * n;
+        const cplx* seg = X1 + k * TS + m;
+        cplx acc = cmake(0.0, 0.0);
+        for (int o = 0; o < md.O; ++o) {
+            const double pf = filt[o * n + m];
+            const cplx v = seg[o * n];
+            acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+        }
+        X0[idx] = acc;
+    }
+    __syncthreads();
+    const cplx* Y = fft_shared_batch(X0, X1, tw, md.plan, false, Ksym);
+    cplx* out = p.y + (int64_t)col * K;
+    for (int i = tid; i < K; i += nthr) {
+        const int k = i / L, l = i - k * L;
+        const cplx u0 = cmulc(md.phase[i], Y[k * n + bins[l]]);
+        out[i] = cmake(u0.x * md.inv_demod, u0.y * md.inv_demod);
     }
 }
 
