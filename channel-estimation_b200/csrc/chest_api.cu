@@ -66,6 +66,7 @@ struct Waveform {
     DevBuf<cplx> G, Q, Gt;
     DevBuf<cplx> Q1; DevBuf<double> Q2;                // three-multiplication planes of Q^H: (re, re - im), im; row stride Np
     DevBuf<cplx> Gt1; DevBuf<double> Gt2;              // planes of G (not conjugated), rows = samples: (re, re + im), -im; row stride Kp
+    bool twin_on = false;                              // the perfect-CSI twin of this waveform runs in k_perfect_twin_fbmc (no PERF units)
     int pf_state = 0;                                  // polyphase perfect-CSI pass: 0 unchecked, 1 usable, -1 not (no modem description, mismatch, too large)
     DevBuf<int2> pf_groups; int pf_n_groups = 0;
     DevBuf<cplx> f_r1; DevBuf<double> f_r2;            // planes of r = H s of the factored perfect-CSI pass: (re, re + im), im - re; [column][Np]
@@ -179,6 +180,7 @@ struct Ctx {
     cudaEvent_t ev_gd[2] = {};   // end of k_gemm_d of the two waveforms
     cudaEvent_t ev_ic[36] = {};  // after every k_ic_main (+ factored chain) / k_ic_light launch
     cudaEvent_t ev_mn[18] = {};  // after k_ic_main alone (before the factored perfect-CSI chain)
+    cudaEvent_t ev_tw[2] = {};   // around the fused perfect-CSI twin kernels
     cudaEvent_t ev_k1[8] = {};   // inside stage 1: after k_synth_h, k_tx_symbols, per waveform after s = G x and after r0 = H s
     float kernel_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // k_apply_hg, k_gemm_d, k_ic_main, k_ic_light, factored perfect-CSI chain, diag(D) GEMM, k_synth_h, k_tx_symbols, s = G x, k_apply_h
     float hg_ms = 0; double hg_bytes = 0;
@@ -674,10 +676,21 @@ int build_ctas(Ctx* c, int n_rep) {
     // heavy work first; compute-bound EST CTAs and memory-heavy PERF CTAs are interleaved so that both the
     // FP64 tensor pipe and HBM stay busy
     std::vector<IcCta> e1, p1, e2, p2;
+    for (int wfi = 0; wfi < 2; ++wfi) {                        // waveforms whose perfect-CSI twin runs as one fused kernel
+        Waveform& w = c->wf[wfi];
+        w.twin_on = false;
+        if (!w.set || !w.nsch || c->perf_mode != 1 || getenv("CHEST_NO_TWIN")) continue;
+        int rc = check_polyphase_pass(c, w); if (rc) return rc;
+        bool ok = w.pf_state == 1;
+        for (int q = 0; q < w.nsch && ok; ++q) ok = c->cst[c->sch[w.sch[q]].constellation].order <= 256;
+        w.twin_on = ok;
+    }
     est(CHEST_SCHEME_AUX); est(CHEST_SCHEME_COD); e1.swap(v);
-    perf(CHEST_WF_FBMC); p1.swap(v);
+    if (!c->wf[CHEST_WF_FBMC].twin_on) perf(CHEST_WF_FBMC);
+    p1.swap(v);
     est(CHEST_SCHEME_OFDM); e2.swap(v);
-    perf(CHEST_WF_OFDM); p2.swap(v);
+    if (!c->wf[CHEST_WF_OFDM].twin_on) perf(CHEST_WF_OFDM);
+    p2.swap(v);
     auto weave = [&](std::vector<IcCta>& a, std::vector<IcCta>& b) {
         size_t ia = 0, ib = 0;
         while (ia < a.size() || ib < b.size()) {
@@ -718,7 +731,7 @@ int build_ctas(Ctx* c, int n_rep) {
         const int S = c->S, nblk = (S + 7) / 8;
         for (int wfi = 0; wfi < 2; ++wfi) {
             Waveform& w = c->wf[wfi];
-            if (!w.set || !w.nsch) { w.f_cols = 0; continue; }
+            if (!w.set || !w.nsch || w.twin_on) { w.f_cols = 0; w.pf_n_groups = 0; continue; }
             const int nv = w.nsch * S;
             w.perf_nblk = nblk; w.f_cols = nv * n_rep;
             std::vector<int64_t> voff(w.f_cols), yoff(w.f_cols);
@@ -1003,6 +1016,26 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     int light_grid = std::min(c->ic_light_grid * IC_LIGHT_WAVES, n_units);
     if (const char* e = getenv("CHEST_IC_MAIN_GRID")) main_grid = std::max(1, std::min(main_grid, atoi(e)));
     if (const char* e = getenv("CHEST_IC_LIGHT_GRID")) light_grid = std::max(1, std::min(light_grid, atoi(e)));
+    if (c->profiling) CK(cudaEventRecord(c->ev_tw[0], st));
+    for (int wfi = 0; wfi < 2; ++wfi) {                            // perfect-CSI twin of whole waveforms: all iterations, one launch
+        Waveform& w = c->wf[wfi];
+        if (!w.twin_on) continue;
+        const ModemDev& md = w.modem;
+        PerfTwinParams tp{};
+        tp.md = md; tp.nsch = w.nsch; tp.n_snr = S; tp.n_rep = n_rep; tp.n_iter = n_iter; tp.T = c->T; tp.N = N; tp.K = w.K;
+        int n_data_max = 0;
+        for (int q = 0; q < w.nsch; ++q) { tp.sch[q] = ip.sch[w.sch[q]]; tp.scheme_id[q] = w.sch[q]; n_data_max = std::max(n_data_max, c->sch[w.sch[q]].n_data); }
+        for (int k = 0; k < 2; ++k) tp.cst[k] = c->cst[k].dev;
+        tp.htrue = w.htrue.p; tp.h = c->h.p; tp.tap_delay = c->d_tap_delay.p; tp.err = err;
+        const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int)
+                            + (size_t)((n_data_max + 15) & ~15);
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) { CK(cudaFuncSetAttribute(k_perfect_twin_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+        k_perfect_twin_fbmc<<<n_rep * w.nsch * S, PERF_FBMC_THREADS, smem, st>>>(tp);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev_tw[1], st));
     for (int it = 0; it <= n_iter; ++it) {
         ip.it = it;
         if (it > 0) {                                              // phase B of iteration it
@@ -1096,6 +1129,7 @@ int finish_pipeline(Ctx* c) {
             cudaEventElapsedTime(&t, it > 0 ? c->ev_ic[2 * it] : c->ev[4], c->ev_ic[2 * it + 1]);
             c->kernel_ms[3] += t;
         }
+        { float t = 0; cudaEventElapsedTime(&t, c->ev_tw[0], c->ev_tw[1]); c->kernel_ms[4] += t; }      // fused perfect-CSI twin
         c->kernel_ms[0] = c->kernel_ms[1] = 0;
         c->kernel_ms[5] = c->perf_mode == 1 ? c->stage_ms[2] : 0;              // factored mode: stage 2 is the diag(D) GEMM
         cudaEventElapsedTime(&c->kernel_ms[6], c->ev[1], c->ev_k1[0]);         // k_synth_h
@@ -1167,6 +1201,7 @@ int chest_create(int device, uint64_t* handle) {
     for (auto& e : c->ev_ic) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_mn) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_k1) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_tw) CK(cudaEventCreate(&e));
     *handle = (uint64_t)(uintptr_t)c;
     return CHEST_OK;
 }
@@ -1183,6 +1218,7 @@ int chest_destroy(uint64_t handle) {
     for (auto& e : c->ev_ic) cudaEventDestroy(e);
     for (auto& e : c->ev_mn) cudaEventDestroy(e);
     for (auto& e : c->ev_k1) cudaEventDestroy(e);
+    for (auto& e : c->ev_tw) cudaEventDestroy(e);
     for (auto& q : c->pf) { cudaEventDestroy(q.landed); cudaEventDestroy(q.released); }
     cudaStreamSynchronize(c->copy_stream);
     if (c->err_pinned) cudaFreeHost(c->err_pinned);

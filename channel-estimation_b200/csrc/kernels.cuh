@@ -2588,6 +2588,159 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The whole perfect-CSI twin of an FBMC column (DS.m:450-466 and 541-561 for every iteration) in ONE launch per batch:
+// one CTA owns one (realization, scheme, SNR point) column and runs, entirely in shared memory,
+//     it = 0:        x = y / h                                   -> select / de-spread, decide, count
+//     it = 1..I:     v = C [xP; decided symbols]                 (precoder in CSR form)
+//                    y_ic = y - Demodulation(H Modulation(v)) + h v     (polyphase modem, as k_perfect_fbmc)
+//                    x = y_ic / h                                -> select / de-spread, decide, count
+// The twin needs nothing from the estimated-CSI path, so v and y_ic never touch HBM and the scalar kernel k_ic_light has no
+// perfect-CSI units left for this waveform.  Decisions, counters and the parity state (chest_get_state) follow k_ic_light.
+struct PerfTwinParams {
+    ModemDev md;
+    SchemeDev sch[2];              // the schemes on this waveform, by slot
+    ConstDev cst[2];
+    int scheme_id[2];              // their global ids (index of the error counters)
+    int nsch, n_snr, n_rep, n_iter, T, N, K;
+    const cplx* htrue; const cplx* h; const int* tap_delay;
+    uint32_t* err;
+};
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfect_twin_fbmc(PerfTwinParams p) {
+    extern __shared__ __align__(16) cplx pf_smem[];
+    const ModemDev& md = p.md;
+    const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
+    cplx* X0 = pf_smem;
+    cplx* X1 = X0 + nx;
+    cplx* tw = X1 + nx;
+    double* filt = reinterpret_cast<double*>(tw + n);
+    int* bins = reinterpret_cast<int*>(filt + md.Np);
+    uint8_t* zw = reinterpret_cast<uint8_t*>(bins + L);        // decided word per data symbol
+    __shared__ unsigned int cnt[2];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int col = blockIdx.x, snr = col % p.n_snr, slot = (col / p.n_snr) % p.nsch, rep = col / (p.n_snr * p.nsch);
+    const SchemeDev& sd = p.sch[slot];
+    const ConstDev& cd = p.cst[sd.constellation];
+    const int P = sd.P, n_data = sd.n_data;
+    const bool select = sd.detect_mode != 1;
+    const int scheme_id = p.scheme_id[slot];
+    const cplx* ycol = sd.y + ((int64_t)snr * p.n_rep + rep) * K;
+    const cplx* ht = p.htrue + (int64_t)rep * K;
+    const cplx* xP = sd.xP + (int64_t)rep * P;
+    const uint32_t* txw = sd.txword + (int64_t)rep * n_data;
+    const cplx* hr = p.h + (int64_t)rep * p.T * N;
+    const int64_t colbase = ((int64_t)snr * p.n_rep + rep) * n_data;
+    for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
+    for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+    for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
+    // z[c] of the precoder input: transmitted pilot, or the symbol decided for data index c - P
+    auto z_of = [&](int c) -> cplx { return c < P ? xP[c] : cd.symbol[zw[c - P]]; };
+    auto v_of = [&](int i) -> cplx {                            // v[i] = sum_c C[i, c] z[c]
+        const int c0 = sd.row_col0[i];
+        if (c0 >= 0) return cmul(sd.row_val0[i], z_of(c0));
+        cplx acc = cmake(0.0, 0.0);
+        if (c0 == -2) for (int e = sd.c_rowptr[i]; e < sd.c_rowptr[i + 1]; ++e) cfma(acc, sd.c_val[e], z_of(sd.c_col[e]));
+        return acc;
+    };
+    for (int it = 0; it <= p.n_iter; ++it) {
+        const bool last = it == p.n_iter;
+        if (tid < 2) cnt[tid] = 0;
+        cplx* Xe;                                               // equalised symbols x = y_ic / h of this iteration, [K]
+        if (it == 0) {
+            __syncthreads();
+            for (int i = tid; i < K; i += nthr) X1[i] = cdiv_fast(ycol[i], ht[i]);
+            Xe = X1;
+        } else {
+            if (L < n) for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0);
+            __syncthreads();                                    // decided words of the previous iteration are complete
+            for (int i = tid; i < K; i += nthr) {
+                const int k = i / L, l = i - k * L;
+                const cplx v = cmul(v_of(i), md.phase[i]);
+                X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
+            }
+            __syncthreads();
+            cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
+            cplx* Xo = (Xz == X0) ? X1 : X0;
+            const double inv_n = 1.0 / n;
+            for (int nn = tid; nn < N; nn += nthr) {            // overlap-add
+                int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+                const int k_hi = min(Ksym - 1, nn / TS);
+                cplx acc = cmake(0.0, 0.0);
+                int tap = nn - k_lo * TS, mm = tap % n;
+                const cplx* zc = Xz + k_lo * n;
+                for (int k = k_lo; k <= k_hi; ++k) {
+                    if (tap >= 0 && tap < md.Np) {
+                        const cplx z = zc[mm];
+                        const double pf = filt[tap];
+                        acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+                    }
+                    tap -= TS; mm -= TS; if (mm < 0) mm += n;
+                    zc += n;
+                }
+                Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
+            }
+            __syncthreads();
+            for (int nn = tid; nn < N; nn += nthr) {            // r = H s
+                cplx acc = cmake(0.0, 0.0);
+                for (int t = 0; t < p.T; ++t) {
+                    const int d = p.tap_delay[t];
+                    if (nn >= d) cfma(acc, hr[(int64_t)t * N + nn], Xo[nn - d]);
+                }
+                Xz[nn] = acc;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nx; idx += nthr) {        // fold
+                const int k = idx / n, m = idx - k * n;
+                const cplx* seg = Xz + k * TS + m;
+                cplx acc = cmake(0.0, 0.0);
+                for (int o = 0; o < md.O; ++o) {
+                    const double pf = filt[o * n + m];
+                    const cplx v = seg[o * n];
+                    acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+                }
+                Xo[idx] = acc;
+            }
+            __syncthreads();
+            cplx* Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, Ksym);
+            Xe = (Y == X0) ? X1 : X0;                           // the FFT scratch buffer is free again
+            for (int i = tid; i < K; i += nthr) {               // y_ic = y - U + h v, then x = y_ic / h
+                const int k = i / L, l = i - k * L;
+                const cplx u0 = cmulc(md.phase[i], Y[k * n + bins[l]]);
+                const cplx hv = ht[i], yv = ycol[i];
+                const cplx hvv = cmul(hv, v_of(i));
+                const cplx yic = cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y);
+                Xe[i] = cdiv_fast(yic, hv);
+            }
+        }
+        __syncthreads();                                        // x complete; every v_of() of this iteration has read zw
+        unsigned e_all = 0, e_edge = 0;
+        for (int d = tid; d < n_data; d += nthr) {
+            cplx xd;
+            if (select) {
+                const cplx xh = Xe[sd.data_pos[d]];
+                xd = cmake(xh.x * sd.inv_sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y * sd.inv_sqrt_dpr);
+            } else {                                            // de-spreading: x_d = C_d^H x / dpr over the spreading set
+                cplx acc = cmake(0.0, 0.0);
+                for (int e = sd.ct_colptr[P + d]; e < sd.ct_colptr[P + d + 1]; ++e) {
+                    const cplx t = cmulc(sd.ct_val[e], Xe[sd.ct_row[e]]);
+                    acc.x += t.x; acc.y += t.y;
+                }
+                xd = cmake(acc.x * sd.inv_dpr, 0.0);
+            }
+            const int word = ic_decide(cd, xd, txw[d], sd.edge_mask[d], e_all, e_edge);
+            if (last) sd.xD[1][colbase + d] = xd;
+            zw[d] = (uint8_t)word;
+        }
+        if (e_all) atomicAdd(&cnt[0], e_all);
+        if (e_edge) atomicAdd(&cnt[1], e_edge);
+        __syncthreads();
+        if (tid < 2) {
+            const int64_t o = ((((int64_t)rep * p.n_snr + snr) * (p.n_iter + 1) + it) * 3 + scheme_id) * 4 + 2 + tid;     // csi = 1 (perfect)
+            p.err[o] = cnt[tid];
+        }
+    }
+}
+
 // y = Q^H (r0 + sqrt(Pn/2) noise) of FBMC columns through the polyphase demodulator (DS.m:401-409 with Q^H r = Demodulation(r),
 // FBMC.m:287-302): column = (scheme slot g, SNR point, realization) as in k_gemm<GEMM_DEMOD>; one column per CTA, the received
 // samples, the folded symbols and the FFT ping-pong in two shared-memory buffers.

@@ -527,3 +527,35 @@ def test_mse_sums_match_oracle(ds_default):
     assert mse[:, -1, n_iter, :].mean() < mse[:, -1, 0, :].mean()
     ctx.set_mse_accumulation(False)
     ctx.close()
+
+
+def test_fused_perfect_twin_and_polyphase_pass_equal_the_gemm_chain():
+    """Three implementations of the perfect-CSI twin of the FBMC schemes give identical counters and the same data-symbol
+    estimates: (1) the fused kernel k_perfect_twin_fbmc (all iterations of a column in shared memory, polyphase modem),
+    (2) PERF units + k_perfect_fbmc per iteration (CHEST_NO_TWIN), (3) PERF units + the ring GEMMs (CHEST_CHAIN_GEMM)."""
+    from chest_b200.simulation import DoublySelectiveSimulation
+    B, seed = 37, 5
+    sim = DoublySelectiveSimulation(max_batch=B, seed=seed)
+    ctx = sim.ctx
+    keys = [(name, r, s) for name in ("aux", "cod", "ofdm") for r in (0, 16, B - 1) for s in (0, ctx.n_snr - 1)]
+
+    def run():
+        ctx.set_perfect_csi_mode("factored")                    # forces the unit lists to be rebuilt under the current knobs
+        err = ctx.run_batch(B, 4, None, seed=seed, first_rep=100)
+        return err, {k: ctx.get_state("xD_perf", *k) for k in keys}
+    err1, st1 = run()
+    os.environ["CHEST_NO_TWIN"] = "1"
+    try:
+        err2, st2 = run()
+        os.environ["CHEST_CHAIN_GEMM"] = "1"
+        ctx2 = DoublySelectiveSimulation(max_batch=B, seed=seed).ctx      # the probe result is cached per waveform: fresh context
+        err3 = ctx2.run_batch(B, 4, None, seed=seed, first_rep=100)
+        st3 = {k: ctx2.get_state("xD_perf", *k) for k in keys}
+        ctx2.close()
+    finally:
+        os.environ.pop("CHEST_NO_TWIN", None); os.environ.pop("CHEST_CHAIN_GEMM", None)
+    assert np.array_equal(err1, err2) and np.array_equal(err1, err3)
+    for k in keys:
+        scale = np.max(np.abs(st3[k]))
+        assert np.max(np.abs(st1[k] - st3[k])) < 1e-10 * scale and np.max(np.abs(st2[k] - st3[k])) < 1e-10 * scale, k
+    sim.close()
