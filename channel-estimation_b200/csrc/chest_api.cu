@@ -679,7 +679,10 @@ int build_ctas(Ctx* c, int n_rep) {
     for (int wfi = 0; wfi < 2; ++wfi) {                        // waveforms whose perfect-CSI twin runs as one fused kernel
         Waveform& w = c->wf[wfi];
         w.twin_on = false;
-        if (!w.set || !w.nsch || c->perf_mode != 1 || getenv("CHEST_NO_TWIN")) continue;
+        // measured on B200 (default geometry, B = 4096): 20.9 ms per step against 15.8 ms for PERF units + k_perfect_fbmc -- the
+        // long precoder rows (64 auxiliary rows x 204 entries) are re-read per column here, while k_ic_light shares them
+        // across 16 columns on DMMA tiles -- so the fused twin stays opt-in (CHEST_TWIN=1); parity-tested either way
+        if (!w.set || !w.nsch || c->perf_mode != 1 || !getenv("CHEST_TWIN")) continue;
         int rc = check_polyphase_pass(c, w); if (rc) return rc;
         bool ok = w.pf_state == 1;
         for (int q = 0; q < w.nsch && ok; ++q) ok = c->cst[c->sch[w.sch[q]].constellation].order <= 256;
@@ -1023,12 +1026,16 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         const ModemDev& md = w.modem;
         PerfTwinParams tp{};
         tp.md = md; tp.nsch = w.nsch; tp.n_snr = S; tp.n_rep = n_rep; tp.n_iter = n_iter; tp.T = c->T; tp.N = N; tp.K = w.K;
-        int n_data_max = 0;
-        for (int q = 0; q < w.nsch; ++q) { tp.sch[q] = ip.sch[w.sch[q]]; tp.scheme_id[q] = w.sch[q]; n_data_max = std::max(n_data_max, c->sch[w.sch[q]].n_data); }
+        int n_data_max = 0, n_long_max = 0;
+        for (int q = 0; q < w.nsch; ++q) {
+            tp.sch[q] = ip.sch[w.sch[q]]; tp.scheme_id[q] = w.sch[q];
+            n_data_max = std::max(n_data_max, c->sch[w.sch[q]].n_data); n_long_max = std::max(n_long_max, c->sch[w.sch[q]].n_long_rows);
+        }
+        tp.n_long_max = (n_long_max + 3) & ~3;
         for (int k = 0; k < 2; ++k) tp.cst[k] = c->cst[k].dev;
         tp.htrue = w.htrue.p; tp.h = c->h.p; tp.tap_delay = c->d_tap_delay.p; tp.err = err;
-        const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int)
-                            + (size_t)((n_data_max + 15) & ~15);
+        const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)((md.L + 3) & ~3) * sizeof(int)
+                            + (size_t)tp.n_long_max * sizeof(cplx) + (size_t)((w.K + 7) & ~7) * sizeof(unsigned short) + (size_t)((n_data_max + 15) & ~15);
         static size_t attr_smem = 0;
         if (smem > attr_smem) { CK(cudaFuncSetAttribute(k_perfect_twin_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
         k_perfect_twin_fbmc<<<n_rep * w.nsch * S, PERF_FBMC_THREADS, smem, st>>>(tp);

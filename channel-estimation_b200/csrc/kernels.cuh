@@ -2597,12 +2597,14 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
 //                    x = y_ic / h                                -> select / de-spread, decide, count
 // The twin needs nothing from the estimated-CSI path, so v and y_ic never touch HBM and the scalar kernel k_ic_light has no
 // perfect-CSI units left for this waveform.  Decisions, counters and the parity state (chest_get_state) follow k_ic_light.
+// Opt-in (CHEST_TWIN=1): on B200 it measured SLOWER than PERF units + k_perfect_fbmc (20.9 vs 15.8 ms per step at the default
+// geometry) because every column re-reads the long precoder rows that k_ic_light shares across 16 columns on DMMA tiles.
 struct PerfTwinParams {
     ModemDev md;
     SchemeDev sch[2];              // the schemes on this waveform, by slot
     ConstDev cst[2];
     int scheme_id[2];              // their global ids (index of the error counters)
-    int nsch, n_snr, n_rep, n_iter, T, N, K;
+    int nsch, n_snr, n_rep, n_iter, T, N, K, n_long_max;
     const cplx* htrue; const cplx* h; const int* tap_delay;
     uint32_t* err;
 };
@@ -2615,7 +2617,9 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
     cplx* tw = X1 + nx;
     double* filt = reinterpret_cast<double*>(tw + n);
     int* bins = reinterpret_cast<int*>(filt + md.Np);
-    uint8_t* zw = reinterpret_cast<uint8_t*>(bins + L);        // decided word per data symbol
+    cplx* vlong = reinterpret_cast<cplx*>(bins + ((L + 3) & ~3));   // v of the long precoder rows (auxiliary / spread positions)
+    unsigned short* lrmap = reinterpret_cast<unsigned short*>(vlong + p.n_long_max);   // row -> index into vlong
+    uint8_t* zw = reinterpret_cast<uint8_t*>(lrmap + ((K + 7) & ~7));                  // decided word per data symbol
     __shared__ unsigned int cnt[2];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int col = blockIdx.x, snr = col % p.n_snr, slot = (col / p.n_snr) % p.nsch, rep = col / (p.n_snr * p.nsch);
@@ -2633,14 +2637,13 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
     for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
     for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
     for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
+    for (int r = tid; r < sd.n_long_rows; r += nthr) lrmap[sd.long_rows[r]] = (unsigned short)r;
     // z[c] of the precoder input: transmitted pilot, or the symbol decided for data index c - P
     auto z_of = [&](int c) -> cplx { return c < P ? xP[c] : cd.symbol[zw[c - P]]; };
     auto v_of = [&](int i) -> cplx {                            // v[i] = sum_c C[i, c] z[c]
         const int c0 = sd.row_col0[i];
         if (c0 >= 0) return cmul(sd.row_val0[i], z_of(c0));
-        cplx acc = cmake(0.0, 0.0);
-        if (c0 == -2) for (int e = sd.c_rowptr[i]; e < sd.c_rowptr[i + 1]; ++e) cfma(acc, sd.c_val[e], z_of(sd.c_col[e]));
-        return acc;
+        return c0 == -2 ? vlong[lrmap[i]] : cmake(0.0, 0.0);    // long rows: summed once per iteration, one warp per row
     };
     for (int it = 0; it <= p.n_iter; ++it) {
         const bool last = it == p.n_iter;
@@ -2653,6 +2656,15 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         } else {
             if (L < n) for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0);
             __syncthreads();                                    // decided words of the previous iteration are complete
+            for (int r = tid >> 5; r < sd.n_long_rows; r += nthr >> 5) {
+                const int i = sd.long_rows[r];
+                cplx acc = cmake(0.0, 0.0);
+                for (int e = sd.c_rowptr[i] + (tid & 31); e < sd.c_rowptr[i + 1]; e += 32) cfma(acc, sd.c_val[e], z_of(sd.c_col[e]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
+                if ((tid & 31) == 0) vlong[r] = acc;
+            }
+            __syncthreads();
             for (int i = tid; i < K; i += nthr) {
                 const int k = i / L, l = i - k * L;
                 const cplx v = cmul(v_of(i), md.phase[i]);
