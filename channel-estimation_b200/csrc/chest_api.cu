@@ -66,6 +66,7 @@ struct Waveform {
     DevBuf<cplx> G, Q, Gt;
     DevBuf<cplx> Q1; DevBuf<double> Q2;                // three-multiplication planes of Q^H: (re, re - im), im; row stride Np
     DevBuf<cplx> Gt1; DevBuf<double> Gt2;              // planes of G (not conjugated), rows = samples: (re, re + im), -im; row stride Kp
+    bool det_on = false; DevBuf<uint8_t> zw_g; int zw_stride = 0;   // FBMC perfect-CSI columns equalised / detected by k_perfect_fbmc_det
     bool twin_on = false;                              // the perfect-CSI twin of this waveform runs in k_perfect_twin_fbmc (no PERF units)
     int pf_state = 0;                                  // polyphase perfect-CSI pass: 0 unchecked, 1 usable, -1 not (no modem description, mismatch, too large)
     DevBuf<int2> pf_groups; int pf_n_groups = 0;
@@ -506,12 +507,28 @@ cudaError_t launch_gemm_ring(Ctx* c, GemmRingParams& p, int tile) {
     return launch_gemm_ring_geo<2, 4, 4, BG, EPI>(c, p);
 }
 
-int stage_factored_perfect_csi(Ctx* c, int n_rep) {
+int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* err, const IcParams& ip) {
     const int N = c->N, Np = (N + 1) & ~1;
     static const bool legacy = getenv("CHEST_CHAIN_LEGACY") != nullptr;      // development: the block-barrier k_gemm<PLAIN> chain
     for (int wfi = 0; wfi < 2; ++wfi) {
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch || !w.f_cols) continue;
+        if (!legacy && w.det_on) {                                 // FBMC: polyphase modem + equalisation + detection + counters
+            const ModemDev& md = w.modem;
+            PerfDetParams dp{};
+            dp.md = md; dp.it = it; dp.n_iter = n_iter; dp.n_snr = c->S; dp.n_rep = n_rep; dp.nsch = w.nsch; dp.n_cols = w.f_cols;
+            dp.T = c->T; dp.N = N; dp.K = w.K; dp.zw_stride = w.zw_stride;
+            for (int q = 0; q < w.nsch; ++q) { dp.sch[q] = ip.sch[w.sch[q]]; dp.scheme_id[q] = w.sch[q]; }
+            for (int k = 0; k < 2; ++k) dp.cst[k] = c->cst[k].dev;
+            dp.voff = w.f_voff.p; dp.yoff = w.f_yoff.p; dp.rep = w.f_rep.p; dp.v_base = c->scratch.p;
+            dp.y = w.y.p; dp.htrue = w.htrue.p; dp.h = c->h.p; dp.tap_delay = c->d_tap_delay.p; dp.zw_g = w.zw_g.p; dp.err = err;
+            const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
+            k_perfect_fbmc_det<<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
+            c->launches++;
+            CK(cudaGetLastError());
+            continue;
+        }
+        if (it == 0) continue;                                      // (the one-tap stage of the other columns runs in k_ic_light)
         if (!legacy && w.pf_state == 1 && w.pf_n_groups > 0) {                             // FBMC: the polyphase modem instead of the GEMMs
             const ModemDev& md = w.modem;
             PerfFbmcParams pp{};
@@ -734,6 +751,7 @@ int build_ctas(Ctx* c, int n_rep) {
         const int S = c->S, nblk = (S + 7) / 8;
         for (int wfi = 0; wfi < 2; ++wfi) {
             Waveform& w = c->wf[wfi];
+            w.det_on = false;
             if (!w.set || !w.nsch || w.twin_on) { w.f_cols = 0; w.pf_n_groups = 0; continue; }
             const int nv = w.nsch * S;
             w.perf_nblk = nblk; w.f_cols = nv * n_rep;
@@ -760,6 +778,16 @@ int build_ctas(Ctx* c, int n_rep) {
                                     groups.push_back(make_int2(r * nv + slot * S + q, std::min(PERF_FBMC_CW, std::min(S, s0 + 8) - q)));
                 w.pf_n_groups = (int)groups.size();
                 if (!groups.empty()) CK(w.pf_groups.upload(groups, c->stream));
+                // one column per CTA: the same kernel also equalises, detects and counts (k_perfect_fbmc_det); k_ic_light then
+                // only precodes these columns.  CHEST_NO_PERF_DETECT keeps the two-kernel split (development / tests).
+                w.det_on = w.pf_state == 1 && PERF_FBMC_CW == 1 && !getenv("CHEST_NO_PERF_DETECT") && !getenv("CHEST_CHAIN_LEGACY");
+                if (w.det_on) {
+                    int nd = 0;
+                    for (int q = 0; q < w.nsch; ++q) nd = std::max(nd, c->sch[w.sch[q]].n_data);
+                    w.zw_stride = (nd + 15) & ~15;
+                    CK(w.zw_g.alloc((size_t)w.f_cols * w.zw_stride));
+                    CK(cudaFuncSetAttribute(k_perfect_fbmc_det, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                }
             }
             CK(w.f_s.alloc((size_t)w.f_cols * c->N)); CK(w.f_r.alloc((size_t)w.f_cols * c->N));
             {
@@ -1002,6 +1030,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     uint32_t* err = err_dev ? err_dev : c->err.p;
     CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
     ip.err = err;
+    for (int wfi = 0; wfi < 2; ++wfi) { ip.perf_zw[wfi] = c->wf[wfi].det_on ? c->wf[wfi].zw_g.p : nullptr; if (c->wf[wfi].det_on) ip.perf_zw_stride = c->wf[wfi].zw_stride; }
     ip.mse = nullptr;
     if (c->mse_on) {
         if (use_post) return fail(CHEST_ERR_STATE, "MSE accumulation is implemented in k_ic_light (unset CHEST_LIGHT=post)");
@@ -1042,9 +1071,10 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         c->launches++;
         CK(cudaGetLastError());
     }
-    if (c->profiling) CK(cudaEventRecord(c->ev_tw[1], st));
     for (int it = 0; it <= n_iter; ++it) {
         ip.it = it;
+        if (it == 0 && c->perf_mode == 1) { rc = stage_factored_perfect_csi(c, n_rep, 0, n_iter, err, ip); if (rc) return rc; }   // one-tap stage of the detected columns
+        if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev_tw[1], st));
         if (it > 0) {                                              // phase B of iteration it
             ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
             if (c->precision == 1) {
@@ -1075,7 +1105,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
             c->launches++;
             ip.trace = nullptr;
             if (c->profiling) CK(cudaEventRecord(c->ev_mn[it], st));
-            if (c->perf_mode == 1) { rc = stage_factored_perfect_csi(c, n_rep); if (rc) return rc; }
+            if (c->perf_mode == 1) { rc = stage_factored_perfect_csi(c, n_rep, it, n_iter, err, ip); if (rc) return rc; }
             if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
         }
         // phases C, D, E of iteration it (+ phase A of iteration it+1)
@@ -1133,7 +1163,7 @@ int finish_pipeline(Ctx* c) {
                 cudaEventElapsedTime(&t, c->ev_ic[2 * it - 1], c->ev_mn[it]); c->kernel_ms[2] += t;
                 cudaEventElapsedTime(&t, c->ev_mn[it], c->ev_ic[2 * it]); c->kernel_ms[4] += t;
             }
-            cudaEventElapsedTime(&t, it > 0 ? c->ev_ic[2 * it] : c->ev[4], c->ev_ic[2 * it + 1]);
+            cudaEventElapsedTime(&t, it > 0 ? c->ev_ic[2 * it] : c->ev_tw[1], c->ev_ic[2 * it + 1]);
             c->kernel_ms[3] += t;
         }
         { float t = 0; cudaEventElapsedTime(&t, c->ev_tw[0], c->ev_tw[1]); c->kernel_ms[4] += t; }      // fused perfect-CSI twin

@@ -1066,6 +1066,9 @@ struct IcParams {
     int n_units_main;          // units k_ic_main processes (all of them, or only the EST units in factored mode)
     unsigned long long* trace; // development: per CTA {smid, t0, t_pre, t_main_own, t_main_all, t_end, B busy ns, units}
     double* mse;               // optional: sum_i |h_est[i] - h[i]|^2 per [rep][snr][it][scheme] (estimated-CSI columns); nullptr = off
+    // perfect-CSI columns of a waveform whose equalisation / detection / counting is done by k_perfect_fbmc_det: the decided words
+    // [column][perf_zw_stride] (column = rep * nsch * n_snr + slot * n_snr + snr); k_ic_light then only precodes (phase A)
+    const uint8_t* perf_zw[2]; int perf_zw_stride;
 };
 
 // Column -> (scheme, SNR point, realization); false for an unused slot.  PERF units keep each 8-column half
@@ -1629,8 +1632,22 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
             const cplx* yp = sh.ycolp[c];
             return yp ? yp[i] : cmake(1.0, 0.0);
         };
+        const bool detected = csi == 1 && p.perf_zw[wf] != nullptr;      // equalised, decided and counted by k_perfect_fbmc_det
+        if (detected && !next_pre) continue;
         bool any_despread = false;
         for (int c = 0; c < cta.n_cols; ++c) any_despread |= p.sch[sh.c_scheme[c]].detect_mode == 1;
+        if (detected) {
+            any_despread = false;
+            const int nv = p.wf_nscheme[wf] * p.n_snr;
+            for (int idx = tid; idx < p.K_max * NC; idx += nthr) {
+                const int c = idx % NC, d = idx / NC;
+                if (sh.c_rep[c] < 0) continue;
+                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
+                if (d >= sd.n_data) continue;
+                const int64_t col = (int64_t)sh.c_rep[c] * nv + (c >> 3) * p.n_snr + sh.c_snr[c];
+                zw[d * NC + c] = p.perf_zw[wf][col * p.perf_zw_stride + d];
+            }
+        }
         {   // transmitted pilots of the columns (phase C divides by them, phase A re-inserts them)
             const int Pw = p.sch[p.wf_scheme[wf][0]].P;
             for (int idx = tid; idx < Pw * NC; idx += nthr) {
@@ -1740,7 +1757,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                             }
                         }
                 }
-            } else {
+            } else if (!detected) {
                 const int c = tid % NC;
                 const bool okc = sh.c_rep[c] >= 0;
                 const SchemeDev& sd = p.sch[sh.c_scheme[c]];
@@ -1831,7 +1848,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
             if (e_edge) atomicAdd(&sh.cnt[c][1], e_edge);
             __syncthreads();                                   // readers of vbuf done, decided words complete
         }
-        if (tid < 2 * NC) {
+        if (tid < 2 * NC && !detected) {
             int cc = tid >> 1, e = tid & 1;
             if (cc < cta.n_cols && sh.c_rep[cc] >= 0) {
                 int64_t o = ((((int64_t)sh.c_rep[cc] * p.n_snr + sh.c_snr[cc]) * (p.n_iter + 1) + it) * 3 + sh.c_scheme[cc]) * 4 + csi * 2 + e;
@@ -2586,6 +2603,136 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         const cplx hvv = cmul(hv, vv);
         p.y_base[o] = cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y);
     }
+}
+
+// k_perfect_fbmc for one column per CTA with the rest of the perfect-CSI iteration behind it: instead of writing y_ic the
+// epilogue equalises (x = y_ic / h, DS.m:545-548), a block barrier later the data symbols are selected / de-spread, decided
+// and counted exactly as k_ic_light does (DS.m:549-561), and the decided words go to a byte array from which k_ic_light
+// builds the next v = C z.  it = 0 is the one-tap stage (x = y / h, DS.m:450-466): no modem chain.
+struct PerfDetParams {
+    ModemDev md;
+    SchemeDev sch[2]; ConstDev cst[2]; int scheme_id[2];
+    int it, n_iter, n_snr, n_rep, nsch, n_cols, T, N, K, zw_stride;
+    const int64_t* voff; const int64_t* yoff; const int* rep;
+    const cplx* v_base; const cplx* y; const cplx* htrue; const cplx* h; const int* tap_delay;
+    uint8_t* zw_g; uint32_t* err;
+};
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfect_fbmc_det(PerfDetParams p) {
+    extern __shared__ __align__(16) cplx pf_smem[];
+    const ModemDev& md = p.md;
+    const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
+    cplx* X0 = pf_smem;
+    cplx* X1 = X0 + nx;
+    cplx* tw = X1 + nx;
+    double* filt = reinterpret_cast<double*>(tw + n);
+    int* bins = reinterpret_cast<int*>(filt + md.Np);
+    __shared__ unsigned int cnt[2];
+    const int tid = threadIdx.x, nthr = blockDim.x, col = blockIdx.x;
+    const int snr = col % p.n_snr, slot = (col / p.n_snr) % p.nsch, rep = p.rep[col];
+    const SchemeDev& sd = p.sch[slot];
+    const ConstDev& cd = p.cst[sd.constellation];
+    const cplx* ycol = p.y + p.yoff[col];
+    const cplx* ht = p.htrue + (int64_t)rep * K;
+    if (tid < 2) cnt[tid] = 0;
+    cplx* Xe;
+    if (p.it == 0) {
+        for (int i = tid; i < K; i += nthr) X1[i] = cdiv_fast(ycol[i], ht[i]);
+        Xe = X1;
+    } else {
+        for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
+        for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+        for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
+        if (L < n) for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0);
+        __syncthreads();
+        const cplx* vcol = p.v_base + p.voff[col];
+        for (int i = tid; i < K; i += nthr) {
+            const int k = i / L, l = i - k * L;
+            const cplx v = cmul(vcol[(int64_t)i * NC_MAX], md.phase[i]);
+            X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
+        }
+        __syncthreads();
+        cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
+        cplx* Xo = (Xz == X0) ? X1 : X0;
+        const double inv_n = 1.0 / n;
+        for (int nn = tid; nn < N; nn += nthr) {                // overlap-add
+            int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+            const int k_hi = min(Ksym - 1, nn / TS);
+            cplx acc = cmake(0.0, 0.0);
+            int tap = nn - k_lo * TS, mm = tap % n;
+            const cplx* zc = Xz + k_lo * n;
+            for (int k = k_lo; k <= k_hi; ++k) {
+                if (tap >= 0 && tap < md.Np) {
+                    const cplx z = zc[mm];
+                    const double pf = filt[tap];
+                    acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+                }
+                tap -= TS; mm -= TS; if (mm < 0) mm += n;
+                zc += n;
+            }
+            Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
+        }
+        __syncthreads();
+        const cplx* hr = p.h + (int64_t)rep * p.T * N;
+        for (int nn = tid; nn < N; nn += nthr) {                // r = H s
+            cplx acc = cmake(0.0, 0.0);
+            for (int t = 0; t < p.T; ++t) {
+                const int d = p.tap_delay[t];
+                if (nn >= d) cfma(acc, hr[(int64_t)t * N + nn], Xo[nn - d]);
+            }
+            Xz[nn] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nx; idx += nthr) {            // fold
+            const int k = idx / n, m = idx - k * n;
+            const cplx* seg = Xz + k * TS + m;
+            cplx acc = cmake(0.0, 0.0);
+            for (int o = 0; o < md.O; ++o) {
+                const double pf = filt[o * n + m];
+                const cplx v = seg[o * n];
+                acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+            }
+            Xo[idx] = acc;
+        }
+        __syncthreads();
+        cplx* Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, Ksym);
+        Xe = (Y == X0) ? X1 : X0;
+        for (int i = tid; i < K; i += nthr) {                   // y_ic = y - U + h v, x = y_ic / h
+            const int k = i / L, l = i - k * L;
+            const cplx u0 = cmulc(md.phase[i], Y[k * n + bins[l]]);
+            const cplx hv = ht[i], yv = ycol[i];
+            const cplx hvv = cmul(hv, vcol[(int64_t)i * NC_MAX]);
+            Xe[i] = cdiv_fast(cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y), hv);
+        }
+    }
+    __syncthreads();
+    const int P = sd.P, n_data = sd.n_data;
+    const bool select = sd.detect_mode != 1, last = p.it == p.n_iter;
+    const uint32_t* txw = sd.txword + (int64_t)rep * n_data;
+    const int64_t colbase = ((int64_t)snr * p.n_rep + rep) * n_data;
+    uint8_t* zw = p.zw_g + (int64_t)col * p.zw_stride;
+    unsigned e_all = 0, e_edge = 0;
+    for (int d = tid; d < n_data; d += nthr) {
+        cplx xd;
+        if (select) {
+            const cplx xh = Xe[sd.data_pos[d]];
+            xd = cmake(xh.x * sd.inv_sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y * sd.inv_sqrt_dpr);
+        } else {
+            cplx acc = cmake(0.0, 0.0);
+            for (int e = sd.ct_colptr[P + d]; e < sd.ct_colptr[P + d + 1]; ++e) {
+                const cplx t = cmulc(sd.ct_val[e], Xe[sd.ct_row[e]]);
+                acc.x += t.x; acc.y += t.y;
+            }
+            xd = cmake(acc.x * sd.inv_dpr, 0.0);
+        }
+        const int word = ic_decide(cd, xd, txw[d], sd.edge_mask[d], e_all, e_edge);
+        if (last) sd.xD[1][colbase + d] = xd;
+        else zw[d] = (uint8_t)word;
+    }
+    if (e_all) atomicAdd(&cnt[0], e_all);
+    if (e_edge) atomicAdd(&cnt[1], e_edge);
+    __syncthreads();
+    if (tid < 2)
+        p.err[((((int64_t)rep * p.n_snr + snr) * (p.n_iter + 1) + p.it) * 3 + p.scheme_id[slot]) * 4 + 2 + tid] = cnt[tid];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -529,35 +529,38 @@ def test_mse_sums_match_oracle(ds_default):
     ctx.close()
 
 
-def test_fused_perfect_twin_and_polyphase_pass_equal_the_gemm_chain():
-    """Three implementations of the perfect-CSI twin of the FBMC schemes give identical counters and the same data-symbol
-    estimates: (1) the fused kernel k_perfect_twin_fbmc (all iterations of a column in shared memory, polyphase modem),
-    (2) PERF units + k_perfect_fbmc per iteration (the default), (3) PERF units + the ring GEMMs (CHEST_CHAIN_GEMM).
-    (1) is opt-in (CHEST_TWIN=1): it measured slower than (2) on B200, see chest_api.cu build_ctas."""
+def test_perfect_csi_pass_variants_agree():
+    """Four implementations of the perfect-CSI twin of the FBMC schemes give identical counters and the same data-symbol
+    estimates: (1) the default -- k_perfect_fbmc_det (polyphase modem + equalisation + detection + counters per column) with
+    k_ic_light only precoding; (2) k_perfect_fbmc + PERF units in k_ic_light (CHEST_NO_PERF_DETECT); (3) the fused kernel
+    k_perfect_twin_fbmc over all iterations (CHEST_TWIN: opt-in, measured slower); (4) PERF units + the ring GEMMs
+    (CHEST_CHAIN_GEMM: what a context without a modem description runs)."""
     from chest_b200.simulation import DoublySelectiveSimulation
     B, seed = 37, 5
     sim = DoublySelectiveSimulation(max_batch=B, seed=seed)
     ctx = sim.ctx
     keys = [(name, r, s) for name in ("aux", "cod", "ofdm") for r in (0, 16, B - 1) for s in (0, ctx.n_snr - 1)]
 
-    def run():
-        ctx.set_perfect_csi_mode("factored")                    # forces the unit lists to be rebuilt under the current knobs
-        err = ctx.run_batch(B, 4, None, seed=seed, first_rep=100)
-        return err, {k: ctx.get_state("xD_perf", *k) for k in keys}
-    os.environ["CHEST_TWIN"] = "1"
+    def run(c=ctx):
+        c.set_perfect_csi_mode("factored")                      # forces the unit lists to be rebuilt under the current knobs
+        err = c.run_batch(B, 4, None, seed=seed, first_rep=100)
+        return err, {k: c.get_state("xD_perf", *k) for k in keys}
+    results = [run()]
     try:
-        err1, st1 = run()
-        os.environ.pop("CHEST_TWIN")
-        err2, st2 = run()
+        for knob in ("CHEST_NO_PERF_DETECT", "CHEST_TWIN"):
+            os.environ[knob] = "1"
+            results.append(run())
+            os.environ.pop(knob)
         os.environ["CHEST_CHAIN_GEMM"] = "1"
-        ctx2 = DoublySelectiveSimulation(max_batch=B, seed=seed).ctx      # the probe result is cached per waveform: fresh context
-        err3 = ctx2.run_batch(B, 4, None, seed=seed, first_rep=100)
-        st3 = {k: ctx2.get_state("xD_perf", *k) for k in keys}
-        ctx2.close()
+        sim2 = DoublySelectiveSimulation(max_batch=B, seed=seed)          # the probe result is cached per waveform: fresh context
+        results.append(run(sim2.ctx))
+        sim2.close()
     finally:
-        os.environ.pop("CHEST_TWIN", None); os.environ.pop("CHEST_CHAIN_GEMM", None)
-    assert np.array_equal(err1, err2) and np.array_equal(err1, err3)
-    for k in keys:
-        scale = np.max(np.abs(st3[k]))
-        assert np.max(np.abs(st1[k] - st3[k])) < 1e-10 * scale and np.max(np.abs(st2[k] - st3[k])) < 1e-10 * scale, k
+        for knob in ("CHEST_NO_PERF_DETECT", "CHEST_TWIN", "CHEST_CHAIN_GEMM"):
+            os.environ.pop(knob, None)
+    err_ref, st_ref = results[-1]
+    for q, (err, st) in enumerate(results[:-1]):
+        assert np.array_equal(err, err_ref), q
+        for k in keys:
+            assert np.max(np.abs(st[k] - st_ref[k])) < 1e-10 * np.max(np.abs(st_ref[k])), (q, k)
     sim.close()
