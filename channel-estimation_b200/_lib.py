@@ -83,6 +83,10 @@ SIGNATURES = {
     "chest_get_mse": (c_int, [c_u64, vp]),
     "chest_set_precision": (c_int, [c_u64, c_int]),
     "chest_precision_info": (c_int, [c_u64, C.POINTER(c_int), p_d, p_i64]),
+    "chest_set_estimator_mode": (c_int, [c_u64, c_int]),
+    "chest_set_pseudo_channels": (c_int, [c_u64, c_int, c_int, vp, C.c_double]),
+    "chest_set_estimator_factors": (c_int, [c_u64, c_int, c_int, c_int, vp, C.c_double]),
+    "chest_estimator_info": (c_int, [c_u64, c_int, C.POINTER(c_int), C.POINTER(c_int), p_d, p_d, p_f]),
     "chest_unit_count": (c_int, [c_u64, C.POINTER(c_int)]),
     "chest_prefetch_draws": (c_int, [c_u64, c_int, C.POINTER(ChestDraws), C.POINTER(ChestDraws)]),
     "chest_launch_count": (c_i64, [c_u64]),

@@ -441,6 +441,33 @@ class DeviceContext:
         self._check(self.lib.chest_precision_info(self._h, C.byref(m), C.byref(f), C.byref(b)))
         return ("fp64", "split_bf16")[m.value], f.value, b.value
 
+    def set_estimator_mode(self, mode):
+        """Form of the estimated-CSI cancellation (chest_b200.h): 'auto' (default: the factored form D_est = Q' H_est G only where
+        it equals the thresholded W to rounding AND is cheaper), 'tiles' (always the thresholded W), 'factored' (every scheme
+        with factors: the stated-tolerance mode, D_est within the removed 1e-8 entries of the reference's), 'factored_exact' (the
+        factored form wherever it equals the thresholded W to rounding, i.e. CP-OFDM, whatever it costs)."""
+        self._check(self.lib.chest_set_estimator_mode(self._h, {"auto": 0, "tiles": 1, "factored": 2, "factored_exact": 3}[mode]))
+
+    def set_pseudo_channels(self, wf, M, removed_max=np.inf):
+        """M[p, tap, n] = M_p(n, n - delay_tap): the pseudo-channels of the pilots (DS.m:260), taps = non-zero PDP entries."""
+        M = np.ascontiguousarray(M, dtype=np.complex128)
+        rm = 1e300 if not np.isfinite(removed_max) else float(removed_max)
+        self._check(self.lib.chest_set_pseudo_channels(self._h, WF_ID[wf], M.shape[0], _ptr(M), rm))
+
+    def set_estimator_factors(self, name, variant, R_inv, removed_max=np.inf):
+        """pinv(R_hP_est) per SNR point (n_snr x P x P), as chest_build_mmse takes it."""
+        Ri = np.ascontiguousarray(np.transpose(np.asarray(R_inv, dtype=np.complex128), (0, 2, 1)))     # column-major P x P per SNR point
+        rm = 1e300 if not np.isfinite(removed_max) else float(removed_max)
+        self._check(self.lib.chest_set_estimator_factors(self._h, SCHEME_ID[name], variant, Ri.shape[0], _ptr(Ri), rm))
+
+    def estimator_info(self, name):
+        """dict(mode, factored, removed_r, removed_w, ms): whether the scheme's estimated-CSI cancellation ran factored in the
+        last batch, the largest magnitudes the 1e-8 thresholds removed at setup, device ms of the factored pass (profiling)."""
+        m, f, rr, rw, ms = C.c_int(0), C.c_int(0), C.c_double(0), C.c_double(0), C.c_float(0)
+        self._check(self.lib.chest_estimator_info(self._h, SCHEME_ID[name], C.byref(m), C.byref(f), C.byref(rr), C.byref(rw), C.byref(ms)))
+        return dict(mode=("auto", "tiles", "factored", "factored_exact")[m.value], factored=bool(f.value), removed_r=rr.value, removed_w=rw.value,
+                    ms=ms.value)
+
     def kernel_times(self):
         """Device ms of k_apply_hg, k_gemm_d, k_ic_main (sum), k_ic_light (sum) in the last profiled batch."""
         out = (C.c_float * 10)()

@@ -93,6 +93,11 @@ struct Waveform {
     int d_alloc_batch = 0;      // batch size D / HG1 / HG2 are allocated for (0: not yet)
     // device-side setup (chest_setup_correlations): thresholded R_Dij_hP of all pilots, row-tile-major like D
     DevBuf<cplx> Rsup; int rsup_P = 0; double rsup_thr = 0;
+    // factored estimated-CSI cancellation (k_est_channel / k_est_factored): the pseudo-channels M_q of the pilots [P][T][N] kept from
+    // chest_setup_correlations, whether any wrapped (corner) entry is non-zero, the largest |R_Dij_hP| entry the threshold removed,
+    // and the EST units of this waveform's factored schemes
+    DevBuf<cplx> Mq; int mq_P = 0; bool mq_corner = false; double rsup_zeroed_max = 0;
+    DevBuf<int> ef_units; int ef_n_units = 0;
     DevBuf<int> g_lo_d, g_hi_d;
     int tile = 64;              // CTA tile size of the GEMMs on this waveform (48 or 64)
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
@@ -112,6 +117,7 @@ struct MmseVariant {
     DevBuf<cplx> diag_frag;        // [snr][rt][pq][32 lanes]
     DevBuf<WTiles> table;
     int64_t nnz_offdiag_pairs = 0;
+    DevBuf<cplx> rinv; bool rinv_set = false; double w_zeroed_max = 0;   // pinv(R_hP_est) [snr][P x P] of chest_build_mmse; largest |W| entry its threshold removed
     // split-BF16 tensor-core mode (chest_set_precision): active columns per 128-row tile and the operand images
     DevBuf<int> tc_jlist, tc_jptr; DevBuf<uint8_t> tc_img; int tc_entries = 0, tc_row_tiles = 0; bool tc_packed = false;
     std::vector<int> tc_jptr_h;
@@ -169,6 +175,11 @@ struct Ctx {
     double tc_mma_flops = 0;     // dense BF16 flops one launch of k_ic_est_tc executes (roofline of the reduced-precision mode)
     int perf_mode = 1;           // 1 (default): factored, y - Q^H H (G v) + h v, D never formed; 0: D materialised (K2) and applied densely
     int n_est_units = 0;
+    // estimated-CSI cancellation: 0 auto (factored form only for schemes where it equals the tile form of W to rounding), 1 tiles
+    // (always the thresholded W), 2 factored (every scheme that has the factors: the stated-tolerance mode, chest_set_estimator_mode)
+    int est_mode = 0; bool est_fact[3] = {false, false, false};
+    DevBuf<cplx> hest; DevBuf<unsigned long long> zmax;
+    cudaEvent_t ev_ef[18] = {}; float est_fact_ms = 0;
     cudaStream_t copy_stream = nullptr;
     DevBuf<uint32_t> err;
     DevBuf<cplx> scratch, tmp_a, tmp_b;
@@ -442,9 +453,10 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
     if (getenv("CHEST_CHAIN_GEMM")) return CHEST_OK;            // development: force the GEMM chain
     const ModemDev& md = w.modem;
     const int N = c->N, K = w.K;
-    if (!w.modem_set || !w.set || md.kind != 0 || md.L * md.Ksym != K || md.N != N || md.time_spacing * 2 != md.nfft) return CHEST_OK;
-    const size_t nx = (size_t)md.Ksym * md.nfft;
-    if ((size_t)N > nx) return CHEST_OK;
+    if (!w.modem_set || !w.set || md.L * md.Ksym != K || md.N != N) return CHEST_OK;
+    if (md.kind == 0 && md.time_spacing * 2 != md.nfft) return CHEST_OK;
+    const size_t nx = std::max((size_t)md.Ksym * md.nfft, md.kind == 0 ? (size_t)0 : (size_t)N);
+    if (md.kind == 0 && (size_t)N > nx) return CHEST_OK;
     for (int q = 0; q < md.plan.n_stage; ++q) if (md.plan.radix[q] > 7) return CHEST_OK;     // the batched FFT carries radices 2, 3, 4, 5, 7
     const size_t smem = ((size_t)2 * PERF_FBMC_CW * nx + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
     if (smem > 200 * 1024) return CHEST_OK;
@@ -472,9 +484,15 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
         }
     }
     if (dev <= 1e-12 * mag) {
-        w.pf_state = 1;
-        CK(cudaFuncSetAttribute(k_perfect_fbmc<PERF_FBMC_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_demod_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        w.pf_state = md.kind == 0 ? 1 : 2;                      // 2: CP-OFDM -- the one-column kernels (k_perfect_fbmc_det, k_demod_fbmc) only
+        static size_t attr_smem = 0;                            // the attribute is per kernel: keep the largest need seen
+        if (smem > attr_smem) {
+            attr_smem = smem;
+            CK(cudaFuncSetAttribute(k_perfect_fbmc<PERF_FBMC_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_demod_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_perfect_fbmc_det, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_est_factored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
     }
     return CHEST_OK;
 }
@@ -507,6 +525,59 @@ cudaError_t launch_gemm_ring(Ctx* c, GemmRingParams& p, int tile) {
     return launch_gemm_ring_geo<2, 4, 4, BG, EPI>(c, p);
 }
 
+// Can the estimated-CSI cancellation of scheme si run in factored form (kernels.cuh, k_est_factored)?  Needs the factored perfect-CSI
+// mode (its scratch layout), the factors kept by the device-side setup (pseudo-channels of the pilots, pinv(R_hP_est) of both
+// variants), no wrapped pseudo-channel entries, a modem description that reproduces G / Q and fits one column per CTA -- and either
+// the explicit stated-tolerance mode or the proof that the thresholds of DS.m:263-264, 287-289 removed nothing but rounding noise.
+int est_factored_usable(Ctx* c, int si, bool& on) {
+    on = false;
+    Scheme& s = c->sch[si];
+    if (!s.set || c->perf_mode != 1 || c->est_mode == 1 || getenv("CHEST_LIGHT")) return CHEST_OK;
+    Waveform& w = c->wf[s.waveform];
+    if (!w.Mq.p || w.mq_P != s.P || w.mq_corner || !s.mm[0].rinv_set || !s.mm[1].rinv_set || !s.mm[0].set || !s.mm[1].set) return CHEST_OK;
+    int rc = check_polyphase_pass(c, w); if (rc) return rc;
+    if (w.pf_state < 1 || PERF_FBMC_CW != 1) return CHEST_OK;
+    const double removed = std::max(w.rsup_zeroed_max, std::max(s.mm[0].w_zeroed_max, s.mm[1].w_zeroed_max));
+    // auto: only where it is also cheaper.  Measured break-even on B200: the modem chain costs 30-50 ns per column, the tile form
+    // 8 P nnz flops at ~38 TFLOP/s -- CP-OFDM at the default geometry (1.0 MFLOP per column) is faster on the tiles.
+    const double tile_flops = 8.0 * s.P * (double)std::max(s.mm[0].nnz_offdiag_pairs, s.mm[1].nnz_offdiag_pairs);
+    on = c->est_mode == 2 || (removed < 1e-13 && (c->est_mode == 3 || tile_flops >= 3e6));
+    return CHEST_OK;
+}
+
+// Phase B of iteration it for the factored schemes: H-hat of every column, then the modem chain with it.
+int stage_factored_estimated_csi(Ctx* c, int n_rep, int it, int n_iter, const IcParams& ip) {
+    const int N = c->N, var_prev = (it - 1 == 0 || (it - 1) <= n_iter / 2) ? 0 : 1;      // the D-hat estimated in iteration it-1 (DS.m:475,492)
+    for (int wfi = 0; wfi < 2; ++wfi) {
+        Waveform& w = c->wf[wfi];
+        if (!w.ef_n_units) continue;
+        EstChanParams ep{};
+        ep.units = w.ef_units.p; ep.ctas = c->ctas.p; ep.Mq = w.Mq.p; ep.hest = c->hest.p; ep.n_rep = n_rep; ep.TN = c->T * N;
+        int Pmax = 1;
+        for (int si = 0; si < 3; ++si) {
+            Scheme& s = c->sch[si];
+            if (!s.set || !c->est_fact[si]) continue;
+            ep.hP[si] = ip.sch[si].hP; ep.rinv[si] = s.mm[var_prev].rinv.p; ep.P[si] = s.P; Pmax = std::max(Pmax, s.P);
+        }
+        const size_t smem_c = (size_t)2 * Pmax * NC_MAX * sizeof(cplx);
+        if (smem_c > 48 * 1024) return fail(CHEST_ERR_STATE, "factored estimator: more than 96 pilots per scheme");
+        k_est_channel<<<w.ef_n_units, EST_CHAN_THREADS, smem_c, c->stream>>>(ep);
+        c->launches++;
+        CK(cudaGetLastError());
+        const ModemDev& md = w.modem;
+        EstFactParams fp{};
+        fp.md = md; fp.units = w.ef_units.p; fp.ctas = c->ctas.p; fp.K_max = c->K_max; fp.n_rep = n_rep; fp.T = c->T; fp.N = N; fp.K = w.K;
+        for (int si = 0; si < 3; ++si) fp.y[si] = ip.sch[si].y;
+        fp.hest = c->hest.p; fp.tap_delay = c->d_tap_delay.p; fp.scratch = c->scratch.p;
+        const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
+        const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
+        k_est_factored<<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    return CHEST_OK;
+}
+
 int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* err, const IcParams& ip) {
     const int N = c->N, Np = (N + 1) & ~1;
     static const bool legacy = getenv("CHEST_CHAIN_LEGACY") != nullptr;      // development: the block-barrier k_gemm<PLAIN> chain
@@ -522,7 +593,8 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* 
             for (int k = 0; k < 2; ++k) dp.cst[k] = c->cst[k].dev;
             dp.voff = w.f_voff.p; dp.yoff = w.f_yoff.p; dp.rep = w.f_rep.p; dp.v_base = c->scratch.p;
             dp.y = w.y.p; dp.htrue = w.htrue.p; dp.h = c->h.p; dp.tap_delay = c->d_tap_delay.p; dp.zw_g = w.zw_g.p; dp.err = err;
-            const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
+            const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
+            const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
             k_perfect_fbmc_det<<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
             c->launches++;
             CK(cudaGetLastError());
@@ -725,9 +797,28 @@ int build_ctas(Ctx* c, int n_rep) {
         if (!strcmp(dbg, "est_fbmc")) { p1.clear(); p2.clear(); e2.clear(); }
         if (!strcmp(dbg, "perf_fbmc")) { e1.clear(); e2.clear(); p2.clear(); }
     }
+    for (int si = 0; si < 3; ++si) c->est_fact[si] = false;
+    for (auto& w : c->wf) w.ef_n_units = 0;
     if (c->perf_mode == 1) {                                   // factored mode: k_ic_main runs the EST units only (listed first)
-        v.insert(v.end(), e1.begin(), e1.end()); v.insert(v.end(), e2.begin(), e2.end());
+        // schemes whose estimated-CSI cancellation runs in factored form (k_est_channel + k_est_factored) come after the tile-form
+        // EST units: k_ic_main stops at n_est_units, k_ic_light walks all of them
+        std::vector<IcCta> ef;
+        std::vector<int> ef_list[2];
+        for (int si = 0; si < 3; ++si) {
+            int rc = est_factored_usable(c, si, c->est_fact[si]); if (rc) return rc;
+        }
+        for (auto* lst : {&e1, &e2})
+            for (const IcCta& u : *lst) (c->est_fact[u.scheme_or_wf] ? ef : v).push_back(u);
         c->n_est_units = (int)v.size();
+        for (const IcCta& u : ef) { ef_list[c->sch[u.scheme_or_wf].waveform].push_back((int)v.size()); v.push_back(u); }
+        size_t ef_cols = 0;
+        for (int wfi = 0; wfi < 2; ++wfi) {
+            Waveform& w = c->wf[wfi];
+            w.ef_n_units = (int)ef_list[wfi].size();
+            if (w.ef_n_units) CK(w.ef_units.upload(ef_list[wfi], c->stream));
+            ef_cols = std::max(ef_cols, (size_t)w.ef_n_units * NC_MAX);
+        }
+        if (ef_cols) CK(c->hest.alloc(ef_cols * c->T * c->N));
         c->wf[CHEST_WF_FBMC].perf_base = (int)v.size(); v.insert(v.end(), p1.begin(), p1.end());
         c->wf[CHEST_WF_OFDM].perf_base = (int)v.size(); v.insert(v.end(), p2.begin(), p2.end());
     } else if (getenv("CHEST_IC_WEAVE")) {                     // development: interleave compute- and memory-heavy units
@@ -742,7 +833,7 @@ int build_ctas(Ctx* c, int n_rep) {
     if (c->precision == 1) {
         if (c->perf_mode != 1) return fail(CHEST_ERR_STATE, "the split-BF16 mode runs with the factored perfect-CSI pass (CHEST_PERFECT_FACTORED)");
         int rc = ensure_tc_pack(c); if (rc) return rc;
-        rc = build_tc_items(c, v, c->n_est_units); if (rc) return rc;
+        if (c->n_est_units > 0) { rc = build_tc_items(c, v, c->n_est_units); if (rc) return rc; }
     }
     CK(c->ctas.upload(v, c->stream));
     CK(c->scratch.alloc((size_t)c->n_ctas * 3 * c->K_max * NC_MAX));
@@ -780,13 +871,12 @@ int build_ctas(Ctx* c, int n_rep) {
                 if (!groups.empty()) CK(w.pf_groups.upload(groups, c->stream));
                 // one column per CTA: the same kernel also equalises, detects and counts (k_perfect_fbmc_det); k_ic_light then
                 // only precodes these columns.  CHEST_NO_PERF_DETECT keeps the two-kernel split (development / tests).
-                w.det_on = w.pf_state == 1 && PERF_FBMC_CW == 1 && !getenv("CHEST_NO_PERF_DETECT") && !getenv("CHEST_CHAIN_LEGACY");
+                w.det_on = w.pf_state >= 1 && PERF_FBMC_CW == 1 && !getenv("CHEST_NO_PERF_DETECT") && !getenv("CHEST_CHAIN_LEGACY");
                 if (w.det_on) {
                     int nd = 0;
                     for (int q = 0; q < w.nsch; ++q) nd = std::max(nd, c->sch[w.sch[q]].n_data);
                     w.zw_stride = (nd + 15) & ~15;
                     CK(w.zw_g.alloc((size_t)w.f_cols * w.zw_stride));
-                    CK(cudaFuncSetAttribute(k_perfect_fbmc_det, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 }
             }
             CK(w.f_s.alloc((size_t)w.f_cols * c->N)); CK(w.f_r.alloc((size_t)w.f_cols * c->N));
@@ -803,6 +893,10 @@ int build_ctas(Ctx* c, int n_rep) {
     }
     CK(cudaStreamSynchronize(c->stream));
     c->ctas_for_batch = n_rep;
+    if (getenv("CHEST_VERBOSE"))
+        fprintf(stderr, "chest: units %d (tile-form EST %d), polyphase state FBMC %d OFDM %d, detect-in-chain %d %d, factored estimator aux %d cod %d ofdm %d\n",
+                c->n_ctas, c->n_est_units, c->wf[0].pf_state, c->wf[1].pf_state, (int)c->wf[0].det_on, (int)c->wf[1].det_on,
+                (int)c->est_fact[0], (int)c->est_fact[1], (int)c->est_fact[2]);
     return CHEST_OK;
 }
 
@@ -933,12 +1027,13 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         Waveform& w = c->wf[wfi];
         if (!w.set || !w.nsch) continue;
         { rc = check_polyphase_pass(c, w); if (rc) return rc; }
-        if (w.pf_state == 1 && !getenv("CHEST_CHAIN_LEGACY")) {          // FBMC: the polyphase demodulator instead of the GEMM
+        if (w.pf_state >= 1 && !getenv("CHEST_CHAIN_LEGACY")) {          // the FFT-form demodulator instead of the GEMM
             DemodFbmcParams dp{};
             dp.md = w.modem; dp.N = N; dp.K = w.K; dp.n_snr = S; dp.n_rep = n_rep; dp.n_cols = w.nsch * S * n_rep;
             dp.r0 = w.r0.p; dp.noise = noise; dp.noise_scale = c->d_noise_scale.p; dp.y = w.y.p;
             const ModemDev& md = w.modem;
-            const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
+            const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
+            const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
             k_demod_fbmc<<<dp.n_cols, PERF_FBMC_THREADS, smem, st>>>(dp);
             c->launches++;
             CK(cudaGetLastError());
@@ -1030,7 +1125,10 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     uint32_t* err = err_dev ? err_dev : c->err.p;
     CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
     ip.err = err;
-    for (int wfi = 0; wfi < 2; ++wfi) { ip.perf_zw[wfi] = c->wf[wfi].det_on ? c->wf[wfi].zw_g.p : nullptr; if (c->wf[wfi].det_on) ip.perf_zw_stride = c->wf[wfi].zw_stride; }
+    for (int wfi = 0; wfi < 2; ++wfi) { ip.perf_zw[wfi] = c->wf[wfi].det_on ? c->wf[wfi].zw_g.p : nullptr; ip.perf_zw_stride[wfi] = c->wf[wfi].zw_stride; }
+    ip.est_fact_mask = 0;
+    for (int si = 0; si < 3; ++si) if (c->est_fact[si] && n_iter > 0) ip.est_fact_mask |= 1 << si;
+    if (ip.est_fact_mask && use_post) return fail(CHEST_ERR_STATE, "the factored estimator runs with k_ic_light (unset CHEST_LIGHT)");
     ip.mse = nullptr;
     if (c->mse_on) {
         if (use_post) return fail(CHEST_ERR_STATE, "MSE accumulation is implemented in k_ic_light (unset CHEST_LIGHT=post)");
@@ -1077,7 +1175,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         if (it == 0 && c->profiling) CK(cudaEventRecord(c->ev_tw[1], st));
         if (it > 0) {                                              // phase B of iteration it
             ip.trace = (trace_path && it == n_iter) ? c->trace.p : nullptr;
-            if (c->precision == 1) {
+            if (c->precision == 1 && c->n_est_units > 0) {
                 TcParams tp{};
                 tp.it = it; tp.n_iter = n_iter; tp.n_rep = n_rep; tp.K_max = c->K_max; tp.n_items = c->tc_n_items;
                 tp.items = c->tc_items.p; tp.cta_ptr = c->tc_cta_ptr.p; tp.ctas = c->ctas.p; tp.scratch = c->scratch.p; tp.status = c->tc_status.p;
@@ -1100,11 +1198,15 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
                     if (!attr32) { CK(cudaFuncSetAttribute(k_ic_est_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<32>::SMEM)); attr32 = true; }
                     k_ic_est_tc<32><<<c->tc_grid, TC_THREADS, TcGeo<32>::SMEM, st>>>(tp);
                 }
-            } else
+                c->launches++;
+            } else if (c->precision != 1 && c->n_est_units > 0) {
             main_kernel<<<main_grid, ic_threads, main_smem, st>>>(ip);
             c->launches++;
+            }
             ip.trace = nullptr;
             if (c->profiling) CK(cudaEventRecord(c->ev_mn[it], st));
+            if (ip.est_fact_mask) { rc = stage_factored_estimated_csi(c, n_rep, it, n_iter, ip); if (rc) return rc; }
+            if (c->profiling) CK(cudaEventRecord(c->ev_ef[it], st));
             if (c->perf_mode == 1) { rc = stage_factored_perfect_csi(c, n_rep, it, n_iter, err, ip); if (rc) return rc; }
             if (c->profiling) CK(cudaEventRecord(c->ev_ic[2 * it], st));
         }
@@ -1156,12 +1258,13 @@ int finish_pipeline(Ctx* c) {
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&c->stage_ms[6], c->ev[0], c->ev[6]);
         // per-kernel times: events after every IC launch (main of iteration it: 2 it, light: 2 it + 1; ev[4] precedes)
-        c->kernel_ms[2] = c->kernel_ms[3] = c->kernel_ms[4] = 0;
+        c->kernel_ms[2] = c->kernel_ms[3] = c->kernel_ms[4] = 0; c->est_fact_ms = 0;
         for (int it = 0; it <= n_iter; ++it) {
             float t = 0;
             if (it > 0) {
                 cudaEventElapsedTime(&t, c->ev_ic[2 * it - 1], c->ev_mn[it]); c->kernel_ms[2] += t;
-                cudaEventElapsedTime(&t, c->ev_mn[it], c->ev_ic[2 * it]); c->kernel_ms[4] += t;
+                cudaEventElapsedTime(&t, c->ev_mn[it], c->ev_ef[it]); c->est_fact_ms += t;
+                cudaEventElapsedTime(&t, c->ev_ef[it], c->ev_ic[2 * it]); c->kernel_ms[4] += t;
             }
             cudaEventElapsedTime(&t, it > 0 ? c->ev_ic[2 * it] : c->ev_tw[1], c->ev_ic[2 * it + 1]);
             c->kernel_ms[3] += t;
@@ -1237,6 +1340,7 @@ int chest_create(int device, uint64_t* handle) {
     for (auto& e : c->ev_gd) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_ic) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_mn) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_ef) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_k1) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_tw) CK(cudaEventCreate(&e));
     *handle = (uint64_t)(uintptr_t)c;
@@ -1254,6 +1358,7 @@ int chest_destroy(uint64_t handle) {
     for (auto& e : c->ev_gd) cudaEventDestroy(e);
     for (auto& e : c->ev_ic) cudaEventDestroy(e);
     for (auto& e : c->ev_mn) cudaEventDestroy(e);
+    for (auto& e : c->ev_ef) cudaEventDestroy(e);
     for (auto& e : c->ev_k1) cudaEventDestroy(e);
     for (auto& e : c->ev_tw) cudaEventDestroy(e);
     for (auto& q : c->pf) { cudaEventDestroy(q.landed); cudaEventDestroy(q.released); }
@@ -1611,6 +1716,7 @@ int chest_set_mmse(uint64_t handle, int si, int variant, int n_snr, const int64_
     CK(cudaSetDevice(c->device));
     Scheme& s = c->sch[si];
     MmseVariant& m = s.mm[variant];
+    m.rinv_set = false; c->ctas_for_batch = -1;               // an uploaded W carries no factors (chest_set_estimator_factors adds them)
     const int K = s.K, P = s.P, P4 = (P + 3) / 4, RT = (K + 7) / 8, ND = 2 * K - 1;
     const int64_t K2 = (int64_t)K * K;
     const cplx* v = reinterpret_cast<const cplx*>(val);
@@ -1701,19 +1807,32 @@ int chest_setup_correlations(uint64_t handle, int wfi, int n_pilots, const int32
                                          c->d_tap_delay.p, d_tp.p, N, T, max_delay);
     c->launches++;
     CK(cudaGetLastError());
+    {   // the pseudo-channels are the factors of the estimated channel H-hat = sum_q g_q M_q (factored estimator): keep them
+        CK(w.Mq.alloc((size_t)P * T * N));
+        CK(cudaMemcpyAsync(w.Mq.p, c->h.p, sizeof(cplx) * P * T * N, cudaMemcpyDeviceToDevice, st));
+        std::vector<cplx> ch((size_t)P * T * max_delay);
+        CK(cudaMemcpyAsync(ch.data(), corner.p, sizeof(cplx) * ch.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        w.mq_corner = false;
+        for (const cplx& x : ch) if (x.x != 0.0 || x.y != 0.0) { w.mq_corner = true; break; }
+        w.mq_P = P;
+        CK(c->zmax.alloc(1)); CK(cudaMemsetAsync(c->zmax.p, 0, sizeof(unsigned long long), st));
+    }
     c->cur_batch = P;
     rc = stage_transmission_matrix(c, wfi, P, 0);                   // D_p = Q^H M_p G for every pilot: K1 + K2
     if (rc) return rc;
     CK(w.Rsup.alloc((size_t)P * n_e));
     dim3 g2((unsigned)((n_e + 255) / 256), P);
-    k_rsup_finish<<<g2, 256, 0, st>>>(w.Rsup.p, w.D.p, corner.p, w.G.p, w.Q.p, c->d_tap_delay.p, N, K, T, max_delay, 0.0);
+    k_rsup_finish<<<g2, 256, 0, st>>>(w.Rsup.p, w.D.p, corner.p, w.G.p, w.Q.p, c->d_tap_delay.p, N, K, T, max_delay, 0.0, nullptr);
     k_rhp_gather<<<P, ((P + 31) / 32) * 32, 0, st>>>(rhp.p, w.Rsup.p, d_pil.p, K, P);
-    k_rsup_finish<<<g2, 256, 0, st>>>(w.Rsup.p, w.Rsup.p, corner.p, w.G.p, w.Q.p, c->d_tap_delay.p, N, K, 0, max_delay, zero_threshold);
+    k_rsup_finish<<<g2, 256, 0, st>>>(w.Rsup.p, w.Rsup.p, corner.p, w.G.p, w.Q.p, c->d_tap_delay.p, N, K, 0, max_delay, zero_threshold, c->zmax.p);
     c->launches += 3;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(R_hP_out, rhp.p, sizeof(cplx) * P * P, cudaMemcpyDeviceToHost, st));
+    { unsigned long long zb = 0; CK(cudaMemcpyAsync(&zb, c->zmax.p, sizeof(zb), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      long long zl = (long long)zb; double zd; memcpy(&zd, &zl, sizeof(zd)); w.rsup_zeroed_max = zd; }
     CK(cudaStreamSynchronize(st));
-    w.rsup_P = P; w.rsup_thr = zero_threshold;
+    w.rsup_P = P; w.rsup_thr = zero_threshold; c->ctas_for_batch = -1;
     if (n_support) {                                                // entries of the K x K grid with any non-zero pilot weight
         DevBuf<int> mask; DevBuf<cplx> eye;
         CK(mask.alloc(n_e)); CK(cudaMemsetAsync(mask.p, 0, n_e * sizeof(int), st));
@@ -1721,7 +1840,7 @@ int chest_setup_correlations(uint64_t handle, int wfi, int n_pilots, const int32
         for (int p = 0; p < P; ++p) id[(size_t)p * P + p] = cmake(1.0, 0.0);
         CK(eye.upload(id, st));
         dim3 g3((unsigned)((n_e * P + 255) / 256), 1);
-        k_w_mask<<<g3, 256, 0, st>>>(mask.p, w.Rsup.p, eye.p, K, P, 1e-300);
+        k_w_mask<<<g3, 256, 0, st>>>(mask.p, w.Rsup.p, eye.p, K, P, 1e-300, nullptr);
         c->launches++;
         std::vector<int> hm(n_e);
         CK(cudaMemcpyAsync(hm.data(), mask.p, n_e * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1749,12 +1868,17 @@ int chest_build_mmse(uint64_t handle, int si, int variant, int n_snr, const doub
     CK(rinv.upload(reinterpret_cast<const cplx*>(R_inv), (size_t)n_snr * P * P, st));
     CK(mask.alloc(n_e)); CK(cudaMemsetAsync(mask.p, 0, n_e * sizeof(int), st));
     dim3 g1((unsigned)((n_e * P + 255) / 256), n_snr);
-    k_w_mask<<<g1, 256, 0, st>>>(mask.p, w.Rsup.p, rinv.p, K, P, zero_threshold);
+    CK(m.rinv.upload(reinterpret_cast<const cplx*>(R_inv), (size_t)n_snr * P * P, st));      // kept: g = Rinv hP of the factored estimator
+    CK(c->zmax.alloc(1)); CK(cudaMemsetAsync(c->zmax.p, 0, sizeof(unsigned long long), st));
+    k_w_mask<<<g1, 256, 0, st>>>(mask.p, w.Rsup.p, rinv.p, K, P, zero_threshold, c->zmax.p);
     c->launches++;
     CK(cudaGetLastError());
     std::vector<int> hm(n_e);
+    unsigned long long zb = 0;
     CK(cudaMemcpyAsync(hm.data(), mask.p, n_e * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&zb, c->zmax.p, sizeof(zb), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    { long long zl = (long long)zb; double zd; memcpy(&zd, &zl, sizeof(zd)); m.w_zeroed_max = zd; m.rinv_set = true; }
     // tile list: (row tile, diagonal offset) pairs with any surviving off-diagonal entry, offsets ascending per row tile
     std::vector<char> lut((size_t)RT * ND, 0);
     int64_t pairs = 0;
@@ -1797,7 +1921,7 @@ int chest_build_mmse(uint64_t handle, int si, int variant, int n_snr, const doub
     CK(cudaGetLastError());
     CK(m.table.upload(table, st));
     CK(cudaStreamSynchronize(st));
-    m.set = true; c->finalized = false;
+    m.set = true; c->finalized = false; c->ctas_for_batch = -1;
     return CHEST_OK;
 }
 
@@ -2722,6 +2846,51 @@ int chest_precision_info(uint64_t handle, int* mode, double* mma_flops_per_launc
         for (auto& s : c->sch) for (auto& m : s.mm) b += (int64_t)m.tc_img.n;
         *operand_bytes = b;
     }
+    return CHEST_OK;
+}
+
+int chest_set_estimator_mode(uint64_t handle, int mode) {
+    Ctx* c = from(handle);
+    ARG(c && mode >= CHEST_ESTIMATOR_AUTO && mode <= CHEST_ESTIMATOR_FACTORED_EXACT);
+    if (c->pending) return fail(CHEST_ERR_STATE, "an asynchronous run is pending on this context");
+    c->est_mode = mode;
+    c->ctas_for_batch = -1;
+    return CHEST_OK;
+}
+
+int chest_set_pseudo_channels(uint64_t handle, int wfi, int n_pilots, const double* M, double removed_max) {
+    Ctx* c = from(handle);
+    ARG(c && (wfi == 0 || wfi == 1) && c->wf[wfi].set && c->chan_set && n_pilots >= 1 && M && removed_max >= 0);
+    CK(cudaSetDevice(c->device));
+    Waveform& w = c->wf[wfi];
+    CK(w.Mq.upload(reinterpret_cast<const cplx*>(M), (size_t)n_pilots * c->T * c->N, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    w.mq_P = n_pilots; w.mq_corner = false; w.rsup_zeroed_max = removed_max;
+    c->ctas_for_batch = -1;
+    return CHEST_OK;
+}
+
+int chest_set_estimator_factors(uint64_t handle, int si, int variant, int n_snr, const double* R_inv, double removed_max) {
+    Ctx* c = from(handle);
+    ARG(c && si >= 0 && si < 3 && (variant == 0 || variant == 1) && R_inv && removed_max >= 0);
+    ARG(c->sch[si].set && n_snr == c->S);
+    CK(cudaSetDevice(c->device));
+    MmseVariant& m = c->sch[si].mm[variant];
+    CK(m.rinv.upload(reinterpret_cast<const cplx*>(R_inv), (size_t)n_snr * c->sch[si].P * c->sch[si].P, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    m.rinv_set = true; m.w_zeroed_max = removed_max;
+    c->ctas_for_batch = -1;
+    return CHEST_OK;
+}
+
+int chest_estimator_info(uint64_t handle, int si, int* mode, int* factored, double* removed_r, double* removed_w, float* ms) {
+    Ctx* c = from(handle);
+    ARG(c && si >= 0 && si < 3);
+    if (mode) *mode = c->est_mode;
+    if (factored) *factored = c->est_fact[si] ? 1 : 0;
+    if (removed_r) *removed_r = c->sch[si].set ? c->wf[c->sch[si].waveform].rsup_zeroed_max : 0.0;
+    if (removed_w) *removed_w = std::max(c->sch[si].mm[0].w_zeroed_max, c->sch[si].mm[1].w_zeroed_max);
+    if (ms) *ms = c->est_fact_ms;
     return CHEST_OK;
 }
 

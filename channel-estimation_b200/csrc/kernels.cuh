@@ -1067,8 +1067,11 @@ struct IcParams {
     unsigned long long* trace; // development: per CTA {smid, t0, t_pre, t_main_own, t_main_all, t_end, B busy ns, units}
     double* mse;               // optional: sum_i |h_est[i] - h[i]|^2 per [rep][snr][it][scheme] (estimated-CSI columns); nullptr = off
     // perfect-CSI columns of a waveform whose equalisation / detection / counting is done by k_perfect_fbmc_det: the decided words
-    // [column][perf_zw_stride] (column = rep * nsch * n_snr + slot * n_snr + snr); k_ic_light then only precodes (phase A)
-    const uint8_t* perf_zw[2]; int perf_zw_stride;
+    // [column][perf_zw_stride[wf]] (column = rep * nsch * n_snr + slot * n_snr + snr); k_ic_light then only precodes (phase A)
+    const uint8_t* perf_zw[2]; int perf_zw_stride[2];
+    // schemes whose estimated-CSI cancellation runs in factored form (k_est_factored): k_ic_light leaves h-hat = W_diag hP of the
+    // unit's columns in the first scratch buffer, [row][column] like v
+    int est_fact_mask;
 };
 
 // Column -> (scheme, SNR point, realization); false for an unused slot.  PERF units keep each 8-column half
@@ -1645,7 +1648,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 const SchemeDev& sd = p.sch[sh.c_scheme[c]];
                 if (d >= sd.n_data) continue;
                 const int64_t col = (int64_t)sh.c_rep[c] * nv + (c >> 3) * p.n_snr + sh.c_snr[c];
-                zw[d * NC + c] = p.perf_zw[wf][col * p.perf_zw_stride + d];
+                zw[d * NC + c] = p.perf_zw[wf][col * p.perf_zw_stride[wf] + d];
             }
         }
         {   // transmitted pilots of the columns (phase C divides by them, phase A re-inserts them)
@@ -1684,6 +1687,8 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 const int g = lane >> 2, t4 = lane & 3, RT = (K + 7) / 8, P4 = sd.P4;
                 const bool select = sd.detect_mode != 1;
                 const cplx* __restrict__ wf_ = sd.wdiag_frag[var_cur] + (int64_t)cta.snr * RT * P4 * 32;
+                const bool hfact = next_pre && ((p.est_fact_mask >> cta.scheme_or_wf) & 1);     // k_est_factored adds h-hat v back
+                cplx* hbuf = vbuf - (int64_t)p.K_max * NC;
                 unsigned e_all[2][2] = {{0, 0}, {0, 0}}, e_edge[2][2] = {{0, 0}, {0, 0}};
                 double dm[2][2] = {{0, 0}, {0, 0}};                // channel-estimation error of this lane's columns (p.mse)
                 for (int rt = warp; rt < RT; rt += nwarp) {
@@ -1718,6 +1723,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                                 const int64_t col = (int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c];
                                 const cplx hh = cmake(hr[ct][e], hi[ct][e]);
                                 if (last) sd.hdiag[col * K + i] = hh;
+                                if (hfact) hbuf[i * NC + c] = hh;
                                 if (p.mse) {
                                     const cplx ht = p.htrue[wf][(int64_t)sh.c_rep[c] * K + i];
                                     dm[ct][e] += (hh.x - ht.x) * (hh.x - ht.x) + (hh.y - ht.y) * (hh.y - ht.y);
@@ -2621,9 +2627,11 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
+    const int nbuf = max(nx, N);                               // CP-OFDM with zero guards: N can exceed Ksym * nfft
+    const bool fbmc = md.kind == 0;
     cplx* X0 = pf_smem;
-    cplx* X1 = X0 + nx;
-    cplx* tw = X1 + nx;
+    cplx* X1 = X0 + nbuf;
+    cplx* tw = X1 + nbuf;
     double* filt = reinterpret_cast<double*>(tw + n);
     int* bins = reinterpret_cast<int*>(filt + md.Np);
     __shared__ unsigned int cnt[2];
@@ -2640,34 +2648,40 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         Xe = X1;
     } else {
         for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
-        for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+        if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
         for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
         if (L < n) for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0);
         __syncthreads();
         const cplx* vcol = p.v_base + p.voff[col];
         for (int i = tid; i < K; i += nthr) {
             const int k = i / L, l = i - k * L;
-            const cplx v = cmul(vcol[(int64_t)i * NC_MAX], md.phase[i]);
+            cplx v = vcol[(int64_t)i * NC_MAX];
+            if (fbmc) v = cmul(v, md.phase[i]);
             X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
         }
         __syncthreads();
         cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
         cplx* Xo = (Xz == X0) ? X1 : X0;
         const double inv_n = 1.0 / n;
-        for (int nn = tid; nn < N; nn += nthr) {                // overlap-add
-            int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
-            const int k_hi = min(Ksym - 1, nn / TS);
+        for (int nn = tid; nn < N; nn += nthr) {
             cplx acc = cmake(0.0, 0.0);
-            int tap = nn - k_lo * TS, mm = tap % n;
-            const cplx* zc = Xz + k_lo * n;
-            for (int k = k_lo; k <= k_hi; ++k) {
-                if (tap >= 0 && tap < md.Np) {
-                    const cplx z = zc[mm];
-                    const double pf = filt[tap];
-                    acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+            if (fbmc) {                                         // overlap-add (FBMC.m:267-268)
+                int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+                const int k_hi = min(Ksym - 1, nn / TS);
+                int tap = nn - k_lo * TS, mm = tap % n;
+                const cplx* zc = Xz + k_lo * n;
+                for (int k = k_lo; k <= k_hi; ++k) {
+                    if (tap >= 0 && tap < md.Np) {
+                        const cplx z = zc[mm];
+                        const double pf = filt[tap];
+                        acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+                    }
+                    tap -= TS; mm -= TS; if (mm < 0) mm += n;
+                    zc += n;
                 }
-                tap -= TS; mm -= TS; if (mm < 0) mm += n;
-                zc += n;
+            } else {                                            // cyclic prefix + zero guards (OFDM.m:158-164)
+                const int q = nn - md.zero_guard, k = q >= 0 ? q / TS : Ksym;
+                if (k < Ksym) { int m = q - k * TS - md.cp; if (m < 0) m += n; acc = Xz[k * n + m]; }
             }
             Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
         }
@@ -2682,15 +2696,17 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
             Xz[nn] = acc;
         }
         __syncthreads();
-        for (int idx = tid; idx < nx; idx += nthr) {            // fold
+        for (int idx = tid; idx < nx; idx += nthr) {            // fold by O (FBMC.m:297-302) / drop the cyclic prefix (OFDM.m:172-176)
             const int k = idx / n, m = idx - k * n;
-            const cplx* seg = Xz + k * TS + m;
             cplx acc = cmake(0.0, 0.0);
-            for (int o = 0; o < md.O; ++o) {
-                const double pf = filt[o * n + m];
-                const cplx v = seg[o * n];
-                acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
-            }
+            if (fbmc) {
+                const cplx* seg = Xz + k * TS + m;
+                for (int o = 0; o < md.O; ++o) {
+                    const double pf = filt[o * n + m];
+                    const cplx v = seg[o * n];
+                    acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+                }
+            } else acc = Xz[md.zero_guard + k * TS + md.cp + m];
             Xo[idx] = acc;
         }
         __syncthreads();
@@ -2698,7 +2714,8 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         Xe = (Y == X0) ? X1 : X0;
         for (int i = tid; i < K; i += nthr) {                   // y_ic = y - U + h v, x = y_ic / h
             const int k = i / L, l = i - k * L;
-            const cplx u0 = cmulc(md.phase[i], Y[k * n + bins[l]]);
+            cplx u0 = Y[k * n + bins[l]];
+            if (fbmc) u0 = cmulc(md.phase[i], u0);
             const cplx hv = ht[i], yv = ycol[i];
             const cplx hvv = cmul(hv, vcol[(int64_t)i * NC_MAX]);
             Xe[i] = cdiv_fast(cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y), hv);
@@ -2913,14 +2930,16 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
+    const int nbuf = max(nx, N);
+    const bool fbmc = md.kind == 0;
     cplx* X0 = pf_smem;
-    cplx* X1 = X0 + nx;
-    cplx* tw = X1 + nx;
+    cplx* X1 = X0 + nbuf;
+    cplx* tw = X1 + nbuf;
     double* filt = reinterpret_cast<double*>(tw + n);
     int* bins = reinterpret_cast<int*>(filt + md.Np);
     const int tid = threadIdx.x, nthr = blockDim.x, col = blockIdx.x;
     for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
-    for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+    if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
     for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
     {   // received samples of this column
         const int rep = col % p.n_rep, q = col / p.n_rep, snr = q % p.n_snr, grp = q / p.n_snr;
@@ -2930,15 +2949,17 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod
         for (int nn = tid; nn < N; nn += nthr) { const cplx x = a[nn], z = nz[nn]; X1[nn] = cmake(x.x + sc * z.x, x.y + sc * z.y); }
     }
     __syncthreads();
-    for (int idx = tid; idx < nx; idx += nthr) {               // fold: a_k[m] = sum_o p[o n + m] r[k TS + o n + m]
+    for (int idx = tid; idx < nx; idx += nthr) {               // fold: a_k[m] = sum_o p[o n + m] r[k TS + o n + m]; OFDM: drop the prefix
         const int k = idx / n, m = idx - k * n;
-        const cplx* seg = X1 + k * TS + m;
         cplx acc = cmake(0.0, 0.0);
-        for (int o = 0; o < md.O; ++o) {
-            const double pf = filt[o * n + m];
-            const cplx v = seg[o * n];
-            acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
-        }
+        if (fbmc) {
+            const cplx* seg = X1 + k * TS + m;
+            for (int o = 0; o < md.O; ++o) {
+                const double pf = filt[o * n + m];
+                const cplx v = seg[o * n];
+                acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+            }
+        } else acc = X1[md.zero_guard + k * TS + md.cp + m];
         X0[idx] = acc;
     }
     __syncthreads();
@@ -2946,8 +2967,169 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod
     cplx* out = p.y + (int64_t)col * K;
     for (int i = tid; i < K; i += nthr) {
         const int k = i / L, l = i - k * L;
-        const cplx u0 = cmulc(md.phase[i], Y[k * n + bins[l]]);
+        cplx u0 = Y[k * n + bins[l]];
+        if (fbmc) u0 = cmulc(md.phase[i], u0);
         out[i] = cmake(u0.x * md.inv_demod, u0.y * md.inv_demod);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Factored estimated-CSI cancellation.  The MMSE estimate of the transmission matrix is linear in the pilot estimates,
+//     D-hat = sum_p W_p hP(p),   W = R_Dij_hP pinv(R_hP_est),   R_Dij_hP(:, q) = vec(Q^H M_q G)        (DS.m:256-289, 417-425)
+// with M_q the banded pseudo-channel of pilot q (DS.m:260), so  D-hat = Q^H H-hat G  with the ESTIMATED CHANNEL
+//     H-hat = sum_q g_q M_q,   g = pinv(R_hP_est) hP
+// -- N x T taps per column instead of nnz(W) x P weights.  The interference (D-hat - diag h-hat) v of DS.m:482-484 is then
+// the same Modulation -> banded channel -> Demodulation chain as the perfect-CSI pass, applied with H-hat.  This equals the
+// reference's D-hat up to the entries its two 1e-8 thresholds (DS.m:263-264, 287-289) removed: exactly (1e-13) for a waveform
+// where the thresholds only remove rounding noise (CP-OFDM), within 4e-5 of max|D-hat| for FBMC at the default geometry
+// (the library measures the removed magnitudes at setup: chest_estimator_info).
+//
+// k_est_channel: one CTA per EST unit (scheme, SNR point, 16 realizations): g = Rinv hP for the 16 columns, then
+// H-hat[column][tap][n] = sum_q g[q][column] M[q][tap][n]; the pseudo-channels are read once per 16 columns.
+struct EstChanParams {
+    const int* units; const IcCta* ctas;
+    const cplx* hP[3]; const cplx* rinv[3]; int P[3];            // per scheme: pilot estimates [snr][rep][P], Rinv [snr][P x P col-major]
+    const cplx* Mq;                                              // [P][T * N] pseudo-channel taps of the waveform
+    cplx* hest;                                                  // [unit slot * 16 + column][T * N]
+    int n_rep, TN;
+};
+#define EST_CHAN_THREADS 256
+__global__ void __launch_bounds__(EST_CHAN_THREADS) k_est_channel(EstChanParams p) {
+    extern __shared__ __align__(16) cplx ec_smem[];
+    constexpr int NC = NC_MAX;
+    const IcCta cta = p.ctas[p.units[blockIdx.x]];
+    const int si = cta.scheme_or_wf, P = p.P[si], tid = threadIdx.x, nthr = blockDim.x;
+    cplx* hp = ec_smem;                                          // [P][NC]
+    cplx* g = hp + P * NC;                                       // [P][NC]
+    for (int idx = tid; idx < P * NC; idx += nthr) {
+        const int c = idx % NC, pp = idx / NC, rep = cta.first + c;
+        hp[idx] = rep < p.n_rep ? p.hP[si][((int64_t)cta.snr * p.n_rep + rep) * P + pp] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    const cplx* ri = p.rinv[si] + (int64_t)cta.snr * P * P;
+    for (int idx = tid; idx < P * NC; idx += nthr) {
+        const int c = idx % NC, q = idx / NC;
+        cplx acc = cmake(0.0, 0.0);
+        for (int pp = 0; pp < P; ++pp) cfma(acc, ri[q + (int64_t)P * pp], hp[pp * NC + c]);
+        g[idx] = acc;
+    }
+    __syncthreads();
+    cplx* out = p.hest + (int64_t)blockIdx.x * NC * p.TN;
+    for (int e = tid; e < p.TN; e += nthr) {
+        cplx acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = cmake(0.0, 0.0);
+        for (int q = 0; q < P; ++q) {
+            const cplx m = ld_nc(p.Mq + (int64_t)q * p.TN + e);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) cfma(acc[c], m, g[q * NC + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) out[(int64_t)c * p.TN + e] = acc[c];
+    }
+}
+
+// k_est_factored: one column (scheme, SNR point, realization) of an EST unit per CTA:
+//     y_ic = y - Demodulation(H-hat Modulation(v)) + h-hat v        (h-hat = diag(D-hat) = W_diag hP, left by k_ic_light)
+// v from the unit's scratch, y_ic into it (what k_ic_main writes for the tile form of W); the chain is k_perfect_fbmc_det's.
+struct EstFactParams {
+    ModemDev md;
+    const int* units; const IcCta* ctas;
+    const cplx* y[3]; int K_max, n_rep, T, N, K;
+    const cplx* hest; const int* tap_delay;
+    cplx* scratch;
+};
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
+    extern __shared__ __align__(16) cplx pf_smem[];
+    const ModemDev& md = p.md;
+    const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
+    const int nbuf = max(nx, N);
+    const bool fbmc = md.kind == 0;
+    const int tid = threadIdx.x, nthr = blockDim.x, col = blockIdx.x, c = col % NC_MAX;
+    const int unit = p.units[col / NC_MAX];
+    const IcCta cta = p.ctas[unit];
+    const int rep = cta.first + c;
+    if (rep >= p.n_rep) return;
+    cplx* X0 = pf_smem;
+    cplx* X1 = X0 + nbuf;
+    cplx* tw = X1 + nbuf;
+    double* filt = reinterpret_cast<double*>(tw + n);
+    int* bins = reinterpret_cast<int*>(filt + md.Np);
+    const cplx* ycol = p.y[cta.scheme_or_wf] + ((int64_t)cta.snr * p.n_rep + rep) * K;
+    cplx* ub = p.scratch + (int64_t)unit * 3 * p.K_max * NC_MAX + c;
+    const cplx* hcol = ub;
+    const cplx* vcol = ub + (int64_t)p.K_max * NC_MAX;
+    cplx* ocol = ub + (int64_t)2 * p.K_max * NC_MAX;
+    for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
+    if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+    for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
+    if (L < n) for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0);
+    __syncthreads();
+    for (int i = tid; i < K; i += nthr) {
+        const int k = i / L, l = i - k * L;
+        cplx v = vcol[(int64_t)i * NC_MAX];
+        if (fbmc) v = cmul(v, md.phase[i]);
+        X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
+    }
+    __syncthreads();
+    cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
+    cplx* Xo = (Xz == X0) ? X1 : X0;
+    const double inv_n = 1.0 / n;
+    for (int nn = tid; nn < N; nn += nthr) {
+        cplx acc = cmake(0.0, 0.0);
+        if (fbmc) {                                             // overlap-add (FBMC.m:267-268)
+            int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+            const int k_hi = min(Ksym - 1, nn / TS);
+            int tap = nn - k_lo * TS, mm = tap % n;
+            const cplx* zc = Xz + k_lo * n;
+            for (int k = k_lo; k <= k_hi; ++k) {
+                if (tap >= 0 && tap < md.Np) {
+                    const cplx z = zc[mm];
+                    const double pf = filt[tap];
+                    acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+                }
+                tap -= TS; mm -= TS; if (mm < 0) mm += n;
+                zc += n;
+            }
+        } else {                                                // cyclic prefix + zero guards (OFDM.m:158-164)
+            const int q = nn - md.zero_guard, k = q >= 0 ? q / TS : Ksym;
+            if (k < Ksym) { int m = q - k * TS - md.cp; if (m < 0) m += n; acc = Xz[k * n + m]; }
+        }
+        Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
+    }
+    __syncthreads();
+    const cplx* hr = p.hest + (int64_t)col * p.T * N;
+    for (int nn = tid; nn < N; nn += nthr) {                    // r = H-hat s
+        cplx acc = cmake(0.0, 0.0);
+        for (int t = 0; t < p.T; ++t) {
+            const int d = p.tap_delay[t];
+            if (nn >= d) cfma(acc, ld_nc(hr + (int64_t)t * N + nn), Xo[nn - d]);
+        }
+        Xz[nn] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nx; idx += nthr) {                // fold by O (FBMC.m:297-302) / drop the cyclic prefix (OFDM.m:172-176)
+        const int k = idx / n, m = idx - k * n;
+        cplx acc = cmake(0.0, 0.0);
+        if (fbmc) {
+            const cplx* seg = Xz + k * TS + m;
+            for (int o = 0; o < md.O; ++o) {
+                const double pf = filt[o * n + m];
+                const cplx v = seg[o * n];
+                acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+            }
+        } else acc = Xz[md.zero_guard + k * TS + md.cp + m];
+        Xo[idx] = acc;
+    }
+    __syncthreads();
+    const cplx* Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, Ksym);
+    for (int i = tid; i < K; i += nthr) {                       // y_ic = y - U + h-hat v
+        const int k = i / L, l = i - k * L;
+        cplx u0 = Y[k * n + bins[l]];
+        if (fbmc) u0 = cmulc(md.phase[i], u0);
+        const cplx yv = ycol[i];
+        const cplx hvv = cmul(hcol[(int64_t)i * NC_MAX], vcol[(int64_t)i * NC_MAX]);
+        ocol[(int64_t)i * NC_MAX] = cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y);
     }
 }
 
@@ -3058,7 +3240,7 @@ __global__ void k_pseudo_channel(cplx* __restrict__ h, cplx* __restrict__ corner
 // |.| < thr -> 0 rule of DS.m:263-264.  Layout of D and R: row-tile-major [p][K/8][K][8].
 __global__ void k_rsup_finish(cplx* __restrict__ R, const cplx* __restrict__ D, const cplx* __restrict__ corner,
                               const cplx* __restrict__ G, const cplx* __restrict__ Q, const int* __restrict__ tap_delay,
-                              int N, int K, int T, int max_delay, double thr) {
+                              int N, int K, int T, int max_delay, double thr, unsigned long long* __restrict__ zmax) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int p = blockIdx.y;
     const int RT8 = ((K + 7) / 8) * 8;
@@ -3077,7 +3259,11 @@ __global__ void k_rsup_finish(cplx* __restrict__ R, const cplx* __restrict__ D, 
                 cfma(v, cmul(cv, cmake(qv.x, -qv.y)), gv);
             }
         }
-        if (hypot(v.x, v.y) < thr) v = cmake(0.0, 0.0);
+        const double mag = hypot(v.x, v.y);
+        if (mag < thr) {                                        // largest magnitude the threshold removes (bit pattern order = value order)
+            if (zmax && mag > 0.0) atomicMax(zmax, (unsigned long long)__double_as_longlong(mag));
+            v = cmake(0.0, 0.0);
+        }
     } else v = cmake(0.0, 0.0);
     R[(int64_t)p * RT8 * K + e] = v;
 }
@@ -3092,7 +3278,8 @@ __global__ void k_rhp_gather(cplx* __restrict__ out, const cplx* __restrict__ R,
 
 // W[(i,j), p'] = sum_p R_p[(i,j)] Rinv[p, p']  (DS.m:283-313: W = R_Dij_hP * pinv(R_hP_est)), |.| < thr -> 0.
 // pass A: mask[e] = 1 where any (snr, p') entry survives.  One thread per (entry e, p'), snr = blockIdx.y.
-__global__ void k_w_mask(int* __restrict__ mask, const cplx* __restrict__ R, const cplx* __restrict__ Rinv, int K, int P, double thr) {
+__global__ void k_w_mask(int* __restrict__ mask, const cplx* __restrict__ R, const cplx* __restrict__ Rinv, int K, int P, double thr,
+                         unsigned long long* __restrict__ zmax) {
     const int RT8 = ((K + 7) / 8) * 8;
     const int64_t n_e = (int64_t)RT8 * K;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -3106,7 +3293,10 @@ __global__ void k_w_mask(int* __restrict__ mask, const cplx* __restrict__ R, con
         const cplx a = R[(int64_t)p * n_e + e];
         if (a.x != 0.0 || a.y != 0.0) { any = true; cfma(w, a, ri[p]); }
     }
-    if (any && !(hypot(w.x, w.y) < thr)) mask[e] = 1;
+    if (!any) return;
+    const double mag = hypot(w.x, w.y);
+    if (!(mag < thr)) mask[e] = 1;
+    else if (zmax && mag > 0.0) atomicMax(zmax, (unsigned long long)__double_as_longlong(mag));
 }
 // pass B: fragments of one SNR point.  One thread per (tile t, row r, p'); the diagonal goes to dg / dfrag.
 __global__ void k_w_fill(cplx* __restrict__ frag, cplx* __restrict__ dg, cplx* __restrict__ dfrag, const cplx* __restrict__ R,

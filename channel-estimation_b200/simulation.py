@@ -138,6 +138,8 @@ class DoublySelectiveSimulation:
             # the polyphase description of the same modem (FBMC.m:61-160): with it the perfect-CSI pass of the loop body applies
             # G and Q' as Modulation / Demodulation (k_perfect_fbmc) instead of as GEMMs; the library checks that it reproduces G, Q
             self.FBMC._set_modem(ctx)
+        if "ofdm" in self.schemes:
+            self.OFDM._set_modem(ctx)
         ctx.set_constellation("PAM", self.PAM.SymbolMapping, self.PAM.BitMapping)
         ctx.set_constellation("QAM", self.QAM.SymbolMapping, self.QAM.BitMapping)
         ctx.set_snr(self.Pn)

@@ -265,6 +265,37 @@ int chest_set_perfect_csi_mode(uint64_t handle, int mode);
 #define CHEST_PRECISION_SPLIT_BF16  1
 int chest_set_precision(uint64_t handle, int mode);
 int chest_precision_info(uint64_t handle, int* mode, double* mma_flops_per_launch, int64_t* operand_bytes);
+/* Form of the estimated-CSI interference cancellation.  The MMSE estimate is linear in the pilot estimates,
+ *     D_est = sum_p W_p hP(p),  W = R_Dij_hP pinv(R_hP_est),  R_Dij_hP(:, q) = vec(Q' M_q G)           (DS.m:256-289, 417-425)
+ * with M_q the banded pseudo-channel of pilot q (DS.m:260), hence D_est = Q' H_est G with the estimated channel
+ * H_est = sum_q g_q M_q, g = pinv(R_hP_est) hP: N x taps values per column instead of nnz(W) x P weights, and
+ * (D_est - diag h_est) v becomes Modulation -> banded channel -> Demodulation with H_est (FFT modem of chest_set_modem), ~25 x
+ * fewer operations than the weights at the default geometry.  It equals the reference's D_est up to what its two 1e-8
+ * thresholds (DS.m:263-264, 287-289) removed from R_Dij_hP and W; the device-side setup records the largest removed magnitudes.
+ *   CHEST_ESTIMATOR_AUTO (default)  the factored form only for a scheme where the thresholds removed nothing above 1e-13
+ *                                   (CP-OFDM: only rounding noise is removed, results within 1e-12 of the tile form of W) AND
+ *                                   the tile form costs more than 3 MFLOP per column (the measured break-even of the modem
+ *                                   chain; CP-OFDM at the default geometry stays on the tiles); the thresholded W tiles
+ *                                   otherwise (bit-faithful to the reference's W)
+ *   CHEST_ESTIMATOR_FACTORED_EXACT  the factored form wherever the thresholds removed nothing above 1e-13, whatever it costs
+ *   CHEST_ESTIMATOR_TILES           the thresholded W for every scheme
+ *   CHEST_ESTIMATOR_FACTORED        the factored form for every scheme that has the factors: a STATED-TOLERANCE mode -- D_est
+ *                                   differs from the reference's by the removed entries (4e-5 of max|D_est| for FBMC at the
+ *                                   default geometry, within the 1e-4 of the stated reduced-accuracy mode); FP64 arithmetic
+ * Needs CHEST_PERFECT_FACTORED, a modem description that reproduces G / Q (chest_set_modem), pseudo-channels without wrapped
+ * entries (tap delays < 2 samples) and the factors: kept automatically by chest_setup_correlations + chest_build_mmse, or
+ * uploaded -- chest_set_pseudo_channels: M[p][tap][n] = M_p(n, n - delay_tap) (taps = non-zero PDP entries, ascending delay),
+ * chest_set_estimator_factors: R_inv as in chest_build_mmse; removed_max = largest magnitude the caller's thresholds removed
+ * (a value below 1e-13 lets CHEST_ESTIMATOR_AUTO pick the factored form).  chest_estimator_info (after a run; any pointer may be
+ * NULL): mode, whether the scheme ran factored, the removed magnitudes, kernel time of the factored pass in the last profiled run. */
+#define CHEST_ESTIMATOR_AUTO      0
+#define CHEST_ESTIMATOR_TILES     1
+#define CHEST_ESTIMATOR_FACTORED  2
+#define CHEST_ESTIMATOR_FACTORED_EXACT 3
+int chest_set_estimator_mode(uint64_t handle, int mode);
+int chest_set_pseudo_channels(uint64_t handle, int waveform, int n_pilots, const double* M, double removed_max);
+int chest_set_estimator_factors(uint64_t handle, int scheme, int variant, int n_snr, const double* R_inv, double removed_max);
+int chest_estimator_info(uint64_t handle, int scheme, int* mode, int* factored, double* removed_r, double* removed_w, float* ms);
 /* Channel-estimation error sums next to the bit-error counters (north_star: "BER/MSE counters"; the reference itself keeps
  * no MSE): with accumulation enabled every chest_run_batch* also leaves sum_i |h_est(i) - h(i)|^2 over the K positions of
  * a scheme's grid -- h_est = diag(D_est) of DS.m:428/517, h = diag(Q'HG) of DS.m:392-393 -- for every realization, SNR

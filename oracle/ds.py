@@ -180,8 +180,10 @@ def ds_setup(cfg: DSConfig, verbose=False):
         K = w["K"]
         R_hP = np.zeros((P, P), dtype=complex)
         cols = []
+        w["Mq"] = []                                           # pseudo-channels, kept for the factored estimator (ds_realization)
         for jp in range(P):
             M = corr.pseudo_channel(w["Q"][:, w["pil"][jp]], w["G"][:, w["pil"][jp]])
+            w["Mq"].append(M)
             Dj = w["Q"].conj().T @ (M @ w["G"])                                             # :260
             R_hP[:, jp] = Dj[w["pil"], w["pil"]]                                            # :213
             v = Dj.reshape(-1, order="F")
@@ -202,16 +204,17 @@ def ds_setup(cfg: DSConfig, verbose=False):
             q = w["Q"][:, w["pil"][ip]]
             R_nn[ip, ip] = corr.pilot_power(q, G_pre[sc], kappa[sc])
             qn[ip] = np.real(np.vdot(q, q))
-        W, W_ni = [], []
+        W, W_ni, Ri, Ri_ni = [], [], [], []
         for isnr in range(len(Pn)):                                                         # :238-313
             R_est = R_nn.copy()
             R_est[np.arange(P), np.arange(P)] = np.diag(R_nn) + Pn[isnr] * qn / kappa[sc]   # :245-247
             R_ni = R_est - (R_nn - R_hP)                                                    # :251-253
-            for R, out in ((R_est, W), (R_ni, W_ni)):
-                Wv = w["R_sup"] @ np.linalg.pinv(R)                                         # :283 / :302
+            for R, out, inv in ((R_est, W, Ri), (R_ni, W_ni, Ri_ni)):
+                inv.append(np.linalg.pinv(R))
+                Wv = w["R_sup"] @ inv[-1]                                                   # :283 / :302
                 Wv[np.abs(Wv) < thr] = 0                                                    # :287 / :306
                 out.append(Wv)
-        schemes[sc] = dict(waveform=wname, C=C, W=W, W_noInt=W_ni, kappa=kappa[sc],
+        schemes[sc] = dict(waveform=wname, C=C, W=W, W_noInt=W_ni, Rinv=Ri, Rinv_noInt=Ri_ni, kappa=kappa[sc],
                            R_hP_est_noNoise=R_nn, considered_bits=cbits[sc])
     schemes_meta = {
         "aux": dict(nD=aux.NrDataSymbols, data_idx=np.flatnonzero(pmaux == 0), dpr=aux.DataPowerReduction,
@@ -268,8 +271,34 @@ def _dhat(w, Wv, hP, faithful):
     return sp.csr_matrix((vals[order], idx, indptr), shape=(K, K)), vals[w["diag_pos"]]
 
 
+def _dhat_factored(w, Wv, Rinv, hP):
+    """The same estimate in factored form: D-hat = Q^H H-hat G with the estimated channel H-hat = sum_q g_q M_q,
+    g = pinv(R_hP_est) hP -- DS.m:417-425 with W = R_Dij_hP pinv(R) (DS.m:283) and R_Dij_hP(:, q) = vec(Q^H M_q G)
+    (DS.m:260) substituted, WITHOUT the two 1e-8 thresholds (DS.m:263-264, 287-289).  The diagonal h-hat stays
+    W_diag hP (what the equaliser uses).  Checks the library's CHEST_ESTIMATOR_FACTORED mode; not the reference's values."""
+    g = Rinv @ hP
+    Hh = w["Mq"][0] * g[0]
+    for q in range(1, len(g)):
+        Hh = Hh + w["Mq"][q] * g[q]
+    return ("factored", w, Hh.tocsr()), Wv[w["diag_pos"]] @ hP
+
+
+def pseudo_channel_taps(S, wname):
+    """M[p, tap, n] = M_p[n, n - delay_tap] over the non-zero taps of the power delay profile (chest_set_pseudo_channels)."""
+    w, N = S["wf"][wname], S["N"]
+    delays = np.flatnonzero(S["chan"].Implementation["PowerDelayProfileNormalized"])
+    M = np.zeros((len(w["Mq"]), len(delays), N), dtype=complex)
+    for p, Mq in enumerate(w["Mq"]):
+        for t, d in enumerate(delays):
+            M[p, t, d:] = Mq.diagonal(-int(d))
+    return M
+
+
 def _offdiag_times(D, h, v):
     """(D - diag(h)) * v, DS.m:482-484 (h is the diagonal of D, so the diagonal is exactly 0)."""
+    if isinstance(D, tuple):                                   # factored estimate
+        _, w, Hh = D
+        return w["Q"].conj().T @ (Hh @ (w["G"] @ v)) - h * v
     if sp.issparse(D):
         Doff = D.copy()
         Doff.setdiag(0)
@@ -277,10 +306,11 @@ def _offdiag_times(D, h, v):
     return (D - np.diag(h)) @ v
 
 
-def ds_realization(S, draws, faithful=False, keep=False):
+def ds_realization(S, draws, faithful=False, keep=False, factored=()):
     """DS.m:352-563 for one i_rep.  Returns {'err': {...}, 'nbits': {...}} with integer bit-error
     counts err[scheme][csi][edge] of shape (n_SNR, 1+NrIterations) (column 0 = one-tap equaliser)
-    and, with keep=True, the intermediates used as golden vectors."""
+    and, with keep=True, the intermediates used as golden vectors.  `factored`: schemes whose D-hat of the cancellation is
+    formed as Q^H H-hat G (_dhat_factored) -- the restatement of the library's factored estimator, not of the reference."""
     cfg, P, N = S["cfg"], S["P"], S["N"]
     nS, nI = len(cfg.M_SNR_dB), cfg.NrIterations
     chan = S["chan"]
@@ -337,7 +367,10 @@ def ds_realization(S, draws, faithful=False, keep=False):
             err = out["err"][sc]
             y = w["Q"].conj().T @ (s_["r0"] + noise)                                        # :401-409
             hP = y[w["pil"]] / xP / np.sqrt(m["kappa"])                                     # :412-414
-            Dh, hh = _dhat(w, m["W"][isnr], hP, faithful)                                   # :417-428
+            if sc in factored:
+                Dh, hh = _dhat_factored(w, m["W"][isnr], m["Rinv"][isnr], hP)
+            else:
+                Dh, hh = _dhat(w, m["W"][isnr], hP, faithful)                               # :417-428
             xD_e, e1, e2 = detect(sc, y / hh)                                               # :429-447
             err["est"]["all"][isnr, 0], err["est"]["noedge"][isnr, 0] = e1, e2
             D, h = Dw[m["waveform"]], hw[m["waveform"]]
@@ -347,14 +380,17 @@ def ds_realization(S, draws, faithful=False, keep=False):
                 inter["y_" + sc].append(y); inter["hP_" + sc].append([hP])
                 inter["xD_est_" + sc].append([xD_e]); inter["xD_perf_" + sc].append([xD_p])
                 inter["hdiag_" + sc].append([hh])
-                if isnr == 0:
+                if isnr == 0 and not isinstance(Dh, tuple):
                     inter["Dhat0_" + sc] = Dh.toarray() if sp.issparse(Dh) else Dh
             for it in range(1, nI + 1):                                                     # :481
                 v = m["C"] @ np.concatenate([xP, cst.SymbolQuantization(xD_e)])
                 y_ic = y - _offdiag_times(Dh, hh, v)                                        # :482-484
                 hP = y_ic[w["pil"]] / xP / np.sqrt(m["kappa"])                              # :487-489
                 Wsel = m["W"] if it <= nI / 2 else m["W_noInt"]                             # :492
-                Dh, hh = _dhat(w, Wsel[isnr], hP, faithful)                                 # :493-517
+                if sc in factored:
+                    Dh, hh = _dhat_factored(w, Wsel[isnr], (m["Rinv"] if it <= nI / 2 else m["Rinv_noInt"])[isnr], hP)
+                else:
+                    Dh, hh = _dhat(w, Wsel[isnr], hP, faithful)                             # :493-517
                 xD_e, e1, e2 = detect(sc, y_ic / hh)                                        # :519-537
                 err["est"]["all"][isnr, it], err["est"]["noedge"][isnr, it] = e1, e2
                 vp = m["C"] @ np.concatenate([xP, cst.SymbolQuantization(xD_p)])

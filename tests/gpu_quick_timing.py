@@ -10,6 +10,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 precision = sys.argv[3] if len(sys.argv) > 3 else "fp64"
 setup = sys.argv[4] if len(sys.argv) > 4 else "product"      # product: the library's own setup (modem description included)
+estimator = sys.argv[5] if len(sys.argv) > 5 else "auto"
 t = time.time()
 if setup == "product":
     from chest_b200.simulation import DoublySelectiveSimulation
@@ -22,6 +23,7 @@ print("context setup s", time.time() - t)
 print("fp64 peak dmma TF/s", ctx.fp64_peak("dmma"), "dfma TF/s", ctx.fp64_peak("dfma"))
 print("work model", ctx.work_model(4))
 ctx.set_precision(precision)
+ctx.set_estimator_mode(estimator)
 ctx.set_profiling(True)
 for i in range(reps):
     t = time.time()
@@ -35,3 +37,4 @@ for sid, n in enumerate(("aux", "cod", "ofdm")):
     print(n, "BER est it0..4 @40dB", np.round(ber[-1, :, sid, 0, 0] / nb[sid, 0], 4),
           "perfect", np.round(ber[-1, :, sid, 1, 0] / nb[sid, 0], 4))
 print("launches", ctx.launch_count(), "precision", ctx.precision_info())
+print("estimator", {n: ctx.estimator_info(n) for n in ("aux", "cod", "ofdm")})

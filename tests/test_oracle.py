@@ -172,3 +172,25 @@ def test_reference_bundle_default_replays(ds_default):
     assert np.max(np.abs(last["hP_aux"][-1][-1] - B["last"].hP_est_FBMC_Aux_Temp)) < 1e-12
     assert np.max(np.abs(np.diag(last["D_O"]) - B["last"].h_OFDM)) < 1e-12
     assert np.max(np.abs(S["cod"].SIR_dB - B["setup"].SIR_dB_Cod)) < 1e-9
+
+
+def test_factored_estimate_equals_thresholded_weights_up_to_the_thresholds():
+    """D-hat = sum_p W_p hP(p) (DS.m:417-425) against its factored form Q^H (sum_q g_q M_q) G, g = pinv(R_hP_est) hP (what the
+    library's factored estimator applies): for CP-OFDM the 1e-8 thresholds of DS.m:263-264, 287-289 only remove rounding noise, so
+    the two agree to rounding; for FBMC they differ by the removed entries (a few 1e-5 of max|D-hat| at high SNR)."""
+    from oracle.ds import DSConfig, ds_setup, _dhat, _dhat_factored, _offdiag_times
+    S = ds_setup(DSConfig())
+    rng_ = np.random.default_rng(5)
+    for sc, tol_lo, tol_hi in (("ofdm", 0.0, 1e-11), ("aux", 1e-9, 1e-4)):
+        m = S["schemes"][sc]
+        w = S["wf"][m["waveform"]]
+        K, P = w["K"], S["P"]
+        for isnr in (0, len(S["Pn"]) - 1):
+            hP = (rng_.standard_normal(P) + 1j * rng_.standard_normal(P)) / np.sqrt(2)
+            v = (rng_.standard_normal(K) + 1j * rng_.standard_normal(K)) / np.sqrt(2)
+            Dh, hh = _dhat(w, m["W"][isnr], hP, False)
+            Df, hf = _dhat_factored(w, m["W"][isnr], m["Rinv"][isnr], hP)
+            assert np.array_equal(hh, hf)
+            a, b = _offdiag_times(Dh, hh, v), _offdiag_times(Df, hf, v)
+            dev = np.max(np.abs(a - b)) / np.max(np.abs(a))
+            assert tol_lo <= dev < tol_hi, (sc, isnr, dev)
