@@ -490,8 +490,10 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
             attr_smem = smem;
             CK(cudaFuncSetAttribute(k_perfect_fbmc<PERF_FBMC_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaFuncSetAttribute(k_demod_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(k_perfect_fbmc_det, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(k_est_factored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_perfect_fbmc_det<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_perfect_fbmc_det<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_est_factored<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_est_factored<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
     }
     return CHEST_OK;
@@ -571,7 +573,9 @@ int stage_factored_estimated_csi(Ctx* c, int n_rep, int it, int n_iter, const Ic
         fp.hest = c->hest.p; fp.tap_delay = c->d_tap_delay.p; fp.scratch = c->scratch.p;
         const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
         const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
-        k_est_factored<<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
+        static const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;
+        if (modem_fast24(md) && !no24) k_est_factored<true><<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
+        else k_est_factored<false><<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
         c->launches++;
         CK(cudaGetLastError());
     }
@@ -595,7 +599,9 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* 
             dp.y = w.y.p; dp.htrue = w.htrue.p; dp.h = c->h.p; dp.tap_delay = c->d_tap_delay.p; dp.zw_g = w.zw_g.p; dp.err = err;
             const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
             const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
-            k_perfect_fbmc_det<<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
+            static const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;      // development / tests: the generic chain
+            if (modem_fast24(md) && !no24) k_perfect_fbmc_det<true><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
+            else k_perfect_fbmc_det<false><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
             c->launches++;
             CK(cudaGetLastError());
             continue;

@@ -2517,6 +2517,176 @@ __device__ cplx* fft_shared_batch(cplx* a, cplx* b, const cplx* tw, const FftPla
     }
     return a;
 }
+// ---------------------------------------------------------------------------------------------
+// Specialised modem chain for 24-point transforms (the default geometry: 24 subcarriers; FBMC with TimeSpacing 12 and
+// overlapping factor 8, CP-OFDM): the generic kernels above spend most of their issue slots on index arithmetic (the chain is
+// issue-bound, not shared-memory-bound), so here every loop has compile-time trip counts and register-resident coefficients.
+//   * 24-point DFT as 6 x 4 (Cooley-Tukey, b = 4 b1 + b2, m = m1 + 6 m2): pass 1 = one 6-point DFT over b1 per (symbol, b2) and
+//     the twiddle e^{-+2 pi i b2 m1 / 24}; pass 2 = one 4-point DFT over b2 per (symbol, m1), in place.
+//   * overlap-add (FBMC.m:267-268) as a 16-tap FIR along the symbol index: s[12 a + b] = 1/24 sum_j p[12 j + b] Z_{a-j}[b + 12 (j & 1)];
+//     a work item owns one b and CH consecutive a: the 16 filter taps and the CH accumulators stay in registers, every
+//     Z value is read once per item.
+//   * fold (FBMC.m:297-302): a_k[m] = sum_o p[24 o + m] r[12 (k + 2 o + h) + b], m = b + 12 h; item = one m and CK consecutive k.
+template <bool INV>
+__device__ __forceinline__ void dft3_regs(cplx& x0, cplx& x1, cplx& x2) {
+    const double h3 = 0.86602540378443864676;
+    const cplx sm = cadd(x1, x2), df = csub(x1, x2);
+    const cplx base = cmake(x0.x - 0.5 * sm.x, x0.y - 0.5 * sm.y);
+    const cplx rot = INV ? cmake(-h3 * df.y, h3 * df.x) : cmake(h3 * df.y, -h3 * df.x);     // forward: -i h3 df
+    x0 = cadd(x0, sm); x1 = cadd(base, rot); x2 = csub(base, rot);
+}
+// X[m] = sum_b x[b] e^{-+2 pi i b m / 6}: two 3-point DFTs over the even / odd inputs, then X[m] = E[m mod 3] + w6^m O[m mod 3]
+template <bool INV>
+__device__ __forceinline__ void dft6_regs(cplx (&x)[6]) {
+    cplx e0 = x[0], e1 = x[2], e2 = x[4], o0 = x[1], o1 = x[3], o2 = x[5];
+    dft3_regs<INV>(e0, e1, e2);
+    dft3_regs<INV>(o0, o1, o2);
+    const double c = 0.5, sn = INV ? 0.86602540378443864676 : -0.86602540378443864676;     // w6 = c + i sn
+    const cplx t1 = cmake(c * o1.x - sn * o1.y, c * o1.y + sn * o1.x);                      // w6   o1
+    const cplx t2 = cmake(-c * o2.x - sn * o2.y, -c * o2.y + sn * o2.x);                    // w6^2 o2 = (-c + i sn) o2
+    x[0] = cadd(e0, o0); x[3] = csub(e0, o0);                  // w6^3 = -1
+    x[1] = cadd(e1, t1); x[4] = csub(e1, t1);                  // w6^4 = -w6
+    x[2] = cadd(e2, t2); x[5] = csub(e2, t2);                  // w6^5 = -w6^2
+}
+template <bool INV>
+__device__ __forceinline__ void dft4_regs(cplx (&x)[4]) {
+    const cplx s02 = cadd(x[0], x[2]), d02 = csub(x[0], x[2]), s13 = cadd(x[1], x[3]), d13 = csub(x[1], x[3]);
+    const cplx r = INV ? cmake(-d13.y, d13.x) : cmake(d13.y, -d13.x);
+    x[0] = cadd(s02, s13); x[1] = cadd(d02, r); x[2] = csub(s02, s13); x[3] = csub(d02, r);
+}
+// n_sym transforms of 24 points: A (input, destroyed) -> B (result), tw[m] = e^{-2 pi i m / 24}.  Ends with a block barrier.
+template <bool INV>
+__device__ __forceinline__ void fft24_batch(const cplx* __restrict__ A, cplx* __restrict__ B, const cplx* __restrict__ tw, int n_sym) {
+    for (int item = threadIdx.x; item < n_sym * 4; item += blockDim.x) {
+        const int k = item >> 2, b2 = item & 3;
+        const cplx* a = A + k * 24 + b2;
+        cplx x[6];
+#pragma unroll
+        for (int b1 = 0; b1 < 6; ++b1) x[b1] = a[4 * b1];
+        dft6_regs<INV>(x);
+        cplx* o = B + k * 24 + 6 * b2;
+        o[0] = x[0];
+#pragma unroll
+        for (int m1 = 1; m1 < 6; ++m1) {
+            cplx w = tw[b2 * m1];
+            if (INV) w.y = -w.y;
+            o[m1] = cmul(x[m1], w);
+        }
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < n_sym * 6; item += blockDim.x) {
+        const int k = item / 6, m1 = item - k * 6;
+        cplx* a = B + k * 24 + m1;
+        cplx x[4];
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) x[b2] = a[6 * b2];
+        dft4_regs<INV>(x);
+#pragma unroll
+        for (int m2 = 0; m2 < 4; ++m2) a[6 * m2] = x[m2];
+    }
+    __syncthreads();
+}
+// FBMC overlap-add for nfft = 24, TimeSpacing = 12, O = 8: Z [Ksym][24] -> S [N].  No trailing barrier.
+template <int CH>
+__device__ __forceinline__ void fbmc_overlap_add24(const cplx* __restrict__ Z, cplx* __restrict__ S, const double* __restrict__ filt,
+                                                   int Ksym, int N) {
+    const int A = (N + 11) / 12, nchunk = (A + CH - 1) / CH;
+    for (int item = threadIdx.x; item < 12 * nchunk; item += blockDim.x) {
+        const int ch = item / 12, b = item - ch * 12, a0 = ch * CH;
+        double c[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) c[j] = filt[12 * j + b];
+        cplx acc[CH];
+#pragma unroll
+        for (int ai = 0; ai < CH; ++ai) acc[ai] = cmake(0.0, 0.0);
+#pragma unroll
+        for (int d = 0; d < 15 + CH; ++d) {
+            const int kk = a0 - 15 + d;
+            if (kk < 0 || kk >= Ksym) continue;
+            const cplx zA = Z[kk * 24 + b], zB = Z[kk * 24 + b + 12];
+#pragma unroll
+            for (int ai = 0; ai < CH; ++ai) {
+                const int j = 15 + ai - d;                      // compile-time after unrolling
+                if (j < 0 || j > 15) continue;
+                const cplx z = (j & 1) ? zB : zA;
+                acc[ai].x = fma(c[j], z.x, acc[ai].x); acc[ai].y = fma(c[j], z.y, acc[ai].y);
+            }
+        }
+#pragma unroll
+        for (int ai = 0; ai < CH; ++ai) {
+            const int nn = 12 * (a0 + ai) + b;
+            if (nn < N) S[nn] = cmake(acc[ai].x * (1.0 / 24), acc[ai].y * (1.0 / 24));
+        }
+    }
+}
+// FBMC fold for nfft = 24, TimeSpacing = 12, O = 8: R [N] -> Aout [Ksym][24].  No trailing barrier.
+template <int CK>
+__device__ __forceinline__ void fbmc_fold24(const cplx* __restrict__ R, cplx* __restrict__ Aout, const double* __restrict__ filt,
+                                            int Ksym, int N) {
+    const int nchunk = (Ksym + CK - 1) / CK;
+    for (int item = threadIdx.x; item < 24 * nchunk; item += blockDim.x) {
+        const int ch = item / 24, m = item - ch * 24, k0 = ch * CK, h = m >= 12 ? 1 : 0, b = m - 12 * h;
+        double c[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) c[o] = filt[24 * o + m];
+        cplx acc[CK];
+#pragma unroll
+        for (int ki = 0; ki < CK; ++ki) acc[ki] = cmake(0.0, 0.0);
+#pragma unroll
+        for (int d = 0; d < CK + 14; ++d) {
+            const int idx = 12 * (k0 + h + d) + b;
+            if (idx >= N) continue;
+            const cplx r = R[idx];
+#pragma unroll
+            for (int ki = 0; ki < CK; ++ki) {
+                const int e = d - ki;                           // = 2 o
+                if (e < 0 || (e & 1) || e > 14) continue;
+                acc[ki].x = fma(c[e / 2], r.x, acc[ki].x); acc[ki].y = fma(c[e / 2], r.y, acc[ki].y);
+            }
+        }
+#pragma unroll
+        for (int ki = 0; ki < CK; ++ki) if (k0 + ki < Ksym) Aout[(k0 + ki) * 24 + m] = acc[ki];
+    }
+}
+// The chain  symbols in X0 [Ksym][24] (already phase-shifted and scaled)  ->  demodulated bins Y [Ksym][24]  with the banded
+// channel `taps` ([T][N], tap t delayed by tap_delay[t]) in between.  Returns Y (= X1); X0 is free afterwards.
+// Requires md.nfft == 24 and, for FBMC, time_spacing == 12, O == 8.  The caller has synchronised after filling X0.
+__device__ __forceinline__ cplx* modem_chain24(const ModemDev& md, cplx* X0, cplx* X1, const cplx* tw, const double* filt,
+                                               const cplx* __restrict__ taps, int T, const int* __restrict__ tap_delay, int N) {
+    const int Ksym = md.Ksym, TS = md.time_spacing, tid = threadIdx.x, nthr = blockDim.x;
+    fft24_batch<true>(X0, X1, tw, Ksym);                                   // Z in X1
+    if (md.kind == 0) fbmc_overlap_add24<5>(X1, X0, filt, Ksym, N);        // s in X0
+    else
+        for (int nn = tid; nn < N; nn += nthr) {                           // cyclic prefix + zero guards (OFDM.m:158-164)
+            const int q = nn - md.zero_guard, k = q >= 0 ? q / TS : Ksym;
+            cplx acc = cmake(0.0, 0.0);
+            if (k < Ksym) { int m = q - k * TS - md.cp; if (m < 0) m += 24; acc = X1[k * 24 + m]; }
+            X0[nn] = cmake(acc.x * (1.0 / 24), acc.y * (1.0 / 24));
+        }
+    __syncthreads();
+    for (int nn = tid; nn < N; nn += nthr) {                               // r = H s, into X1
+        cplx acc = cmake(0.0, 0.0);
+        for (int t = 0; t < T; ++t) {
+            const int d = tap_delay[t];
+            if (nn >= d) cfma(acc, ld_nc(taps + (int64_t)t * N + nn), X0[nn - d]);
+        }
+        X1[nn] = acc;
+    }
+    __syncthreads();
+    if (md.kind == 0) fbmc_fold24<6>(X1, X0, filt, Ksym, N);               // folded symbols in X0
+    else
+        for (int idx = tid; idx < Ksym * 24; idx += nthr) {                // drop the cyclic prefix (OFDM.m:172-176)
+            const int k = idx / 24, m = idx - k * 24;
+            X0[idx] = X1[md.zero_guard + k * TS + md.cp + m];
+        }
+    __syncthreads();
+    fft24_batch<false>(X0, X1, tw, Ksym);                                  // Y in X1
+    return X1;
+}
+__host__ __device__ __forceinline__ bool modem_fast24(const ModemDev& md) {
+    return md.nfft == 24 && (md.kind == 1 || (md.time_spacing == 12 && md.O == 8 && md.Np == 192));
+}
+
 template <int CW>
 __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfect_fbmc(PerfFbmcParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
@@ -2623,6 +2793,7 @@ struct PerfDetParams {
     const cplx* v_base; const cplx* y; const cplx* htrue; const cplx* h; const int* tap_delay;
     uint8_t* zw_g; uint32_t* err;
 };
+template <bool FAST24>
 __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfect_fbmc_det(PerfDetParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
@@ -2660,58 +2831,64 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
             X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
         }
         __syncthreads();
-        cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
-        cplx* Xo = (Xz == X0) ? X1 : X0;
-        const double inv_n = 1.0 / n;
-        for (int nn = tid; nn < N; nn += nthr) {
-            cplx acc = cmake(0.0, 0.0);
-            if (fbmc) {                                         // overlap-add (FBMC.m:267-268)
-                int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
-                const int k_hi = min(Ksym - 1, nn / TS);
-                int tap = nn - k_lo * TS, mm = tap % n;
-                const cplx* zc = Xz + k_lo * n;
-                for (int k = k_lo; k <= k_hi; ++k) {
-                    if (tap >= 0 && tap < md.Np) {
-                        const cplx z = zc[mm];
-                        const double pf = filt[tap];
-                        acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+        cplx* Y;
+        if (FAST24) {
+            Y = modem_chain24(md, X0, X1, tw, filt, p.h + (int64_t)rep * p.T * N, p.T, p.tap_delay, N);
+            Xe = X0;
+        } else {
+            cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
+            cplx* Xo = (Xz == X0) ? X1 : X0;
+            const double inv_n = 1.0 / n;
+            for (int nn = tid; nn < N; nn += nthr) {
+                cplx acc = cmake(0.0, 0.0);
+                if (fbmc) {                                         // overlap-add (FBMC.m:267-268)
+                    int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+                    const int k_hi = min(Ksym - 1, nn / TS);
+                    int tap = nn - k_lo * TS, mm = tap % n;
+                    const cplx* zc = Xz + k_lo * n;
+                    for (int k = k_lo; k <= k_hi; ++k) {
+                        if (tap >= 0 && tap < md.Np) {
+                            const cplx z = zc[mm];
+                            const double pf = filt[tap];
+                            acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+                        }
+                        tap -= TS; mm -= TS; if (mm < 0) mm += n;
+                        zc += n;
                     }
-                    tap -= TS; mm -= TS; if (mm < 0) mm += n;
-                    zc += n;
+                } else {                                            // cyclic prefix + zero guards (OFDM.m:158-164)
+                    const int q = nn - md.zero_guard, k = q >= 0 ? q / TS : Ksym;
+                    if (k < Ksym) { int m = q - k * TS - md.cp; if (m < 0) m += n; acc = Xz[k * n + m]; }
                 }
-            } else {                                            // cyclic prefix + zero guards (OFDM.m:158-164)
-                const int q = nn - md.zero_guard, k = q >= 0 ? q / TS : Ksym;
-                if (k < Ksym) { int m = q - k * TS - md.cp; if (m < 0) m += n; acc = Xz[k * n + m]; }
+                Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
             }
-            Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
-        }
-        __syncthreads();
-        const cplx* hr = p.h + (int64_t)rep * p.T * N;
-        for (int nn = tid; nn < N; nn += nthr) {                // r = H s
-            cplx acc = cmake(0.0, 0.0);
-            for (int t = 0; t < p.T; ++t) {
-                const int d = p.tap_delay[t];
-                if (nn >= d) cfma(acc, hr[(int64_t)t * N + nn], Xo[nn - d]);
-            }
-            Xz[nn] = acc;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < nx; idx += nthr) {            // fold by O (FBMC.m:297-302) / drop the cyclic prefix (OFDM.m:172-176)
-            const int k = idx / n, m = idx - k * n;
-            cplx acc = cmake(0.0, 0.0);
-            if (fbmc) {
-                const cplx* seg = Xz + k * TS + m;
-                for (int o = 0; o < md.O; ++o) {
-                    const double pf = filt[o * n + m];
-                    const cplx v = seg[o * n];
-                    acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+            __syncthreads();
+            const cplx* hr = p.h + (int64_t)rep * p.T * N;
+            for (int nn = tid; nn < N; nn += nthr) {                // r = H s
+                cplx acc = cmake(0.0, 0.0);
+                for (int t = 0; t < p.T; ++t) {
+                    const int d = p.tap_delay[t];
+                    if (nn >= d) cfma(acc, hr[(int64_t)t * N + nn], Xo[nn - d]);
                 }
-            } else acc = Xz[md.zero_guard + k * TS + md.cp + m];
-            Xo[idx] = acc;
+                Xz[nn] = acc;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nx; idx += nthr) {            // fold by O (FBMC.m:297-302) / drop the cyclic prefix (OFDM.m:172-176)
+                const int k = idx / n, m = idx - k * n;
+                cplx acc = cmake(0.0, 0.0);
+                if (fbmc) {
+                    const cplx* seg = Xz + k * TS + m;
+                    for (int o = 0; o < md.O; ++o) {
+                        const double pf = filt[o * n + m];
+                        const cplx v = seg[o * n];
+                        acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+                    }
+                } else acc = Xz[md.zero_guard + k * TS + md.cp + m];
+                Xo[idx] = acc;
+            }
+            __syncthreads();
+            Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, Ksym);
+            Xe = (Y == X0) ? X1 : X0;
         }
-        __syncthreads();
-        cplx* Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, Ksym);
-        Xe = (Y == X0) ? X1 : X0;
         for (int i = tid; i < K; i += nthr) {                   // y_ic = y - U + h v, x = y_ic / h
             const int k = i / L, l = i - k * L;
             cplx u0 = Y[k * n + bins[l]];
@@ -3039,6 +3216,7 @@ struct EstFactParams {
     const cplx* hest; const int* tap_delay;
     cplx* scratch;
 };
+template <bool FAST24>
 __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
@@ -3072,57 +3250,61 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_est_f
         X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
     }
     __syncthreads();
-    cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
-    cplx* Xo = (Xz == X0) ? X1 : X0;
-    const double inv_n = 1.0 / n;
-    for (int nn = tid; nn < N; nn += nthr) {
-        cplx acc = cmake(0.0, 0.0);
-        if (fbmc) {                                             // overlap-add (FBMC.m:267-268)
-            int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
-            const int k_hi = min(Ksym - 1, nn / TS);
-            int tap = nn - k_lo * TS, mm = tap % n;
-            const cplx* zc = Xz + k_lo * n;
-            for (int k = k_lo; k <= k_hi; ++k) {
-                if (tap >= 0 && tap < md.Np) {
-                    const cplx z = zc[mm];
-                    const double pf = filt[tap];
-                    acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+    const cplx* Y;
+    if (FAST24) Y = modem_chain24(md, X0, X1, tw, filt, p.hest + (int64_t)col * p.T * N, p.T, p.tap_delay, N);
+    else {
+        cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
+        cplx* Xo = (Xz == X0) ? X1 : X0;
+        const double inv_n = 1.0 / n;
+        for (int nn = tid; nn < N; nn += nthr) {
+            cplx acc = cmake(0.0, 0.0);
+            if (fbmc) {                                             // overlap-add (FBMC.m:267-268)
+                int k_lo = (nn - md.Np + TS) / TS; if (nn - md.Np + 1 <= 0) k_lo = 0;
+                const int k_hi = min(Ksym - 1, nn / TS);
+                int tap = nn - k_lo * TS, mm = tap % n;
+                const cplx* zc = Xz + k_lo * n;
+                for (int k = k_lo; k <= k_hi; ++k) {
+                    if (tap >= 0 && tap < md.Np) {
+                        const cplx z = zc[mm];
+                        const double pf = filt[tap];
+                        acc.x = fma(pf, z.x, acc.x); acc.y = fma(pf, z.y, acc.y);
+                    }
+                    tap -= TS; mm -= TS; if (mm < 0) mm += n;
+                    zc += n;
                 }
-                tap -= TS; mm -= TS; if (mm < 0) mm += n;
-                zc += n;
+            } else {                                                // cyclic prefix + zero guards (OFDM.m:158-164)
+                const int q = nn - md.zero_guard, k = q >= 0 ? q / TS : Ksym;
+                if (k < Ksym) { int m = q - k * TS - md.cp; if (m < 0) m += n; acc = Xz[k * n + m]; }
             }
-        } else {                                                // cyclic prefix + zero guards (OFDM.m:158-164)
-            const int q = nn - md.zero_guard, k = q >= 0 ? q / TS : Ksym;
-            if (k < Ksym) { int m = q - k * TS - md.cp; if (m < 0) m += n; acc = Xz[k * n + m]; }
+            Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
         }
-        Xo[nn] = cmake(acc.x * inv_n, acc.y * inv_n);
-    }
-    __syncthreads();
-    const cplx* hr = p.hest + (int64_t)col * p.T * N;
-    for (int nn = tid; nn < N; nn += nthr) {                    // r = H-hat s
-        cplx acc = cmake(0.0, 0.0);
-        for (int t = 0; t < p.T; ++t) {
-            const int d = p.tap_delay[t];
-            if (nn >= d) cfma(acc, ld_nc(hr + (int64_t)t * N + nn), Xo[nn - d]);
-        }
-        Xz[nn] = acc;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < nx; idx += nthr) {                // fold by O (FBMC.m:297-302) / drop the cyclic prefix (OFDM.m:172-176)
-        const int k = idx / n, m = idx - k * n;
-        cplx acc = cmake(0.0, 0.0);
-        if (fbmc) {
-            const cplx* seg = Xz + k * TS + m;
-            for (int o = 0; o < md.O; ++o) {
-                const double pf = filt[o * n + m];
-                const cplx v = seg[o * n];
-                acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+        __syncthreads();
+        const cplx* hr = p.hest + (int64_t)col * p.T * N;
+        for (int nn = tid; nn < N; nn += nthr) {                    // r = H-hat s
+            cplx acc = cmake(0.0, 0.0);
+            for (int t = 0; t < p.T; ++t) {
+                const int d = p.tap_delay[t];
+                if (nn >= d) cfma(acc, ld_nc(hr + (int64_t)t * N + nn), Xo[nn - d]);
             }
-        } else acc = Xz[md.zero_guard + k * TS + md.cp + m];
-        Xo[idx] = acc;
+            Xz[nn] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nx; idx += nthr) {                // fold by O (FBMC.m:297-302) / drop the cyclic prefix (OFDM.m:172-176)
+            const int k = idx / n, m = idx - k * n;
+            cplx acc = cmake(0.0, 0.0);
+            if (fbmc) {
+                const cplx* seg = Xz + k * TS + m;
+                for (int o = 0; o < md.O; ++o) {
+                    const double pf = filt[o * n + m];
+                    const cplx v = seg[o * n];
+                    acc.x = fma(pf, v.x, acc.x); acc.y = fma(pf, v.y, acc.y);
+                }
+            } else acc = Xz[md.zero_guard + k * TS + md.cp + m];
+            Xo[idx] = acc;
+        }
+        __syncthreads();
+        Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, Ksym);
     }
-    __syncthreads();
-    const cplx* Y = fft_shared_batch(Xo, Xz, tw, md.plan, false, Ksym);
     for (int i = tid; i < K; i += nthr) {                       // y_ic = y - U + h-hat v
         const int k = i / L, l = i - k * L;
         cplx u0 = Y[k * n + bins[l]];
