@@ -97,7 +97,7 @@ struct Waveform {
     // chest_setup_correlations, whether any wrapped (corner) entry is non-zero, the largest |R_Dij_hP| entry the threshold removed,
     // and the EST units of this waveform's factored schemes
     DevBuf<cplx> Mq; int mq_P = 0; bool mq_corner = false; double rsup_zeroed_max = 0;
-    DevBuf<int> ef_units; int ef_n_units = 0;
+    DevBuf<int4> ef_desc; int ef_n_units = 0;
     DevBuf<int> g_lo_d, g_hi_d;
     int tile = 64;              // CTA tile size of the GEMMs on this waveform (48 or 64)
     double flops_d = 0, flops_demod = 0, flops_mod = 0;
@@ -554,7 +554,7 @@ int stage_factored_estimated_csi(Ctx* c, int n_rep, int it, int n_iter, const Ic
         Waveform& w = c->wf[wfi];
         if (!w.ef_n_units) continue;
         EstChanParams ep{};
-        ep.units = w.ef_units.p; ep.ctas = c->ctas.p; ep.Mq = w.Mq.p; ep.hest = c->hest.p; ep.n_rep = n_rep; ep.TN = c->T * N;
+        ep.desc = w.ef_desc.p; ep.Mq = w.Mq.p; ep.hest = c->hest.p; ep.n_rep = n_rep; ep.TN = c->T * N;
         int Pmax = 1;
         for (int si = 0; si < 3; ++si) {
             Scheme& s = c->sch[si];
@@ -568,13 +568,13 @@ int stage_factored_estimated_csi(Ctx* c, int n_rep, int it, int n_iter, const Ic
         CK(cudaGetLastError());
         const ModemDev& md = w.modem;
         EstFactParams fp{};
-        fp.md = md; fp.units = w.ef_units.p; fp.ctas = c->ctas.p; fp.K_max = c->K_max; fp.n_rep = n_rep; fp.T = c->T; fp.N = N; fp.K = w.K;
+        fp.md = md; fp.desc = w.ef_desc.p; fp.K_max = c->K_max; fp.n_rep = n_rep; fp.T = c->T; fp.N = N; fp.K = w.K;
         for (int si = 0; si < 3; ++si) fp.y[si] = ip.sch[si].y;
         fp.hest = c->hest.p; fp.tap_delay = c->d_tap_delay.p; fp.scratch = c->scratch.p;
         const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
         const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
         static const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;
-        if (modem_fast24(md) && !no24) k_est_factored<true><<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
+        if (modem_fast24(md) && !no24 && w.K <= CHAIN24_NE * PERF_FBMC_THREADS && N <= CHAIN24_NH * PERF_FBMC_THREADS) k_est_factored<true><<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
         else k_est_factored<false><<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
         c->launches++;
         CK(cudaGetLastError());
@@ -600,7 +600,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* 
             const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
             const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
             static const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;      // development / tests: the generic chain
-            if (modem_fast24(md) && !no24) k_perfect_fbmc_det<true><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
+            if (modem_fast24(md) && !no24 && w.K <= CHAIN24_NE * PERF_FBMC_THREADS && N <= CHAIN24_NH * PERF_FBMC_THREADS) k_perfect_fbmc_det<true><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
             else k_perfect_fbmc_det<false><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
             c->launches++;
             CK(cudaGetLastError());
@@ -809,19 +809,19 @@ int build_ctas(Ctx* c, int n_rep) {
         // schemes whose estimated-CSI cancellation runs in factored form (k_est_channel + k_est_factored) come after the tile-form
         // EST units: k_ic_main stops at n_est_units, k_ic_light walks all of them
         std::vector<IcCta> ef;
-        std::vector<int> ef_list[2];
+        std::vector<int4> ef_list[2];
         for (int si = 0; si < 3; ++si) {
             int rc = est_factored_usable(c, si, c->est_fact[si]); if (rc) return rc;
         }
         for (auto* lst : {&e1, &e2})
             for (const IcCta& u : *lst) (c->est_fact[u.scheme_or_wf] ? ef : v).push_back(u);
         c->n_est_units = (int)v.size();
-        for (const IcCta& u : ef) { ef_list[c->sch[u.scheme_or_wf].waveform].push_back((int)v.size()); v.push_back(u); }
+        for (const IcCta& u : ef) { ef_list[c->sch[u.scheme_or_wf].waveform].push_back(make_int4((int)v.size(), u.scheme_or_wf, u.snr, u.first)); v.push_back(u); }
         size_t ef_cols = 0;
         for (int wfi = 0; wfi < 2; ++wfi) {
             Waveform& w = c->wf[wfi];
             w.ef_n_units = (int)ef_list[wfi].size();
-            if (w.ef_n_units) CK(w.ef_units.upload(ef_list[wfi], c->stream));
+            if (w.ef_n_units) CK(w.ef_desc.upload(ef_list[wfi], c->stream));
             ef_cols = std::max(ef_cols, (size_t)w.ef_n_units * NC_MAX);
         }
         if (ef_cols) CK(c->hest.alloc(ef_cols * c->T * c->N));

@@ -2651,6 +2651,7 @@ __device__ __forceinline__ void fbmc_fold24(const cplx* __restrict__ R, cplx* __
 // The chain  symbols in X0 [Ksym][24] (already phase-shifted and scaled)  ->  demodulated bins Y [Ksym][24]  with the banded
 // channel `taps` ([T][N], tap t delayed by tap_delay[t]) in between.  Returns Y (= X1); X0 is free afterwards.
 // Requires md.nfft == 24 and, for FBMC, time_spacing == 12, O == 8.  The caller has synchronised after filling X0.
+template <int NH>
 __device__ __forceinline__ cplx* modem_chain24(const ModemDev& md, cplx* X0, cplx* X1, const cplx* tw, const double* filt,
                                                const cplx* __restrict__ taps, int T, const int* __restrict__ tap_delay, int N) {
     const int Ksym = md.Ksym, TS = md.time_spacing, tid = threadIdx.x, nthr = blockDim.x;
@@ -2664,7 +2665,23 @@ __device__ __forceinline__ cplx* modem_chain24(const ModemDev& md, cplx* X0, cpl
             X0[nn] = cmake(acc.x * (1.0 / 24), acc.y * (1.0 / 24));
         }
     __syncthreads();
-    for (int nn = tid; nn < N; nn += nthr) {                               // r = H s, into X1
+    if (NH > 0) {                                                          // r = H s, into X1: N <= NH * blockDim.x; the tap loads of a
+        cplx acc[NH > 0 ? NH : 1];                                         // thread's samples are issued together
+#pragma unroll
+        for (int u = 0; u < NH; ++u) acc[u] = cmake(0.0, 0.0);
+        for (int t = 0; t < T; ++t) {
+            const int d = tap_delay[t];
+            const cplx* tp = taps + (int64_t)t * N;
+            cplx hv[NH > 0 ? NH : 1];
+#pragma unroll
+            for (int u = 0; u < NH; ++u) { const int nn = tid + u * nthr; hv[u] = nn < N ? ld_nc(tp + nn) : cmake(0.0, 0.0); }
+#pragma unroll
+            for (int u = 0; u < NH; ++u) { const int nn = tid + u * nthr; if (nn < N && nn >= d) cfma(acc[u], hv[u], X0[nn - d]); }
+        }
+#pragma unroll
+        for (int u = 0; u < NH; ++u) { const int nn = tid + u * nthr; if (nn < N) X1[nn] = acc[u]; }
+    } else
+    for (int nn = tid; nn < N; nn += nthr) {
         cplx acc = cmake(0.0, 0.0);
         for (int t = 0; t < T; ++t) {
             const int d = tap_delay[t];
@@ -2685,6 +2702,61 @@ __device__ __forceinline__ cplx* modem_chain24(const ModemDev& md, cplx* X0, cpl
 }
 __host__ __device__ __forceinline__ bool modem_fast24(const ModemDev& md) {
     return md.nfft == 24 && (md.kind == 1 || (md.time_spacing == 12 && md.O == 8 && md.Np == 192));
+}
+// Head and tail of a chain column with every global operand of a thread's NE symbols loaded in one batch (the chain kernels
+// are latency-bound: independent loads in flight are what hides it).  K <= NE * blockDim.x.
+//   head: X0[symbol][bin] = v * phase * norm (the modulator's input),  e = y + h v  (kept in registers across the chain)
+//   tail: out = e - conj(phase) Y[bin] / (norm F)                      (divided by hdiv where the caller equalises right away)
+#define CHAIN24_NE 6
+#define CHAIN24_NH 5
+template <int NE>
+__device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, const cplx* __restrict__ hcol,
+                                             int hstride, const cplx* __restrict__ ycol, int K, cplx (&e)[NE]) {
+    const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
+    const bool fbmc = md.kind == 0;
+    cplx vv[NE], hh[NE], ph[NE];
+    int bl[NE];
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int i = tid + u * nthr;
+        const bool ok = i < K;
+        vv[u] = ok ? ld_nc(vcol + (int64_t)i * NC_MAX) : cmake(0.0, 0.0);
+        hh[u] = ok ? ld_nc(hcol + (int64_t)i * hstride) : cmake(0.0, 0.0);
+        e[u] = ok ? ld_nc(ycol + i) : cmake(0.0, 0.0);
+        ph[u] = (ok && fbmc) ? ld_nc(md.phase + i) : cmake(1.0, 0.0);
+        bl[u] = ok ? md.bin[i % L] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int i = tid + u * nthr;
+        if (i >= K) continue;
+        cfma(e[u], hh[u], vv[u]);
+        const cplx x = cmul(vv[u], ph[u]);
+        X0[(i / L) * 24 + bl[u]] = cmake(x.x * md.norm, x.y * md.norm);
+    }
+}
+template <int NE, bool DIV>
+__device__ __forceinline__ void chain24_tail(const ModemDev& md, const cplx* Y, const int* bins, const cplx (&e)[NE],
+                                             const cplx* __restrict__ hdiv, cplx* out, int ostride, int K) {
+    const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
+    const bool fbmc = md.kind == 0;
+    cplx ph[NE], hd[NE];
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int i = tid + u * nthr;
+        const bool ok = i < K;
+        ph[u] = (ok && fbmc) ? ld_nc(md.phase + i) : cmake(1.0, 0.0);
+        if (DIV) hd[u] = ok ? ld_nc(hdiv + i) : cmake(1.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int i = tid + u * nthr;
+        if (i >= K) continue;
+        const int k = i / L, l = i - k * L;
+        const cplx u0 = cmulc(ph[u], Y[k * 24 + bins[l]]);
+        const cplx r = cmake(e[u].x - u0.x * md.inv_demod, e[u].y - u0.y * md.inv_demod);
+        out[(int64_t)i * ostride] = DIV ? cdiv_fast(r, hd[u]) : r;
+    }
 }
 
 template <int CW>
@@ -2794,7 +2866,7 @@ struct PerfDetParams {
     uint8_t* zw_g; uint32_t* err;
 };
 template <bool FAST24>
-__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfect_fbmc_det(PerfDetParams p) {
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? 6 : PERF_FBMC_MIN_CTAS) k_perfect_fbmc_det(PerfDetParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
@@ -2817,6 +2889,17 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
     if (p.it == 0) {
         for (int i = tid; i < K; i += nthr) X1[i] = cdiv_fast(ycol[i], ht[i]);
         Xe = X1;
+    } else if (FAST24) {                                       // K <= CHAIN24_NE * 128, N <= CHAIN24_NH * 128 (the host checks)
+        if (tid < 24) tw[tid] = md.tw[tid];
+        if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+        if (tid < L) bins[tid] = md.bin[tid];
+        if (L < 24) { for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0); __syncthreads(); }
+        cplx e[CHAIN24_NE];
+        chain24_head<CHAIN24_NE>(md, X0, p.v_base + p.voff[col], ht, 1, ycol, K, e);
+        __syncthreads();
+        const cplx* Y = modem_chain24<CHAIN24_NH>(md, X0, X1, tw, filt, p.h + (int64_t)rep * p.T * N, p.T, p.tap_delay, N);
+        chain24_tail<CHAIN24_NE, true>(md, Y, bins, e, ht, X0, 1, K);
+        Xe = X0;
     } else {
         for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
         if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
@@ -2832,10 +2915,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
         }
         __syncthreads();
         cplx* Y;
-        if (FAST24) {
-            Y = modem_chain24(md, X0, X1, tw, filt, p.h + (int64_t)rep * p.T * N, p.T, p.tap_delay, N);
-            Xe = X0;
-        } else {
+        {
             cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
             cplx* Xo = (Xz == X0) ? X1 : X0;
             const double inv_n = 1.0 / n;
@@ -3164,7 +3244,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod
 // k_est_channel: one CTA per EST unit (scheme, SNR point, 16 realizations): g = Rinv hP for the 16 columns, then
 // H-hat[column][tap][n] = sum_q g[q][column] M[q][tap][n]; the pseudo-channels are read once per 16 columns.
 struct EstChanParams {
-    const int* units; const IcCta* ctas;
+    const int4* desc;                                            // per unit slot: {unit, scheme, SNR point, first realization}
     const cplx* hP[3]; const cplx* rinv[3]; int P[3];            // per scheme: pilot estimates [snr][rep][P], Rinv [snr][P x P col-major]
     const cplx* Mq;                                              // [P][T * N] pseudo-channel taps of the waveform
     cplx* hest;                                                  // [unit slot * 16 + column][T * N]
@@ -3174,7 +3254,8 @@ struct EstChanParams {
 __global__ void __launch_bounds__(EST_CHAN_THREADS) k_est_channel(EstChanParams p) {
     extern __shared__ __align__(16) cplx ec_smem[];
     constexpr int NC = NC_MAX;
-    const IcCta cta = p.ctas[p.units[blockIdx.x]];
+    const int4 dsc = p.desc[blockIdx.x];
+    IcCta cta; cta.scheme_or_wf = dsc.y; cta.snr = dsc.z; cta.first = dsc.w;
     const int si = cta.scheme_or_wf, P = p.P[si], tid = threadIdx.x, nthr = blockDim.x;
     cplx* hp = ec_smem;                                          // [P][NC]
     cplx* g = hp + P * NC;                                       // [P][NC]
@@ -3196,10 +3277,16 @@ __global__ void __launch_bounds__(EST_CHAN_THREADS) k_est_channel(EstChanParams 
         cplx acc[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[c] = cmake(0.0, 0.0);
-        for (int q = 0; q < P; ++q) {
-            const cplx m = ld_nc(p.Mq + (int64_t)q * p.TN + e);
+        for (int q0 = 0; q0 < P; q0 += 8) {                       // eight pseudo-channel values in flight per thread
+            cplx m[8];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) cfma(acc[c], m, g[q * NC + c]);
+            for (int u = 0; u < 8; ++u) m[u] = q0 + u < P ? ld_nc(p.Mq + (int64_t)(q0 + u) * p.TN + e) : cmake(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (q0 + u >= P) break;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) cfma(acc[c], m[u], g[(q0 + u) * NC + c]);
+            }
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) out[(int64_t)c * p.TN + e] = acc[c];
@@ -3211,21 +3298,22 @@ __global__ void __launch_bounds__(EST_CHAN_THREADS) k_est_channel(EstChanParams 
 // v from the unit's scratch, y_ic into it (what k_ic_main writes for the tile form of W); the chain is k_perfect_fbmc_det's.
 struct EstFactParams {
     ModemDev md;
-    const int* units; const IcCta* ctas;
+    const int4* desc;                                           // per unit slot: {unit, scheme, SNR point, first realization}
     const cplx* y[3]; int K_max, n_rep, T, N, K;
     const cplx* hest; const int* tap_delay;
     cplx* scratch;
 };
 template <bool FAST24>
-__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? 6 : PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
     const int nbuf = max(nx, N);
     const bool fbmc = md.kind == 0;
     const int tid = threadIdx.x, nthr = blockDim.x, col = blockIdx.x, c = col % NC_MAX;
-    const int unit = p.units[col / NC_MAX];
-    const IcCta cta = p.ctas[unit];
+    const int4 dsc = p.desc[col / NC_MAX];                     // {unit, scheme, SNR point, first realization}: one load, not a chain
+    const int unit = dsc.x;
+    IcCta cta; cta.mode = 0; cta.scheme_or_wf = dsc.y; cta.snr = dsc.z; cta.first = dsc.w; cta.n_cols = NC_MAX;
     const int rep = cta.first + c;
     if (rep >= p.n_rep) return;
     cplx* X0 = pf_smem;
@@ -3238,6 +3326,18 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_est_f
     const cplx* hcol = ub;
     const cplx* vcol = ub + (int64_t)p.K_max * NC_MAX;
     cplx* ocol = ub + (int64_t)2 * p.K_max * NC_MAX;
+    if (FAST24) {                                              // K <= CHAIN24_NE * 128, N <= CHAIN24_NH * 128 (the host checks)
+        if (tid < 24) tw[tid] = md.tw[tid];
+        if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
+        if (tid < L) bins[tid] = md.bin[tid];
+        if (L < 24) { for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0); __syncthreads(); }
+        cplx e[CHAIN24_NE];
+        chain24_head<CHAIN24_NE>(md, X0, vcol, hcol, NC_MAX, ycol, K, e);
+        __syncthreads();
+        const cplx* Y = modem_chain24<CHAIN24_NH>(md, X0, X1, tw, filt, p.hest + (int64_t)col * p.T * N, p.T, p.tap_delay, N);
+        chain24_tail<CHAIN24_NE, false>(md, Y, bins, e, nullptr, ocol, NC_MAX, K);
+        return;
+    }
     for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
     if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
     for (int m = tid; m < L; m += nthr) bins[m] = md.bin[m];
@@ -3251,8 +3351,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_est_f
     }
     __syncthreads();
     const cplx* Y;
-    if (FAST24) Y = modem_chain24(md, X0, X1, tw, filt, p.hest + (int64_t)col * p.T * N, p.T, p.tap_delay, N);
-    else {
+    {
         cplx* Xz = fft_shared_batch(X0, X1, tw, md.plan, true, Ksym);
         cplx* Xo = (Xz == X0) ? X1 : X0;
         const double inv_n = 1.0 / n;
