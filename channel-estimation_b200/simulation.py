@@ -26,10 +26,14 @@ class DoublySelectiveSimulation:
                  L=24, F=15e3, SamplingRate=15e3 * 24, NrSubframes=1, QAM_ModulationOrder=256,
                  PilotToDataPowerOffset=2, PilotToDataPowerOffsetAux=4.685, NrIterations=4,
                  Velocity_kmh=500, PowerDelayProfile="VehicularA", DopplerModel="Jakes", Paths=200,
-                 schemes=("aux", "cod", "ofdm"), max_batch=256, device=0, seed=0, verbose=False, setup="device"):
+                 schemes=("aux", "cod", "ofdm"), max_batch=256, device=0, seed=0, verbose=False, setup="device",
+                 estimator="auto"):
         if setup not in ("device", "host"):
             raise ValueError("setup must be 'device' (DS.m:208-313 on the GPU) or 'host' (NumPy, cross-check)")
+        if estimator not in ("auto", "tiles", "factored", "factored_exact"):
+            raise ValueError("estimator must be 'auto', 'tiles', 'factored' or 'factored_exact' (DeviceContext.set_estimator_mode)")
         self.setup_mode = setup
+        self.estimator = estimator
         self.setup_times = {}
         self.p = dict(M_SNR_dB=tuple(M_SNR_dB), NrRepetitions=NrRepetitions, ZeroThresholdSparse=ZeroThresholdSparse,
                       L=L, F=F, SamplingRate=SamplingRate, NrSubframes=NrSubframes,
@@ -41,6 +45,8 @@ class DoublySelectiveSimulation:
         self.seed, self.verbose = seed, verbose
         self.ctx = DeviceContext(device)
         self._setup(max_batch)
+        if estimator != "auto":                                 # the factors come from the device-side setup (setup="device")
+            self.ctx.set_estimator_mode(estimator)
 
     @classmethod
     def paper(cls, **kw):

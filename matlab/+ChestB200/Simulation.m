@@ -85,6 +85,16 @@ classdef Simulation < handle
             BER = obj.BerArrays(err, NrIterations);
         end
 
+        function SetEstimatorMode(obj, Mode)
+            % Form of the estimated-CSI cancellation (include/chest_b200.h): 'auto' (default), 'tiles' (the thresholded W_MMSE of
+            % DS.m:279-313, bit-faithful), 'factored' (stated-tolerance mode: D_est = Q' H_est G with the estimated channel
+            % H_est = sum_q g_q M_q, without the two 1e-8 thresholds), 'factored_exact' (factored only where the thresholds
+            % removed nothing, i.e. CP-OFDM).  Needs the device-side setup (R_hP_est_noNoise given) and set_modem descriptions.
+            m = find(strcmp(Mode, {'auto', 'tiles', 'factored', 'factored_exact'})) - 1;
+            assert(~isempty(m), 'Mode must be auto, tiles, factored or factored_exact');
+            for h = obj.Handles, chest_mex('set_estimator_mode', h, m); end
+        end
+
         function BER = RunWithDraws(obj, NrIterations, Draws)
             % explicit draws exported from a MATLAB run (bit-exact replay of DS.m:352-368,399); Draws fields, one column
             % (page for Noise) per realization: DopplerU, PhaseU (T*Paths x reps, rand([T 1 Paths]) order), BitsAux, BitsCod,

@@ -284,6 +284,19 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     } else if (!strcmp(cmd, "set_perfect_csi_mode")) {   /* (h, mode): 0 dense D, 1 factored */
         rc = chest_set_perfect_csi_mode(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]));
         fail_if(rc);
+    } else if (!strcmp(cmd, "set_precision")) {          /* (h, mode): 0 FP64, 1 split-BF16 tensor-core mode (stated 1e-4) */
+        rc = chest_set_precision(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "set_estimator_mode")) {     /* (h, mode): 0 auto, 1 thresholded W tiles, 2 factored (stated tolerance), 3 factored where exact */
+        rc = chest_set_estimator_mode(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]));
+        fail_if(rc);
+    } else if (!strcmp(cmd, "estimator_info")) {         /* [factored, removed_R, removed_W] = (h, scheme) */
+        int factored = 0; double rr = 0, rw = 0;
+        rc = chest_estimator_info(handle_of(prhs[1]), (int)mxGetScalar(prhs[2]), NULL, &factored, &rr, &rw, NULL);
+        fail_if(rc);
+        plhs[0] = mxCreateDoubleScalar((double)factored);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(rr);
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(rw);
     } else if (!strcmp(cmd, "run_batch_draws")) {
         /* err = (h, n_rep, n_iter, n_snr, doppler_u, phase_u, bits_aux, bits_cod, bits_ofdm, pilot_idx_fbmc, pilot_idx_ofdm, noise)
          * one column per realization, in the order DS.m:352-368,399 draws them; pilot indices 1-based; noise N x n_snr x n_rep */
