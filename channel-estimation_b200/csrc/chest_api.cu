@@ -1420,6 +1420,11 @@ int chest_set_channel(uint64_t handle, int n_samples, int n_taps, const double* 
     }
     CK(cudaStreamSynchronize(c->stream));
     c->chan_set = true; c->finalized = false;
+    // the pseudo-channels / estimator factors belong to the previous channel statistics: the setup of the new channel
+    // (chest_setup_correlations + chest_build_mmse, or the factor uploads) brings them back
+    for (auto& w : c->wf) w.mq_P = 0;
+    for (auto& s : c->sch) for (auto& m : s.mm) m.rinv_set = false;
+    c->ctas_for_batch = -1;
     return CHEST_OK;
 }
 

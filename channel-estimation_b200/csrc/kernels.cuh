@@ -2708,6 +2708,9 @@ __host__ __device__ __forceinline__ bool modem_fast24(const ModemDev& md) {
 //   head: X0[symbol][bin] = v * phase * norm (the modulator's input),  e = y + h v  (kept in registers across the chain)
 //   tail: out = e - conj(phase) Y[bin] / (norm F)                      (divided by hdiv where the caller equalises right away)
 #define CHAIN24_NE 6
+#ifndef CHAIN24_MIN_CTAS
+#define CHAIN24_MIN_CTAS 6          // 80 registers; measured against 5 (102 registers) and 4 (128): see profiles
+#endif
 #define CHAIN24_NH 5
 template <int NE>
 __device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, const cplx* __restrict__ hcol,
@@ -2866,7 +2869,7 @@ struct PerfDetParams {
     uint8_t* zw_g; uint32_t* err;
 };
 template <bool FAST24>
-__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? 6 : PERF_FBMC_MIN_CTAS) k_perfect_fbmc_det(PerfDetParams p) {
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS : PERF_FBMC_MIN_CTAS) k_perfect_fbmc_det(PerfDetParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
@@ -3304,7 +3307,7 @@ struct EstFactParams {
     cplx* scratch;
 };
 template <bool FAST24>
-__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? 6 : PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS : PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
