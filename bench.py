@@ -685,6 +685,7 @@ def run_sweep(args):
     if world > 1:
         dist.barrier()
     setup_s, loop_s = 0.0, 0.0
+    setup_list, setup_parts = [], []
     t_all = time.perf_counter()
     totals = []
     n_snr = len(sim.Pn)
@@ -692,6 +693,7 @@ def run_sweep(args):
         t = time.perf_counter()
         sim.set_velocity(v)
         setup_s += time.perf_counter() - t
+        setup_list.append(round(time.perf_counter() - t, 4)); setup_parts.append({k: round(x, 4) for k, x in sim.setup_times.items()})
         t = time.perf_counter()
         lo = per_v * rank // world; hi = per_v * (rank + 1) // world     # this rank's contiguous block of the velocity's realizations
         tot = sim.run_totals(hi - lo, NrIterations=I, first_rep=lo)
@@ -722,7 +724,8 @@ def run_sweep(args):
                           "realizations_per_velocity": per_v, "batch": B, "timing": "host wall clock around the whole sweep (setup + loop + reduce), max over ranks"},
                "setup_s_per_velocity": setup_s / len(velocities), "loop_s": loop_s, "reduce_ms": reduce_ms, "one_time_setup_s": one_time_s,
                "loop_only_value": n_total / loop_s, "sanity_ber_ofdm_40dB_iteration4_by_velocity": ber,
-               "setup_breakdown_last_velocity_s": {k: round(v, 4) for k, v in sim.setup_times.items()}}
+               "setup_breakdown_last_velocity_s": {k: round(v, 4) for k, v in sim.setup_times.items()},
+               "setup_s_by_velocity": setup_list, "setup_breakdown_first_velocity_s": setup_parts[0] if setup_parts else None}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -240,7 +240,8 @@ template <int MODE, int WM, int WN, int TMW>
 cudaError_t launch_gemm_geo(Ctx* c, const GemmParams& p, int n_z) {
     constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
     constexpr int smem = 3 * (TM + TN) * 20 * (int)sizeof(cplx);     // 2 stages x (A + B) rows x (16+4) x (complex + double plane)
-    static bool attr_done = false;
+    static bool attr_dev[64] = {};                                   // function attributes are per device
+    bool& attr_done = attr_dev[c->device & 63];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm<MODE, WM, WN, TMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
@@ -255,7 +256,8 @@ template <int WM, int WN, int TMW>
 cudaError_t launch_gemm_d_geo(Ctx* c, const GemmDParams& p) {
     constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
     constexpr int smem = GEMMD_STAGES * 3 * (TM + TN) * (GEMMD_KT + 4) * (int)sizeof(double);   // stages x rows x (KT+4) x (complex + double plane)
-    static int grid = 0;
+    static int grid_dev[64] = {};                                    // function attributes and occupancy are per device
+    int& grid = grid_dev[c->device & 63];
     if (!grid) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_d<WM, WN, TMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
@@ -485,7 +487,8 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
     }
     if (dev <= 1e-12 * mag) {
         w.pf_state = md.kind == 0 ? 1 : 2;                      // 2: CP-OFDM -- the one-column kernels (k_perfect_fbmc_det, k_demod_fbmc) only
-        static size_t attr_smem = 0;                            // the attribute is per kernel: keep the largest need seen
+        static size_t attr_dev[64] = {};                        // the attribute is per kernel and device: keep the largest need seen
+        size_t& attr_smem = attr_dev[c->device & 63];
         if (smem > attr_smem) {
             attr_smem = smem;
             CK(cudaFuncSetAttribute(k_perfect_fbmc<PERF_FBMC_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -503,7 +506,8 @@ template <int WM, int WN, int TMW, bool BG, int EPI>
 cudaError_t launch_gemm_ring_geo(Ctx* c, GemmRingParams& p) {
     constexpr int TM = 8 * TMW * WM, TN = 16 * WN;
     constexpr int smem = GEMMD_STAGES * 3 * (TM + TN) * (GEMMD_KT + 4) * (int)sizeof(double);
-    static int grid = 0;
+    static int grid_dev[64] = {};                                    // function attributes and occupancy are per device
+    int& grid = grid_dev[c->device & 63];
     if (!grid) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_ring<WM, WN, TMW, BG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
@@ -1169,7 +1173,8 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         tp.htrue = w.htrue.p; tp.h = c->h.p; tp.tap_delay = c->d_tap_delay.p; tp.err = err;
         const size_t smem = ((size_t)2 * md.Ksym * md.nfft + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)((md.L + 3) & ~3) * sizeof(int)
                             + (size_t)tp.n_long_max * sizeof(cplx) + (size_t)((w.K + 7) & ~7) * sizeof(unsigned short) + (size_t)((n_data_max + 15) & ~15);
-        static size_t attr_smem = 0;
+        static size_t attr_dev[64] = {};
+        size_t& attr_smem = attr_dev[c->device & 63];
         if (smem > attr_smem) { CK(cudaFuncSetAttribute(k_perfect_twin_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
         k_perfect_twin_fbmc<<<n_rep * w.nsch * S, PERF_FBMC_THREADS, smem, st>>>(tp);
         c->launches++;
@@ -1196,11 +1201,13 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
                     }
                 }
                 if (c->tc_p8 == 16) {
-                    static bool attr16 = false;
+                    static bool attr16_dev[64] = {};
+                    bool& attr16 = attr16_dev[c->device & 63];
                     if (!attr16) { CK(cudaFuncSetAttribute(k_ic_est_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<16>::SMEM)); attr16 = true; }
                     k_ic_est_tc<16><<<c->tc_grid, TC_THREADS, TcGeo<16>::SMEM, st>>>(tp);
                 } else {
-                    static bool attr32 = false;
+                    static bool attr32_dev[64] = {};
+                    bool& attr32 = attr32_dev[c->device & 63];
                     if (!attr32) { CK(cudaFuncSetAttribute(k_ic_est_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<32>::SMEM)); attr32 = true; }
                     k_ic_est_tc<32><<<c->tc_grid, TC_THREADS, TcGeo<32>::SMEM, st>>>(tp);
                 }
@@ -1919,7 +1926,7 @@ int chest_build_mmse(uint64_t handle, int si, int variant, int n_snr, const doub
     CK(cudaMemsetAsync(m.diag_frag.p, 0, sizeof(cplx) * n_snr * n_dfrag, st));
     const int64_t n_thr = ((int64_t)m.n_tiles + RT) * 8 * P;
     for (int snr = 0; snr < n_snr; ++snr) {
-        if (m.frag[snr].n < n_frag) CK(m.frag[snr].alloc(n_frag + n_frag / 8));
+        if (m.frag[snr].n < n_frag) CK(m.frag[snr].alloc(n_frag + n_frag / 2));      // (a velocity sweep grows the support step by step)
         CK(m.diag[snr].alloc((size_t)K * P));
         CK(cudaMemsetAsync(m.frag[snr].p, 0, sizeof(cplx) * n_frag, st));
         CK(cudaMemsetAsync(m.diag[snr].p, 0, sizeof(cplx) * K * P, st));
