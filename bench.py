@@ -725,7 +725,7 @@ def run_sweep(args):
                "setup_s_per_velocity": setup_s / len(velocities), "loop_s": loop_s, "reduce_ms": reduce_ms, "one_time_setup_s": one_time_s,
                "loop_only_value": n_total / loop_s, "sanity_ber_ofdm_40dB_iteration4_by_velocity": ber,
                "setup_breakdown_last_velocity_s": {k: round(v, 4) for k, v in sim.setup_times.items()},
-               "setup_s_by_velocity": setup_list, "setup_breakdown_first_velocity_s": setup_parts[0] if setup_parts else None}
+               "setup_s_by_velocity": setup_list, "setup_breakdown_by_velocity_s": setup_parts}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

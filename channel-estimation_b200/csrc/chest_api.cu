@@ -207,6 +207,7 @@ struct Ctx {
     DevBuf<unsigned long long> totals;    // [snr][it][12] sums over realizations (chest_multi_run)
     DevBuf<cplx> sv_h, sv_noise; DevBuf<double> sv_pn; DevBuf<uint32_t> sv_err;   // chest_sv_run_batch
     bool mse_on = false; DevBuf<double> mse;                      // chest_set_mse_accumulation: [rep][snr][it][scheme]
+    DevBuf<int> setup_pil; DevBuf<double> setup_rt, setup_tp; DevBuf<cplx> setup_corner, setup_rhp;   // chest_setup_correlations scratch
     DevBuf<cplx> setup_rinv; DevBuf<int> setup_mask, setup_trt;   // chest_build_mmse scratch, kept across calls (a velocity sweep rebuilds W per velocity)
 };
 
@@ -1814,7 +1815,9 @@ int chest_setup_correlations(uint64_t handle, int wfi, int n_pilots, const int32
     for (int x : pil) ARG(x >= 0 && x < K);
     std::vector<double> tp(T);
     for (int t = 0; t < T; ++t) tp[t] = c->tap_amp[t] * c->tap_amp[t];
-    DevBuf<int> d_pil; DevBuf<double> d_rt, d_tp; DevBuf<cplx> corner, rhp;
+    // scratch of this call, kept in the context: a velocity sweep calls it once per velocity
+    DevBuf<int>& d_pil = c->setup_pil; DevBuf<double>& d_rt = c->setup_rt; DevBuf<double>& d_tp = c->setup_tp;
+    DevBuf<cplx>& corner = c->setup_corner; DevBuf<cplx>& rhp = c->setup_rhp;
     cudaStream_t st = c->stream;
     CK(d_pil.upload(pil, st)); CK(d_rt.upload(time_corr, (size_t)2 * N - 1, st)); CK(d_tp.upload(tp, st));
     CK(w.g_lo_d.upload(w.g_lo, st)); CK(w.g_hi_d.upload(w.g_hi, st));

@@ -165,6 +165,7 @@ class DoublySelectiveSimulation:
         self.ChannelModel = FastFading(p["SamplingRate"], p["PowerDelayProfile"], self.N, fD, p["DopplerModel"],
                                        p["Paths"], 1, 1, False, create_device=False)
         self.setup_times = {}
+        self._keep_setup_buffers = True
         t0 = time.perf_counter()
         self.ctx.set_channel(self.N, self._pdp, fD, self.ChannelModel.PHY["dt"], p["Paths"], p["DopplerModel"])
         self.ctx.finalize(max(self.NrPilotSymbols, 1))
@@ -226,8 +227,8 @@ class DoublySelectiveSimulation:
                     ctx.set_mmse_arrays(name, variant, np.array(jc), np.concatenate(ir), np.concatenate(val))
                 t0 = self._tick("mmse_%s" % self.setup_mode, t0)
             s["R_hP_est_noNoise"] = R_nn
-        if self.setup_mode == "device":
-            ctx.release_setup()
+        if self.setup_mode == "device" and not getattr(self, "_keep_setup_buffers", False):
+            ctx.release_setup()                                # (a velocity sweep keeps R_Dij_hP's buffer: cudaMalloc / cudaFree of 130 MB per step)
         ctx.finalize(max_batch)
         self._tick("finalize", t0)
         self.max_batch = max_batch
