@@ -578,7 +578,7 @@ int stage_factored_estimated_csi(Ctx* c, int n_rep, int it, int n_iter, const Ic
         fp.hest = c->hest.p; fp.tap_delay = c->d_tap_delay.p; fp.scratch = c->scratch.p;
         const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
         const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
-        static const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;
+        const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;
         if (modem_fast24(md) && !no24 && w.K <= CHAIN24_NE * PERF_FBMC_THREADS && N <= CHAIN24_NH * PERF_FBMC_THREADS) k_est_factored<true><<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
         else k_est_factored<false><<<w.ef_n_units * NC_MAX, PERF_FBMC_THREADS, smem, c->stream>>>(fp);
         c->launches++;
@@ -604,7 +604,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* 
             dp.y = w.y.p; dp.htrue = w.htrue.p; dp.h = c->h.p; dp.tap_delay = c->d_tap_delay.p; dp.zw_g = w.zw_g.p; dp.err = err;
             const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
             const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
-            static const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;      // development / tests: the generic chain
+            const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;             // development / tests: the generic chain
             if (modem_fast24(md) && !no24 && w.K <= CHAIN24_NE * PERF_FBMC_THREADS && N <= CHAIN24_NH * PERF_FBMC_THREADS) k_perfect_fbmc_det<true><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
             else k_perfect_fbmc_det<false><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
             c->launches++;

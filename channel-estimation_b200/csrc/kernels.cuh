@@ -1113,6 +1113,10 @@ __device__ __forceinline__ void ld_cplx2(const cplx* ptr, cplx& a, cplx& b) {
     asm("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(ptr));
 }
 
+__device__ __forceinline__ void st_cplx2(cplx* ptr, cplx a, cplx b) {   // 32 bytes, 32-byte aligned
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(ptr), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
 // ---- phase B, estimated CSI: acc[i, c] = sum_{delta} ( sum_p W[i, i+delta, p] hP[p, c] ) * v[i+delta, c]
 // One warp owns 8 rows (a row tile) at a time and walks its diagonal tiles.  Per tile the P4 pilot
 // quads are DMMA k-steps with the hP fragments as B operand (shared by every tile), followed by an
@@ -1642,13 +1646,18 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
         if (detected) {
             any_despread = false;
             const int nv = p.wf_nscheme[wf] * p.n_snr;
-            for (int idx = tid; idx < p.K_max * NC; idx += nthr) {
-                const int c = idx % NC, d = idx / NC;
+            // sixteen decided words of one column per 16-byte load (the column stride is a multiple of 16 bytes)
+            for (int idx = tid; idx < ((p.K_max + 15) >> 4) * NC; idx += nthr) {
+                const int c = idx % NC, d0 = (idx / NC) << 4;
                 if (sh.c_rep[c] < 0) continue;
-                const SchemeDev& sd = p.sch[sh.c_scheme[c]];
-                if (d >= sd.n_data) continue;
+                const int n_data = p.sch[sh.c_scheme[c]].n_data;
+                if (d0 >= n_data) continue;
                 const int64_t col = (int64_t)sh.c_rep[c] * nv + (c >> 3) * p.n_snr + sh.c_snr[c];
-                zw[d * NC + c] = p.perf_zw[wf][col * p.perf_zw_stride[wf] + d];
+                const uint4 w = *reinterpret_cast<const uint4*>(p.perf_zw[wf] + col * p.perf_zw_stride[wf] + d0);
+                const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (d0 + j < n_data) zw[(d0 + j) * NC + c] = (uint8_t)(ww[j >> 2] >> (8 * (j & 3)));
             }
         }
         {   // transmitted pilots of the columns (phase C divides by them, phase A re-inserts them)
@@ -1696,9 +1705,12 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                     const int i = rt * 8 + g;
                     cplx yv[2][2];
 #pragma unroll
-                    for (int ct = 0; ct < 2; ++ct)
+                    for (int ct = 0; ct < 2; ++ct) {
+                        if (it > 0 && i < K) ld_cplx2(ybuf + i * NC + ct * 8 + 2 * t4, yv[ct][0], yv[ct][1]);      // the lane's column pair: 32 bytes
+                        else
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) yv[ct][e] = i < K ? yic(i, ct * 8 + 2 * t4 + e) : cmake(0.0, 0.0);
+                            for (int e = 0; e < 2; ++e) yv[ct][e] = i < K ? yic(i, ct * 8 + 2 * t4 + e) : cmake(0.0, 0.0);
+                    }
                     const int d = (select && i < K) ? sd.pos2data[i] : -1;
                     const uint32_t em = d >= 0 ? sd.edge_mask[d] : 0;
                     for (int pq = 0; pq < P4; ++pq) {
@@ -1714,6 +1726,10 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                         }
                     }
                     if (i < K) {
+                        if (hfact)
+#pragma unroll
+                            for (int ct = 0; ct < 2; ++ct)
+                                st_cplx2(hbuf + i * NC + ct * 8 + 2 * t4, cmake(hr[ct][0], hi[ct][0]), cmake(hr[ct][1], hi[ct][1]));
 #pragma unroll
                         for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
@@ -1723,7 +1739,6 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                                 const int64_t col = (int64_t)sh.c_snr[c] * p.n_rep + sh.c_rep[c];
                                 const cplx hh = cmake(hr[ct][e], hi[ct][e]);
                                 if (last) sd.hdiag[col * K + i] = hh;
-                                if (hfact) hbuf[i * NC + c] = hh;
                                 if (p.mse) {
                                     const cplx ht = p.htrue[wf][(int64_t)sh.c_rep[c] * K + i];
                                     dm[ct][e] += (hh.x - ht.x) * (hh.x - ht.x) + (hh.y - ht.y) * (hh.y - ht.y);
@@ -1969,9 +1984,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
                     "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void st_cplx2(cplx* ptr, cplx a, cplx b) {   // 32 bytes, 32-byte aligned
-    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(ptr), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
 }
 
 template <int P4T>

@@ -644,3 +644,29 @@ def test_factored_estimator_stated_mode_fbmc(ds_default):
     for r in (0, 16, B - 1):
         assert np.array_equal(err_a[r], _oracle_inter(S, seed, first + r)[0]), r
     sim.close()
+
+
+def test_specialised_and_generic_modem_chain_agree():
+    """The 24-point chain (modem_chain24: 6 x 4 DFT passes, register-resident overlap-add / fold, batched operand loads) against
+    the generic mixed-radix chain of the same kernels (CHEST_NO_FAST24) in the factored-estimator mode, where both the
+    perfect-CSI columns (k_perfect_fbmc_det) and the estimated-CSI columns (k_est_factored) of all three schemes run through it:
+    identical counters, estimates within 1e-10."""
+    from chest_b200.simulation import DoublySelectiveSimulation
+    B, seed = 35, 3
+    sim = DoublySelectiveSimulation(max_batch=B, seed=seed, estimator="factored")
+    ctx = sim.ctx
+    keys = [(what, name, r, s) for what in ("hP", "xD_est", "xD_perf") for name in ("aux", "cod", "ofdm") for r in (0, 17, B - 1) for s in (0, ctx.n_snr - 1)]
+
+    def run():
+        err = ctx.run_batch(B, 4, None, seed=seed, first_rep=50)
+        return err, {k: ctx.get_state(*k) for k in keys}
+    err_fast, st_fast = run()
+    os.environ["CHEST_NO_FAST24"] = "1"
+    try:
+        err_gen, st_gen = run()
+    finally:
+        os.environ.pop("CHEST_NO_FAST24", None)
+    assert np.array_equal(err_fast, err_gen)
+    for k in keys:
+        assert np.max(np.abs(st_fast[k] - st_gen[k])) < 1e-10 * np.max(np.abs(st_gen[k])), k
+    sim.close()
