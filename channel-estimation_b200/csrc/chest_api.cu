@@ -492,12 +492,13 @@ int check_polyphase_pass(Ctx* c, Waveform& w) {
         size_t& attr_smem = attr_dev[c->device & 63];
         if (smem > attr_smem) {
             attr_smem = smem;
+            const int smem_e = (int)(smem + CHAIN24_NE * PERF_FBMC_THREADS * sizeof(cplx) + 16);      // + the e = y + h v buffer of the 24-point chain
             CK(cudaFuncSetAttribute(k_perfect_fbmc<PERF_FBMC_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaFuncSetAttribute(k_demod_fbmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaFuncSetAttribute(k_perfect_fbmc_det<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(k_perfect_fbmc_det<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_perfect_fbmc_det<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_e));
             CK(cudaFuncSetAttribute(k_est_factored<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(k_est_factored<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(k_est_factored<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_e));
         }
     }
     return CHEST_OK;
@@ -605,7 +606,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* 
             const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
             const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
             const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;             // development / tests: the generic chain
-            if (modem_fast24(md) && !no24 && w.K <= CHAIN24_NE * PERF_FBMC_THREADS && N <= CHAIN24_NH * PERF_FBMC_THREADS) k_perfect_fbmc_det<true><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
+            if (modem_fast24(md) && !no24 && w.K <= CHAIN24_NE * PERF_FBMC_THREADS && N <= CHAIN24_NH * PERF_FBMC_THREADS) k_perfect_fbmc_det<true><<<w.f_cols, PERF_FBMC_THREADS, smem + CHAIN24_NE * PERF_FBMC_THREADS * sizeof(cplx) + 16, c->stream>>>(dp);
             else k_perfect_fbmc_det<false><<<w.f_cols, PERF_FBMC_THREADS, smem, c->stream>>>(dp);
             c->launches++;
             CK(cudaGetLastError());

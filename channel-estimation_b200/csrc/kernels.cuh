@@ -2720,12 +2720,20 @@ __host__ __device__ __forceinline__ bool modem_fast24(const ModemDev& md) {
 //   head: X0[symbol][bin] = v * phase * norm (the modulator's input),  e = y + h v  (kept in registers across the chain)
 //   tail: out = e - conj(phase) Y[bin] / (norm F)                      (divided by hdiv where the caller equalises right away)
 #define CHAIN24_NE 6
+#ifndef CHAIN24_EST_NB
+#define CHAIN24_EST_NB 3
+#endif
+#ifndef CHAIN24_EST_MIN_CTAS
+#define CHAIN24_EST_MIN_CTAS CHAIN24_MIN_CTAS
+#endif
 #ifndef CHAIN24_MIN_CTAS
 #define CHAIN24_MIN_CTAS 6          // 80 registers; measured against 5 (102 registers) and 4 (128): see profiles
 #endif
 #define CHAIN24_NH 5
+// (register-carried variant: e = y + h v stays in NE complex registers across the chain -- measured faster for k_est_factored,
+// whose three strided operand streams want all 4 NE loads in flight; the shared-memory variant below is faster for k_perfect_fbmc_det)
 template <int NE>
-__device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, const cplx* __restrict__ hcol,
+__device__ __forceinline__ void chain24_head_regs(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, const cplx* __restrict__ hcol,
                                              int hstride, const cplx* __restrict__ ycol, int K, cplx (&e)[NE]) {
     const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
     const bool fbmc = md.kind == 0;
@@ -2751,7 +2759,7 @@ __device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const
     }
 }
 template <int NE, bool DIV>
-__device__ __forceinline__ void chain24_tail(const ModemDev& md, const cplx* Y, const int* bins, const cplx (&e)[NE],
+__device__ __forceinline__ void chain24_tail_regs(const ModemDev& md, const cplx* Y, const int* bins, const cplx (&e)[NE],
                                              const cplx* __restrict__ hdiv, cplx* out, int ostride, int K) {
     const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
     const bool fbmc = md.kind == 0;
@@ -2770,6 +2778,62 @@ __device__ __forceinline__ void chain24_tail(const ModemDev& md, const cplx* Y, 
         const int k = i / L, l = i - k * L;
         const cplx u0 = cmulc(ph[u], Y[k * 24 + bins[l]]);
         const cplx r = cmake(e[u].x - u0.x * md.inv_demod, e[u].y - u0.y * md.inv_demod);
+        out[(int64_t)i * ostride] = DIV ? cdiv_fast(r, hd[u]) : r;
+    }
+}
+
+template <int NE, int NB>
+__device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, const cplx* __restrict__ hcol,
+                                             int hstride, const cplx* __restrict__ ycol, int K, cplx* __restrict__ E) {
+    const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
+    const bool fbmc = md.kind == 0;
+    // NB symbols per batch: 4 x NB 16-byte loads in flight per thread
+#pragma unroll
+    for (int u0 = 0; u0 < NE; u0 += NB) {
+        cplx vv[NB], hh[NB], ph[NB], e[NB];
+        int bl[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int i = tid + (u0 + u) * nthr;
+            const bool ok = i < K;
+            vv[u] = ok ? ld_nc(vcol + (int64_t)i * NC_MAX) : cmake(0.0, 0.0);
+            hh[u] = ok ? ld_nc(hcol + (int64_t)i * hstride) : cmake(0.0, 0.0);
+            e[u] = ok ? ld_nc(ycol + i) : cmake(0.0, 0.0);
+            ph[u] = (ok && fbmc) ? ld_nc(md.phase + i) : cmake(1.0, 0.0);
+            bl[u] = ok ? md.bin[i % L] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int i = tid + (u0 + u) * nthr;
+            if (i >= K) continue;
+            cfma(e[u], hh[u], vv[u]);
+            E[i] = e[u];                                        // (carried in registers it spilled: shared memory instead)
+            const cplx x = cmul(vv[u], ph[u]);
+            X0[(i / L) * 24 + bl[u]] = cmake(x.x * md.norm, x.y * md.norm);
+        }
+    }
+}
+template <int NE, bool DIV>
+__device__ __forceinline__ void chain24_tail(const ModemDev& md, const cplx* Y, const int* bins, const cplx* __restrict__ E,
+                                             const cplx* __restrict__ hdiv, cplx* out, int ostride, int K) {
+    const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
+    const bool fbmc = md.kind == 0;
+    cplx ph[NE], hd[NE];
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int i = tid + u * nthr;
+        const bool ok = i < K;
+        ph[u] = (ok && fbmc) ? ld_nc(md.phase + i) : cmake(1.0, 0.0);
+        if (DIV) hd[u] = ok ? ld_nc(hdiv + i) : cmake(1.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int i = tid + u * nthr;
+        if (i >= K) continue;
+        const int k = i / L, l = i - k * L;
+        const cplx u0 = cmulc(ph[u], Y[k * 24 + bins[l]]);
+        const cplx ev = E[i];
+        const cplx r = cmake(ev.x - u0.x * md.inv_demod, ev.y - u0.y * md.inv_demod);
         out[(int64_t)i * ostride] = DIV ? cdiv_fast(r, hd[u]) : r;
     }
 }
@@ -2909,8 +2973,8 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS :
         if (fbmc) for (int m = tid; m < md.Np; m += nthr) filt[m] = md.filt[m];
         if (tid < L) bins[tid] = md.bin[tid];
         if (L < 24) { for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0); __syncthreads(); }
-        cplx e[CHAIN24_NE];
-        chain24_head<CHAIN24_NE>(md, X0, p.v_base + p.voff[col], ht, 1, ycol, K, e);
+        cplx* e = reinterpret_cast<cplx*>((reinterpret_cast<uintptr_t>(bins + L) + 15) & ~(uintptr_t)15);
+        chain24_head<CHAIN24_NE, 3>(md, X0, p.v_base + p.voff[col], ht, 1, ycol, K, e);
         __syncthreads();
         const cplx* Y = modem_chain24<CHAIN24_NH>(md, X0, X1, tw, filt, p.h + (int64_t)rep * p.T * N, p.T, p.tap_delay, N);
         chain24_tail<CHAIN24_NE, true>(md, Y, bins, e, ht, X0, 1, K);
@@ -3319,7 +3383,7 @@ struct EstFactParams {
     cplx* scratch;
 };
 template <bool FAST24>
-__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS : PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_EST_MIN_CTAS : PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
@@ -3347,10 +3411,10 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS :
         if (tid < L) bins[tid] = md.bin[tid];
         if (L < 24) { for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0); __syncthreads(); }
         cplx e[CHAIN24_NE];
-        chain24_head<CHAIN24_NE>(md, X0, vcol, hcol, NC_MAX, ycol, K, e);
+        chain24_head_regs<CHAIN24_NE>(md, X0, vcol, hcol, NC_MAX, ycol, K, e);
         __syncthreads();
         const cplx* Y = modem_chain24<CHAIN24_NH>(md, X0, X1, tw, filt, p.hest + (int64_t)col * p.T * N, p.T, p.tap_delay, N);
-        chain24_tail<CHAIN24_NE, false>(md, Y, bins, e, nullptr, ocol, NC_MAX, K);
+        chain24_tail_regs<CHAIN24_NE, false>(md, Y, bins, e, nullptr, ocol, NC_MAX, K);
         return;
     }
     for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
