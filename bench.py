@@ -208,7 +208,7 @@ def split_bf16_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last_first, 
                              "tolerance": "estimated channel within 1e-4 of the FP64 mode (tests/test_gpu_tc.py measures 3e-6 on the pilot estimates, 1e-5 on diag(D_est))"}}
 
 
-def factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last_first, hbm_peak):
+def factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last_first, hbm_peak, run_e2e=None, h2d=0, d2h=0):
     """The stated-tolerance mode chest_set_estimator_mode(FACTORED) on the same context and workload: the estimated-CSI
     cancellation (D_est - diag h_est) v applied as Modulation -> estimated banded channel H_est = sum_q g_q M_q -> Demodulation
     (k_est_channel + k_est_factored) instead of through the thresholded W tiles.  FP64 arithmetic throughout; D_est differs
@@ -236,6 +236,15 @@ def factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last
     ctx.event_record(1)
     ms = ctx.event_elapsed_ms(0, 1)
     info = {n: ctx.estimator_info(n) for n in ctx.schemes}
+    e2e = None
+    if run_e2e is not None:                                     # the same end-to-end leg as the main line, in this mode
+        run_e2e(2)
+        torch.cuda.synchronize()
+        t_e = time.perf_counter()
+        run_e2e(K)
+        torch.cuda.synchronize()
+        e2e = {"value": B * K / (time.perf_counter() - t_e), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "api": "chest_prefetch_draws + chest_run_batch with pinned host buffers, estimator mode FACTORED"}
     run(first=last_first)
     torch.cuda.synchronize()
     got = err_dev.view(B, n_snr, I + 1, 3, 2, 2).cpu().numpy().astype(np.int64)
@@ -249,7 +258,7 @@ def factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last
     # per column and launch: H_est written and read (2 x 16 T N), v + h_est + y read, y_ic written (4 x 16 K)
     bytes_launch = n_cols * (2.0 * 16 * T_taps * N_s + 4.0 * 16 * Kmean)
     pass_ms = ef_ms / (K * I)
-    return {"value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "realizations_per_step": B, "dtype": "f64",
+    return {"value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "realizations_per_step": B, "dtype": "f64", "e2e": e2e,
             "estimator": {n: {"factored": info[n]["factored"], "largest_removed_R_Dij_hP": info[n]["removed_r"],
                               "largest_removed_W": info[n]["removed_w"]} for n in info},
             "kernel_ms_per_step": dict({k: v / K for k, v in kern.items()}, est_factored_pass=ef_ms / K),
@@ -603,7 +612,7 @@ def run_b200(args):
                     pass
         if world == 1 and not args.no_split_leg:
             try:
-                out["factored_estimator_mode"] = factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_last, last_first, hbm_peak)
+                out["factored_estimator_mode"] = factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_last, last_first, hbm_peak, run_e2e, h2d, d2h)
             except Exception as e:                              # noqa: BLE001
                 out["factored_estimator_mode"] = {"error": repr(e)[:300]}
                 try:

@@ -569,7 +569,14 @@ int stage_factored_estimated_csi(Ctx* c, int n_rep, int it, int n_iter, const Ic
         }
         const size_t smem_c = (size_t)2 * Pmax * NC_MAX * sizeof(cplx);
         if (smem_c > 48 * 1024) return fail(CHEST_ERR_STATE, "factored estimator: more than 96 pilots per scheme");
-        k_est_channel<<<w.ef_n_units, EST_CHAN_THREADS, smem_c, c->stream>>>(ep);
+        const int P4 = (Pmax + 3) / 4;
+        const size_t smem_m = (size_t)(Pmax + 4 * P4) * NC_MAX * sizeof(cplx);
+        const bool scalar = getenv("CHEST_EST_CHANNEL_SCALAR") != nullptr;     // development / tests: the DFMA form
+        bool same_p = true;                                                    // the DMMA form is instantiated per pilot-quad count
+        for (int si = 0; si < 3; ++si) if (c->sch[si].set && c->est_fact[si] && c->sch[si].waveform == wfi && (c->sch[si].P + 3) / 4 != P4) same_p = false;
+        if (!scalar && same_p && P4 == 4) k_est_channel_mma<4><<<w.ef_n_units, EST_CHAN_THREADS, smem_m, c->stream>>>(ep);
+        else if (!scalar && same_p && P4 == 2) k_est_channel_mma<2><<<w.ef_n_units, EST_CHAN_THREADS, smem_m, c->stream>>>(ep);
+        else k_est_channel<<<w.ef_n_units, EST_CHAN_THREADS, smem_c, c->stream>>>(ep);
         c->launches++;
         CK(cudaGetLastError());
         const ModemDev& md = w.modem;

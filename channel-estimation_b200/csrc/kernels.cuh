@@ -3372,6 +3372,79 @@ __global__ void __launch_bounds__(EST_CHAN_THREADS) k_est_channel(EstChanParams 
     }
 }
 
+// The same product on the FP64 tensor pipe (P <= 16): H-hat[e, c] = sum_q M[q][e] g[q][c] as DMMA tiles of 8 samples x 8 columns x 4
+// pilots; the g operand stays in registers for the whole unit, the pseudo-channel fragments of the next tile are loaded while the
+// current one is multiplied.  Four real products per complex one: g = pinv(R) hP has a large dynamic range at high SNR (the sum
+// cancels), and the three-multiplication form measurably costs accuracy here (2e-10 instead of a few 1e-11 on the symbol estimates).
+template <int P4>
+__global__ void __launch_bounds__(EST_CHAN_THREADS, 2) k_est_channel_mma(EstChanParams p) {
+    extern __shared__ __align__(16) cplx ec_smem[];
+    constexpr int NC = NC_MAX;
+    const int4 dsc = p.desc[blockIdx.x];
+    const int si = dsc.y, snr = dsc.z, first = dsc.w, P = p.P[si], tid = threadIdx.x, nthr = blockDim.x;
+    cplx* hp = ec_smem;                                          // [P][NC]
+    cplx* g = hp + P * NC;                                       // [4 P4][NC], rows >= P zero
+    for (int idx = tid; idx < P * NC; idx += nthr) {
+        const int c = idx % NC, pp = idx / NC, rep = first + c;
+        hp[idx] = rep < p.n_rep ? p.hP[si][((int64_t)snr * p.n_rep + rep) * P + pp] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    const cplx* ri = p.rinv[si] + (int64_t)snr * P * P;
+    for (int idx = tid; idx < 4 * P4 * NC; idx += nthr) {
+        const int c = idx % NC, q = idx / NC;
+        cplx acc = cmake(0.0, 0.0);
+        if (q < P) for (int pp = 0; pp < P; ++pp) cfma(acc, ri[q + (int64_t)P * pp], hp[pp * NC + c]);
+        g[idx] = acc;
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5, gl = lane >> 2, t = lane & 3;
+    double b_r[P4][2], b_i[P4][2];                               // B[t][gl] per k-step and n-tile
+#pragma unroll
+    for (int ks = 0; ks < P4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const cplx b = g[(4 * ks + t) * NC + nt * 8 + gl];
+            b_r[ks][nt] = b.x; b_i[ks][nt] = b.y;
+        }
+    const int TN = p.TN, n_tile = (TN + 7) >> 3;
+    cplx* out = p.hest + (int64_t)blockIdx.x * NC * TN;
+    cplx a[P4], an[P4];
+    auto load = [&](cplx (&dst)[P4], int tile) {
+        const int e = tile * 8 + gl;
+#pragma unroll
+        for (int ks = 0; ks < P4; ++ks) {
+            const int q = 4 * ks + t;
+            dst[ks] = (tile < n_tile && e < TN && q < P) ? ld_nc(p.Mq + (int64_t)q * TN + e) : cmake(0.0, 0.0);
+        }
+    };
+    load(a, warp);
+    for (int tile = warp; tile < n_tile; tile += nwarp) {
+        load(an, tile + nwarp);
+        double cr[2][2] = {{0, 0}, {0, 0}}, ci[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+        for (int ks = 0; ks < P4; ++ks) {
+            const double nai = dneg(a[ks].y);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                dmma884(cr[nt][0], cr[nt][1], a[ks].x, b_r[ks][nt]);
+                dmma884(cr[nt][0], cr[nt][1], nai, b_i[ks][nt]);
+                dmma884(ci[nt][0], ci[nt][1], a[ks].x, b_i[ks][nt]);
+                dmma884(ci[nt][0], ci[nt][1], a[ks].y, b_r[ks][nt]);
+            }
+        }
+        const int e = tile * 8 + gl;
+        if (e < TN) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    out[(int64_t)(nt * 8 + 2 * t + j) * TN + e] = cmake(cr[nt][j], ci[nt][j]);
+        }
+#pragma unroll
+        for (int ks = 0; ks < P4; ++ks) a[ks] = an[ks];
+    }
+}
+
 // k_est_factored: one column (scheme, SNR point, realization) of an EST unit per CTA:
 //     y_ic = y - Demodulation(H-hat Modulation(v)) + h-hat v        (h-hat = diag(D-hat) = W_diag hP, left by k_ic_light)
 // v from the unit's scratch, y_ic into it (what k_ic_main writes for the tile form of W); the chain is k_perfect_fbmc_det's.

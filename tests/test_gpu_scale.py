@@ -669,4 +669,13 @@ def test_specialised_and_generic_modem_chain_agree():
     assert np.array_equal(err_fast, err_gen)
     for k in keys:
         assert np.max(np.abs(st_fast[k] - st_gen[k])) < 1e-10 * np.max(np.abs(st_gen[k])), k
+    # the estimated channel H-hat = sum_q g_q M_q on the FP64 tensor pipe (k_est_channel_mma, default) against the DFMA form
+    os.environ["CHEST_EST_CHANNEL_SCALAR"] = "1"
+    try:
+        err_sc, st_sc = run()
+    finally:
+        os.environ.pop("CHEST_EST_CHANNEL_SCALAR", None)
+    assert np.array_equal(err_fast, err_sc)
+    for k in keys:                                              # (g = pinv(R) hP cancels at high SNR: summation orders differ by ~1e-11)
+        assert np.max(np.abs(st_fast[k] - st_sc[k])) < 2e-10 * np.max(np.abs(st_sc[k])), k
     sim.close()
