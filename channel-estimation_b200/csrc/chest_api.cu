@@ -1049,7 +1049,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
         if (w.pf_state >= 1 && !getenv("CHEST_CHAIN_LEGACY")) {          // the FFT-form demodulator instead of the GEMM
             DemodFbmcParams dp{};
             dp.md = w.modem; dp.N = N; dp.K = w.K; dp.n_snr = S; dp.n_rep = n_rep; dp.n_cols = w.nsch * S * n_rep;
-            dp.r0 = w.r0.p; dp.noise = noise; dp.noise_scale = c->d_noise_scale.p; dp.y = w.y.p;
+            dp.r0 = w.r0.p; dp.noise = noise; dp.noise_scale = c->d_noise_scale.p; dp.y = w.y.p; dp.fast24 = getenv("CHEST_NO_FAST24") ? 0 : 1;
             const ModemDev& md = w.modem;
             const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
             const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);

@@ -3258,11 +3258,11 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_perfe
 // samples, the folded symbols and the FFT ping-pong in two shared-memory buffers.
 struct DemodFbmcParams {
     ModemDev md;
-    int N, K, n_snr, n_rep, n_cols;
+    int N, K, n_snr, n_rep, n_cols, fast24;
     const cplx* r0; const cplx* noise; const double* noise_scale;
     cplx* y;                       // [col][K]
 };
-__global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod_fbmc(DemodFbmcParams p) {
+__global__ void __launch_bounds__(PERF_FBMC_THREADS, 6) k_demod_fbmc(DemodFbmcParams p) {
     extern __shared__ __align__(16) cplx pf_smem[];
     const ModemDev& md = p.md;
     const int n = md.nfft, Ksym = md.Ksym, L = md.L, N = p.N, K = p.K, TS = md.time_spacing, nx = Ksym * n;
@@ -3285,6 +3285,9 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod
         for (int nn = tid; nn < N; nn += nthr) { const cplx x = a[nn], z = nz[nn]; X1[nn] = cmake(x.x + sc * z.x, x.y + sc * z.y); }
     }
     __syncthreads();
+    const bool fast24 = modem_fast24(md) && p.fast24;          // 24-point transforms: the specialised fold / DFT passes (modem_chain24)
+    if (fast24 && fbmc) fbmc_fold24<6>(X1, X0, filt, Ksym, N);
+    else
     for (int idx = tid; idx < nx; idx += nthr) {               // fold: a_k[m] = sum_o p[o n + m] r[k TS + o n + m]; OFDM: drop the prefix
         const int k = idx / n, m = idx - k * n;
         cplx acc = cmake(0.0, 0.0);
@@ -3299,7 +3302,9 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, PERF_FBMC_MIN_CTAS) k_demod
         X0[idx] = acc;
     }
     __syncthreads();
-    const cplx* Y = fft_shared_batch(X0, X1, tw, md.plan, false, Ksym);
+    const cplx* Y;
+    if (fast24) { fft24_batch<false>(X0, X1, tw, Ksym); Y = X1; }
+    else Y = fft_shared_batch(X0, X1, tw, md.plan, false, Ksym);
     cplx* out = p.y + (int64_t)col * K;
     for (int i = tid; i < K; i += nthr) {
         const int k = i / L, l = i - k * L;
