@@ -1713,16 +1713,24 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                     }
                     const int d = (select && i < K) ? sd.pos2data[i] : -1;
                     const uint32_t em = d >= 0 ? sd.edge_mask[d] : 0;
-                    for (int pq = 0; pq < P4; ++pq) {
-                        const cplx a = ld_stream(wf_ + ((int64_t)rt * P4 + pq) * 32 + lane);
-                        const double nai = dneg(a.y);
+                    for (int pq0 = 0; pq0 < P4; pq0 += 4) {         // four diagonal-W fragments in flight (the loads were serialised)
+                        cplx a4[4];
 #pragma unroll
-                        for (int ct = 0; ct < 2; ++ct) {
-                            const cplx b = hPn[(pq * 4 + t4) * HS + ct * 8 + g];
-                            dmma884(hr[ct][0], hr[ct][1], a.x, b.x);
-                            dmma884(hr[ct][0], hr[ct][1], nai, b.y);
-                            dmma884(hi[ct][0], hi[ct][1], a.x, b.y);
-                            dmma884(hi[ct][0], hi[ct][1], a.y, b.x);
+                        for (int u = 0; u < 4; ++u)
+                            a4[u] = pq0 + u < P4 ? ld_nc(wf_ + ((int64_t)rt * P4 + pq0 + u) * 32 + lane) : cmake(0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (pq0 + u >= P4) break;
+                            const cplx a = a4[u];
+                            const double nai = dneg(a.y);
+#pragma unroll
+                            for (int ct = 0; ct < 2; ++ct) {
+                                const cplx b = hPn[((pq0 + u) * 4 + t4) * HS + ct * 8 + g];
+                                dmma884(hr[ct][0], hr[ct][1], a.x, b.x);
+                                dmma884(hr[ct][0], hr[ct][1], nai, b.y);
+                                dmma884(hi[ct][0], hi[ct][1], a.x, b.y);
+                                dmma884(hi[ct][0], hi[ct][1], a.y, b.x);
+                            }
                         }
                     }
                     if (i < K) {
