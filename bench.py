@@ -267,8 +267,8 @@ def factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last
                          "achieved": bytes_launch / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                          "frac": bytes_launch / (pass_ms * 1e-3) / 1e9 / hbm_peak if pass_ms > 0 else None, "avg_launch_ms": pass_ms,
                          "algorithmic_bytes_per_launch": bytes_launch, "columns_per_launch": n_cols,
-                         "note": "the chain itself lives in shared memory (the polyphase kernel is L1 / shared-memory bound, "
-                                 "profiles/r02_perfect_fbmc_summary.txt); the HBM figure is reported because no other pipe has a stated peak"},
+                         "note": "the chain itself lives in shared memory (L1 data pipe 76 % busy, DRAM 31 %: "
+                                 "profiles/r02_final_kernels_summary.txt); the HBM figure is reported because no other pipe has a stated peak"},
             "vs_default_mode": {"bit_decisions_that_differ": int(np.abs(got - ref)[:, :, 1:, :, 0, 0].sum()), "of": int(n_dec),
                                 "perfect_csi_and_one_tap_counters_identical": bool(np.array_equal(got[:, :, :, :, 1], ref[:, :, :, :, 1]) and np.array_equal(got[:, :, 0], ref[:, :, 0])),
                                 "tolerance": "D_est within 1e-4 of max|D_est| of the reference formulation (stated; tests/test_gpu_scale.py "
@@ -277,23 +277,24 @@ def factored_estimator_line(torch, np, ctx, sim, B, K, W, I, err_fp64_last, last
 
 
 def perfect_csi_roofline(ctx, sim, B, I, wm, chain_ms, peak_dmma, hbm_peak):
-    """The perfect-CSI pass y - Q^H H G v + h v of one iteration.  FBMC columns go through the polyphase modem (k_perfect_fbmc:
-    G and Q^H applied as IFFT / filter / overlap-add and filter / fold / FFT, all in shared memory), OFDM columns through
-    the ring GEMMs: the pass is bound by memory traffic, not by the FP64 pipe, so its roofline is bytes, with the flops of the
-    GEMM formulation it replaces reported beside it."""
+    """The perfect-CSI pass y - Q^H H G v + h v of one iteration.  FBMC and CP-OFDM columns go through the FFT-form modem
+    (k_perfect_fbmc_det: G and Q^H applied as IFFT / filter / overlap-add -- or cyclic prefix -- and filter / fold / FFT, all in
+    shared memory, with equalisation, detection and counters behind it): the pass is bound by the L1 data pipe (shared-memory and
+    strided global wavefronts), not by HBM or the FP64 pipe, so its roofline is reported in bytes with the flops of the GEMM
+    formulation it replaces beside it.  (Geometries without a usable modem description run k_gemm_ring x2 + k_apply_h_cols_planes.)"""
     n_snr = len(sim.Pn)
     cols = {name: B * n_snr for name in sim.sch}
     k_of = {name: ctx.schemes[name]["K"] for name in sim.sch}
     alg_bytes = sum(cols[n] * k_of[n] * 3 * 16.0 for n in sim.sch)           # v in, y in, y_ic out (16 B each per symbol)
     gemm_flops = B * wm["factored_perf_flops"] / I
-    return {"kernel": "k_perfect_fbmc (FBMC columns: polyphase Modulation -> banded H -> Demodulation -> cancellation, one column per CTA in "
-                      "shared memory) + k_gemm_ring x2 + k_apply_h_cols_planes (OFDM columns)",
+    return {"kernel": "k_perfect_fbmc_det (FBMC and CP-OFDM columns: Modulation -> banded H -> Demodulation -> cancellation -> equalise / detect / count, "
+                      "one column per CTA in shared memory; 24-point specialised chain at the default geometry)",
             "bound": "hbm", "achieved": alg_bytes / (chain_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": alg_bytes / (chain_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_iteration": alg_bytes, "avg_iteration_ms": chain_ms,
             "gemm_formulation_flops_per_iteration": gemm_flops, "gemm_equivalent_tflops": gemm_flops / (chain_ms * 1e-3) / 1e12,
             "gemm_equivalent_frac_of_dmma_peak": gemm_flops / (chain_ms * 1e-3) / 1e12 / peak_dmma,
-            "note": "algorithmic bytes: v and y read, y_ic written once per column (48 B per symbol); the kernel is bound by shared-memory / L1 "
-                    "throughput (ncu l1tex 86 %, profiles/r02_perfect_fbmc_summary.txt), not by HBM or the FP64 pipe (15 %).  The GEMM formulation "
+            "note": "algorithmic bytes: v and y read, y_ic written once per column (48 B per symbol); the kernel is bound by the L1 data pipe "
+                    "(ncu l1tex 78 %, profiles/r02_final_kernels_summary.txt), not by HBM (11 %) or the FP64 pipe (16 %).  The GEMM formulation "
                     "of round 1 needed 13 x the flops; gemm_equivalent_* divides THOSE flops by the time of the pass (above 1 = faster than a "
                     "perfect DMMA GEMM could be)"}
 
