@@ -178,6 +178,7 @@ struct Ctx {
     // estimated-CSI cancellation: 0 auto (factored form only for schemes where it equals the tile form of W to rounding), 1 tiles
     // (always the thresholded W), 2 factored (every scheme that has the factors: the stated-tolerance mode, chest_set_estimator_mode)
     int est_mode = 0; bool est_fact[3] = {false, false, false};
+    bool chain_cm = true, chain_cm_perf = true;   // unit scratch of the chain kernels' columns is column-major (IcParams::chain_colmajor): factored EST units / detected PERF units
     DevBuf<cplx> hest; DevBuf<unsigned long long> zmax;
     cudaEvent_t ev_ef[18] = {}; float est_fact_ms = 0;
     cudaStream_t copy_stream = nullptr;
@@ -583,7 +584,7 @@ int stage_factored_estimated_csi(Ctx* c, int n_rep, int it, int n_iter, const Ic
         EstFactParams fp{};
         fp.md = md; fp.desc = w.ef_desc.p; fp.K_max = c->K_max; fp.n_rep = n_rep; fp.T = c->T; fp.N = N; fp.K = w.K;
         for (int si = 0; si < 3; ++si) fp.y[si] = ip.sch[si].y;
-        fp.hest = c->hest.p; fp.tap_delay = c->d_tap_delay.p; fp.scratch = c->scratch.p;
+        fp.hest = c->hest.p; fp.tap_delay = c->d_tap_delay.p; fp.scratch = c->scratch.p; fp.colmajor = c->chain_cm ? 1 : 0;
         const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
         const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
         const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;
@@ -610,6 +611,7 @@ int stage_factored_perfect_csi(Ctx* c, int n_rep, int it, int n_iter, uint32_t* 
             for (int k = 0; k < 2; ++k) dp.cst[k] = c->cst[k].dev;
             dp.voff = w.f_voff.p; dp.yoff = w.f_yoff.p; dp.rep = w.f_rep.p; dp.v_base = c->scratch.p;
             dp.y = w.y.p; dp.htrue = w.htrue.p; dp.h = c->h.p; dp.tap_delay = c->d_tap_delay.p; dp.zw_g = w.zw_g.p; dp.err = err;
+            dp.vstride = c->chain_cm_perf ? 1 : NC_MAX;
             const size_t nbuf = std::max((size_t)md.Ksym * md.nfft, (size_t)N);
             const size_t smem = (2 * nbuf + md.nfft) * sizeof(cplx) + (size_t)md.Np * sizeof(double) + (size_t)md.L * sizeof(int);
             const bool no24 = getenv("CHEST_NO_FAST24") != nullptr;             // development / tests: the generic chain
@@ -818,6 +820,8 @@ int build_ctas(Ctx* c, int n_rep) {
     }
     for (int si = 0; si < 3; ++si) c->est_fact[si] = false;
     for (auto& w : c->wf) w.ef_n_units = 0;
+    c->chain_cm = getenv("CHEST_CHAIN_ROWMAJOR") == nullptr;              // development knobs: the row-major layout everywhere / for the PERF units
+    c->chain_cm_perf = c->chain_cm && getenv("CHEST_PERF_ROWMAJOR") == nullptr;
     if (c->perf_mode == 1) {                                   // factored mode: k_ic_main runs the EST units only (listed first)
         // schemes whose estimated-CSI cancellation runs in factored form (k_est_channel + k_est_factored) come after the tile-form
         // EST units: k_ic_main stops at n_est_units, k_ic_light walks all of them
@@ -865,6 +869,12 @@ int build_ctas(Ctx* c, int n_rep) {
             if (!w.set || !w.nsch || w.twin_on) { w.f_cols = 0; w.pf_n_groups = 0; continue; }
             const int nv = w.nsch * S;
             w.perf_nblk = nblk; w.f_cols = nv * n_rep;
+            {   // one column per CTA with detection behind the chain (k_perfect_fbmc_det)?  Decides the layout of these units' v
+                int rc = check_polyphase_pass(c, w); if (rc) return rc;
+                const char* le = getenv("CHEST_LIGHT");
+                w.det_on = w.pf_state >= 1 && PERF_FBMC_CW == 1 && !getenv("CHEST_NO_PERF_DETECT") && !getenv("CHEST_CHAIN_LEGACY") && !(le && !strcmp(le, "post"));
+            }
+            const bool vcm = w.det_on && c->chain_cm_perf;
             std::vector<int64_t> voff(w.f_cols), yoff(w.f_cols);
             std::vector<int> rep(w.f_cols);
             for (int r = 0; r < n_rep; ++r)
@@ -872,7 +882,7 @@ int build_ctas(Ctx* c, int n_rep) {
                     for (int snr = 0; snr < S; ++snr) {
                         const int col = r * nv + slot * S + snr;
                         const int64_t unit = w.perf_base + (int64_t)r * nblk + snr / 8;
-                        voff[col] = (unit * 3 + 1) * c->K_max * NC_MAX + slot * 8 + snr % 8;
+                        voff[col] = (unit * 3 + 1) * c->K_max * NC_MAX + (vcm ? (int64_t)(slot * 8 + snr % 8) * c->K_max : slot * 8 + snr % 8);
                         yoff[col] = ((int64_t)slot * S * n_rep + (int64_t)snr * n_rep + r) * w.K;
                         rep[col] = r;
                     }
@@ -890,7 +900,6 @@ int build_ctas(Ctx* c, int n_rep) {
                 if (!groups.empty()) CK(w.pf_groups.upload(groups, c->stream));
                 // one column per CTA: the same kernel also equalises, detects and counts (k_perfect_fbmc_det); k_ic_light then
                 // only precodes these columns.  CHEST_NO_PERF_DETECT keeps the two-kernel split (development / tests).
-                w.det_on = w.pf_state >= 1 && PERF_FBMC_CW == 1 && !getenv("CHEST_NO_PERF_DETECT") && !getenv("CHEST_CHAIN_LEGACY");
                 if (w.det_on) {
                     int nd = 0;
                     for (int q = 0; q < w.nsch; ++q) nd = std::max(nd, c->sch[w.sch[q]].n_data);
@@ -1145,6 +1154,7 @@ int run_pipeline(Ctx* c, int n_rep, int n_iter, const chest_draws* draws, uint64
     CK(cudaMemsetAsync(err, 0, n_err * sizeof(uint32_t), st));
     ip.err = err;
     for (int wfi = 0; wfi < 2; ++wfi) { ip.perf_zw[wfi] = c->wf[wfi].det_on ? c->wf[wfi].zw_g.p : nullptr; ip.perf_zw_stride[wfi] = c->wf[wfi].zw_stride; }
+    ip.chain_colmajor = (c->chain_cm ? 1 : 0) | (c->chain_cm_perf ? 2 : 0);
     ip.est_fact_mask = 0;
     for (int si = 0; si < 3; ++si) if (c->est_fact[si] && n_iter > 0) ip.est_fact_mask |= 1 << si;
     if (ip.est_fact_mask && use_post) return fail(CHEST_ERR_STATE, "the factored estimator runs with k_ic_light (unset CHEST_LIGHT)");

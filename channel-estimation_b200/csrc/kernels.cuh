@@ -1072,6 +1072,11 @@ struct IcParams {
     // schemes whose estimated-CSI cancellation runs in factored form (k_est_factored): k_ic_light leaves h-hat = W_diag hP of the
     // unit's columns in the first scratch buffer, [row][column] like v
     int est_fact_mask;
+    // scratch layout of the units the one-column-per-CTA chain kernels read and write (factored EST units, detected PERF units):
+    // column-major, [column][K_max] (a column's K values contiguous: coalesced for the chain kernels, 128-byte runs for the DMMA
+    // fragments of k_ic_light) -- bit 0: factored EST units, bit 1: detected PERF units; otherwise row-major [row][16] (what
+    // k_ic_main / k_ic_est_tc / the GEMM chain use)
+    int chain_colmajor;
 };
 
 // Column -> (scheme, SNR point, realization); false for an unused slot.  PERF units keep each 8-column half
@@ -1633,14 +1638,19 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
         const int K = p.sch[p.wf_scheme[wf][0]].K;
         cplx* vbuf = p.scratch + (int64_t)unit * 3 * p.K_max * NC + (int64_t)p.K_max * NC;
         const cplx* ybuf = vbuf + (int64_t)p.K_max * NC;
+        const bool detected = csi == 1 && p.perf_zw[wf] != nullptr;      // equalised, decided and counted by k_perfect_fbmc_det
+        if (detected && !next_pre) continue;
+        // units whose v / y_ic / h-hat go through the chain kernels keep them column-major (IcParams::chain_colmajor)
+        const bool cm = ((p.chain_colmajor & 2) && detected) || ((p.chain_colmajor & 1) && csi == 0 && ((p.est_fact_mask >> cta.scheme_or_wf) & 1));
+        const int KM = p.K_max;
+        auto VI = [&](int i, int c) -> int64_t { return cm ? (int64_t)c * KM + i : (int64_t)i * NC + c; };
+        auto ZI = [&](int d, int c) -> int { return cm ? c * KM + d : d * NC + c; };      // the decided words follow the layout
         // y_ic of this unit: the cancelled symbols, or y itself in the one-tap stage
         auto yic = [&](int i, int c) -> cplx {
-            if (it > 0) return ybuf[i * NC + c];
+            if (it > 0) return ybuf[VI(i, c)];
             const cplx* yp = sh.ycolp[c];
             return yp ? yp[i] : cmake(1.0, 0.0);
         };
-        const bool detected = csi == 1 && p.perf_zw[wf] != nullptr;      // equalised, decided and counted by k_perfect_fbmc_det
-        if (detected && !next_pre) continue;
         bool any_despread = false;
         for (int c = 0; c < cta.n_cols; ++c) any_despread |= p.sch[sh.c_scheme[c]].detect_mode == 1;
         if (detected) {
@@ -1654,10 +1664,11 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                 if (d0 >= n_data) continue;
                 const int64_t col = (int64_t)sh.c_rep[c] * nv + (c >> 3) * p.n_snr + sh.c_snr[c];
                 const uint4 w = *reinterpret_cast<const uint4*>(p.perf_zw[wf] + col * p.perf_zw_stride[wf] + d0);
+                if (cm && (KM & 15) == 0) { *reinterpret_cast<uint4*>(zw + c * KM + d0) = w; continue; }      // same order in shared memory
                 const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (d0 + j < n_data) zw[(d0 + j) * NC + c] = (uint8_t)(ww[j >> 2] >> (8 * (j & 3)));
+                    if (d0 + j < n_data) zw[ZI(d0 + j, c)] = (uint8_t)(ww[j >> 2] >> (8 * (j & 3)));
             }
         }
         {   // transmitted pilots of the columns (phase C divides by them, phase A re-inserts them)
@@ -1706,7 +1717,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                     cplx yv[2][2];
 #pragma unroll
                     for (int ct = 0; ct < 2; ++ct) {
-                        if (it > 0 && i < K) ld_cplx2(ybuf + i * NC + ct * 8 + 2 * t4, yv[ct][0], yv[ct][1]);      // the lane's column pair: 32 bytes
+                        if (it > 0 && i < K && !cm) ld_cplx2(ybuf + i * NC + ct * 8 + 2 * t4, yv[ct][0], yv[ct][1]);      // the lane's column pair: 32 bytes
                         else
 #pragma unroll
                             for (int e = 0; e < 2; ++e) yv[ct][e] = i < K ? yic(i, ct * 8 + 2 * t4 + e) : cmake(0.0, 0.0);
@@ -1736,8 +1747,12 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                     if (i < K) {
                         if (hfact)
 #pragma unroll
-                            for (int ct = 0; ct < 2; ++ct)
-                                st_cplx2(hbuf + i * NC + ct * 8 + 2 * t4, cmake(hr[ct][0], hi[ct][0]), cmake(hr[ct][1], hi[ct][1]));
+                            for (int ct = 0; ct < 2; ++ct) {
+                                if (cm) {
+                                    hbuf[VI(i, ct * 8 + 2 * t4)] = cmake(hr[ct][0], hi[ct][0]);
+                                    hbuf[VI(i, ct * 8 + 2 * t4 + 1)] = cmake(hr[ct][1], hi[ct][1]);
+                                } else st_cplx2(hbuf + i * NC + ct * 8 + 2 * t4, cmake(hr[ct][0], hi[ct][0]), cmake(hr[ct][1], hi[ct][1]));
+                            }
 #pragma unroll
                         for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
@@ -1757,7 +1772,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                                 const cplx xd = cmake(xh.x * sd.inv_sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y * sd.inv_sqrt_dpr);
                                 const int word = ic_decide(cd, xd, sd.txw_t[((int64_t)(sh.c_rep[c] >> 4) * sd.n_data + d) * 16 + (sh.c_rep[c] & 15)], em, e_all[ct][e], e_edge[ct][e]);
                                 if (last) sd.xD[0][col * sd.n_data + d] = xd;
-                                if (next_pre) zw[d * NC + c] = (uint8_t)word;
+                                if (next_pre) zw[ZI(d, c)] = (uint8_t)word;
                             }
                     }
                 }
@@ -1818,7 +1833,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                         const cplx xd = cmake(xh.x * sd.inv_sqrt_dpr, sd.detect_mode == 0 ? 0.0 : xh.y * sd.inv_sqrt_dpr);
                         const int word = ic_decide(cd, xd, txw[d], sd.edge_mask[d], e_all, e_edge);
                         if (last) sd.xD[1][colbase + d] = xd;
-                        if (next_pre) zw[d * NC + c] = (uint8_t)word;
+                        if (next_pre) zw[ZI(d, c)] = (uint8_t)word;
                     }
                 }
                 if (e_all) atomicAdd(&sh.cnt[c][0], e_all);
@@ -1868,7 +1883,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                         if (d < sd.n_data) {
                             const int word = ic_decide(cd, xd[u], txw[(int64_t)d * 16], sd.edge_mask[d], e_all, e_edge);
                             if (last) sd.xD[csi][colbase + d] = xd[u];
-                            if (next_pre) zw[d * NC + c] = (uint8_t)word;
+                            if (next_pre) zw[ZI(d, c)] = (uint8_t)word;
                         }
                     }
                 }
@@ -1888,12 +1903,32 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
             p.mse[(((int64_t)sh.c_rep[tid] * p.n_snr + sh.c_snr[tid]) * (p.n_iter + 1) + it) * 3 + sh.c_scheme[tid]] = sh.mse[tid];
         if (!next_pre) continue;
         // ---- phase A of iteration it+1: v = C z with z = [xP; decided symbols]   (DS.m:482-484, 541-543)
-        {   // rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread
+        if (cm) {
+            // column-major units: a thread owns a row and walks the columns, so the row's precoder entry is read once per scheme
+            // and every store of a warp is one contiguous run of a column
+            for (int i = tid; i < K; i += nthr)
+                for (int half = 0; half < 2; ++half) {         // an 8-column half is on one scheme
+                    const int cb = half * 8;
+                    if (cb >= cta.n_cols) break;
+                    const SchemeDev& sd = p.sch[sh.c_scheme[cb]];
+                    const int col0 = sd.row_col0[i];
+                    if (col0 == -2) continue;
+                    const cplx val0 = sd.row_val0[i];
+                    const cplx* sym = sh.cst[sd.constellation].symbol;
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        const int c = cb + cc;
+                        if (sh.c_rep[c] < 0) continue;
+                        const cplx zz = col0 < 0 ? cmake(0.0, 0.0) : (col0 < sd.P ? xPs[col0 * NC + c] : sym[zw[ZI(col0 - sd.P, c)]]);
+                        vbuf[VI(i, c)] = cmul(val0, zz);
+                    }
+                }
+        } else {   // rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread
+            const int istep = nthr / NC;
             const int c = tid % NC;
             const bool okc = sh.c_rep[c] >= 0;
             const SchemeDev& sd = p.sch[sh.c_scheme[c]];
             const cplx* sym = sh.cst[sd.constellation].symbol;
-            const int istep = nthr / NC;
             for (int i0 = tid / NC; i0 < K; i0 += 8 * istep) {
                 int col[8]; cplx val[8];
 #pragma unroll
@@ -1907,8 +1942,8 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                     const int i = i0 + u * istep;
                     if (i < K && col[u] != -2) {
                         const cplx zz = col[u] < 0 ? cmake(0.0, 0.0)
-                                       : (col[u] < sd.P ? xPs[col[u] * NC + c] : sym[zw[(col[u] - sd.P) * NC + c]]);
-                        vbuf[i * NC + c] = cmul(val[u], zz);
+                                       : (col[u] < sd.P ? xPs[col[u] * NC + c] : sym[zw[ZI(col[u] - sd.P, c)]]);
+                        vbuf[VI(i, c)] = cmul(val[u], zz);
                     }
                 }
             }
@@ -1939,7 +1974,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
                         for (int ct = 0; ct < 2; ++ct) {
                             if (ct < ct0 || ct >= ct1) continue;
                             const int c = ct * 8 + g;
-                            const cplx b = kc < P ? xPs[kc * NC + c] : sym[zw[(kc - P) * NC + c]];
+                            const cplx b = kc < P ? xPs[kc * NC + c] : sym[zw[ZI(kc - P, c)]];
                             dmma884(cr[ct][0], cr[ct][1], a.x, b.x);
                             dmma884(cr[ct][0], cr[ct][1], nai, b.y);
                             dmma884(ci[ct][0], ci[ct][1], a.x, b.y);
@@ -1954,7 +1989,7 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int c = ct * 8 + 2 * t4 + e;
-                                if (ct >= ct0 && ct < ct1 && sh.c_rep[c] >= 0) vbuf[i * NC + c] = cmake(cr[ct][e], ci[ct][e]);
+                                if (ct >= ct0 && ct < ct1 && sh.c_rep[c] >= 0) vbuf[VI(i, c)] = cmake(cr[ct][e], ci[ct][e]);
                             }
                     }
                 }
@@ -2741,7 +2776,7 @@ __host__ __device__ __forceinline__ bool modem_fast24(const ModemDev& md) {
 // (register-carried variant: e = y + h v stays in NE complex registers across the chain -- measured faster for k_est_factored,
 // whose three strided operand streams want all 4 NE loads in flight; the shared-memory variant below is faster for k_perfect_fbmc_det)
 template <int NE>
-__device__ __forceinline__ void chain24_head_regs(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, const cplx* __restrict__ hcol,
+__device__ __forceinline__ void chain24_head_regs(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, int vstride, const cplx* __restrict__ hcol,
                                              int hstride, const cplx* __restrict__ ycol, int K, cplx (&e)[NE]) {
     const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
     const bool fbmc = md.kind == 0;
@@ -2751,7 +2786,7 @@ __device__ __forceinline__ void chain24_head_regs(const ModemDev& md, cplx* X0, 
     for (int u = 0; u < NE; ++u) {
         const int i = tid + u * nthr;
         const bool ok = i < K;
-        vv[u] = ok ? ld_nc(vcol + (int64_t)i * NC_MAX) : cmake(0.0, 0.0);
+        vv[u] = ok ? ld_nc(vcol + (int64_t)i * vstride) : cmake(0.0, 0.0);
         hh[u] = ok ? ld_nc(hcol + (int64_t)i * hstride) : cmake(0.0, 0.0);
         e[u] = ok ? ld_nc(ycol + i) : cmake(0.0, 0.0);
         ph[u] = (ok && fbmc) ? ld_nc(md.phase + i) : cmake(1.0, 0.0);
@@ -2791,7 +2826,7 @@ __device__ __forceinline__ void chain24_tail_regs(const ModemDev& md, const cplx
 }
 
 template <int NE, int NB>
-__device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, const cplx* __restrict__ hcol,
+__device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const cplx* __restrict__ vcol, int vstride, const cplx* __restrict__ hcol,
                                              int hstride, const cplx* __restrict__ ycol, int K, cplx* __restrict__ E) {
     const int tid = threadIdx.x, nthr = blockDim.x, L = md.L;
     const bool fbmc = md.kind == 0;
@@ -2804,7 +2839,7 @@ __device__ __forceinline__ void chain24_head(const ModemDev& md, cplx* X0, const
         for (int u = 0; u < NB; ++u) {
             const int i = tid + (u0 + u) * nthr;
             const bool ok = i < K;
-            vv[u] = ok ? ld_nc(vcol + (int64_t)i * NC_MAX) : cmake(0.0, 0.0);
+            vv[u] = ok ? ld_nc(vcol + (int64_t)i * vstride) : cmake(0.0, 0.0);
             hh[u] = ok ? ld_nc(hcol + (int64_t)i * hstride) : cmake(0.0, 0.0);
             e[u] = ok ? ld_nc(ycol + i) : cmake(0.0, 0.0);
             ph[u] = (ok && fbmc) ? ld_nc(md.phase + i) : cmake(1.0, 0.0);
@@ -2951,6 +2986,7 @@ struct PerfDetParams {
     const int64_t* voff; const int64_t* yoff; const int* rep;
     const cplx* v_base; const cplx* y; const cplx* htrue; const cplx* h; const int* tap_delay;
     uint8_t* zw_g; uint32_t* err;
+    int vstride;                   // distance of a column's consecutive rows in the unit scratch: NC_MAX (row-major) or 1 (column-major)
 };
 template <bool FAST24>
 __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS : PERF_FBMC_MIN_CTAS) k_perfect_fbmc_det(PerfDetParams p) {
@@ -2982,7 +3018,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS :
         if (tid < L) bins[tid] = md.bin[tid];
         if (L < 24) { for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0); __syncthreads(); }
         cplx* e = reinterpret_cast<cplx*>((reinterpret_cast<uintptr_t>(bins + L) + 15) & ~(uintptr_t)15);
-        chain24_head<CHAIN24_NE, 3>(md, X0, p.v_base + p.voff[col], ht, 1, ycol, K, e);
+        chain24_head<CHAIN24_NE, 3>(md, X0, p.v_base + p.voff[col], p.vstride, ht, 1, ycol, K, e);
         __syncthreads();
         const cplx* Y = modem_chain24<CHAIN24_NH>(md, X0, X1, tw, filt, p.h + (int64_t)rep * p.T * N, p.T, p.tap_delay, N);
         chain24_tail<CHAIN24_NE, true>(md, Y, bins, e, ht, X0, 1, K);
@@ -2996,7 +3032,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS :
         const cplx* vcol = p.v_base + p.voff[col];
         for (int i = tid; i < K; i += nthr) {
             const int k = i / L, l = i - k * L;
-            cplx v = vcol[(int64_t)i * NC_MAX];
+            cplx v = vcol[(int64_t)i * p.vstride];
             if (fbmc) v = cmul(v, md.phase[i]);
             X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
         }
@@ -3061,7 +3097,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_MIN_CTAS :
             cplx u0 = Y[k * n + bins[l]];
             if (fbmc) u0 = cmulc(md.phase[i], u0);
             const cplx hv = ht[i], yv = ycol[i];
-            const cplx hvv = cmul(hv, vcol[(int64_t)i * NC_MAX]);
+            const cplx hvv = cmul(hv, vcol[(int64_t)i * p.vstride]);
             Xe[i] = cdiv_fast(cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y), hv);
         }
     }
@@ -3467,6 +3503,7 @@ struct EstFactParams {
     const cplx* y[3]; int K_max, n_rep, T, N, K;
     const cplx* hest; const int* tap_delay;
     cplx* scratch;
+    int colmajor;                  // unit scratch layout: 1 = [column][K_max], 0 = [row][NC_MAX]
 };
 template <bool FAST24>
 __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_EST_MIN_CTAS : PERF_FBMC_MIN_CTAS) k_est_factored(EstFactParams p) {
@@ -3487,7 +3524,8 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_EST_MIN_CT
     double* filt = reinterpret_cast<double*>(tw + n);
     int* bins = reinterpret_cast<int*>(filt + md.Np);
     const cplx* ycol = p.y[cta.scheme_or_wf] + ((int64_t)cta.snr * p.n_rep + rep) * K;
-    cplx* ub = p.scratch + (int64_t)unit * 3 * p.K_max * NC_MAX + c;
+    const int cs = p.colmajor ? 1 : NC_MAX;                   // distance of the column's consecutive rows
+    cplx* ub = p.scratch + (int64_t)unit * 3 * p.K_max * NC_MAX + (p.colmajor ? (int64_t)c * p.K_max : c);
     const cplx* hcol = ub;
     const cplx* vcol = ub + (int64_t)p.K_max * NC_MAX;
     cplx* ocol = ub + (int64_t)2 * p.K_max * NC_MAX;
@@ -3497,10 +3535,10 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_EST_MIN_CT
         if (tid < L) bins[tid] = md.bin[tid];
         if (L < 24) { for (int idx = tid; idx < nx; idx += nthr) X0[idx] = cmake(0.0, 0.0); __syncthreads(); }
         cplx e[CHAIN24_NE];
-        chain24_head_regs<CHAIN24_NE>(md, X0, vcol, hcol, NC_MAX, ycol, K, e);
+        chain24_head_regs<CHAIN24_NE>(md, X0, vcol, cs, hcol, cs, ycol, K, e);
         __syncthreads();
         const cplx* Y = modem_chain24<CHAIN24_NH>(md, X0, X1, tw, filt, p.hest + (int64_t)col * p.T * N, p.T, p.tap_delay, N);
-        chain24_tail_regs<CHAIN24_NE, false>(md, Y, bins, e, nullptr, ocol, NC_MAX, K);
+        chain24_tail_regs<CHAIN24_NE, false>(md, Y, bins, e, nullptr, ocol, cs, K);
         return;
     }
     for (int m = tid; m < n; m += nthr) tw[m] = md.tw[m];
@@ -3510,7 +3548,7 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_EST_MIN_CT
     __syncthreads();
     for (int i = tid; i < K; i += nthr) {
         const int k = i / L, l = i - k * L;
-        cplx v = vcol[(int64_t)i * NC_MAX];
+        cplx v = vcol[(int64_t)i * cs];
         if (fbmc) v = cmul(v, md.phase[i]);
         X0[k * n + bins[l]] = cmake(v.x * md.norm, v.y * md.norm);
     }
@@ -3574,8 +3612,8 @@ __global__ void __launch_bounds__(PERF_FBMC_THREADS, FAST24 ? CHAIN24_EST_MIN_CT
         cplx u0 = Y[k * n + bins[l]];
         if (fbmc) u0 = cmulc(md.phase[i], u0);
         const cplx yv = ycol[i];
-        const cplx hvv = cmul(hcol[(int64_t)i * NC_MAX], vcol[(int64_t)i * NC_MAX]);
-        ocol[(int64_t)i * NC_MAX] = cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y);
+        const cplx hvv = cmul(hcol[(int64_t)i * cs], vcol[(int64_t)i * cs]);
+        ocol[(int64_t)i * cs] = cmake(yv.x - u0.x * md.inv_demod + hvv.x, yv.y - u0.y * md.inv_demod + hvv.y);
     }
 }
 
