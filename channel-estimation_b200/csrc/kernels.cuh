@@ -1905,24 +1905,35 @@ __global__ void __launch_bounds__(IC_LIGHT_THREADS, IC_LIGHT_BLOCKS) k_ic_light(
         // ---- phase A of iteration it+1: v = C z with z = [xP; decided symbols]   (DS.m:482-484, 541-543)
         if (cm) {
             // column-major units: a thread owns a row and walks the columns, so the row's precoder entry is read once per scheme
-            // and every store of a warp is one contiguous run of a column
-            for (int i = tid; i < K; i += nthr)
-                for (int half = 0; half < 2; ++half) {         // an 8-column half is on one scheme
-                    const int cb = half * 8;
-                    if (cb >= cta.n_cols) break;
-                    const SchemeDev& sd = p.sch[sh.c_scheme[cb]];
-                    const int col0 = sd.row_col0[i];
+            // and every store of a warp is one contiguous run of a column; the next row's entry is loaded under the current stores
+            const int nh = cta.n_cols > 8 ? 2 : 1;             // an 8-column half is on one scheme
+            const SchemeDev& sA = p.sch[sh.c_scheme[0]];
+            const SchemeDev& sB = p.sch[sh.c_scheme[nh > 1 ? 8 : 0]];
+            const bool same = nh < 2 || sh.c_scheme[8] == sh.c_scheme[0];
+            int cA = -2, cB = -2; cplx vA = cmake(0.0, 0.0), vB = cmake(0.0, 0.0);
+            if (tid < K) { cA = sA.row_col0[tid]; vA = sA.row_val0[tid]; if (!same) { cB = sB.row_col0[tid]; vB = sB.row_val0[tid]; } }
+            for (int i = tid; i < K; i += nthr) {
+                const int in = i + nthr;
+                int nA = -2, nB = -2; cplx wA = cmake(0.0, 0.0), wB = cmake(0.0, 0.0);
+                if (in < K) { nA = sA.row_col0[in]; wA = sA.row_val0[in]; if (!same) { nB = sB.row_col0[in]; wB = sB.row_val0[in]; } }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (half >= nh) break;
+                    const SchemeDev& sd = half ? sB : sA;
+                    const int col0 = (half && !same) ? cB : cA;
+                    const cplx val0 = (half && !same) ? vB : vA;
                     if (col0 == -2) continue;
-                    const cplx val0 = sd.row_val0[i];
                     const cplx* sym = sh.cst[sd.constellation].symbol;
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc) {
-                        const int c = cb + cc;
+                        const int c = half * 8 + cc;
                         if (sh.c_rep[c] < 0) continue;
                         const cplx zz = col0 < 0 ? cmake(0.0, 0.0) : (col0 < sd.P ? xPs[col0 * NC + c] : sym[zw[ZI(col0 - sd.P, c)]]);
                         vbuf[VI(i, c)] = cmul(val0, zz);
                     }
                 }
+                cA = nA; vA = wA; cB = nB; vB = wB;
+            }
         } else {   // rows with at most one entry: v[i] = val0[i] * z[col0[i]]; eight rows in flight per thread
             const int istep = nthr / NC;
             const int c = tid % NC;
