@@ -679,3 +679,30 @@ def test_specialised_and_generic_modem_chain_agree():
     for k in keys:                                              # (g = pinv(R) hP cancels at high SNR: summation orders differ by ~1e-11)
         assert np.max(np.abs(st_fast[k] - st_sc[k])) < 2e-10 * np.max(np.abs(st_sc[k])), k
     sim.close()
+
+
+@pytest.mark.parametrize("n_iter", [0, 1, 3])
+def test_factored_estimator_iteration_counts_and_mse(ds_default, n_iter):
+    """The factored estimator with other iteration counts than the default four (the MMSE variant switches at NrIterations / 2,
+    DS.m:492; with no iteration nothing is cancelled), a ragged batch (19 realizations: one full 16-column unit and a 3-column
+    tail), and the MSE sums accumulated next to the counters: counts equal the oracle's restatement of the factored form."""
+    import dataclasses
+    from oracle import rng
+    from oracle.ds import ds_realization
+    from chest_b200.simulation import DoublySelectiveSimulation
+    S, B, seed, first = ds_default, 19, 31, 900
+    sim = DoublySelectiveSimulation(max_batch=B, seed=seed, estimator="factored", NrIterations=max(n_iter, 1))
+    ctx = sim.ctx
+    ctx.set_mse_accumulation(True)
+    err = ctx.run_batch(B, n_iter, None, seed=seed, first_rep=first)
+    mse = ctx.get_mse(B, n_iter)
+    S_it = dict(S)
+    S_it["cfg"] = dataclasses.replace(S["cfg"], NrIterations=n_iter)
+    for r in (0, 15, 16, B - 1):
+        out = ds_realization(S_it, rng.draws_for(S, seed, first + r), factored=("aux", "cod", "ofdm"))
+        assert np.array_equal(err[r], err_from_oracle(out, n_iter)), (n_iter, r)
+    assert np.all(np.isfinite(mse)) and np.all(mse[:, :, :, :] >= 0)
+    if n_iter >= 1:
+        assert all(ctx.estimator_info(n)["factored"] for n in ("aux", "cod", "ofdm"))
+    ctx.set_mse_accumulation(False)
+    sim.close()
