@@ -736,6 +736,30 @@ def run_sweep(args):
                "loop_only_value": n_total / loop_s, "sanity_ber_ofdm_40dB_iteration4_by_velocity": ber,
                "setup_breakdown_last_velocity_s": {k: round(v, 4) for k, v in sim.setup_times.items()},
                "setup_s_by_velocity": setup_list, "setup_breakdown_by_velocity_s": setup_parts}
+        if world == 1:
+            # the same sweep in the stated-tolerance mode chest_set_estimator_mode(FACTORED): D_est = Q^H H_est G, FP64, without the
+            # reference's 1e-8 thresholds; the per-velocity setup rebuilds the factors as well
+            try:
+                sim.ctx.set_estimator_mode("factored")
+                sim.set_velocity(velocities[0]); sim.run_totals(min(B, 256), NrIterations=I, first_rep=0)       # warm-up of the new unit tables
+                torch.cuda.synchronize()
+                f_setup, f_loop, f_tot = 0.0, 0.0, []
+                t_f = time.perf_counter()
+                for v in velocities:
+                    t = time.perf_counter(); sim.set_velocity(v); f_setup += time.perf_counter() - t
+                    t = time.perf_counter(); f_tot.append(sim.run_totals(per_v, NrIterations=I, first_rep=0)); f_loop += time.perf_counter() - t
+                torch.cuda.synchronize()
+                f_wall = time.perf_counter() - t_f
+                ft = np.stack(f_tot).astype(np.int64).reshape(len(velocities), n_snr, I + 1, 3, 2, 2)
+                out["factored_estimator_mode"] = {
+                    "value": n_total / f_wall, "unit": UNIT, "setup_s_per_velocity": f_setup / len(velocities), "loop_s": f_loop,
+                    "loop_only_value": n_total / f_loop,
+                    "factored": {n: sim.ctx.estimator_info(n)["factored"] for n in sim.sch},
+                    "bit_decisions_that_differ_from_default_mode": int(np.abs(ft - tt)[:, :, 1:, :, 0, 0].sum()),
+                    "of": int(n_total * n_snr * I * float(sum(nb[sid, 0] for sid in range(3))))}
+                sim.ctx.set_estimator_mode("auto")
+            except Exception as e:                              # noqa: BLE001
+                out["factored_estimator_mode"] = {"error": repr(e)[:300]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -208,7 +208,7 @@ struct Ctx {
     DevBuf<unsigned long long> totals;    // [snr][it][12] sums over realizations (chest_multi_run)
     DevBuf<cplx> sv_h, sv_noise; DevBuf<double> sv_pn; DevBuf<uint32_t> sv_err;   // chest_sv_run_batch
     bool mse_on = false; DevBuf<double> mse;                      // chest_set_mse_accumulation: [rep][snr][it][scheme]
-    DevBuf<int> setup_pil; DevBuf<double> setup_rt, setup_tp; DevBuf<cplx> setup_corner, setup_rhp;   // chest_setup_correlations scratch
+    DevBuf<int> setup_pil; DevBuf<double> setup_rt, setup_tp; DevBuf<cplx> setup_corner, setup_rhp, setup_eye;   // chest_setup_correlations scratch
     DevBuf<cplx> setup_rinv; DevBuf<int> setup_mask, setup_trt;   // chest_build_mmse scratch, kept across calls (a velocity sweep rebuilds W per velocity)
 };
 
@@ -1873,7 +1873,7 @@ int chest_setup_correlations(uint64_t handle, int wfi, int n_pilots, const int32
     CK(cudaStreamSynchronize(st));
     w.rsup_P = P; w.rsup_thr = zero_threshold; c->ctas_for_batch = -1;
     if (n_support) {                                                // entries of the K x K grid with any non-zero pilot weight
-        DevBuf<int> mask; DevBuf<cplx> eye;
+        DevBuf<int>& mask = c->setup_mask; DevBuf<cplx>& eye = c->setup_eye;       // kept in the context: no cudaMalloc / cudaFree per velocity
         CK(mask.alloc(n_e)); CK(cudaMemsetAsync(mask.p, 0, n_e * sizeof(int), st));
         std::vector<cplx> id((size_t)P * P, cmake(0.0, 0.0));
         for (int p = 0; p < P; ++p) id[(size_t)p * P + p] = cmake(1.0, 0.0);
