@@ -301,30 +301,35 @@ class DoublySelectiveSimulation:
         B over the pilot's sample window depends on neither tap nor velocity: it is built once per (scheme, pilot) from
         the sparse precoder and cached (a velocity sweep re-uses it)."""
         N = self.N
-        per_tap = []
-        X = []
-        for m in taps:
-            row, col, ok = self._positions(m)
-            sel = np.flatnonzero(ok & (q[row] != 0))
-            per_tap.append((m, sel, row[sel], col[sel]))
-            X.append(col[sel])
         key = (name, ip)
         if key not in self._power_cache:
+            per_tap = []
+            X = []
+            for m in taps:
+                row, col, ok = self._positions(m)
+                sel = np.flatnonzero(ok & (q[row] != 0))
+                per_tap.append((m, sel, row[sel], col[sel]))
+                X.append(col[sel])
             rows = np.unique(np.concatenate(X))
             if "GA_sparse" not in s:
                 s["GA_sparse"] = sp.csr_matrix(sp.csr_matrix(d["G"]) @ sp.csc_matrix(s["C"]))   # DS.m:203-205
             GAx = s["GA_sparse"][rows, :]
             GAx = GAx[:, np.flatnonzero(np.diff(GAx.tocsc().indptr))].toarray()
-            self._power_cache[key] = (rows, GAx @ GAx.conj().T)
-        rows, B = self._power_cache[key]
-        pos = np.full(N, -1); pos[rows] = np.arange(len(rows))
-        tot = 0.0
-        for m, sel, r, c in per_tap:
-            qq = q[r]
-            T = rt[(N - 1) + sel[:, None] - sel[None, :]]
-            Bc = B[np.ix_(pos[c], pos[c])].T                                   # B[c_a', c_a] indexed [a, a']
-            tot = tot + pdp[m] / s["kappa"] * np.sum(T * (qq[:, None] * np.conj(qq)[None, :]) * Bc)
-        return abs(tot)
+            B = GAx @ GAx.conj().T
+            pos = np.full(N, -1); pos[rows] = np.arange(len(rows))
+            # only R_t depends on the velocity, and it enters through the lag a - a' alone: fold everything else into one
+            # weight per lag, w[lag] = sum_m pdp_m / kappa sum_{a - a' = lag} q[r_a] conj(q[r_a']) B[c_a', c_a]
+            w = np.zeros(2 * N - 1, dtype=np.complex128)
+            for m, sel, r, c in per_tap:
+                qq = q[r]
+                Bc = B[np.ix_(pos[c], pos[c])].T                               # B[c_a', c_a] indexed [a, a']
+                Mm = (pdp[m] / s["kappa"]) * (qq[:, None] * np.conj(qq)[None, :]) * Bc
+                lag = ((N - 1) + sel[:, None] - sel[None, :]).ravel()
+                w += np.bincount(lag, weights=Mm.real.ravel(), minlength=2 * N - 1) + 1j * np.bincount(lag, weights=Mm.imag.ravel(), minlength=2 * N - 1)
+            nz = np.flatnonzero(w)
+            self._power_cache[key] = (nz, w[nz])
+        nz, w = self._power_cache[key]
+        return abs(np.dot(rt[nz], w))
 
     # ------------------------------------------------------------------ DS.m:350-565
     def run(self, NrRepetitions=None, NrIterations=None, seed=None, draws=None, first_rep=0):
