@@ -639,6 +639,17 @@ def test_factored_estimator_stated_mode_fbmc(ds_default):
                     assert np.max(np.abs(got - ref)) < 1e-9 * np.max(np.abs(ref)), (r, name, isnr, what)
                     worst = max(worst, np.max(np.abs(got - fref)) / np.max(np.abs(fref)))
     assert worst < 1e-4, worst
+    # the factors uploaded through the ABI instead of kept by the device-side setup (chest_set_pseudo_channels,
+    # chest_set_estimator_factors), taken from the ORACLE's setup: same counters
+    from oracle.ds import pseudo_channel_taps
+    for wname in ("F", "O"):
+        ctx.set_pseudo_channels(wname, pseudo_channel_taps(S, wname))
+    for name in ("aux", "cod", "ofdm"):
+        ctx.set_estimator_factors(name, 0, np.stack(S["schemes"][name]["Rinv"]))
+        ctx.set_estimator_factors(name, 1, np.stack(S["schemes"][name]["Rinv_noInt"]))
+    err_u = ctx.run_batch(B, 4, None, seed=seed, first_rep=first)
+    assert all(ctx.estimator_info(n)["factored"] for n in ("aux", "cod", "ofdm"))
+    assert np.array_equal(err_u, err)
     ctx.set_estimator_mode("auto")
     err_a = ctx.run_batch(B, 4, None, seed=seed, first_rep=first)
     for r in (0, 16, B - 1):
