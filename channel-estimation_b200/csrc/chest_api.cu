@@ -1909,7 +1909,9 @@ int chest_build_mmse(uint64_t handle, int si, int variant, int n_snr, const doub
     dim3 g1((unsigned)((n_e * P + 255) / 256), n_snr);
     CK(m.rinv.upload(reinterpret_cast<const cplx*>(R_inv), (size_t)n_snr * P * P, st));      // kept: g = Rinv hP of the factored estimator
     CK(c->zmax.alloc(1)); CK(cudaMemsetAsync(c->zmax.p, 0, sizeof(unsigned long long), st));
-    k_w_mask<<<g1, 256, 0, st>>>(mask.p, w.Rsup.p, rinv.p, K, P, zero_threshold, c->zmax.p);
+    if (P <= 16) { dim3 gm((unsigned)((n_e + 255) / 256), n_snr); k_w_mask_rows<16><<<gm, 256, (size_t)P * P * sizeof(cplx), st>>>(mask.p, w.Rsup.p, rinv.p, K, P, zero_threshold, c->zmax.p); }
+    else if (P <= 32) { dim3 gm((unsigned)((n_e + 127) / 128), n_snr); k_w_mask_rows<32><<<gm, 128, (size_t)P * P * sizeof(cplx), st>>>(mask.p, w.Rsup.p, rinv.p, K, P, zero_threshold, c->zmax.p); }
+    else k_w_mask<<<g1, 256, 0, st>>>(mask.p, w.Rsup.p, rinv.p, K, P, zero_threshold, c->zmax.p);
     c->launches++;
     CK(cudaGetLastError());
     std::vector<int> hm(n_e);

@@ -3793,6 +3793,47 @@ __global__ void k_w_mask(int* __restrict__ mask, const cplx* __restrict__ R, con
     if (!(mag < thr)) mask[e] = 1;
     else if (zmax && mag > 0.0) atomicMax(zmax, (unsigned long long)__double_as_longlong(mag));
 }
+// The same pass with one thread per (entry e, SNR point): the P correlations of the entry are loaded once and held in registers,
+// pinv(R)[snr] sits in shared memory (P <= 32).  k_w_mask re-reads them once per output column p': 16 x the traffic, which made
+// it the largest term of the per-velocity setup of a sweep.
+template <int PMAX>
+__global__ void k_w_mask_rows(int* __restrict__ mask, const cplx* __restrict__ R, const cplx* __restrict__ Rinv, int K, int P, double thr,
+                              unsigned long long* __restrict__ zmax) {
+    extern __shared__ __align__(16) cplx wm_smem[];
+    const int RT8 = ((K + 7) / 8) * 8;
+    const int64_t n_e = (int64_t)RT8 * K;
+    const cplx* ri = Rinv + (int64_t)blockIdx.y * P * P;
+    for (int idx = threadIdx.x; idx < P * P; idx += blockDim.x) wm_smem[idx] = ri[idx];
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double zm = 0.0;
+    if (e < n_e) {
+        cplx a[PMAX];
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) {
+            a[p] = p < P ? R[(int64_t)p * n_e + e] : cmake(0.0, 0.0);
+            any |= (a[p].x != 0.0 || a[p].y != 0.0);
+        }
+        if (any) {
+            bool keep = false;
+            for (int pp = 0; pp < P; ++pp) {
+                cplx w = cmake(0.0, 0.0);
+#pragma unroll
+                for (int p = 0; p < PMAX; ++p) if (p < P && (a[p].x != 0.0 || a[p].y != 0.0)) cfma(w, a[p], wm_smem[p + P * pp]);
+                const double mag = hypot(w.x, w.y);
+                if (!(mag < thr)) keep = true;
+                else zm = fmax(zm, mag);
+            }
+            if (keep) mask[e] = 1;
+        }
+    }
+    if (zmax) {                                                 // one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) zm = fmax(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+        if ((threadIdx.x & 31) == 0 && zm > 0.0) atomicMax(zmax, (unsigned long long)__double_as_longlong(zm));
+    }
+}
 // pass B: fragments of one SNR point.  One thread per (tile t, row r, p'); the diagonal goes to dg / dfrag.
 __global__ void k_w_fill(cplx* __restrict__ frag, cplx* __restrict__ dg, cplx* __restrict__ dfrag, const cplx* __restrict__ R,
                          const cplx* __restrict__ Rinv, const int* __restrict__ tile_rt, const int* __restrict__ tile_delta,
